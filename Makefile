@@ -1,0 +1,28 @@
+# Builds the C-ABI library (sm_100a only) and the CPU oracle (test infrastructure).
+NVCC      ?= nvcc
+CC        := gcc
+PKG       := motifs.jl_b200
+CSRC      := $(PKG)/csrc
+LIB       := $(PKG)/lib/libmotifs_b200.so
+NVFLAGS   := -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xcompiler -Wall
+CU        := $(wildcard $(CSRC)/*.cu)
+HDR       := $(wildcard $(CSRC)/*.cuh) include/motifs_b200.h
+
+all: $(LIB) oracle
+
+$(LIB): $(CU) $(HDR)
+	@mkdir -p $(PKG)/lib
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CU)
+
+oracle: oracle/liboracle.so
+
+oracle/liboracle.so: oracle/scan_oracle.c
+	$(CC) -O3 -march=x86-64-v3 -fopenmp -fPIC -shared -Wall -o $@ $< -lm
+
+ptxas-info:
+	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o /tmp/_mb200_info.so $(CU)
+
+clean:
+	rm -f $(LIB) oracle/liboracle.so
+
+.PHONY: all oracle clean ptxas-info

@@ -1,0 +1,111 @@
+/*
+ * motifs_b200.h — C ABI of libmotifs_b200.so, the B200 (sm_100a) implementation of the
+ * data-parallel hot path of kchu25/MOTIFs.jl.
+ *
+ * The reference has no FFI: the path sits behind plain Julia functions.  Each entry point below
+ * names the reference function (file:line under the reference's src/) whose body it replaces when
+ * the Julia host calls this library through `ccall`.
+ *
+ * Conventions
+ *   - every function returns int32: 0 = MB200_OK, <0 = error; text via mb200_last_error(ctx).
+ *   - no exceptions, no torch/C++ types cross the ABI: plain pointers and sizes only.
+ *   - the caller owns every host buffer; the library owns device memory behind opaque handles.
+ *   - a ctx is bound to one CUDA device and is NOT thread-safe (one in-flight call per ctx).
+ *     Calls block until their host-visible outputs are written.
+ *   - all indices crossing the ABI are 0-based (the Julia glue adds 1).
+ *   - there is no CPU fallback: without a CUDA device mb200_create fails.
+ */
+#ifndef MOTIFS_B200_H
+#define MOTIFS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB200_OK                 0
+#define MB200_E_INVALID         -1   /* bad argument */
+#define MB200_E_CUDA            -2   /* CUDA runtime error (see mb200_last_error) */
+#define MB200_E_NOMEM           -3
+#define MB200_E_BAD_SEQUENCE    -4   /* a byte that is not A,C,G,T (either case) / not one-hot */
+#define MB200_E_HITS_OVERFLOW   -5   /* hits_cap too small; *n_hits holds the required size */
+#define MB200_E_UNSUPPORTED     -6
+
+#define MB200_MAX_MOTIF_LEN     64   /* longest PWM the scan kernel accepts */
+
+typedef struct mb200_ctx  mb200_ctx;
+typedef struct mb200_seqs mb200_seqs;
+typedef struct mb200_csc  mb200_csc;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int32_t     mb200_version(void);
+int32_t     mb200_create(mb200_ctx** out, int32_t device_id);
+int32_t     mb200_destroy(mb200_ctx* ctx);
+const char* mb200_last_error(const mb200_ctx* ctx);
+/* Launch all kernels of this ctx on an existing stream (a cudaStream_t passed as void*; NULL =
+ * the ctx's own stream).  Lets a host that already owns a stream (e.g. torch) order work. */
+int32_t     mb200_set_stream(mb200_ctx* ctx, void* cuda_stream);
+/* Device-side timing of the last scan/step call, measured with CUDA events on the launch stream.
+ * out_ms[0]=pack, [1]=scan kernel, [2]=count kernel, [3]=emit (+prefix), [4]=csc step,
+ * [5]=h2d copies, [6]=d2h copies, [7]=total of the call.  launches[i] = kernels launched. */
+int32_t     mb200_last_timing(const mb200_ctx* ctx, float* out_ms8, int64_t* launches8);
+
+/* ---- sequences: replaces the one-hot Float32 arrays of loadfasta/fasta.jl:13-22 ------------
+ * Sequences are stored 2 bit/base (A=0,C=1,G=2,T=3; same row order as helpers.jl:125-128),
+ * 16 bases per little-endian uint32, each sequence padded to a whole number of words.        */
+/* ascii: N rows of Lb bytes, row-major, upper or lower case. */
+int32_t mb200_seqs_from_ascii(mb200_ctx* ctx, const uint8_t* ascii, int64_t N, int64_t Lb,
+                              mb200_seqs** out);
+/* same, but `ascii_dev` is a device pointer on ctx's device (no host copy). */
+int32_t mb200_seqs_from_device_ascii(mb200_ctx* ctx, const void* ascii_dev, int64_t N, int64_t Lb,
+                                     mb200_seqs** out);
+/* onehot: the reference's data_matrix (helpers.jl:123-139, fasta.jl:75): Float32, column-major
+ * (4*Lb, N) (the singleton middle dimension is a reshape), exactly one 1 per group of 4. */
+int32_t mb200_seqs_from_onehot_f32(mb200_ctx* ctx, const float* onehot, int64_t N, int64_t Lb,
+                                   mb200_seqs** out);
+int32_t mb200_seqs_free(mb200_ctx* ctx, mb200_seqs* s);
+int32_t mb200_seqs_shape(const mb200_seqs* s, int64_t* N, int64_t* Lb, int64_t* words_per_seq);
+/* copy the packed words back (N * words_per_seq uint32) — used by tests. */
+int32_t mb200_seqs_download(mb200_ctx* ctx, const mb200_seqs* s, uint32_t* out_words, int64_t n_words);
+
+/* ---- PWM scan: replaces greedy_search! + get_pos_scores_arr + gpu_scan
+ *      (inference/_h3_1_alignment.jl:18-36, 57-87, 89-99), the threshold filter
+ *      filter_position_by_best_thresh! (_s2_filter_pos_w_scores.jl:116-125) and the occurrence
+ *      counts get_uniq_pos / union_ranges / get_total_occupied_positions
+ *      (_h4_overlap_ratio.jl:5-15, 40-79).                                                   */
+typedef struct {
+    uint32_t seq;        /* 0-based sequence index                                            */
+    uint32_t pos;        /* 0-based start position on the forward strand (reference `l` - 1)  */
+    uint16_t motif;      /* 0-based motif index                                               */
+    uint16_t score_f16;  /* IEEE binary16 bits; bit-identical to the reference's Float16 sum  */
+    uint8_t  comp;       /* 0 = scored with pwm, 1 = scored with reverse(pwm) (use_comp)      */
+    uint8_t  _pad[3];
+} mb200_hit;             /* 16 bytes */
+
+#define MB200_SCAN_FWD          0x1u   /* score with pwm                 (rc=false pass)      */
+#define MB200_SCAN_RC           0x2u   /* score with reverse(pwm)        (rc=true pass)       */
+#define MB200_SCAN_WANT_HITS    0x4u
+#define MB200_SCAN_WANT_COUNTS  0x8u
+
+/* pwms_f16 : Float16 bits, Julia column-major (K,4,maxlen) exactly as built at
+ *            _h3_1_alignment.jl:66-69 with rc=false (element (k,a,ind) at k + K*(a + 4*ind));
+ *            the library derives reverse(pwm) itself.
+ * lens     : K motif lengths (Int64, as cu(ms.lens)).
+ * thresh_f16: K Float16 bits or NULL.  NULL = reference scan semantics "score > 0";
+ *            otherwise a hit needs score > 0 AND score > thresh (scan followed by
+ *            filter_position_by_best_thresh!).
+ * hits     : sorted by (seq, motif, comp, pos) — per (motif, seq) this is the reference's dict
+ *            order (forward hits ascending, then reverse hits ascending; _h3_1:38-52,89-99).
+ * counts   : K*4 int64, row k = { n_hits, n_unique_start (get_uniq_pos),
+ *            coverage as the reference computes it (union_ranges, last interval dropped when a
+ *            (motif,seq) has >= 2 hits: _h4_overlap_ratio.jl:48-56), true union coverage }.  */
+int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs,
+                   const uint16_t* pwms_f16, const int64_t* lens, int32_t K, int32_t maxlen,
+                   const uint16_t* thresh_f16, uint32_t flags,
+                   mb200_hit* hits, int64_t hits_cap, int64_t* n_hits, int64_t* counts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOTIFS_B200_H */

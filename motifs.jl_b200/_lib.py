@@ -1,0 +1,204 @@
+"""ctypes binding of libmotifs_b200.so (C ABI declared in include/motifs_b200.h).
+
+This is the same surface a Julia host binds with `ccall`; nothing here computes
+anything — it marshals numpy arrays to plain pointers and raises on error codes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "lib", "libmotifs_b200.so")
+
+
+class MB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libmotifs_b200 error {code}: {msg}")
+        self.code = code
+
+
+OK, E_INVALID, E_CUDA, E_NOMEM, E_BAD_SEQUENCE, E_HITS_OVERFLOW, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+SCAN_FWD, SCAN_RC, SCAN_WANT_HITS, SCAN_WANT_COUNTS = 1, 2, 4, 8
+MAX_MOTIF_LEN = 64
+
+HIT_DTYPE = np.dtype([("seq", "<u4"), ("pos", "<u4"), ("motif", "<u2"), ("score_f16", "<u2"),
+                      ("comp", "u1"), ("_pad", "u1", (3,))])
+assert HIT_DTYPE.itemsize == 16
+
+_lib = None
+
+
+def load():
+    """dlopen the library; fails loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise MB200Error(E_UNSUPPORTED, f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'` or `make`")
+    lib = C.CDLL(path)
+    p, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    sig = {
+        "mb200_version": (i32, []),
+        "mb200_create": (i32, [C.POINTER(p), i32]),
+        "mb200_destroy": (i32, [p]),
+        "mb200_last_error": (C.c_char_p, [p]),
+        "mb200_set_stream": (i32, [p, p]),
+        "mb200_last_timing": (i32, [p, p, p]),
+        "mb200_seqs_from_ascii": (i32, [p, p, i64, i64, C.POINTER(p)]),
+        "mb200_seqs_from_device_ascii": (i32, [p, p, i64, i64, C.POINTER(p)]),
+        "mb200_seqs_from_onehot_f32": (i32, [p, p, i64, i64, C.POINTER(p)]),
+        "mb200_seqs_free": (i32, [p, p]),
+        "mb200_seqs_shape": (i32, [p, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+        "mb200_seqs_download": (i32, [p, p, p, i64]),
+        "mb200_scan": (i32, [p, p, p, p, i32, i32, p, C.c_uint32, p, i64, C.POINTER(i64), p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One CUDA device + stream (mb200_ctx).  Not thread-safe."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load()
+        h = C.c_void_p()
+        rc = self._lib.mb200_create(C.byref(h), int(device))
+        if rc != OK:
+            raise MB200Error(rc, "mb200_create failed (no CUDA device / not a B200-class GPU?)")
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise MB200Error(rc, self._lib.mb200_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self._lib.mb200_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def last_timing(self):
+        ms = np.zeros(8, np.float32)
+        n = np.zeros(8, np.int64)
+        self._check(self._lib.mb200_last_timing(self._h, _ptr(ms), _ptr(n)))
+        names = ["pack", "scan", "count", "emit", "csc", "h2d", "d2h", "total"]
+        return {k: float(v) for k, v in zip(names, ms)}, {k: int(v) for k, v in zip(names, n)}
+
+    # ---- sequences ---------------------------------------------------------------------------
+    def seqs_from_ascii(self, ascii_rows: np.ndarray) -> "Sequences":
+        a = np.ascontiguousarray(ascii_rows, dtype=np.uint8)
+        if a.ndim != 2:
+            raise ValueError("ascii_rows must be (N, Lb) uint8")
+        h = C.c_void_p()
+        self._check(self._lib.mb200_seqs_from_ascii(self._h, _ptr(a), a.shape[0], a.shape[1], C.byref(h)))
+        return Sequences(self, h, a.shape[0], a.shape[1])
+
+    def seqs_from_host_ptr(self, ptr: int, N: int, Lb: int) -> "Sequences":
+        """ASCII rows at a raw host address (e.g. a pinned torch tensor's data_ptr())."""
+        h = C.c_void_p()
+        self._check(self._lib.mb200_seqs_from_ascii(self._h, C.c_void_p(ptr), N, Lb, C.byref(h)))
+        return Sequences(self, h, N, Lb)
+
+    def seqs_from_device_ptr(self, ptr: int, N: int, Lb: int) -> "Sequences":
+        h = C.c_void_p()
+        self._check(self._lib.mb200_seqs_from_device_ascii(self._h, C.c_void_p(ptr), N, Lb, C.byref(h)))
+        return Sequences(self, h, N, Lb)
+
+    def seqs_from_onehot(self, onehot: np.ndarray) -> "Sequences":
+        """onehot: the reference's data_matrix, Float32 (4*Lb, 1, N) or (4*Lb, N), Fortran (Julia) order,
+        i.e. a C-order numpy array of shape (N, 4*Lb) / (N, Lb, 4)."""
+        a = np.ascontiguousarray(onehot, dtype=np.float32)
+        a = a.reshape(a.shape[0], -1)
+        if a.shape[1] % 4:
+            raise ValueError("one-hot rows must have 4*Lb entries")
+        h = C.c_void_p()
+        self._check(self._lib.mb200_seqs_from_onehot_f32(self._h, _ptr(a), a.shape[0], a.shape[1] // 4, C.byref(h)))
+        return Sequences(self, h, a.shape[0], a.shape[1] // 4)
+
+    # ---- scan --------------------------------------------------------------------------------
+    def scan(self, seqs: "Sequences", pwms_f16: np.ndarray, lens, thresh_f16=None, *, fwd=True, rc=True,
+             want_hits=True, want_counts=True, hits_cap=None):
+        """pwms_f16: (K, 4, maxlen) array in Julia memory order, i.e. numpy shape (maxlen, 4, K) C-order
+        holding float16 (or uint16 bits).  Returns (hits structured array | None, counts (K,4) int64 | None)."""
+        pw = np.ascontiguousarray(pwms_f16)
+        if pw.dtype == np.float16:
+            pw = pw.view(np.uint16)
+        if pw.dtype != np.uint16 or pw.ndim != 3 or pw.shape[1] != 4:
+            raise ValueError("pwms_f16 must be float16/uint16 of numpy shape (maxlen, 4, K)")
+        maxlen, _, K = pw.shape
+        ln = np.ascontiguousarray(lens, dtype=np.int64)
+        if ln.shape != (K,):
+            raise ValueError("lens must have K entries")
+        th = None
+        if thresh_f16 is not None:
+            th = np.ascontiguousarray(thresh_f16)
+            if th.dtype == np.float16:
+                th = th.view(np.uint16)
+            if th.dtype != np.uint16 or th.shape != (K,):
+                raise ValueError("thresh_f16 must be K float16/uint16 values")
+        flags = (SCAN_FWD if fwd else 0) | (SCAN_RC if rc else 0) | (SCAN_WANT_HITS if want_hits else 0) | \
+                (SCAN_WANT_COUNTS if want_counts else 0)
+        counts = np.zeros((K, 4), np.int64) if want_counts else None
+        n_hits = C.c_int64(0)
+        cap = int(hits_cap) if hits_cap is not None else (1 << 16)
+        while True:
+            hits = np.zeros(cap if want_hits else 0, HIT_DTYPE)
+            rc_ = self._lib.mb200_scan(self._h, seqs._h, _ptr(pw), _ptr(ln), K, maxlen, _ptr(th), flags,
+                                       _ptr(hits) if want_hits else None, cap if want_hits else 0,
+                                       C.byref(n_hits), _ptr(counts))
+            if rc_ == E_HITS_OVERFLOW and hits_cap is None:
+                cap = int(n_hits.value)          # exact size reported by the library; retry once
+                continue
+            self._check(rc_)
+            break
+        return (hits[: n_hits.value] if want_hits else None), counts
+
+
+class Sequences:
+    """2 bit/base packed sequences resident in HBM (mb200_seqs)."""
+
+    def __init__(self, ctx: Context, handle, N, Lb):
+        self.ctx, self._h, self.N, self.Lb = ctx, handle, int(N), int(Lb)
+
+    @property
+    def words_per_seq(self):
+        return (self.Lb + 15) // 16
+
+    def download(self) -> np.ndarray:
+        out = np.zeros((self.N, self.words_per_seq), np.uint32)
+        self.ctx._check(self.ctx._lib.mb200_seqs_download(self.ctx._h, self._h, _ptr(out), out.size))
+        return out
+
+    def free(self):
+        if self._h and self.ctx._h:
+            self.ctx._lib.mb200_seqs_free(self.ctx._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

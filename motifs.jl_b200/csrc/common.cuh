@@ -1,0 +1,65 @@
+// Shared host-side plumbing of libmotifs_b200: context, error capture, event timers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/motifs_b200.h"
+
+enum { T_PACK = 0, T_SCAN = 1, T_COUNT = 2, T_EMIT = 3, T_CSC = 4, T_H2D = 5, T_D2H = 6, T_TOTAL = 7, T_N = 8 };
+
+struct mb200_ctx {
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;            // stream every kernel of this ctx is launched on
+    std::string err;
+    // timing of the last call
+    float ms[T_N] = {0};
+    int64_t launches[T_N] = {0};
+    cudaEvent_t ev[2 * T_N] = {nullptr};      // start/stop per slot
+    // grow-only device buffers reused across calls (slot 0 = generic scratch)
+    void* scratch = nullptr; size_t scratch_bytes = 0;
+    void* bufs[8] = {nullptr}; size_t buf_bytes[8] = {0};
+    void* pinned = nullptr;  size_t pinned_bytes = 0;
+};
+
+struct mb200_seqs {
+    int64_t N = 0, Lb = 0;
+    int64_t rowwords = 0;        // uint32 words per sequence = ceil(Lb/16)
+    uint32_t* words = nullptr;   // device, N*rowwords (+ zeroed tail pad of PAD_WORDS)
+    int device = 0;
+};
+static const int64_t SEQ_PAD_WORDS = 64;
+
+#define MB_FAIL(ctx, code, ...) do { char _b[512]; snprintf(_b, sizeof _b, __VA_ARGS__); \
+    if (ctx) (ctx)->err = _b; return (code); } while (0)
+
+#define MB_CUDA(ctx, expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
+    MB_FAIL(ctx, MB200_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); } } while (0)
+
+// Accumulating CUDA-event timer on the ctx stream.  Events are read back in mb_timers_collect().
+struct MbSpan { int slot; cudaEvent_t a, b; };
+struct MbTimers {
+    mb200_ctx* ctx; std::vector<MbSpan> spans;
+    explicit MbTimers(mb200_ctx* c) : ctx(c) {}
+    int begin(int slot) {
+        MbSpan s; s.slot = slot; cudaEventCreate(&s.a); cudaEventCreate(&s.b);
+        cudaEventRecord(s.a, ctx->stream); spans.push_back(s); return (int)spans.size() - 1;
+    }
+    void end(int id) { cudaEventRecord(spans[id].b, ctx->stream); }
+    void collect() {   // call after the stream was synchronised
+        for (auto& s : spans) { float ms = 0; if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) ctx->ms[s.slot] += ms;
+            cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+        spans.clear();
+    }
+    ~MbTimers() { for (auto& s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); } }
+};
+
+int mb_ensure_scratch(mb200_ctx* ctx, size_t bytes);
+int mb_ensure_pinned(mb200_ctx* ctx, size_t bytes);
+int mb_ensure_buf(mb200_ctx* ctx, int slot, size_t bytes);
+static inline void mb_reset_timing(mb200_ctx* ctx) { for (int i = 0; i < T_N; ++i) { ctx->ms[i] = 0; ctx->launches[i] = 0; } }

@@ -1,0 +1,91 @@
+// Context management of libmotifs_b200 (C ABI in include/motifs_b200.h).
+#include "common.cuh"
+
+extern "C" int32_t mb200_version(void) { return 100; }
+
+extern "C" int32_t mb200_create(mb200_ctx** out, int32_t device_id) {
+    if (!out) return MB200_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) return MB200_E_CUDA;     // no CPU fallback: fail loudly
+    if (device_id < 0 || device_id >= ndev) return MB200_E_INVALID;
+    mb200_ctx* ctx = new mb200_ctx();
+    ctx->device = device_id;
+    if (cudaSetDevice(device_id) != cudaSuccess) { delete ctx; return MB200_E_CUDA; }
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device_id) != cudaSuccess) { delete ctx; return MB200_E_CUDA; }
+    ctx->sm_count = p.multiProcessorCount;
+    ctx->smem_optin = p.sharedMemPerBlockOptin;
+    if (p.major < 10) {
+        // built for sm_100a only; any other device cannot run the cubin
+        delete ctx; return MB200_E_UNSUPPORTED;
+    }
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MB200_E_CUDA; }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return MB200_OK;
+}
+
+extern "C" int32_t mb200_destroy(mb200_ctx* ctx) {
+    if (!ctx) return MB200_E_INVALID;
+    cudaSetDevice(ctx->device);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    for (int i = 0; i < 8; ++i) if (ctx->bufs[i]) cudaFree(ctx->bufs[i]);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return MB200_OK;
+}
+
+extern "C" const char* mb200_last_error(const mb200_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : "null ctx";
+}
+
+extern "C" int32_t mb200_set_stream(mb200_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return MB200_E_INVALID;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return MB200_OK;
+}
+
+extern "C" int32_t mb200_last_timing(const mb200_ctx* ctx, float* out_ms8, int64_t* launches8) {
+    if (!ctx) return MB200_E_INVALID;
+    for (int i = 0; i < T_N; ++i) {
+        if (out_ms8) out_ms8[i] = ctx->ms[i];
+        if (launches8) launches8[i] = ctx->launches[i];
+    }
+    return MB200_OK;
+}
+
+int mb_ensure_scratch(mb200_ctx* ctx, size_t bytes) {
+    if (ctx->scratch_bytes >= bytes) return MB200_OK;
+    if (ctx->scratch) { cudaFree(ctx->scratch); ctx->scratch = nullptr; ctx->scratch_bytes = 0; }
+    if (cudaMalloc(&ctx->scratch, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        MB_FAIL(ctx, MB200_E_NOMEM, "cudaMalloc(%zu) for scratch failed", bytes);
+    }
+    ctx->scratch_bytes = bytes;
+    return MB200_OK;
+}
+
+int mb_ensure_pinned(mb200_ctx* ctx, size_t bytes) {
+    if (ctx->pinned_bytes >= bytes) return MB200_OK;
+    if (ctx->pinned) { cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
+    if (cudaMallocHost(&ctx->pinned, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        MB_FAIL(ctx, MB200_E_NOMEM, "cudaMallocHost(%zu) failed", bytes);
+    }
+    ctx->pinned_bytes = bytes;
+    return MB200_OK;
+}
+
+int mb_ensure_buf(mb200_ctx* ctx, int slot, size_t bytes) {
+    if (ctx->buf_bytes[slot] >= bytes) return MB200_OK;
+    if (ctx->bufs[slot]) { cudaFree(ctx->bufs[slot]); ctx->bufs[slot] = nullptr; ctx->buf_bytes[slot] = 0; }
+    if (cudaMalloc(&ctx->bufs[slot], bytes) != cudaSuccess) {
+        cudaGetLastError();
+        MB_FAIL(ctx, MB200_E_NOMEM, "cudaMalloc(%zu) for buffer %d failed", bytes, slot);
+    }
+    ctx->buf_bytes[slot] = bytes;
+    return MB200_OK;
+}

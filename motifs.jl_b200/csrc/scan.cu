@@ -1,0 +1,681 @@
+// PWM scan on sm_100a: scoring, threshold, hit masks, occurrence counts, sorted hit list.
+//
+// Reference being replaced (paths under the reference's src/):
+//   inference/_h3_1_alignment.jl:18-36   greedy_search!   — the score of motif k at start l is the
+//        LEFT-TO-RIGHT Float16 running sum of pwm[k, base(l+ind-1), ind] (x is one-hot, so the four
+//        products per column are one exact value and three signed zeros); kept when > 0.
+//   inference/_h3_1_alignment.jl:57-99   get_pos_scores_arr / gpu_scan — fwd pass with pwm, second
+//        pass with reverse(pwm) (both dims reversed = reverse complement), dense D2H + host findall.
+//   inference/_s2_filter_pos_w_scores.jl:116-125 filter_position_by_best_thresh! — score .> thresh.
+//   inference/_h4_overlap_ratio.jl:5-15,40-79    unique start positions, union_ranges coverage
+//        (with its dropped-last-interval behaviour), summed over sequences.
+//
+// Design:
+//   * sequences are 2 bit/base in HBM; a CTA stages a tile of packed words in shared memory with
+//     1-D bulk TMA (cp.async.bulk + mbarrier, double buffered); the window of one start position
+//     is 4 funnel-shifted registers, so the halo is just "read 6 words instead of 2".
+//   * motifs are sorted by length and processed 8 at a time; per (column, base) the table holds
+//     16 halves {k0 fwd, k0 rc, ..., k7 rc} = two LDS.128, feeding 8 HADD2 (one sequential
+//     Float16 add per cell, which is exactly the reference's rounding order).
+//   * threshold compare + warp ballot turn 32 start positions x 16 (motif,strand) into 16 mask
+//     words, stored as one coalesced 64 B line.  Counting and the sorted hit list are derived
+//     from the masks (deterministic, no atomics on the hit path, no sort).
+#include "common.cuh"
+#include <algorithm>
+#include <cstring>
+
+#define GROUP_MOTIFS 8
+#define GROUP_SLOTS 16                 // (motif, strand) accumulators per lane
+#define COL_BYTES 128                  // 4 bases x 16 halves
+#define SCAN_THREADS 512
+
+struct __align__(16) GroupMeta {
+    int32_t len;                       // columns to run (longest motif of the group)
+    int32_t tab_off;                   // byte offset of the group's table inside the motif block
+    int32_t npos[GROUP_MOTIFS];        // valid start positions per motif (Lb - len_k + 1, >= 0)
+    uint32_t thr2[GROUP_MOTIFS];       // half2 bits (thr_fwd, thr_rc)
+    int32_t pad[2];
+};                                     // 80 bytes
+static_assert(sizeof(GroupMeta) == 80, "GroupMeta must be 80 bytes");
+
+struct MBlock {
+    int64_t blob_off;                  // byte offset of this motif block's blob (tables then metas)
+    int32_t blob_bytes;                // multiple of 16
+    int32_t tab_bytes;                 // bytes of tables (metas follow)
+    int32_t g0, ng;                    // global group range
+    int32_t cost, pad;
+};
+
+struct ScanArgs {
+    const uint32_t* seqw; int64_t rowwords; int32_t W;
+    int64_t chunk0, nchunks;
+    uint32_t* mask; int32_t K2pad;
+    const uint8_t* blob; const MBlock* mblocks; int32_t n_mblocks;
+    int32_t tile_chunks; int64_t ntiles; int32_t tile_cap_words; int32_t blob_cap_bytes;
+    const int64_t* cta_range;          // [gridDim.x + 1] pair ranges (pair = mblock * ntiles + tile)
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: shared-memory addressing, mbarrier, 1-D bulk TMA.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// issue a (possibly large) copy as <=32 KiB bulk pieces, all completing on one mbarrier
+__device__ __forceinline__ void tma_load(uint32_t dst, const uint8_t* src, uint32_t bytes, uint32_t bar) {
+    mbar_expect_tx(bar, bytes);
+    for (uint32_t o = 0; o < bytes; o += 32768u) {
+        uint32_t n = min(32768u, bytes - o);
+        tma_bulk_g2s(dst + o, src + o, n, bar);
+    }
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+
+// one PWM column for 8 motifs x 2 strands: two 16 B table reads, eight sequential-Float16 adds
+__device__ __forceinline__ void column_step(uint32_t tab_col, uint32_t b32, __half2 (&acc)[8]) {
+    const uint4 v0 = lds128(tab_col + b32);
+    const uint4 v1 = lds128(tab_col + b32 + 16);
+    acc[0] = __hadd2(acc[0], as_h2(v0.x)); acc[1] = __hadd2(acc[1], as_h2(v0.y));
+    acc[2] = __hadd2(acc[2], as_h2(v0.z)); acc[3] = __hadd2(acc[3], as_h2(v0.w));
+    acc[4] = __hadd2(acc[4], as_h2(v1.x)); acc[5] = __hadd2(acc[5], as_h2(v1.y));
+    acc[6] = __hadd2(acc[6], as_h2(v1.z)); acc[7] = __hadd2(acc[7], as_h2(v1.w));
+}
+
+#define SCAN_SEGMENT(XS, J0)                                                            \
+    _Pragma("unroll") for (int jj = 0; jj < 16; ++jj) {                                 \
+        if ((J0) + jj >= len) goto columns_done;                                        \
+        const uint32_t b32 = (((XS) >> (2 * jj)) & 3u) << 5;                            \
+        column_step(tab + ((J0) + jj) * COL_BYTES, b32, acc);                           \
+    }
+
+__device__ __forceinline__ int64_t chunk_word(int64_t gq, int32_t W, int64_t rowwords, int64_t* n_out, int32_t* c_out) {
+    int64_t n = gq / W;
+    int32_t c = (int32_t)(gq - n * W);
+    *n_out = n; *c_out = c;
+    return n * rowwords + 2 * (int64_t)c;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* s_blob = smem;                                                        // tables + metas of one motif block
+    uint32_t* s_tile0 = reinterpret_cast<uint32_t*>(smem + a.blob_cap_bytes);
+    uint32_t* s_tile1 = s_tile0 + a.tile_cap_words;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tile1 + a.tile_cap_words);     // [0],[1] tiles, [2] blob
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int64_t q_lo = a.cta_range[blockIdx.x], q_hi = a.cta_range[blockIdx.x + 1];
+    if (q_lo >= q_hi) return;
+
+    const uint32_t bar0 = smem_u32(&s_bar[0]), bar1 = smem_u32(&s_bar[1]), bar2 = smem_u32(&s_bar[2]);
+    if (threadIdx.x == 0) {
+        mbar_init(bar0, 1); mbar_init(bar1, 1); mbar_init(bar2, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // tile geometry helper: words [lo4, hi) of the packed array feed local chunks [t*TC, ...)
+    auto tile_span = [&](int64_t tile, int64_t& lo4, uint32_t& bytes, int64_t& first, int32_t& cnt) {
+        first = tile * a.tile_chunks;
+        cnt = (int32_t)min((int64_t)a.tile_chunks, a.nchunks - first);
+        int64_t n; int32_t c;
+        int64_t lo = chunk_word(a.chunk0 + first, a.W, a.rowwords, &n, &c);
+        int64_t hi = chunk_word(a.chunk0 + first + cnt - 1, a.W, a.rowwords, &n, &c) + 6;
+        lo4 = lo & ~(int64_t)3;
+        bytes = (uint32_t)(((hi - lo4 + 3) & ~(int64_t)3) * 4);
+    };
+
+    uint32_t phase0 = 0, phase1 = 0, phase2 = 0;
+    int32_t cur_mb = -1;
+    // prefetch the first tile
+    if (threadIdx.x == 0) {
+        int64_t lo4, first; uint32_t bytes; int32_t cnt;
+        tile_span(q_lo % a.ntiles, lo4, bytes, first, cnt);
+        tma_load(smem_u32(s_tile0), reinterpret_cast<const uint8_t*>(a.seqw + lo4), bytes, bar0);
+    }
+
+    for (int64_t q = q_lo; q < q_hi; ++q) {
+        const int32_t mb = (int32_t)(q / a.ntiles);
+        const int64_t tile = q - (int64_t)mb * a.ntiles;
+        const int buf = (int)((q - q_lo) & 1);
+        const MBlock mbk = a.mblocks[mb];
+        if (mb != cur_mb) {
+            // every warp finished the previous pair at the __syncthreads closing the last iteration
+            if (threadIdx.x == 0) tma_load(smem_u32(s_blob), a.blob + mbk.blob_off, (uint32_t)mbk.blob_bytes, bar2);
+            cur_mb = mb;
+            mbar_wait(bar2, phase2); phase2 ^= 1;
+        }
+        if (threadIdx.x == 0 && q + 1 < q_hi) {      // prefetch next tile into the other buffer
+            int64_t lo4, first; uint32_t bytes; int32_t cnt;
+            tile_span((q + 1) % a.ntiles, lo4, bytes, first, cnt);
+            tma_load(smem_u32(buf ? s_tile0 : s_tile1), reinterpret_cast<const uint8_t*>(a.seqw + lo4), bytes, buf ? bar0 : bar1);
+        }
+        int64_t lo4, first; uint32_t tbytes; int32_t cnt;
+        tile_span(tile, lo4, tbytes, first, cnt);
+        if (buf == 0) { mbar_wait(bar0, phase0); phase0 ^= 1; } else { mbar_wait(bar1, phase1); phase1 ^= 1; }
+        const uint32_t* s_tile = buf ? s_tile1 : s_tile0;
+        const GroupMeta* s_meta = reinterpret_cast<const GroupMeta*>(s_blob + mbk.tab_bytes);
+        const uint32_t tab_base = smem_u32(s_blob);
+
+        for (int32_t i = warp; i < cnt; i += nwarps) {
+            int64_t n; int32_t c;
+            const int64_t lq = first + i;
+            const int64_t w0i = chunk_word(a.chunk0 + lq, a.W, a.rowwords, &n, &c) - lo4;
+            const int32_t pos = c * 32 + lane;
+            const uint32_t* wp = s_tile + w0i + (lane >> 4);
+            const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+            const uint32_t sh = (lane & 15) * 2;
+            const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
+            const uint32_t x2 = __funnelshift_r(w2, w3, sh), x3 = __funnelshift_r(w3, w4, sh);
+            uint32_t* mrow = a.mask + lq * (int64_t)a.K2pad + (int64_t)mbk.g0 * GROUP_SLOTS;
+
+            for (int32_t g = 0; g < mbk.ng; ++g) {
+                const GroupMeta* gm = s_meta + g;
+                const int32_t len = gm->len;
+                const uint32_t tab = tab_base + gm->tab_off;
+                __half2 acc[8];
+                #pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = as_h2(0u);
+                SCAN_SEGMENT(x0, 0)
+                SCAN_SEGMENT(x1, 16)
+                SCAN_SEGMENT(x2, 32)
+                SCAN_SEGMENT(x3, 48)
+            columns_done:
+                uint32_t myword = 0;
+                #pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t m = __hgt2_mask(acc[k], as_h2(gm->thr2[k]));
+                    const bool valid = pos < gm->npos[k];
+                    const uint32_t bf = __ballot_sync(0xffffffffu, valid && (m & 0xFFFFu));
+                    const uint32_t br = __ballot_sync(0xffffffffu, valid && (m >> 16));
+                    if (lane == 2 * k) myword = bf;
+                    if (lane == 2 * k + 1) myword = br;
+                }
+                if (lane < GROUP_SLOTS) mrow[g * GROUP_SLOTS + lane] = myword;
+            }
+        }
+        __syncthreads();      // tile buffer `buf` and (possibly) the blob may be overwritten next
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Counting from the masks: one thread per (sequence, motif).  Mask word layout:
+//   mask[(n*W + w) * K2pad + slotpair*2 + strand]
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t dilate32(uint32_t u, int len) {
+    // set bits i..i+len-1 for every set bit i (bits above 31 are dropped)
+    uint32_t r = u; int k = 1;
+    while (k < len && k < 32) { int s = min(k, len - k); r |= r << s; k += s; }
+    return r;
+}
+
+__global__ void __launch_bounds__(256) count_kernel(const uint32_t* __restrict__ mask, int64_t nseq, int32_t W, int32_t K2pad,
+                                                    const int32_t* __restrict__ pair2motif, const int32_t* __restrict__ pairlen,
+                                                    unsigned long long* __restrict__ counts, uint32_t* __restrict__ unit_cnt, int32_t K) {
+    const int32_t P = K2pad / 2;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nseq * P) return;
+    const int64_t n = t / P;
+    const int32_t m2 = (int32_t)(t - n * P);
+    const int32_t k = pair2motif[m2];
+    if (k < 0) return;
+    const int32_t len = pairlen[m2];
+    const uint2* mp = reinterpret_cast<const uint2*>(mask) + (n * W) * (int64_t)P + m2;
+    uint32_t nf = 0, nr = 0, uq = 0, cov = 0;
+    int32_t cu = 0;             // positions < cu are covered by earlier hits
+    int32_t p1 = -1, p2 = -1;   // largest / second largest distinct start position
+    bool dup = false;           // p1 hit on both strands
+    for (int32_t w = 0; w < W; ++w) {
+        const uint2 fr = __ldg(mp + (int64_t)w * P);
+        const uint32_t f = fr.x, r = fr.y, U = f | r;
+        const int32_t base = w * 32;
+        const int32_t cb = cu - base;
+        uint32_t cm = cb >= 32 ? 0xffffffffu : (cb > 0 ? ((1u << cb) - 1u) : 0u);
+        if (U) {
+            nf += __popc(f); nr += __popc(r); uq += __popc(U);
+            cm |= dilate32(U, len);
+            const int32_t hi = 31 - __clz(U);
+            cu = max(cu, base + hi + len);
+            const uint32_t U2 = U & ~(1u << hi);
+            p2 = U2 ? base + 31 - __clz(U2) : p1;
+            p1 = base + hi;
+            dup = ((f >> hi) & (r >> hi) & 1u) != 0;
+        }
+        cov += __popc(cm);
+    }
+    cov += max(0, cu - W * 32);
+    const uint32_t nh = nf + nr;
+    if (unit_cnt) {
+        reinterpret_cast<uint2*>(unit_cnt)[n * K + k] = make_uint2(nf, nr);
+    }
+    if (nh) {
+        uint32_t covq = cov;
+        if (nh >= 2 && !dup) covq -= (uint32_t)min(len, p1 - p2);   // union_ranges drops the last interval
+        atomicAdd(&counts[k * 4 + 0], (unsigned long long)nh);
+        atomicAdd(&counts[k * 4 + 1], (unsigned long long)uq);
+        atomicAdd(&counts[k * 4 + 2], (unsigned long long)covq);
+        atomicAdd(&counts[k * 4 + 3], (unsigned long long)cov);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exclusive prefix sum u32 -> u64 (three small kernels), used to place hits without atomics.
+// ---------------------------------------------------------------------------------------------
+#define PS_THREADS 256
+#define PS_ITEMS 8
+#define PS_TILE (PS_THREADS * PS_ITEMS)
+
+__device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long v, unsigned long long* total) {
+    __shared__ unsigned long long s_w[PS_THREADS / 32 + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = v;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long x = lane < (int)(blockDim.x >> 5) ? s_w[lane] : 0ull, xi = x;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, xi, o); if (lane >= o) xi += y; }
+        if (lane < (int)(blockDim.x >> 5)) s_w[lane] = xi - x;
+        if (lane == 31) s_w[PS_THREADS / 32] = xi;
+    }
+    __syncthreads();
+    unsigned long long r = s_w[warp] + inc - v;
+    if (total) *total = s_w[PS_THREADS / 32];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(PS_THREADS) ps_block_sums(const uint32_t* __restrict__ in, int64_t n, unsigned long long* __restrict__ bsum) {
+    const int64_t base = (int64_t)blockIdx.x * PS_TILE;
+    unsigned long long s = 0;
+    #pragma unroll
+    for (int i = 0; i < PS_ITEMS; ++i) { int64_t j = base + (int64_t)i * PS_THREADS + threadIdx.x; if (j < n) s += in[j]; }
+    unsigned long long tot;
+    block_excl_scan(s, &tot);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(PS_THREADS) ps_scan_sums(unsigned long long* __restrict__ bsum, int64_t nb, unsigned long long* __restrict__ total) {
+    unsigned long long carry = 0;
+    for (int64_t b0 = 0; b0 < nb; b0 += PS_THREADS) {
+        int64_t j = b0 + threadIdx.x;
+        unsigned long long v = j < nb ? bsum[j] : 0ull, tot;
+        unsigned long long e = block_excl_scan(v, &tot);
+        if (j < nb) bsum[j] = carry + e;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(PS_THREADS) ps_apply(const uint32_t* __restrict__ in, int64_t n, const unsigned long long* __restrict__ bsum,
+                                                       unsigned long long* __restrict__ out) {
+    const int64_t base = (int64_t)blockIdx.x * PS_TILE + (int64_t)threadIdx.x * PS_ITEMS;
+    uint32_t v[PS_ITEMS]; unsigned long long s = 0;
+    #pragma unroll
+    for (int i = 0; i < PS_ITEMS; ++i) { v[i] = (base + i < n) ? in[base + i] : 0u; s += v[i]; }
+    unsigned long long e = block_excl_scan(s, nullptr) + bsum[blockIdx.x];
+    #pragma unroll
+    for (int i = 0; i < PS_ITEMS; ++i) { if (base + i < n) out[base + i] = e; e += v[i]; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Hit emission: one thread per (sequence, motif, strand) walks its mask bits in ascending position
+// and recomputes the Float16 score with the same sequential adds as the scan kernel.
+// ---------------------------------------------------------------------------------------------
+struct EmitMotif { int32_t slot; int32_t len; int64_t tab_off; };   // slot = global (group*16 + i*2) of the fwd strand
+
+__global__ void __launch_bounds__(256) emit_kernel(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ seqw, int64_t rowwords,
+                                                   int64_t seq0, int64_t nseq, int32_t W, int32_t K2pad, int32_t K,
+                                                   const EmitMotif* __restrict__ em, const uint8_t* __restrict__ blob,
+                                                   const uint32_t* __restrict__ unit_cnt, const unsigned long long* __restrict__ unit_off,
+                                                   mb200_hit* __restrict__ hits) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nseq * K * 2) return;
+    if (unit_cnt[u] == 0) return;
+    const int32_t strand = (int32_t)(u & 1);
+    const int64_t nk = u >> 1;
+    const int64_t n = nk / K;
+    const int32_t k = (int32_t)(nk - n * K);
+    const EmitMotif m = em[k];
+    const int32_t slot = m.slot + strand;
+    const uint8_t* tab = blob + m.tab_off + (slot & (GROUP_SLOTS - 1)) * 2;
+    const uint32_t* srow = seqw + (seq0 + n) * rowwords;
+    unsigned long long off = unit_off[u];
+    for (int32_t w = 0; w < W; ++w) {
+        uint32_t bits = mask[((n * W) + w) * (int64_t)K2pad + slot];
+        while (bits) {
+            const int32_t b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int32_t p = w * 32 + b;
+            __half s = __ushort_as_half((unsigned short)0);
+            for (int32_t j = 0; j < m.len; ++j) {
+                const int32_t q = p + j;
+                const uint32_t base = (srow[q >> 4] >> ((q & 15) * 2)) & 3u;
+                const __half e = *reinterpret_cast<const __half*>(tab + (int64_t)j * COL_BYTES + base * 32);
+                s = __hadd(s, e);
+            }
+            // mb200_hit as one 16 B store: {seq, pos, motif | score<<16, comp}
+            const uint4 h = make_uint4((uint32_t)(seq0 + n), (uint32_t)p,
+                                       (uint32_t)k | ((uint32_t)__half_as_ushort(s) << 16), (uint32_t)strand);
+            reinterpret_cast<uint4*>(hits)[off++] = h;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side: plan (sorted groups, tables, thresholds), batching, launches.
+// ---------------------------------------------------------------------------------------------
+static inline bool h16_nonfinite(uint16_t h) { return (h & 0x7C00u) == 0x7C00u; }
+static inline float h16_to_float(uint16_t h) { __half_raw r; r.x = h; return __half2float(__half(r)); }
+
+struct ScanPlan {
+    int K = 0, ngroups = 0, K2pad = 0;
+    std::vector<uint8_t> blob;
+    std::vector<MBlock> mblocks;
+    std::vector<int32_t> pair2motif, pairlen;
+    std::vector<EmitMotif> em;
+    int max_blob_bytes = 0;
+    int minlen = 0;
+};
+
+static int build_plan(mb200_ctx* ctx, const uint16_t* pwms, const int64_t* lens, int K, int maxlen, const uint16_t* thresh,
+                      uint32_t flags, int64_t Lb, size_t table_budget, ScanPlan& P) {
+    P.K = K;
+    std::vector<int> order(K);
+    for (int k = 0; k < K; ++k) {
+        if (lens[k] < 1 || lens[k] > maxlen || lens[k] > MB200_MAX_MOTIF_LEN)
+            MB_FAIL(ctx, MB200_E_INVALID, "motif %d: length %lld outside [1, min(maxlen=%d, %d)]", k, (long long)lens[k], maxlen, MB200_MAX_MOTIF_LEN);
+        order[k] = k;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lens[a] < lens[b]; });
+    P.minlen = (int)lens[order[0]];
+    P.ngroups = (K + GROUP_MOTIFS - 1) / GROUP_MOTIFS;
+    P.K2pad = P.ngroups * GROUP_SLOTS;
+    P.pair2motif.assign(P.K2pad / 2, -1);
+    P.pairlen.assign(P.K2pad / 2, 0);
+    P.em.resize(K);
+    auto pw = [&](int k, int a, int ind) -> uint16_t { return pwms[(size_t)k + (size_t)K * ((size_t)a + 4 * (size_t)ind)]; };
+
+    // group lengths, then greedy partition into motif blocks under the shared-memory budget
+    std::vector<int> glen(P.ngroups);
+    for (int g = 0; g < P.ngroups; ++g) glen[g] = (int)lens[order[std::min(K - 1, g * GROUP_MOTIFS + GROUP_MOTIFS - 1)]];
+    int g = 0;
+    while (g < P.ngroups) {
+        MBlock mb; memset(&mb, 0, sizeof mb);
+        mb.g0 = g; size_t tb = 0; int cost = 0;
+        while (g < P.ngroups) {
+            size_t add = (size_t)glen[g] * COL_BYTES;
+            size_t metas = (size_t)(g - mb.g0 + 1) * sizeof(GroupMeta);
+            if (g > mb.g0 && tb + add + metas > table_budget) break;
+            tb += add; cost += glen[g]; ++g;
+        }
+        mb.ng = g - mb.g0; mb.tab_bytes = (int32_t)tb; mb.cost = cost;
+        mb.blob_bytes = (int32_t)((tb + (size_t)mb.ng * sizeof(GroupMeta) + 15) & ~(size_t)15);
+        if ((size_t)mb.blob_bytes > table_budget + 4096)
+            MB_FAIL(ctx, MB200_E_UNSUPPORTED, "a single motif group needs %d B of shared memory", mb.blob_bytes);
+        P.mblocks.push_back(mb);
+    }
+    size_t total = 0;
+    for (auto& mb : P.mblocks) { mb.blob_off = (int64_t)total; total += ((size_t)mb.blob_bytes + 127) & ~(size_t)127; P.max_blob_bytes = std::max(P.max_blob_bytes, mb.blob_bytes); }
+    P.blob.assign(total, 0);
+
+    for (auto& mb : P.mblocks) {
+        uint8_t* tabs = P.blob.data() + mb.blob_off;
+        GroupMeta* metas = reinterpret_cast<GroupMeta*>(tabs + mb.tab_bytes);
+        int toff = 0;
+        for (int gi = 0; gi < mb.ng; ++gi) {
+            const int gg = mb.g0 + gi;
+            GroupMeta gm; memset(&gm, 0, sizeof gm);
+            gm.len = glen[gg]; gm.tab_off = toff;
+            uint16_t* T = reinterpret_cast<uint16_t*>(tabs + toff);   // [col][base][16]
+            for (int i = 0; i < GROUP_MOTIFS; ++i) {
+                const int idx = gg * GROUP_MOTIFS + i;
+                uint16_t thr_f = 0x7C00u, thr_r = 0x7C00u;            // +Inf: never a hit
+                if (idx < K) {
+                    const int k = order[idx];
+                    const int len = (int)lens[k];
+                    gm.npos[i] = (int32_t)std::max<int64_t>(0, Lb - len + 1);
+                    uint16_t t = 0;
+                    if (thresh) {
+                        const uint16_t raw = thresh[k];
+                        const bool isnan = h16_nonfinite(raw) && (raw & 0x03FFu);
+                        if (isnan) t = 0x7C00u;
+                        else t = h16_to_float(raw) > 0.f ? raw : (uint16_t)0;
+                    }
+                    if (flags & MB200_SCAN_FWD) thr_f = t;
+                    if (flags & MB200_SCAN_RC) thr_r = t;
+                    P.pair2motif[gg * GROUP_MOTIFS + i] = k;
+                    P.pairlen[gg * GROUP_MOTIFS + i] = len;
+                    P.em[k].slot = gg * GROUP_SLOTS + i * 2;
+                    P.em[k].len = len;
+                    P.em[k].tab_off = mb.blob_off + toff;
+                    for (int j = 0; j < len; ++j) {
+                        int nf_f = 0;
+                        for (int a2 = 0; a2 < 4; ++a2) nf_f += h16_nonfinite(pw(k, a2, j));
+                        for (int b = 0; b < 4; ++b) {
+                            // forward table: column j, base b.  A non-selected non-finite entry times 0 is NaN
+                            // in the reference's sum (greedy_search! adds pwm*x for all four a).
+                            const uint16_t v = pw(k, b, j);
+                            const uint16_t ef = (nf_f - (int)h16_nonfinite(v)) > 0 ? (uint16_t)0x7E00u : v;
+                            T[(size_t)j * 64 + b * 16 + i * 2 + 0] = ef;
+                            // reverse(pwm): rc[a][j] = pwm[3-a][len-1-j]; its column j mirrors forward column len-1-j
+                            const int jr = len - 1 - j;
+                            const uint16_t vr = pw(k, 3 - b, jr);
+                            int nf_r = 0;
+                            for (int a2 = 0; a2 < 4; ++a2) nf_r += h16_nonfinite(pw(k, a2, jr));
+                            const uint16_t er = (nf_r - (int)h16_nonfinite(vr)) > 0 ? (uint16_t)0x7E00u : vr;
+                            T[(size_t)j * 64 + b * 16 + i * 2 + 1] = er;
+                        }
+                    }
+                }
+                gm.thr2[i] = (uint32_t)thr_f | ((uint32_t)thr_r << 16);
+            }
+            metas[gi] = gm;
+            toff += glen[gg] * COL_BYTES;
+        }
+    }
+    return MB200_OK;
+}
+
+extern "C" int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t* pwms_f16, const int64_t* lens, int32_t K,
+                              int32_t maxlen, const uint16_t* thresh_f16, uint32_t flags, mb200_hit* hits, int64_t hits_cap,
+                              int64_t* n_hits, int64_t* counts) {
+    if (!ctx) return MB200_E_INVALID;
+    if (!seqs || !pwms_f16 || !lens || K <= 0 || K > 65535 || maxlen <= 0)
+        MB_FAIL(ctx, MB200_E_INVALID, "scan: bad arguments (K=%d maxlen=%d)", K, maxlen);
+    if (!(flags & (MB200_SCAN_FWD | MB200_SCAN_RC))) MB_FAIL(ctx, MB200_E_INVALID, "scan: neither FWD nor RC requested");
+    const bool want_hits = (flags & MB200_SCAN_WANT_HITS) != 0;
+    const bool want_counts = (flags & MB200_SCAN_WANT_COUNTS) != 0;
+    if (want_hits && (!n_hits || (hits_cap > 0 && !hits))) MB_FAIL(ctx, MB200_E_INVALID, "scan: WANT_HITS needs hits/n_hits");
+    if (want_counts && !counts) MB_FAIL(ctx, MB200_E_INVALID, "scan: WANT_COUNTS needs counts");
+    if (seqs->device != ctx->device) MB_FAIL(ctx, MB200_E_INVALID, "scan: sequences live on device %d, ctx on %d", seqs->device, ctx->device);
+    MB_CUDA(ctx, cudaSetDevice(ctx->device));
+    mb_reset_timing(ctx);
+    if (n_hits) *n_hits = 0;
+    if (counts) memset(counts, 0, sizeof(int64_t) * 4 * (size_t)K);
+
+    const int64_t N = seqs->N, Lb = seqs->Lb, rowwords = seqs->rowwords;
+    const size_t table_budget = 160 * 1024;
+    ScanPlan P;
+    int rc = build_plan(ctx, pwms_f16, lens, K, maxlen, thresh_f16, flags, Lb, table_budget, P);
+    if (rc) return rc;
+    const int64_t npos_max = Lb - P.minlen + 1;
+    if (N == 0 || npos_max <= 0) return MB200_OK;       // nothing can be scored
+    const int64_t W64 = (npos_max + 31) / 32;
+    if (W64 > 0x3fffffff) MB_FAIL(ctx, MB200_E_UNSUPPORTED, "sequence too long");
+    const int32_t W = (int32_t)W64;
+
+    // ---- device buffers -------------------------------------------------------------------
+    // buf 1: plan (blob, mblocks, pair tables, emit table, cta ranges, counts)
+    const size_t off_blob = 0;
+    const size_t off_mb = (P.blob.size() + 255) & ~(size_t)255;
+    const size_t off_p2m = off_mb + ((P.mblocks.size() * sizeof(MBlock) + 255) & ~(size_t)255);
+    const size_t off_plen = off_p2m + ((P.pair2motif.size() * 4 + 255) & ~(size_t)255);
+    const size_t off_em = off_plen + ((P.pairlen.size() * 4 + 255) & ~(size_t)255);
+    const size_t off_rng = off_em + ((P.em.size() * sizeof(EmitMotif) + 255) & ~(size_t)255);
+    const int grid = ctx->sm_count;
+    const size_t off_cnt = off_rng + (((size_t)(grid + 1) * 8 + 255) & ~(size_t)255);
+    const size_t off_tot = off_cnt + (((size_t)K * 4 * 8 + 255) & ~(size_t)255);
+    const size_t plan_bytes = off_tot + 256;
+    rc = mb_ensure_buf(ctx, 1, plan_bytes); if (rc) return rc;
+    uint8_t* d_plan = (uint8_t*)ctx->bufs[1];
+    std::vector<uint8_t> h_plan(plan_bytes, 0);
+    memcpy(h_plan.data() + off_blob, P.blob.data(), P.blob.size());
+    memcpy(h_plan.data() + off_mb, P.mblocks.data(), P.mblocks.size() * sizeof(MBlock));
+    memcpy(h_plan.data() + off_p2m, P.pair2motif.data(), P.pair2motif.size() * 4);
+    memcpy(h_plan.data() + off_plen, P.pairlen.data(), P.pairlen.size() * 4);
+    memcpy(h_plan.data() + off_em, P.em.data(), P.em.size() * sizeof(EmitMotif));
+
+    // ---- batching: masks of one batch stay under a budget -----------------------------------
+    const size_t mask_budget = (size_t)2 << 30;
+    const size_t mask_bytes_per_seq = (size_t)W * P.K2pad * 4;
+    int64_t seqs_per_batch = std::max<int64_t>(1, (int64_t)(mask_budget / mask_bytes_per_seq));
+    if (seqs_per_batch > N) seqs_per_batch = N;
+    if ((double)seqs_per_batch * W > 2.0e9) seqs_per_batch = std::max<int64_t>(1, (int64_t)(2.0e9 / W));
+    rc = mb_ensure_buf(ctx, 2, (size_t)seqs_per_batch * mask_bytes_per_seq); if (rc) return rc;
+    uint32_t* d_mask = (uint32_t*)ctx->bufs[2];
+    uint32_t* d_unit_cnt = nullptr; unsigned long long* d_unit_off = nullptr; unsigned long long* d_bsum = nullptr;
+    int64_t units_per_batch = seqs_per_batch * K * 2;
+    int64_t ps_blocks = (units_per_batch + PS_TILE - 1) / PS_TILE;
+    if (want_hits) {
+        size_t b = (((size_t)units_per_batch * 4 + 255) & ~(size_t)255) + (((size_t)units_per_batch * 8 + 255) & ~(size_t)255) +
+                   (size_t)ps_blocks * 8 + 256;
+        rc = mb_ensure_buf(ctx, 3, b); if (rc) return rc;
+        d_unit_cnt = (uint32_t*)ctx->bufs[3];
+        d_unit_off = (unsigned long long*)((uint8_t*)ctx->bufs[3] + (((size_t)units_per_batch * 4 + 255) & ~(size_t)255));
+        d_bsum = (unsigned long long*)((uint8_t*)d_unit_off + (((size_t)units_per_batch * 8 + 255) & ~(size_t)255));
+    }
+
+    // ---- tiling and per-CTA pair ranges (balanced by column count of the motif block) --------
+    const int32_t tile_chunks = 16 * 14;
+    auto tiles_of = [&](int64_t nchunks) { return (nchunks + tile_chunks - 1) / tile_chunks; };
+    const int64_t crossings = (tile_chunks - 1) / W + 1;
+    const int64_t gap = std::max<int64_t>(0, rowwords - 2 * (int64_t)W + 2);
+    const int32_t tile_cap_words = (int32_t)((2 * (int64_t)tile_chunks + crossings * gap + 6 + 4 + 3) & ~(int64_t)3);
+    const int32_t blob_cap = (P.max_blob_bytes + 127) & ~127;
+    const size_t smem_bytes = (size_t)blob_cap + (size_t)tile_cap_words * 8 + 64;
+    if (smem_bytes > ctx->smem_optin) MB_FAIL(ctx, MB200_E_UNSUPPORTED, "scan needs %zu B shared memory (> %zu)", smem_bytes, ctx->smem_optin);
+    MB_CUDA(ctx, cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+
+    MbTimers tm(ctx);
+    const int t_total = tm.begin(T_TOTAL);
+    int th = tm.begin(T_H2D);
+    MB_CUDA(ctx, cudaMemcpyAsync(d_plan, h_plan.data(), plan_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    tm.end(th);
+    unsigned long long* d_counts = (unsigned long long*)(d_plan + off_cnt);
+    unsigned long long* d_total = (unsigned long long*)(d_plan + off_tot);
+    int64_t* d_rng = (int64_t*)(d_plan + off_rng);
+
+    int64_t hits_written = 0, hits_needed = 0;
+    std::vector<int64_t> h_rng(grid + 1);
+    int64_t last_nchunks = -1;
+    for (int64_t s0 = 0; s0 < N; s0 += seqs_per_batch) {
+        const int64_t ns = std::min(seqs_per_batch, N - s0);
+        const int64_t nchunks = ns * W;
+        const int64_t ntiles = tiles_of(nchunks);
+        if (nchunks != last_nchunks) {
+            // weighted contiguous split of pairs (mblock-major) over CTAs
+            double total_cost = 0;
+            for (auto& mb : P.mblocks) total_cost += (double)mb.cost * (double)ntiles;
+            size_t mbi = 0; double acc = 0; int64_t q = 0;
+            h_rng[0] = 0;
+            for (int b = 1; b <= grid; ++b) {
+                const double target = total_cost * b / grid;
+                while (mbi < P.mblocks.size()) {
+                    const double c = (double)P.mblocks[mbi].cost;
+                    const int64_t qend = (int64_t)(mbi + 1) * ntiles;
+                    int64_t take = (int64_t)((target - acc) / c + 0.5);
+                    if (take < 0) take = 0;
+                    if (q + take >= qend) { acc += (double)(qend - q) * c; q = qend; ++mbi; }
+                    else { acc += (double)take * c; q += take; break; }
+                }
+                h_rng[b] = (b == grid) ? (int64_t)P.mblocks.size() * ntiles : q;
+            }
+            MB_CUDA(ctx, cudaMemcpyAsync(d_rng, h_rng.data(), (size_t)(grid + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+            MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // h_rng is reused by the next batch shape
+            last_nchunks = nchunks;
+        }
+        ScanArgs a;
+        a.seqw = seqs->words; a.rowwords = rowwords; a.W = W;
+        a.chunk0 = s0 * W; a.nchunks = nchunks;
+        a.mask = d_mask; a.K2pad = P.K2pad;
+        a.blob = d_plan + off_blob; a.mblocks = (const MBlock*)(d_plan + off_mb); a.n_mblocks = (int32_t)P.mblocks.size();
+        a.tile_chunks = tile_chunks; a.ntiles = ntiles; a.tile_cap_words = tile_cap_words; a.blob_cap_bytes = blob_cap;
+        a.cta_range = d_rng;
+        int t1 = tm.begin(T_SCAN);
+        scan_kernel<<<grid, SCAN_THREADS, smem_bytes, ctx->stream>>>(a);
+        tm.end(t1);
+        ctx->launches[T_SCAN] += 1;
+        MB_CUDA(ctx, cudaGetLastError());
+
+        int t2 = tm.begin(T_COUNT);
+        const int64_t cthreads = ns * (P.K2pad / 2);
+        count_kernel<<<(unsigned)((cthreads + 255) / 256), 256, 0, ctx->stream>>>(d_mask, ns, W, P.K2pad, (const int32_t*)(d_plan + off_p2m),
+                                                                              (const int32_t*)(d_plan + off_plen), d_counts, d_unit_cnt, K);
+        tm.end(t2);
+        ctx->launches[T_COUNT] += 1;
+        MB_CUDA(ctx, cudaGetLastError());
+
+        if (want_hits) {
+            const int64_t units = ns * K * 2;
+            const int64_t nb = (units + PS_TILE - 1) / PS_TILE;
+            int t3 = tm.begin(T_EMIT);
+            ps_block_sums<<<(unsigned)nb, PS_THREADS, 0, ctx->stream>>>(d_unit_cnt, units, d_bsum);
+            ps_scan_sums<<<1, PS_THREADS, 0, ctx->stream>>>(d_bsum, nb, d_total);
+            ps_apply<<<(unsigned)nb, PS_THREADS, 0, ctx->stream>>>(d_unit_cnt, units, d_bsum, d_unit_off);
+            tm.end(t3);
+            ctx->launches[T_EMIT] += 3;
+            unsigned long long h_total = 0;
+            MB_CUDA(ctx, cudaMemcpyAsync(&h_total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            hits_needed += (int64_t)h_total;
+            if (h_total && hits_needed <= hits_cap) {
+                rc = mb_ensure_buf(ctx, 4, (size_t)h_total * sizeof(mb200_hit)); if (rc) return rc;
+                mb200_hit* d_hits = (mb200_hit*)ctx->bufs[4];
+                int t4 = tm.begin(T_EMIT);
+                emit_kernel<<<(unsigned)((units + 255) / 256), 256, 0, ctx->stream>>>(d_mask, seqs->words, rowwords, s0, ns, W, P.K2pad, K,
+                                                                                   (const EmitMotif*)(d_plan + off_em), d_plan + off_blob,
+                                                                                   d_unit_cnt, d_unit_off, d_hits);
+                tm.end(t4);
+                ctx->launches[T_EMIT] += 1;
+                MB_CUDA(ctx, cudaGetLastError());
+                int t5 = tm.begin(T_D2H);
+                MB_CUDA(ctx, cudaMemcpyAsync(hits + hits_written, d_hits, (size_t)h_total * sizeof(mb200_hit), cudaMemcpyDeviceToHost, ctx->stream));
+                tm.end(t5);
+                MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                hits_written += (int64_t)h_total;
+            }
+        }
+    }
+    if (want_counts) {
+        int t6 = tm.begin(T_D2H);
+        MB_CUDA(ctx, cudaMemcpyAsync(counts, d_counts, (size_t)K * 4 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        tm.end(t6);
+    }
+    tm.end(t_total);
+    MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    tm.collect();
+    if (n_hits) *n_hits = hits_needed;
+    if (want_hits && hits_needed > hits_cap)
+        MB_FAIL(ctx, MB200_E_HITS_OVERFLOW, "scan: %lld hits, capacity %lld", (long long)hits_needed, (long long)hits_cap);
+    return MB200_OK;
+}

@@ -1,0 +1,182 @@
+"""Parity of the CUDA scan path (through the C ABI) against the CPU oracle.  Bit-exact: positions, strands,
+Float16 score bits, counts.  Reference: inference/_h3_1_alignment.jl, _s2_filter_pos_w_scores.jl:116-125,
+_h4_overlap_ratio.jl:5-79."""
+import numpy as np
+import pytest
+
+import motifs_jl_b200 as mb
+from motifs_jl_b200 import inference, synth
+from oracle import scan_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(ctx, ascii_rows, ms, thresh=None, strands=3):
+    codes = so.ascii_to_codes(ascii_rows)
+    pw, lens = so.pack_pwms(ms.pwms)
+    seqs = ctx.seqs_from_ascii(ascii_rows)
+    hits, counts = ctx.scan(seqs, pw, lens, thresh, fwd=bool(strands & 1), rc=bool(strands & 2))
+    ohits, ocounts = so.scan(pw, lens, codes, thresh, strands)
+    assert len(hits) == len(ohits)
+    for f in ("seq", "pos", "motif", "score_f16", "comp"):
+        assert np.array_equal(hits[f], ohits[f]), f
+    assert np.array_equal(counts, ocounts)
+    # counts-only call must agree with the hits call
+    _, c2 = ctx.scan(seqs, pw, lens, thresh, fwd=bool(strands & 1), rc=bool(strands & 2), want_hits=False)
+    assert np.array_equal(c2, ocounts)
+    seqs.free()
+    return hits, counts
+
+
+def test_pack_matches_layout(ctx):
+    a = synth.random_ascii(37, 101, 7)
+    s = ctx.seqs_from_ascii(a)
+    assert np.array_equal(s.download(), so.pack_codes(so.ascii_to_codes(a)))
+    s.free()
+    # lower case and one-hot input give the same words
+    low = np.char.lower(a.view("S1")).view(np.uint8).reshape(a.shape)
+    s2 = ctx.seqs_from_ascii(low)
+    assert np.array_equal(s2.download(), so.pack_codes(so.ascii_to_codes(a)))
+    s2.free()
+    codes = so.ascii_to_codes(a)
+    onehot = np.zeros((37, 101, 4), np.float32)
+    np.put_along_axis(onehot, codes[:, :, None].astype(np.int64), 1.0, axis=2)
+    s3 = ctx.seqs_from_onehot(onehot)
+    assert np.array_equal(s3.download(), so.pack_codes(codes))
+    s3.free()
+
+
+def test_bad_symbol_rejected(ctx):
+    a = synth.random_ascii(4, 50, 1)
+    a[2, 17] = ord("N")
+    with pytest.raises(mb.MB200Error) as e:
+        ctx.seqs_from_ascii(a)
+    assert e.value.code == mb._lib.E_BAD_SEQUENCE
+
+
+def test_config1_planted_motif_scan(ctx):
+    """config 1: 1,000 x 100 bp with a planted gapped motif; K=3 PWMs (half sites and the full site)."""
+    a = synth.planted_gapped(1000, 100, 1)
+    sites_full = ["TGACGT" + sp + "ACGTCA" for sp in ("AAAAA", "CCCCC", "GGGGG", "TTTTT", "ACGTA")]
+    cms = [synth.count_matrix_from_sites(["TGACGT"] * 40), synth.count_matrix_from_sites(["ACGTCA"] * 40),
+           synth.count_matrix_from_sites(sites_full * 8)]
+    ms = synth.motifs_from_count_matrices(cms)
+    hits, counts = _check(ctx, a, ms)
+    assert counts[:, 0].min() > 0
+    thr = synth.stated_thresholds(ms, 0.7)
+    _check(ctx, a, ms, thr)
+    _check(ctx, a, ms, thr, strands=1)
+    _check(ctx, a, ms, thr, strands=2)
+    bg = synth.shuffle_rows(a, 11)
+    _check(ctx, bg, ms, thr)
+
+
+@pytest.mark.parametrize("K,Lb,N,seed", [(1, 100, 300, 3), (7, 64, 257, 4), (8, 200, 100, 5), (9, 33, 64, 6),
+                                         (40, 200, 500, 8), (130, 100, 200, 9)])
+def test_random_pwms(ctx, K, Lb, N, seed):
+    a = synth.random_ascii(N, Lb, seed)
+    ms = synth.motifs_from_count_matrices(synth.random_count_matrices(K, 8, min(40, Lb), seed))
+    _check(ctx, a, ms)                                   # reference scan semantics: score > 0
+    _check(ctx, a, ms, synth.stated_thresholds(ms, 0.5))
+
+
+def test_long_and_short_edges(ctx):
+    # motif as long as the sequence, longer than the sequence, length 1 and the maximum supported length
+    a = synth.random_ascii(50, 40, 21)
+    cms = synth.random_count_matrices(3, 40, 40, 22) + synth.random_count_matrices(2, 41, 64, 23) + \
+        synth.random_count_matrices(2, 1, 1, 24)
+    ms = synth.motifs_from_count_matrices(cms)
+    _check(ctx, a, ms)
+    b = synth.random_ascii(20, 300, 25)
+    ms2 = synth.motifs_from_count_matrices(synth.random_count_matrices(5, 60, 64, 26))
+    _check(ctx, b, ms2)
+    _check(ctx, b, ms2, np.full(5, -3.0, np.float16))    # negative threshold: still needs score > 0
+
+
+def test_nonfinite_and_negative_pwms(ctx):
+    a = synth.random_ascii(64, 80, 31)
+    ms = synth.motifs_from_count_matrices(synth.random_count_matrices(6, 8, 12, 32))
+    ms.pwms[0][:] = np.float16(-1.0)                     # all negative: no hit anywhere
+    ms.pwms[1][2, 3] = np.float16(-np.inf)               # -Inf entry: Inf*0 = NaN poisons every other base of that column
+    ms.pwms[2][1, 0] = np.float16(np.nan)
+    ms.pwms[3][0, 5] = np.float16(np.inf)
+    hits, counts = _check(ctx, a, ms)
+    assert counts[0, 0] == 0
+
+
+def test_palindrome_and_dense_hits(ctx):
+    # a palindromic site hits on both strands at the same start: unique starts < hits; union_ranges quirk exercised
+    a = np.frombuffer((b"ACGTACGT" * 13)[:100] * 16, np.uint8).reshape(16, 100).copy()
+    ms = synth.motifs_from_count_matrices([synth.count_matrix_from_sites(["ACGTACGT"] * 30)])
+    hits, counts = _check(ctx, a, ms)
+    assert counts[0, 1] < counts[0, 0]
+    assert counts[0, 2] <= counts[0, 3]
+
+
+def test_all_positive_pwm_every_position_hits(ctx):
+    a = synth.random_ascii(33, 130, 41)
+    ms = synth.motifs_from_count_matrices(synth.random_count_matrices(2, 8, 9, 42))
+    for p in ms.pwms:
+        p[:] = np.abs(p) + np.float16(0.01)
+    hits, counts = _check(ctx, a, ms)
+    assert counts[0, 0] == 2 * 33 * (130 - ms.lens[0] + 1)
+
+
+def test_single_long_sequence(ctx):
+    a = synth.random_ascii(1, 50000, 51)
+    ms = synth.motifs_from_count_matrices(synth.random_count_matrices(12, 8, 40, 52))
+    _check(ctx, a, ms, synth.stated_thresholds(ms, 0.6))
+
+
+def test_hits_overflow_reports_required_size(ctx):
+    a = synth.random_ascii(100, 100, 61)
+    ms = synth.motifs_from_count_matrices(synth.random_count_matrices(4, 8, 12, 62))
+    pw, lens = so.pack_pwms(ms.pwms)
+    seqs = ctx.seqs_from_ascii(a)
+    with pytest.raises(mb.MB200Error) as e:
+        ctx.scan(seqs, pw, lens, hits_cap=3)
+    assert e.value.code == mb._lib.E_HITS_OVERFLOW
+    seqs.free()
+
+
+def test_reference_entry_points(ctx):
+    """gpu_scan / scan_w_gpu! / filter / counts / Fisher through the host mirror == oracle-side restatement."""
+    from types import SimpleNamespace
+    from oracle import stats_oracle as st
+    a = synth.planted_gapped(600, 100, 2)
+    bg = synth.shuffle_rows(a, 3)
+    cms = [synth.count_matrix_from_sites(["TGACGT"] * 40), synth.count_matrix_from_sites(["TGACGTAAAAAACGTCA"] * 9 + ["TGACGTCCCCCACGTCA"] * 9)]
+    ms = synth.motifs_from_count_matrices(cms)
+    data = SimpleNamespace(N=600, L=100, seqs=ctx.seqs_from_ascii(a), seqs_bg=ctx.seqs_from_ascii(bg))
+    inference.scan_w_gpu_(ms, data)
+    inference.scan_w_gpu_(ms, data, bg=True)
+    codes, codes_bg = so.ascii_to_codes(a), so.ascii_to_codes(bg)
+    pw, lens = so.pack_pwms(ms.pwms)
+    oh, _ = so.scan(pw, lens, codes)
+    ohb, _ = so.scan(pw, lens, codes_bg)
+    # dict contents: forward hits ascending then rc hits ascending, 1-based
+    for m in range(2):
+        sel = oh[oh["motif"] == m]
+        for n in np.unique(sel["seq"]):
+            r = sel[sel["seq"] == n]
+            assert np.array_equal(ms.positions[m][int(n) + 1], r["pos"].astype(np.int64) + 1)
+            assert np.array_equal(ms.scores[m][int(n) + 1].view(np.uint16), r["score_f16"])
+            assert np.array_equal(ms.use_comp[m][int(n) + 1], r["comp"].astype(bool))
+        assert len(ms.positions[m]) == len(np.unique(sel["seq"]))
+    bgfreq = np.array([0.25, 0.25, 0.25, 0.25], np.float32)
+    inference.filter_positions_scores_usecomp_(ms, data, bgfreq)
+    for m in range(2):
+        segs0 = [(r.start - 1, r.stop - 1) for r in ms.effective_segments[m]]
+        t = st.get_best_thresh(oh[oh["motif"] == m]["score_f16"].view(np.float16), ohb[ohb["motif"] == m]["score_f16"].view(np.float16),
+                               segs0, ms.pwms[m], 600 * 100, bgfreq)
+        assert np.float16(t) == ms.score_thresh[m]
+    # fused counts with the derived thresholds == dict-based counts of the mirror == oracle
+    c = inference.scan_counts(ms, data, thresh=ms.score_thresh)
+    cb = inference.scan_counts(ms, data, bg=True, thresh=ms.score_thresh)
+    _, oc = so.scan(pw, lens, codes, ms.score_thresh, want_hits=False)
+    _, ocb = so.scan(pw, lens, codes_bg, ms.score_thresh, want_hits=False)
+    assert np.array_equal(c, oc) and np.array_equal(cb, ocb)
+    uq, uqb = inference.get_uniq_counts(ms)
+    assert np.array_equal(uq, c[:, 1]) and np.array_equal(uqb, cb[:, 1])
+    p = inference.get_fisher_p_values(ms, data)
+    assert np.allclose(p, st.fisher_pvec(oc[:, 2], ocb[:, 2], 600, 100), rtol=1e-9, atol=0)
