@@ -252,13 +252,10 @@ def get_pvalue(pwm):
 # ---------------------------------------------------------------------------------------------
 # Fisher exact test, right tail (HypothesisTests.FisherExactTest(a, c, b, d), tail=:right)
 # ---------------------------------------------------------------------------------------------
-def _log_choose(n, k):
-    return math.lgamma(n + 1) - math.lgamma(k + 1) - math.lgamma(n - k + 1)
-
-
 def fisher_right(a, c, b, d):
-    """P[X >= a], X ~ Hypergeometric(a+c successes, b+d failures, a+b draws) — summed in log space from the
-    mode outward in Float64 (the reference reaches Rmath's phyper; agreement is ~1e-12 relative)."""
+    """P[X >= a], X ~ Hypergeometric(a+c successes, b+d failures, a+b draws).  Float64: probability ratios
+    pmf(x+1)/pmf(x) accumulated in log space around the mode and normalised by their own sum (no lgamma of large
+    arguments), ~1e-12 relative to Rmath's phyper that the reference reaches through HypothesisTests."""
     a, c, b, d = int(a), int(c), int(b), int(d)
     succ, fail, draws = a + c, b + d, a + b
     hi = min(draws, succ)
@@ -267,20 +264,25 @@ def fisher_right(a, c, b, d):
         return 1.0
     if a > hi:
         return 0.0
-    denom = _log_choose(succ + fail, draws)
-    # upper tail directly; when it is the larger side use 1 - lower tail for accuracy
-    def logpmf(x):
-        return _log_choose(succ, x) + _log_choose(fail, draws - x) - denom
-    mean = draws * succ / (succ + fail)
-    if a > mean:
-        xs = range(a, hi + 1)
-        terms = [logpmf(x) for x in xs]
-        mx = max(terms)
-        return min(1.0, math.exp(mx) * math.fsum(math.exp(t - mx) for t in terms))
-    xs = range(lo, a)
-    terms = [logpmf(x) for x in xs]
-    mx = max(terms)
-    return max(0.0, 1.0 - math.exp(mx) * math.fsum(math.exp(t - mx) for t in terms))
+    tot = succ + fail
+    mean = draws * succ / tot
+    sigma = math.sqrt(max(draws * (succ / tot) * (fail / tot), 1.0))
+    w = int(60 * sigma) + 100
+    x_lo = max(lo, int(mean) - w)
+    x_hi = min(hi, max(int(mean), a) + w)
+    if a < x_lo:
+        return 1.0
+    x = np.arange(x_lo, x_hi, dtype=np.float64)               # ratios pmf(x+1)/pmf(x)
+    logratio = np.log((succ - x) * (draws - x)) - np.log((x + 1.0) * (fail - draws + x + 1.0))
+    logr = np.concatenate([[0.0], np.cumsum(logratio)])
+    logr -= logr.max()
+    r = np.exp(logr)
+    total = r.sum()
+    k = a - x_lo
+    upper = r[k:].sum()
+    if upper <= 0.5 * total:
+        return float(upper / total)
+    return float(1.0 - r[:k].sum() / total)
 
 
 def fisher_pvec(activate_counts, activate_counts_bg, data, test=False):
