@@ -105,6 +105,58 @@ int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs,
                    const uint16_t* thresh_f16, uint32_t flags,
                    mb200_hit* hits, int64_t hits_cap, int64_t* n_hits, int64_t* counts);
 
+
+/* ---- unrolled convolutional-sparse-coding network: replaces the GPU work inside
+ *      forward_pass_return_loss (model.jl:375-395) + gradient(ps) + Flux.Optimise.update!
+ *      (train.jl:42-46) and code_retrieval (inference/_1_code_retrieval.jl:33-56).            */
+typedef struct {                 /* Hyperparam, model.jl:1-14 (same defaults expected)         */
+    int32_t filter_len, M, h, K, q, batch_size, num_pass_xyz, num_pass_df;
+    float   magnifying_factor, gamma;
+} mb200_hparams;
+
+/* n_groups independent batches of batch_size sequences are processed per call (1 = the reference's
+ * step).  forward_only != 0 builds only ADMM_XYZ (enough for mb200_csc_codes, far less memory).   */
+int32_t mb200_csc_create(mb200_ctx* ctx, const mb200_hparams* hp, int64_t Lb, int32_t n_groups,
+                         int32_t forward_only, mb200_csc** out);
+int32_t mb200_csc_destroy(mb200_ctx* ctx, mb200_csc* csc);
+int32_t mb200_csc_n_params(const mb200_csc* csc, int64_t* n_trainable, int64_t* n_total);
+/* flat Float32 parameter vector in Flux.params(cdl) order (model.jl:67-137, arrays only):
+ * lambda_sparsity[6] kappa_sparsity[3] lambda_stepsize[6] omega_stepsize[6] kappa_stepsize[3]
+ * D[32*M] (Julia (32,1,M) memory order) F[h*2M*K] (Julia (h,2M,1,K) memory order) penalty_xyz[6] mu[3]
+ * = n_trainable, followed by the three non-trainable warm-up scalars lambda_sparsity_warmup,
+ * lambda_stepsize_warmup, omega_stepsize_warmup (model.jl:68,72-73) = n_total.                  */
+int32_t mb200_csc_set_params(mb200_ctx* ctx, mb200_csc* csc, const float* p, int64_t n_total);
+int32_t mb200_csc_get_params(mb200_ctx* ctx, mb200_csc* csc, float* p, int64_t n_total);
+int32_t mb200_csc_reset_optimizer(mb200_ctx* ctx, mb200_csc* csc);
+/* device addresses of the parameter and gradient vectors (n_total floats each), so that the host
+ * framework can all-reduce gradients in place with one NCCL call per step.                      */
+int32_t mb200_csc_device_ptrs(const mb200_csc* csc, void** params_dev, void** grads_dev);
+/* loss and gradient of n_groups batches: seq_idx[n_groups*batch_size] indexes `seqs`.
+ * loss_out: n_groups*3 floats {loss, reconstruction term, syntax term}; grads: n_trainable floats,
+ * mean over groups (NULL to leave them on the device).                                          */
+int32_t mb200_csc_loss_grad(mb200_ctx* ctx, mb200_csc* csc, const mb200_seqs* seqs,
+                            const int64_t* seq_idx, float* loss_out, float* grads);
+/* same computation, asynchronous, results stay on the device */
+int32_t mb200_csc_step_begin(mb200_ctx* ctx, mb200_csc* csc, const mb200_seqs* seqs, const int64_t* seq_idx);
+/* AdaBelief update (Flux.Optimise.AdaBelief defaults eta=1e-3, beta=(0.9,0.999), eps=1e-8) with the
+ * gradients on the device; returns the mean loss of that step and l1 = sum|prep_syntax_filters(F)|
+ * (the early-stop statistic of train.jl:47-52).                                                  */
+int32_t mb200_csc_adabelief_step(mb200_ctx* ctx, mb200_csc* csc, float eta, float beta1, float beta2,
+                                 float eps, float* loss_out, float* l1_F_out);
+/* named intermediates of the last forward pass ("z","y","x","zy","D","F","D0","F0","loss") — tests */
+int32_t mb200_csc_get_buffer(mb200_ctx* ctx, mb200_csc* csc, const char* name, float* out, int64_t n);
+
+typedef struct {                 /* stored_code_component_t, inference/_0_const.jl:3-4 (0-based) */
+    uint16_t position, fil;
+    uint32_t seq;
+    uint16_t mag_f16, _pad;
+} mb200_code;                    /* 12 bytes */
+/* ADMM_XYZ forward over sequences first_seq .. first_seq+n_seqs-1 (n_seqs a multiple of batch_size, groups of
+ * batch_size consecutive sequences share the median mask like the reference's DataLoader(shuffle=false)).
+ * Records ordered by seq, fil, position.                                                        */
+int32_t mb200_csc_codes(mb200_ctx* ctx, mb200_csc* csc, const mb200_seqs* seqs, int64_t first_seq,
+                        int64_t n_seqs, mb200_code* out, int64_t cap, int64_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,17 @@ HIT_DTYPE = np.dtype([("seq", "<u4"), ("pos", "<u4"), ("motif", "<u2"), ("score_
                       ("comp", "u1"), ("_pad", "u1", (3,))])
 assert HIT_DTYPE.itemsize == 16
 
+CODE_DTYPE = np.dtype([("position", "<u2"), ("fil", "<u2"), ("seq", "<u4"), ("mag_f16", "<u2"), ("_pad", "<u2")])
+assert CODE_DTYPE.itemsize == 12
+
+
+class HParams(C.Structure):
+    """mb200_hparams = Hyperparam (model.jl:1-14)."""
+    _fields_ = [("filter_len", C.c_int32), ("M", C.c_int32), ("h", C.c_int32), ("K", C.c_int32), ("q", C.c_int32),
+                ("batch_size", C.c_int32), ("num_pass_xyz", C.c_int32), ("num_pass_df", C.c_int32),
+                ("magnifying_factor", C.c_float), ("gamma", C.c_float)]
+
+
 _lib = None
 
 
@@ -58,6 +69,18 @@ def load():
         "mb200_seqs_shape": (i32, [p, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
         "mb200_seqs_download": (i32, [p, p, p, i64]),
         "mb200_scan": (i32, [p, p, p, p, i32, i32, p, C.c_uint32, p, i64, C.POINTER(i64), p]),
+        "mb200_csc_create": (i32, [p, C.POINTER(HParams), i64, i32, i32, C.POINTER(p)]),
+        "mb200_csc_destroy": (i32, [p, p]),
+        "mb200_csc_n_params": (i32, [p, C.POINTER(i64), C.POINTER(i64)]),
+        "mb200_csc_set_params": (i32, [p, p, p, i64]),
+        "mb200_csc_get_params": (i32, [p, p, p, i64]),
+        "mb200_csc_reset_optimizer": (i32, [p, p]),
+        "mb200_csc_device_ptrs": (i32, [p, C.POINTER(p), C.POINTER(p)]),
+        "mb200_csc_loss_grad": (i32, [p, p, p, p, p, p]),
+        "mb200_csc_step_begin": (i32, [p, p, p, p]),
+        "mb200_csc_adabelief_step": (i32, [p, p, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+        "mb200_csc_get_buffer": (i32, [p, p, C.c_char_p, p, i64]),
+        "mb200_csc_codes": (i32, [p, p, p, i64, i64, p, i64, C.POINTER(i64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -202,3 +225,84 @@ class Sequences:
             self.free()
         except Exception:
             pass
+
+
+class CscModel:
+    """mb200_csc: the unrolled CSC network for one (hyper-parameters, Lb, n_groups) shape on one device."""
+
+    def __init__(self, ctx: Context, hp, Lb: int, n_groups: int = 1, forward_only: bool = False):
+        self.ctx = ctx
+        self.hp = hp
+        self.Lb, self.n_groups, self.forward_only = int(Lb), int(n_groups), bool(forward_only)
+        chp = HParams(hp.filter_len, hp.M, hp.h, hp.K, hp.q, hp.batch_size, hp.num_pass_xyz, hp.num_pass_df,
+                      float(hp.magnifying_factor), float(hp.gamma))
+        h = C.c_void_p()
+        ctx._check(ctx._lib.mb200_csc_create(ctx._h, C.byref(chp), self.Lb, self.n_groups, int(self.forward_only), C.byref(h)))
+        self._h = h
+        nt, na = C.c_int64(), C.c_int64()
+        ctx._check(ctx._lib.mb200_csc_n_params(self._h, C.byref(nt), C.byref(na)))
+        self.n_trainable, self.n_total = nt.value, na.value
+        self.batch = hp.batch_size * self.n_groups
+
+    def free(self):
+        if getattr(self, "_h", None) and self.ctx._h:
+            self.ctx._lib.mb200_csc_destroy(self.ctx._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def set_params(self, flat):
+        a = np.ascontiguousarray(flat, np.float32)
+        self.ctx._check(self.ctx._lib.mb200_csc_set_params(self.ctx._h, self._h, _ptr(a), a.size))
+
+    def get_params(self):
+        a = np.zeros(self.n_total, np.float32)
+        self.ctx._check(self.ctx._lib.mb200_csc_get_params(self.ctx._h, self._h, _ptr(a), a.size))
+        return a
+
+    def reset_optimizer(self):
+        self.ctx._check(self.ctx._lib.mb200_csc_reset_optimizer(self.ctx._h, self._h))
+
+    def device_ptrs(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        self.ctx._check(self.ctx._lib.mb200_csc_device_ptrs(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def loss_grad(self, seqs: "Sequences", seq_idx, want_grads=True):
+        idx = np.ascontiguousarray(seq_idx, np.int64)
+        if idx.size != self.batch:
+            raise ValueError(f"need {self.batch} sequence indices")
+        loss = np.zeros((self.n_groups, 3), np.float32)
+        g = np.zeros(self.n_trainable, np.float32) if want_grads else None
+        self.ctx._check(self.ctx._lib.mb200_csc_loss_grad(self.ctx._h, self._h, seqs._h, _ptr(idx), _ptr(loss), _ptr(g)))
+        return loss, g
+
+    def step_begin(self, seqs: "Sequences", seq_idx):
+        idx = np.ascontiguousarray(seq_idx, np.int64)
+        if idx.size != self.batch:
+            raise ValueError(f"need {self.batch} sequence indices")
+        self.ctx._check(self.ctx._lib.mb200_csc_step_begin(self.ctx._h, self._h, seqs._h, _ptr(idx)))
+
+    def adabelief_step(self, eta=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+        loss, l1 = C.c_float(), C.c_float()
+        self.ctx._check(self.ctx._lib.mb200_csc_adabelief_step(self.ctx._h, self._h, eta, beta1, beta2, eps, C.byref(loss), C.byref(l1)))
+        return loss.value, l1.value
+
+    def get_buffer(self, name: str, n: int):
+        a = np.zeros(int(n), np.float32)
+        self.ctx._check(self.ctx._lib.mb200_csc_get_buffer(self.ctx._h, self._h, name.encode(), _ptr(a), a.size))
+        return a
+
+    def codes(self, seqs: "Sequences", first_seq=0, n_seqs=None):
+        B = self.hp.batch_size
+        if n_seqs is None:
+            n_seqs = (seqs.N - first_seq) - (seqs.N - first_seq) % B          # DataLoader(partial=false)
+        cap = max(1024, 64 * int(n_seqs))
+        out = np.zeros(cap, CODE_DTYPE)
+        n = C.c_int64()
+        self.ctx._check(self.ctx._lib.mb200_csc_codes(self.ctx._h, self._h, seqs._h, int(first_seq), int(n_seqs), _ptr(out), cap, C.byref(n)))
+        return out[: n.value]

@@ -1,0 +1,609 @@
+// Unrolled convolutional-sparse-coding network: forward, hand-derived reverse pass, AdaBelief, code retrieval.
+//
+// Reference being replaced (paths under the reference's src/):
+//   model.jl:330-395  ADMM_XYZ / ADMM_DF / forward_pass_return_loss   (forward)
+//   train.jl:42-46    gradient(ps) do ... end ; Flux.Optimise.update!  (reverse pass + AdaBelief)
+//   train.jl:47-52    l1 early-stop statistic
+//   inference/_1_code_retrieval.jl:33-56  code_retrieval
+//
+// The forward pass is recorded once as a tape of ~100 primitive ops over statically allocated buffers; the reverse
+// pass replays the tape backwards with each op's adjoint (csc_kernels.cuh).  Shapes are static, selections
+// (batch median, per-sequence top-q) are computed on the device, so a whole step is a fixed kernel sequence with
+// no host synchronisation inside — it is captured into a CUDA graph and replayed per step.
+#include "common.cuh"
+#include "csc_kernels.cuh"
+#include <algorithm>
+#include <cstring>
+#include <functional>
+#include <map>
+
+namespace {
+
+struct Buf { size_t off = 0; size_t n = 0; };            // offsets in floats into the data / grad arenas
+
+struct Op {
+    std::function<void(cudaStream_t)> fwd, bwd;
+    const char* name;
+};
+
+}  // namespace
+
+struct mb200_csc {
+    mb200_ctx* ctx = nullptr;
+    CscDims d{};
+    mb200_hparams hp{};
+    int64_t n_train = 0, n_total = 0, n_scalar_train = 0;
+    // parameter storage (raw, Flux.params order + 3 warm-up scalars), gradients, AdaBelief state
+    float *p_raw = nullptr, *g_raw = nullptr, *mt = nullptr, *st = nullptr;
+    int64_t step_count = 0;
+    // arenas
+    float *data = nullptr, *grad = nullptr;
+    size_t arena = 0;
+    uint8_t* bits = nullptr; size_t bits_n = 0;          // top-q bitmasks
+    uint8_t* bases = nullptr;
+    int64_t* idx_dev = nullptr;
+    int64_t* idx_pinned = nullptr;
+    float* host_out = nullptr;                           // pinned: loss[G*3], l1
+    std::vector<Op> tape;
+    std::map<std::string, Buf> named;
+    // raw-vector offsets
+    int64_t off_lam, off_kaps, off_eta, off_om, off_kap, off_D, off_F, off_rho, off_mu, off_warm;
+    // effective-scalar slots (index into sc buffer)
+    Buf sc; Buf Deff, Feff, Fnrm0, loss;
+    int i_lam0, i_kaps0, i_eta0, i_om0, i_kap0, i_rho0, i_mu0, i_lam_w, i_eta_w, i_om_w;
+    bool xyz_only = false;
+    cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr; bool graph_ok = false;
+    const uint32_t* graph_words = nullptr; int64_t graph_rowwords = 0;
+};
+
+namespace {
+
+struct Builder {
+    mb200_csc* s;
+    size_t cursor = 0;
+    size_t bit_cursor = 0;
+    Buf alloc(size_t n, const char* name = nullptr) {
+        Buf b; b.off = cursor; b.n = n; cursor += (n + 63) & ~(size_t)63;
+        if (name) s->named[name] = b;
+        return b;
+    }
+};
+
+inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+#define D_(b) (s->data + (b).off)
+#define G_(b) (s->grad + (b).off)
+
+// Records the whole network.  xyz_only = forward ADMM_XYZ without loss (code retrieval).
+static void build_tape(mb200_csc* s, bool xyz_only) {
+    const CscDims d = s->d;
+    Builder B{s};
+    const int64_t nZ = (int64_t)d.NS * d.c * d.M, nZY = (int64_t)d.NS * d.c * d.M2, nX = (int64_t)d.NS * d.l * d.K, nS = (int64_t)d.NS * d.L4;
+    const int64_t nD = (int64_t)d.f_len * d.M, nF = (int64_t)d.h * d.M2 * d.K;
+    const int n_sc = 3 * d.npx + d.npx + 3 * d.npd + 3;       // lam, eta, om, rho per xyz pass; kaps, kap, mu per df pass; 3 warm
+    s->sc = B.alloc(n_sc);
+    // scalar slot order = raw order of the scalar arrays, then warm-ups: lam[npx] kaps[npd] eta[npx] om[npx] kap[npd] rho[npx] mu[npd] | lam_w eta_w om_w
+    s->i_lam0 = 0; s->i_kaps0 = d.npx; s->i_eta0 = s->i_kaps0 + d.npd; s->i_om0 = s->i_eta0 + d.npx; s->i_kap0 = s->i_om0 + d.npx;
+    s->i_rho0 = s->i_kap0 + d.npd; s->i_mu0 = s->i_rho0 + d.npx; s->i_lam_w = s->i_mu0 + d.npd; s->i_eta_w = s->i_lam_w + 1; s->i_om_w = s->i_eta_w + 1;
+    s->Deff = B.alloc(nD, "D0"); s->Feff = B.alloc(nF, "F0"); s->Fnrm0 = B.alloc(d.K);
+    s->loss = B.alloc((size_t)d.G * 3 + 4, "loss");
+    mb200_csc* S = s;
+    auto& T = s->tape;
+    T.clear();
+
+    // ---- prep (model.jl:153-169) -----------------------------------------------------------------
+    {
+        const Buf sc = s->sc, De = s->Deff, Fe = s->Feff, Fn0 = s->Fnrm0;
+        T.push_back({[=](cudaStream_t q) {
+                         // scalar arrays are contiguous in the raw vector except D,F in the middle: copy slot by slot
+                         const int npx = d.npx, npd = d.npd;
+                         k_prep_scalars<<<1, 64, 0, q>>>(S->p_raw + S->off_lam, S->data + sc.off + S->i_lam0, npx);
+                         k_prep_scalars<<<1, 64, 0, q>>>(S->p_raw + S->off_kaps, S->data + sc.off + S->i_kaps0, npd);
+                         k_prep_scalars<<<1, 64, 0, q>>>(S->p_raw + S->off_eta, S->data + sc.off + S->i_eta0, npx);
+                         k_prep_scalars<<<1, 64, 0, q>>>(S->p_raw + S->off_om, S->data + sc.off + S->i_om0, npx);
+                         k_prep_scalars<<<1, 64, 0, q>>>(S->p_raw + S->off_kap, S->data + sc.off + S->i_kap0, npd);
+                         k_prep_scalars<<<1, 64, 0, q>>>(S->p_raw + S->off_rho, S->data + sc.off + S->i_rho0, npx);
+                         k_prep_scalars<<<1, 64, 0, q>>>(S->p_raw + S->off_mu, S->data + sc.off + S->i_mu0, npd);
+                         k_prep_scalars<<<1, 64, 0, q>>>(S->p_raw + S->off_warm, S->data + sc.off + S->i_lam_w, 3);
+                         k_prep_D<<<nblk(d.fl * d.M, 128), 128, 0, q>>>(S->p_raw + S->off_D, S->data + De.off, d);
+                         k_prep_F<<<d.K, 256, 0, q>>>(S->p_raw + S->off_F, S->data + Fe.off, S->data + Fn0.off, d);
+                     },
+                     [=](cudaStream_t q) {
+                         const int npx = d.npx, npd = d.npd;
+                         k_prep_scalars_bwd<<<1, 64, 0, q>>>(S->p_raw + S->off_lam, S->grad + sc.off + S->i_lam0, S->g_raw + S->off_lam, npx);
+                         k_prep_scalars_bwd<<<1, 64, 0, q>>>(S->p_raw + S->off_kaps, S->grad + sc.off + S->i_kaps0, S->g_raw + S->off_kaps, npd);
+                         k_prep_scalars_bwd<<<1, 64, 0, q>>>(S->p_raw + S->off_eta, S->grad + sc.off + S->i_eta0, S->g_raw + S->off_eta, npx);
+                         k_prep_scalars_bwd<<<1, 64, 0, q>>>(S->p_raw + S->off_om, S->grad + sc.off + S->i_om0, S->g_raw + S->off_om, npx);
+                         k_prep_scalars_bwd<<<1, 64, 0, q>>>(S->p_raw + S->off_kap, S->grad + sc.off + S->i_kap0, S->g_raw + S->off_kap, npd);
+                         k_prep_scalars_bwd<<<1, 64, 0, q>>>(S->p_raw + S->off_rho, S->grad + sc.off + S->i_rho0, S->g_raw + S->off_rho, npx);
+                         k_prep_scalars_bwd<<<1, 64, 0, q>>>(S->p_raw + S->off_mu, S->grad + sc.off + S->i_mu0, S->g_raw + S->off_mu, npd);
+                         k_prep_D_bwd<<<nblk(d.fl * d.M, 128), 128, 0, q>>>(S->p_raw + S->off_D, S->data + De.off, S->grad + De.off, S->g_raw + S->off_D, d);
+                         k_prep_F_bwd<<<d.K, 256, 0, q>>>(S->p_raw + S->off_F, S->data + Fe.off, S->data + Fn0.off, S->grad + Fe.off, S->g_raw + S->off_F, d);
+                     },
+                     "prep"});
+    }
+    const Buf sc = s->sc, De = s->Deff, Fe = s->Feff;
+    float* const SC = nullptr; (void)SC;
+#define SCP (S->data + sc.off)
+#define DSCP (S->grad + sc.off)
+
+    // helpers that append one op each -------------------------------------------------------------
+    auto op_recon = [&](Buf ca, Buf cb, Buf filt, int64_t gs, Buf out, const char* nm) {
+        T.push_back({[=](cudaStream_t q) { k_recon<<<nblk(nS * 32, 256), 256, 0, q>>>(S->data + ca.off, S->data + cb.off, S->data + filt.off, gs, S->data + out.off, 0, d); },
+                     [=](cudaStream_t q) {
+                         // d ca, d cb: corr_sig form with signal = d out ; d filt: dgrad form with signal = d out
+                         k_corr_sig<<<nblk(nZ, 256), 256, 0, q>>>(S->grad + out.off, S->bases, 0.f, S->data + filt.off, gs, S->grad + ca.off, S->grad + cb.off, 1, d);
+                         k_dgrad<<<dim3(nblk(nD, 128), d.G), 128, 0, q>>>(S->data + ca.off, S->data + cb.off, S->grad + out.off, S->bases, 0.f, S->grad + filt.off, gs, 1, d);
+                     },
+                     nm});
+    };
+    auto op_corr_sig = [&](Buf sig, float sgn, Buf filt, int64_t gs, Buf oa, Buf ob, const char* nm) {
+        T.push_back({[=](cudaStream_t q) { k_corr_sig<<<nblk(nZ, 256), 256, 0, q>>>(S->data + sig.off, S->bases, sgn, S->data + filt.off, gs, S->data + oa.off, S->data + ob.off, 0, d); },
+                     [=](cudaStream_t q) {
+                         k_recon<<<nblk(nS * 32, 256), 256, 0, q>>>(S->grad + oa.off, S->grad + ob.off, S->data + filt.off, gs, S->grad + sig.off, 1, d);
+                         k_dgrad<<<dim3(nblk(nD, 128), d.G), 128, 0, q>>>(S->grad + oa.off, S->grad + ob.off, S->data + sig.off, S->bases, sgn, S->grad + filt.off, gs, 1, d);
+                     },
+                     nm});
+    };
+    auto op_dgrad = [&](Buf ca, Buf cb, Buf sig, float sgn, Buf outG, const char* nm) {      // per-group output
+        T.push_back({[=](cudaStream_t q) { k_dgrad<<<dim3(nblk(nD, 128), d.G), 128, 0, q>>>(S->data + ca.off, S->data + cb.off, S->data + sig.off, S->bases, sgn, S->data + outG.off, nD, 0, d); },
+                     [=](cudaStream_t q) {
+                         // d ca, d cb: corr_sig with filter = dG (per group) ; d sig: recon with filter = dG
+                         k_corr_sig<<<nblk(nZ, 256), 256, 0, q>>>(S->data + sig.off, S->bases, sgn, S->grad + outG.off, nD, S->grad + ca.off, S->grad + cb.off, 1, d);
+                         k_recon<<<nblk(nS * 32, 256), 256, 0, q>>>(S->data + ca.off, S->data + cb.off, S->grad + outG.off, nD, S->grad + sig.off, 1, d);
+                     },
+                     nm});
+    };
+    auto op_corr2d = [&](Buf A, Buf filt, int64_t gs, Buf out, const char* nm) {
+        T.push_back({[=](cudaStream_t q) { k_corr2d<<<nblk(nX, 128), 128, 0, q>>>(S->data + A.off, S->data + filt.off, gs, S->data + out.off, 0, d); },
+                     [=](cudaStream_t q) {
+                         k_tconv<<<nblk(nZY, 128), 128, 0, q>>>(S->grad + out.off, S->data + filt.off, gs, S->grad + A.off, 1, d);
+                         k_fgrad<<<dim3(nblk(nF, 128), d.G), 128, 0, q>>>(S->data + A.off, S->grad + out.off, S->grad + filt.off, gs, 1, d);
+                     },
+                     nm});
+    };
+    auto op_tconv = [&](Buf x, Buf filt, int64_t gs, Buf out, const char* nm) {
+        T.push_back({[=](cudaStream_t q) { k_tconv<<<nblk(nZY, 128), 128, 0, q>>>(S->data + x.off, S->data + filt.off, gs, S->data + out.off, 0, d); },
+                     [=](cudaStream_t q) {
+                         k_corr2d<<<nblk(nX, 128), 128, 0, q>>>(S->grad + out.off, S->data + filt.off, gs, S->grad + x.off, 1, d);
+                         k_fgrad<<<dim3(nblk(nF, 128), d.G), 128, 0, q>>>(S->grad + out.off, S->data + x.off, S->grad + filt.off, gs, 1, d);
+                     },
+                     nm});
+    };
+    auto op_fgrad = [&](Buf A, Buf x, Buf outF, const char* nm) {                               // per-group output
+        T.push_back({[=](cudaStream_t q) { k_fgrad<<<dim3(nblk(nF, 128), d.G), 128, 0, q>>>(S->data + A.off, S->data + x.off, S->data + outF.off, nF, 0, d); },
+                     [=](cudaStream_t q) {
+                         k_tconv<<<nblk(nZY, 128), 128, 0, q>>>(S->data + x.off, S->grad + outF.off, nF, S->grad + A.off, 1, d);
+                         k_corr2d<<<nblk(nX, 128), 128, 0, q>>>(S->data + A.off, S->grad + outF.off, nF, S->grad + x.off, 1, d);
+                     },
+                     nm});
+    };
+    auto op_mask_scale = [&](Buf z, Buf y, Buf zy, const char* nm) {
+        Buf med = B.alloc(d.G);
+        T.push_back({[=](cudaStream_t q) { k_mask_scale<<<d.G, 1024, 0, q>>>(S->data + z.off, S->data + y.off, S->data + zy.off, S->data + med.off, d); },
+                     [=](cudaStream_t q) { k_mask_scale_bwd<<<nblk(nZY, 256), 256, 0, q>>>(S->data + z.off, S->data + y.off, S->data + med.off, S->grad + zy.off, S->grad + z.off, S->grad + y.off, d); },
+                     nm});
+    };
+    auto op_topq = [&](const Buf* xprev, Buf g, int i_om, float coef, int om_train, Buf xout, const char* nm) {
+        const size_t bo = B.bit_cursor; B.bit_cursor += (size_t)nX;
+        Buf vq = B.alloc(d.NS);
+        const bool hp_ = xprev != nullptr; const Buf xp = hp_ ? *xprev : Buf{};
+        T.push_back({[=](cudaStream_t q) { k_topq<<<d.NS, 256, 0, q>>>(hp_ ? S->data + xp.off : nullptr, S->data + g.off, SCP, i_om, coef, S->data + xout.off, S->bits + bo, S->data + vq.off, d); },
+                     [=](cudaStream_t q) { k_topq_bwd<<<nblk(nX, 256), 256, 0, q>>>(S->bits + bo, S->data + g.off, SCP, i_om, coef, S->grad + xout.off, hp_ ? S->grad + xp.off : nullptr, S->grad + g.off, DSCP, om_train, d); },
+                     nm});
+    };
+
+    // ---- warm-up (model.jl:224-232) --------------------------------------------------------------
+    Buf z = B.alloc(nZ), y = B.alloc(nZ);
+    T.push_back({[=](cudaStream_t q) { k_warm_zy<<<nblk(nZ, 256), 256, 0, q>>>(S->bases, S->data + De.off, SCP, S->i_eta_w, S->i_lam_w, S->data + z.off, S->data + y.off, d); },
+                 [=](cudaStream_t q) { k_warm_zy_bwd<<<nblk(nZ, 256), 256, 0, q>>>(S->bases, SCP, S->i_eta_w, S->data + z.off, S->data + y.off, S->grad + z.off, S->grad + y.off, S->grad + De.off, d); },
+                 "warm_zy"});
+    Buf zy = B.alloc(nZY);
+    op_mask_scale(z, y, zy, "warm_mask");
+    Buf g0 = B.alloc(nX), x = B.alloc(nX);
+    op_corr2d(zy, Fe, 0, g0, "warm_corr2d");
+    op_topq(nullptr, g0, s->i_om_w, 1.f, 0, x, "warm_topq");
+    Buf fx = B.alloc(nZY);
+    op_tconv(x, Fe, 0, fx, "warm_tconv");
+    Buf al{}, be{};
+    bool have_dual = false;
+
+    // ---- ADMM_XYZ passes (model.jl:256-268, 347-355) ---------------------------------------------
+    for (int n = 0; n < d.npx; ++n) {
+        const int i_eta = s->i_eta0 + n, i_lam = s->i_lam0 + n, i_rho = s->i_rho0 + n, i_om = s->i_om0 + n;
+        Buf rec = B.alloc(nS), gz = B.alloc(nZ), gy = B.alloc(nZ), zn = B.alloc(nZ), yn = B.alloc(nZ);
+        op_recon(z, y, De, 0, rec, "recon");
+        op_corr_sig(rec, -1.f, De, 0, gz, gy, "corr_sig");
+        if (!have_dual) { al = B.alloc(nZ); be = B.alloc(nZ); }      // zero duals (model.jl:338): arenas are zero-filled, never written
+        {
+            const Buf zc = z, yc = y, fxc = fx, alc = al, bec = be;
+            T.push_back({[=](cudaStream_t q) { k_zy_update<<<nblk(nZ, 256), 256, 0, q>>>(S->data + zc.off, S->data + yc.off, S->data + gz.off, S->data + gy.off, S->data + fxc.off, S->data + alc.off, S->data + bec.off, SCP, i_eta, i_lam, i_rho, S->data + zn.off, S->data + yn.off, d); },
+                         [=](cudaStream_t q) { k_zy_update_bwd<<<nblk(nZ, 256), 256, 0, q>>>(S->data + zc.off, S->data + yc.off, S->data + gz.off, S->data + gy.off, S->data + fxc.off, S->data + alc.off, S->data + bec.off, SCP, i_eta, i_lam, i_rho, S->data + zn.off, S->data + yn.off, S->grad + zn.off, S->grad + yn.off, S->grad + zc.off, S->grad + yc.off, S->grad + gz.off, S->grad + gy.off, S->grad + fxc.off, S->grad + alc.off, S->grad + bec.off, DSCP, d); },
+                         "zy_update"});
+        }
+        z = zn; y = yn;
+        Buf zy2 = B.alloc(nZY), dd = B.alloc(nZY), g = B.alloc(nX), xn = B.alloc(nX), fxn = B.alloc(nZY);
+        op_mask_scale(z, y, zy2, "mask_scale");
+        {
+            const Buf fxc = fx, alc = al, bec = be;
+            T.push_back({[=](cudaStream_t q) { k_d_build<<<nblk(nZY, 256), 256, 0, q>>>(S->data + fxc.off, S->data + zy2.off, S->data + alc.off, S->data + bec.off, S->data + dd.off, d); },
+                         [=](cudaStream_t q) { k_d_build_bwd<<<nblk(nZY, 256), 256, 0, q>>>(S->grad + dd.off, S->grad + fxc.off, S->grad + zy2.off, S->grad + alc.off, S->grad + bec.off, d); },
+                         "d_build"});
+        }
+        op_corr2d(dd, Fe, 0, g, "corr2d");
+        op_topq(&x, g, i_om, -1.f, 1, xn, "topq");
+        x = xn;
+        op_tconv(x, Fe, 0, fxn, "tconv");
+        fx = fxn;
+        if (n + 1 < d.npx) {      // the duals after the last pass are never read (model.jl:356 returns Z, Y, X)
+            Buf an = B.alloc(nZ), bn = B.alloc(nZ);
+            const Buf alc = al, bec = be, fxc = fx, zc = z, yc = y;
+            T.push_back({[=](cudaStream_t q) { k_dual<<<nblk(nZ, 256), 256, 0, q>>>(S->data + alc.off, S->data + bec.off, S->data + fxc.off, S->data + zc.off, S->data + yc.off, S->data + an.off, S->data + bn.off, d); },
+                         [=](cudaStream_t q) { k_dual_bwd<<<nblk(nZ, 256), 256, 0, q>>>(S->grad + an.off, S->grad + bn.off, S->grad + alc.off, S->grad + bec.off, S->grad + fxc.off, S->grad + zc.off, S->grad + yc.off, d); },
+                         "dual"});
+            al = an; be = bn;
+        }
+        have_dual = true;
+    }
+    s->named["z"] = z; s->named["y"] = y; s->named["x"] = x;
+    if (xyz_only) { s->arena = B.cursor; s->bits_n = B.bit_cursor; return; }
+
+    // ---- ADMM_DF (model.jl:362-373) ---------------------------------------------------------------
+    Buf zyF = B.alloc(nZY, "zy");
+    op_mask_scale(z, y, zyF, "df_mask");
+    Buf Dc = De, Fc = Fe; int64_t Dgs = 0, Fgs = 0;
+    Buf theta{}; bool have_theta = false;
+    for (int n = 0; n < d.npd; ++n) {
+        const int i_mu = s->i_mu0 + n, i_kap = s->i_kap0 + n, i_kaps = s->i_kaps0 + n;
+        // update_D
+        Buf rec = B.alloc(nS), Gm = B.alloc((size_t)d.G * nD), Dn = B.alloc((size_t)d.G * nD);
+        op_recon(z, y, Dc, Dgs, rec, "df_recon");
+        op_dgrad(z, y, rec, +1.f, Gm, "df_dgrad");                      // R = sumZD + sumYRD + S  ('+S': model.jl:282-285)
+        {
+            const Buf Dcc = Dc; const int64_t gsc = Dgs;
+            T.push_back({[=](cudaStream_t q) { k_d_update<<<nblk((int64_t)d.G * d.fl * d.M, 128), 128, 0, q>>>(S->data + Dcc.off, gsc, S->data + Gm.off, SCP, i_mu, S->data + Dn.off, d); },
+                         [=](cudaStream_t q) { k_d_update_bwd<<<nblk((int64_t)d.G * d.fl * d.M, 128), 128, 0, q>>>(S->data + Dcc.off, gsc, S->data + Gm.off, SCP, i_mu, S->data + Dn.off, S->grad + Dn.off, S->grad + Dcc.off, gsc, S->grad + Gm.off, DSCP, d); },
+                         "d_update"});
+        }
+        Dc = Dn; Dgs = nD;
+        // update_F
+        Buf fxc = B.alloc(nZY), e = B.alloc(nZY), Fg = B.alloc((size_t)d.G * nF), Fn = B.alloc((size_t)d.G * nF), nrm = B.alloc((size_t)d.G * d.K);
+        op_tconv(x, Fc, Fgs, fxc, "df_tconv");
+        {
+            const Buf th = theta; const bool ht = have_theta;
+            T.push_back({[=](cudaStream_t q) { k_sub3<<<nblk(nZY, 256), 256, 0, q>>>(S->data + fxc.off, S->data + zyF.off, ht ? S->data + th.off : nullptr, -1.f, S->data + e.off, nZY); },
+                         [=](cudaStream_t q) { k_sub3_bwd<<<nblk(nZY, 256), 256, 0, q>>>(S->grad + e.off, S->grad + fxc.off, S->grad + zyF.off, ht ? S->grad + th.off : nullptr, -1.f, nZY); },
+                         "e_build"});
+        }
+        op_fgrad(e, x, Fg, "df_fgrad");
+        {
+            const Buf Fcc = Fc; const int64_t gsc = Fgs;
+            T.push_back({[=](cudaStream_t q) { k_f_update<<<d.G * d.K, 256, 0, q>>>(S->data + Fcc.off, gsc, S->data + Fg.off, SCP, i_kap, i_kaps, S->data + Fn.off, S->data + nrm.off, d); },
+                         [=](cudaStream_t q) { k_f_update_bwd<<<d.G * d.K, 256, 0, q>>>(S->data + Fn.off, S->data + nrm.off, S->data + Fg.off, SCP, i_kap, i_kaps, S->grad + Fn.off, S->grad + Fcc.off, gsc, S->grad + Fg.off, DSCP, d); },
+                         "f_update"});
+        }
+        Fc = Fn; Fgs = nF;
+        // theta = theta + FX(X, F_new) - ZY   (only needed by the next pass)
+        if (n + 1 < d.npd) {
+            Buf fx2 = B.alloc(nZY), thn = B.alloc(nZY);
+            op_tconv(x, Fc, Fgs, fx2, "theta_tconv");
+            const Buf th = theta; const bool ht = have_theta;
+            T.push_back({[=](cudaStream_t q) { k_sub3<<<nblk(nZY, 256), 256, 0, q>>>(S->data + fx2.off, S->data + zyF.off, ht ? S->data + th.off : nullptr, +1.f, S->data + thn.off, nZY); },
+                         [=](cudaStream_t q) { k_sub3_bwd<<<nblk(nZY, 256), 256, 0, q>>>(S->grad + thn.off, S->grad + fx2.off, S->grad + zyF.off, ht ? S->grad + th.off : nullptr, +1.f, nZY); },
+                         "theta"});
+            theta = thn; have_theta = true;
+        }
+    }
+    s->named["D"] = Dc; s->named["F"] = Fc;
+    // ---- loss (model.jl:310-325) ------------------------------------------------------------------
+    Buf recL = B.alloc(nS), fxL = B.alloc(nZY);
+    op_recon(z, y, Dc, Dgs, recL, "loss_recon");
+    op_tconv(x, Fc, Fgs, fxL, "loss_tconv");
+    {
+        const Buf ls = s->loss;
+        T.push_back({[=](cudaStream_t q) { k_loss<<<d.G, 1024, 0, q>>>(S->data + recL.off, S->bases, S->data + fxL.off, S->data + zyF.off, S->data + ls.off, d); },
+                     [=](cudaStream_t q) { k_loss_bwd<<<nblk(std::max(nS, nZY), 256), 256, 0, q>>>(S->data + recL.off, S->bases, S->data + fxL.off, S->data + zyF.off, 1.f / (float)d.G, S->grad + recL.off, S->grad + fxL.off, S->grad + zyF.off, d); },
+                     "loss"});
+    }
+    s->arena = B.cursor; s->bits_n = B.bit_cursor;
+}
+
+static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
+    MB_CUDA(ctx, cudaMalloc(&s->p_raw, (size_t)s->n_total * 4));
+    MB_CUDA(ctx, cudaMalloc(&s->g_raw, (size_t)s->n_total * 4));
+    MB_CUDA(ctx, cudaMalloc(&s->mt, (size_t)s->n_total * 4));
+    MB_CUDA(ctx, cudaMalloc(&s->st, (size_t)s->n_total * 4));
+    MB_CUDA(ctx, cudaMemset(s->p_raw, 0, (size_t)s->n_total * 4));
+    MB_CUDA(ctx, cudaMemset(s->g_raw, 0, (size_t)s->n_total * 4));
+    MB_CUDA(ctx, cudaMemset(s->mt, 0, (size_t)s->n_total * 4));
+    MB_CUDA(ctx, cudaMemset(s->st, 0, (size_t)s->n_total * 4));
+    MB_CUDA(ctx, cudaMalloc(&s->data, s->arena * 4));
+    MB_CUDA(ctx, cudaMemset(s->data, 0, s->arena * 4));
+    if (!s->xyz_only) { MB_CUDA(ctx, cudaMalloc(&s->grad, s->arena * 4)); MB_CUDA(ctx, cudaMemset(s->grad, 0, s->arena * 4)); }
+    MB_CUDA(ctx, cudaMalloc(&s->bits, std::max<size_t>(s->bits_n, 16)));
+    MB_CUDA(ctx, cudaMalloc(&s->bases, (size_t)s->d.NS * s->d.Lb));
+    MB_CUDA(ctx, cudaMalloc(&s->idx_dev, (size_t)s->d.NS * 8));
+    MB_CUDA(ctx, cudaMallocHost(&s->idx_pinned, (size_t)s->d.NS * 8));
+    MB_CUDA(ctx, cudaMallocHost(&s->host_out, ((size_t)s->d.G * 3 + 8) * 4));
+    return MB200_OK;
+}
+
+extern "C" int32_t mb200_csc_create(mb200_ctx* ctx, const mb200_hparams* hp, int64_t Lb, int32_t n_groups, int32_t forward_only, mb200_csc** out) {
+    if (!ctx || !hp || !out) return MB200_E_INVALID;
+    *out = nullptr;
+    if (hp->filter_len < 1 || hp->M < 1 || hp->h < 1 || hp->K < 1 || hp->q < 1 || hp->batch_size < 1 || hp->num_pass_xyz < 1 || hp->num_pass_df < 1 || n_groups < 1)
+        MB_FAIL(ctx, MB200_E_INVALID, "csc: bad hyper-parameters");
+    const int64_t c = Lb - hp->filter_len + 1, l = c - hp->h + 1;
+    if (l < 1 || (int64_t)l * hp->K < hp->q) MB_FAIL(ctx, MB200_E_INVALID, "csc: sequence length %lld too short for filter_len %d, h %d, q %d", (long long)Lb, hp->filter_len, hp->h, hp->q);
+    MB_CUDA(ctx, cudaSetDevice(ctx->device));
+    mb200_csc* s = new mb200_csc();
+    s->ctx = ctx; s->hp = *hp; s->xyz_only = forward_only != 0;
+    CscDims& d = s->d;
+    d.B = hp->batch_size; d.G = n_groups; d.NS = d.B * d.G; d.Lb = (int)Lb; d.L4 = 4 * (int)Lb; d.c = (int)c; d.l = (int)l;
+    d.M = hp->M; d.M2 = 2 * hp->M; d.K = hp->K; d.h = hp->h; d.q = hp->q; d.fl = hp->filter_len; d.f_len = 4 * hp->filter_len;
+    d.npx = hp->num_pass_xyz; d.npd = hp->num_pass_df; d.mf = hp->magnifying_factor;
+    // raw vector layout = Flux.params(cdl) order (model.jl:67-137): lam[npx] kaps[npd] eta[npx] om[npx] kap[npd] D F rho[npx] mu[npd] | 3 warm-ups
+    int64_t o = 0;
+    s->off_lam = o; o += d.npx; s->off_kaps = o; o += d.npd; s->off_eta = o; o += d.npx; s->off_om = o; o += d.npx; s->off_kap = o; o += d.npd;
+    s->off_D = o; o += (int64_t)d.f_len * d.M; s->off_F = o; o += (int64_t)d.h * d.M2 * d.K; s->off_rho = o; o += d.npx; s->off_mu = o; o += d.npd;
+    s->n_train = o; s->off_warm = o; o += 3; s->n_total = o;
+    build_tape(s, s->xyz_only);
+    int rc = csc_alloc(ctx, s);
+    if (rc) { delete s; return rc; }
+    *out = s;
+    return MB200_OK;
+}
+
+extern "C" int32_t mb200_csc_destroy(mb200_ctx* ctx, mb200_csc* s) {
+    if (!s) return MB200_E_INVALID;
+    if (ctx) cudaSetDevice(ctx->device);
+    if (s->gexec) cudaGraphExecDestroy(s->gexec);
+    if (s->graph) cudaGraphDestroy(s->graph);
+    cudaFree(s->p_raw); cudaFree(s->g_raw); cudaFree(s->mt); cudaFree(s->st); cudaFree(s->data); cudaFree(s->grad); cudaFree(s->bits);
+    cudaFree(s->bases); cudaFree(s->idx_dev); cudaFreeHost(s->idx_pinned); cudaFreeHost(s->host_out);
+    delete s;
+    return MB200_OK;
+}
+
+extern "C" int32_t mb200_csc_n_params(const mb200_csc* s, int64_t* n_trainable, int64_t* n_total) {
+    if (!s) return MB200_E_INVALID;
+    if (n_trainable) *n_trainable = s->n_train;
+    if (n_total) *n_total = s->n_total;
+    return MB200_OK;
+}
+
+extern "C" int32_t mb200_csc_set_params(mb200_ctx* ctx, mb200_csc* s, const float* p, int64_t n) {
+    if (!ctx || !s || !p) return MB200_E_INVALID;
+    if (n != s->n_total) MB_FAIL(ctx, MB200_E_INVALID, "csc: expected %lld parameters (trainable %lld + 3 warm-up scalars)", (long long)s->n_total, (long long)s->n_train);
+    MB_CUDA(ctx, cudaSetDevice(ctx->device));
+    MB_CUDA(ctx, cudaMemcpyAsync(s->p_raw, p, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MB200_OK;
+}
+
+extern "C" int32_t mb200_csc_get_params(mb200_ctx* ctx, mb200_csc* s, float* p, int64_t n) {
+    if (!ctx || !s || !p) return MB200_E_INVALID;
+    if (n != s->n_total) MB_FAIL(ctx, MB200_E_INVALID, "csc: expected %lld parameters", (long long)s->n_total);
+    MB_CUDA(ctx, cudaSetDevice(ctx->device));
+    MB_CUDA(ctx, cudaMemcpyAsync(p, s->p_raw, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MB200_OK;
+}
+
+extern "C" int32_t mb200_csc_reset_optimizer(mb200_ctx* ctx, mb200_csc* s) {
+    if (!ctx || !s) return MB200_E_INVALID;
+    MB_CUDA(ctx, cudaMemsetAsync(s->mt, 0, (size_t)s->n_total * 4, ctx->stream));
+    MB_CUDA(ctx, cudaMemsetAsync(s->st, 0, (size_t)s->n_total * 4, ctx->stream));
+    s->step_count = 0;
+    return MB200_OK;
+}
+
+extern "C" int32_t mb200_csc_device_ptrs(const mb200_csc* s, void** params_dev, void** grads_dev) {
+    if (!s) return MB200_E_INVALID;
+    if (params_dev) *params_dev = s->p_raw;
+    if (grads_dev) *grads_dev = s->g_raw;
+    return MB200_OK;
+}
+
+// enqueue: gather the batch, forward tape, (optionally) reverse tape.  No host sync inside.
+static void enqueue_step(mb200_csc* s, const uint32_t* words, int64_t rowwords, bool backward, cudaStream_t q) {
+    const CscDims d = s->d;
+    k_unpack_bases<<<nblk((int64_t)d.NS * d.Lb, 256), 256, 0, q>>>(words, rowwords, s->idx_dev, s->bases, d);
+    for (auto& op : s->tape) op.fwd(q);
+    if (backward) {
+        cudaMemsetAsync(s->grad, 0, s->arena * 4, q);
+        cudaMemsetAsync(s->g_raw, 0, (size_t)s->n_total * 4, q);
+        for (auto it = s->tape.rbegin(); it != s->tape.rend(); ++it) it->bwd(q);
+    }
+}
+
+static int run_step(mb200_ctx* ctx, mb200_csc* s, const mb200_seqs* seqs, const int64_t* seq_idx, bool backward) {
+    const CscDims d = s->d;
+    if (seqs->Lb != d.Lb) MB_FAIL(ctx, MB200_E_INVALID, "csc: model built for Lb=%d, sequences have Lb=%lld", d.Lb, (long long)seqs->Lb);
+    for (int i = 0; i < d.NS; ++i) {
+        if (seq_idx[i] < 0 || seq_idx[i] >= seqs->N) MB_FAIL(ctx, MB200_E_INVALID, "csc: sequence index %lld out of range", (long long)seq_idx[i]);
+        s->idx_pinned[i] = seq_idx[i];
+    }
+    MB_CUDA(ctx, cudaMemcpyAsync(s->idx_dev, s->idx_pinned, (size_t)d.NS * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const bool use_graph = backward;       // the training step is replayed thousands of times: capture it once
+    if (use_graph) {
+        if (!s->graph_ok || s->graph_words != seqs->words || s->graph_rowwords != seqs->rowwords) {
+            if (s->gexec) { cudaGraphExecDestroy(s->gexec); s->gexec = nullptr; }
+            if (s->graph) { cudaGraphDestroy(s->graph); s->graph = nullptr; }
+            MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            MB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            enqueue_step(s, seqs->words, seqs->rowwords, true, ctx->stream);
+            MB_CUDA(ctx, cudaStreamEndCapture(ctx->stream, &s->graph));
+            MB_CUDA(ctx, cudaGraphInstantiate(&s->gexec, s->graph, 0));
+            s->graph_ok = true; s->graph_words = seqs->words; s->graph_rowwords = seqs->rowwords;
+        }
+        MB_CUDA(ctx, cudaGraphLaunch(s->gexec, ctx->stream));
+    } else {
+        enqueue_step(s, seqs->words, seqs->rowwords, false, ctx->stream);
+    }
+    MB_CUDA(ctx, cudaGetLastError());
+    return MB200_OK;
+}
+
+static int64_t tape_launches(const mb200_csc* s, bool backward) {
+    // counted once by running the tape on a capture-free dry pass is overkill; kernels per op are fixed:
+    int64_t n = 1;
+    for (auto& op : s->tape) {
+        const std::string nm = op.name;
+        const int f = nm == "prep" ? 10 : 1;
+        int b = 1;
+        if (nm == "prep") b = 9;
+        else if (nm.find("recon") != std::string::npos || nm.find("corr_sig") != std::string::npos || nm.find("dgrad") != std::string::npos ||
+                 nm.find("corr2d") != std::string::npos || nm.find("tconv") != std::string::npos || nm.find("fgrad") != std::string::npos) b = 2;
+        n += f + (backward ? b : 0);
+    }
+    return n;
+}
+
+// loss (and gradient) of n_groups batches.  seq_idx: n_groups*batch_size indices into seqs.
+// loss_out: n_groups*3 floats {total, reconstruction, syntax} per group; grads: n_trainable floats = mean over groups (or NULL).
+extern "C" int32_t mb200_csc_loss_grad(mb200_ctx* ctx, mb200_csc* s, const mb200_seqs* seqs, const int64_t* seq_idx, float* loss_out, float* grads) {
+    if (!ctx || !s || !seqs || !seq_idx) return MB200_E_INVALID;
+    if (s->xyz_only) MB_FAIL(ctx, MB200_E_INVALID, "csc: handle was created forward_only");
+    MB_CUDA(ctx, cudaSetDevice(ctx->device));
+    mb_reset_timing(ctx);
+    MbTimers tm(ctx);
+    const int tt = tm.begin(T_TOTAL), tc = tm.begin(T_CSC);
+    int rc = run_step(ctx, s, seqs, seq_idx, true);
+    if (rc) return rc;
+    tm.end(tc);
+    ctx->launches[T_CSC] += tape_launches(s, true);
+    const int td = tm.begin(T_D2H);
+    if (loss_out) MB_CUDA(ctx, cudaMemcpyAsync(loss_out, s->data + s->loss.off, (size_t)s->d.G * 3 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (grads) MB_CUDA(ctx, cudaMemcpyAsync(grads, s->g_raw, (size_t)s->n_train * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    tm.end(td); tm.end(tt);
+    MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    tm.collect();
+    return MB200_OK;
+}
+
+// forward + reverse pass only; gradients stay on the device (mb200_csc_device_ptrs) so that the host framework can
+// all-reduce them in place (one NCCL call) before mb200_csc_adabelief_step.  Asynchronous on the ctx stream.
+extern "C" int32_t mb200_csc_step_begin(mb200_ctx* ctx, mb200_csc* s, const mb200_seqs* seqs, const int64_t* seq_idx) {
+    if (!ctx || !s || !seqs || !seq_idx) return MB200_E_INVALID;
+    if (s->xyz_only) MB_FAIL(ctx, MB200_E_INVALID, "csc: handle was created forward_only");
+    MB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->launches[T_CSC] += tape_launches(s, true);
+    return run_step(ctx, s, seqs, seq_idx, true);
+}
+
+// AdaBelief update of the trainable vector with the gradients currently on the device (train.jl:46), then the
+// early-stop statistic l1 = sum |prep_syntax_filters(F)| (train.jl:47).  Blocks; returns mean loss of the last step.
+extern "C" int32_t mb200_csc_adabelief_step(mb200_ctx* ctx, mb200_csc* s, float eta, float beta1, float beta2, float eps,
+                                            float* loss_out, float* l1_F_out) {
+    if (!ctx || !s) return MB200_E_INVALID;
+    MB_CUDA(ctx, cudaSetDevice(ctx->device));
+    s->step_count += 1;
+    const float c1 = 1.f - powf(beta1, (float)s->step_count), c2 = 1.f - powf(beta2, (float)s->step_count);
+    k_adabelief<<<nblk(s->n_train, 256), 256, 0, ctx->stream>>>(s->p_raw, s->g_raw, s->mt, s->st, eta, beta1, beta2, eps * eps, c1, c2, (int)s->n_train);
+    float* d_l1 = s->data + s->loss.off + (size_t)s->d.G * 3;       // slot right after the per-group losses
+    MB_CUDA(ctx, cudaMemsetAsync(d_l1, 0, 4, ctx->stream));
+    k_l1_F<<<s->d.K, 256, 0, ctx->stream>>>(s->p_raw + s->off_F, d_l1, s->d);
+    ctx->launches[T_CSC] += 2;
+    MB_CUDA(ctx, cudaMemcpyAsync(s->host_out, s->data + s->loss.off, ((size_t)s->d.G * 3 + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (loss_out) { float m = 0.f; for (int g = 0; g < s->d.G; ++g) m += s->host_out[g * 3]; *loss_out = m / (float)s->d.G; }
+    if (l1_F_out) *l1_F_out = s->host_out[(size_t)s->d.G * 3];
+    return MB200_OK;
+}
+
+// debug / test access to named intermediates of the last forward pass: "z","y","x","zy","D","F","D0","F0","loss"
+extern "C" int32_t mb200_csc_get_buffer(mb200_ctx* ctx, mb200_csc* s, const char* name, float* out, int64_t n) {
+    if (!ctx || !s || !name || !out) return MB200_E_INVALID;
+    auto it = s->named.find(name);
+    if (it == s->named.end()) MB_FAIL(ctx, MB200_E_INVALID, "csc: no buffer named %s", name);
+    int64_t have = (int64_t)it->second.n;
+    if (std::string(name) == "loss") have = (int64_t)s->d.G * 3;
+    if (std::string(name) == "D" || std::string(name) == "F") have = (std::string(name) == "D") ? (int64_t)s->d.G * s->d.f_len * s->d.M : (int64_t)s->d.G * s->d.h * s->d.M2 * s->d.K;
+    if (n != have) MB_FAIL(ctx, MB200_E_INVALID, "csc: buffer %s has %lld floats", name, (long long)have);
+    MB_CUDA(ctx, cudaMemcpyAsync(out, s->data + it->second.off, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// code retrieval (inference/_1_code_retrieval.jl:33-56): forward-only ADMM_XYZ over consecutive groups of batch_size
+// sequences; non-zeros of X as (position, fil, seq, Float16 mag), ordered by seq, fil, position.
+// ---------------------------------------------------------------------------------------------
+#define CODE_SLOTS 96
+__global__ void __launch_bounds__(128) k_emit_codes(const float* __restrict__ x, int64_t seq0, mb200_code* __restrict__ slots, int32_t* __restrict__ counts, CscDims d) {
+    // one warp per sequence walks (fil, position) in order and compacts entries > 0 with ballots
+    const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= d.NS) return;
+    const int E = d.l * d.K;
+    int cnt = 0;
+    for (int e0 = 0; e0 < E; e0 += 32) {
+        const int e = e0 + lane;                      // e = fil * l + position
+        float v = 0.f; int k = 0, i = 0;
+        if (e < E) { k = e / d.l; i = e - k * d.l; v = x[(n * d.l + i) * d.K + k]; }
+        const bool hit = v > 0.f;
+        const unsigned m = __ballot_sync(FULLMASK, hit);
+        if (hit) {
+            const int o = cnt + __popc(m & ((1u << lane) - 1u));
+            if (o < CODE_SLOTS) {
+                mb200_code c; c.position = (uint16_t)i; c.fil = (uint16_t)k; c.seq = (uint32_t)(seq0 + n);
+                c.mag_f16 = __half_as_ushort(__float2half_rn(v)); c._pad = 0;
+                slots[n * CODE_SLOTS + o] = c;
+            }
+        }
+        cnt += __popc(m);
+    }
+    if (lane == 0) counts[n] = cnt;
+}
+
+extern "C" int32_t mb200_csc_codes(mb200_ctx* ctx, mb200_csc* s, const mb200_seqs* seqs, int64_t first_seq, int64_t n_seqs,
+                                   mb200_code* out, int64_t cap, int64_t* n_out) {
+    if (!ctx || !s || !seqs || !n_out) return MB200_E_INVALID;
+    const CscDims d = s->d;
+    if (seqs->Lb != d.Lb) MB_FAIL(ctx, MB200_E_INVALID, "csc: model built for Lb=%d, sequences have Lb=%lld", d.Lb, (long long)seqs->Lb);
+    if (first_seq < 0 || n_seqs < 0 || first_seq + n_seqs > seqs->N || n_seqs % d.B) MB_FAIL(ctx, MB200_E_INVALID, "csc_codes: range must be whole batches inside the data");
+    MB_CUDA(ctx, cudaSetDevice(ctx->device));
+    mb_reset_timing(ctx);
+    MbTimers tm(ctx);
+    const int tt = tm.begin(T_TOTAL);
+    int rc = mb_ensure_buf(ctx, 5, (size_t)d.NS * CODE_SLOTS * sizeof(mb200_code) + (size_t)d.NS * 4 + 256); if (rc) return rc;
+    mb200_code* d_slots = (mb200_code*)ctx->bufs[5];
+    int32_t* d_cnt = (int32_t*)((uint8_t*)ctx->bufs[5] + (size_t)d.NS * CODE_SLOTS * sizeof(mb200_code));
+    std::vector<mb200_code> h_slots((size_t)d.NS * CODE_SLOTS);
+    std::vector<int32_t> h_cnt(d.NS);
+    int64_t total = 0; bool overflow = false;
+    for (int64_t s0 = 0; s0 < n_seqs; s0 += d.NS) {
+        const int64_t ns = std::min<int64_t>(d.NS, n_seqs - s0);
+        for (int i = 0; i < d.NS; ++i) s->idx_pinned[i] = first_seq + s0 + (i < ns ? i : 0);   // tail: repeat a valid sequence, results ignored
+        MB_CUDA(ctx, cudaMemcpyAsync(s->idx_dev, s->idx_pinned, (size_t)d.NS * 8, cudaMemcpyHostToDevice, ctx->stream));
+        const int tc = tm.begin(T_CSC);
+        // forward-only: run ops up to the last XYZ pass (a forward_only handle holds exactly those)
+        k_unpack_bases<<<nblk((int64_t)d.NS * d.Lb, 256), 256, 0, ctx->stream>>>(seqs->words, seqs->rowwords, s->idx_dev, s->bases, d);
+        for (auto& op : s->tape) { op.fwd(ctx->stream); if (std::string(op.name) == "df_mask") break; }
+        k_emit_codes<<<nblk((int64_t)d.NS * 32, 128), 128, 0, ctx->stream>>>(s->data + s->named["x"].off, first_seq + s0, d_slots, d_cnt, d);
+        tm.end(tc);
+        ctx->launches[T_CSC] += tape_launches(s, false) + 1;
+        MB_CUDA(ctx, cudaGetLastError());
+        const int td = tm.begin(T_D2H);
+        MB_CUDA(ctx, cudaMemcpyAsync(h_cnt.data(), d_cnt, (size_t)d.NS * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        MB_CUDA(ctx, cudaMemcpyAsync(h_slots.data(), d_slots, (size_t)d.NS * CODE_SLOTS * sizeof(mb200_code), cudaMemcpyDeviceToHost, ctx->stream));
+        tm.end(td);
+        MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int64_t i = 0; i < ns; ++i) {
+            if (h_cnt[i] > CODE_SLOTS) MB_FAIL(ctx, MB200_E_UNSUPPORTED, "csc_codes: sequence %lld has %d non-zero codes (> %d slots)", (long long)(first_seq + s0 + i), h_cnt[i], CODE_SLOTS);
+            for (int j = 0; j < h_cnt[i]; ++j) {
+                if (total < cap && out) out[total] = h_slots[(size_t)i * CODE_SLOTS + j]; else overflow = overflow || (total >= cap);
+                ++total;
+            }
+        }
+    }
+    tm.end(tt);
+    MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    tm.collect();
+    *n_out = total;
+    if (overflow || (total > cap)) MB_FAIL(ctx, MB200_E_HITS_OVERFLOW, "csc_codes: %lld records, capacity %lld", (long long)total, (long long)cap);
+    return MB200_OK;
+}

@@ -1,0 +1,732 @@
+// Device kernels of the unrolled convolutional-sparse-coding network in "position space"
+// (SURVEY.md Appendix B).  Reference: src/model.jl (all), restated index by index:
+//   * z_mask_n zeroes every row of Z,Y that is not a multiple of 4 (model.jl:54-55,176-177,244), so the
+//     network lives on c = Lb-7 positions; mapclarge / mapdrange / upsample_nearest / groups=M*B convs
+//     (model.jl:46-51,240-241,270-273,285) are indexing, not arithmetic.
+//   * the D layer is three bilinear forms (code x filter -> signal, signal x filter -> code,
+//     code x signal -> filter) and the F layer three more (x (*) F -> fx, A (x) F -> x, A (x) x -> F);
+//     each form's adjoints are the other two, so six kernels serve forward and backward.
+// Layouts (fp32): z,y,alpha,beta [NS][c][M]; zy,fx,theta,d,e [NS][c][2M]; x,g [NS][l][K];
+//   signals [NS][4Lb]; D [32][M]; F [h][2M][K]; NS = groups * batch, group g owns sequences g*B..g*B+B-1.
+// A filter operand is either shared by all groups (gstride 0) or per group (gstride = its size).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct CscDims {
+    int B, G, NS, Lb, L4, c, l, M, M2, K, h, q, fl, f_len, npx, npd;
+    float mf;
+};
+
+#define FULLMASK 0xffffffffu
+__device__ __forceinline__ float warp_sum(float v) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+    return v;
+}
+// block-wide sum (blockDim.x multiple of 32, <= 1024); result valid in thread 0
+__device__ __forceinline__ float block_sum(float v) {
+    __shared__ float s_part[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) s_part[w] = v;
+    __syncthreads();
+    float r = 0.f;
+    if (w == 0) { r = lane < (int)(blockDim.x >> 5) ? s_part[lane] : 0.f; r = warp_sum(r); }
+    return r;
+}
+
+// =============================================================================================
+// D layer
+// =============================================================================================
+// A3 warm-up (model.jl:171-179) fused: z = relu(eta*(sum_j D[4j+s[p+j]][m]) - lam*eta), y with the
+// reverse-complement filter D[4(fl-1-j) + 3 - s[p+j]][m].  One thread per (n,p,m).
+__global__ void __launch_bounds__(256) k_warm_zy(const uint8_t* __restrict__ bases, const float* __restrict__ D,
+                                                 const float* __restrict__ sc, int i_eta, int i_lam,
+                                                 float* __restrict__ z, float* __restrict__ y, CscDims d) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)d.NS * d.c * d.M) return;
+    const int m = (int)(t % d.M);
+    const int64_t np = t / d.M;
+    const int p = (int)(np % d.c);
+    const int64_t n = np / d.c;
+    const uint8_t* s = bases + n * d.Lb + p;
+    float uf = 0.f, ur = 0.f;
+    for (int j = 0; j < d.fl; ++j) {
+        const int b = s[j];
+        uf += D[(4 * j + b) * d.M + m];
+        ur += D[(4 * (d.fl - 1 - j) + 3 - b) * d.M + m];
+    }
+    const float eta = sc[i_eta], lam = sc[i_lam];
+    z[t] = fmaxf(eta * uf - lam * eta, 0.f);
+    y[t] = fmaxf(eta * ur - lam * eta, 0.f);
+}
+// adjoint wrt D only (the warm-up scalars are not trainable: model.jl:68,72-73,137)
+__global__ void __launch_bounds__(256) k_warm_zy_bwd(const uint8_t* __restrict__ bases, const float* __restrict__ sc, int i_eta,
+                                                     const float* __restrict__ z, const float* __restrict__ y,
+                                                     const float* __restrict__ dz, const float* __restrict__ dy,
+                                                     float* __restrict__ dD, CscDims d) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)d.NS * d.c * d.M) return;
+    const int m = (int)(t % d.M);
+    const int64_t np = t / d.M;
+    const int p = (int)(np % d.c);
+    const int64_t n = np / d.c;
+    const float eta = sc[i_eta];
+    const float gz = z[t] > 0.f ? eta * dz[t] : 0.f;
+    const float gy = y[t] > 0.f ? eta * dy[t] : 0.f;
+    if (gz == 0.f && gy == 0.f) return;
+    const uint8_t* s = bases + n * d.Lb + p;
+    for (int j = 0; j < d.fl; ++j) {
+        const int b = s[j];
+        if (gz != 0.f) atomicAdd(&dD[(4 * j + b) * d.M + m], gz);
+        if (gy != 0.f) atomicAdd(&dD[(4 * (d.fl - 1 - j) + 3 - b) * d.M + m], gy);
+    }
+}
+
+// T1 "recon": out[n][t] (+)= sum_m sum_{p: 0<=t-4p<f_len} ca[n,p,m] F[t-4p][m] + cb[n,p,m] F[f_len-1-(t-4p)][m]
+// (model.jl:238-239, 276-277, 313-314).  One warp per (n,t), lanes over m.
+__global__ void __launch_bounds__(256) k_recon(const float* __restrict__ ca, const float* __restrict__ cb,
+                                               const float* __restrict__ filt, int64_t filt_gs,
+                                               float* __restrict__ out, int accumulate, CscDims d) {
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= (int64_t)d.NS * d.L4) return;
+    const int t = (int)(wid % d.L4);
+    const int64_t n = wid / d.L4;
+    const float* F = filt + (n / d.B) * filt_gs;
+    const int p_hi = min(d.c - 1, t >> 2);
+    const int p_lo = max(0, (t - d.f_len + 4) >> 2);            // smallest p with t-4p <= f_len-1
+    float acc = 0.f;
+    for (int p = p_lo; p <= p_hi; ++p) {
+        const int k = t - 4 * p;
+        const float* a = ca + (n * d.c + p) * d.M;
+        const float* b = cb + (n * d.c + p) * d.M;
+        const float* f0 = F + k * d.M;
+        const float* f1 = F + (d.f_len - 1 - k) * d.M;
+        for (int m = lane; m < d.M; m += 32) acc += a[m] * f0[m] + b[m] * f1[m];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) { if (accumulate) out[wid] += acc; else out[wid] = acc; }
+}
+
+// signal element with the one-hot input folded in: sig[n][t] + sgn * S[n][t], S[n][4p+a] = (base[n][p]==a)
+__device__ __forceinline__ float sig_at(const float* __restrict__ sig, const uint8_t* __restrict__ bases, float sgn, int64_t n, int t, const CscDims& d) {
+    float v = sig[n * d.L4 + t];
+    if (sgn != 0.f && bases[n * d.Lb + (t >> 2)] == (t & 3)) v += sgn;
+    return v;
+}
+
+// T2 "corr_sig": oa[n,p,m] (+)= sum_k r[n,4p+k] F[k][m];  ob[n,p,m] (+)= sum_k r[n,4p+k] F[f_len-1-k][m],  r = sig + sgn*S
+// (model.jl:240-241 z_grad/y_grad data terms).  One thread per (n,p,m).
+__global__ void __launch_bounds__(256) k_corr_sig(const float* __restrict__ sig, const uint8_t* __restrict__ bases, float sgn,
+                                                  const float* __restrict__ filt, int64_t filt_gs,
+                                                  float* __restrict__ oa, float* __restrict__ ob, int accumulate, CscDims d) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)d.NS * d.c * d.M) return;
+    const int m = (int)(t % d.M);
+    const int64_t np = t / d.M;
+    const int p = (int)(np % d.c);
+    const int64_t n = np / d.c;
+    const float* F = filt + (n / d.B) * filt_gs;
+    float a = 0.f, b = 0.f;
+    for (int k = 0; k < d.f_len; ++k) {
+        const float r = sig_at(sig, bases, sgn, n, 4 * p + k, d);
+        a += r * F[k * d.M + m];
+        b += r * F[(d.f_len - 1 - k) * d.M + m];
+    }
+    if (accumulate) { oa[t] += a; ob[t] += b; } else { oa[t] = a; ob[t] = b; }
+}
+
+// T3 "dgrad": of[g][tau][m] (+)= sum_{n in g} sum_p ca[n,p,m] r[n,4p+tau] + cb[n,p,m] r[n,4p+f_len-1-tau]
+// (model.jl:270-290 conv_code_diff + mapdrange, with r = sumZD+sumYRD+S there).  grid.y = group; one thread per
+// (tau,m).  When the output is shared by all groups (out_gs == 0) contributions are added atomically.
+__global__ void __launch_bounds__(256) k_dgrad(const float* __restrict__ ca, const float* __restrict__ cb,
+                                               const float* __restrict__ sig, const uint8_t* __restrict__ bases, float sgn,
+                                               float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= d.f_len * d.M) return;
+    const int g = blockIdx.y;
+    const int m = t % d.M, tau = t / d.M;
+    float acc = 0.f;
+    for (int64_t n = (int64_t)g * d.B; n < (int64_t)(g + 1) * d.B; ++n)
+        for (int p = 0; p < d.c; ++p) {
+            const float a = ca[(n * d.c + p) * d.M + m], b = cb[(n * d.c + p) * d.M + m];
+            if (a != 0.f) acc += a * sig_at(sig, bases, sgn, n, 4 * p + tau, d);
+            if (b != 0.f) acc += b * sig_at(sig, bases, sgn, n, 4 * p + d.f_len - 1 - tau, d);
+        }
+    float* o = of + (int64_t)g * out_gs + t;
+    if (out_gs == 0 && d.G > 1) atomicAdd(o, acc);
+    else if (accumulate) *o += acc; else *o = acc;
+}
+
+// =============================================================================================
+// F layer
+// =============================================================================================
+// U2 "corr2d": out[n,i,k] (+)= sum_{a<h} sum_{j<2M} A[n,i+a,j] F[a][j][k]   (model.jl:214,251). One thread per (n,i,k).
+__global__ void __launch_bounds__(128) k_corr2d(const float* __restrict__ A, const float* __restrict__ filt, int64_t filt_gs,
+                                                float* __restrict__ out, int accumulate, CscDims d) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)d.NS * d.l * d.K) return;
+    const int k = (int)(t % d.K);
+    const int64_t ni = t / d.K;
+    const int i = (int)(ni % d.l);
+    const int64_t n = ni / d.l;
+    const float* F = filt + (n / d.B) * filt_gs + k;
+    const float* a0 = A + (n * d.c + i) * d.M2;
+    float acc = 0.f;
+    const int hj = d.h * d.M2;                      // rows i..i+h-1 of A are contiguous: A[n,i+a,j] = a0[a*2M + j]
+    for (int e = 0; e < hj; ++e) {
+        const float av = a0[e];
+        if (av != 0.f) acc += av * F[(int64_t)e * d.K];
+    }
+    if (accumulate) out[t] += acc; else out[t] = acc;
+}
+
+// U1 "tconv": out[n,i,j] (+)= sum_a sum_k x[n,i-a,k] F[a][j][k], 0 <= i-a < l   (model.jl:229,263,294,316,370).
+// One thread per (n,i,j); x holds few non-zeros (top-q), so zero rows are skipped (warp-uniform test).
+__global__ void __launch_bounds__(128) k_tconv(const float* __restrict__ x, const float* __restrict__ filt, int64_t filt_gs,
+                                               float* __restrict__ out, int accumulate, CscDims d) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)d.NS * d.c * d.M2) return;
+    const int j = (int)(t % d.M2);
+    const int64_t ni = t / d.M2;
+    const int i = (int)(ni % d.c);
+    const int64_t n = ni / d.c;
+    const float* F = filt + (n / d.B) * filt_gs;
+    float acc = 0.f;
+    const int a_lo = max(0, i - d.l + 1), a_hi = min(d.h - 1, i);
+    for (int a = a_lo; a <= a_hi; ++a) {
+        const float* xr = x + (n * d.l + (i - a)) * d.K;
+        const float* fr = F + ((int64_t)a * d.M2 + j) * d.K;
+        for (int k = 0; k < d.K; ++k) {
+            const float xv = xr[k];
+            if (xv != 0.f) acc += xv * fr[k];
+        }
+    }
+    if (accumulate) out[t] += acc; else out[t] = acc;
+}
+
+// U3 "fgrad": of[g][a][j][k] (+)= sum_{n in g} sum_{i<l} A[n,a+i,j] x[n,i,k]   (model.jl:292-302). grid.y = group.
+__global__ void __launch_bounds__(128) k_fgrad(const float* __restrict__ A, const float* __restrict__ x,
+                                               float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= d.h * d.M2 * d.K) return;
+    const int g = blockIdx.y;
+    const int k = t % d.K;
+    const int aj = t / d.K;
+    const int j = aj % d.M2, a = aj / d.M2;
+    float acc = 0.f;
+    for (int64_t n = (int64_t)g * d.B; n < (int64_t)(g + 1) * d.B; ++n) {
+        const float* Ar = A + (n * d.c + a) * d.M2 + j;
+        const float* xr = x + n * d.l * d.K + k;
+        for (int i = 0; i < d.l; ++i) {
+            const float xv = xr[(int64_t)i * d.K];
+            if (xv != 0.f) acc += xv * Ar[(int64_t)i * d.M2];
+        }
+    }
+    float* o = of + (int64_t)g * out_gs + t;
+    if (out_gs == 0 && d.G > 1) atomicAdd(o, acc);
+    else if (accumulate) *o += acc; else *o = acc;
+}
+
+// =============================================================================================
+// element-wise updates (with their adjoints)
+// =============================================================================================
+// A8 (model.jl:240-244): zn = relu(z - eta*(gz + rho*(z - fx[:, :M] - alpha)) - lam*eta), same for y with fx[:, M:], beta.
+__global__ void __launch_bounds__(256) k_zy_update(const float* __restrict__ z, const float* __restrict__ y,
+                                                   const float* __restrict__ gz, const float* __restrict__ gy,
+                                                   const float* __restrict__ fx, const float* __restrict__ al, const float* __restrict__ be,
+                                                   const float* __restrict__ sc, int i_eta, int i_lam, int i_rho,
+                                                   float* __restrict__ zn, float* __restrict__ yn, CscDims d) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)d.NS * d.c * d.M) return;
+    const int m = (int)(t % d.M);
+    const int64_t np = t / d.M;
+    const float eta = sc[i_eta], lam = sc[i_lam], rho = sc[i_rho];
+    const float l = fx[np * d.M2 + m], r = fx[np * d.M2 + d.M + m];
+    zn[t] = fmaxf(z[t] - eta * (gz[t] + rho * (z[t] - l - al[t])) - lam * eta, 0.f);
+    yn[t] = fmaxf(y[t] - eta * (gy[t] + rho * (y[t] - r - be[t])) - lam * eta, 0.f);
+}
+__global__ void __launch_bounds__(256) k_zy_update_bwd(const float* __restrict__ z, const float* __restrict__ y,
+                                                       const float* __restrict__ gz, const float* __restrict__ gy,
+                                                       const float* __restrict__ fx, const float* __restrict__ al, const float* __restrict__ be,
+                                                       const float* __restrict__ sc, int i_eta, int i_lam, int i_rho,
+                                                       const float* __restrict__ zn, const float* __restrict__ yn,
+                                                       const float* __restrict__ dzn, const float* __restrict__ dyn,
+                                                       float* __restrict__ dz, float* __restrict__ dy, float* __restrict__ dgz, float* __restrict__ dgy,
+                                                       float* __restrict__ dfx, float* __restrict__ dal, float* __restrict__ dbe,
+                                                       float* __restrict__ dsc, CscDims d) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float s_eta = 0.f, s_lam = 0.f, s_rho = 0.f;
+    if (t < (int64_t)d.NS * d.c * d.M) {
+        const int m = (int)(t % d.M);
+        const int64_t np = t / d.M;
+        const float eta = sc[i_eta], lam = sc[i_lam], rho = sc[i_rho];
+        const float tz = zn[t] > 0.f ? dzn[t] : 0.f;
+        const float ty = yn[t] > 0.f ? dyn[t] : 0.f;
+        const float l = fx[np * d.M2 + m], r = fx[np * d.M2 + d.M + m];
+        const float ez = z[t] - l - al[t], ey = y[t] - r - be[t];
+        dz[t] += tz * (1.f - eta * rho);
+        dy[t] += ty * (1.f - eta * rho);
+        dgz[t] += -eta * tz;
+        dgy[t] += -eta * ty;
+        dfx[np * d.M2 + m] += eta * rho * tz;
+        dfx[np * d.M2 + d.M + m] += eta * rho * ty;
+        dal[t] += eta * rho * tz;
+        dbe[t] += eta * rho * ty;
+        s_eta = tz * (-(gz[t] + rho * ez) - lam) + ty * (-(gy[t] + rho * ey) - lam);
+        s_lam = -eta * (tz + ty);
+        s_rho = -eta * (tz * ez + ty * ey);
+    }
+    s_eta = block_sum(s_eta); s_lam = block_sum(s_lam); s_rho = block_sum(s_rho);
+    if (threadIdx.x == 0) {
+        if (s_eta != 0.f) atomicAdd(&dsc[i_eta], s_eta);
+        if (s_lam != 0.f) atomicAdd(&dsc[i_lam], s_lam);
+        if (s_rho != 0.f) atomicAdd(&dsc[i_rho], s_rho);
+    }
+}
+
+// A4 (model.jl:194-210): zy' = mf * [zy >= median{zy > 0 over the whole batch}] * zy.  One block per group:
+// exact selection of the middle order statistic(s) of the positive entries by an MSB-first radix select on the
+// float bit patterns (positive floats order like unsigned ints), then the mask is applied.  med[g] is kept for
+// the adjoint (the mask is a constant for AD: model.jl:208).
+__device__ __forceinline__ float zy_elem(const float* __restrict__ z, const float* __restrict__ y, int64_t e, const CscDims& d) {
+    // e indexes [n_local][p][j] inside the group's block of B*c*2M values
+    const int j = (int)(e % d.M2);
+    const int64_t np = e / d.M2;
+    return j < d.M ? z[np * d.M + j] : y[np * d.M + (j - d.M)];
+}
+__global__ void __launch_bounds__(1024) k_mask_scale(const float* __restrict__ z, const float* __restrict__ y,
+                                                     float* __restrict__ zy, float* __restrict__ med_out, CscDims d) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned int s_prefix, s_rank, s_cnt;
+    __shared__ float s_med;
+    const int g = blockIdx.x;
+    const int64_t E = (int64_t)d.B * d.c * d.M2;
+    const float* zg = z + (int64_t)g * d.B * d.c * d.M;
+    const float* yg = y + (int64_t)g * d.B * d.c * d.M;
+    // 1. number of positive entries
+    unsigned int cnt = 0;
+    for (int64_t e = threadIdx.x; e < E; e += blockDim.x) cnt += zy_elem(zg, yg, e, d) > 0.f;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    if (cnt) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    const unsigned int npos = s_cnt;
+    float med = -INFINITY;                                       // no positives: "no mask" (model.jl:197-198,209)
+    if (npos > 0) {
+        // ranks (0-based, ascending) of the middle element(s): odd -> npos/2 ; even -> npos/2-1 and npos/2
+        const unsigned int k1 = (npos & 1u) ? npos / 2 : npos / 2 - 1;
+        if (threadIdx.x == 0) { s_prefix = 0; s_rank = k1; }
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+            __syncthreads();
+            const unsigned int prefix = s_prefix;
+            const unsigned int pmask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+            for (int64_t e = threadIdx.x; e < E; e += blockDim.x) {
+                const float v = zy_elem(zg, yg, e, d);
+                if (v > 0.f) {
+                    const unsigned int b = __float_as_uint(v);
+                    if ((b & pmask) == prefix) atomicAdd(&hist[(b >> shift) & 255u], 1u);
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned int r = s_rank, c0 = 0; int bin = 0;
+                for (; bin < 256; ++bin) { if (c0 + hist[bin] > r) break; c0 += hist[bin]; }
+                s_rank = r - c0; s_prefix = prefix | ((unsigned int)bin << shift);
+            }
+            __syncthreads();
+        }
+        const float v1 = __uint_as_float(s_prefix);
+        if (npos & 1u) med = v1;
+        else {
+            // next order statistic: v1 again if it is repeated past rank k1, else the smallest value above v1
+            __syncthreads();
+            if (threadIdx.x == 0) { s_cnt = 0; s_prefix = 0x7f800000u; }
+            __syncthreads();
+            unsigned int le = 0, mn = 0x7f800000u;
+            for (int64_t e = threadIdx.x; e < E; e += blockDim.x) {
+                const float v = zy_elem(zg, yg, e, d);
+                if (v > 0.f) { if (v <= v1) ++le; else mn = min(mn, __float_as_uint(v)); }
+            }
+            if (le) atomicAdd(&s_cnt, le);
+            atomicMin(&s_prefix, mn);
+            __syncthreads();
+            const float v2 = (s_cnt >= k1 + 2) ? v1 : __uint_as_float(s_prefix);
+            med = v1 * 0.5f + v2 * 0.5f;                         // Statistics.middle(a, b) = a/2 + b/2
+        }
+    }
+    if (threadIdx.x == 0) { s_med = med; med_out[g] = med; }
+    __syncthreads();
+    med = s_med;
+    float* og = zy + (int64_t)g * E;
+    for (int64_t e = threadIdx.x; e < E; e += blockDim.x) {
+        const float v = zy_elem(zg, yg, e, d);
+        og[e] = v >= med ? d.mf * v : 0.f;
+    }
+}
+__global__ void __launch_bounds__(256) k_mask_scale_bwd(const float* __restrict__ z, const float* __restrict__ y, const float* __restrict__ med,
+                                                        const float* __restrict__ dzy, float* __restrict__ dz, float* __restrict__ dy, CscDims d) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)d.NS * d.c * d.M2) return;
+    const int j = (int)(t % d.M2);
+    const int64_t np = t / d.M2;
+    const float mg = med[(np / d.c) / d.B];
+    if (j < d.M) { const int64_t o = np * d.M + j; if (z[o] >= mg) dz[o] += d.mf * dzy[t]; }
+    else { const int64_t o = np * d.M + (j - d.M); if (y[o] >= mg) dy[o] += d.mf * dzy[t]; }
+}
+
+// A9 input: dd = fx - (zy' - [alpha beta])   (model.jl:248-250)
+__global__ void __launch_bounds__(256) k_d_build(const float* __restrict__ fx, const float* __restrict__ zy, const float* __restrict__ al,
+                                                 const float* __restrict__ be, float* __restrict__ dd, CscDims d) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)d.NS * d.c * d.M2) return;
+    const int j = (int)(t % d.M2);
+    const int64_t np = t / d.M2;
+    const float ab = j < d.M ? al[np * d.M + j] : be[np * d.M + j - d.M];
+    dd[t] = fx[t] - (zy[t] - ab);
+}
+__global__ void __launch_bounds__(256) k_d_build_bwd(const float* __restrict__ ddd, float* __restrict__ dfx, float* __restrict__ dzy,
+                                                     float* __restrict__ dal, float* __restrict__ dbe, CscDims d) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)d.NS * d.c * d.M2) return;
+    const int j = (int)(t % d.M2);
+    const int64_t np = t / d.M2;
+    const float g = ddd[t];
+    dfx[t] += g; dzy[t] -= g;
+    if (j < d.M) dal[np * d.M + j] += g; else dbe[np * d.M + j - d.M] += g;
+}
+
+// A5/A6/A9 (model.jl:181-192, 212-216, 252-253): v = (xprev ? xprev : 0) - sgn_omega*omega*g ; keep entries >= the
+// q-th largest of the sequence.  One block per sequence; MSB-first radix select on order-preserving keys.
+__device__ __forceinline__ unsigned int fkey(float v) { unsigned int b = __float_as_uint(v); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+__device__ __forceinline__ float fkey_inv(unsigned int k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+__global__ void __launch_bounds__(256) k_topq(const float* __restrict__ xprev, const float* __restrict__ g, const float* __restrict__ sc, int i_om,
+                                              float coef, float* __restrict__ xout, uint8_t* __restrict__ bit, float* __restrict__ vq_out, CscDims d) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned int s_prefix, s_rank;
+    const int64_t n = blockIdx.x;
+    const int E = d.l * d.K;
+    const float om = coef * sc[i_om];
+    const float* gp = g + n * E;
+    const float* xp = xprev ? xprev + n * E : nullptr;
+    if (threadIdx.x == 0) { s_prefix = 0; s_rank = (unsigned int)(E - d.q); }      // q-th largest = ascending rank E-q
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        hist[threadIdx.x] = 0;
+        __syncthreads();
+        const unsigned int prefix = s_prefix;
+        const unsigned int pmask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+        for (int e = threadIdx.x; e < E; e += blockDim.x) {
+            const float v = (xp ? xp[e] : 0.f) + om * gp[e];
+            const unsigned int kk = fkey(v);
+            if ((kk & pmask) == prefix) atomicAdd(&hist[(kk >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int r = s_rank, c0 = 0; int bin = 0;
+            for (; bin < 256; ++bin) { if (c0 + hist[bin] > r) break; c0 += hist[bin]; }
+            s_rank = r - c0; s_prefix = prefix | ((unsigned int)bin << shift);
+        }
+        __syncthreads();
+    }
+    const float vq = fkey_inv(s_prefix);
+    if (threadIdx.x == 0) vq_out[n] = vq;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        const float v = (xp ? xp[e] : 0.f) + om * gp[e];
+        const bool keep = v >= vq;
+        xout[n * E + e] = keep ? v : 0.f;
+        bit[n * E + e] = keep;
+    }
+}
+__global__ void __launch_bounds__(256) k_topq_bwd(const uint8_t* __restrict__ bit, const float* __restrict__ g, const float* __restrict__ sc, int i_om,
+                                                  float coef, const float* __restrict__ dxout, float* __restrict__ dxprev, float* __restrict__ dg,
+                                                  float* __restrict__ dsc, int om_trainable, CscDims d) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float s = 0.f;
+    if (t < (int64_t)d.NS * d.l * d.K) {
+        const float gr = bit[t] ? dxout[t] : 0.f;
+        if (dxprev) dxprev[t] += gr;
+        dg[t] += coef * sc[i_om] * gr;
+        s = coef * gr * g[t];
+    }
+    if (om_trainable) { s = block_sum(s); if (threadIdx.x == 0 && s != 0.f) atomicAdd(&dsc[i_om], s); }
+}
+
+// dual update (model.jl:265-266): an = al + fx[:, :M] - z ; bn = be + fx[:, M:] - y
+__global__ void __launch_bounds__(256) k_dual(const float* __restrict__ al, const float* __restrict__ be, const float* __restrict__ fx,
+                                              const float* __restrict__ z, const float* __restrict__ y, float* __restrict__ an, float* __restrict__ bn, CscDims d) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)d.NS * d.c * d.M) return;
+    const int m = (int)(t % d.M);
+    const int64_t np = t / d.M;
+    an[t] = (al ? al[t] : 0.f) + fx[np * d.M2 + m] - z[t];
+    bn[t] = (be ? be[t] : 0.f) + fx[np * d.M2 + d.M + m] - y[t];
+}
+__global__ void __launch_bounds__(256) k_dual_bwd(const float* __restrict__ dan, const float* __restrict__ dbn, float* __restrict__ dal, float* __restrict__ dbe,
+                                                  float* __restrict__ dfx, float* __restrict__ dz, float* __restrict__ dy, CscDims d) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)d.NS * d.c * d.M) return;
+    const int m = (int)(t % d.M);
+    const int64_t np = t / d.M;
+    const float ga = dan[t], gb = dbn[t];
+    if (dal) { dal[t] += ga; dbe[t] += gb; }
+    dfx[np * d.M2 + m] += ga; dfx[np * d.M2 + d.M + m] += gb;
+    dz[t] -= ga; dy[t] -= gb;
+}
+
+// out = a - b - (c ? c : 0)   over [NS][c][2M]   (e = fx - (zy + theta), model.jl:294; theta' = theta + fx - zy, :370 as out = fx - zy + theta)
+__global__ void __launch_bounds__(256) k_sub3(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c3, float csign,
+                                              float* __restrict__ out, int64_t n) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    out[t] = a[t] - b[t] + (c3 ? csign * c3[t] : 0.f);
+}
+__global__ void __launch_bounds__(256) k_sub3_bwd(const float* __restrict__ dout, float* __restrict__ da, float* __restrict__ db, float* __restrict__ dc3,
+                                                  float csign, int64_t n) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float g = dout[t];
+    da[t] += g; db[t] -= g;
+    if (dc3) dc3[t] += csign * g;
+}
+
+// A10 update (model.jl:287-288): Dn[g][4j+a][m] = D exp(-mu G) / sum_a' (D exp(-mu G)).  One thread per (g,j,m).
+__global__ void __launch_bounds__(256) k_d_update(const float* __restrict__ D, int64_t D_gs, const float* __restrict__ G, const float* __restrict__ sc, int i_mu,
+                                                  float* __restrict__ Dn, CscDims d) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= d.G * d.fl * d.M) return;
+    const int m = t % d.M;
+    const int gj = t / d.M;
+    const int j = gj % d.fl, g = gj / d.fl;
+    const float mu = sc[i_mu];
+    const float* Dg = D + (int64_t)g * D_gs;
+    const int64_t gs = (int64_t)d.f_len * d.M;
+    float u[4], s = 0.f;
+    #pragma unroll
+    for (int a = 0; a < 4; ++a) { const int o = (4 * j + a) * d.M + m; u[a] = Dg[o] * expf(-mu * G[g * gs + o]); s += u[a]; }
+    #pragma unroll
+    for (int a = 0; a < 4; ++a) Dn[g * gs + (4 * j + a) * d.M + m] = u[a] / s;
+}
+__global__ void __launch_bounds__(256) k_d_update_bwd(const float* __restrict__ D, int64_t D_gs, const float* __restrict__ G, const float* __restrict__ sc, int i_mu,
+                                                      const float* __restrict__ Dn, const float* __restrict__ dDn,
+                                                      float* __restrict__ dD, int64_t dD_gs, float* __restrict__ dG, float* __restrict__ dsc, CscDims d) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    float s_mu = 0.f;
+    if (t < d.G * d.fl * d.M) {
+        const int m = t % d.M;
+        const int gj = t / d.M;
+        const int j = gj % d.fl, g = gj / d.fl;
+        const float mu = sc[i_mu];
+        const float* Dg = D + (int64_t)g * D_gs;
+        const int64_t gs = (int64_t)d.f_len * d.M;
+        float u[4], s = 0.f, dot = 0.f;
+        #pragma unroll
+        for (int a = 0; a < 4; ++a) { const int o = (4 * j + a) * d.M + m; u[a] = Dg[o] * expf(-mu * G[g * gs + o]); s += u[a]; dot += dDn[g * gs + o] * Dn[g * gs + o]; }
+        #pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int o = (4 * j + a) * d.M + m;
+            const float du = (dDn[g * gs + o] - dot) / s;                 // d loss / d u_a
+            const float e = expf(-mu * G[g * gs + o]);
+            const float gD = du * e;
+            if (dD_gs == 0 && d.G > 1) atomicAdd(&dD[o], gD); else dD[(int64_t)g * dD_gs + o] += gD;
+            dG[g * gs + o] += du * u[a] * (-mu);
+            s_mu += du * u[a] * (-G[g * gs + o]);
+        }
+    }
+    s_mu = block_sum(s_mu);
+    if (threadIdx.x == 0 && s_mu != 0.f) atomicAdd(&dsc[i_mu], s_mu);
+}
+
+// A11 update (model.jl:304-308): Fu = relu(F - kap*Fg - kap*kaps) ; Fn[:,:,k] = Fu[:,:,k] / ||Fu[:,:,k]||_2.  One block per (g,k).
+__global__ void __launch_bounds__(256) k_f_update(const float* __restrict__ F, int64_t F_gs, const float* __restrict__ Fg, const float* __restrict__ sc,
+                                                  int i_kap, int i_kaps, float* __restrict__ Fn, float* __restrict__ nrm, CscDims d) {
+    __shared__ float s_n;
+    const int k = blockIdx.x % d.K, g = blockIdx.x / d.K;
+    const float kap = sc[i_kap], kaps = sc[i_kaps];
+    const int HJ = d.h * d.M2;
+    const int64_t gs = (int64_t)HJ * d.K;
+    const float* Fp = F + (int64_t)g * F_gs;
+    float ss = 0.f;
+    for (int e = threadIdx.x; e < HJ; e += blockDim.x) {
+        const float u = fmaxf(Fp[(int64_t)e * d.K + k] - kap * Fg[g * gs + (int64_t)e * d.K + k] - kap * kaps, 0.f);
+        ss += u * u;
+    }
+    ss = block_sum(ss);
+    if (threadIdx.x == 0) { s_n = sqrtf(ss); nrm[g * d.K + k] = s_n; }
+    __syncthreads();
+    const float nn = s_n;
+    for (int e = threadIdx.x; e < HJ; e += blockDim.x) {
+        const float u = fmaxf(Fp[(int64_t)e * d.K + k] - kap * Fg[g * gs + (int64_t)e * d.K + k] - kap * kaps, 0.f);
+        Fn[g * gs + (int64_t)e * d.K + k] = u / nn;
+    }
+}
+__global__ void __launch_bounds__(256) k_f_update_bwd(const float* __restrict__ Fn, const float* __restrict__ nrm, const float* __restrict__ Fg,
+                                                      const float* __restrict__ sc, int i_kap, int i_kaps, const float* __restrict__ dFn,
+                                                      float* __restrict__ dF, int64_t dF_gs, float* __restrict__ dFg, float* __restrict__ dsc, CscDims d) {
+    __shared__ float s_dot;
+    const int k = blockIdx.x % d.K, g = blockIdx.x / d.K;
+    const float kap = sc[i_kap], kaps = sc[i_kaps];
+    const int HJ = d.h * d.M2;
+    const int64_t gs = (int64_t)HJ * d.K;
+    const float nn = nrm[g * d.K + k];
+    float dot = 0.f;
+    for (int e = threadIdx.x; e < HJ; e += blockDim.x) dot += dFn[g * gs + (int64_t)e * d.K + k] * Fn[g * gs + (int64_t)e * d.K + k];
+    dot = block_sum(dot);
+    if (threadIdx.x == 0) s_dot = dot;
+    __syncthreads();
+    dot = s_dot;
+    float s_kap = 0.f, s_kaps = 0.f;
+    for (int e = threadIdx.x; e < HJ; e += blockDim.x) {
+        const int64_t o = g * gs + (int64_t)e * d.K + k;
+        const float fn = Fn[o];
+        if (fn > 0.f) {                                             // relu active (u = fn * nn > 0)
+            const float du = (dFn[o] - dot * fn) / nn;
+            if (dF_gs == 0 && d.G > 1) atomicAdd(&dF[(int64_t)e * d.K + k], du); else dF[(int64_t)g * dF_gs + (int64_t)e * d.K + k] += du;
+            dFg[o] += -kap * du;
+            s_kap += du * (-Fg[o] - kaps);
+            s_kaps += du * (-kap);
+        }
+    }
+    s_kap = block_sum(s_kap); s_kaps = block_sum(s_kaps);
+    if (threadIdx.x == 0) { if (s_kap != 0.f) atomicAdd(&dsc[i_kap], s_kap); if (s_kaps != 0.f) atomicAdd(&dsc[i_kaps], s_kaps); }
+}
+
+// A12 (model.jl:310-325): loss[g] = (1/B) (sum (recon - S)^2 + sum (fx - zy)^2).  One block per group.
+__global__ void __launch_bounds__(1024) k_loss(const float* __restrict__ recon, const uint8_t* __restrict__ bases, const float* __restrict__ fx,
+                                               const float* __restrict__ zy, float* __restrict__ loss, CscDims d) {
+    const int g = blockIdx.x;
+    float a = 0.f, b = 0.f;
+    const int64_t n0 = (int64_t)g * d.B;
+    for (int64_t e = threadIdx.x; e < (int64_t)d.B * d.L4; e += blockDim.x) {
+        const int64_t n = n0 + e / d.L4; const int t = (int)(e % d.L4);
+        const float r = sig_at(recon, bases, -1.f, n, t, d);
+        a += r * r;
+    }
+    const int64_t E2 = (int64_t)d.B * d.c * d.M2, o2 = n0 * d.c * d.M2;
+    for (int64_t e = threadIdx.x; e < E2; e += blockDim.x) { const float v = fx[o2 + e] - zy[o2 + e]; b += v * v; }
+    a = block_sum(a); b = block_sum(b);
+    if (threadIdx.x == 0) { loss[g * 3 + 0] = (a + b) / (float)d.B; loss[g * 3 + 1] = a / (float)d.B; loss[g * 3 + 2] = b / (float)d.B; }
+}
+// seeds the adjoints: d loss_total / d loss[g] = wgt (1/G for the mean over groups)
+__global__ void __launch_bounds__(256) k_loss_bwd(const float* __restrict__ recon, const uint8_t* __restrict__ bases, const float* __restrict__ fx,
+                                                  const float* __restrict__ zy, float wgt, float* __restrict__ drecon, float* __restrict__ dfx,
+                                                  float* __restrict__ dzy, CscDims d) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const float s = 2.f * wgt / (float)d.B;
+    if (t < (int64_t)d.NS * d.L4) drecon[t] += s * sig_at(recon, bases, -1.f, t / d.L4, (int)(t % d.L4), d);
+    if (t < (int64_t)d.NS * d.c * d.M2) { const float v = s * (fx[t] - zy[t]); dfx[t] += v; dzy[t] -= v; }
+}
+
+// =============================================================================================
+// parameter preparation (model.jl:139-169) and its adjoint; raw parameter vector in Flux.params order
+// =============================================================================================
+// scalars: eff = raw^2
+__global__ void k_prep_scalars(const float* __restrict__ raw, float* __restrict__ eff, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) eff[t] = raw[t] * raw[t];
+}
+__global__ void k_prep_scalars_bwd(const float* __restrict__ raw, const float* __restrict__ deff, float* __restrict__ draw, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) draw[t] += 2.f * raw[t] * deff[t];
+}
+// D: raw is Julia (32,1,M) column-major = raw[m*32 + 4j + a]; eff[(4j+a)*M + m] = (raw^2 + 1e-3) / sum_a'(...)
+__global__ void k_prep_D(const float* __restrict__ raw, float* __restrict__ eff, CscDims d) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= d.fl * d.M) return;
+    const int m = t % d.M, j = t / d.M;
+    float u[4], s = 0.f;
+    #pragma unroll
+    for (int a = 0; a < 4; ++a) { const float r = raw[m * d.f_len + 4 * j + a]; u[a] = r * r + 0.001f; s += u[a]; }
+    #pragma unroll
+    for (int a = 0; a < 4; ++a) eff[(4 * j + a) * d.M + m] = u[a] / s;
+}
+__global__ void k_prep_D_bwd(const float* __restrict__ raw, const float* __restrict__ eff, const float* __restrict__ deff, float* __restrict__ draw, CscDims d) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= d.fl * d.M) return;
+    const int m = t % d.M, j = t / d.M;
+    float s = 0.f, dot = 0.f;
+    #pragma unroll
+    for (int a = 0; a < 4; ++a) { const float r = raw[m * d.f_len + 4 * j + a]; s += r * r + 0.001f; dot += deff[(4 * j + a) * d.M + m] * eff[(4 * j + a) * d.M + m]; }
+    #pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const float r = raw[m * d.f_len + 4 * j + a];
+        draw[m * d.f_len + 4 * j + a] += (deff[(4 * j + a) * d.M + m] - dot) / s * 2.f * r;
+    }
+}
+// F: raw is Julia (h,2M,1,K) column-major = raw[(k*2M + j)*h + a]; eff[(a*2M + j)*K + k] = raw^2 / sqrt(sum_{a,j} raw^4). One block per k.
+__global__ void __launch_bounds__(256) k_prep_F(const float* __restrict__ raw, float* __restrict__ eff, float* __restrict__ nrm, CscDims d) {
+    __shared__ float s_n;
+    const int k = blockIdx.x;
+    const int HJ = d.h * d.M2;
+    float ss = 0.f;
+    for (int e = threadIdx.x; e < HJ; e += blockDim.x) {           // e = j*h + a in raw order
+        const float r = raw[(int64_t)k * HJ + e]; const float u = r * r; ss += u * u;
+    }
+    ss = block_sum(ss);
+    if (threadIdx.x == 0) { s_n = sqrtf(ss); nrm[k] = s_n; }
+    __syncthreads();
+    for (int e = threadIdx.x; e < HJ; e += blockDim.x) {
+        const int a = e % d.h, j = e / d.h;
+        const float r = raw[(int64_t)k * HJ + e];
+        eff[((int64_t)a * d.M2 + j) * d.K + k] = r * r / s_n;
+    }
+}
+__global__ void __launch_bounds__(256) k_prep_F_bwd(const float* __restrict__ raw, const float* __restrict__ eff, const float* __restrict__ nrm,
+                                                    const float* __restrict__ deff, float* __restrict__ draw, CscDims d) {
+    __shared__ float s_dot;
+    const int k = blockIdx.x;
+    const int HJ = d.h * d.M2;
+    float dot = 0.f;
+    for (int e = threadIdx.x; e < HJ; e += blockDim.x) {
+        const int a = e % d.h, j = e / d.h;
+        const int64_t o = ((int64_t)a * d.M2 + j) * d.K + k;
+        dot += deff[o] * eff[o];
+    }
+    dot = block_sum(dot);
+    if (threadIdx.x == 0) s_dot = dot;
+    __syncthreads();
+    dot = s_dot;
+    const float nn = nrm[k];
+    for (int e = threadIdx.x; e < HJ; e += blockDim.x) {
+        const int a = e % d.h, j = e / d.h;
+        const int64_t o = ((int64_t)a * d.M2 + j) * d.K + k;
+        const float r = raw[(int64_t)k * HJ + e];
+        draw[(int64_t)k * HJ + e] += (deff[o] - dot * eff[o]) / nn * 2.f * r;     // u = r^2, eff = u/||u||
+    }
+}
+
+// unpack the selected sequences' bases from the 2-bit store: bases[n][p] for n in idx
+__global__ void __launch_bounds__(256) k_unpack_bases(const uint32_t* __restrict__ words, int64_t rowwords, const int64_t* __restrict__ idx,
+                                                      uint8_t* __restrict__ bases, CscDims d) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)d.NS * d.Lb) return;
+    const int p = (int)(t % d.Lb);
+    const int64_t n = t / d.Lb;
+    const uint32_t w = words[idx[n] * rowwords + (p >> 4)];
+    bases[t] = (uint8_t)((w >> ((p & 15) * 2)) & 3u);
+}
+
+// AdaBelief (Flux 0.14.6 Optimise.AdaBelief, restated; see oracle/csc_oracle.py) over the trainable vector, fp32.
+__global__ void __launch_bounds__(256) k_adabelief(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mt, float* __restrict__ st,
+                                                   float eta, float b1, float b2, float eps2, float c1, float c2, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float gr = g[t];
+    const float m = b1 * mt[t] + (1.f - b1) * gr;
+    const float dv = gr - m;
+    const float s = b2 * st[t] + (1.f - b2) * dv * dv + eps2;
+    mt[t] = m; st[t] = s;
+    p[t] -= eta * m / c1 / (sqrtf(s / c2) + eps2);
+}
+// l1 = sum |prep_syntax_filters(F)| (train.jl:47): per k sum(r^2)/sqrt(sum r^4), summed over k.  One block per k, atomics into out.
+__global__ void __launch_bounds__(256) k_l1_F(const float* __restrict__ raw, float* __restrict__ out, CscDims d) {
+    const int k = blockIdx.x;
+    const int HJ = d.h * d.M2;
+    float s2 = 0.f, s4 = 0.f;
+    for (int e = threadIdx.x; e < HJ; e += blockDim.x) { const float r = raw[(int64_t)k * HJ + e]; const float u = r * r; s2 += u; s4 += u * u; }
+    s2 = block_sum(s2); s4 = block_sum(s4);
+    if (threadIdx.x == 0) atomicAdd(out, s2 / sqrtf(s4));
+}

@@ -34,7 +34,8 @@ struct __align__(16) GroupMeta {
     int32_t tab_off;                   // byte offset of the group's table inside the motif block
     int32_t npos[GROUP_MOTIFS];        // valid start positions per motif (Lb - len_k + 1, >= 0)
     uint32_t thr2[GROUP_MOTIFS];       // half2 bits (thr_fwd, thr_rc)
-    int32_t pad[2];
+    int32_t npos_max;                  // max over npos[]: chunks starting at or beyond it have nothing to score
+    int32_t pad;
 };                                     // 80 bytes
 static_assert(sizeof(GroupMeta) == 80, "GroupMeta must be 80 bytes");
 
@@ -190,6 +191,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a)
 
             for (int32_t g = 0; g < mbk.ng; ++g) {
                 const GroupMeta* gm = s_meta + g;
+                if (c * 32 >= gm->npos_max) {                 // warp-uniform: no valid start position in this chunk
+                    if (lane < GROUP_SLOTS) mrow[g * GROUP_SLOTS + lane] = 0u;
+                    continue;
+                }
                 const int32_t len = gm->len;
                 const uint32_t tab = tab_base + gm->tab_off;
                 __half2 acc[8];
@@ -454,6 +459,7 @@ static int build_plan(mb200_ctx* ctx, const uint16_t* pwms, const int64_t* lens,
                     const int k = order[idx];
                     const int len = (int)lens[k];
                     gm.npos[i] = (int32_t)std::max<int64_t>(0, Lb - len + 1);
+                    gm.npos_max = std::max(gm.npos_max, gm.npos[i]);
                     uint16_t t = 0;
                     if (thresh) {
                         const uint16_t raw = thresh[k];
