@@ -40,6 +40,9 @@ struct mb200_csc {
     float *data = nullptr, *grad = nullptr;
     size_t arena = 0;
     uint8_t* bits = nullptr; size_t bits_n = 0;          // top-q bitmasks
+    int n_lists = 0;                                     // ordered non-zero lists of the x-role tensors (x and d g)
+    int32_t* lcnt = nullptr; uint16_t* lidx = nullptr; float* lval = nullptr;
+    int mask_cap = 0;
     uint8_t* bases = nullptr;
     int64_t* idx_dev = nullptr;
     int64_t* idx_pinned = nullptr;
@@ -62,6 +65,7 @@ struct Builder {
     mb200_csc* s;
     size_t cursor = 0;
     size_t bit_cursor = 0;
+    int n_lists = 0;
     Buf alloc(size_t n, const char* name = nullptr) {
         Buf b; b.off = cursor; b.n = n; cursor += (n + 63) & ~(size_t)63;
         if (name) s->named[name] = b;
@@ -130,12 +134,31 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
 #define DSCP (S->grad + sc.off)
 
     // helpers that append one op each -------------------------------------------------------------
+    const bool fastK = (d.K == 24), fastM = (d.M <= 64);
+#define LCNT(L) (S->lcnt + (size_t)(L) * d.NS)
+#define LIDX(L) (S->lidx + (size_t)(L) * d.NS * LIST_CAP)
+#define LVAL(L) (S->lval + (size_t)(L) * d.NS * LIST_CAP)
+    auto run_corr2d = [=](const float* A, const float* filt, int64_t gs, float* out, int acc, cudaStream_t q) {
+        if (fastK) k_corr2d_w<24, 4><<<nblk((int64_t)d.NS * ((d.l + 3) / 4) * 32, 128), 128, 0, q>>>(A, filt, gs, out, acc, d);
+        else k_corr2d<<<nblk(nX, 128), 128, 0, q>>>(A, filt, gs, out, acc, d);
+    };
+    auto run_dgrad = [=](const float* ca, const float* cb, const float* sig, float sgn, float* of, int64_t ogs, int acc, cudaStream_t q) {
+        if (fastM) k_dgrad_b<<<dim3(d.f_len, d.G), 256, 0, q>>>(ca, cb, sig, S->bases, sgn, of, ogs, acc, d);
+        else k_dgrad<<<dim3(nblk(nD, 128), d.G), 128, 0, q>>>(ca, cb, sig, S->bases, sgn, of, ogs, acc, d);
+    };
+    auto run_tconv = [=](const float* x, int L, const float* filt, int64_t gs, float* out, int acc, cudaStream_t q) {
+        k_tconv_l<<<d.NS * d.c, 128, 0, q>>>(x, LCNT(L), LIDX(L), LVAL(L), filt, gs, out, acc, d);
+    };
+    auto run_fgrad = [=](const float* A, const float* x, int L, float* of, int64_t ogs, int acc, cudaStream_t q) {
+        k_fgrad_l<<<dim3(d.K, d.G), 256, 0, q>>>(A, x, LCNT(L), LIDX(L), LVAL(L), of, ogs, acc, d);
+    };
+    std::map<size_t, int> xlist;                 // buffer offset of an x tensor -> list of its data
     auto op_recon = [&](Buf ca, Buf cb, Buf filt, int64_t gs, Buf out, const char* nm) {
         T.push_back({[=](cudaStream_t q) { k_recon<<<nblk(nS * 32, 256), 256, 0, q>>>(S->data + ca.off, S->data + cb.off, S->data + filt.off, gs, S->data + out.off, 0, d); },
                      [=](cudaStream_t q) {
                          // d ca, d cb: corr_sig form with signal = d out ; d filt: dgrad form with signal = d out
                          k_corr_sig<<<nblk(nZ, 256), 256, 0, q>>>(S->grad + out.off, S->bases, 0.f, S->data + filt.off, gs, S->grad + ca.off, S->grad + cb.off, 1, d);
-                         k_dgrad<<<dim3(nblk(nD, 128), d.G), 128, 0, q>>>(S->data + ca.off, S->data + cb.off, S->grad + out.off, S->bases, 0.f, S->grad + filt.off, gs, 1, d);
+                         run_dgrad(S->data + ca.off, S->data + cb.off, S->grad + out.off, 0.f, S->grad + filt.off, gs, 1, q);
                      },
                      nm});
     };
@@ -143,12 +166,12 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         T.push_back({[=](cudaStream_t q) { k_corr_sig<<<nblk(nZ, 256), 256, 0, q>>>(S->data + sig.off, S->bases, sgn, S->data + filt.off, gs, S->data + oa.off, S->data + ob.off, 0, d); },
                      [=](cudaStream_t q) {
                          k_recon<<<nblk(nS * 32, 256), 256, 0, q>>>(S->grad + oa.off, S->grad + ob.off, S->data + filt.off, gs, S->grad + sig.off, 1, d);
-                         k_dgrad<<<dim3(nblk(nD, 128), d.G), 128, 0, q>>>(S->grad + oa.off, S->grad + ob.off, S->data + sig.off, S->bases, sgn, S->grad + filt.off, gs, 1, d);
+                         run_dgrad(S->grad + oa.off, S->grad + ob.off, S->data + sig.off, sgn, S->grad + filt.off, gs, 1, q);
                      },
                      nm});
     };
     auto op_dgrad = [&](Buf ca, Buf cb, Buf sig, float sgn, Buf outG, const char* nm) {      // per-group output
-        T.push_back({[=](cudaStream_t q) { k_dgrad<<<dim3(nblk(nD, 128), d.G), 128, 0, q>>>(S->data + ca.off, S->data + cb.off, S->data + sig.off, S->bases, sgn, S->data + outG.off, nD, 0, d); },
+        T.push_back({[=](cudaStream_t q) { run_dgrad(S->data + ca.off, S->data + cb.off, S->data + sig.off, sgn, S->data + outG.off, nD, 0, q); },
                      [=](cudaStream_t q) {
                          // d ca, d cb: corr_sig with filter = dG (per group) ; d sig: recon with filter = dG
                          k_corr_sig<<<nblk(nZ, 256), 256, 0, q>>>(S->data + sig.off, S->bases, sgn, S->grad + outG.off, nD, S->grad + ca.off, S->grad + cb.off, 1, d);
@@ -156,42 +179,50 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
                      },
                      nm});
     };
-    auto op_corr2d = [&](Buf A, Buf filt, int64_t gs, Buf out, const char* nm) {
-        T.push_back({[=](cudaStream_t q) { k_corr2d<<<nblk(nX, 128), 128, 0, q>>>(S->data + A.off, S->data + filt.off, gs, S->data + out.off, 0, d); },
+    // out = g feeds exactly one top-q op, whose adjoint writes d g and its non-zero list `glist`
+    auto op_corr2d = [&](Buf A, Buf filt, int64_t gs, Buf out, int glist, const char* nm) {
+        T.push_back({[=](cudaStream_t q) { run_corr2d(S->data + A.off, S->data + filt.off, gs, S->data + out.off, 0, q); },
                      [=](cudaStream_t q) {
-                         k_tconv<<<nblk(nZY, 128), 128, 0, q>>>(S->grad + out.off, S->data + filt.off, gs, S->grad + A.off, 1, d);
-                         k_fgrad<<<dim3(nblk(nF, 128), d.G), 128, 0, q>>>(S->data + A.off, S->grad + out.off, S->grad + filt.off, gs, 1, d);
+                         run_tconv(S->grad + out.off, glist, S->data + filt.off, gs, S->grad + A.off, 1, q);
+                         run_fgrad(S->data + A.off, S->grad + out.off, glist, S->grad + filt.off, gs, 1, q);
                      },
                      nm});
     };
     auto op_tconv = [&](Buf x, Buf filt, int64_t gs, Buf out, const char* nm) {
-        T.push_back({[=](cudaStream_t q) { k_tconv<<<nblk(nZY, 128), 128, 0, q>>>(S->data + x.off, S->data + filt.off, gs, S->data + out.off, 0, d); },
+        const int xl = xlist.at(x.off);
+        T.push_back({[=](cudaStream_t q) { run_tconv(S->data + x.off, xl, S->data + filt.off, gs, S->data + out.off, 0, q); },
                      [=](cudaStream_t q) {
-                         k_corr2d<<<nblk(nX, 128), 128, 0, q>>>(S->grad + out.off, S->data + filt.off, gs, S->grad + x.off, 1, d);
-                         k_fgrad<<<dim3(nblk(nF, 128), d.G), 128, 0, q>>>(S->grad + out.off, S->data + x.off, S->grad + filt.off, gs, 1, d);
+                         run_corr2d(S->grad + out.off, S->data + filt.off, gs, S->grad + x.off, 1, q);
+                         run_fgrad(S->grad + out.off, S->data + x.off, xl, S->grad + filt.off, gs, 1, q);
                      },
                      nm});
     };
     auto op_fgrad = [&](Buf A, Buf x, Buf outF, const char* nm) {                               // per-group output
-        T.push_back({[=](cudaStream_t q) { k_fgrad<<<dim3(nblk(nF, 128), d.G), 128, 0, q>>>(S->data + A.off, S->data + x.off, S->data + outF.off, nF, 0, d); },
+        const int xl = xlist.at(x.off);
+        T.push_back({[=](cudaStream_t q) { run_fgrad(S->data + A.off, S->data + x.off, xl, S->data + outF.off, nF, 0, q); },
                      [=](cudaStream_t q) {
-                         k_tconv<<<nblk(nZY, 128), 128, 0, q>>>(S->data + x.off, S->grad + outF.off, nF, S->grad + A.off, 1, d);
-                         k_corr2d<<<nblk(nX, 128), 128, 0, q>>>(S->data + A.off, S->grad + outF.off, nF, S->grad + x.off, 1, d);
+                         run_tconv(S->data + x.off, xl, S->grad + outF.off, nF, S->grad + A.off, 1, q);
+                         run_corr2d(S->data + A.off, S->grad + outF.off, nF, S->grad + x.off, 1, q);
                      },
                      nm});
     };
+    const int mask_cap = (int)std::min<int64_t>(2 * (int64_t)d.B * d.c * d.M, 49152);
+    s->mask_cap = mask_cap;
     auto op_mask_scale = [&](Buf z, Buf y, Buf zy, const char* nm) {
         Buf med = B.alloc(d.G);
-        T.push_back({[=](cudaStream_t q) { k_mask_scale<<<d.G, 1024, 0, q>>>(S->data + z.off, S->data + y.off, S->data + zy.off, S->data + med.off, d); },
+        T.push_back({[=](cudaStream_t q) { k_mask_scale_s<<<d.G, 1024, (size_t)mask_cap * 4, q>>>(S->data + z.off, S->data + y.off, S->data + zy.off, S->data + med.off, mask_cap, d); },
                      [=](cudaStream_t q) { k_mask_scale_bwd<<<nblk(nZY, 256), 256, 0, q>>>(S->data + z.off, S->data + y.off, S->data + med.off, S->grad + zy.off, S->grad + z.off, S->grad + y.off, d); },
                      nm});
     };
-    auto op_topq = [&](const Buf* xprev, Buf g, int i_om, float coef, int om_train, Buf xout, const char* nm) {
+    // returns nothing; registers the data list of xout; `glist` = list id for d g (allocated by the caller)
+    auto op_topq = [&](const Buf* xprev, Buf g, int i_om, float coef, int om_train, Buf xout, int glist, const char* nm) {
         const size_t bo = B.bit_cursor; B.bit_cursor += (size_t)nX;
-        Buf vq = B.alloc(d.NS);
+        const int xl = B.n_lists++;
+        xlist[xout.off] = xl;
         const bool hp_ = xprev != nullptr; const Buf xp = hp_ ? *xprev : Buf{};
-        T.push_back({[=](cudaStream_t q) { k_topq<<<d.NS, 256, 0, q>>>(hp_ ? S->data + xp.off : nullptr, S->data + g.off, SCP, i_om, coef, S->data + xout.off, S->bits + bo, S->data + vq.off, d); },
-                     [=](cudaStream_t q) { k_topq_bwd<<<nblk(nX, 256), 256, 0, q>>>(S->bits + bo, S->data + g.off, SCP, i_om, coef, S->grad + xout.off, hp_ ? S->grad + xp.off : nullptr, S->grad + g.off, DSCP, om_train, d); },
+        const size_t smem = (size_t)d.l * d.K * 4;
+        T.push_back({[=](cudaStream_t q) { k_topq_s<<<d.NS, 256, smem, q>>>(hp_ ? S->data + xp.off : nullptr, S->data + g.off, SCP, i_om, coef, S->data + xout.off, S->bits + bo, LCNT(xl), LIDX(xl), LVAL(xl), d); },
+                     [=](cudaStream_t q) { k_topq_s_bwd<<<d.NS, 256, 0, q>>>(S->bits + bo, S->data + g.off, SCP, i_om, coef, S->grad + xout.off, hp_ ? S->grad + xp.off : nullptr, S->grad + g.off, DSCP, om_train, LCNT(glist), LIDX(glist), LVAL(glist), d); },
                      nm});
     };
 
@@ -203,8 +234,7 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
     Buf zy = B.alloc(nZY);
     op_mask_scale(z, y, zy, "warm_mask");
     Buf g0 = B.alloc(nX), x = B.alloc(nX);
-    op_corr2d(zy, Fe, 0, g0, "warm_corr2d");
-    op_topq(nullptr, g0, s->i_om_w, 1.f, 0, x, "warm_topq");
+    { const int gl = B.n_lists++; op_corr2d(zy, Fe, 0, g0, gl, "warm_corr2d"); op_topq(nullptr, g0, s->i_om_w, 1.f, 0, x, gl, "warm_topq"); }
     Buf fx = B.alloc(nZY);
     op_tconv(x, Fe, 0, fx, "warm_tconv");
     Buf al{}, be{};
@@ -232,8 +262,7 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
                          [=](cudaStream_t q) { k_d_build_bwd<<<nblk(nZY, 256), 256, 0, q>>>(S->grad + dd.off, S->grad + fxc.off, S->grad + zy2.off, S->grad + alc.off, S->grad + bec.off, d); },
                          "d_build"});
         }
-        op_corr2d(dd, Fe, 0, g, "corr2d");
-        op_topq(&x, g, i_om, -1.f, 1, xn, "topq");
+        { const int gl = B.n_lists++; op_corr2d(dd, Fe, 0, g, gl, "corr2d"); op_topq(&x, g, i_om, -1.f, 1, xn, gl, "topq"); }
         x = xn;
         op_tconv(x, Fe, 0, fxn, "tconv");
         fx = fxn;
@@ -248,7 +277,7 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         have_dual = true;
     }
     s->named["z"] = z; s->named["y"] = y; s->named["x"] = x;
-    if (xyz_only) { s->arena = B.cursor; s->bits_n = B.bit_cursor; return; }
+    if (xyz_only) { s->arena = B.cursor; s->bits_n = B.bit_cursor; s->n_lists = B.n_lists; return; }
 
     // ---- ADMM_DF (model.jl:362-373) ---------------------------------------------------------------
     Buf zyF = B.alloc(nZY, "zy");
@@ -307,7 +336,7 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
                      [=](cudaStream_t q) { k_loss_bwd<<<nblk(std::max(nS, nZY), 256), 256, 0, q>>>(S->data + recL.off, S->bases, S->data + fxL.off, S->data + zyF.off, 1.f / (float)d.G, S->grad + recL.off, S->grad + fxL.off, S->grad + zyF.off, d); },
                      "loss"});
     }
-    s->arena = B.cursor; s->bits_n = B.bit_cursor;
+    s->arena = B.cursor; s->bits_n = B.bit_cursor; s->n_lists = B.n_lists;
 }
 
 static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
@@ -323,6 +352,12 @@ static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
     MB_CUDA(ctx, cudaMemset(s->data, 0, s->arena * 4));
     if (!s->xyz_only) { MB_CUDA(ctx, cudaMalloc(&s->grad, s->arena * 4)); MB_CUDA(ctx, cudaMemset(s->grad, 0, s->arena * 4)); }
     MB_CUDA(ctx, cudaMalloc(&s->bits, std::max<size_t>(s->bits_n, 16)));
+    MB_CUDA(ctx, cudaMalloc(&s->lcnt, (size_t)std::max(1, s->n_lists) * s->d.NS * 4));
+    MB_CUDA(ctx, cudaMalloc(&s->lidx, (size_t)std::max(1, s->n_lists) * s->d.NS * LIST_CAP * 2));
+    MB_CUDA(ctx, cudaMalloc(&s->lval, (size_t)std::max(1, s->n_lists) * s->d.NS * LIST_CAP * 4));
+    MB_CUDA(ctx, cudaMemset(s->lcnt, 0, (size_t)std::max(1, s->n_lists) * s->d.NS * 4));
+    MB_CUDA(ctx, cudaFuncSetAttribute(k_mask_scale_s, cudaFuncAttributeMaxDynamicSharedMemorySize, s->mask_cap * 4));
+    MB_CUDA(ctx, cudaFuncSetAttribute(k_topq_s, cudaFuncAttributeMaxDynamicSharedMemorySize, s->d.l * s->d.K * 4));
     MB_CUDA(ctx, cudaMalloc(&s->bases, (size_t)s->d.NS * s->d.Lb));
     MB_CUDA(ctx, cudaMalloc(&s->idx_dev, (size_t)s->d.NS * 8));
     MB_CUDA(ctx, cudaMallocHost(&s->idx_pinned, (size_t)s->d.NS * 8));
@@ -336,6 +371,7 @@ extern "C" int32_t mb200_csc_create(mb200_ctx* ctx, const mb200_hparams* hp, int
     if (hp->filter_len < 1 || hp->M < 1 || hp->h < 1 || hp->K < 1 || hp->q < 1 || hp->batch_size < 1 || hp->num_pass_xyz < 1 || hp->num_pass_df < 1 || n_groups < 1)
         MB_FAIL(ctx, MB200_E_INVALID, "csc: bad hyper-parameters");
     const int64_t c = Lb - hp->filter_len + 1, l = c - hp->h + 1;
+    if ((int64_t)l * hp->K * 4 > 200 * 1024 || (int64_t)l * hp->K > 65535) MB_FAIL(ctx, MB200_E_UNSUPPORTED, "csc: sequence length %lld too long for the shared-memory top-q", (long long)Lb);
     if (l < 1 || (int64_t)l * hp->K < hp->q) MB_FAIL(ctx, MB200_E_INVALID, "csc: sequence length %lld too short for filter_len %d, h %d, q %d", (long long)Lb, hp->filter_len, hp->h, hp->q);
     MB_CUDA(ctx, cudaSetDevice(ctx->device));
     mb200_csc* s = new mb200_csc();
@@ -361,7 +397,7 @@ extern "C" int32_t mb200_csc_destroy(mb200_ctx* ctx, mb200_csc* s) {
     if (ctx) cudaSetDevice(ctx->device);
     if (s->gexec) cudaGraphExecDestroy(s->gexec);
     if (s->graph) cudaGraphDestroy(s->graph);
-    cudaFree(s->p_raw); cudaFree(s->g_raw); cudaFree(s->mt); cudaFree(s->st); cudaFree(s->data); cudaFree(s->grad); cudaFree(s->bits);
+    cudaFree(s->p_raw); cudaFree(s->g_raw); cudaFree(s->mt); cudaFree(s->st); cudaFree(s->data); cudaFree(s->grad); cudaFree(s->bits); cudaFree(s->lcnt); cudaFree(s->lidx); cudaFree(s->lval);
     cudaFree(s->bases); cudaFree(s->idx_dev); cudaFreeHost(s->idx_pinned); cudaFreeHost(s->host_out);
     delete s;
     return MB200_OK;

@@ -730,3 +730,370 @@ __global__ void __launch_bounds__(256) k_l1_F(const float* __restrict__ raw, flo
     s2 = block_sum(s2); s4 = block_sum(s4);
     if (threadIdx.x == 0) atomicAdd(out, s2 / sqrtf(s4));
 }
+
+// =============================================================================================
+// Faster variants used by the tape (the plain kernels above remain as fallbacks for unusual shapes).
+// =============================================================================================
+#define LIST_CAP 64        // non-zeros kept per sequence in a code list; more -> consumers use their dense path
+
+// U2 dense, lane-split reduction: one warp computes ROWS consecutive output rows (same sequence) for all KK outputs.
+// The 1200-long reduction index e = a*2M + j is strided over lanes; every F row (KK floats) is loaded once per ROWS rows.
+template <int KK, int ROWS>
+__global__ void __launch_bounds__(128) k_corr2d_w(const float* __restrict__ A, const float* __restrict__ filt, int64_t filt_gs,
+                                                  float* __restrict__ out, int accumulate, CscDims d) {
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tiles = (d.l + ROWS - 1) / ROWS;
+    if (wid >= (int64_t)d.NS * tiles) return;
+    const int64_t n = wid / tiles;
+    const int i0 = (int)(wid % tiles) * ROWS;
+    const float* F = filt + (n / d.B) * filt_gs;
+    const float* a0 = A + (n * d.c + i0) * d.M2;
+    const int hj = d.h * d.M2;
+    const int rows = min(ROWS, d.l - i0);
+    float acc[ROWS][KK];
+    #pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+        #pragma unroll
+        for (int k = 0; k < KK; ++k) acc[r][k] = 0.f;
+    for (int e = lane; e < hj; e += 32) {
+        float av[ROWS];
+        #pragma unroll
+        for (int r = 0; r < ROWS; ++r) av[r] = r < rows ? a0[(int64_t)r * d.M2 + e] : 0.f;
+        const float4* fr = reinterpret_cast<const float4*>(F + (int64_t)e * KK);
+        #pragma unroll
+        for (int k4 = 0; k4 < KK / 4; ++k4) {
+            const float4 f = __ldg(fr + k4);
+            #pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                acc[r][4 * k4 + 0] += av[r] * f.x; acc[r][4 * k4 + 1] += av[r] * f.y;
+                acc[r][4 * k4 + 2] += av[r] * f.z; acc[r][4 * k4 + 3] += av[r] * f.w;
+            }
+        }
+    }
+    #pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+        #pragma unroll
+        for (int k = 0; k < KK; ++k) {
+            const float v = warp_sum(acc[r][k]);
+            if (lane == (k & 31) && r < rows) {
+                float* o = out + (n * d.l + i0 + r) * KK + k;
+                if (accumulate) *o += v; else *o = v;
+            }
+        }
+}
+
+// T3, one block per (group, tau): 4 reduction phases x 64 filter slots, deterministic shared-memory reduction.
+__global__ void __launch_bounds__(256) k_dgrad_b(const float* __restrict__ ca, const float* __restrict__ cb,
+                                                 const float* __restrict__ sig, const uint8_t* __restrict__ bases, float sgn,
+                                                 float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) {
+    __shared__ float s_red[4][64];
+    const int tau = blockIdx.x, g = blockIdx.y;
+    const int m = threadIdx.x & 63, ph = threadIdx.x >> 6;
+    float acc = 0.f;
+    if (m < d.M) {
+        for (int64_t n = (int64_t)g * d.B; n < (int64_t)(g + 1) * d.B; ++n)
+            for (int p = ph; p < d.c; p += 4) {
+                const float a = ca[(n * d.c + p) * d.M + m], b = cb[(n * d.c + p) * d.M + m];
+                acc += a * sig_at(sig, bases, sgn, n, 4 * p + tau, d) + b * sig_at(sig, bases, sgn, n, 4 * p + d.f_len - 1 - tau, d);
+            }
+    }
+    s_red[ph][m] = acc;
+    __syncthreads();
+    if (ph == 0 && m < d.M) {
+        const float v = (s_red[0][m] + s_red[1][m]) + (s_red[2][m] + s_red[3][m]);
+        float* o = of + (int64_t)g * out_gs + tau * d.M + m;
+        if (out_gs == 0 && d.G > 1) atomicAdd(o, v);
+        else if (accumulate) *o += v; else *o = v;
+    }
+}
+
+// ordered block-wide compaction helper: returns the exclusive prefix of `cnt` over threads (blockDim.x == 256)
+__device__ __forceinline__ int block_excl_scan256(int cnt, int* total) {
+    __shared__ int s_w[9];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = cnt;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULLMASK, inc, o); if (lane >= o) inc += y; }
+    __syncthreads();
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) { int run = 0; for (int i = 0; i < 8; ++i) { const int t = s_w[i]; s_w[i] = run; run += t; } s_w[8] = run; }
+    __syncthreads();
+    *total = s_w[8];
+    return s_w[w] + inc - cnt;
+}
+
+// A5 top-q with the sequence's values staged in shared memory (E = l*K floats of dynamic smem) and an ordered
+// non-zero list (entry = flat index i*K+k, value) written for the sparse consumers.
+__global__ void __launch_bounds__(256) k_topq_s(const float* __restrict__ xprev, const float* __restrict__ g, const float* __restrict__ sc, int i_om,
+                                                float coef, float* __restrict__ xout, uint8_t* __restrict__ bit,
+                                                int32_t* __restrict__ lcnt, uint16_t* __restrict__ lidx, float* __restrict__ lval, CscDims d) {
+    extern __shared__ float s_v[];
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned int s_prefix, s_rank;
+    const int64_t n = blockIdx.x;
+    const int E = d.l * d.K;
+    const float om = coef * sc[i_om];
+    for (int e = threadIdx.x; e < E; e += blockDim.x) s_v[e] = (xprev ? xprev[n * E + e] : 0.f) + om * g[n * E + e];
+    if (threadIdx.x == 0) { s_prefix = 0; s_rank = (unsigned int)(E - d.q); }
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        hist[threadIdx.x] = 0;
+        __syncthreads();
+        const unsigned int prefix = s_prefix;
+        const unsigned int pmask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+        for (int e = threadIdx.x; e < E; e += blockDim.x) {
+            const unsigned int kk = fkey(s_v[e]);
+            if ((kk & pmask) == prefix) atomicAdd(&hist[(kk >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int r = s_rank, c0 = 0; int bin = 0;
+            for (; bin < 256; ++bin) { if (c0 + hist[bin] > r) break; c0 += hist[bin]; }
+            s_rank = r - c0; s_prefix = prefix | ((unsigned int)bin << shift);
+        }
+        __syncthreads();
+    }
+    const float vq = fkey_inv(s_prefix);
+    // contiguous chunk per thread so that the list is ordered by flat index
+    const int per = (E + 255) / 256;
+    const int e0 = threadIdx.x * per, e1 = min(E, e0 + per);
+    int cnt = 0;
+    for (int e = e0; e < e1; ++e) {
+        const float v = s_v[e];
+        const bool keep = v >= vq;
+        xout[n * E + e] = keep ? v : 0.f;
+        bit[n * E + e] = keep;
+        cnt += keep && v != 0.f;
+    }
+    int total;
+    int o = block_excl_scan256(cnt, &total);
+    for (int e = e0; e < e1; ++e) {
+        const float v = s_v[e];
+        if (v >= vq && v != 0.f) { if (o < LIST_CAP) { lidx[n * LIST_CAP + o] = (uint16_t)e; lval[n * LIST_CAP + o] = v; } ++o; }
+    }
+    if (threadIdx.x == 0) lcnt[n] = total;
+}
+// adjoint of top-q, one block per sequence; also writes the ordered non-zero list of dg (the x-role operand of the
+// adjoints of corr2d) and reduces d omega.
+__global__ void __launch_bounds__(256) k_topq_s_bwd(const uint8_t* __restrict__ bit, const float* __restrict__ g, const float* __restrict__ sc, int i_om,
+                                                    float coef, const float* __restrict__ dxout, float* __restrict__ dxprev, float* __restrict__ dg,
+                                                    float* __restrict__ dsc, int om_trainable,
+                                                    int32_t* __restrict__ lcnt, uint16_t* __restrict__ lidx, float* __restrict__ lval, CscDims d) {
+    const int64_t n = blockIdx.x;
+    const int E = d.l * d.K;
+    const float om = coef * sc[i_om];
+    const int per = (E + 255) / 256;
+    const int e0 = threadIdx.x * per, e1 = min(E, e0 + per);
+    float s = 0.f; int cnt = 0;
+    for (int e = e0; e < e1; ++e) {
+        const int64_t t = n * E + e;
+        const float gr = bit[t] ? dxout[t] : 0.f;
+        if (dxprev) dxprev[t] += gr;
+        const float dgv = om * gr;
+        dg[t] = dgv;                       // g has a single consumer (this op): plain store, the arena value is overwritten
+        s += coef * gr * g[t];
+        cnt += dgv != 0.f;
+    }
+    int total;
+    int o = block_excl_scan256(cnt, &total);
+    for (int e = e0; e < e1; ++e) {
+        const float dgv = dg[n * E + e];
+        if (dgv != 0.f) { if (o < LIST_CAP) { lidx[n * LIST_CAP + o] = (uint16_t)e; lval[n * LIST_CAP + o] = dgv; } ++o; }
+    }
+    if (threadIdx.x == 0) lcnt[n] = total;
+    if (om_trainable) { s = block_sum(s); if (threadIdx.x == 0 && s != 0.f) atomicAdd(&dsc[i_om], s); }
+}
+
+// U1 with the x operand given as a list: one block per (n, i), threads over j.
+__global__ void __launch_bounds__(128) k_tconv_l(const float* __restrict__ x, const int32_t* __restrict__ lcnt, const uint16_t* __restrict__ lidx,
+                                                 const float* __restrict__ lval, const float* __restrict__ filt, int64_t filt_gs,
+                                                 float* __restrict__ out, int accumulate, CscDims d) {
+    __shared__ int s_i[LIST_CAP], s_k[LIST_CAP];
+    __shared__ float s_v[LIST_CAP];
+    const int64_t n = blockIdx.x / d.c;
+    const int i = blockIdx.x % d.c;
+    const float* F = filt + (n / d.B) * filt_gs;
+    const int cnt = lcnt[n];
+    if (cnt <= LIST_CAP) {
+        if (threadIdx.x < cnt) {
+            const int e = lidx[n * LIST_CAP + threadIdx.x];
+            s_i[threadIdx.x] = e / d.K; s_k[threadIdx.x] = e % d.K; s_v[threadIdx.x] = lval[n * LIST_CAP + threadIdx.x];
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < d.M2; j += blockDim.x) {
+            float acc = 0.f;
+            for (int q = 0; q < cnt; ++q) {
+                const int a = i - s_i[q];
+                if (a >= 0 && a < d.h) acc += s_v[q] * F[((int64_t)a * d.M2 + j) * d.K + s_k[q]];
+            }
+            float* o = out + (n * d.c + i) * d.M2 + j;
+            if (accumulate) *o += acc; else *o = acc;
+        }
+    } else {                                     // dense path (more than LIST_CAP non-zeros in this sequence)
+        const int a_lo = max(0, i - d.l + 1), a_hi = min(d.h - 1, i);
+        for (int j = threadIdx.x; j < d.M2; j += blockDim.x) {
+            float acc = 0.f;
+            for (int a = a_lo; a <= a_hi; ++a) {
+                const float* xr = x + (n * d.l + (i - a)) * d.K;
+                const float* fr = F + ((int64_t)a * d.M2 + j) * d.K;
+                for (int k = 0; k < d.K; ++k) { const float xv = xr[k]; if (xv != 0.f) acc += xv * fr[k]; }
+            }
+            float* o = out + (n * d.c + i) * d.M2 + j;
+            if (accumulate) *o += acc; else *o = acc;
+        }
+    }
+}
+
+// U3 with the x operand given as lists: one block per (group, k); the group's entries with fil == k are gathered in
+// order (sequence, position) and every thread accumulates a few (a, j) outputs over them.
+__global__ void __launch_bounds__(256) k_fgrad_l(const float* __restrict__ A, const float* __restrict__ x, const int32_t* __restrict__ lcnt,
+                                                 const uint16_t* __restrict__ lidx, const float* __restrict__ lval,
+                                                 float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) {
+    __shared__ int s_n[256], s_i[256];
+    __shared__ float s_v[256];
+    __shared__ int s_cnt, s_dense;
+    const int k = blockIdx.x, g = blockIdx.y;
+    if (threadIdx.x == 0) { s_cnt = 0; s_dense = 0; }
+    __syncthreads();
+    if (threadIdx.x < 32) {                      // one warp gathers in order
+        int cnt = 0;
+        for (int b = 0; b < d.B; ++b) {
+            const int64_t n = (int64_t)g * d.B + b;
+            const int c = lcnt[n];
+            if (c > LIST_CAP) { if (threadIdx.x == 0) s_dense = 1; break; }
+            for (int q0 = 0; q0 < c; q0 += 32) {
+                const int q = q0 + threadIdx.x;
+                int e = 0; bool hit = false;
+                if (q < c) { e = lidx[n * LIST_CAP + q]; hit = (e % d.K) == k; }
+                const unsigned m = __ballot_sync(FULLMASK, hit);
+                if (hit) {
+                    const int o = cnt + __popc(m & ((1u << threadIdx.x) - 1u));
+                    if (o < 256) { s_n[o] = (int)n; s_i[o] = e / d.K; s_v[o] = lval[n * LIST_CAP + q]; }
+                }
+                cnt += __popc(m);
+            }
+        }
+        if (threadIdx.x == 0) { s_cnt = cnt; if (cnt > 256) s_dense = 1; }
+    }
+    __syncthreads();
+    const int HJ = d.h * d.M2;
+    if (!s_dense) {
+        const int cnt = s_cnt;
+        for (int o = threadIdx.x; o < HJ; o += blockDim.x) {
+            const int a = o / d.M2, j = o - a * d.M2;
+            float acc = 0.f;
+            for (int q = 0; q < cnt; ++q) acc += s_v[q] * A[((int64_t)s_n[q] * d.c + a + s_i[q]) * d.M2 + j];
+            float* op = of + (int64_t)g * out_gs + (int64_t)o * d.K + k;
+            if (out_gs == 0 && d.G > 1) atomicAdd(op, acc);
+            else if (accumulate) *op += acc; else *op = acc;
+        }
+    } else {
+        for (int o = threadIdx.x; o < HJ; o += blockDim.x) {
+            const int a = o / d.M2, j = o - a * d.M2;
+            float acc = 0.f;
+            for (int64_t n = (int64_t)g * d.B; n < (int64_t)(g + 1) * d.B; ++n)
+                for (int i = 0; i < d.l; ++i) {
+                    const float xv = x[(n * d.l + i) * d.K + k];
+                    if (xv != 0.f) acc += xv * A[(n * d.c + a + i) * d.M2 + j];
+                }
+            float* op = of + (int64_t)g * out_gs + (int64_t)o * d.K + k;
+            if (out_gs == 0 && d.G > 1) atomicAdd(op, acc);
+            else if (accumulate) *op += acc; else *op = acc;
+        }
+    }
+}
+
+// A4 with the positive entries of the group compacted into shared memory (cap floats of dynamic smem); falls back to
+// re-reading global memory in every pass when there are more positives than fit.
+__global__ void __launch_bounds__(1024) k_mask_scale_s(const float* __restrict__ z, const float* __restrict__ y,
+                                                       float* __restrict__ zy, float* __restrict__ med_out, int cap, CscDims d) {
+    extern __shared__ float s_pos[];
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned int s_prefix, s_rank, s_cnt, s_min;
+    __shared__ float s_med;
+    const int g = blockIdx.x;
+    const int64_t EZ = (int64_t)d.B * d.c * d.M;
+    const float* zg = z + (int64_t)g * EZ;
+    const float* yg = y + (int64_t)g * EZ;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    // 1. compact positives (order is irrelevant for order statistics)
+    for (int64_t e0 = 0; e0 < 2 * EZ; e0 += blockDim.x) {
+        const int64_t e = e0 + threadIdx.x;
+        float v = 0.f;
+        if (e < EZ) v = zg[e]; else if (e < 2 * EZ) v = yg[e - EZ];
+        const bool pos = v > 0.f;
+        const unsigned m = __ballot_sync(FULLMASK, pos);
+        unsigned base = 0;
+        if (lane == 0 && m) base = atomicAdd(&s_cnt, __popc(m));
+        base = __shfl_sync(FULLMASK, base, 0);
+        if (pos) { const unsigned o = base + __popc(m & ((1u << lane) - 1u)); if (o < (unsigned)cap) s_pos[o] = v; }
+    }
+    __syncthreads();
+    const unsigned int npos = s_cnt;
+    const bool in_smem = npos <= (unsigned)cap;
+    float med = -INFINITY;
+    if (npos > 0) {
+        const unsigned int k1 = (npos & 1u) ? npos / 2 : npos / 2 - 1;
+        if (threadIdx.x == 0) { s_prefix = 0; s_rank = k1; }
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+            __syncthreads();
+            const unsigned int prefix = s_prefix;
+            const unsigned int pmask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+            if (in_smem) {
+                for (unsigned e = threadIdx.x; e < npos; e += blockDim.x) {
+                    const unsigned int b = __float_as_uint(s_pos[e]);
+                    if ((b & pmask) == prefix) atomicAdd(&hist[(b >> shift) & 255u], 1u);
+                }
+            } else {
+                for (int64_t e = threadIdx.x; e < 2 * EZ; e += blockDim.x) {
+                    const float v = e < EZ ? zg[e] : yg[e - EZ];
+                    if (v > 0.f) { const unsigned int b = __float_as_uint(v); if ((b & pmask) == prefix) atomicAdd(&hist[(b >> shift) & 255u], 1u); }
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned int r = s_rank, c0 = 0; int bin = 0;
+                for (; bin < 256; ++bin) { if (c0 + hist[bin] > r) break; c0 += hist[bin]; }
+                s_rank = r - c0; s_prefix = prefix | ((unsigned int)bin << shift);
+            }
+            __syncthreads();
+        }
+        const float v1 = __uint_as_float(s_prefix);
+        if (npos & 1u) med = v1;
+        else {
+            __syncthreads();
+            if (threadIdx.x == 0) { s_cnt = 0; s_min = 0x7f800000u; }
+            __syncthreads();
+            unsigned int le = 0, mn = 0x7f800000u;
+            if (in_smem) {
+                for (unsigned e = threadIdx.x; e < npos; e += blockDim.x) { const float v = s_pos[e]; if (v <= v1) ++le; else mn = min(mn, __float_as_uint(v)); }
+            } else {
+                for (int64_t e = threadIdx.x; e < 2 * EZ; e += blockDim.x) {
+                    const float v = e < EZ ? zg[e] : yg[e - EZ];
+                    if (v > 0.f) { if (v <= v1) ++le; else mn = min(mn, __float_as_uint(v)); }
+                }
+            }
+            if (le) atomicAdd(&s_cnt, le);
+            atomicMin(&s_min, mn);
+            __syncthreads();
+            const float v2 = (s_cnt >= k1 + 2) ? v1 : __uint_as_float(s_min);
+            med = v1 * 0.5f + v2 * 0.5f;
+        }
+    }
+    if (threadIdx.x == 0) { s_med = med; med_out[g] = med; }
+    __syncthreads();
+    med = s_med;
+    // 2. apply: rows np = (n_local, p), lanes over m
+    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float* og = zy + (int64_t)g * d.B * d.c * d.M2;
+    for (int np = warp; np < d.B * d.c; np += nw)
+        for (int m = lane; m < d.M; m += 32) {
+            const float vz = zg[(int64_t)np * d.M + m], vy = yg[(int64_t)np * d.M + m];
+            og[(int64_t)np * d.M2 + m] = vz >= med ? d.mf * vz : 0.f;
+            og[(int64_t)np * d.M2 + d.M + m] = vy >= med ? d.mf * vy : 0.f;
+        }
+}
