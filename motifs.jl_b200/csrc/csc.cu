@@ -139,18 +139,18 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
 #define LIDX(L) (S->lidx + (size_t)(L) * d.NS * LIST_CAP)
 #define LVAL(L) (S->lval + (size_t)(L) * d.NS * LIST_CAP)
     auto run_corr2d = [=](const float* A, const float* filt, int64_t gs, float* out, int acc, cudaStream_t q) {
-        if (fastK) k_corr2d_w<24, 4><<<nblk((int64_t)d.NS * ((d.l + 3) / 4) * 32, 128), 128, 0, q>>>(A, filt, gs, out, acc, d);
+        if (fastK) k_corr2d_w<24, 4><<<d.NS * ((d.l + 3) / 4), 128, 0, q>>>(A, filt, gs, out, acc, d);
         else k_corr2d<<<nblk(nX, 128), 128, 0, q>>>(A, filt, gs, out, acc, d);
     };
     auto run_dgrad = [=](const float* ca, const float* cb, const float* sig, float sgn, float* of, int64_t ogs, int acc, cudaStream_t q) {
-        if (fastM) k_dgrad_b<<<dim3(d.f_len, d.G), 256, 0, q>>>(ca, cb, sig, S->bases, sgn, of, ogs, acc, d);
+        if (fastM) k_dgrad_b<<<dim3(d.f_len, d.G), 1024, 0, q>>>(ca, cb, sig, S->bases, sgn, of, ogs, acc, d);
         else k_dgrad<<<dim3(nblk(nD, 128), d.G), 128, 0, q>>>(ca, cb, sig, S->bases, sgn, of, ogs, acc, d);
     };
     auto run_tconv = [=](const float* x, int L, const float* filt, int64_t gs, float* out, int acc, cudaStream_t q) {
         k_tconv_l<<<d.NS * d.c, 128, 0, q>>>(x, LCNT(L), LIDX(L), LVAL(L), filt, gs, out, acc, d);
     };
     auto run_fgrad = [=](const float* A, const float* x, int L, float* of, int64_t ogs, int acc, cudaStream_t q) {
-        k_fgrad_l<<<dim3(d.K, d.G), 256, 0, q>>>(A, x, LCNT(L), LIDX(L), LVAL(L), of, ogs, acc, d);
+        k_fgrad_l<<<dim3(d.K, d.h, d.G), 128, 0, q>>>(A, x, LCNT(L), LIDX(L), LVAL(L), of, ogs, acc, d);
     };
     std::map<size_t, int> xlist;                 // buffer offset of an x tensor -> list of its data
     auto op_recon = [&](Buf ca, Buf cb, Buf filt, int64_t gs, Buf out, const char* nm) {

@@ -736,17 +736,26 @@ __global__ void __launch_bounds__(256) k_l1_F(const float* __restrict__ raw, flo
 // =============================================================================================
 #define LIST_CAP 64        // non-zeros kept per sequence in a code list; more -> consumers use their dense path
 
-// U2 dense, lane-split reduction: one warp computes ROWS consecutive output rows (same sequence) for all KK outputs.
-// The 1200-long reduction index e = a*2M + j is strided over lanes; every F row (KK floats) is loaded once per ROWS rows.
+// histogram increment with intra-warp aggregation: lanes that hit the same bin elect one leader (values of one
+// group/sequence share their leading bytes, so plain shared-memory atomics would serialise on one bin)
+__device__ __forceinline__ void hist_add(unsigned int* hist, bool active, unsigned int bin) {
+    const unsigned act = __ballot_sync(FULLMASK, active);
+    if (!active) return;
+    const unsigned peers = __match_any_sync(act, bin);
+    if ((threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&hist[bin], (unsigned int)__popc(peers));
+}
+
+// U2 dense: one block (4 warps) computes ROWS consecutive output rows (same sequence) for all KK outputs.  The
+// 1200-long reduction index e = a*2M + j is strided over the 128 threads; every F row (KK floats) is loaded once per
+// ROWS rows; partial sums are combined by warp shuffles and a small shared-memory reduction (fixed order).
 template <int KK, int ROWS>
 __global__ void __launch_bounds__(128) k_corr2d_w(const float* __restrict__ A, const float* __restrict__ filt, int64_t filt_gs,
                                                   float* __restrict__ out, int accumulate, CscDims d) {
-    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    __shared__ float s_part[4][ROWS * KK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tiles = (d.l + ROWS - 1) / ROWS;
-    if (wid >= (int64_t)d.NS * tiles) return;
-    const int64_t n = wid / tiles;
-    const int i0 = (int)(wid % tiles) * ROWS;
+    const int64_t n = blockIdx.x / tiles;
+    const int i0 = (int)(blockIdx.x % tiles) * ROWS;
     const float* F = filt + (n / d.B) * filt_gs;
     const float* a0 = A + (n * d.c + i0) * d.M2;
     const int hj = d.h * d.M2;
@@ -756,7 +765,8 @@ __global__ void __launch_bounds__(128) k_corr2d_w(const float* __restrict__ A, c
     for (int r = 0; r < ROWS; ++r)
         #pragma unroll
         for (int k = 0; k < KK; ++k) acc[r][k] = 0.f;
-    for (int e = lane; e < hj; e += 32) {
+    #pragma unroll 2
+    for (int e = threadIdx.x; e < hj; e += 128) {
         float av[ROWS];
         #pragma unroll
         for (int r = 0; r < ROWS; ++r) av[r] = r < rows ? a0[(int64_t)r * d.M2 + e] : 0.f;
@@ -776,32 +786,41 @@ __global__ void __launch_bounds__(128) k_corr2d_w(const float* __restrict__ A, c
         #pragma unroll
         for (int k = 0; k < KK; ++k) {
             const float v = warp_sum(acc[r][k]);
-            if (lane == (k & 31) && r < rows) {
-                float* o = out + (n * d.l + i0 + r) * KK + k;
-                if (accumulate) *o += v; else *o = v;
-            }
+            if (lane == ((r * KK + k) & 31)) s_part[warp][r * KK + k] = v;
         }
+    __syncthreads();
+    for (int o = threadIdx.x; o < rows * KK; o += 128) {
+        const float v = (s_part[0][o] + s_part[1][o]) + (s_part[2][o] + s_part[3][o]);
+        float* op = out + (n * d.l + i0) * KK + o;
+        if (accumulate) *op += v; else *op = v;
+    }
 }
 
-// T3, one block per (group, tau): 4 reduction phases x 64 filter slots, deterministic shared-memory reduction.
-__global__ void __launch_bounds__(256) k_dgrad_b(const float* __restrict__ ca, const float* __restrict__ cb,
-                                                 const float* __restrict__ sig, const uint8_t* __restrict__ bases, float sgn,
-                                                 float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) {
-    __shared__ float s_red[4][64];
+// T3, one block per (group, tau): 16 reduction phases x 64 filter slots, deterministic shared-memory reduction.
+__global__ void __launch_bounds__(1024) k_dgrad_b(const float* __restrict__ ca, const float* __restrict__ cb,
+                                                  const float* __restrict__ sig, const uint8_t* __restrict__ bases, float sgn,
+                                                  float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) {
+    __shared__ float s_red[16][64];
     const int tau = blockIdx.x, g = blockIdx.y;
     const int m = threadIdx.x & 63, ph = threadIdx.x >> 6;
     float acc = 0.f;
     if (m < d.M) {
-        for (int64_t n = (int64_t)g * d.B; n < (int64_t)(g + 1) * d.B; ++n)
-            for (int p = ph; p < d.c; p += 4) {
-                const float a = ca[(n * d.c + p) * d.M + m], b = cb[(n * d.c + p) * d.M + m];
-                acc += a * sig_at(sig, bases, sgn, n, 4 * p + tau, d) + b * sig_at(sig, bases, sgn, n, 4 * p + d.f_len - 1 - tau, d);
-            }
+        const int total = d.B * d.c;                               // (n_local, p) pairs of the group
+        const int64_t n0 = (int64_t)g * d.B;
+        #pragma unroll 4
+        for (int e = ph; e < total; e += 16) {
+            const int nl = e / d.c, p = e - nl * d.c;
+            const int64_t n = n0 + nl;
+            const float a = ca[(n * d.c + p) * d.M + m], b = cb[(n * d.c + p) * d.M + m];
+            acc += a * sig_at(sig, bases, sgn, n, 4 * p + tau, d) + b * sig_at(sig, bases, sgn, n, 4 * p + d.f_len - 1 - tau, d);
+        }
     }
     s_red[ph][m] = acc;
     __syncthreads();
     if (ph == 0 && m < d.M) {
-        const float v = (s_red[0][m] + s_red[1][m]) + (s_red[2][m] + s_red[3][m]);
+        float v = 0.f;
+        #pragma unroll
+        for (int i = 0; i < 16; ++i) v += s_red[i][m];
         float* o = of + (int64_t)g * out_gs + tau * d.M + m;
         if (out_gs == 0 && d.G > 1) atomicAdd(o, v);
         else if (accumulate) *o += v; else *o = v;
@@ -842,9 +861,10 @@ __global__ void __launch_bounds__(256) k_topq_s(const float* __restrict__ xprev,
         __syncthreads();
         const unsigned int prefix = s_prefix;
         const unsigned int pmask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
-        for (int e = threadIdx.x; e < E; e += blockDim.x) {
-            const unsigned int kk = fkey(s_v[e]);
-            if ((kk & pmask) == prefix) atomicAdd(&hist[(kk >> shift) & 255u], 1u);
+        for (int e0 = 0; e0 < E; e0 += blockDim.x) {
+            const int e = e0 + threadIdx.x;
+            const unsigned int kk = e < E ? fkey(s_v[e]) : 0u;
+            hist_add(hist, e < E && (kk & pmask) == prefix, (kk >> shift) & 255u);
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -945,22 +965,23 @@ __global__ void __launch_bounds__(128) k_tconv_l(const float* __restrict__ x, co
     }
 }
 
-// U3 with the x operand given as lists: one block per (group, k); the group's entries with fil == k are gathered in
-// order (sequence, position) and every thread accumulates a few (a, j) outputs over them.
-__global__ void __launch_bounds__(256) k_fgrad_l(const float* __restrict__ A, const float* __restrict__ x, const int32_t* __restrict__ lcnt,
+// U3 with the x operand given as lists: one block per (k, a, group); the group's entries with fil == k are gathered in
+// order (sequence, position) by the first warp and every thread accumulates one j over them.
+__global__ void __launch_bounds__(128) k_fgrad_l(const float* __restrict__ A, const float* __restrict__ x, const int32_t* __restrict__ lcnt,
                                                  const uint16_t* __restrict__ lidx, const float* __restrict__ lval,
                                                  float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) {
     __shared__ int s_n[256], s_i[256];
     __shared__ float s_v[256];
     __shared__ int s_cnt, s_dense;
-    const int k = blockIdx.x, g = blockIdx.y;
+    const int k = blockIdx.x, a = blockIdx.y, g = blockIdx.z;
     if (threadIdx.x == 0) { s_cnt = 0; s_dense = 0; }
     __syncthreads();
     if (threadIdx.x < 32) {                      // one warp gathers in order
         int cnt = 0;
+        int c_all = threadIdx.x < d.B ? lcnt[(int64_t)g * d.B + threadIdx.x] : 0;       // B <= 32 counts in one load
         for (int b = 0; b < d.B; ++b) {
             const int64_t n = (int64_t)g * d.B + b;
-            const int c = lcnt[n];
+            const int c = d.B <= 32 ? __shfl_sync(FULLMASK, c_all, b) : lcnt[n];
             if (c > LIST_CAP) { if (threadIdx.x == 0) s_dense = 1; break; }
             for (int q0 = 0; q0 < c; q0 += 32) {
                 const int q = q0 + threadIdx.x;
@@ -977,27 +998,24 @@ __global__ void __launch_bounds__(256) k_fgrad_l(const float* __restrict__ A, co
         if (threadIdx.x == 0) { s_cnt = cnt; if (cnt > 256) s_dense = 1; }
     }
     __syncthreads();
-    const int HJ = d.h * d.M2;
     if (!s_dense) {
         const int cnt = s_cnt;
-        for (int o = threadIdx.x; o < HJ; o += blockDim.x) {
-            const int a = o / d.M2, j = o - a * d.M2;
+        for (int j = threadIdx.x; j < d.M2; j += blockDim.x) {
             float acc = 0.f;
             for (int q = 0; q < cnt; ++q) acc += s_v[q] * A[((int64_t)s_n[q] * d.c + a + s_i[q]) * d.M2 + j];
-            float* op = of + (int64_t)g * out_gs + (int64_t)o * d.K + k;
+            float* op = of + (int64_t)g * out_gs + ((int64_t)a * d.M2 + j) * d.K + k;
             if (out_gs == 0 && d.G > 1) atomicAdd(op, acc);
             else if (accumulate) *op += acc; else *op = acc;
         }
     } else {
-        for (int o = threadIdx.x; o < HJ; o += blockDim.x) {
-            const int a = o / d.M2, j = o - a * d.M2;
+        for (int j = threadIdx.x; j < d.M2; j += blockDim.x) {
             float acc = 0.f;
             for (int64_t n = (int64_t)g * d.B; n < (int64_t)(g + 1) * d.B; ++n)
                 for (int i = 0; i < d.l; ++i) {
                     const float xv = x[(n * d.l + i) * d.K + k];
                     if (xv != 0.f) acc += xv * A[(n * d.c + a + i) * d.M2 + j];
                 }
-            float* op = of + (int64_t)g * out_gs + (int64_t)o * d.K + k;
+            float* op = of + (int64_t)g * out_gs + ((int64_t)a * d.M2 + j) * d.K + k;
             if (out_gs == 0 && d.G > 1) atomicAdd(op, acc);
             else if (accumulate) *op += acc; else *op = acc;
         }
@@ -1044,9 +1062,10 @@ __global__ void __launch_bounds__(1024) k_mask_scale_s(const float* __restrict__
             const unsigned int prefix = s_prefix;
             const unsigned int pmask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
             if (in_smem) {
-                for (unsigned e = threadIdx.x; e < npos; e += blockDim.x) {
-                    const unsigned int b = __float_as_uint(s_pos[e]);
-                    if ((b & pmask) == prefix) atomicAdd(&hist[(b >> shift) & 255u], 1u);
+                for (unsigned e0 = 0; e0 < npos; e0 += blockDim.x) {
+                    const unsigned e = e0 + threadIdx.x;
+                    const unsigned int b = e < npos ? __float_as_uint(s_pos[e]) : 0u;
+                    hist_add(hist, e < npos && (b & pmask) == prefix, (b >> shift) & 255u);
                 }
             } else {
                 for (int64_t e = threadIdx.x; e < 2 * EZ; e += blockDim.x) {
