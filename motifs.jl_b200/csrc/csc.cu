@@ -143,7 +143,7 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         else k_corr2d<<<nblk(nX, 128), 128, 0, q>>>(A, filt, gs, out, acc, d);
     };
     auto run_dgrad = [=](const float* ca, const float* cb, const float* sig, float sgn, float* of, int64_t ogs, int acc, cudaStream_t q) {
-        if (fastM) k_dgrad_b<<<dim3(d.f_len, d.G), 1024, 0, q>>>(ca, cb, sig, S->bases, sgn, of, ogs, acc, d);
+        if (fastM) k_dgrad_c<<<dim3(d.f_len * CL, d.G), 256, 0, q>>>(ca, cb, sig, S->bases, sgn, of, ogs, acc, d);
         else k_dgrad<<<dim3(nblk(nD, 128), d.G), 128, 0, q>>>(ca, cb, sig, S->bases, sgn, of, ogs, acc, d);
     };
     auto run_tconv = [=](const float* x, int L, const float* filt, int64_t gs, float* out, int acc, cudaStream_t q) {
@@ -206,11 +206,11 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
                      },
                      nm});
     };
-    const int mask_cap = (int)std::min<int64_t>(2 * (int64_t)d.B * d.c * d.M, 49152);
+    const int mask_cap = 2 * ((d.B * d.c + CL - 1) / CL) * d.M;      // floats of dynamic smem per CTA: its slice of rows, z and y
     s->mask_cap = mask_cap;
     auto op_mask_scale = [&](Buf z, Buf y, Buf zy, const char* nm) {
         Buf med = B.alloc(d.G);
-        T.push_back({[=](cudaStream_t q) { k_mask_scale_s<<<d.G, 1024, (size_t)mask_cap * 4, q>>>(S->data + z.off, S->data + y.off, S->data + zy.off, S->data + med.off, mask_cap, d); },
+        T.push_back({[=](cudaStream_t q) { k_mask_scale_c<<<d.G * CL, 512, (size_t)mask_cap * 4, q>>>(S->data + z.off, S->data + y.off, S->data + zy.off, S->data + med.off, d); },
                      [=](cudaStream_t q) { k_mask_scale_bwd<<<nblk(nZY, 256), 256, 0, q>>>(S->data + z.off, S->data + y.off, S->data + med.off, S->grad + zy.off, S->grad + z.off, S->grad + y.off, d); },
                      nm});
     };
@@ -356,7 +356,7 @@ static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
     MB_CUDA(ctx, cudaMalloc(&s->lidx, (size_t)std::max(1, s->n_lists) * s->d.NS * LIST_CAP * 2));
     MB_CUDA(ctx, cudaMalloc(&s->lval, (size_t)std::max(1, s->n_lists) * s->d.NS * LIST_CAP * 4));
     MB_CUDA(ctx, cudaMemset(s->lcnt, 0, (size_t)std::max(1, s->n_lists) * s->d.NS * 4));
-    MB_CUDA(ctx, cudaFuncSetAttribute(k_mask_scale_s, cudaFuncAttributeMaxDynamicSharedMemorySize, s->mask_cap * 4));
+    MB_CUDA(ctx, cudaFuncSetAttribute(k_mask_scale_c, cudaFuncAttributeMaxDynamicSharedMemorySize, s->mask_cap * 4));
     MB_CUDA(ctx, cudaFuncSetAttribute(k_topq_s, cudaFuncAttributeMaxDynamicSharedMemorySize, s->d.l * s->d.K * 4));
     MB_CUDA(ctx, cudaMalloc(&s->bases, (size_t)s->d.NS * s->d.Lb));
     MB_CUDA(ctx, cudaMalloc(&s->idx_dev, (size_t)s->d.NS * 8));
@@ -372,6 +372,7 @@ extern "C" int32_t mb200_csc_create(mb200_ctx* ctx, const mb200_hparams* hp, int
         MB_FAIL(ctx, MB200_E_INVALID, "csc: bad hyper-parameters");
     const int64_t c = Lb - hp->filter_len + 1, l = c - hp->h + 1;
     if ((int64_t)l * hp->K * 4 > 200 * 1024 || (int64_t)l * hp->K > 65535) MB_FAIL(ctx, MB200_E_UNSUPPORTED, "csc: sequence length %lld too long for the shared-memory top-q", (long long)Lb);
+    if (2 * ((int64_t)hp->batch_size * c / 8 + 1) * hp->M * 4 > 200 * 1024) MB_FAIL(ctx, MB200_E_UNSUPPORTED, "csc: batch x positions too large for the shared-memory median");
     if (l < 1 || (int64_t)l * hp->K < hp->q) MB_FAIL(ctx, MB200_E_INVALID, "csc: sequence length %lld too short for filter_len %d, h %d, q %d", (long long)Lb, hp->filter_len, hp->h, hp->q);
     MB_CUDA(ctx, cudaSetDevice(ctx->device));
     mb200_csc* s = new mb200_csc();

@@ -736,6 +736,30 @@ __global__ void __launch_bounds__(256) k_l1_F(const float* __restrict__ raw, flo
 // =============================================================================================
 #define LIST_CAP 64        // non-zeros kept per sequence in a code list; more -> consumers use their dense path
 
+// warp-parallel search of the radix bin that contains ascending rank `rank` in a 256-bin histogram.
+// Call with the 32 lanes of one warp; returns (bin, count below the bin) to every lane.
+__device__ __forceinline__ void find_bin(const unsigned int* hist, unsigned int rank, int* bin_out, unsigned int* below_out) {
+    const int lane = threadIdx.x & 31;
+    unsigned int h[8], s = 0;
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) { h[i] = hist[lane * 8 + i]; s += h[i]; }
+    unsigned int inc = s;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(FULLMASK, inc, o); if (lane >= o) inc += y; }
+    const unsigned int exc = inc - s;
+    const unsigned hitmask = __ballot_sync(FULLMASK, inc > rank);
+    const int owner = __ffs(hitmask) - 1;                          // first lane whose cumulative count exceeds rank
+    int bin = 0; unsigned int below = 0;
+    if (lane == owner) {
+        unsigned int c0 = exc; int b = 0;
+        #pragma unroll
+        for (; b < 8; ++b) { if (c0 + h[b] > rank) break; c0 += h[b]; }
+        bin = lane * 8 + b; below = c0;
+    }
+    *bin_out = __shfl_sync(FULLMASK, bin, owner);
+    *below_out = __shfl_sync(FULLMASK, below, owner);
+}
+
 // histogram increment with intra-warp aggregation: lanes that hit the same bin elect one leader (values of one
 // group/sequence share their leading bytes, so plain shared-memory atomics would serialise on one bin)
 __device__ __forceinline__ void hist_add(unsigned int* hist, bool active, unsigned int bin) {
@@ -867,10 +891,11 @@ __global__ void __launch_bounds__(256) k_topq_s(const float* __restrict__ xprev,
             hist_add(hist, e < E && (kk & pmask) == prefix, (kk >> shift) & 255u);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned int r = s_rank, c0 = 0; int bin = 0;
-            for (; bin < 256; ++bin) { if (c0 + hist[bin] > r) break; c0 += hist[bin]; }
-            s_rank = r - c0; s_prefix = prefix | ((unsigned int)bin << shift);
+        if (threadIdx.x < 32) {
+            int bin; unsigned int below;
+            find_bin(hist, s_rank, &bin, &below);
+            __syncwarp();
+            if (threadIdx.x == 0) { s_rank -= below; s_prefix = prefix | ((unsigned int)bin << shift); }
         }
         __syncthreads();
     }
@@ -1074,10 +1099,11 @@ __global__ void __launch_bounds__(1024) k_mask_scale_s(const float* __restrict__
                 }
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                unsigned int r = s_rank, c0 = 0; int bin = 0;
-                for (; bin < 256; ++bin) { if (c0 + hist[bin] > r) break; c0 += hist[bin]; }
-                s_rank = r - c0; s_prefix = prefix | ((unsigned int)bin << shift);
+            if (threadIdx.x < 32) {
+                int bin; unsigned int below;
+                find_bin(hist, s_rank, &bin, &below);
+                __syncwarp();
+                if (threadIdx.x == 0) { s_rank -= below; s_prefix = prefix | ((unsigned int)bin << shift); }
             }
             __syncthreads();
         }
@@ -1115,4 +1141,157 @@ __global__ void __launch_bounds__(1024) k_mask_scale_s(const float* __restrict__
             og[(int64_t)np * d.M2 + m] = vz >= med ? d.mf * vz : 0.f;
             og[(int64_t)np * d.M2 + d.M + m] = vy >= med ? d.mf * vy : 0.f;
         }
+}
+
+// =============================================================================================
+// Thread-block-cluster variants: 8 CTAs cooperate through distributed shared memory (DSMEM), so that a reduction
+// that used to run on one SM spreads over 8 while staying ONE launch with a fixed (deterministic) summation order.
+// =============================================================================================
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+#define CL 8
+
+// T3 on a cluster: CTA r of the cluster reduces slice r of the group's (sequence, position) pairs; the 8 partial rows
+// land in CTA 0's shared memory and are summed there in rank order.
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256) k_dgrad_c(const float* __restrict__ ca, const float* __restrict__ cb,
+                                                                            const float* __restrict__ sig, const uint8_t* __restrict__ bases, float sgn,
+                                                                            float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) {
+    __shared__ float s_red[4][64];
+    __shared__ float s_all[CL][64];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int r = (int)cluster.block_rank();
+    const int tau = blockIdx.x / CL, g = blockIdx.y;
+    const int m = threadIdx.x & 63, ph = threadIdx.x >> 6;
+    const int total = d.B * d.c;
+    const int per = (total + CL - 1) / CL;
+    const int e_lo = r * per, e_hi = min(total, e_lo + per);
+    float acc = 0.f;
+    if (m < d.M) {
+        const int64_t n0 = (int64_t)g * d.B;
+        #pragma unroll 4
+        for (int e = e_lo + ph; e < e_hi; e += 4) {
+            const int nl = e / d.c, p = e - nl * d.c;
+            const int64_t n = n0 + nl;
+            const float a = ca[(n * d.c + p) * d.M + m], b = cb[(n * d.c + p) * d.M + m];
+            acc += a * sig_at(sig, bases, sgn, n, 4 * p + tau, d) + b * sig_at(sig, bases, sgn, n, 4 * p + d.f_len - 1 - tau, d);
+        }
+    }
+    s_red[ph][m] = acc;
+    __syncthreads();
+    if (ph == 0) {
+        float* dst = cluster.map_shared_rank(&s_all[0][0], 0);
+        dst[r * 64 + m] = (s_red[0][m] + s_red[1][m]) + (s_red[2][m] + s_red[3][m]);
+    }
+    cluster.sync();
+    if (r == 0 && ph == 0 && m < d.M) {
+        float v = 0.f;
+        #pragma unroll
+        for (int i = 0; i < CL; ++i) v += s_all[i][m];
+        float* o = of + (int64_t)g * out_gs + tau * d.M + m;
+        if (out_gs == 0 && d.G > 1) atomicAdd(o, v);
+        else if (accumulate) *o += v; else *o = v;
+    }
+}
+
+// A4 on a cluster: every CTA compacts the positive entries of its slice of rows into its own shared memory; the radix
+// histograms are combined in CTA 0 through DSMEM atomics; the mask is applied by all 8 CTAs.
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(512) k_mask_scale_c(const float* __restrict__ z, const float* __restrict__ y,
+                                                                                 float* __restrict__ zy, float* __restrict__ med_out, CscDims d) {
+    extern __shared__ float s_pos[];
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned int ghist[256];           // meaningful in CTA 0
+    __shared__ unsigned int ctl[8];               // CTA 0: [0] prefix, [1] rank, [2] total positives, [3] count <= v1, [4] min bits > v1
+    __shared__ unsigned int s_lcnt, s_b0, s_b1;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int r = (int)cluster.block_rank();
+    const int g = blockIdx.x / CL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int rows_total = d.B * d.c;
+    const int R = (rows_total + CL - 1) / CL;
+    const int row0 = min(rows_total, r * R), row1 = min(rows_total, row0 + R);
+    const float* zg = z + ((int64_t)g * rows_total + row0) * d.M;
+    const float* yg = y + ((int64_t)g * rows_total + row0) * d.M;
+    const int EZ = (row1 - row0) * d.M;
+    unsigned int* ghist0 = cluster.map_shared_rank(ghist, 0);
+    unsigned int* ctl0 = cluster.map_shared_rank(ctl, 0);
+    if (threadIdx.x == 0) s_lcnt = 0;
+    if (r == 0) { if (threadIdx.x < 256) ghist[threadIdx.x] = 0; if (threadIdx.x < 8) ctl[threadIdx.x] = threadIdx.x == 4 ? 0x7f800000u : 0u; }
+    __syncthreads();
+    // 1. compact local positives
+    for (int e0 = 0; e0 < 2 * EZ; e0 += blockDim.x) {
+        const int e = e0 + threadIdx.x;
+        float v = 0.f;
+        if (e < EZ) v = zg[e]; else if (e < 2 * EZ) v = yg[e - EZ];
+        const bool pos = v > 0.f;
+        const unsigned mk = __ballot_sync(FULLMASK, pos);
+        unsigned base = 0;
+        if (lane == 0 && mk) base = atomicAdd(&s_lcnt, __popc(mk));
+        base = __shfl_sync(FULLMASK, base, 0);
+        if (pos) s_pos[base + __popc(mk & ((1u << lane) - 1u))] = v;
+    }
+    __syncthreads();
+    const unsigned int lpos = s_lcnt;
+    cluster.sync();                                              // CTA 0's control block is initialised
+    if (threadIdx.x == 0 && lpos) atomicAdd(&ctl0[2], lpos);
+    cluster.sync();
+    if (threadIdx.x == 0) s_b0 = ctl0[2];
+    __syncthreads();
+    const unsigned int npos = s_b0;
+    float med = -INFINITY;
+    if (npos > 0) {                                              // cluster-uniform
+        const unsigned int k1 = (npos & 1u) ? npos / 2 : npos / 2 - 1;
+        if (r == 0 && threadIdx.x == 0) { ctl[0] = 0; ctl[1] = k1; }
+        unsigned int prefix = 0;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+            __syncthreads();
+            const unsigned int pmask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+            for (unsigned e0 = 0; e0 < lpos; e0 += blockDim.x) {
+                const unsigned e = e0 + threadIdx.x;
+                const unsigned int b = e < lpos ? __float_as_uint(s_pos[e]) : 0u;
+                hist_add(hist, e < lpos && (b & pmask) == prefix, (b >> shift) & 255u);
+            }
+            __syncthreads();
+            if (threadIdx.x < 256 && hist[threadIdx.x]) atomicAdd(&ghist0[threadIdx.x], hist[threadIdx.x]);
+            cluster.sync();
+            if (r == 0) {
+                if (threadIdx.x < 32) {
+                    int bin; unsigned int below;
+                    find_bin(ghist, ctl[1], &bin, &below);
+                    __syncwarp();
+                    if (threadIdx.x == 0) { ctl[1] -= below; ctl[0] = prefix | ((unsigned int)bin << shift); }
+                }
+                __syncthreads();
+                if (threadIdx.x < 256) ghist[threadIdx.x] = 0;
+            }
+            cluster.sync();
+            if (threadIdx.x == 0) s_b0 = ctl0[0];
+            __syncthreads();
+            prefix = s_b0;
+        }
+        const float v1 = __uint_as_float(prefix);
+        if (npos & 1u) med = v1;
+        else {
+            unsigned int le = 0, mn = 0x7f800000u;
+            for (unsigned e = threadIdx.x; e < lpos; e += blockDim.x) { const float v = s_pos[e]; if (v <= v1) ++le; else mn = min(mn, __float_as_uint(v)); }
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { le += __shfl_xor_sync(FULLMASK, le, o); mn = min(mn, __shfl_xor_sync(FULLMASK, mn, o)); }
+            if (lane == 0) { if (le) atomicAdd(&ctl0[3], le); atomicMin(&ctl0[4], mn); }
+            cluster.sync();
+            if (threadIdx.x == 0) { s_b0 = ctl0[3]; s_b1 = ctl0[4]; }
+            __syncthreads();
+            const float v2 = (s_b0 >= k1 + 2) ? v1 : __uint_as_float(s_b1);
+            med = v1 * 0.5f + v2 * 0.5f;                         // Statistics.middle(a, b) = a/2 + b/2
+        }
+    }
+    if (r == 0 && threadIdx.x == 0) med_out[g] = med;
+    // 2. apply on the CTA's rows: lanes over m
+    float* og = zy + ((int64_t)g * rows_total + row0) * d.M2;
+    for (int np = warp; np < row1 - row0; np += nw)
+        for (int m = lane; m < d.M; m += 32) {
+            const float vz = zg[(int64_t)np * d.M + m], vy = yg[(int64_t)np * d.M + m];
+            og[(int64_t)np * d.M2 + m] = vz >= med ? d.mf * vz : 0.f;
+            og[(int64_t)np * d.M2 + d.M + m] = vy >= med ? d.mf * vy : 0.f;
+        }
+    cluster.sync();                                              // CTA 0's shared memory must outlive every remote access
 }
