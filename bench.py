@@ -6,11 +6,14 @@
       bench.py --gpus N --steps K --warmup W
   python bench.py --impl reference ...     # the CPU restatement of the reference on the host cores
 
-Workload (config.workload): BASELINE.json configs[3], the scan sweep — 500 PWMs (len 8-40) over 10M x 200 bp
-(2 Gbp), forward + reverse strands, fused threshold, per-motif occurrence counts.  A "step" is one pass of the
-scan over all sequences.  At N>1 the 10M sequences are sharded over ranks (strong scaling: total work fixed),
-no data-path collective; the per-motif counts are summed once per step with one NCCL all_reduce.
-Inputs are larger than L2 (0.5 GB packed, 4 KB of masks per 32 positions), so no explicit L2 flush is needed.
+BASELINE.json's metric has two halves and the line carries both:
+  * top level  — scanned bp/s on configs[3], the scan sweep: 500 PWMs (len 8-40) over 10M x 200 bp (2 Gbp), forward +
+    reverse strands, fused threshold, per-motif occurrence counts.  A "step" is one pass of the scan over all sequences.
+    At N>1 the sequences are sharded over ranks (strong scaling: total work fixed), no data-path collective; the per-motif
+    counts are summed once per step with one NCCL all_reduce.  Inputs exceed L2 (0.5 GB packed), no flush needed.
+  * "training" — training sequences/s on configs[1] (20k x 100 bp, batch 6 per rank, AdaBelief): optimiser steps of the
+    unrolled CSC network (forward + hand-derived reverse pass + update), one all_reduce of the 30 433 gradients per step
+    at N>1 (weak scaling: every rank adds a batch of 6).
 """
 import argparse
 import json
@@ -32,10 +35,14 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="both", choices=["both", "scan", "train"])
     ap.add_argument("--nseq", type=int, default=10_000_000)
     ap.add_argument("--seqlen", type=int, default=200)
     ap.add_argument("--motifs", type=int, default=500)
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--train-nseq", type=int, default=20_000)
+    ap.add_argument("--train-seqlen", type=int, default=100)
+    ap.add_argument("--train-steps", type=int, default=1500, help="optimiser steps per timed bench step")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of each cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -74,6 +81,16 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# scan half
+# ------------------------------------------------------------------------------------------------------------------
 def make_motifs(K, seed=4):
     from motifs_jl_b200 import synth
     ms = synth.motifs_from_count_matrices(synth.random_count_matrices(K, 8, 40, seed))
@@ -83,6 +100,23 @@ def make_motifs(K, seed=4):
 def cells_per_seq(lens, Lb):
     lens = np.asarray(lens, np.int64)
     return int(2 * ((Lb - lens + 1).clip(min=0) * lens).sum())
+
+
+def scan_config(args, **extra):
+    c = {"workload": f"scan sweep: {args.motifs} PWMs (len 8-40) x {args.nseq} seqs x {args.seqlen} bp, fwd+rc, fused threshold, counts",
+         "baseline_config_index": 3, "n_seqs": args.nseq, "seq_len": args.seqlen, "n_motifs": args.motifs,
+         "thresholds": "0.7 x max score (Float16)", "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"seq-shard x{args.gpus}"}
+    c.update(extra)
+    return c
+
+
+def train_config(args, world, **extra):
+    c = {"workload": f"CSC training: {args.train_nseq} seqs x {args.train_seqlen} bp (planted gapped motif), batch 6 per rank, "
+                     f"M=50 K=24 h=12 q=32, 6 XYZ + 3 DF passes, AdaBelief",
+         "baseline_config_index": 1, "n_seqs": args.train_nseq, "seq_len": args.train_seqlen, "global_batch": 6 * world,
+         "optimizer_steps_per_bench_step": args.train_steps, "parallelism": f"dp{world}", "l2": "working set (<20 MB) is L2 resident by design"}
+    c.update(extra)
+    return c
 
 
 def cpu_scan_rate(pw, lens, thr, ascii_rows, target_s):
@@ -101,76 +135,39 @@ def cpu_scan_rate(pw, lens, thr, ascii_rows, target_s):
     return n * codes.shape[1] / dt, n, cores, dt
 
 
-def run_reference(args):
-    """--impl reference: the reference cannot run here (Julia absent, CuArray-typed), so this arm times the
-    oracle's CPU restatement of the same path on the host cores."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    from motifs_jl_b200 import synth
-    from oracle import scan_oracle as so
-    ms, thr = make_motifs(args.motifs)
-    pw, lens = so.pack_pwms(ms.pwms)
-    per_step_target = max(2.0, min(args.cpu_seconds, 60.0 / max(1, args.steps + args.warmup)))
-    sample = synth.random_ascii(min(args.nseq, 20000), args.seqlen, 4)
-    rate0, n, cores, dt = cpu_scan_rate(pw, lens, thr, sample, per_step_target)
-    times = []
-    codes = so.ascii_to_codes(sample[:n])
-    for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        so.scan(pw, lens, codes, thr, want_hits=False)
-        if i >= args.warmup:
-            times.append(time.perf_counter() - t0)
-    ms_step = 1e3 * float(np.mean(times))
-    value = n * args.seqlen / (ms_step / 1e3)
-    out = {"impl": "reference", "metric": "scanned_bp_per_sec", "value": value, "unit": "bp/s", "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-           "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-           "config": workload_config(args, sample_seqs=n),
-           "cpu_baseline": {"value": value, "unit": "bp/s", "cores": cores, "kind": "port",
-                            "sample": f"{n} of {args.nseq} sequences x {args.seqlen} bp, all {args.motifs} PWMs, both strands, per step"},
-           "e2e": {"value": value, "unit": "bp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
-
-
-def workload_config(args, **extra):
-    c = {"workload": f"scan sweep: {args.motifs} PWMs (len 8-40) x {args.nseq} seqs x {args.seqlen} bp, fwd+rc, fused threshold, counts",
-         "baseline_config_index": 3, "n_seqs": args.nseq, "seq_len": args.seqlen, "n_motifs": args.motifs,
-         "thresholds": "0.7 x max score (Float16)", "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"seq-shard x{args.gpus}"}
-    c.update(extra)
-    return c
-
-
-def main():
-    args = parse()
-    if args.impl == "reference":
-        return run_reference(args)
-
+def cpu_train_rate(ascii_rows, flat, target_s):
+    """oracle (PyTorch-CPU position-space restatement + autograd) loss/gradient/AdaBelief steps on the host cores."""
     import torch
-    import torch.distributed as dist
-    import motifs_jl_b200 as mb
-    from oracle import scan_oracle as so   # only for the cpu_baseline leg (rank 0, N=1)
+    from oracle import csc_oracle as co, scan_oracle as so
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    hp = co.Hyperparam()
+    codes = so.ascii_to_codes(ascii_rows)
+    n = co.n_params(hp)
+    p = flat.astype(np.float32).copy()
+    mt, st = np.zeros(n), np.zeros(n)
+    rng = np.random.default_rng(0)
+    steps, t0 = 0, time.perf_counter()
+    while True:
+        idx = rng.permutation(len(codes))[:hp.batch_size]
+        _, g, _ = co.loss_and_grad(codes[idx], p, hp)
+        pn, mt, st = co.adabelief_step(p[:n].astype(np.float64), g[:n].astype(np.float64), mt, st, t=steps + 1)
+        p[:n] = pn.astype(np.float32)
+        steps += 1
+        dt = time.perf_counter() - t0
+        if dt >= target_s or steps >= 400:
+            break
+    return hp.batch_size * steps / dt, steps, cores, dt
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
-    ctx = mb.Context(local)
-    stream = torch.cuda.current_stream()
-    ctx.set_stream(stream.cuda_stream)
 
+def bench_scan(args, ctx, torch, dist, world, rank, local, dev, stream):
+    import motifs_jl_b200 as mb  # noqa: F401
+    from oracle import scan_oracle as so                                     # cpu_baseline leg + pwm layout helper only
     K, Lb = args.motifs, args.seqlen
-    n_lo = args.nseq * rank // world
-    n_hi = args.nseq * (rank + 1) // world
+    n_lo, n_hi = args.nseq * rank // world, args.nseq * (rank + 1) // world
     n_local = n_hi - n_lo
     ms, thr = make_motifs(K)
-    pw, lens = so.pack_pwms(ms.pwms)        # layout helper only (numpy)
-
-    # synthetic sequences: iid uniform bases generated on the device, then an ASCII copy in pinned host memory
+    pw, lens = so.pack_pwms(ms.pwms)
     g = torch.Generator(device=dev)
     g.manual_seed(4 + 1000 * rank)
     lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
@@ -184,26 +181,24 @@ def main():
     torch.cuda.synchronize()
     seqs = ctx.seqs_from_device_ptr(ascii_dev.data_ptr(), n_local, Lb)
     del ascii_dev
-
     counts_dev = torch.zeros((K, 4), dtype=torch.int64, device=dev)
 
-    def step_resident():
-        _, c = ctx.scan(seqs, pw, lens, thr, want_hits=False, want_counts=True)
+    def reduce_counts(c):
         if world > 1:
             counts_dev.copy_(torch.from_numpy(c))
             dist.all_reduce(counts_dev)
             return counts_dev.cpu().numpy()
         return c
+
+    def step_resident():
+        _, c = ctx.scan(seqs, pw, lens, thr, want_hits=False, want_counts=True)
+        return reduce_counts(c)
 
     def step_e2e():
         s2 = ctx.seqs_from_host_ptr(ascii_host.data_ptr(), n_local, Lb)     # H2D of this step's input + pack
         _, c = ctx.scan(s2, pw, lens, thr, want_hits=False, want_counts=True)
         s2.free()
-        if world > 1:
-            counts_dev.copy_(torch.from_numpy(c))
-            dist.all_reduce(counts_dev)
-            return counts_dev.cpu().numpy()
-        return c
+        return reduce_counts(c)
 
     def barrier():
         if world > 1:
@@ -216,8 +211,7 @@ def main():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_scan = t_cnt = 0.0
-        n_launch = 0
-        nk = 0
+        n_launch = nk = 0
         e0.record(stream)
         for _ in range(steps):
             res = fn()
@@ -226,8 +220,7 @@ def main():
             n_launch += sum(l.values())
         e1.record(stream)
         barrier()
-        ms_total = e0.elapsed_time(e1)
-        tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item()) / steps, res, t_scan, t_cnt, nk, n_launch
@@ -239,54 +232,205 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, counts2, *_ = timed(step_e2e, max(1, args.steps), 1)
     assert np.array_equal(counts, counts2)
-
     total_bp = args.nseq * Lb
-    value = total_bp / (ms_step / 1e3)
-    e2e = total_bp / (ms_e2e / 1e3)
-
     out = None
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
+        peaks = load_peaks()
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        # dominant kernel: scan_kernel.  Algorithmic bytes per launch = packed sequence bytes of the batch (0.25 B/bp)
-        # + the PWM tables once; cells = table look-up-adds (the binding resource, 2 B of smem each).
+        # dominant kernel: scan_kernel.  Algorithmic bytes per launch = packed sequence bytes of the batch (0.25 B/bp) + the PWM
+        # tables once; cells = table look-up-adds (the binding resource, 2 B of shared memory each).
         launches_per_step = n_scan_launch / args.steps
         bytes_per_launch = (n_local * Lb / 4.0) / launches_per_step + float(2 * 4 * lens.sum() * 2)
         ms_per_launch = t_scan / max(1, n_scan_launch)
         ach = bytes_per_launch / (ms_per_launch * 1e-3) / 1e9
-        cells_step = cells_per_seq(lens, Lb) * n_local
-        cells_rate = cells_step / ((t_scan / args.steps) * 1e-3)
+        cells_rate = cells_per_seq(lens, Lb) * n_local / ((t_scan / args.steps) * 1e-3)
         sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
-        smem_peak = 148 * 128 * sm_mhz * 1e6                                 # B/s of shared-memory read bandwidth
-        out = {"metric": "scanned_bp_per_sec", "value": value, "unit": "bp/s", "n_gpus": world, "steps": args.steps,
+        smem_peak = 148 * 128 * sm_mhz * 1e6
+        out = {"metric": "scanned_bp_per_sec", "value": total_bp / (ms_step / 1e3), "unit": "bp/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-               "dtype": "f16", "data": "synthetic", "config": workload_config(args),
-               "e2e": {"value": e2e, "unit": "bp/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(n_local * Lb + pw.nbytes + lens.nbytes + 2 * K),
-                       "d2h_bytes_per_step": int(K * 4 * 8)},
-               "gpu_launches": int(n_launch),
-               "clocks": clocks,
+               "dtype": "f16", "data": "synthetic", "config": scan_config(args),
+               "e2e": {"value": total_bp / (ms_e2e / 1e3), "unit": "bp/s", "ms_per_step": ms_e2e,
+                       "h2d_bytes_per_step": int(n_local * Lb + pw.nbytes + lens.nbytes + 2 * K), "d2h_bytes_per_step": int(K * 4 * 8)},
+               "gpu_launches": int(n_launch), "clocks": clocks,
                "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
-                            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                            "kernel": "scan_kernel", "ms_per_launch": ms_per_launch, "kernel_share_of_step": (t_scan / args.steps) / ms_step,
+                            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "kernel": "scan_kernel",
+                            "ms_per_launch": ms_per_launch, "kernel_share_of_step": (t_scan / args.steps) / ms_step,
                             "count_kernel_share_of_step": (t_cnt / args.steps) / ms_step,
+                            "note": "2-bit packing makes the scan table-lookup bound, not HBM bound (SURVEY §8d): see binding",
                             "binding": {"bound": "smem-gather", "what": "2 B shared-memory table read + 1 Float16 add per PWM cell",
                                         "cells_per_s": cells_rate, "achieved": cells_rate * 2 / 1e9, "peak": smem_peak / 1e9, "unit": "GB/s",
-                                        "frac": cells_rate * 2 / smem_peak, "peak_source": "148 SM x 128 B/clk x measured SM clock"}},
+                                        "frac": cells_rate * 2 / smem_peak, "peak_source": "148 SM x 128 B/clk x SM clock under load"}},
                "checks": {"counts_sum": [int(x) for x in counts.sum(axis=0)]}}
         if world == 1 and not args.no_cpu_baseline:
             sample = ascii_host[: min(n_local, 20000)].numpy()
             rate, n, cores, dt = cpu_scan_rate(pw, lens, thr, sample, args.cpu_seconds)
             out["cpu_baseline"] = {"value": rate, "unit": "bp/s", "cores": cores, "kind": "port", "seconds": dt,
                                    "sample": f"first {n} of {args.nseq} sequences x {Lb} bp, all {K} PWMs, both strands (oracle/scan_oracle.c, OpenMP)"}
-            # the sample is also a parity check of the full-size run's first sequences
             _, oc = so.scan(pw, lens, so.ascii_to_codes(sample[:n]), thr, want_hits=False)
             s3 = ctx.seqs_from_ascii(sample[:n])
             _, gc = ctx.scan(s3, pw, lens, thr, want_hits=False)
             out["checks"]["sample_counts_match_oracle"] = bool(np.array_equal(oc, gc))
+            s3.free()
+    seqs.free()
+    del ascii_host
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# training half
+# ------------------------------------------------------------------------------------------------------------------
+def bench_train(args, ctx, torch, dist, world, rank, local, dev):
+    from motifs_jl_b200 import model as mdl, parallel, synth
+    from motifs_jl_b200._lib import CscModel
+    hp = mdl.Hyperparam()
+    N, Lb = args.train_nseq, args.train_seqlen
+    a = synth.planted_gapped(N, Lb, 2)
+    n_train = N - int(np.floor((1 - 0.9) * N))                            # loadfasta/helpers.jl:144
+    a = a[:n_train]
+    pinned = torch.from_numpy(a).pin_memory()
+    cdl = mdl.ucdl(hp, np.random.default_rng(2))
+    side = torch.cuda.Stream(device=dev)                                  # library stream; NCCL orders itself against it
+    ctx.set_stream(side.cuda_stream)
+    out = None
+    with torch.cuda.stream(side):
+        seqs = ctx.seqs_from_host_ptr(pinned.data_ptr(), n_train, Lb)
+        model = CscModel(ctx, hp, Lb, n_groups=1)
+        model.set_params(cdl.flat)
+        grad_view = None
+        if world > 1:
+            _, gptr = model.device_ptrs()
+            grad_view = torch.as_tensor(mdl._DevArray(gptr, model.n_total), device=dev)
+        rng = np.random.default_rng(1234)                                 # same permutation stream on every rank
+        per_step = hp.batch_size * world
+        state = {"perm": rng.permutation(n_train), "pos": 0, "loss": None, "l1": None, "launches": 0}
+
+        def opt_step():
+            if state["pos"] + per_step > n_train:
+                state["perm"], state["pos"] = rng.permutation(n_train), 0
+            lo = state["pos"] + rank * hp.batch_size
+            idx = state["perm"][lo: lo + hp.batch_size]
+            state["pos"] += per_step
+            model.step_begin(seqs, idx)                                   # H2D: 6 sequence indices; graph replay of fwd + reverse pass
+            if world > 1:
+                parallel.all_reduce_mean_(grad_view)                      # one NCCL all-reduce of the gradient vector
+            state["loss"], state["l1"] = model.adabelief_step()           # update + D2H of loss and l1(F)
+
+        def bench_step():
+            for _ in range(args.train_steps):
+                opt_step()
+
+        for _ in range(min(args.warmup, 3) * 50):                         # >= 3 warm-up iterations of the step (graph capture included)
+            opt_step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.last_timing()[1]["csc"]
+        e0.record(side)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            bench_step()
+        e1.record(side)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_bench_step = float(tt.item()) / args.steps
+        n_opt = args.steps * args.train_steps
+        if rank == 0:
+            seq_s = hp.batch_size * world * args.train_steps / (ms_bench_step / 1e3)
+            out = {"metric": "training_sequences_per_sec", "value": seq_s, "unit": "seq/s", "n_gpus": world, "steps": args.steps,
+                   "ms_per_step": ms_bench_step, "ms_per_optimizer_step": ms_bench_step / args.train_steps, "higher_is_better": True,
+                   "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": train_config(args, world),
+                   # every optimiser step already goes through the public API with host-side indices in and loss/l1 out
+                   "e2e": {"value": seq_s, "unit": "seq/s", "h2d_bytes_per_step": int(args.train_steps * hp.batch_size * 8),
+                           "d2h_bytes_per_step": int(args.train_steps * 16), "note": "sequences are uploaded once (2 bit/base); a step ships 6 indices"},
+                   "gpu_launches": int(ctx.last_timing()[1]["csc"] - l0) if ctx.last_timing()[1]["csc"] >= l0 else None,
+                   "kernels_per_optimizer_step": None, "final_loss": state["loss"], "final_l1_F": state["l1"],
+                   "wall_s": wall, "optimizer_steps_timed": n_opt}
+            if world == 1 and not args.no_cpu_baseline:
+                rate, steps, cores, dt = cpu_train_rate(a[:2000], cdl.flat, args.cpu_seconds)
+                out["cpu_baseline"] = {"value": rate, "unit": "seq/s", "cores": cores, "kind": "port", "seconds": dt,
+                                       "sample": f"{steps} optimiser steps of batch 6 (oracle/csc_oracle.py, PyTorch-CPU fp32 + autograd, {cores} threads)"}
+        model.free()
+        seqs.free()
+    ctx.set_stream(None)
+    return out
+
+
+def run_reference(args):
+    """--impl reference: the reference cannot run here (Julia absent, CuArray-typed code), so this arm times the oracle's CPU
+    restatement of the same path on the host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from motifs_jl_b200 import model as mdl, synth
+    from oracle import scan_oracle as so
+    ms, thr = make_motifs(args.motifs)
+    pw, lens = so.pack_pwms(ms.pwms)
+    per_step_target = max(2.0, min(args.cpu_seconds, 60.0 / max(1, args.steps + args.warmup)))
+    sample = synth.random_ascii(min(args.nseq, 20000), args.seqlen, 4)
+    _, n, cores, _ = cpu_scan_rate(pw, lens, thr, sample, per_step_target)
+    codes = so.ascii_to_codes(sample[:n])
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        so.scan(pw, lens, codes, thr, want_hits=False)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    ms_step = 1e3 * float(np.mean(times))
+    value = n * args.seqlen / (ms_step / 1e3)
+    out = {"impl": "reference", "metric": "scanned_bp_per_sec", "value": value, "unit": "bp/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": scan_config(args, sample_seqs=n),
+           "cpu_baseline": {"value": value, "unit": "bp/s", "cores": cores, "kind": "port",
+                            "sample": f"{n} of {args.nseq} sequences x {args.seqlen} bp, all {args.motifs} PWMs, both strands, per step"},
+           "e2e": {"value": value, "unit": "bp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    if args.workload in ("both", "train"):
+        a = synth.planted_gapped(2000, args.train_seqlen, 2)
+        cdl = mdl.ucdl(mdl.Hyperparam(), np.random.default_rng(2))
+        rate, steps, cores, dt = cpu_train_rate(a, cdl.flat, min(args.cpu_seconds, 20.0))
+        out["training"] = {"impl": "reference", "metric": "training_sequences_per_sec", "value": rate, "unit": "seq/s",
+                           "config": train_config(args, 1), "higher_is_better": True,
+                           "cpu_baseline": {"value": rate, "unit": "seq/s", "cores": cores, "kind": "port",
+                                            "sample": f"{steps} optimiser steps of batch 6 in {dt:.1f} s (oracle/csc_oracle.py)"},
+                           "e2e": {"value": rate, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    import motifs_jl_b200 as mb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = mb.Context(local)
+    stream = torch.cuda.current_stream()
+    out = None
+    if args.workload in ("both", "scan"):
+        out = bench_scan(args, ctx, torch, dist, world, rank, local, dev, stream)
+    if args.workload in ("both", "train"):
+        tr = bench_train(args, ctx, torch, dist, world, rank, local, dev)
+        if rank == 0:
+            if out is None:
+                out = tr
+                out["warmup"] = args.warmup
+            else:
+                out["training"] = tr
+                out["gpu_launches"] = int(out["gpu_launches"]) + int(tr.get("gpu_launches") or 0)
+    if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

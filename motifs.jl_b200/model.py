@@ -146,10 +146,17 @@ def train_ucdl(data, num_epochs=None, l1_loss_thresh=np.float32(95.0), rng: np.r
     model.set_params(cdl.flat)
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
-    grad_view = None
+    grad_view, stream_cm = None, None
     if world > 1:
+        # the library launches on a torch-owned side stream so that NCCL (which orders itself against torch's current
+        # stream) sees the reverse pass finish before the all-reduce and the optimiser waits for the all-reduce
+        dev = torch.device("cuda", seqs.ctx.device)
+        side = torch.cuda.Stream(device=dev)
+        seqs.ctx.set_stream(side.cuda_stream)
+        stream_cm = torch.cuda.stream(side)
+        stream_cm.__enter__()
         _, gptr = model.device_ptrs()
-        grad_view = torch.as_tensor(_DevArray(gptr, model.n_total), device=torch.device("cuda", seqs.ctx.device))
+        grad_view = torch.as_tensor(_DevArray(gptr, model.n_total), device=dev)
     num_epochs = setup_num_epochs(data.N) if num_epochs is None else num_epochs
     per_step = hp.batch_size * groups_per_rank * world
     steps_per_epoch = data.N // per_step
@@ -161,8 +168,7 @@ def train_ucdl(data, num_epochs=None, l1_loss_thresh=np.float32(95.0), rng: np.r
             idx = perm[lo: lo + hp.batch_size * groups_per_rank]
             model.step_begin(seqs, idx)
             if world > 1:
-                torch.cuda.current_stream().synchronize()
-                parallel.all_reduce_mean_(grad_view)
+                parallel.all_reduce_mean_(grad_view)                     # ONE all-reduce of 30 433 fp32 per step
             loss, l1 = model.adabelief_step()
             step += 1
             if on_step is not None:
@@ -177,6 +183,10 @@ def train_ucdl(data, num_epochs=None, l1_loss_thresh=np.float32(95.0), rng: np.r
         if verbose:
             print(f"Epoch: {epoch} completed")                           # train.jl:55
     cdl.flat[:] = model.get_params()
+    if stream_cm is not None:
+        torch.cuda.current_stream().synchronize()
+        stream_cm.__exit__(None, None, None)
+        seqs.ctx.set_stream(None)
     return cdl, hp, ln, None, model
 
 

@@ -56,3 +56,31 @@ def test_shard_helpers():
             assert cuts[0][0] == 0 and cuts[-1][1] == n
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(w - 1))
     assert parallel.shard_groups(20, 6, 0, 2) == (0, 6) and parallel.shard_groups(20, 6, 1, 2) == (6, 18)
+
+
+def _grad_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from motifs_jl_b200 import parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.arange(30433, dtype=torch.float32) * (rank + 1)
+    parallel.all_reduce_mean_(g)
+    if rank == 0:
+        q.put(bool(torch.allclose(g, torch.arange(30433, dtype=torch.float32) * 1.5)))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_is_a_mean():
+    """the per-step filter-gradient all-reduce averages the ranks' gradient vectors."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+    assert ok
