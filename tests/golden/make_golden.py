@@ -64,3 +64,23 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def csc_golden():
+    """config 1, first batch of 6: loss, gradient and final codes of the default network (position-space oracle, fp32)."""
+    import torch
+    from oracle import csc_oracle as co
+    hp = co.Hyperparam()
+    flat = co.init_params(hp, 1)
+    train, _, _, _ = config1_inputs()
+    codes = so.ascii_to_codes(train[:6])
+    loss, grad, aux = co.loss_and_grad(codes, flat, hp, "pos", torch.float32)
+    recs = co.code_retrieval(so.ascii_to_codes(train[:12]), flat, hp)
+    np.savez_compressed(os.path.join(HERE, "csc_config1.npz"), codes=codes, flat=flat, loss=np.float32(loss), grad=grad,
+                        x=aux["x"].detach().numpy(), z=aux["z"].detach().numpy().astype(np.float32), D=aux["D"].detach().numpy(),
+                        code_records=recs, code_input=so.ascii_to_codes(train[:12]))
+    print("csc: loss", loss, "grad max", np.abs(grad).max(), "codes", len(recs))
+
+
+if __name__ == "__main__":
+    csc_golden()
