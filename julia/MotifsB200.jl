@@ -1,0 +1,110 @@
+# MotifsB200.jl — the `ccall` glue a MOTIFs.jl maintainer adds to route the hot path through libmotifs_b200.so.
+# Julia is not installed in the build image, so this file is exercised only by inspection; the same symbols are bound and
+# tested from Python (motifs.jl_b200/_lib.py, tests/test_abi.py).  Each function replaces the BODY of the reference function
+# named in its comment; signatures and return conventions (1-based, Dict{Int,Vector}) stay the reference's.
+module MotifsB200
+
+const lib = get(ENV, "MOTIFS_B200_LIB", "libmotifs_b200.so")
+
+struct Hit            # mb200_hit (16 bytes)
+    seq::UInt32; pos::UInt32; motif::UInt16; score::Float16; comp::UInt8; p1::UInt8; p2::UInt8; p3::UInt8
+end
+struct Code           # mb200_code (12 bytes)
+    position::UInt16; fil::UInt16; seq::UInt32; mag::Float16; pad::UInt16
+end
+struct HParams        # mb200_hparams = Hyperparam (model.jl:1-14)
+    filter_len::Int32; M::Int32; h::Int32; K::Int32; q::Int32; batch_size::Int32; num_pass_xyz::Int32; num_pass_df::Int32
+    magnifying_factor::Float32; gamma::Float32
+end
+
+const SCAN_FWD, SCAN_RC, SCAN_WANT_HITS, SCAN_WANT_COUNTS = UInt32(1), UInt32(2), UInt32(4), UInt32(8)
+
+check(ctx, rc) = rc == 0 || error("libmotifs_b200 ($rc): " * unsafe_string(ccall((:mb200_last_error, lib), Cstring, (Ptr{Cvoid},), ctx)))
+
+function create(device::Integer=0)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:mb200_create, lib), Int32, (Ref{Ptr{Cvoid}}, Int32), h, device)
+    rc == 0 || error("mb200_create failed ($rc): no B200-class CUDA device")
+    h[]
+end
+destroy(ctx) = ccall((:mb200_destroy, lib), Int32, (Ptr{Cvoid},), ctx)
+
+# replaces the per-batch `cu(float_type_retrieval.(data_matrix[:,1,n:nend]))` uploads (inference/_h3_1_alignment.jl:74) and
+# `S |> gpu` (train.jl:41): the whole one-hot array is packed to 2 bit/base once.  data_matrix is (4L,1,N) or (4L,N) Float32.
+function upload_onehot(ctx, data_matrix::Array{Float32})
+    L4 = size(data_matrix, 1); N = size(data_matrix, ndims(data_matrix))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve data_matrix check(ctx, ccall((:mb200_seqs_from_onehot_f32, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Float32}, Int64, Int64, Ref{Ptr{Cvoid}}), ctx, data_matrix, N, L4 ÷ 4, h))
+    h[]
+end
+free_seqs(ctx, s) = ccall((:mb200_seqs_free, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), ctx, s)
+
+# replaces get_pos_scores_arr + gpu_scan (inference/_h3_1_alignment.jl:57-99).  `pwms` is the (K,4,maxlen) Float16 array the
+# reference builds at :65-69 with rc=false; thresh === nothing gives the reference's "score > 0" scan.
+function gpu_scan(ctx, seqs, pwms::Array{Float16,3}, lens::Vector{Int64}; thresh::Union{Nothing,Vector{Float16}}=nothing,
+                  want_hits=true)
+    K, _, maxlen = size(pwms)
+    counts = zeros(Int64, 4, K)                       # column k = (n_hits, unique starts, union_ranges coverage, true coverage)
+    nhits = Ref{Int64}(0)
+    flags = SCAN_FWD | SCAN_RC | SCAN_WANT_COUNTS | (want_hits ? SCAN_WANT_HITS : UInt32(0))
+    cap = 1 << 16
+    hits = Vector{Hit}(undef, want_hits ? cap : 0)
+    while true
+        rc = GC.@preserve pwms lens hits counts ccall((:mb200_scan, lib), Int32,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float16}, Ptr{Int64}, Int32, Int32, Ptr{Float16}, UInt32, Ptr{Hit}, Int64, Ref{Int64}, Ptr{Int64}),
+            ctx, seqs, pwms, lens, K, maxlen, thresh === nothing ? C_NULL : pointer(thresh), flags,
+            want_hits ? pointer(hits) : C_NULL, want_hits ? cap : 0, nhits, counts)
+        if rc == -5 && want_hits                      # MB200_E_HITS_OVERFLOW: nhits[] is the exact size
+            cap = nhits[]; resize!(hits, cap); continue
+        end
+        check(ctx, rc); break
+    end
+    resize!(hits, want_hits ? nhits[] : 0)
+    # modify_w_found! (:38-52): hits arrive sorted (seq, motif, comp, pos) => per (motif, seq) forward hits then rc hits
+    positions = [Dict{Int,Vector{Int}}() for _ = 1:K]; scores = [Dict{Int,Vector{Float16}}() for _ = 1:K]
+    use_comp = [Dict{Int,Vector{Bool}}() for _ = 1:K]
+    for h in hits
+        m, n = Int(h.motif) + 1, Int(h.seq) + 1
+        push!(get!(positions[m], n, Int[]), Int(h.pos) + 1)
+        push!(get!(scores[m], n, Float16[]), h.score)
+        push!(get!(use_comp[m], n, Bool[]), h.comp != 0)
+    end
+    positions, scores, use_comp, counts
+end
+
+# replaces the loop body of train_ucdl (train.jl:40-52): gradient(ps) do forward_pass_return_loss(...) end ; update! ; l1 test
+function csc_create(ctx, hp::HParams, L::Integer; n_groups=1, forward_only=false)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx, ccall((:mb200_csc_create, lib), Int32, (Ptr{Cvoid}, Ref{HParams}, Int64, Int32, Int32, Ref{Ptr{Cvoid}}),
+                     ctx, hp, L, n_groups, forward_only ? 1 : 0, h))
+    h[]
+end
+# flat = vcat(lambda_sparsity, kappa_sparsity, lambda_stepsize, omega_stepsize, kappa_stepsize, vec(D), vec(F), penalty_xyz, mu,
+#             [lambda_sparsity_warmup, lambda_stepsize_warmup, omega_stepsize_warmup])   — Flux.params(cdl) order + warm-ups
+csc_set_params(ctx, m, flat::Vector{Float32}) = GC.@preserve flat check(ctx, ccall((:mb200_csc_set_params, lib), Int32,
+    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float32}, Int64), ctx, m, flat, length(flat)))
+function csc_get_params(ctx, m, n::Integer)
+    flat = Vector{Float32}(undef, n)
+    GC.@preserve flat check(ctx, ccall((:mb200_csc_get_params, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float32}, Int64), ctx, m, flat, n))
+    flat
+end
+function train_step!(ctx, m, seqs, batch_idx0::Vector{Int64}; eta=1f-3, beta=(0.9f0, 0.999f0), eps=1f-8)
+    GC.@preserve batch_idx0 check(ctx, ccall((:mb200_csc_step_begin, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}),
+                                             ctx, m, seqs, batch_idx0))
+    loss = Ref{Float32}(0); l1 = Ref{Float32}(0)
+    check(ctx, ccall((:mb200_csc_adabelief_step, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Float32, Float32, Float32, Float32, Ref{Float32}, Ref{Float32}),
+                     ctx, m, eta, beta[1], beta[2], eps, loss, l1))
+    loss[], l1[]          # println("loss $(loss[])") keeps the reference's log (model.jl:392); stop when l1 < 95 (train.jl:47-52)
+end
+
+# replaces code_retrieval (inference/_1_code_retrieval.jl:33-56)
+function code_retrieval(ctx, m, seqs, N::Integer, batch_size::Integer)
+    n = N - N % batch_size
+    cap = 64 * n; out = Vector{Code}(undef, cap); cnt = Ref{Int64}(0)
+    GC.@preserve out check(ctx, ccall((:mb200_csc_codes, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ptr{Code}, Int64, Ref{Int64}),
+                                      ctx, m, seqs, 0, n, out, cap, cnt))
+    [(position=c.position + 0x0001, fil=c.fil + 0x0001, seq=c.seq + 0x00000001, mag=c.mag) for c in view(out, 1:cnt[])]
+end
+
+end # module
