@@ -14,30 +14,38 @@
 //   * sequences are 2 bit/base in HBM; a CTA stages a tile of packed words in shared memory with
 //     1-D bulk TMA (cp.async.bulk + mbarrier, double buffered); the window of one start position
 //     is 4 funnel-shifted registers, so the halo is just "read 6 words instead of 2".
-//   * motifs are sorted by length and processed 8 at a time; per (column, base) the table holds
-//     16 halves {k0 fwd, k0 rc, ..., k7 rc} = two LDS.128, feeding 8 HADD2 (one sequential
-//     Float16 add per cell, which is exactly the reference's rounding order).
-//   * threshold compare + warp ballot turn 32 start positions x 16 (motif,strand) into 16 mask
-//     words, stored as one coalesced 64 B line.  Counting and the sorted hit list are derived
-//     from the masks (deterministic, no atomics on the hit path, no sort).
+//   * a lane owns one (motif, strand) "slot" and scores 16 consecutive start positions of one
+//     sequence at a time (8 half2 accumulators); motifs are sorted by length, 16 motifs x 2 strands
+//     per warp pass.  Per PWM column the lane reads ITS 8-byte column {A,C,G,T} once (LDS.64,
+//     conflict free) and a PRMT picks the two entries the position pair needs; the PRMT selectors
+//     depend only on the sequence, are built once per 16-position block and shared by all lanes
+//     and all motif groups.  One HADD2/HFMA2 per two cells = one correctly rounded sequential
+//     Float16 add per cell, exactly the reference's rounding order.  Shared-memory traffic is
+//     0.5 B per cell (a per-lane table gather would need 2 B per cell and is bound by the
+//     128 B/clk/SM shared-memory port: that was v0 of this kernel, profiles/r01_scan_v0_*).
+//   * threshold compare turns 16 positions x 32 slots into 32 half-words of the hit masks.
+//     Counting and the sorted hit list are derived from the masks (deterministic, no atomics on
+//     the hit path, no sort).
 #include "common.cuh"
 #include <algorithm>
 #include <cstring>
 
-#define GROUP_MOTIFS 8
-#define GROUP_SLOTS 16                 // (motif, strand) accumulators per lane
-#define COL_BYTES 128                  // 4 bases x 16 halves
+#define GROUP_MOTIFS 16                // motifs per warp pass
+#define GROUP_SLOTS 32                 // (motif, strand) slots = lanes
+#define COL_BYTES 256                  // 32 slots x {A,C,G,T} halves
+#define POS_BLOCK 16                   // start positions scored per lane and pass (8 half2)
+#define NSEL (POS_BLOCK - 2 + MB200_MAX_MOTIF_LEN + 2)   // selector registers of one position block
 #define SCAN_THREADS 512
 
 struct __align__(16) GroupMeta {
     int32_t len;                       // columns to run (longest motif of the group)
     int32_t tab_off;                   // byte offset of the group's table inside the motif block
-    int32_t npos[GROUP_MOTIFS];        // valid start positions per motif (Lb - len_k + 1, >= 0)
-    uint32_t thr2[GROUP_MOTIFS];       // half2 bits (thr_fwd, thr_rc)
-    int32_t npos_max;                  // max over npos[]: chunks starting at or beyond it have nothing to score
+    int32_t npos_max;                  // max over npos[]: position blocks starting at or beyond it have nothing to score
     int32_t pad;
-};                                     // 80 bytes
-static_assert(sizeof(GroupMeta) == 80, "GroupMeta must be 80 bytes");
+    int32_t npos[GROUP_MOTIFS];        // valid start positions per motif (Lb - len_k + 1, >= 0)
+    uint16_t thr[GROUP_SLOTS];         // Float16 bits per slot: max(thresh, 0), +Inf for a disabled strand / padding
+};                                     // 144 bytes
+static_assert(sizeof(GroupMeta) == 144, "GroupMeta must be 144 bytes");
 
 struct MBlock {
     int64_t blob_off;                  // byte offset of this motif block's blob (tables then metas)
@@ -85,35 +93,18 @@ __device__ __forceinline__ void tma_load(uint32_t dst, const uint8_t* src, uint3
         tma_bulk_g2s(dst + o, src + o, n, bar);
     }
 }
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
-
-// one PWM column for 8 motifs x 2 strands: two 16 B table reads, eight sequential-Float16 adds
-__device__ __forceinline__ void column_step(uint32_t tab_col, uint32_t b32, __half2 (&acc)[8]) {
-    const uint4 v0 = lds128(tab_col + b32);
-    const uint4 v1 = lds128(tab_col + b32 + 16);
-    acc[0] = __hadd2(acc[0], as_h2(v0.x)); acc[1] = __hadd2(acc[1], as_h2(v0.y));
-    acc[2] = __hadd2(acc[2], as_h2(v0.z)); acc[3] = __hadd2(acc[3], as_h2(v0.w));
-    acc[4] = __hadd2(acc[4], as_h2(v1.x)); acc[5] = __hadd2(acc[5], as_h2(v1.y));
-    acc[6] = __hadd2(acc[6], as_h2(v1.z)); acc[7] = __hadd2(acc[7], as_h2(v1.w));
-}
-
-#define SCAN_SEGMENT(XS, J0)                                                            \
-    _Pragma("unroll") for (int jj = 0; jj < 16; ++jj) {                                 \
-        if ((J0) + jj >= len) goto columns_done;                                        \
-        const uint32_t b32 = (((XS) >> (2 * jj)) & 3u) << 5;                            \
-        column_step(tab + ((J0) + jj) * COL_BYTES, b32, acc);                           \
-    }
-
-__device__ __forceinline__ int64_t chunk_word(int64_t gq, int32_t W, int64_t rowwords, int64_t* n_out, int32_t* c_out) {
-    int64_t n = gq / W;
-    int32_t c = (int32_t)(gq - n * W);
-    *n_out = n; *c_out = c;
-    return n * rowwords + 2 * (int64_t)c;
+// first packed word of position block `pb` of sequence n (16 bases per word, so a block starts on a word)
+__device__ __forceinline__ int64_t block_word(int64_t gq, int32_t W16, int64_t rowwords, int64_t* n_out, int32_t* pb_out) {
+    int64_t n = gq / W16;
+    int32_t pb = (int32_t)(gq - n * W16);
+    *n_out = n; *pb_out = pb;
+    return n * rowwords + (int64_t)pb;
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a) {
@@ -122,33 +113,34 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a)
     uint32_t* s_tile0 = reinterpret_cast<uint32_t*>(smem + a.blob_cap_bytes);
     uint32_t* s_tile1 = s_tile0 + a.tile_cap_words;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tile1 + a.tile_cap_words);     // [0],[1] tiles, [2] blob
+    int32_t* s_ticket = reinterpret_cast<int32_t*>(s_bar + 3);                     // next position block of the current tile
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int64_t q_lo = a.cta_range[blockIdx.x], q_hi = a.cta_range[blockIdx.x + 1];
     if (q_lo >= q_hi) return;
 
     const uint32_t bar0 = smem_u32(&s_bar[0]), bar1 = smem_u32(&s_bar[1]), bar2 = smem_u32(&s_bar[2]);
     if (threadIdx.x == 0) {
         mbar_init(bar0, 1); mbar_init(bar1, 1); mbar_init(bar2, 1);
+        *s_ticket = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // tile geometry helper: words [lo4, hi) of the packed array feed local chunks [t*TC, ...)
+    // tile geometry: words [lo4, hi) of the packed array feed local position blocks [t*TC, ...)
     auto tile_span = [&](int64_t tile, int64_t& lo4, uint32_t& bytes, int64_t& first, int32_t& cnt) {
         first = tile * a.tile_chunks;
         cnt = (int32_t)min((int64_t)a.tile_chunks, a.nchunks - first);
         int64_t n; int32_t c;
-        int64_t lo = chunk_word(a.chunk0 + first, a.W, a.rowwords, &n, &c);
-        int64_t hi = chunk_word(a.chunk0 + first + cnt - 1, a.W, a.rowwords, &n, &c) + 6;
+        int64_t lo = block_word(a.chunk0 + first, a.W, a.rowwords, &n, &c);
+        int64_t hi = block_word(a.chunk0 + first + cnt - 1, a.W, a.rowwords, &n, &c) + 6;
         lo4 = lo & ~(int64_t)3;
         bytes = (uint32_t)(((hi - lo4 + 3) & ~(int64_t)3) * 4);
     };
 
     uint32_t phase0 = 0, phase1 = 0, phase2 = 0;
     int32_t cur_mb = -1;
-    // prefetch the first tile
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {                                   // prefetch the first tile
         int64_t lo4, first; uint32_t bytes; int32_t cnt;
         tile_span(q_lo % a.ntiles, lo4, bytes, first, cnt);
         tma_load(smem_u32(s_tile0), reinterpret_cast<const uint8_t*>(a.seqw + lo4), bytes, bar0);
@@ -165,7 +157,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a)
             cur_mb = mb;
             mbar_wait(bar2, phase2); phase2 ^= 1;
         }
-        if (threadIdx.x == 0 && q + 1 < q_hi) {      // prefetch next tile into the other buffer
+        if (threadIdx.x == 0 && q + 1 < q_hi) {               // prefetch next tile into the other buffer
             int64_t lo4, first; uint32_t bytes; int32_t cnt;
             tile_span((q + 1) % a.ntiles, lo4, bytes, first, cnt);
             tma_load(smem_u32(buf ? s_tile0 : s_tile1), reinterpret_cast<const uint8_t*>(a.seqw + lo4), bytes, buf ? bar0 : bar1);
@@ -175,50 +167,79 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a)
         if (buf == 0) { mbar_wait(bar0, phase0); phase0 ^= 1; } else { mbar_wait(bar1, phase1); phase1 ^= 1; }
         const uint32_t* s_tile = buf ? s_tile1 : s_tile0;
         const GroupMeta* s_meta = reinterpret_cast<const GroupMeta*>(s_blob + mbk.tab_bytes);
-        const uint32_t tab_base = smem_u32(s_blob);
+        const uint32_t tab_base = smem_u32(s_blob) + lane * 8;
 
-        for (int32_t i = warp; i < cnt; i += nwarps) {
-            int64_t n; int32_t c;
+        for (;;) {
+            int32_t i = 0;
+            if (lane == 0) i = atomicAdd(s_ticket, 1);
+            i = __shfl_sync(0xffffffffu, i, 0);
+            if (i >= cnt) break;
+            int64_t n; int32_t pb;
             const int64_t lq = first + i;
-            const int64_t w0i = chunk_word(a.chunk0 + lq, a.W, a.rowwords, &n, &c) - lo4;
-            const int32_t pos = c * 32 + lane;
-            const uint32_t* wp = s_tile + w0i + (lane >> 4);
-            const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
-            const uint32_t sh = (lane & 15) * 2;
-            const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
-            const uint32_t x2 = __funnelshift_r(w2, w3, sh), x3 = __funnelshift_r(w3, w4, sh);
-            uint32_t* mrow = a.mask + lq * (int64_t)a.K2pad + (int64_t)mbk.g0 * GROUP_SLOTS;
+            const int64_t w0i = block_word(a.chunk0 + lq, a.W, a.rowwords, &n, &pb) - lo4;
+            const int32_t p0 = pb * POS_BLOCK;
+            // PRMT selectors of this position block: sel[u] picks, from a column's 8 bytes {A,C,G,T}, the entries of
+            // base[p0+u] (low half) and base[p0+u+1] (high half).  Same value in every lane (broadcast loads).
+            uint32_t sel[NSEL];
+            {
+                const uint32_t* wp = s_tile + w0i;
+                uint32_t wlo = wp[0];
+                #pragma unroll
+                for (int wi = 0; wi < (NSEL + 15) / 16; ++wi) {
+                    const uint32_t whi = wp[wi + 1];
+                    #pragma unroll
+                    for (int uu = 0; uu < 16; ++uu) {
+                        const int u = wi * 16 + uu;
+                        if (u < NSEL) {
+                            const uint32_t x = __funnelshift_r(wlo, whi, 2 * uu) & 15u;
+                            sel[u] = 0x1010u + 0x22u * (x & 3u) + 0x2200u * (x >> 2);
+                        }
+                    }
+                    wlo = whi;
+                }
+            }
+            // this block is the low (pb even) or high (pb odd) half of mask word (n, pb/2)
+            uint16_t* mrow = reinterpret_cast<uint16_t*>(a.mask + (lq >> 1) * (int64_t)a.K2pad + (int64_t)mbk.g0 * GROUP_SLOTS) + (pb & 1);
 
             for (int32_t g = 0; g < mbk.ng; ++g) {
                 const GroupMeta* gm = s_meta + g;
-                if (c * 32 >= gm->npos_max) {                 // warp-uniform: no valid start position in this chunk
-                    if (lane < GROUP_SLOTS) mrow[g * GROUP_SLOTS + lane] = 0u;
+                if (p0 >= gm->npos_max) {                     // warp-uniform: no valid start position in this block
+                    mrow[(g * GROUP_SLOTS + lane) * 2] = 0;
                     continue;
                 }
                 const int32_t len = gm->len;
                 const uint32_t tab = tab_base + gm->tab_off;
-                __half2 acc[8];
+                __half2 acc[POS_BLOCK / 2];
                 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] = as_h2(0u);
-                SCAN_SEGMENT(x0, 0)
-                SCAN_SEGMENT(x1, 16)
-                SCAN_SEGMENT(x2, 32)
-                SCAN_SEGMENT(x3, 48)
-            columns_done:
-                uint32_t myword = 0;
+                for (int k = 0; k < POS_BLOCK / 2; ++k) acc[k] = as_h2(0u);
+                // Columns are processed two per trip (tables are padded with a zero column to an even length: x + (+0) = x).
+                // ptxas splits the adds between HADD2 (ALU pipe) and HFMA2(x,1,y) (FMA pipe); both round identically.
                 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t m = __hgt2_mask(acc[k], as_h2(gm->thr2[k]));
-                    const bool valid = pos < gm->npos[k];
-                    const uint32_t bf = __ballot_sync(0xffffffffu, valid && (m & 0xFFFFu));
-                    const uint32_t br = __ballot_sync(0xffffffffu, valid && (m >> 16));
-                    if (lane == 2 * k) myword = bf;
-                    if (lane == 2 * k + 1) myword = br;
+                for (int j = 0; j < MB200_MAX_MOTIF_LEN; j += 2) {
+                    if (j >= len) break;
+                    const uint2 e0 = lds64(tab + j * COL_BYTES);
+                    const uint2 e1 = lds64(tab + (j + 1) * COL_BYTES);
+                    #pragma unroll
+                    for (int k = 0; k < POS_BLOCK / 2; ++k) acc[k] = __hadd2(acc[k], as_h2(__byte_perm(e0.x, e0.y, sel[2 * k + j])));
+                    #pragma unroll
+                    for (int k = 0; k < POS_BLOCK / 2; ++k) acc[k] = __hadd2(acc[k], as_h2(__byte_perm(e1.x, e1.y, sel[2 * k + j + 1])));
                 }
-                if (lane < GROUP_SLOTS) mrow[g * GROUP_SLOTS + lane] = myword;
+                const uint32_t t16 = gm->thr[lane];
+                const __half2 thr = as_h2(t16 | (t16 << 16));
+                uint32_t bits = 0;
+                #pragma unroll
+                for (int k = 0; k < POS_BLOCK / 2; ++k) {
+                    const uint32_t m = __hgt2_mask(acc[k], thr);
+                    bits |= ((m & 1u) | ((m >> 15) & 2u)) << (2 * k);
+                }
+                const int32_t nvalid = min(max(gm->npos[lane >> 1] - p0, 0), POS_BLOCK);
+                bits &= (1u << nvalid) - 1u;
+                mrow[(g * GROUP_SLOTS + lane) * 2] = (uint16_t)bits;
             }
         }
         __syncthreads();      // tile buffer `buf` and (possibly) the blob may be overwritten next
+        if (threadIdx.x == 0) *s_ticket = 0;
+        __syncthreads();
     }
 }
 
@@ -362,7 +383,7 @@ __global__ void __launch_bounds__(256) emit_kernel(const uint32_t* __restrict__ 
     const int32_t k = (int32_t)(nk - n * K);
     const EmitMotif m = em[k];
     const int32_t slot = m.slot + strand;
-    const uint8_t* tab = blob + m.tab_off + (slot & (GROUP_SLOTS - 1)) * 2;
+    const uint8_t* tab = blob + m.tab_off + (slot & (GROUP_SLOTS - 1)) * 8;
     const uint32_t* srow = seqw + (seq0 + n) * rowwords;
     unsigned long long off = unit_off[u];
     for (int32_t w = 0; w < W; ++w) {
@@ -375,7 +396,7 @@ __global__ void __launch_bounds__(256) emit_kernel(const uint32_t* __restrict__ 
             for (int32_t j = 0; j < m.len; ++j) {
                 const int32_t q = p + j;
                 const uint32_t base = (srow[q >> 4] >> ((q & 15) * 2)) & 3u;
-                const __half e = *reinterpret_cast<const __half*>(tab + (int64_t)j * COL_BYTES + base * 32);
+                const __half e = *reinterpret_cast<const __half*>(tab + (int64_t)j * COL_BYTES + base * 2);
                 s = __hadd(s, e);
             }
             // mb200_hit as one 16 B store: {seq, pos, motif | score<<16, comp}
@@ -422,7 +443,7 @@ static int build_plan(mb200_ctx* ctx, const uint16_t* pwms, const int64_t* lens,
 
     // group lengths, then greedy partition into motif blocks under the shared-memory budget
     std::vector<int> glen(P.ngroups);
-    for (int g = 0; g < P.ngroups; ++g) glen[g] = (int)lens[order[std::min(K - 1, g * GROUP_MOTIFS + GROUP_MOTIFS - 1)]];
+    for (int g = 0; g < P.ngroups; ++g) glen[g] = ((int)lens[order[std::min(K - 1, g * GROUP_MOTIFS + GROUP_MOTIFS - 1)]] + 1) & ~1;   // even: zero pad column
     int g = 0;
     while (g < P.ngroups) {
         MBlock mb; memset(&mb, 0, sizeof mb);
@@ -451,7 +472,7 @@ static int build_plan(mb200_ctx* ctx, const uint16_t* pwms, const int64_t* lens,
             const int gg = mb.g0 + gi;
             GroupMeta gm; memset(&gm, 0, sizeof gm);
             gm.len = glen[gg]; gm.tab_off = toff;
-            uint16_t* T = reinterpret_cast<uint16_t*>(tabs + toff);   // [col][base][16]
+            uint16_t* T = reinterpret_cast<uint16_t*>(tabs + toff);   // [col][slot][base]
             for (int i = 0; i < GROUP_MOTIFS; ++i) {
                 const int idx = gg * GROUP_MOTIFS + i;
                 uint16_t thr_f = 0x7C00u, thr_r = 0x7C00u;            // +Inf: never a hit
@@ -482,18 +503,18 @@ static int build_plan(mb200_ctx* ctx, const uint16_t* pwms, const int64_t* lens,
                             // in the reference's sum (greedy_search! adds pwm*x for all four a).
                             const uint16_t v = pw(k, b, j);
                             const uint16_t ef = (nf_f - (int)h16_nonfinite(v)) > 0 ? (uint16_t)0x7E00u : v;
-                            T[(size_t)j * 64 + b * 16 + i * 2 + 0] = ef;
+                            T[((size_t)j * GROUP_SLOTS + i * 2 + 0) * 4 + b] = ef;
                             // reverse(pwm): rc[a][j] = pwm[3-a][len-1-j]; its column j mirrors forward column len-1-j
                             const int jr = len - 1 - j;
                             const uint16_t vr = pw(k, 3 - b, jr);
                             int nf_r = 0;
                             for (int a2 = 0; a2 < 4; ++a2) nf_r += h16_nonfinite(pw(k, a2, jr));
                             const uint16_t er = (nf_r - (int)h16_nonfinite(vr)) > 0 ? (uint16_t)0x7E00u : vr;
-                            T[(size_t)j * 64 + b * 16 + i * 2 + 1] = er;
+                            T[((size_t)j * GROUP_SLOTS + i * 2 + 1) * 4 + b] = er;
                         }
                     }
                 }
-                gm.thr2[i] = (uint32_t)thr_f | ((uint32_t)thr_r << 16);
+                gm.thr[i * 2 + 0] = thr_f; gm.thr[i * 2 + 1] = thr_r;
             }
             metas[gi] = gm;
             toff += glen[gg] * COL_BYTES;
@@ -526,9 +547,10 @@ extern "C" int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs, const uint
     if (rc) return rc;
     const int64_t npos_max = Lb - P.minlen + 1;
     if (N == 0 || npos_max <= 0) return MB200_OK;       // nothing can be scored
-    const int64_t W64 = (npos_max + 31) / 32;
-    if (W64 > 0x3fffffff) MB_FAIL(ctx, MB200_E_UNSUPPORTED, "sequence too long");
+    const int64_t W64 = (npos_max + 31) / 32;                      // 32-position mask words per sequence
+    if (W64 > 0x1fffffff) MB_FAIL(ctx, MB200_E_UNSUPPORTED, "sequence too long");
     const int32_t W = (int32_t)W64;
+    const int32_t W16 = 2 * W;                                     // 16-position blocks per sequence (two per mask word)
 
     // ---- device buffers -------------------------------------------------------------------
     // buf 1: plan (blob, mblocks, pair tables, emit table, cta ranges, counts)
@@ -552,7 +574,7 @@ extern "C" int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs, const uint
     memcpy(h_plan.data() + off_em, P.em.data(), P.em.size() * sizeof(EmitMotif));
 
     // ---- batching: masks of one batch stay under a budget -----------------------------------
-    const size_t mask_budget = (size_t)2 << 30;
+    const size_t mask_budget = (size_t)8 << 30;
     const size_t mask_bytes_per_seq = (size_t)W * P.K2pad * 4;
     int64_t seqs_per_batch = std::max<int64_t>(1, (int64_t)(mask_budget / mask_bytes_per_seq));
     if (seqs_per_batch > N) seqs_per_batch = N;
@@ -572,11 +594,12 @@ extern "C" int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs, const uint
     }
 
     // ---- tiling and per-CTA pair ranges (balanced by column count of the motif block) --------
-    const int32_t tile_chunks = 16 * 14;
+    const int32_t tile_chunks = 16 * 26;                           // position blocks per tile
     auto tiles_of = [&](int64_t nchunks) { return (nchunks + tile_chunks - 1) / tile_chunks; };
-    const int64_t crossings = (tile_chunks - 1) / W + 1;
-    const int64_t gap = std::max<int64_t>(0, rowwords - 2 * (int64_t)W + 2);
-    const int32_t tile_cap_words = (int32_t)((2 * (int64_t)tile_chunks + crossings * gap + 6 + 4 + 3) & ~(int64_t)3);
+    // words spanned by a tile: +1 per block inside a sequence, + (rowwords - W16 + 1) when crossing to the next sequence
+    const int64_t crossings = (tile_chunks - 1) / W16 + 1;
+    const int64_t gap = std::max<int64_t>(0, rowwords - (int64_t)W16 + 1);
+    const int32_t tile_cap_words = (int32_t)(((int64_t)tile_chunks + crossings * gap + 6 + 4 + 3) & ~(int64_t)3);
     const int32_t blob_cap = (P.max_blob_bytes + 127) & ~127;
     const size_t smem_bytes = (size_t)blob_cap + (size_t)tile_cap_words * 8 + 64;
     if (smem_bytes > ctx->smem_optin) MB_FAIL(ctx, MB200_E_UNSUPPORTED, "scan needs %zu B shared memory (> %zu)", smem_bytes, ctx->smem_optin);
@@ -596,7 +619,7 @@ extern "C" int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs, const uint
     int64_t last_nchunks = -1;
     for (int64_t s0 = 0; s0 < N; s0 += seqs_per_batch) {
         const int64_t ns = std::min(seqs_per_batch, N - s0);
-        const int64_t nchunks = ns * W;
+        const int64_t nchunks = ns * (int64_t)W16;
         const int64_t ntiles = tiles_of(nchunks);
         if (nchunks != last_nchunks) {
             // weighted contiguous split of pairs (mblock-major) over CTAs
@@ -621,8 +644,8 @@ extern "C" int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs, const uint
             last_nchunks = nchunks;
         }
         ScanArgs a;
-        a.seqw = seqs->words; a.rowwords = rowwords; a.W = W;
-        a.chunk0 = s0 * W; a.nchunks = nchunks;
+        a.seqw = seqs->words; a.rowwords = rowwords; a.W = W16;
+        a.chunk0 = s0 * (int64_t)W16; a.nchunks = nchunks;
         a.mask = d_mask; a.K2pad = P.K2pad;
         a.blob = d_plan + off_blob; a.mblocks = (const MBlock*)(d_plan + off_mb); a.n_mblocks = (int32_t)P.mblocks.size();
         a.tile_chunks = tile_chunks; a.ntiles = ntiles; a.tile_cap_words = tile_cap_words; a.blob_cap_bytes = blob_cap;
