@@ -157,6 +157,14 @@ typedef struct {                 /* stored_code_component_t, inference/_0_const.
 int32_t mb200_csc_codes(mb200_ctx* ctx, mb200_csc* csc, const mb200_seqs* seqs, int64_t first_seq,
                         int64_t n_seqs, mb200_code* out, int64_t cap, int64_t* n_out);
 
+/* ---- positions -> count matrices: replaces posdicts2countmats / msa_add! (inference/_h6_positions2countmat.jl:7-54),
+ *      obtain_count_matrices (_3_make_pfms.jl:28-46) and the counting half of enriched_keys2motifs
+ *      (_s1_make_motifs.jl:234-259).                                                              */
+typedef struct { uint32_t motif, seq, pos, comp; } mb200_site;   /* 0-based; comp != 0 adds the reverse complement */
+/* counts: K*maxlen*4 uint32, entry [(k*maxlen + col)*4 + base]; columns >= lens[k] stay 0. */
+int32_t mb200_count_matrices(mb200_ctx* ctx, const mb200_seqs* seqs, const mb200_site* sites, int64_t n_sites,
+                             const int64_t* lens, int32_t K, int32_t maxlen, uint32_t* counts);
+
 #ifdef __cplusplus
 }
 #endif

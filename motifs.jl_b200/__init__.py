@@ -11,3 +11,9 @@ There is no CPU fallback: every entry point raises if the CUDA library is missin
 """
 from . import _lib  # noqa: F401
 from ._lib import Context, Sequences, MB200Error, library_path  # noqa: F401
+
+
+def discover_motifs(datapath, save_path, num_epochs=None, **kw):
+    """discover_motifs(datapath, save_path; num_epochs) — src/wrap.jl:1-11."""
+    from .wrap import discover_motifs as _dm
+    return _dm(datapath, save_path, num_epochs=num_epochs, **kw)

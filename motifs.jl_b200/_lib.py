@@ -31,6 +31,7 @@ HIT_DTYPE = np.dtype([("seq", "<u4"), ("pos", "<u4"), ("motif", "<u2"), ("score_
                       ("comp", "u1"), ("_pad", "u1", (3,))])
 assert HIT_DTYPE.itemsize == 16
 
+SITE_DTYPE = np.dtype([("motif", "<u4"), ("seq", "<u4"), ("pos", "<u4"), ("comp", "<u4")])
 CODE_DTYPE = np.dtype([("position", "<u2"), ("fil", "<u2"), ("seq", "<u4"), ("mag_f16", "<u2"), ("_pad", "<u2")])
 assert CODE_DTYPE.itemsize == 12
 
@@ -81,6 +82,7 @@ def load():
         "mb200_csc_adabelief_step": (i32, [p, p, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "mb200_csc_get_buffer": (i32, [p, p, C.c_char_p, p, i64]),
         "mb200_csc_codes": (i32, [p, p, p, i64, i64, p, i64, C.POINTER(i64)]),
+        "mb200_count_matrices": (i32, [p, p, p, i64, p, i32, i32, p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -198,6 +200,16 @@ class Context:
             self._check(rc_)
             break
         return (hits[: n_hits.value] if want_hits else None), counts
+
+
+def count_matrices(ctx: "Context", seqs: "Sequences", sites, lens):
+    """sites: structured array (motif, seq, pos, comp), 0-based -> list of (4, len_k) uint32 count matrices."""
+    st = np.ascontiguousarray(sites, SITE_DTYPE)
+    ln = np.ascontiguousarray(lens, np.int64)
+    K, maxlen = len(ln), int(ln.max())
+    out = np.zeros((K, maxlen, 4), np.uint32)
+    ctx._check(ctx._lib.mb200_count_matrices(ctx._h, seqs._h, _ptr(st), len(st), _ptr(ln), K, maxlen, _ptr(out)))
+    return [out[k, : ln[k]].T.copy() for k in range(K)]
 
 
 class Sequences:

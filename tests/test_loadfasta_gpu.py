@@ -49,3 +49,42 @@ def test_mirror_pipeline_end_to_end(ctx):
     pvec, uniq_test = inference.pvec_from_test_data(ms, data)
     assert np.all(pvec < 1e-5) and np.all(uniq_test > 0)          # the planted half sites are enriched over the shuffled background
     m.free(); data.free()
+
+
+def test_count_matrices_kernel(ctx):
+    from motifs_jl_b200 import _lib
+    from oracle import extract_oracle as eo
+    a = synth.random_ascii(40, 70, 3)
+    codes = so.ascii_to_codes(a)
+    seqs = ctx.seqs_from_ascii(a)
+    rng = np.random.default_rng(5)
+    lens = np.array([8, 21, 13], np.int64)
+    sites = np.zeros(300, _lib.SITE_DTYPE)
+    sites["motif"] = rng.integers(0, 3, 300)
+    sites["seq"] = rng.integers(0, 40, 300)
+    sites["pos"] = [int(rng.integers(0, 70 - lens[m] + 1)) for m in sites["motif"]]
+    sites["comp"] = rng.integers(0, 2, 300)
+    got = _lib.count_matrices(ctx, seqs, sites, lens)
+    for m in range(3):
+        sel = sites[sites["motif"] == m]
+        exp = eo.count_matrix(codes, sel["seq"].astype(int) + 1, sel["pos"].astype(int) + 1, sel["comp"].astype(bool), int(lens[m]))
+        assert np.array_equal(got[m].astype(np.float32), exp)
+    seqs.free()
+
+
+def test_discover_motifs_writes_reference_layout(ctx, tmp_path):
+    """discover_motifs(fasta, outdir; num_epochs) end to end on a planted motif; checks the output tree of render/const.jl."""
+    import motifs_jl_b200 as mb
+    a = synth.planted_gapped(1500, 100, 8)
+    fa = os.path.join(tmp_path, "reads.fa")
+    loadfasta.write_fasta(fa, a)
+    out = os.path.join(tmp_path, "out")
+    ms, res = mb.discover_motifs(fa, out, num_epochs=2, rng=np.random.default_rng(0))
+    assert os.path.isfile(os.path.join(out, "summary.html"))
+    for d in ("logos_olap", "logos_no_olap", "pics_olap", "pics_no_olap"):
+        assert os.path.isdir(os.path.join(out, d))
+    assert ms.num_motifs >= 1
+    for i in range(1, ms.num_motifs + 1):
+        for f in (f"d{i}.transfac", f"d{i}_c.transfac", f"d{i}.meme"):
+            assert os.path.isfile(os.path.join(out, "logos_olap", f))
+    assert (res["pvec"] < 1e-5).any()                       # the planted motif is found and enriched on the held-out split
