@@ -32,7 +32,7 @@ extern "C" {
 #define MB200_E_HITS_OVERFLOW   -5   /* hits_cap too small; *n_hits holds the required size */
 #define MB200_E_UNSUPPORTED     -6
 
-#define MB200_MAX_MOTIF_LEN     64   /* longest PWM the scan kernel accepts */
+#define MB200_MAX_MOTIF_LEN     64   /* longest PWM the register-resident scan kernel scores; longer PWMs take a plain kernel */
 
 typedef struct mb200_ctx  mb200_ctx;
 typedef struct mb200_seqs mb200_seqs;

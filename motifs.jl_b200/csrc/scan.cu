@@ -243,6 +243,42 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a)
     }
 }
 
+// Motifs longer than MB200_MAX_MOTIF_LEN columns (rare: the reference trims PWMs to their informative span) are scored by a
+// plain kernel: one warp per (sequence, slot), lanes over 32 start positions, table read from global memory.  Same
+// sequential Float16 adds, same mask layout.
+__global__ void __launch_bounds__(256) scan_long_kernel(const uint32_t* __restrict__ seqw, int64_t rowwords, int64_t seq0, int64_t nseq,
+                                                        int32_t W, int32_t K2pad, const uint8_t* __restrict__ blob,
+                                                        const MBlock* __restrict__ lblocks, int32_t n_lblocks, uint32_t* __restrict__ mask) {
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t per_seq = (int64_t)n_lblocks * GROUP_SLOTS;
+    if (wid >= nseq * per_seq) return;
+    const int64_t n = wid / per_seq;
+    const int rem = (int)(wid - n * per_seq);
+    const MBlock mb = lblocks[rem / GROUP_SLOTS];
+    const int slot = rem % GROUP_SLOTS;
+    const GroupMeta* gm = reinterpret_cast<const GroupMeta*>(blob + mb.blob_off + mb.tab_bytes);
+    const uint8_t* tab = blob + mb.blob_off + slot * 8;
+    const int len = gm->len, npos = gm->npos[slot >> 1];
+    const __half thr = __ushort_as_half(gm->thr[slot]);
+    const uint32_t* srow = seqw + (seq0 + n) * rowwords;
+    for (int w = 0; w < W; ++w) {
+        const int pos = w * 32 + lane;
+        bool hit = false;
+        if (pos < npos) {
+            __half s = __ushort_as_half((unsigned short)0);
+            for (int j = 0; j < len; ++j) {
+                const int q = pos + j;
+                const uint32_t base = (srow[q >> 4] >> ((q & 15) * 2)) & 3u;
+                s = __hadd(s, *reinterpret_cast<const __half*>(tab + (int64_t)j * COL_BYTES + base * 2));
+            }
+            hit = __hgt(s, thr);
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) mask[(n * W + w) * (int64_t)K2pad + (int64_t)mb.g0 * GROUP_SLOTS + slot] = word;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Counting from the masks: one thread per (sequence, motif).  Mask word layout:
 //   mask[(n*W + w) * K2pad + slotpair*2 + strand]
@@ -417,6 +453,7 @@ struct ScanPlan {
     int K = 0, ngroups = 0, K2pad = 0;
     std::vector<uint8_t> blob;
     std::vector<MBlock> mblocks;
+    std::vector<MBlock> lblocks;          // one per group of motifs longer than MB200_MAX_MOTIF_LEN (slow path)
     std::vector<int32_t> pair2motif, pairlen;
     std::vector<EmitMotif> em;
     int max_blob_bytes = 0;
@@ -428,8 +465,8 @@ static int build_plan(mb200_ctx* ctx, const uint16_t* pwms, const int64_t* lens,
     P.K = K;
     std::vector<int> order(K);
     for (int k = 0; k < K; ++k) {
-        if (lens[k] < 1 || lens[k] > maxlen || lens[k] > MB200_MAX_MOTIF_LEN)
-            MB_FAIL(ctx, MB200_E_INVALID, "motif %d: length %lld outside [1, min(maxlen=%d, %d)]", k, (long long)lens[k], maxlen, MB200_MAX_MOTIF_LEN);
+        if (lens[k] < 1 || lens[k] > maxlen)
+            MB_FAIL(ctx, MB200_E_INVALID, "motif %d: length %lld outside [1, maxlen=%d]", k, (long long)lens[k], maxlen);
         order[k] = k;
     }
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lens[a] < lens[b]; });
@@ -444,11 +481,14 @@ static int build_plan(mb200_ctx* ctx, const uint16_t* pwms, const int64_t* lens,
     // group lengths, then greedy partition into motif blocks under the shared-memory budget
     std::vector<int> glen(P.ngroups);
     for (int g = 0; g < P.ngroups; ++g) glen[g] = ((int)lens[order[std::min(K - 1, g * GROUP_MOTIFS + GROUP_MOTIFS - 1)]] + 1) & ~1;   // even: zero pad column
+    // groups longer than the register-resident fast path (MB200_MAX_MOTIF_LEN columns) go to scan_long_kernel
+    int g_long = P.ngroups;
+    for (int gq = 0; gq < P.ngroups; ++gq) if (glen[gq] > MB200_MAX_MOTIF_LEN) { g_long = gq; break; }
     int g = 0;
-    while (g < P.ngroups) {
+    while (g < g_long) {
         MBlock mb; memset(&mb, 0, sizeof mb);
         mb.g0 = g; size_t tb = 0; int cost = 0;
-        while (g < P.ngroups) {
+        while (g < g_long) {
             size_t add = (size_t)glen[g] * COL_BYTES;
             size_t metas = (size_t)(g - mb.g0 + 1) * sizeof(GroupMeta);
             if (g > mb.g0 && tb + add + metas > table_budget) break;
@@ -460,11 +500,22 @@ static int build_plan(mb200_ctx* ctx, const uint16_t* pwms, const int64_t* lens,
             MB_FAIL(ctx, MB200_E_UNSUPPORTED, "a single motif group needs %d B of shared memory", mb.blob_bytes);
         P.mblocks.push_back(mb);
     }
+    for (int gl = g_long; gl < P.ngroups; ++gl) {
+        MBlock mb; memset(&mb, 0, sizeof mb);
+        mb.g0 = gl; mb.ng = 1; mb.tab_bytes = glen[gl] * COL_BYTES; mb.cost = glen[gl];
+        mb.blob_bytes = (int32_t)(((size_t)mb.tab_bytes + sizeof(GroupMeta) + 15) & ~(size_t)15);
+        P.lblocks.push_back(mb);
+    }
     size_t total = 0;
     for (auto& mb : P.mblocks) { mb.blob_off = (int64_t)total; total += ((size_t)mb.blob_bytes + 127) & ~(size_t)127; P.max_blob_bytes = std::max(P.max_blob_bytes, mb.blob_bytes); }
+    for (auto& mb : P.lblocks) { mb.blob_off = (int64_t)total; total += ((size_t)mb.blob_bytes + 127) & ~(size_t)127; }
     P.blob.assign(total, 0);
 
-    for (auto& mb : P.mblocks) {
+    std::vector<MBlock*> all_blocks;
+    for (auto& mb : P.mblocks) all_blocks.push_back(&mb);
+    for (auto& mb : P.lblocks) all_blocks.push_back(&mb);
+    for (MBlock* mbp : all_blocks) {
+        MBlock& mb = *mbp;
         uint8_t* tabs = P.blob.data() + mb.blob_off;
         GroupMeta* metas = reinterpret_cast<GroupMeta*>(tabs + mb.tab_bytes);
         int toff = 0;
@@ -556,7 +607,8 @@ extern "C" int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs, const uint
     // buf 1: plan (blob, mblocks, pair tables, emit table, cta ranges, counts)
     const size_t off_blob = 0;
     const size_t off_mb = (P.blob.size() + 255) & ~(size_t)255;
-    const size_t off_p2m = off_mb + ((P.mblocks.size() * sizeof(MBlock) + 255) & ~(size_t)255);
+    const size_t off_lb = off_mb + ((P.mblocks.size() * sizeof(MBlock) + 255) & ~(size_t)255);
+    const size_t off_p2m = off_lb + ((P.lblocks.size() * sizeof(MBlock) + 255) & ~(size_t)255);
     const size_t off_plen = off_p2m + ((P.pair2motif.size() * 4 + 255) & ~(size_t)255);
     const size_t off_em = off_plen + ((P.pairlen.size() * 4 + 255) & ~(size_t)255);
     const size_t off_rng = off_em + ((P.em.size() * sizeof(EmitMotif) + 255) & ~(size_t)255);
@@ -569,6 +621,7 @@ extern "C" int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs, const uint
     std::vector<uint8_t> h_plan(plan_bytes, 0);
     memcpy(h_plan.data() + off_blob, P.blob.data(), P.blob.size());
     memcpy(h_plan.data() + off_mb, P.mblocks.data(), P.mblocks.size() * sizeof(MBlock));
+    memcpy(h_plan.data() + off_lb, P.lblocks.data(), P.lblocks.size() * sizeof(MBlock));
     memcpy(h_plan.data() + off_p2m, P.pair2motif.data(), P.pair2motif.size() * 4);
     memcpy(h_plan.data() + off_plen, P.pairlen.data(), P.pairlen.size() * 4);
     memcpy(h_plan.data() + off_em, P.em.data(), P.em.size() * sizeof(EmitMotif));
@@ -651,9 +704,14 @@ extern "C" int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs, const uint
         a.tile_chunks = tile_chunks; a.ntiles = ntiles; a.tile_cap_words = tile_cap_words; a.blob_cap_bytes = blob_cap;
         a.cta_range = d_rng;
         int t1 = tm.begin(T_SCAN);
-        scan_kernel<<<grid, SCAN_THREADS, smem_bytes, ctx->stream>>>(a);
+        if (!P.mblocks.empty()) { scan_kernel<<<grid, SCAN_THREADS, smem_bytes, ctx->stream>>>(a); ctx->launches[T_SCAN] += 1; }
+        if (!P.lblocks.empty()) {
+            const int64_t warps = ns * (int64_t)P.lblocks.size() * GROUP_SLOTS;
+            scan_long_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, ctx->stream>>>(seqs->words, rowwords, s0, ns, W, P.K2pad, d_plan + off_blob,
+                                                                                        (const MBlock*)(d_plan + off_lb), (int32_t)P.lblocks.size(), d_mask);
+            ctx->launches[T_SCAN] += 1;
+        }
         tm.end(t1);
-        ctx->launches[T_SCAN] += 1;
         MB_CUDA(ctx, cudaGetLastError());
 
         int t2 = tm.begin(T_COUNT);

@@ -77,10 +77,12 @@ void oracle_pos_scores(const uint16_t* pwms, const int64_t* lens, int K, int max
  * tests/test_scan_oracle.py checks this form against score_literal. */
 static inline int h_nonfinite(uint16_t b) { return (b & 0x7C00u) == 0x7C00u; }
 
-typedef struct { int len; f16 e[2][64][4]; } motif_tab;
+typedef struct { int len; f16 (*e[2])[4]; } motif_tab;      /* e[rc][ind][base], len columns each */
 
 static void build_tab(const uint16_t* pwms, int K, int k, int len, motif_tab* t) {
     t->len = len;
+    t->e[0] = (f16 (*)[4])malloc(sizeof(f16) * 4 * (size_t)len);
+    t->e[1] = (f16 (*)[4])malloc(sizeof(f16) * 4 * (size_t)len);
     for (int rc = 0; rc < 2; ++rc)
         for (int ind = 0; ind < len; ++ind) {
             int nf = 0;
@@ -214,6 +216,7 @@ int64_t oracle_scan(const uint16_t* pwms, const int64_t* lens, int K, int maxlen
             }
         }
     }
+    for (int k = 0; k < K; ++k) { free(tabs[k].e[0]); free(tabs[k].e[1]); }
     free(per_seq); free(tabs);
     return total;
 }
@@ -223,6 +226,7 @@ int64_t oracle_scan(const uint16_t* pwms, const int64_t* lens, int K, int maxlen
 uint16_t oracle_score_tab(const uint16_t* pwms, const int64_t* lens, int K, int k, int rc, const uint8_t* bases, int64_t l) {
     motif_tab t; build_tab(pwms, K, k, (int)lens[k], &t);
     f16 s = score_tab(&t, rc, bases, l);
+    free(t.e[0]); free(t.e[1]);
     return h2bits(s > (f16)0.0f ? s : (f16)0.0f);
 }
 uint16_t oracle_score_literal(const uint16_t* pwms, const int64_t* lens, int K, int k, int rc, const uint8_t* bases, int64_t l) {

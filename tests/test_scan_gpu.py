@@ -91,6 +91,14 @@ def test_long_and_short_edges(ctx):
     ms2 = synth.motifs_from_count_matrices(synth.random_count_matrices(5, 60, 64, 26))
     _check(ctx, b, ms2)
     _check(ctx, b, ms2, np.full(5, -3.0, np.float16))    # negative threshold: still needs score > 0
+    # longer than MB200_MAX_MOTIF_LEN: slow path, mixed with short motifs, and a motif as long as the sequence
+    ms3 = synth.motifs_from_count_matrices(synth.random_count_matrices(3, 65, 120, 27) + synth.random_count_matrices(20, 8, 30, 28)
+                                           + synth.random_count_matrices(1, 300, 300, 29))
+    for p in ms3.pwms[:3] + ms3.pwms[-1:]:
+        p[:] = (p / np.float16(8)).astype(np.float16)       # keep long sums finite and some of them positive
+        p[:, ::3] = np.abs(p[:, ::3])
+    h3, c3 = _check(ctx, b, ms3)
+    assert c3[:3, 0].sum() > 0
 
 
 def test_nonfinite_and_negative_pwms(ctx):
