@@ -24,6 +24,8 @@ struct Buf { size_t off = 0; size_t n = 0; };            // offsets in floats in
 struct Op {
     std::function<void(cudaStream_t)> fwd, bwd;
     const char* name;
+    int branch = 0;      // 1: runs on the aux stream (a parallel branch between a fork and a join marker)
+    int kind = 0;        // 0 kernel op, 1 fork marker, 2 join marker
 };
 
 }  // namespace
@@ -43,6 +45,9 @@ struct mb200_csc {
     int n_lists = 0;                                     // ordered non-zero lists of the x-role tensors (x and d g)
     int32_t* lcnt = nullptr; uint16_t* lidx = nullptr; float* lval = nullptr;
     int mask_cap = 0;
+    cudaStream_t aux = nullptr;                          // second capture stream: independent adjoint kernels / D-F branches run in parallel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
+    bool in_branch = false;                              // set while replaying ops of a forked branch (no nested forking)
     uint8_t* bases = nullptr;
     int64_t* idx_dev = nullptr;
     int64_t* idx_pinned = nullptr;
@@ -152,21 +157,29 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
     auto run_fgrad = [=](const float* A, const float* x, int L, float* of, int64_t ogs, int acc, cudaStream_t q) {
         k_fgrad_l<<<dim3(d.K, d.h, d.G), 128, 0, q>>>(A, x, LCNT(L), LIDX(L), LVAL(L), of, ogs, acc, d);
     };
+    // two independent adjoint kernels of one op: the second runs on the aux stream (a parallel branch of the captured graph)
+    auto par2 = [=](cudaStream_t q, const std::function<void(cudaStream_t)>& k1, const std::function<void(cudaStream_t)>& k2) {
+        if (S->in_branch || !S->aux) { k1(q); k2(q); return; }
+        cudaEventRecord(S->ev_fork, q); cudaStreamWaitEvent(S->aux, S->ev_fork, 0);
+        k2(S->aux);
+        k1(q);
+        cudaEventRecord(S->ev_join, S->aux); cudaStreamWaitEvent(q, S->ev_join, 0);
+    };
     std::map<size_t, int> xlist;                 // buffer offset of an x tensor -> list of its data
     auto op_recon = [&](Buf ca, Buf cb, Buf filt, int64_t gs, Buf out, const char* nm) {
         T.push_back({[=](cudaStream_t q) { k_recon<<<nblk(nS * 32, 256), 256, 0, q>>>(S->data + ca.off, S->data + cb.off, S->data + filt.off, gs, S->data + out.off, 0, d); },
                      [=](cudaStream_t q) {
                          // d ca, d cb: corr_sig form with signal = d out ; d filt: dgrad form with signal = d out
-                         k_corr_sig<<<nblk(nZ, 256), 256, 0, q>>>(S->grad + out.off, S->bases, 0.f, S->data + filt.off, gs, S->grad + ca.off, S->grad + cb.off, 1, d);
-                         run_dgrad(S->data + ca.off, S->data + cb.off, S->grad + out.off, 0.f, S->grad + filt.off, gs, 1, q);
+                         par2(q, [=](cudaStream_t r) { k_corr_sig<<<nblk(nZ, 256), 256, 0, r>>>(S->grad + out.off, S->bases, 0.f, S->data + filt.off, gs, S->grad + ca.off, S->grad + cb.off, 1, d); },
+                                 [=](cudaStream_t r) { run_dgrad(S->data + ca.off, S->data + cb.off, S->grad + out.off, 0.f, S->grad + filt.off, gs, 1, r); });
                      },
                      nm});
     };
     auto op_corr_sig = [&](Buf sig, float sgn, Buf filt, int64_t gs, Buf oa, Buf ob, const char* nm) {
         T.push_back({[=](cudaStream_t q) { k_corr_sig<<<nblk(nZ, 256), 256, 0, q>>>(S->data + sig.off, S->bases, sgn, S->data + filt.off, gs, S->data + oa.off, S->data + ob.off, 0, d); },
                      [=](cudaStream_t q) {
-                         k_recon<<<nblk(nS * 32, 256), 256, 0, q>>>(S->grad + oa.off, S->grad + ob.off, S->data + filt.off, gs, S->grad + sig.off, 1, d);
-                         run_dgrad(S->grad + oa.off, S->grad + ob.off, S->data + sig.off, sgn, S->grad + filt.off, gs, 1, q);
+                         par2(q, [=](cudaStream_t r) { k_recon<<<nblk(nS * 32, 256), 256, 0, r>>>(S->grad + oa.off, S->grad + ob.off, S->data + filt.off, gs, S->grad + sig.off, 1, d); },
+                                 [=](cudaStream_t r) { run_dgrad(S->grad + oa.off, S->grad + ob.off, S->data + sig.off, sgn, S->grad + filt.off, gs, 1, r); });
                      },
                      nm});
     };
@@ -174,8 +187,8 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         T.push_back({[=](cudaStream_t q) { run_dgrad(S->data + ca.off, S->data + cb.off, S->data + sig.off, sgn, S->data + outG.off, nD, 0, q); },
                      [=](cudaStream_t q) {
                          // d ca, d cb: corr_sig with filter = dG (per group) ; d sig: recon with filter = dG
-                         k_corr_sig<<<nblk(nZ, 256), 256, 0, q>>>(S->data + sig.off, S->bases, sgn, S->grad + outG.off, nD, S->grad + ca.off, S->grad + cb.off, 1, d);
-                         k_recon<<<nblk(nS * 32, 256), 256, 0, q>>>(S->data + ca.off, S->data + cb.off, S->grad + outG.off, nD, S->grad + sig.off, 1, d);
+                         par2(q, [=](cudaStream_t r) { k_corr_sig<<<nblk(nZ, 256), 256, 0, r>>>(S->data + sig.off, S->bases, sgn, S->grad + outG.off, nD, S->grad + ca.off, S->grad + cb.off, 1, d); },
+                                 [=](cudaStream_t r) { k_recon<<<nblk(nS * 32, 256), 256, 0, r>>>(S->data + ca.off, S->data + cb.off, S->grad + outG.off, nD, S->grad + sig.off, 1, d); });
                      },
                      nm});
     };
@@ -183,8 +196,8 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
     auto op_corr2d = [&](Buf A, Buf filt, int64_t gs, Buf out, int glist, const char* nm) {
         T.push_back({[=](cudaStream_t q) { run_corr2d(S->data + A.off, S->data + filt.off, gs, S->data + out.off, 0, q); },
                      [=](cudaStream_t q) {
-                         run_tconv(S->grad + out.off, glist, S->data + filt.off, gs, S->grad + A.off, 1, q);
-                         run_fgrad(S->data + A.off, S->grad + out.off, glist, S->grad + filt.off, gs, 1, q);
+                         par2(q, [=](cudaStream_t r) { run_tconv(S->grad + out.off, glist, S->data + filt.off, gs, S->grad + A.off, 1, r); },
+                                 [=](cudaStream_t r) { run_fgrad(S->data + A.off, S->grad + out.off, glist, S->grad + filt.off, gs, 1, r); });
                      },
                      nm});
     };
@@ -192,8 +205,8 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         const int xl = xlist.at(x.off);
         T.push_back({[=](cudaStream_t q) { run_tconv(S->data + x.off, xl, S->data + filt.off, gs, S->data + out.off, 0, q); },
                      [=](cudaStream_t q) {
-                         run_corr2d(S->grad + out.off, S->data + filt.off, gs, S->grad + x.off, 1, q);
-                         run_fgrad(S->grad + out.off, S->data + x.off, xl, S->grad + filt.off, gs, 1, q);
+                         par2(q, [=](cudaStream_t r) { run_corr2d(S->grad + out.off, S->data + filt.off, gs, S->grad + x.off, 1, r); },
+                                 [=](cudaStream_t r) { run_fgrad(S->grad + out.off, S->data + x.off, xl, S->grad + filt.off, gs, 1, r); });
                      },
                      nm});
     };
@@ -201,8 +214,8 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         const int xl = xlist.at(x.off);
         T.push_back({[=](cudaStream_t q) { run_fgrad(S->data + A.off, S->data + x.off, xl, S->data + outF.off, nF, 0, q); },
                      [=](cudaStream_t q) {
-                         run_tconv(S->data + x.off, xl, S->grad + outF.off, nF, S->grad + A.off, 1, q);
-                         run_corr2d(S->data + A.off, S->grad + outF.off, nF, S->grad + x.off, 1, q);
+                         par2(q, [=](cudaStream_t r) { run_tconv(S->data + x.off, xl, S->grad + outF.off, nF, S->grad + A.off, 1, r); },
+                                 [=](cudaStream_t r) { run_corr2d(S->data + A.off, S->grad + outF.off, nF, S->grad + x.off, 1, r); });
                      },
                      nm});
     };
@@ -210,7 +223,12 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
     s->mask_cap = mask_cap;
     auto op_mask_scale = [&](Buf z, Buf y, Buf zy, const char* nm) {
         Buf med = B.alloc(d.G);
-        T.push_back({[=](cudaStream_t q) { k_mask_scale_c<<<d.G * CL, 512, (size_t)mask_cap * 4, q>>>(S->data + z.off, S->data + y.off, S->data + zy.off, S->data + med.off, d); },
+        const bool ms_cluster = mask_cap <= MS_MAXV * 512;       // slice fits the register-staged cluster kernel
+        const int ms_cap1 = (int)std::min<int64_t>(2 * (int64_t)d.B * d.c * d.M, 49152);
+        T.push_back({[=](cudaStream_t q) {
+                         if (ms_cluster) k_mask_scale_c<<<d.G * CL, 512, (size_t)mask_cap * 4, q>>>(S->data + z.off, S->data + y.off, S->data + zy.off, S->data + med.off, d);
+                         else k_mask_scale_s<<<d.G, 1024, (size_t)ms_cap1 * 4, q>>>(S->data + z.off, S->data + y.off, S->data + zy.off, S->data + med.off, ms_cap1, d);
+                     },
                      [=](cudaStream_t q) { k_mask_scale_bwd<<<nblk(nZY, 256), 256, 0, q>>>(S->data + z.off, S->data + y.off, S->data + med.off, S->grad + zy.off, S->grad + z.off, S->grad + y.off, d); },
                      nm});
     };
@@ -286,7 +304,10 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
     Buf theta{}; bool have_theta = false;
     for (int n = 0; n < d.npd; ++n) {
         const int i_mu = s->i_mu0 + n, i_kap = s->i_kap0 + n, i_kaps = s->i_kaps0 + n;
-        // update_D
+        // update_D (model.jl:368) and update_F (:369) of one pass touch disjoint tensors: they are recorded as two parallel
+        // branches (D chain on the aux stream) between a fork and a join marker, in the forward and in the reverse pass
+        T.push_back({nullptr, nullptr, "fork", 0, 1});
+        const size_t d_chain_begin = T.size();
         Buf rec = B.alloc(nS), Gm = B.alloc((size_t)d.G * nD), Dn = B.alloc((size_t)d.G * nD);
         op_recon(z, y, Dc, Dgs, rec, "df_recon");
         op_dgrad(z, y, rec, +1.f, Gm, "df_dgrad");                      // R = sumZD + sumYRD + S  ('+S': model.jl:282-285)
@@ -297,6 +318,7 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
                          "d_update"});
         }
         Dc = Dn; Dgs = nD;
+        for (size_t ti = d_chain_begin; ti < T.size(); ++ti) T[ti].branch = 1;
         // update_F
         Buf fxc = B.alloc(nZY), e = B.alloc(nZY), Fg = B.alloc((size_t)d.G * nF), Fn = B.alloc((size_t)d.G * nF), nrm = B.alloc((size_t)d.G * d.K);
         op_tconv(x, Fc, Fgs, fxc, "df_tconv");
@@ -314,6 +336,7 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
                          "f_update"});
         }
         Fc = Fn; Fgs = nF;
+        T.push_back({nullptr, nullptr, "join", 0, 2});
         // theta = theta + FX(X, F_new) - ZY   (only needed by the next pass)
         if (n + 1 < d.npd) {
             Buf fx2 = B.alloc(nZY), thn = B.alloc(nZY);
@@ -356,8 +379,14 @@ static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
     MB_CUDA(ctx, cudaMalloc(&s->lidx, (size_t)std::max(1, s->n_lists) * s->d.NS * LIST_CAP * 2));
     MB_CUDA(ctx, cudaMalloc(&s->lval, (size_t)std::max(1, s->n_lists) * s->d.NS * LIST_CAP * 4));
     MB_CUDA(ctx, cudaMemset(s->lcnt, 0, (size_t)std::max(1, s->n_lists) * s->d.NS * 4));
-    MB_CUDA(ctx, cudaFuncSetAttribute(k_mask_scale_c, cudaFuncAttributeMaxDynamicSharedMemorySize, s->mask_cap * 4));
+    if (s->mask_cap <= MS_MAXV * 512) MB_CUDA(ctx, cudaFuncSetAttribute(k_mask_scale_c, cudaFuncAttributeMaxDynamicSharedMemorySize, s->mask_cap * 4));
+    MB_CUDA(ctx, cudaFuncSetAttribute(k_mask_scale_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<int64_t>(2 * (int64_t)s->d.B * s->d.c * s->d.M, 49152) * 4));
     MB_CUDA(ctx, cudaFuncSetAttribute(k_topq_s, cudaFuncAttributeMaxDynamicSharedMemorySize, s->d.l * s->d.K * 4));
+    MB_CUDA(ctx, cudaStreamCreateWithFlags(&s->aux, cudaStreamNonBlocking));
+    MB_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+    MB_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+    MB_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_fork2, cudaEventDisableTiming));
+    MB_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_join2, cudaEventDisableTiming));
     MB_CUDA(ctx, cudaMalloc(&s->bases, (size_t)s->d.NS * s->d.Lb));
     MB_CUDA(ctx, cudaMalloc(&s->idx_dev, (size_t)s->d.NS * 8));
     MB_CUDA(ctx, cudaMallocHost(&s->idx_pinned, (size_t)s->d.NS * 8));
@@ -372,7 +401,6 @@ extern "C" int32_t mb200_csc_create(mb200_ctx* ctx, const mb200_hparams* hp, int
         MB_FAIL(ctx, MB200_E_INVALID, "csc: bad hyper-parameters");
     const int64_t c = Lb - hp->filter_len + 1, l = c - hp->h + 1;
     if ((int64_t)l * hp->K * 4 > 200 * 1024 || (int64_t)l * hp->K > 65535) MB_FAIL(ctx, MB200_E_UNSUPPORTED, "csc: sequence length %lld too long for the shared-memory top-q", (long long)Lb);
-    if (2 * ((int64_t)hp->batch_size * c / 8 + 1) * hp->M * 4 > 200 * 1024) MB_FAIL(ctx, MB200_E_UNSUPPORTED, "csc: batch x positions too large for the shared-memory median");
     if (l < 1 || (int64_t)l * hp->K < hp->q) MB_FAIL(ctx, MB200_E_INVALID, "csc: sequence length %lld too short for filter_len %d, h %d, q %d", (long long)Lb, hp->filter_len, hp->h, hp->q);
     MB_CUDA(ctx, cudaSetDevice(ctx->device));
     mb200_csc* s = new mb200_csc();
@@ -398,6 +426,8 @@ extern "C" int32_t mb200_csc_destroy(mb200_ctx* ctx, mb200_csc* s) {
     if (ctx) cudaSetDevice(ctx->device);
     if (s->gexec) cudaGraphExecDestroy(s->gexec);
     if (s->graph) cudaGraphDestroy(s->graph);
+    if (s->aux) cudaStreamDestroy(s->aux);
+    if (s->ev_fork) { cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_join); cudaEventDestroy(s->ev_fork2); cudaEventDestroy(s->ev_join2); }
     cudaFree(s->p_raw); cudaFree(s->g_raw); cudaFree(s->mt); cudaFree(s->st); cudaFree(s->data); cudaFree(s->grad); cudaFree(s->bits); cudaFree(s->lcnt); cudaFree(s->lidx); cudaFree(s->lval);
     cudaFree(s->bases); cudaFree(s->idx_dev); cudaFreeHost(s->idx_pinned); cudaFreeHost(s->host_out);
     delete s;
@@ -445,14 +475,23 @@ extern "C" int32_t mb200_csc_device_ptrs(const mb200_csc* s, void** params_dev, 
 }
 
 // enqueue: gather the batch, forward tape, (optionally) reverse tape.  No host sync inside.
+static void run_op(mb200_csc* s, Op& op, bool fwd, cudaStream_t q) {
+    auto fork = [&]() { cudaEventRecord(s->ev_fork2, q); cudaStreamWaitEvent(s->aux, s->ev_fork2, 0); s->in_branch = true; };
+    auto join = [&]() { cudaEventRecord(s->ev_join2, s->aux); cudaStreamWaitEvent(q, s->ev_join2, 0); s->in_branch = false; };
+    if (op.kind == 1) { if (fwd) fork(); else join(); return; }      // in the reverse pass the markers swap roles
+    if (op.kind == 2) { if (fwd) join(); else fork(); return; }
+    cudaStream_t qq = op.branch ? s->aux : q;
+    if (fwd) op.fwd(qq); else op.bwd(qq);
+}
+
 static void enqueue_step(mb200_csc* s, const uint32_t* words, int64_t rowwords, bool backward, cudaStream_t q) {
     const CscDims d = s->d;
     k_unpack_bases<<<nblk((int64_t)d.NS * d.Lb, 256), 256, 0, q>>>(words, rowwords, s->idx_dev, s->bases, d);
-    for (auto& op : s->tape) op.fwd(q);
+    for (auto& op : s->tape) run_op(s, op, true, q);
     if (backward) {
         cudaMemsetAsync(s->grad, 0, s->arena * 4, q);
         cudaMemsetAsync(s->g_raw, 0, (size_t)s->n_total * 4, q);
-        for (auto it = s->tape.rbegin(); it != s->tape.rend(); ++it) it->bwd(q);
+        for (auto it = s->tape.rbegin(); it != s->tape.rend(); ++it) run_op(s, *it, false, q);
     }
 }
 
@@ -488,6 +527,7 @@ static int64_t tape_launches(const mb200_csc* s, bool backward) {
     // counted once by running the tape on a capture-free dry pass is overkill; kernels per op are fixed:
     int64_t n = 1;
     for (auto& op : s->tape) {
+        if (op.kind) continue;
         const std::string nm = op.name;
         const int f = nm == "prep" ? 10 : 1;
         int b = 1;
@@ -619,7 +659,7 @@ extern "C" int32_t mb200_csc_codes(mb200_ctx* ctx, mb200_csc* s, const mb200_seq
         const int tc = tm.begin(T_CSC);
         // forward-only: run ops up to the last XYZ pass (a forward_only handle holds exactly those)
         k_unpack_bases<<<nblk((int64_t)d.NS * d.Lb, 256), 256, 0, ctx->stream>>>(seqs->words, seqs->rowwords, s->idx_dev, s->bases, d);
-        for (auto& op : s->tape) { op.fwd(ctx->stream); if (std::string(op.name) == "df_mask") break; }
+        for (auto& op : s->tape) { if (op.kind) break; op.fwd(ctx->stream); if (std::string(op.name) == "df_mask") break; }
         k_emit_codes<<<nblk((int64_t)d.NS * 32, 128), 128, 0, ctx->stream>>>(s->data + s->named["x"].off, first_seq + s0, d_slots, d_cnt, d);
         tm.end(tc);
         ctx->launches[T_CSC] += tape_launches(s, false) + 1;

@@ -1150,6 +1150,7 @@ __global__ void __launch_bounds__(1024) k_mask_scale_s(const float* __restrict__
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 #define CL 8
+#define MS_MAXV 32        // values per thread the cluster median kernel keeps in registers (512 threads: 16384 per CTA)
 
 // T3 on a cluster: CTA r of the cluster reduces slice r of the group's (sequence, position) pairs; the 8 partial rows
 // land in CTA 0's shared memory and are summed there in rank order.
@@ -1205,7 +1206,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(512) k_mask_scale_c
     cg::cluster_group cluster = cg::this_cluster();
     const int r = (int)cluster.block_rank();
     const int g = blockIdx.x / CL;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int rows_total = d.B * d.c;
     const int R = (rows_total + CL - 1) / CL;
     const int row0 = min(rows_total, r * R), row1 = min(rows_total, row0 + R);
@@ -1217,17 +1218,24 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(512) k_mask_scale_c
     if (threadIdx.x == 0) s_lcnt = 0;
     if (r == 0) { if (threadIdx.x < 256) ghist[threadIdx.x] = 0; if (threadIdx.x < 8) ctl[threadIdx.x] = threadIdx.x == 4 ? 0x7f800000u : 0u; }
     __syncthreads();
-    // 1. compact local positives
-    for (int e0 = 0; e0 < 2 * EZ; e0 += blockDim.x) {
-        const int e = e0 + threadIdx.x;
-        float v = 0.f;
-        if (e < EZ) v = zg[e]; else if (e < 2 * EZ) v = yg[e - EZ];
-        const bool pos = v > 0.f;
-        const unsigned mk = __ballot_sync(FULLMASK, pos);
-        unsigned base = 0;
-        if (lane == 0 && mk) base = atomicAdd(&s_lcnt, __popc(mk));
-        base = __shfl_sync(FULLMASK, base, 0);
-        if (pos) s_pos[base + __popc(mk & ((1u << lane) - 1u))] = v;
+    // 1. this thread's share of the slice goes to registers with all loads in flight at once (the slice is read from
+    //    global memory exactly once: the same registers feed the compaction and the final masking)
+    float v[MS_MAXV];
+    #pragma unroll
+    for (int it = 0; it < MS_MAXV; ++it) {
+        const int e = it * (int)blockDim.x + threadIdx.x;
+        v[it] = e < EZ ? zg[e] : (e < 2 * EZ ? yg[e - EZ] : 0.f);
+    }
+    #pragma unroll
+    for (int it = 0; it < MS_MAXV; ++it) {
+        if (it * (int)blockDim.x < 2 * EZ) {                       // block-uniform
+            const bool pos = v[it] > 0.f;
+            const unsigned mk = __ballot_sync(FULLMASK, pos);
+            unsigned base = 0;
+            if (lane == 0 && mk) base = atomicAdd(&s_lcnt, __popc(mk));
+            base = __shfl_sync(FULLMASK, base, 0);
+            if (pos) s_pos[base + __popc(mk & ((1u << lane) - 1u))] = v[it];
+        }
     }
     __syncthreads();
     const unsigned int lpos = s_lcnt;
@@ -1285,13 +1293,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(512) k_mask_scale_c
         }
     }
     if (r == 0 && threadIdx.x == 0) med_out[g] = med;
-    // 2. apply on the CTA's rows: lanes over m
+    // 2. apply the mask to the CTA's slice from the registers
     float* og = zy + ((int64_t)g * rows_total + row0) * d.M2;
-    for (int np = warp; np < row1 - row0; np += nw)
-        for (int m = lane; m < d.M; m += 32) {
-            const float vz = zg[(int64_t)np * d.M + m], vy = yg[(int64_t)np * d.M + m];
-            og[(int64_t)np * d.M2 + m] = vz >= med ? d.mf * vz : 0.f;
-            og[(int64_t)np * d.M2 + d.M + m] = vy >= med ? d.mf * vy : 0.f;
+    #pragma unroll
+    for (int it = 0; it < MS_MAXV; ++it) {
+        const int e = it * (int)blockDim.x + threadIdx.x;
+        if (e < 2 * EZ) {
+            const int ee = e < EZ ? e : e - EZ;
+            const int np = ee / d.M, m = ee - np * d.M;
+            og[(int64_t)np * d.M2 + (e < EZ ? 0 : d.M) + m] = v[it] >= med ? d.mf * v[it] : 0.f;
         }
+    }
     cluster.sync();                                              // CTA 0's shared memory must outlive every remote access
 }
