@@ -99,13 +99,28 @@ __global__ void __launch_bounds__(256) k_recon(const float* __restrict__ ca, con
     const int p_hi = min(d.c - 1, t >> 2);
     const int p_lo = max(0, (t - d.f_len + 4) >> 2);            // smallest p with t-4p <= f_len-1
     float acc = 0.f;
-    for (int p = p_lo; p <= p_hi; ++p) {
-        const int k = t - 4 * p;
-        const float* a = ca + (n * d.c + p) * d.M;
-        const float* b = cb + (n * d.c + p) * d.M;
-        const float* f0 = F + k * d.M;
-        const float* f1 = F + (d.f_len - 1 - k) * d.M;
-        for (int m = lane; m < d.M; m += 32) acc += a[m] * f0[m] + b[m] * f1[m];
+    if (p_hi - p_lo < 8) {                                       // f_len = 32: at most 8 positions reach t; unrolled so every load is in flight
+        #pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+            const int p = p_lo + pp;
+            if (p <= p_hi) {
+                const int k = t - 4 * p;
+                const float* a = ca + (n * d.c + p) * d.M;
+                const float* b = cb + (n * d.c + p) * d.M;
+                const float* f0 = F + k * d.M;
+                const float* f1 = F + (d.f_len - 1 - k) * d.M;
+                for (int m = lane; m < d.M; m += 32) acc += a[m] * f0[m] + b[m] * f1[m];
+            }
+        }
+    } else {
+        for (int p = p_lo; p <= p_hi; ++p) {
+            const int k = t - 4 * p;
+            const float* a = ca + (n * d.c + p) * d.M;
+            const float* b = cb + (n * d.c + p) * d.M;
+            const float* f0 = F + k * d.M;
+            const float* f1 = F + (d.f_len - 1 - k) * d.M;
+            for (int m = lane; m < d.M; m += 32) acc += a[m] * f0[m] + b[m] * f1[m];
+        }
     }
     acc = warp_sum(acc);
     if (lane == 0) { if (accumulate) out[wid] += acc; else out[wid] = acc; }
@@ -131,6 +146,7 @@ __global__ void __launch_bounds__(256) k_corr_sig(const float* __restrict__ sig,
     const int64_t n = np / d.c;
     const float* F = filt + (n / d.B) * filt_gs;
     float a = 0.f, b = 0.f;
+    #pragma unroll 8
     for (int k = 0; k < d.f_len; ++k) {
         const float r = sig_at(sig, bases, sgn, n, 4 * p + k, d);
         a += r * F[k * d.M + m];
@@ -999,29 +1015,37 @@ __global__ void __launch_bounds__(128) k_fgrad_l(const float* __restrict__ A, co
     __shared__ float s_v[256];
     __shared__ int s_cnt, s_dense;
     const int k = blockIdx.x, a = blockIdx.y, g = blockIdx.z;
+    // gather: the group's list entries form a virtual array [b][q] (q < LIST_CAP); every thread tests a few of them with
+    // independent loads, then an ordered block-wide compaction keeps (sequence, position) order
+    __shared__ int s_wsum[8];
     if (threadIdx.x == 0) { s_cnt = 0; s_dense = 0; }
     __syncthreads();
-    if (threadIdx.x < 32) {                      // one warp gathers in order
-        int cnt = 0;
-        int c_all = threadIdx.x < d.B ? lcnt[(int64_t)g * d.B + threadIdx.x] : 0;       // B <= 32 counts in one load
-        for (int b = 0; b < d.B; ++b) {
-            const int64_t n = (int64_t)g * d.B + b;
-            const int c = d.B <= 32 ? __shfl_sync(FULLMASK, c_all, b) : lcnt[n];
-            if (c > LIST_CAP) { if (threadIdx.x == 0) s_dense = 1; break; }
-            for (int q0 = 0; q0 < c; q0 += 32) {
-                const int q = q0 + threadIdx.x;
-                int e = 0; bool hit = false;
-                if (q < c) { e = lidx[n * LIST_CAP + q]; hit = (e % d.K) == k; }
-                const unsigned m = __ballot_sync(FULLMASK, hit);
-                if (hit) {
-                    const int o = cnt + __popc(m & ((1u << threadIdx.x) - 1u));
-                    if (o < 256) { s_n[o] = (int)n; s_i[o] = e / d.K; s_v[o] = lval[n * LIST_CAP + q]; }
-                }
-                cnt += __popc(m);
-            }
+    const int total_slots = d.B * LIST_CAP;
+    int running = 0;
+    for (int base0 = 0; base0 < total_slots; base0 += blockDim.x) {          // block-uniform trip count (3 for B = 6)
+        const int slot = base0 + threadIdx.x;
+        const int b = slot / LIST_CAP, q = slot - b * LIST_CAP;
+        bool hit = false; int e = 0; float v = 0.f; int64_t n = 0;
+        if (slot < total_slots) {
+            n = (int64_t)g * d.B + b;
+            const int c = lcnt[n];
+            if (c > LIST_CAP) s_dense = 1;
+            else if (q < c) { e = lidx[n * LIST_CAP + q]; hit = (e % d.K) == k; if (hit) v = lval[n * LIST_CAP + q]; }
         }
-        if (threadIdx.x == 0) { s_cnt = cnt; if (cnt > 256) s_dense = 1; }
+        const unsigned mk = __ballot_sync(FULLMASK, hit);
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (lane == 0) s_wsum[w] = __popc(mk);
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { if (i < w) woff += s_wsum[i]; tot += s_wsum[i]; }
+        if (hit) {
+            const int o = running + woff + __popc(mk & ((1u << lane) - 1u));
+            if (o < 256) { s_n[o] = (int)n; s_i[o] = e / d.K; s_v[o] = v; }
+        }
+        running += tot;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) { s_cnt = running; if (running > 256) s_dense = 1; }
     __syncthreads();
     if (!s_dense) {
         const int cnt = s_cnt;
