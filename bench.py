@@ -252,7 +252,10 @@ def bench_scan(args, ctx, torch, dist, world, rank, local, dev, stream):
                "e2e": {"value": total_bp / (ms_e2e / 1e3), "unit": "bp/s", "ms_per_step": ms_e2e,
                        "h2d_bytes_per_step": int(n_local * Lb + pw.nbytes + lens.nbytes + 2 * K), "d2h_bytes_per_step": int(K * 4 * 8)},
                "gpu_launches": int(n_launch), "clocks": clocks,
-               "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+               "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                            # ncu --set full, profiles/r01_scan_v2_ncu_full_summary.csv: dram read+write = 30.76 KB per sequence of a launch
+                            # (hit-mask writes: 1 bit per motif, strand, position); algorithmic bytes are 50 B per sequence
+                            "traffic": 30760.0 * (n_local / launches_per_step) if (Lb == 200 and K == 500) else None,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "kernel": "scan_kernel",
                             "ms_per_launch": ms_per_launch, "kernel_share_of_step": (t_scan / args.steps) / ms_step,
                             "count_kernel_share_of_step": (t_cnt / args.steps) / ms_step,
