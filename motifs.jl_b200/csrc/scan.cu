@@ -422,6 +422,98 @@ __global__ void __launch_bounds__(256) count_kernel(const uint32_t* __restrict__
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Counting for long sequences (chromosome-scale, BASELINE config 5): the W mask words of a sequence are cut into blocks of
+// WB words so that one thread per (sequence, block, motif) runs in parallel.  Coverage needs only a short look-back (a hit
+// reaches at most len-1 positions forward); the union_ranges quirk needs the two largest distinct start positions of the whole
+// sequence, found with two rounds of atomicMax.
+// ---------------------------------------------------------------------------------------------
+struct LongCand { int32_t p1, p2, dup; };
+
+__global__ void __launch_bounds__(256) count_long_a(const uint32_t* __restrict__ mask, int64_t nseq, int32_t W, int32_t K2pad, int32_t WB, int32_t nblocks,
+                                                    const int32_t* __restrict__ pair2motif, const int32_t* __restrict__ pairlen,
+                                                    unsigned long long* __restrict__ counts, unsigned long long* __restrict__ top1,
+                                                    unsigned int* __restrict__ nh_seq, LongCand* __restrict__ cand) {
+    const int32_t P = K2pad / 2;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nseq * nblocks * P) return;
+    const int32_t m2 = (int32_t)(t % P);
+    const int64_t nb = t / P;
+    const int32_t wb = (int32_t)(nb % nblocks);
+    const int64_t n = nb / nblocks;
+    LongCand c; c.p1 = -1; c.p2 = -1; c.dup = 0;
+    const int32_t k = pair2motif[m2];
+    if (k >= 0) {
+        const int32_t len = pairlen[m2];
+        const uint2* mp = reinterpret_cast<const uint2*>(mask) + (n * W) * (int64_t)P + m2;
+        const int32_t w0 = wb * WB, w1 = min(W, w0 + WB);
+        int32_t cu = 0;
+        const int32_t LB = (len + 31) / 32 + 1;
+        for (int32_t w = w0 - 1; w >= max(0, w0 - LB); --w) {           // nearest earlier hit decides the carried coverage
+            const uint2 fr = __ldg(mp + (int64_t)w * P);
+            const uint32_t U = fr.x | fr.y;
+            if (U) { cu = w * 32 + 31 - __clz(U) + len; break; }
+        }
+        uint32_t nf = 0, nr = 0, uq = 0; unsigned long long cov = 0;
+        for (int32_t w = w0; w < w1; ++w) {
+            const uint2 fr = __ldg(mp + (int64_t)w * P);
+            const uint32_t f = fr.x, r = fr.y, U = f | r;
+            const int32_t base = w * 32;
+            const int32_t cb = cu - base;
+            uint32_t cm = cb >= 32 ? 0xffffffffu : (cb > 0 ? ((1u << cb) - 1u) : 0u);
+            if (U) {
+                nf += __popc(f); nr += __popc(r); uq += __popc(U);
+                cm |= dilate32(U, len);
+                const int32_t hi = 31 - __clz(U);
+                cu = max(cu, base + hi + len);
+                const uint32_t U2 = U & ~(1u << hi);
+                c.p2 = U2 ? base + 31 - __clz(U2) : c.p1;
+                c.p1 = base + hi;
+                c.dup = ((f >> hi) & (r >> hi) & 1u) != 0;
+            }
+            cov += __popc(cm);
+        }
+        if (w1 == W) cov += (unsigned long long)max(0, cu - W * 32);   // positions covered past the last mask word
+        const uint32_t nh = nf + nr;
+        if (nh) {
+            atomicAdd(&counts[k * 4 + 0], (unsigned long long)nh);
+            atomicAdd(&counts[k * 4 + 1], (unsigned long long)uq);
+            atomicAdd(&nh_seq[n * P + m2], nh);
+            atomicMax(&top1[n * P + m2], (unsigned long long)(c.p1 + 1));
+        }
+        if (cov) { atomicAdd(&counts[k * 4 + 2], cov); atomicAdd(&counts[k * 4 + 3], cov); }
+    }
+    cand[t] = c;
+}
+__global__ void __launch_bounds__(256) count_long_b(int64_t nseq, int32_t P, int32_t nblocks, const LongCand* __restrict__ cand,
+                                                    const unsigned long long* __restrict__ top1, unsigned long long* __restrict__ top2,
+                                                    unsigned int* __restrict__ dupflag) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nseq * nblocks * P) return;
+    const int32_t m2 = (int32_t)(t % P);
+    const int64_t n = (t / P) / nblocks;
+    const LongCand c = cand[t];
+    if (c.p1 < 0) return;
+    const long long g1 = (long long)top1[n * P + m2] - 1;
+    int32_t second;
+    if (c.p1 == g1) { second = c.p2; if (c.dup) dupflag[n * P + m2] = 1u; } else second = c.p1;
+    if (second >= 0) atomicMax(&top2[n * P + m2], (unsigned long long)(second + 1));
+}
+__global__ void __launch_bounds__(256) count_long_c(int64_t nseq, int32_t P, const int32_t* __restrict__ pair2motif, const int32_t* __restrict__ pairlen,
+                                                    const unsigned long long* __restrict__ top1, const unsigned long long* __restrict__ top2,
+                                                    const unsigned int* __restrict__ dupflag, const unsigned int* __restrict__ nh_seq,
+                                                    unsigned long long* __restrict__ counts) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nseq * P) return;
+    const int32_t m2 = (int32_t)(t % P);
+    const int32_t k = pair2motif[m2];
+    if (k < 0 || nh_seq[t] < 2 || dupflag[t]) return;
+    const long long p1 = (long long)top1[t] - 1, p2 = (long long)top2[t] - 1;
+    const long long drop = min((long long)pairlen[m2], p1 - p2);           // union_ranges never visits the last sorted interval
+    atomicAdd(&counts[k * 4 + 2], (unsigned long long)(-drop));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Exclusive prefix sum u32 -> u64 (three small kernels), used to place hits without atomics.
 // ---------------------------------------------------------------------------------------------
@@ -820,11 +912,30 @@ extern "C" int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs, const uint
         MB_CUDA(ctx, cudaGetLastError());
 
         int t2 = tm.begin(T_COUNT);
-        const int64_t cthreads = ns * (P.K2pad / 2);
-        count_kernel<<<(unsigned)((cthreads + 255) / 256), 256, 0, ctx->stream>>>(d_mask, ns, W, P.K2pad, (const int32_t*)(d_plan + off_p2m),
-                                                                              (const int32_t*)(d_plan + off_plen), d_counts, d_unit_cnt, K);
+        const int32_t Pp = P.K2pad / 2;
+        if (!want_hits && W > 4096) {
+            // chromosome-scale sequences: blocked parallel counting
+            const int32_t WB = 512, nblocks = (W + WB - 1) / WB;
+            const int64_t nbt = ns * (int64_t)nblocks * Pp;
+            const size_t o_top1 = 0, o_top2 = o_top1 + (size_t)ns * Pp * 8, o_nh = o_top2 + (size_t)ns * Pp * 8, o_dup = o_nh + (size_t)ns * Pp * 4;
+            const size_t o_cand = (o_dup + (size_t)ns * Pp * 4 + 255) & ~(size_t)255;
+            rc = mb_ensure_buf(ctx, 7, o_cand + (size_t)nbt * sizeof(LongCand)); if (rc) return rc;
+            uint8_t* lb = (uint8_t*)ctx->bufs[7];
+            MB_CUDA(ctx, cudaMemsetAsync(lb, 0, o_cand, ctx->stream));
+            count_long_a<<<(unsigned)((nbt + 255) / 256), 256, 0, ctx->stream>>>(d_mask, ns, W, P.K2pad, WB, nblocks, (const int32_t*)(d_plan + off_p2m),
+                (const int32_t*)(d_plan + off_plen), d_counts, (unsigned long long*)(lb + o_top1), (unsigned int*)(lb + o_nh), (LongCand*)(lb + o_cand));
+            count_long_b<<<(unsigned)((nbt + 255) / 256), 256, 0, ctx->stream>>>(ns, Pp, nblocks, (const LongCand*)(lb + o_cand), (const unsigned long long*)(lb + o_top1),
+                (unsigned long long*)(lb + o_top2), (unsigned int*)(lb + o_dup));
+            count_long_c<<<(unsigned)((ns * Pp + 255) / 256), 256, 0, ctx->stream>>>(ns, Pp, (const int32_t*)(d_plan + off_p2m), (const int32_t*)(d_plan + off_plen),
+                (const unsigned long long*)(lb + o_top1), (const unsigned long long*)(lb + o_top2), (const unsigned int*)(lb + o_dup), (const unsigned int*)(lb + o_nh), d_counts);
+            ctx->launches[T_COUNT] += 3;
+        } else {
+            const int64_t cthreads = ns * Pp;
+            count_kernel<<<(unsigned)((cthreads + 255) / 256), 256, 0, ctx->stream>>>(d_mask, ns, W, P.K2pad, (const int32_t*)(d_plan + off_p2m),
+                                                                                  (const int32_t*)(d_plan + off_plen), d_counts, d_unit_cnt, K);
+            ctx->launches[T_COUNT] += 1;
+        }
         tm.end(t2);
-        ctx->launches[T_COUNT] += 1;
         MB_CUDA(ctx, cudaGetLastError());
 
         if (want_hits) {

@@ -188,3 +188,37 @@ def test_reference_entry_points(ctx):
     assert np.array_equal(uq, c[:, 1]) and np.array_equal(uqb, cb[:, 1])
     p = inference.get_fisher_p_values(ms, data)
     assert np.allclose(p, st.fisher_pvec(oc[:, 2], ocb[:, 2], 600, 100), rtol=1e-9, atol=0)
+
+
+def test_chromosome_scale_counts(ctx):
+    """config 5 shape at test size: one long sequence, tiled scan with motif-length halos, blocked parallel counting (W > 4096
+    mask words) — counts equal the oracle's on the untiled sequence; the 1-mer shuffled background gives the Fisher inputs."""
+    from motifs_jl_b200 import inference
+    from types import SimpleNamespace
+    Lb = 400_000
+    a = synth.random_ascii(1, Lb, 81)
+    site = np.frombuffer(b"TGACGTCATTGACGTCA", np.uint8)
+    rng = np.random.default_rng(82)
+    for p in rng.integers(0, Lb - 20, 300):
+        a[0, p:p + len(site)] = site                     # planted family
+    a[0, Lb - 17:] = site                                # a hit ending exactly at the end of the sequence
+    a[0, 131072 - 8:131072 - 8 + 17] = site              # a hit straddling a counting-block boundary (512 words = 16384 positions)
+    bg = synth.shuffle_rows(a, 83)
+    cms = [synth.count_matrix_from_sites(["TGACGTCATTGACGTCA"] * 30), synth.count_matrix_from_sites(["TGACGTCA"] * 30)] + \
+        synth.random_count_matrices(10, 8, 40, 84)
+    ms = synth.motifs_from_count_matrices(cms)
+    pw, lens = so.pack_pwms(ms.pwms)
+    thr = synth.stated_thresholds(ms, 0.6)
+    res = []
+    for rows in (a, bg):
+        seqs = ctx.seqs_from_ascii(rows)
+        _, c = ctx.scan(seqs, pw, lens, thr, want_hits=False)
+        _, oc = so.scan(pw, lens, so.ascii_to_codes(rows), thr, want_hits=False)
+        assert np.array_equal(c, oc)
+        _, c0 = ctx.scan(seqs, pw, lens, None, want_hits=False)          # dense regime (score > 0): exercises the look-back
+        _, oc0 = so.scan(pw, lens, so.ascii_to_codes(rows), None, want_hits=False)
+        assert np.array_equal(c0, oc0)
+        res.append(c)
+        seqs.free()
+    p = inference.fisher_pvec(res[0][:, 2], res[1][:, 2], SimpleNamespace(N=1, L=Lb, N_test=0))
+    assert p[0] < 1e-10 and p[1] < 1e-10                                # the planted family is enriched over the shuffle
