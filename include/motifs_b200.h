@@ -105,6 +105,13 @@ int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs,
                    const uint16_t* thresh_f16, uint32_t flags,
                    mb200_hit* hits, int64_t hits_cap, int64_t* n_hits, int64_t* counts);
 
+/* Score histogram of the unthresholded scan (hits = score > 0): hist[k*32768 + b] = number of hits of motif k whose Float16
+ * score has the 15-bit pattern b (positive halves order like their bit patterns).  Replaces the hit lists as the input of the
+ * threshold sweep in get_best_thresh (inference/_s2_filter_pos_w_scores.jl:99-113) and of get_max_score / get_min_score
+ * (:11-36).  flags: MB200_SCAN_FWD | MB200_SCAN_RC.                                              */
+int32_t mb200_scan_hist(mb200_ctx* ctx, const mb200_seqs* seqs,
+                        const uint16_t* pwms_f16, const int64_t* lens, int32_t K, int32_t maxlen,
+                        uint32_t flags, uint32_t* hist);
 
 /* ---- unrolled convolutional-sparse-coding network: replaces the GPU work inside
  *      forward_pass_return_loss (model.jl:375-395) + gradient(ps) + Flux.Optimise.update!

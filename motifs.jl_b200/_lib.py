@@ -70,6 +70,7 @@ def load():
         "mb200_seqs_shape": (i32, [p, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
         "mb200_seqs_download": (i32, [p, p, p, i64]),
         "mb200_scan": (i32, [p, p, p, p, i32, i32, p, C.c_uint32, p, i64, C.POINTER(i64), p]),
+        "mb200_scan_hist": (i32, [p, p, p, p, i32, i32, C.c_uint32, p]),
         "mb200_csc_create": (i32, [p, C.POINTER(HParams), i64, i32, i32, C.POINTER(p)]),
         "mb200_csc_destroy": (i32, [p, p]),
         "mb200_csc_n_params": (i32, [p, C.POINTER(i64), C.POINTER(i64)]),
@@ -210,6 +211,19 @@ def count_matrices(ctx: "Context", seqs: "Sequences", sites, lens):
     out = np.zeros((K, maxlen, 4), np.uint32)
     ctx._check(ctx._lib.mb200_count_matrices(ctx._h, seqs._h, _ptr(st), len(st), _ptr(ln), K, maxlen, _ptr(out)))
     return [out[k, : ln[k]].T.copy() for k in range(K)]
+
+
+def scan_hist(ctx: "Context", seqs: "Sequences", pwms_f16, lens, fwd=True, rc=True):
+    """(K, 32768) uint32 histogram of the Float16 bit patterns of all hit scores (score > 0)."""
+    pw = np.ascontiguousarray(pwms_f16)
+    if pw.dtype == np.float16:
+        pw = pw.view(np.uint16)
+    maxlen, _, K = pw.shape
+    ln = np.ascontiguousarray(lens, dtype=np.int64)
+    out = np.zeros((K, 32768), np.uint32)
+    flags = (SCAN_FWD if fwd else 0) | (SCAN_RC if rc else 0)
+    ctx._check(ctx._lib.mb200_scan_hist(ctx._h, seqs._h, _ptr(pw), _ptr(ln), K, maxlen, flags, _ptr(out)))
+    return out
 
 
 class Sequences:

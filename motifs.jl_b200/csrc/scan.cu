@@ -619,6 +619,41 @@ __global__ void __launch_bounds__(256) emit_kernel(const uint32_t* __restrict__ 
     }
 }
 
+
+// Score histogram: for every hit the Float16 score is recomputed as in emit_kernel and counted in
+// hist[motif][score bits] (positive halves order like their 15-bit patterns).  Feeds the threshold sweep of get_best_thresh
+// (inference/_s2_filter_pos_w_scores.jl:99-113: hits with score > t for t = min_score : 0.5 : max_score) without building hit lists.
+#define HIST_BINS 32768
+__global__ void __launch_bounds__(256) hist_kernel(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ seqw, int64_t rowwords,
+                                                   int64_t seq0, int64_t nseq, int32_t W, int32_t K2pad, int32_t K,
+                                                   const EmitMotif* __restrict__ em, const uint8_t* __restrict__ blob, unsigned int* __restrict__ hist) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nseq * K * 2) return;
+    const int32_t strand = (int32_t)(u & 1);
+    const int64_t nk = u >> 1;
+    const int64_t n = nk / K;
+    const int32_t k = (int32_t)(nk - n * K);
+    const EmitMotif m = em[k];
+    const int32_t slot = m.slot + strand;
+    const uint8_t* tab = blob + m.tab_off + strand * m.strand_stride;
+    const uint32_t* srow = seqw + (seq0 + n) * rowwords;
+    for (int32_t w = 0; w < W; ++w) {
+        uint32_t bits = mask[((n * W) + w) * (int64_t)K2pad + slot];
+        while (bits) {
+            const int32_t b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int32_t p = w * 32 + b;
+            __half s = __ushort_as_half((unsigned short)0);
+            for (int32_t j = 0; j < m.len; ++j) {
+                const int32_t q = p + j;
+                const uint32_t base = (srow[q >> 4] >> ((q & 15) * 2)) & 3u;
+                s = __hadd(s, *reinterpret_cast<const __half*>(tab + (int64_t)j * m.col_stride + base * m.base_stride));
+            }
+            atomicAdd(&hist[(int64_t)k * HIST_BINS + (__half_as_ushort(s) & 0x7FFFu)], 1u);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host side: plan (sorted groups, tables, thresholds), batching, launches.
 // ---------------------------------------------------------------------------------------------
@@ -764,9 +799,9 @@ static int build_plan(mb200_ctx* ctx, const uint16_t* pwms, const int64_t* lens,
     return MB200_OK;
 }
 
-extern "C" int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t* pwms_f16, const int64_t* lens, int32_t K,
-                              int32_t maxlen, const uint16_t* thresh_f16, uint32_t flags, mb200_hit* hits, int64_t hits_cap,
-                              int64_t* n_hits, int64_t* counts) {
+static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t* pwms_f16, const int64_t* lens, int32_t K,
+                         int32_t maxlen, const uint16_t* thresh_f16, uint32_t flags, mb200_hit* hits, int64_t hits_cap,
+                         int64_t* n_hits, int64_t* counts, uint32_t* hist) {
     if (!ctx) return MB200_E_INVALID;
     if (!seqs || !pwms_f16 || !lens || K <= 0 || K > 65535 || maxlen <= 0)
         MB_FAIL(ctx, MB200_E_INVALID, "scan: bad arguments (K=%d maxlen=%d)", K, maxlen);
@@ -780,6 +815,7 @@ extern "C" int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs, const uint
     mb_reset_timing(ctx);
     if (n_hits) *n_hits = 0;
     if (counts) memset(counts, 0, sizeof(int64_t) * 4 * (size_t)K);
+    if (hist) memset(hist, 0, (size_t)K * HIST_BINS * 4);
 
     const int64_t N = seqs->N, Lb = seqs->Lb, rowwords = seqs->rowwords;
     const size_t table_budget = 160 * 1024;
@@ -864,6 +900,12 @@ extern "C" int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs, const uint
     unsigned long long* d_total = (unsigned long long*)(d_plan + off_tot);
     int64_t* d_rng = (int64_t*)(d_plan + off_rng);
 
+    unsigned int* d_hist = nullptr;
+    if (hist) {
+        rc = mb_ensure_buf(ctx, 0, (size_t)K * HIST_BINS * 4); if (rc) return rc;
+        d_hist = (unsigned int*)ctx->bufs[0];
+        MB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, (size_t)K * HIST_BINS * 4, ctx->stream));
+    }
     int64_t hits_written = 0, hits_needed = 0;
     std::vector<int64_t> h_rng(grid + 1);
     int64_t last_nchunks = -1;
@@ -938,6 +980,15 @@ extern "C" int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs, const uint
         tm.end(t2);
         MB_CUDA(ctx, cudaGetLastError());
 
+        if (hist) {
+            const int64_t units = ns * K * 2;
+            const int t7 = tm.begin(T_EMIT);
+            hist_kernel<<<(unsigned)((units + 255) / 256), 256, 0, ctx->stream>>>(d_mask, seqs->words, rowwords, s0, ns, W, P.K2pad, K,
+                                                                               (const EmitMotif*)(d_plan + off_em), d_plan + off_blob, d_hist);
+            tm.end(t7);
+            ctx->launches[T_EMIT] += 1;
+            MB_CUDA(ctx, cudaGetLastError());
+        }
         if (want_hits) {
             const int64_t units = ns * K * 2;
             const int64_t nb = (units + PS_TILE - 1) / PS_TILE;
@@ -969,6 +1020,11 @@ extern "C" int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs, const uint
             }
         }
     }
+    if (hist) {
+        int t8 = tm.begin(T_D2H);
+        MB_CUDA(ctx, cudaMemcpyAsync(hist, d_hist, (size_t)K * HIST_BINS * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        tm.end(t8);
+    }
     if (want_counts) {
         int t6 = tm.begin(T_D2H);
         MB_CUDA(ctx, cudaMemcpyAsync(counts, d_counts, (size_t)K * 4 * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -981,4 +1037,19 @@ extern "C" int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs, const uint
     if (want_hits && hits_needed > hits_cap)
         MB_FAIL(ctx, MB200_E_HITS_OVERFLOW, "scan: %lld hits, capacity %lld", (long long)hits_needed, (long long)hits_cap);
     return MB200_OK;
+}
+
+extern "C" int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t* pwms_f16, const int64_t* lens, int32_t K,
+                              int32_t maxlen, const uint16_t* thresh_f16, uint32_t flags, mb200_hit* hits, int64_t hits_cap,
+                              int64_t* n_hits, int64_t* counts) {
+    return scan_impl(ctx, seqs, pwms_f16, lens, K, maxlen, thresh_f16, flags, hits, hits_cap, n_hits, counts, nullptr);
+}
+
+// hist: K * 32768 uint32, hist[k][b] = number of hits (score > 0, both requested strands) whose Float16 score has bit pattern b.
+extern "C" int32_t mb200_scan_hist(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t* pwms_f16, const int64_t* lens, int32_t K,
+                                   int32_t maxlen, uint32_t flags, uint32_t* hist) {
+    if (!ctx) return MB200_E_INVALID;
+    if (!hist) MB_FAIL(ctx, MB200_E_INVALID, "scan_hist: null histogram");
+    const uint32_t f = (flags & (MB200_SCAN_FWD | MB200_SCAN_RC));
+    return scan_impl(ctx, seqs, pwms_f16, lens, K, maxlen, nullptr, f, nullptr, 0, nullptr, nullptr, hist);
 }

@@ -419,6 +419,53 @@ def scan_counts(ms: Motifs, data, bg=False, test=False, thresh=None):
     return counts
 
 
+def scan_hist(ms: Motifs, data, bg=False, test=False):
+    """(K, 32768) histogram of the Float16 bit patterns of every hit score (score > 0, both strands) of one data set."""
+    seqs = _which(data, bg=bg, test=test)
+    return _lib.scan_hist(seqs.ctx, seqs, pack_pwms(ms), ms.lens)
+
+
+def get_best_thresh_hist(h_fg, h_bg, eff_pos, pwm, asum, bg):
+    """get_best_thresh (_s2_filter_pos_w_scores.jl:90-114) from the score histograms of the foreground and background scans
+    instead of the hit dictionaries: identical result, no hit lists."""
+    if any(len(r) < max_pwm_length_Touzet2 for r in eff_pos):
+        best = 0.0
+        for r in eff_pos:
+            if len(r) > max_pwm_length_Touzet2 or len(r) <= 1:
+                continue
+            sub = np.asarray(pwm, f16)[:, r.start - 1: r.stop - 1]
+            best += pvalue2score(sub, get_pvalue(sub), bg=bg)
+        return best
+    both = np.nonzero((h_fg + h_bg)[: 0x7C01])[0]                       # positive finite halves and +Inf, ascending in value
+    if len(both) == 0:
+        return f16(np.inf)                                               # get_min_score of nothing (:24-36)
+    min_score = np.array([both[0]], np.uint16).view(f16)[0]
+    max_score = np.array([both[-1]], np.uint16).view(f16)[0]
+    tail_fg = np.concatenate([np.cumsum(h_fg[::-1].astype(np.int64))[::-1], [0]])   # tail[b] = hits with pattern >= b
+    tail_bg = np.concatenate([np.cumsum(h_bg[::-1].astype(np.int64))[::-1], [0]])
+    best_thresh, t, best_p = min_score, min_score, f32(1)
+    while t < max_score:
+        b = int(np.array([t], f16).view(np.uint16)[0])
+        a_, b_ = int(tail_fg[b + 1]), int(tail_bg[b + 1])                # scores strictly greater than t
+        p = fisher_right(a_, asum - a_, b_, asum - b_)
+        if p < best_p:
+            best_p, best_thresh = p, t
+        t = f16(t + score_thresh_increment)
+    return best_thresh
+
+
+def filter_positions_scores_usecomp_fused_(ms: Motifs, data, bg):
+    """filter_positions_scores_usecomp! without hit lists: thresholds from two histogram scans, then the filtered occurrence counts
+    from two fused counting scans.  Sets ms.score_thresh / max_scores / min_scores; returns (counts_fg, counts_bg) as (K,4) arrays."""
+    K = ms.num_motifs
+    h_fg, h_bg = scan_hist(ms, data), scan_hist(ms, data, bg=True)
+    ms.score_thresh = np.zeros(K, f16)
+    for i in range(K):
+        with np.errstate(over="ignore"):
+            ms.score_thresh[i] = f16(get_best_thresh_hist(h_fg[i], h_bg[i], ms.effective_segments[i], ms.pwms[i], data.N * data.L, bg))
+    return scan_counts(ms, data, thresh=ms.score_thresh), scan_counts(ms, data, bg=True, thresh=ms.score_thresh)
+
+
 def pvec_from_test_data(ms: Motifs, data, no_olap=False):
     """render/pvec_calculations.jl:1-22 — test-set scans filtered by ms.score_thresh, union coverage, Fisher.
     The scan, the filter and both counts are one fused library call per data set."""

@@ -222,3 +222,35 @@ def test_chromosome_scale_counts(ctx):
         seqs.free()
     p = inference.fisher_pvec(res[0][:, 2], res[1][:, 2], SimpleNamespace(N=1, L=Lb, N_test=0))
     assert p[0] < 1e-10 and p[1] < 1e-10                                # the planted family is enriched over the shuffle
+
+
+def test_score_histogram_and_fused_thresholds(ctx):
+    """mb200_scan_hist == histogram of the oracle's hit scores; thresholds derived from histograms == thresholds derived from
+    the hit dictionaries (filter_positions_scores_usecomp!), for the Touzet branch and for the Fisher-sweep branch."""
+    from types import SimpleNamespace
+    import copy
+    a = synth.planted_gapped(500, 100, 12)
+    bg = synth.shuffle_rows(a, 13)
+    cms = [synth.count_matrix_from_sites(["TGACGT"] * 40),                                   # short segments: Touzet branch
+           synth.count_matrix_from_sites(["TGACGTAAAAAACGTCA"] * 9 + ["TGACGTCCCCCACGTCA"] * 9),
+           synth.count_matrix_from_sites(["ACGTTGCAACGTTGCAAC"] * 25)]                      # one long high-IC segment: sweep branch
+    ms = synth.motifs_from_count_matrices(cms)
+    assert any(all(len(r) >= 15 for r in segs) for segs in ms.effective_segments)
+    data = SimpleNamespace(N=500, L=100, seqs=ctx.seqs_from_ascii(a), seqs_bg=ctx.seqs_from_ascii(bg))
+    pw, lens = so.pack_pwms(ms.pwms)
+    h = inference.scan_hist(ms, data)
+    oh, _ = so.scan(pw, lens, so.ascii_to_codes(a))
+    exp = np.zeros_like(h)
+    np.add.at(exp, (oh["motif"].astype(np.int64), oh["score_f16"].astype(np.int64)), 1)
+    assert np.array_equal(h, exp)
+    bgfreq = np.full(4, 0.25, np.float32)
+    ms_dict = copy.deepcopy(ms)
+    inference.scan_w_gpu_(ms_dict, data)
+    inference.scan_w_gpu_(ms_dict, data, bg=True)
+    inference.filter_positions_scores_usecomp_(ms_dict, data, bgfreq)
+    c, cb = inference.filter_positions_scores_usecomp_fused_(ms, data, bgfreq)
+    assert np.array_equal(ms.score_thresh.view(np.uint16), ms_dict.score_thresh.view(np.uint16))
+    uq, uqb = inference.get_uniq_counts(ms_dict)
+    assert np.array_equal(uq, c[:, 1]) and np.array_equal(uqb, cb[:, 1])
+    tot = [inference.get_total_occupied_positions(inference.get_union_ranges(p, l)) for p, l in zip(ms_dict.positions, ms_dict.lens)]
+    assert np.array_equal(np.array(tot), c[:, 2])
