@@ -145,6 +145,8 @@ int32_t mb200_csc_loss_grad(mb200_ctx* ctx, mb200_csc* csc, const mb200_seqs* se
                             const int64_t* seq_idx, float* loss_out, float* grads);
 /* same computation, asynchronous, results stay on the device */
 int32_t mb200_csc_step_begin(mb200_ctx* ctx, mb200_csc* csc, const mb200_seqs* seqs, const int64_t* seq_idx);
+/* same for a batch handed over as host ASCII rows (n_groups*batch_size rows of Lb bytes): the per-step `S |> gpu` of train.jl:41 */
+int32_t mb200_csc_step_begin_host(mb200_ctx* ctx, mb200_csc* csc, const uint8_t* ascii_rows, int64_t n_rows);
 /* AdaBelief update (Flux.Optimise.AdaBelief defaults eta=1e-3, beta=(0.9,0.999), eps=1e-8) with the
  * gradients on the device; returns the mean loss of that step and l1 = sum|prep_syntax_filters(F)|
  * (the early-stop statistic of train.jl:47-52).                                                  */

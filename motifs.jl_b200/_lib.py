@@ -80,6 +80,7 @@ def load():
         "mb200_csc_device_ptrs": (i32, [p, C.POINTER(p), C.POINTER(p)]),
         "mb200_csc_loss_grad": (i32, [p, p, p, p, p, p]),
         "mb200_csc_step_begin": (i32, [p, p, p, p]),
+        "mb200_csc_step_begin_host": (i32, [p, p, p, i64]),
         "mb200_csc_adabelief_step": (i32, [p, p, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "mb200_csc_get_buffer": (i32, [p, p, C.c_char_p, p, i64]),
         "mb200_csc_codes": (i32, [p, p, p, i64, i64, p, i64, C.POINTER(i64)]),
@@ -312,6 +313,16 @@ class CscModel:
         if idx.size != self.batch:
             raise ValueError(f"need {self.batch} sequence indices")
         self.ctx._check(self.ctx._lib.mb200_csc_step_begin(self.ctx._h, self._h, seqs._h, _ptr(idx)))
+
+    def step_begin_host(self, ascii_rows):
+        """batch handed over as host ASCII rows (batch x Lb uint8, or a raw host address for pinned buffers)."""
+        if isinstance(ascii_rows, int):
+            self.ctx._check(self.ctx._lib.mb200_csc_step_begin_host(self.ctx._h, self._h, C.c_void_p(ascii_rows), self.batch))
+            return
+        a = np.ascontiguousarray(ascii_rows, np.uint8)
+        if a.shape != (self.batch, self.Lb):
+            raise ValueError(f"need a ({self.batch}, {self.Lb}) uint8 array")
+        self.ctx._check(self.ctx._lib.mb200_csc_step_begin_host(self.ctx._h, self._h, _ptr(a), self.batch))
 
     def adabelief_step(self, eta=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
         loss, l1 = C.c_float(), C.c_float()

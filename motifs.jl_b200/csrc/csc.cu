@@ -17,6 +17,8 @@
 #include <functional>
 #include <map>
 
+#define IDX_RING 8
+
 namespace {
 
 struct Buf { size_t off = 0; size_t n = 0; };            // offsets in floats into the data / grad arenas
@@ -50,7 +52,11 @@ struct mb200_csc {
     bool in_branch = false;                              // set while replaying ops of a forked branch (no nested forking)
     uint8_t* bases = nullptr;
     int64_t* idx_dev = nullptr;
-    int64_t* idx_pinned = nullptr;
+    int64_t* idx_pinned = nullptr;                       // ring of IDX_RING slots of NS indices (a step may still be copying the previous one)
+    int ring = 0;
+    int64_t* idx_identity_dev = nullptr;                 // 0..NS-1, for batches that arrive from the host
+    uint32_t* batch_words = nullptr;                     // NS packed sequences of a host-supplied batch
+    uint32_t* batch_pinned = nullptr;
     float* host_out = nullptr;                           // pinned: loss[G*3], l1
     std::vector<Op> tape;
     std::map<std::string, Buf> named;
@@ -389,7 +395,17 @@ static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
     MB_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_join2, cudaEventDisableTiming));
     MB_CUDA(ctx, cudaMalloc(&s->bases, (size_t)s->d.NS * s->d.Lb));
     MB_CUDA(ctx, cudaMalloc(&s->idx_dev, (size_t)s->d.NS * 8));
-    MB_CUDA(ctx, cudaMallocHost(&s->idx_pinned, (size_t)s->d.NS * 8));
+    MB_CUDA(ctx, cudaMallocHost(&s->idx_pinned, (size_t)s->d.NS * 8 * IDX_RING));
+    {
+        const size_t rw = (size_t)(s->d.Lb + 15) / 16;
+        MB_CUDA(ctx, cudaMalloc(&s->idx_identity_dev, (size_t)s->d.NS * 8));
+        MB_CUDA(ctx, cudaMalloc(&s->batch_words, ((size_t)s->d.NS * rw + 64) * 4));
+        MB_CUDA(ctx, cudaMemset(s->batch_words, 0, ((size_t)s->d.NS * rw + 64) * 4));
+        MB_CUDA(ctx, cudaMallocHost(&s->batch_pinned, (size_t)s->d.NS * rw * 4 * IDX_RING));
+        std::vector<int64_t> id(s->d.NS);
+        for (int i = 0; i < s->d.NS; ++i) id[i] = i;
+        MB_CUDA(ctx, cudaMemcpy(s->idx_identity_dev, id.data(), (size_t)s->d.NS * 8, cudaMemcpyHostToDevice));
+    }
     MB_CUDA(ctx, cudaMallocHost(&s->host_out, ((size_t)s->d.G * 3 + 8) * 4));
     return MB200_OK;
 }
@@ -429,7 +445,7 @@ extern "C" int32_t mb200_csc_destroy(mb200_ctx* ctx, mb200_csc* s) {
     if (s->aux) cudaStreamDestroy(s->aux);
     if (s->ev_fork) { cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_join); cudaEventDestroy(s->ev_fork2); cudaEventDestroy(s->ev_join2); }
     cudaFree(s->p_raw); cudaFree(s->g_raw); cudaFree(s->mt); cudaFree(s->st); cudaFree(s->data); cudaFree(s->grad); cudaFree(s->bits); cudaFree(s->lcnt); cudaFree(s->lidx); cudaFree(s->lval);
-    cudaFree(s->bases); cudaFree(s->idx_dev); cudaFreeHost(s->idx_pinned); cudaFreeHost(s->host_out);
+    cudaFree(s->bases); cudaFree(s->idx_dev); cudaFreeHost(s->idx_pinned); cudaFree(s->idx_identity_dev); cudaFree(s->batch_words); cudaFreeHost(s->batch_pinned); cudaFreeHost(s->host_out);
     delete s;
     return MB200_OK;
 }
@@ -484,9 +500,9 @@ static void run_op(mb200_csc* s, Op& op, bool fwd, cudaStream_t q) {
     if (fwd) op.fwd(qq); else op.bwd(qq);
 }
 
-static void enqueue_step(mb200_csc* s, const uint32_t* words, int64_t rowwords, bool backward, cudaStream_t q) {
+static void enqueue_step(mb200_csc* s, const uint32_t* words, int64_t rowwords, const int64_t* idx_dev, bool backward, cudaStream_t q) {
     const CscDims d = s->d;
-    k_unpack_bases<<<nblk((int64_t)d.NS * d.Lb, 256), 256, 0, q>>>(words, rowwords, s->idx_dev, s->bases, d);
+    k_unpack_bases<<<nblk((int64_t)d.NS * d.Lb, 256), 256, 0, q>>>(words, rowwords, idx_dev, s->bases, d);
     for (auto& op : s->tape) run_op(s, op, true, q);
     if (backward) {
         cudaMemsetAsync(s->grad, 0, s->arena * 4, q);
@@ -495,32 +511,59 @@ static void enqueue_step(mb200_csc* s, const uint32_t* words, int64_t rowwords, 
     }
 }
 
-static int run_step(mb200_ctx* ctx, mb200_csc* s, const mb200_seqs* seqs, const int64_t* seq_idx, bool backward) {
-    const CscDims d = s->d;
-    if (seqs->Lb != d.Lb) MB_FAIL(ctx, MB200_E_INVALID, "csc: model built for Lb=%d, sequences have Lb=%lld", d.Lb, (long long)seqs->Lb);
-    for (int i = 0; i < d.NS; ++i) {
-        if (seq_idx[i] < 0 || seq_idx[i] >= seqs->N) MB_FAIL(ctx, MB200_E_INVALID, "csc: sequence index %lld out of range", (long long)seq_idx[i]);
-        s->idx_pinned[i] = seq_idx[i];
-    }
-    MB_CUDA(ctx, cudaMemcpyAsync(s->idx_dev, s->idx_pinned, (size_t)d.NS * 8, cudaMemcpyHostToDevice, ctx->stream));
-    const bool use_graph = backward;       // the training step is replayed thousands of times: capture it once
-    if (use_graph) {
-        if (!s->graph_ok || s->graph_words != seqs->words || s->graph_rowwords != seqs->rowwords) {
+// launches one step on `words` (resident sequence store, or the handle's own buffer holding a host-supplied batch)
+static int launch_step(mb200_ctx* ctx, mb200_csc* s, const uint32_t* words, int64_t rowwords, const int64_t* idx_dev, bool backward) {
+    if (backward) {                        // the training step is replayed thousands of times: capture it once per source
+        if (!s->graph_ok || s->graph_words != words || s->graph_rowwords != rowwords) {
             if (s->gexec) { cudaGraphExecDestroy(s->gexec); s->gexec = nullptr; }
             if (s->graph) { cudaGraphDestroy(s->graph); s->graph = nullptr; }
             MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             MB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-            enqueue_step(s, seqs->words, seqs->rowwords, true, ctx->stream);
+            enqueue_step(s, words, rowwords, idx_dev, true, ctx->stream);
             MB_CUDA(ctx, cudaStreamEndCapture(ctx->stream, &s->graph));
             MB_CUDA(ctx, cudaGraphInstantiate(&s->gexec, s->graph, 0));
-            s->graph_ok = true; s->graph_words = seqs->words; s->graph_rowwords = seqs->rowwords;
+            s->graph_ok = true; s->graph_words = words; s->graph_rowwords = rowwords;
         }
         MB_CUDA(ctx, cudaGraphLaunch(s->gexec, ctx->stream));
     } else {
-        enqueue_step(s, seqs->words, seqs->rowwords, false, ctx->stream);
+        enqueue_step(s, words, rowwords, idx_dev, false, ctx->stream);
     }
     MB_CUDA(ctx, cudaGetLastError());
     return MB200_OK;
+}
+
+static int run_step(mb200_ctx* ctx, mb200_csc* s, const mb200_seqs* seqs, const int64_t* seq_idx, bool backward) {
+    const CscDims d = s->d;
+    if (seqs->Lb != d.Lb) MB_FAIL(ctx, MB200_E_INVALID, "csc: model built for Lb=%d, sequences have Lb=%lld", d.Lb, (long long)seqs->Lb);
+    int64_t* slot = s->idx_pinned + (size_t)(s->ring++ % IDX_RING) * d.NS;
+    for (int i = 0; i < d.NS; ++i) {
+        if (seq_idx[i] < 0 || seq_idx[i] >= seqs->N) MB_FAIL(ctx, MB200_E_INVALID, "csc: sequence index %lld out of range", (long long)seq_idx[i]);
+        slot[i] = seq_idx[i];
+    }
+    MB_CUDA(ctx, cudaMemcpyAsync(s->idx_dev, slot, (size_t)d.NS * 8, cudaMemcpyHostToDevice, ctx->stream));
+    return launch_step(ctx, s, seqs->words, seqs->rowwords, s->idx_dev, backward);
+}
+
+// a batch that arrives from the host as ASCII rows: packed to 2 bit/base on the host (NS*Lb bytes, a few hundred), one H2D copy
+static int run_step_host(mb200_ctx* ctx, mb200_csc* s, const uint8_t* ascii, int64_t n_rows, bool backward) {
+    const CscDims d = s->d;
+    if (n_rows != d.NS) MB_FAIL(ctx, MB200_E_INVALID, "csc: expected %d rows (groups x batch_size), got %lld", d.NS, (long long)n_rows);
+    const int64_t rw = (d.Lb + 15) / 16;
+    uint32_t* slot = s->batch_pinned + (size_t)(s->ring++ % IDX_RING) * d.NS * rw;
+    for (int64_t n = 0; n < d.NS; ++n)
+        for (int64_t w = 0; w < rw; ++w) {
+            uint32_t word = 0;
+            for (int i = 0; i < 16 && w * 16 + i < d.Lb; ++i) {
+                const uint8_t c = ascii[n * d.Lb + w * 16 + i] & 0xDFu;
+                uint32_t code;
+                if (c == 'A') code = 0; else if (c == 'C') code = 1; else if (c == 'G') code = 2; else if (c == 'T') code = 3;
+                else MB_FAIL(ctx, MB200_E_BAD_SEQUENCE, "csc: row %lld holds a symbol that is not A,C,G,T", (long long)n);
+                word |= code << (2 * i);
+            }
+            slot[n * rw + w] = word;
+        }
+    MB_CUDA(ctx, cudaMemcpyAsync(s->batch_words, slot, (size_t)d.NS * rw * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return launch_step(ctx, s, s->batch_words, rw, s->idx_identity_dev, backward);
 }
 
 static int64_t tape_launches(const mb200_csc* s, bool backward) {
@@ -573,6 +616,16 @@ extern "C" int32_t mb200_csc_step_begin(mb200_ctx* ctx, mb200_csc* s, const mb20
 
 // AdaBelief update of the trainable vector with the gradients currently on the device (train.jl:46), then the
 // early-stop statistic l1 = sum |prep_syntax_filters(F)| (train.jl:47).  Blocks; returns mean loss of the last step.
+// same as mb200_csc_step_begin for a batch handed over as host ASCII rows (n_rows = n_groups*batch_size rows of Lb bytes): the
+// reference's `S |> gpu` per step (train.jl:41) with 1 B/bp instead of 16 B/bp.
+extern "C" int32_t mb200_csc_step_begin_host(mb200_ctx* ctx, mb200_csc* s, const uint8_t* ascii_rows, int64_t n_rows) {
+    if (!ctx || !s || !ascii_rows) return MB200_E_INVALID;
+    if (s->xyz_only) MB_FAIL(ctx, MB200_E_INVALID, "csc: handle was created forward_only");
+    MB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->launches[T_CSC] += tape_launches(s, true);
+    return run_step_host(ctx, s, ascii_rows, n_rows, true);
+}
+
 extern "C" int32_t mb200_csc_adabelief_step(mb200_ctx* ctx, mb200_csc* s, float eta, float beta1, float beta2, float eps,
                                             float* loss_out, float* l1_F_out) {
     if (!ctx || !s) return MB200_E_INVALID;

@@ -117,3 +117,40 @@ def test_adabelief_and_training_reduce_loss(ctx):
     mdl.train_ucdl(data, num_epochs=3, rng=np.random.default_rng(2), cdl=cdl, verbose=False, on_step=lambda s, l, l1: losses.append(l))
     assert len(losses) == 60 and np.mean(losses[-10:]) < np.mean(losses[:10])
     m.free(); seqs.free()
+
+
+def test_host_batch_step_equals_resident_step(ctx):
+    """mb200_csc_step_begin_host (batch shipped from the host per step, train.jl:41) == step on the resident sequence store."""
+    hp, ohp, a, seqs, flat = _setup(ctx, 30, 100, 11)
+    m1 = mb._lib.CscModel(ctx, hp, 100)
+    m2 = mb._lib.CscModel(ctx, hp, 100)
+    m1.set_params(flat); m2.set_params(flat)
+    rng = np.random.default_rng(3)
+    for _ in range(3):
+        idx = rng.permutation(30)[:6]
+        m1.step_begin(seqs, idx); l1a = m1.adabelief_step()
+        m2.step_begin_host(a[idx]); l1b = m2.adabelief_step()
+        assert l1a == pytest.approx(l1b, rel=1e-5)            # scalar-gradient reductions use float atomics: last-bit differences
+    assert np.allclose(m1.get_params(), m2.get_params(), rtol=0, atol=2e-6)
+    bad = a[:6].copy(); bad[2, 5] = ord("N")
+    with pytest.raises(mb.MB200Error) as e:
+        m2.step_begin_host(bad)
+    assert e.value.code == mb._lib.E_BAD_SEQUENCE
+    m1.free(); m2.free(); seqs.free()
+
+
+def test_csc_argument_errors(ctx):
+    hp = mdl.Hyperparam()
+    with pytest.raises(mb.MB200Error):
+        mb._lib.CscModel(ctx, hp, 12)                       # too short for filter_len 8 + h 12
+    m = mb._lib.CscModel(ctx, hp, 64)
+    with pytest.raises(mb.MB200Error):
+        m.set_params(np.zeros(10, np.float32))              # wrong parameter count
+    seqs = ctx.seqs_from_ascii(synth.random_ascii(12, 100, 1))
+    with pytest.raises(mb.MB200Error):
+        m.loss_grad(seqs, np.arange(6))                     # model built for Lb=64, data has Lb=100
+    seqs.free()
+    seqs = ctx.seqs_from_ascii(synth.random_ascii(12, 64, 1))
+    with pytest.raises(mb.MB200Error):
+        m.loss_grad(seqs, np.array([0, 1, 2, 3, 4, 12]))    # index out of range
+    m.free(); seqs.free()

@@ -254,3 +254,32 @@ def test_score_histogram_and_fused_thresholds(ctx):
     assert np.array_equal(uq, c[:, 1]) and np.array_equal(uqb, cb[:, 1])
     tot = [inference.get_total_occupied_positions(inference.get_union_ranges(p, l)) for p, l in zip(ms_dict.positions, ms_dict.lens)]
     assert np.array_equal(np.array(tot), c[:, 2])
+
+
+def test_empty_and_degenerate_inputs(ctx):
+    ms = synth.motifs_from_count_matrices(synth.random_count_matrices(3, 8, 12, 91))
+    pw, lens = so.pack_pwms(ms.pwms)
+    # no sequences at all
+    s0 = ctx.seqs_from_ascii(np.zeros((0, 50), np.uint8))
+    hits, counts = ctx.scan(s0, pw, lens)
+    assert len(hits) == 0 and counts.sum() == 0
+    s0.free()
+    # every motif longer than the sequences: nothing can be scored
+    s1 = ctx.seqs_from_ascii(synth.random_ascii(9, 7, 92))
+    hits, counts = ctx.scan(s1, pw, lens)
+    assert len(hits) == 0 and counts.sum() == 0
+    s1.free()
+    # a single motif, a single sequence, a single valid position
+    one = synth.motifs_from_count_matrices([synth.count_matrix_from_sites(["ACGTACGT"] * 20)])
+    _check(ctx, np.frombuffer(b"ACGTACGT", np.uint8).reshape(1, 8).copy(), one)
+    # argument errors
+    s2 = ctx.seqs_from_ascii(synth.random_ascii(4, 30, 93))
+    with pytest.raises(mb.MB200Error):
+        ctx.scan(s2, pw, np.array([8, 0, 9]))                # zero-length motif
+    with pytest.raises(mb.MB200Error):
+        ctx.scan(s2, pw, lens, fwd=False, rc=False)          # no strand requested
+    s2.free()
+    onehot = np.zeros((3, 20, 4), np.float32); onehot[:, :, 1] = 1; onehot[1, 4, 2] = 1     # two ones in one column
+    with pytest.raises(mb.MB200Error) as e:
+        ctx.seqs_from_onehot(onehot)
+    assert e.value.code == mb._lib.E_BAD_SEQUENCE
