@@ -122,7 +122,10 @@ typedef struct {                 /* Hyperparam, model.jl:1-14 (same defaults exp
 } mb200_hparams;
 
 /* n_groups independent batches of batch_size sequences are processed per call (1 = the reference's
- * step).  forward_only != 0 builds only ADMM_XYZ (enough for mb200_csc_codes, far less memory).   */
+ * step).  forward_only != 0 builds only ADMM_XYZ (enough for mb200_csc_codes, far less memory);
+ * forward_only == 2 additionally routes the dense syntax-filter contraction (model.jl:214,251) through
+ * the tcgen05/TMEM tensor-core kernel with BF16 operands and FP32 accumulation — NOT bit-comparable
+ * with the fp32 path (stated tolerance in tests/test_csc_gpu.py), off by default.                  */
 int32_t mb200_csc_create(mb200_ctx* ctx, const mb200_hparams* hp, int64_t Lb, int32_t n_groups,
                          int32_t forward_only, mb200_csc** out);
 int32_t mb200_csc_destroy(mb200_ctx* ctx, mb200_csc* csc);

@@ -12,6 +12,7 @@
 // no host synchronisation inside — it is captured into a CUDA graph and replayed per step.
 #include "common.cuh"
 #include "csc_kernels.cuh"
+#include "tc_corr2d.cuh"
 #include <algorithm>
 #include <cstring>
 #include <functional>
@@ -66,6 +67,8 @@ struct mb200_csc {
     Buf sc; Buf Deff, Feff, Fnrm0, loss;
     int i_lam0, i_kaps0, i_eta0, i_om0, i_kap0, i_rho0, i_mu0, i_lam_w, i_eta_w, i_om_w;
     bool xyz_only = false;
+    bool tensor = false;                                 // forward-only handle using the tcgen05 BF16 path for corr2d
+    __nv_bfloat16 *tc_A = nullptr, *tc_F = nullptr; int tc_tiles = 0, tc_ld = 104; size_t tc_smem = 0;
     cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr; bool graph_ok = false;
     const uint32_t* graph_words = nullptr; int64_t graph_rowwords = 0;
 };
@@ -124,6 +127,7 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
                          k_prep_scalars<<<1, 64, 0, q>>>(S->p_raw + S->off_warm, S->data + sc.off + S->i_lam_w, 3);
                          k_prep_D<<<nblk(d.fl * d.M, 128), 128, 0, q>>>(S->p_raw + S->off_D, S->data + De.off, d);
                          k_prep_F<<<d.K, 256, 0, q>>>(S->p_raw + S->off_F, S->data + Fe.off, S->data + Fn0.off, d);
+                         if (S->tensor) k_tc_prep_F<<<nblk((int64_t)d.h * TC_CH * TC_N * 8, 256), 256, 0, q>>>(S->data + Fe.off, S->tc_F, d.h, d.M2, d.K);
                      },
                      [=](cudaStream_t q) {
                          const int npx = d.npx, npd = d.npd;
@@ -150,6 +154,12 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
 #define LIDX(L) (S->lidx + (size_t)(L) * d.NS * LIST_CAP)
 #define LVAL(L) (S->lval + (size_t)(L) * d.NS * LIST_CAP)
     auto run_corr2d = [=](const float* A, const float* filt, int64_t gs, float* out, int acc, cudaStream_t q) {
+        if (S->tensor && gs == 0 && !acc) {
+            const int64_t rows = (int64_t)d.NS * d.c;
+            k_tc_prep_A<<<nblk(rows * S->tc_ld, 256), 256, 0, q>>>(A, S->tc_A, rows, d.M2, S->tc_ld);
+            k_corr2d_tc<<<std::min(S->tc_tiles, S->ctx->sm_count), 128, S->tc_smem, q>>>(S->tc_A, S->tc_F, out, rows, S->tc_tiles, S->tc_ld, d);
+            return;
+        }
         if (fastK) k_corr2d_w<24, 4><<<d.NS * ((d.l + 3) / 4), 128, 0, q>>>(A, filt, gs, out, acc, d);
         else k_corr2d<<<nblk(nX, 128), 128, 0, q>>>(A, filt, gs, out, acc, d);
     };
@@ -287,6 +297,7 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
                          "d_build"});
         }
         { const int gl = B.n_lists++; op_corr2d(dd, Fe, 0, g, gl, "corr2d"); op_topq(&x, g, i_om, -1.f, 1, xn, gl, "topq"); }
+        s->named["g_last"] = g;
         x = xn;
         op_tconv(x, Fe, 0, fxn, "tconv");
         fx = fxn;
@@ -388,6 +399,17 @@ static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
     if (s->mask_cap <= MS_MAXV * 512) MB_CUDA(ctx, cudaFuncSetAttribute(k_mask_scale_c, cudaFuncAttributeMaxDynamicSharedMemorySize, s->mask_cap * 4));
     MB_CUDA(ctx, cudaFuncSetAttribute(k_mask_scale_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<int64_t>(2 * (int64_t)s->d.B * s->d.c * s->d.M, 49152) * 4));
     MB_CUDA(ctx, cudaFuncSetAttribute(k_topq_s, cudaFuncAttributeMaxDynamicSharedMemorySize, s->d.l * s->d.K * 4));
+    if (s->tensor) {
+        const int64_t rows = (int64_t)s->d.NS * s->d.c;
+        s->tc_tiles = (int)((rows + TC_M - 1) / TC_M);
+        const size_t arows = (size_t)s->tc_tiles * TC_M + s->d.h + 8;
+        MB_CUDA(ctx, cudaMalloc(&s->tc_A, arows * s->tc_ld * 2));
+        MB_CUDA(ctx, cudaMemset(s->tc_A, 0, arows * s->tc_ld * 2));
+        MB_CUDA(ctx, cudaMalloc(&s->tc_F, (size_t)s->d.h * TC_CH * TC_N * 8 * 2));
+        const int R = TC_M + s->d.h - 1;
+        s->tc_smem = (((size_t)TC_CH * R * 16 + 127) & ~(size_t)127) + (size_t)s->d.h * TC_CH * TC_N * 16;
+        MB_CUDA(ctx, cudaFuncSetAttribute(k_corr2d_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tc_smem));
+    }
     MB_CUDA(ctx, cudaStreamCreateWithFlags(&s->aux, cudaStreamNonBlocking));
     MB_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
     MB_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
@@ -421,6 +443,8 @@ extern "C" int32_t mb200_csc_create(mb200_ctx* ctx, const mb200_hparams* hp, int
     MB_CUDA(ctx, cudaSetDevice(ctx->device));
     mb200_csc* s = new mb200_csc();
     s->ctx = ctx; s->hp = *hp; s->xyz_only = forward_only != 0;
+    s->tensor = forward_only == 2;
+    if (s->tensor && (hp->K > TC_N || 2 * hp->M > (TC_CH - 1) * 8)) { delete s; MB_FAIL(ctx, MB200_E_UNSUPPORTED, "csc: the tensor-core path needs K <= %d and 2M <= %d", TC_N, (TC_CH - 1) * 8); }
     CscDims& d = s->d;
     d.B = hp->batch_size; d.G = n_groups; d.NS = d.B * d.G; d.Lb = (int)Lb; d.L4 = 4 * (int)Lb; d.c = (int)c; d.l = (int)l;
     d.M = hp->M; d.M2 = 2 * hp->M; d.K = hp->K; d.h = hp->h; d.q = hp->q; d.fl = hp->filter_len; d.f_len = 4 * hp->filter_len;
@@ -444,7 +468,7 @@ extern "C" int32_t mb200_csc_destroy(mb200_ctx* ctx, mb200_csc* s) {
     if (s->graph) cudaGraphDestroy(s->graph);
     if (s->aux) cudaStreamDestroy(s->aux);
     if (s->ev_fork) { cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_join); cudaEventDestroy(s->ev_fork2); cudaEventDestroy(s->ev_join2); }
-    cudaFree(s->p_raw); cudaFree(s->g_raw); cudaFree(s->mt); cudaFree(s->st); cudaFree(s->data); cudaFree(s->grad); cudaFree(s->bits); cudaFree(s->lcnt); cudaFree(s->lidx); cudaFree(s->lval);
+    cudaFree(s->p_raw); cudaFree(s->g_raw); cudaFree(s->mt); cudaFree(s->st); cudaFree(s->data); cudaFree(s->grad); cudaFree(s->bits); cudaFree(s->lcnt); cudaFree(s->lidx); cudaFree(s->lval); cudaFree(s->tc_A); cudaFree(s->tc_F);
     cudaFree(s->bases); cudaFree(s->idx_dev); cudaFreeHost(s->idx_pinned); cudaFree(s->idx_identity_dev); cudaFree(s->batch_words); cudaFreeHost(s->batch_pinned); cudaFreeHost(s->host_out);
     delete s;
     return MB200_OK;

@@ -1,0 +1,141 @@
+// tcgen05 / TMEM path for the one genuinely dense contraction of the network at batched shapes:
+//   U2 "corr2d":  out[n,i,k] = sum_{a<h} sum_{j<2M} A[n,i+a,j] F[a][j][k]      (model.jl:214,251)
+// as the GEMM  [rows = NS*c] x [K = h*2M]  .  [K x 24]  with the im2col rows never materialised: row r's operand is the
+// contiguous window A[r .. r+h-1][:] of the position-major buffer.
+//
+// Precision: operands are rounded to BF16, products accumulate in FP32 in TMEM (kind::f16).  This is the "stated bf16
+// tolerance on tensor-core paths" mode of the north star: it is OFF by default (the fp32 SIMT kernels are the parity path) and is
+// only wired into forward-only code retrieval (mb200_csc_create(..., forward_only = 2)).
+//
+// Layout trick that makes the sliding window free: the staged rows live in shared memory as [chunk of 8 columns][row][16 B].
+// In the canonical K-major no-swizzle UMMA layout a core matrix is 8 rows x 16 B with the rows 16 B apart — exactly 8
+// consecutive rows of one chunk — so the operand of window offset `a` is the SAME buffer with the descriptor start address
+// advanced by a*16 B; SBO (next 8 rows) = 128 B, LBO (next K chunk) = R*16 B.  One staged copy of 128+h-1 rows serves all h
+// offsets; nothing is re-read from L2 per offset.
+#pragma once
+#include <cuda_bf16.h>
+
+#define TC_M 128            // output rows per tile = TMEM lanes
+#define TC_N 32             // accumulator columns (K filters padded 24 -> 32)
+#define TC_CH 14            // 16-byte chunks per staged row: 13 hold 2M=100 (+4 zero) columns, chunk 13 is all zero (pairs up chunk 12)
+
+__device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+    // [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout type 0
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// operand preparation: A fp32 [rows][2M] -> bf16 [rows + pad][104]; F fp32 [h][2M][K] -> bf16 [h][TC_CH][TC_N][8]
+__global__ void __launch_bounds__(256) k_tc_prep_A(const float* __restrict__ A, __nv_bfloat16* __restrict__ Ab, int64_t rows, int M2, int ld) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * ld) return;
+    const int j = (int)(t % ld);
+    const int64_t r = t / ld;
+    Ab[t] = __float2bfloat16_rn(j < M2 ? A[r * M2 + j] : 0.f);
+}
+__global__ void __launch_bounds__(256) k_tc_prep_F(const float* __restrict__ F, __nv_bfloat16* __restrict__ Fb, int h, int M2, int K) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= h * TC_CH * TC_N * 8) return;
+    const int e = t & 7, n = (t >> 3) % TC_N, ch = (t / (8 * TC_N)) % TC_CH, a = t / (8 * TC_N * TC_CH);
+    const int j = ch * 8 + e;
+    Fb[t] = __float2bfloat16_rn((j < M2 && n < K) ? F[((int64_t)a * M2 + j) * K + n] : 0.f);
+}
+
+// One CTA = 128 threads; persistent over row tiles.  Thread 0 issues the MMAs; all four warps drain TMEM.
+__global__ void __launch_bounds__(128, 1) k_corr2d_tc(const __nv_bfloat16* __restrict__ Ab, const __nv_bfloat16* __restrict__ Fb,
+                                                      float* __restrict__ out, int64_t rows_total, int ntiles, int ld, CscDims d) {
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    const int R = TC_M + d.h - 1;                               // staged rows per tile
+    uint8_t* sA = tc_smem;                                      // [TC_CH][R][16 B]
+    uint8_t* sB = tc_smem + (((size_t)TC_CH * R * 16 + 127) & ~(size_t)127);        // [h][TC_CH][TC_N][16 B]
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&s_tmem)), "n"(TC_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // resident B operand (all of F, 12 x 14 x 32 x 16 B = 84 KB) and the zero chunk of A
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(Fb);
+        uint4* dst = reinterpret_cast<uint4*>(sB);
+        for (int i = tid; i < d.h * TC_CH * TC_N; i += 128) dst[i] = src[i];
+        uint4* z = reinterpret_cast<uint4*>(sA + (size_t)(TC_CH - 1) * R * 16);
+        for (int i = tid; i < R; i += 128) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    const uint32_t sA_addr = (uint32_t)__cvta_generic_to_shared(sA), sB_addr = (uint32_t)__cvta_generic_to_shared(sB);
+    // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=F32 (1<<4), A=BF16 (1<<7), B=BF16 (1<<10), both K-major,
+    // N>>3 at bit 17, M>>4 at bit 24
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    uint32_t phase = 0;
+    const int nch = TC_CH - 1;                                  // data chunks per row (13)
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t r0 = (int64_t)tile * TC_M;
+        // stage rows r0 .. r0+R-1 as [chunk][row][16 B] (rows past the end of the buffer are zero padding in Ab)
+        for (int i = tid; i < R * nch; i += 128) {
+            const int row = i / nch, ch = i - row * nch;
+            const uint4 v = *reinterpret_cast<const uint4*>(Ab + (r0 + row) * ld + ch * 8);
+            *reinterpret_cast<uint4*>(sA + ((size_t)ch * R + row) * 16) = v;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t acc = 0;
+            for (int a = 0; a < d.h; ++a)
+                for (int t = 0; t < TC_CH / 2; ++t) {            // K = 16 per MMA = two 16-byte chunks
+                    const uint64_t da = tc_desc(sA_addr + ((uint32_t)(2 * t) * R + a) * 16, (uint32_t)R * 16, 128);
+                    const uint64_t db = tc_desc(sB_addr + ((uint32_t)(a * TC_CH + 2 * t) * TC_N) * 16, TC_N * 16, 128);
+                    tc_mma_bf16(tmem, da, db, idesc, acc);
+                    acc = 1;
+                }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+        }
+        {   // wait for the accumulator
+            uint32_t done, spins = 0;
+            do {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+                if (!done && ++spins > (1u << 24)) __trap();         // never hang the device on a lost completion
+            } while (!done);
+            phase ^= 1;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t v[32];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                       "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+                       "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                     : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int64_t r = r0 + warp * 32 + lane;                 // TMEM lane = output row of the tile
+        if (r < rows_total) {
+            const int64_t n = r / d.c;
+            const int i = (int)(r - n * d.c);
+            if (i < d.l) {                                       // rows i >= l are windows that run into the next sequence
+                float* o = out + (n * d.l + i) * d.K;
+                for (int k = 0; k < d.K; ++k) o[k] = __uint_as_float(v[k]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                                         // TMEM and sA are reused by the next tile
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(TC_N) : "memory");
+}
