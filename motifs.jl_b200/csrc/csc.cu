@@ -15,6 +15,7 @@
 #include "tc_corr2d.cuh"
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 #include <functional>
 #include <map>
 
@@ -68,7 +69,8 @@ struct mb200_csc {
     int i_lam0, i_kaps0, i_eta0, i_om0, i_kap0, i_rho0, i_mu0, i_lam_w, i_eta_w, i_om_w;
     bool xyz_only = false;
     bool tensor = false;                                 // forward-only handle using the tcgen05 BF16 path for corr2d
-    __nv_bfloat16 *tc_A = nullptr, *tc_F = nullptr; int tc_tiles = 0, tc_ld = 104; size_t tc_smem = 0;
+    __nv_bfloat16 *tc_A = nullptr, *tc_F = nullptr; int tc_tiles = 0, tc_ld = 104; size_t tc_smem = 0, tc_smem2 = 0;
+    CUtensorMap tc_map; bool tc_pipelined = false;
     cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr; bool graph_ok = false;
     const uint32_t* graph_words = nullptr; int64_t graph_rowwords = 0;
 };
@@ -157,7 +159,8 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         if (S->tensor && gs == 0 && !acc) {
             const int64_t rows = (int64_t)d.NS * d.c;
             k_tc_prep_A<<<nblk(rows * S->tc_ld, 256), 256, 0, q>>>(A, S->tc_A, rows, d.M2, S->tc_ld);
-            k_corr2d_tc<<<std::min(S->tc_tiles, S->ctx->sm_count), 128, S->tc_smem, q>>>(S->tc_A, S->tc_F, out, rows, S->tc_tiles, S->tc_ld, d);
+            if (S->tc_pipelined) k_corr2d_tc2<<<std::min(S->tc_tiles, S->ctx->sm_count), 192, S->tc_smem2, q>>>(S->tc_map, S->tc_F, out, rows, S->tc_tiles, d);
+            else k_corr2d_tc<<<std::min(S->tc_tiles, S->ctx->sm_count), 128, S->tc_smem, q>>>(S->tc_A, S->tc_F, out, rows, S->tc_tiles, S->tc_ld, d);
             return;
         }
         if (fastK) k_corr2d_w<24, 4><<<d.NS * ((d.l + 3) / 4), 128, 0, q>>>(A, filt, gs, out, acc, d);
@@ -409,6 +412,10 @@ static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
         const int R = TC_M + s->d.h - 1;
         s->tc_smem = (((size_t)TC_CH * R * 16 + 127) & ~(size_t)127) + (size_t)s->d.h * TC_CH * TC_N * 16;
         MB_CUDA(ctx, cudaFuncSetAttribute(k_corr2d_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tc_smem));
+        s->tc_smem2 = 2 * ((((size_t)TC_CH * R * 16) + 1023) & ~(size_t)1023) + (size_t)s->d.h * TC_CH * TC_N * 16;
+        MB_CUDA(ctx, cudaFuncSetAttribute(k_corr2d_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tc_smem2));
+        const char* np = getenv("MB200_TC_NO_PIPELINE");
+        s->tc_pipelined = !(np && np[0] == '1') && tc_make_tmap(&s->tc_map, s->tc_A, arows, s->tc_ld, R) == 0;
     }
     MB_CUDA(ctx, cudaStreamCreateWithFlags(&s->aux, cudaStreamNonBlocking));
     MB_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
