@@ -242,7 +242,9 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
     s->mask_cap = mask_cap;
     auto op_mask_scale = [&](Buf z, Buf y, Buf zy, const char* nm) {
         Buf med = B.alloc(d.G);
-        const bool ms_cluster = mask_cap <= MS_MAXV * 512;       // slice fits the register-staged cluster kernel
+        // one 8-CTA cluster per group minimises latency (training, few groups); with many groups (batched code retrieval) one CTA per
+        // group fills the machine better: 148 groups in flight instead of 18 clusters
+        const bool ms_cluster = mask_cap <= MS_MAXV * 512 && d.G < 32;
         const int ms_cap1 = (int)std::min<int64_t>(2 * (int64_t)d.B * d.c * d.M, 49152);
         T.push_back({[=](cudaStream_t q) {
                          if (ms_cluster) k_mask_scale_c<<<d.G * CL, 512, (size_t)mask_cap * 4, q>>>(S->data + z.off, S->data + y.off, S->data + zy.off, S->data + med.off, d);

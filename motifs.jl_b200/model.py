@@ -197,12 +197,14 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
 
 
-def code_retrieval(data, cdl: ucdl, hp: Hyperparam, model: CscModel | None = None, groups_per_call: int = 512):
+def code_retrieval(data, cdl: ucdl, hp: Hyperparam, model: CscModel | None = None, groups_per_call: int = 512, tensor_cores: bool = False):
     """code_retrieval (_1_code_retrieval.jl:33-56) -> structured array (position, fil, seq, mag_f16), 0-based, ordered by
     seq, fil, position.  groups_per_call batches of 6 are decoded per kernel sequence (they are independent)."""
     seqs = data.seqs
     n_groups = max(1, min(groups_per_call, data.N // hp.batch_size))
-    m = CscModel(seqs.ctx, hp, data.L, n_groups=n_groups, forward_only=True)
+    # tensor_cores=True routes the dense syntax-filter contraction through the tcgen05/TMEM BF16 kernel (stated tolerance, not the
+    # fp32 parity path)
+    m = CscModel(seqs.ctx, hp, data.L, n_groups=n_groups, forward_only=True, tensor_cores=tensor_cores)
     m.set_params(cdl.flat)
     out = m.codes(seqs)
     m.free()
