@@ -393,6 +393,28 @@ def bench_train(args, ctx, torch, dist, world, rank, local, dev):
                 out["cpu_baseline"] = {"value": rate, "unit": "seq/s", "cores": cores, "kind": "port", "seconds": dt,
                                        "sample": f"{steps} optimiser steps of batch 6 (oracle/csc_oracle.py, PyTorch-CPU fp32 + autograd, {cores} threads)"}
         model.free()
+        # extra data point (NOT the headline): 16 independent batches of 6 per optimiser step on one GPU — the same arithmetic as
+        # 16 data-parallel ranks (global batch 96, gradients averaged), i.e. a different optimisation trajectory than the reference's
+        if rank == 0 and world == 1:
+            G = 16
+            mg = CscModel(ctx, hp, Lb, n_groups=G)
+            mg.set_params(cdl.flat)
+            r2 = np.random.default_rng(7)
+            for _ in range(20):
+                mg.step_begin(seqs, r2.permutation(n_train)[:6 * G]); mg.adabelief_step()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nst = 200
+            g0.record(side)
+            for _ in range(nst):
+                mg.step_begin(seqs, r2.permutation(n_train)[:6 * G]); mg.adabelief_step()
+            g1.record(side)
+            torch.cuda.synchronize()
+            msg = g0.elapsed_time(g1) / nst
+            out["batched_groups"] = {"groups_per_step": G, "global_batch": 6 * G, "value": 6 * G / (msg / 1e3), "unit": "seq/s",
+                                     "ms_per_optimizer_step": msg,
+                                     "note": "each group is a reference batch (own median mask, own D/F updates); gradients averaged over groups"}
+            mg.free()
         seqs.free()
     ctx.set_stream(None)
     return out
