@@ -157,6 +157,10 @@ int32_t mb200_csc_adabelief_step(mb200_ctx* ctx, mb200_csc* csc, float eta, floa
                                  float eps, float* loss_out, float* l1_F_out);
 /* named intermediates of the last forward pass ("z","y","x","zy","D","F","D0","F0","loss") — tests */
 int32_t mb200_csc_get_buffer(mb200_ctx* ctx, mb200_csc* csc, const char* name, float* out, int64_t n);
+/* the batch-median mask alone: cat_ZY + create_ZY_mask, model.jl:194-210.  z,y host [G][B*c][M] (the position-space rows of
+ * Z,Y for the handle's shape) -> zy_out [G][B*c][2M] = magnifying_factor * (ZY >= median(ZY[ZY>0])) .* ZY, med_out [G]
+ * (-inf when a group has no positive entry).  Same kernel as inside the step.                              */
+int32_t mb200_csc_median_mask(mb200_ctx* ctx, mb200_csc* csc, const float* z, const float* y, float* zy_out, float* med_out);
 
 typedef struct {                 /* stored_code_component_t, inference/_0_const.jl:3-4 (0-based) */
     uint16_t position, fil;

@@ -83,6 +83,7 @@ def load():
         "mb200_csc_step_begin_host": (i32, [p, p, p, i64]),
         "mb200_csc_adabelief_step": (i32, [p, p, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "mb200_csc_get_buffer": (i32, [p, p, C.c_char_p, p, i64]),
+        "mb200_csc_median_mask": (i32, [p, p, p, p, p, p]),
         "mb200_csc_codes": (i32, [p, p, p, i64, i64, p, i64, C.POINTER(i64)]),
         "mb200_count_matrices": (i32, [p, p, p, i64, p, i32, i32, p]),
     }
@@ -335,6 +336,16 @@ class CscModel:
         a = np.zeros(int(n), np.float32)
         self.ctx._check(self.ctx._lib.mb200_csc_get_buffer(self.ctx._h, self._h, name.encode(), _ptr(a), a.size))
         return a
+
+    def median_mask(self, z, y):
+        """cat_ZY + create_ZY_mask (model.jl:194-210) alone: z,y (G, B*c, M) float32 -> zy (G, B*c, 2M), med (G,)."""
+        z = np.ascontiguousarray(z, np.float32); y = np.ascontiguousarray(y, np.float32)
+        G, rows, M = z.shape
+        if y.shape != z.shape or G != self.n_groups or M != self.hp.M:
+            raise ValueError("z,y must be (n_groups, batch*c, M)")
+        zy = np.zeros((G, rows, 2 * M), np.float32); med = np.zeros(G, np.float32)
+        self.ctx._check(self.ctx._lib.mb200_csc_median_mask(self.ctx._h, self._h, _ptr(z), _ptr(y), _ptr(zy), _ptr(med)))
+        return zy, med
 
     def codes(self, seqs: "Sequences", first_seq=0, n_seqs=None):
         B = self.hp.batch_size

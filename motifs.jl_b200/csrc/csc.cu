@@ -64,6 +64,8 @@ struct mb200_csc {
     std::map<std::string, Buf> named;
     // raw-vector offsets
     int64_t off_lam, off_kaps, off_eta, off_om, off_kap, off_D, off_F, off_rho, off_mu, off_warm;
+    ScalarSegs segs;
+    int64_t graph_kernels = 0;
     // effective-scalar slots (index into sc buffer)
     Buf sc; Buf Deff, Feff, Fnrm0, loss;
     int i_lam0, i_kaps0, i_eta0, i_om0, i_kap0, i_rho0, i_mu0, i_lam_w, i_eta_w, i_om_w;
@@ -91,6 +93,24 @@ struct Builder {
 
 inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
+// every kernel of the step is launched through lk().  MB200_PDL=1 adds the programmatic-dependent-launch attribute (each kernel
+// begins with griddepcontrol.wait); measured on B200 it does not shorten the captured step (1.27 vs 1.26 ms: the graph's
+// node-to-node gaps are already small next to the kernels' own run time), so it is off by default.
+static int g_pdl = -1;
+static thread_local int64_t g_lk_count = 0;      // kernels enqueued through lk() by this thread
+template <typename... KA, typename... A>
+inline void lk(void (*k)(KA...), dim3 g, dim3 b, size_t smem, cudaStream_t q, A&&... a) {
+    if (g_pdl < 0) { const char* e = getenv("MB200_PDL"); g_pdl = (e && e[0] == '1') ? 1 : 0; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = smem; cfg.stream = q;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = g_pdl;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k, static_cast<KA>(a)...);
+    ++g_lk_count;
+}
+
 }  // namespace
 
 #define D_(b) (s->data + (b).off)
@@ -107,6 +127,13 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
     // scalar slot order = raw order of the scalar arrays, then warm-ups: lam[npx] kaps[npd] eta[npx] om[npx] kap[npd] rho[npx] mu[npd] | lam_w eta_w om_w
     s->i_lam0 = 0; s->i_kaps0 = d.npx; s->i_eta0 = s->i_kaps0 + d.npd; s->i_om0 = s->i_eta0 + d.npx; s->i_kap0 = s->i_om0 + d.npx;
     s->i_rho0 = s->i_kap0 + d.npd; s->i_mu0 = s->i_rho0 + d.npx; s->i_lam_w = s->i_mu0 + d.npd; s->i_eta_w = s->i_lam_w + 1; s->i_om_w = s->i_eta_w + 1;
+    {
+        const int64_t ro[8] = {s->off_lam, s->off_kaps, s->off_eta, s->off_om, s->off_kap, s->off_rho, s->off_mu, s->off_warm};
+        const int ei[8] = {s->i_lam0, s->i_kaps0, s->i_eta0, s->i_om0, s->i_kap0, s->i_rho0, s->i_mu0, s->i_lam_w};
+        const int nn[8] = {d.npx, d.npd, d.npx, d.npx, d.npd, d.npx, d.npd, 3};
+        for (int i = 0; i < 8; ++i) { s->segs.raw_off[i] = (int)ro[i]; s->segs.eff_idx[i] = ei[i]; s->segs.n[i] = nn[i]; }
+        s->segs.nseg = 8;
+    }
     s->Deff = B.alloc(nD, "D0"); s->Feff = B.alloc(nF, "F0"); s->Fnrm0 = B.alloc(d.K);
     s->loss = B.alloc((size_t)d.G * 3 + 4, "loss");
     mb200_csc* S = s;
@@ -118,30 +145,16 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         const Buf sc = s->sc, De = s->Deff, Fe = s->Feff, Fn0 = s->Fnrm0;
         T.push_back({[=](cudaStream_t q) {
                          // scalar arrays are contiguous in the raw vector except D,F in the middle: copy slot by slot
-                         const int npx = d.npx, npd = d.npd;
-                         k_prep_scalars<<<1, 64, 0, q>>>(S->p_raw + S->off_lam, S->data + sc.off + S->i_lam0, npx);
-                         k_prep_scalars<<<1, 64, 0, q>>>(S->p_raw + S->off_kaps, S->data + sc.off + S->i_kaps0, npd);
-                         k_prep_scalars<<<1, 64, 0, q>>>(S->p_raw + S->off_eta, S->data + sc.off + S->i_eta0, npx);
-                         k_prep_scalars<<<1, 64, 0, q>>>(S->p_raw + S->off_om, S->data + sc.off + S->i_om0, npx);
-                         k_prep_scalars<<<1, 64, 0, q>>>(S->p_raw + S->off_kap, S->data + sc.off + S->i_kap0, npd);
-                         k_prep_scalars<<<1, 64, 0, q>>>(S->p_raw + S->off_rho, S->data + sc.off + S->i_rho0, npx);
-                         k_prep_scalars<<<1, 64, 0, q>>>(S->p_raw + S->off_mu, S->data + sc.off + S->i_mu0, npd);
-                         k_prep_scalars<<<1, 64, 0, q>>>(S->p_raw + S->off_warm, S->data + sc.off + S->i_lam_w, 3);
-                         k_prep_D<<<nblk(d.fl * d.M, 128), 128, 0, q>>>(S->p_raw + S->off_D, S->data + De.off, d);
-                         k_prep_F<<<d.K, 256, 0, q>>>(S->p_raw + S->off_F, S->data + Fe.off, S->data + Fn0.off, d);
-                         if (S->tensor) k_tc_prep_F<<<nblk((int64_t)d.h * TC_CH * TC_N * 8, 256), 256, 0, q>>>(S->data + Fe.off, S->tc_F, d.h, d.M2, d.K);
+                         lk(k_prep_scalars, 1, 256, 0, q, S->p_raw, S->data + sc.off, S->segs);
+                         lk(k_prep_D, nblk(d.fl * d.M, 128), 128, 0, q, S->p_raw + S->off_D, S->data + De.off, d);
+                         lk(k_prep_F, d.K, 256, 0, q, S->p_raw + S->off_F, S->data + Fe.off, S->data + Fn0.off, d);
+                         if (S->tensor) lk(k_tc_prep_F, nblk((int64_t)d.h * TC_CH * TC_N * 8, 256), 256, 0, q, S->data + Fe.off, S->tc_F, d.h, d.M2, d.K);
                      },
                      [=](cudaStream_t q) {
-                         const int npx = d.npx, npd = d.npd;
-                         k_prep_scalars_bwd<<<1, 64, 0, q>>>(S->p_raw + S->off_lam, S->grad + sc.off + S->i_lam0, S->g_raw + S->off_lam, npx);
-                         k_prep_scalars_bwd<<<1, 64, 0, q>>>(S->p_raw + S->off_kaps, S->grad + sc.off + S->i_kaps0, S->g_raw + S->off_kaps, npd);
-                         k_prep_scalars_bwd<<<1, 64, 0, q>>>(S->p_raw + S->off_eta, S->grad + sc.off + S->i_eta0, S->g_raw + S->off_eta, npx);
-                         k_prep_scalars_bwd<<<1, 64, 0, q>>>(S->p_raw + S->off_om, S->grad + sc.off + S->i_om0, S->g_raw + S->off_om, npx);
-                         k_prep_scalars_bwd<<<1, 64, 0, q>>>(S->p_raw + S->off_kap, S->grad + sc.off + S->i_kap0, S->g_raw + S->off_kap, npd);
-                         k_prep_scalars_bwd<<<1, 64, 0, q>>>(S->p_raw + S->off_rho, S->grad + sc.off + S->i_rho0, S->g_raw + S->off_rho, npx);
-                         k_prep_scalars_bwd<<<1, 64, 0, q>>>(S->p_raw + S->off_mu, S->grad + sc.off + S->i_mu0, S->g_raw + S->off_mu, npd);
-                         k_prep_D_bwd<<<nblk(d.fl * d.M, 128), 128, 0, q>>>(S->p_raw + S->off_D, S->data + De.off, S->grad + De.off, S->g_raw + S->off_D, d);
-                         k_prep_F_bwd<<<d.K, 256, 0, q>>>(S->p_raw + S->off_F, S->data + Fe.off, S->data + Fn0.off, S->grad + Fe.off, S->g_raw + S->off_F, d);
+                         ScalarSegs tr = S->segs; tr.nseg = 7;      // the warm-up scalars (segment 7) are not trained
+                         lk(k_prep_scalars_bwd, 1, 256, 0, q, S->p_raw, S->grad + sc.off, S->g_raw, tr);
+                         lk(k_prep_D_bwd, nblk(d.fl * d.M, 128), 128, 0, q, S->p_raw + S->off_D, S->data + De.off, S->grad + De.off, S->g_raw + S->off_D, d);
+                         lk(k_prep_F_bwd, d.K, 256, 0, q, S->p_raw + S->off_F, S->data + Fe.off, S->data + Fn0.off, S->grad + Fe.off, S->g_raw + S->off_F, d);
                      },
                      "prep"});
     }
@@ -158,23 +171,23 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
     auto run_corr2d = [=](const float* A, const float* filt, int64_t gs, float* out, int acc, cudaStream_t q) {
         if (S->tensor && gs == 0 && !acc) {
             const int64_t rows = (int64_t)d.NS * d.c;
-            k_tc_prep_A<<<nblk(rows * S->tc_ld, 256), 256, 0, q>>>(A, S->tc_A, rows, d.M2, S->tc_ld);
-            if (S->tc_pipelined) k_corr2d_tc2<<<std::min(S->tc_tiles, S->ctx->sm_count), 192, S->tc_smem2, q>>>(S->tc_map, S->tc_F, out, rows, S->tc_tiles, d);
-            else k_corr2d_tc<<<std::min(S->tc_tiles, S->ctx->sm_count), 128, S->tc_smem, q>>>(S->tc_A, S->tc_F, out, rows, S->tc_tiles, S->tc_ld, d);
+            lk(k_tc_prep_A, nblk(rows * S->tc_ld, 256), 256, 0, q, A, S->tc_A, rows, d.M2, S->tc_ld);
+            if (S->tc_pipelined) lk(k_corr2d_tc2, std::min(S->tc_tiles, S->ctx->sm_count), 192, S->tc_smem2, q, S->tc_map, S->tc_F, out, rows, S->tc_tiles, d);
+            else lk(k_corr2d_tc, std::min(S->tc_tiles, S->ctx->sm_count), 128, S->tc_smem, q, S->tc_A, S->tc_F, out, rows, S->tc_tiles, S->tc_ld, d);
             return;
         }
-        if (fastK) k_corr2d_w<24, 4><<<d.NS * ((d.l + 3) / 4), 128, 0, q>>>(A, filt, gs, out, acc, d);
-        else k_corr2d<<<nblk(nX, 128), 128, 0, q>>>(A, filt, gs, out, acc, d);
+        if (fastK) lk(k_corr2d_w<24, 4>, d.NS * ((d.l + 3) / 4), 128, 0, q, A, filt, gs, out, acc, d);
+        else lk(k_corr2d, nblk(nX, 128), 128, 0, q, A, filt, gs, out, acc, d);
     };
     auto run_dgrad = [=](const float* ca, const float* cb, const float* sig, float sgn, float* of, int64_t ogs, int acc, cudaStream_t q) {
-        if (fastM) k_dgrad_c<<<dim3(d.f_len * CL, d.G), 256, 0, q>>>(ca, cb, sig, S->bases, sgn, of, ogs, acc, d);
-        else k_dgrad<<<dim3(nblk(nD, 128), d.G), 128, 0, q>>>(ca, cb, sig, S->bases, sgn, of, ogs, acc, d);
+        if (fastM) lk(k_dgrad_c, dim3(d.f_len * CL, d.G), 256, 0, q, ca, cb, sig, S->bases, sgn, of, ogs, acc, d);
+        else lk(k_dgrad, dim3(nblk(nD, 128), d.G), 128, 0, q, ca, cb, sig, S->bases, sgn, of, ogs, acc, d);
     };
     auto run_tconv = [=](const float* x, int L, const float* filt, int64_t gs, float* out, int acc, cudaStream_t q) {
-        k_tconv_l<<<d.NS * d.c, 128, 0, q>>>(x, LCNT(L), LIDX(L), LVAL(L), filt, gs, out, acc, d);
+        lk(k_tconv_l, d.NS * d.c, 128, 0, q, x, LCNT(L), LIDX(L), LVAL(L), filt, gs, out, acc, d);
     };
     auto run_fgrad = [=](const float* A, const float* x, int L, float* of, int64_t ogs, int acc, cudaStream_t q) {
-        k_fgrad_l<<<dim3(d.K, d.h, d.G), 128, 0, q>>>(A, x, LCNT(L), LIDX(L), LVAL(L), of, ogs, acc, d);
+        lk(k_fgrad_l, dim3(d.K, d.h, d.G), 128, 0, q, A, x, LCNT(L), LIDX(L), LVAL(L), of, ogs, acc, d);
     };
     // two independent adjoint kernels of one op: the second runs on the aux stream (a parallel branch of the captured graph)
     auto par2 = [=](cudaStream_t q, const std::function<void(cudaStream_t)>& k1, const std::function<void(cudaStream_t)>& k2) {
@@ -186,18 +199,18 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
     };
     std::map<size_t, int> xlist;                 // buffer offset of an x tensor -> list of its data
     auto op_recon = [&](Buf ca, Buf cb, Buf filt, int64_t gs, Buf out, const char* nm) {
-        T.push_back({[=](cudaStream_t q) { k_recon<<<nblk(nS * 32, 256), 256, 0, q>>>(S->data + ca.off, S->data + cb.off, S->data + filt.off, gs, S->data + out.off, 0, d); },
+        T.push_back({[=](cudaStream_t q) { lk(k_recon, nblk(nS * 32, 256), 256, 0, q, S->data + ca.off, S->data + cb.off, S->data + filt.off, gs, S->data + out.off, 0, d); },
                      [=](cudaStream_t q) {
                          // d ca, d cb: corr_sig form with signal = d out ; d filt: dgrad form with signal = d out
-                         par2(q, [=](cudaStream_t r) { k_corr_sig<<<nblk(nZ, 256), 256, 0, r>>>(S->grad + out.off, S->bases, 0.f, S->data + filt.off, gs, S->grad + ca.off, S->grad + cb.off, 1, d); },
+                         par2(q, [=](cudaStream_t r) { lk(k_corr_sig, nblk(nZ, 256), 256, 0, r, S->grad + out.off, S->bases, 0.f, S->data + filt.off, gs, S->grad + ca.off, S->grad + cb.off, 1, d); },
                                  [=](cudaStream_t r) { run_dgrad(S->data + ca.off, S->data + cb.off, S->grad + out.off, 0.f, S->grad + filt.off, gs, 1, r); });
                      },
                      nm});
     };
     auto op_corr_sig = [&](Buf sig, float sgn, Buf filt, int64_t gs, Buf oa, Buf ob, const char* nm) {
-        T.push_back({[=](cudaStream_t q) { k_corr_sig<<<nblk(nZ, 256), 256, 0, q>>>(S->data + sig.off, S->bases, sgn, S->data + filt.off, gs, S->data + oa.off, S->data + ob.off, 0, d); },
+        T.push_back({[=](cudaStream_t q) { lk(k_corr_sig, nblk(nZ, 256), 256, 0, q, S->data + sig.off, S->bases, sgn, S->data + filt.off, gs, S->data + oa.off, S->data + ob.off, 0, d); },
                      [=](cudaStream_t q) {
-                         par2(q, [=](cudaStream_t r) { k_recon<<<nblk(nS * 32, 256), 256, 0, r>>>(S->grad + oa.off, S->grad + ob.off, S->data + filt.off, gs, S->grad + sig.off, 1, d); },
+                         par2(q, [=](cudaStream_t r) { lk(k_recon, nblk(nS * 32, 256), 256, 0, r, S->grad + oa.off, S->grad + ob.off, S->data + filt.off, gs, S->grad + sig.off, 1, d); },
                                  [=](cudaStream_t r) { run_dgrad(S->grad + oa.off, S->grad + ob.off, S->data + sig.off, sgn, S->grad + filt.off, gs, 1, r); });
                      },
                      nm});
@@ -206,8 +219,8 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         T.push_back({[=](cudaStream_t q) { run_dgrad(S->data + ca.off, S->data + cb.off, S->data + sig.off, sgn, S->data + outG.off, nD, 0, q); },
                      [=](cudaStream_t q) {
                          // d ca, d cb: corr_sig with filter = dG (per group) ; d sig: recon with filter = dG
-                         par2(q, [=](cudaStream_t r) { k_corr_sig<<<nblk(nZ, 256), 256, 0, r>>>(S->data + sig.off, S->bases, sgn, S->grad + outG.off, nD, S->grad + ca.off, S->grad + cb.off, 1, d); },
-                                 [=](cudaStream_t r) { k_recon<<<nblk(nS * 32, 256), 256, 0, r>>>(S->data + ca.off, S->data + cb.off, S->grad + outG.off, nD, S->grad + sig.off, 1, d); });
+                         par2(q, [=](cudaStream_t r) { lk(k_corr_sig, nblk(nZ, 256), 256, 0, r, S->data + sig.off, S->bases, sgn, S->grad + outG.off, nD, S->grad + ca.off, S->grad + cb.off, 1, d); },
+                                 [=](cudaStream_t r) { lk(k_recon, nblk(nS * 32, 256), 256, 0, r, S->data + ca.off, S->data + cb.off, S->grad + outG.off, nD, S->grad + sig.off, 1, d); });
                      },
                      nm});
     };
@@ -247,10 +260,10 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         const bool ms_cluster = mask_cap <= MS_MAXV * 512 && d.G < 32;
         const int ms_cap1 = (int)std::min<int64_t>(2 * (int64_t)d.B * d.c * d.M, 49152);
         T.push_back({[=](cudaStream_t q) {
-                         if (ms_cluster) k_mask_scale_c<<<d.G * CL, 512, (size_t)mask_cap * 4, q>>>(S->data + z.off, S->data + y.off, S->data + zy.off, S->data + med.off, d);
-                         else k_mask_scale_s<<<d.G, 1024, (size_t)ms_cap1 * 4, q>>>(S->data + z.off, S->data + y.off, S->data + zy.off, S->data + med.off, ms_cap1, d);
+                         if (ms_cluster) lk(k_mask_scale_c, d.G * CL, MS_THREADS, ((size_t)mask_cap + 2 * MS_BINS + MS_CAND) * 4, q, S->data + z.off, S->data + y.off, S->data + zy.off, S->data + med.off, mask_cap, d);
+                         else lk(k_mask_scale_s, d.G, 1024, (size_t)ms_cap1 * 4, q, S->data + z.off, S->data + y.off, S->data + zy.off, S->data + med.off, ms_cap1, d);
                      },
-                     [=](cudaStream_t q) { k_mask_scale_bwd<<<nblk(nZY, 256), 256, 0, q>>>(S->data + z.off, S->data + y.off, S->data + med.off, S->grad + zy.off, S->grad + z.off, S->grad + y.off, d); },
+                     [=](cudaStream_t q) { lk(k_mask_scale_bwd, nblk(nZY, 256), 256, 0, q, S->data + z.off, S->data + y.off, S->data + med.off, S->grad + zy.off, S->grad + z.off, S->grad + y.off, d); },
                      nm});
     };
     // returns nothing; registers the data list of xout; `glist` = list id for d g (allocated by the caller)
@@ -260,15 +273,15 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         xlist[xout.off] = xl;
         const bool hp_ = xprev != nullptr; const Buf xp = hp_ ? *xprev : Buf{};
         const size_t smem = (size_t)d.l * d.K * 4;
-        T.push_back({[=](cudaStream_t q) { k_topq_s<<<d.NS, 256, smem, q>>>(hp_ ? S->data + xp.off : nullptr, S->data + g.off, SCP, i_om, coef, S->data + xout.off, S->bits + bo, LCNT(xl), LIDX(xl), LVAL(xl), d); },
-                     [=](cudaStream_t q) { k_topq_s_bwd<<<d.NS, 256, 0, q>>>(S->bits + bo, S->data + g.off, SCP, i_om, coef, S->grad + xout.off, hp_ ? S->grad + xp.off : nullptr, S->grad + g.off, DSCP, om_train, LCNT(glist), LIDX(glist), LVAL(glist), d); },
+        T.push_back({[=](cudaStream_t q) { lk(k_topq_s, d.NS, 256, smem, q, hp_ ? S->data + xp.off : nullptr, S->data + g.off, SCP, i_om, coef, S->data + xout.off, S->bits + bo, LCNT(xl), LIDX(xl), LVAL(xl), d); },
+                     [=](cudaStream_t q) { lk(k_topq_s_bwd, d.NS, 256, 0, q, S->bits + bo, S->data + g.off, SCP, i_om, coef, S->grad + xout.off, hp_ ? S->grad + xp.off : nullptr, S->grad + g.off, DSCP, om_train, LCNT(glist), LIDX(glist), LVAL(glist), d); },
                      nm});
     };
 
     // ---- warm-up (model.jl:224-232) --------------------------------------------------------------
     Buf z = B.alloc(nZ), y = B.alloc(nZ);
-    T.push_back({[=](cudaStream_t q) { k_warm_zy<<<nblk(nZ, 256), 256, 0, q>>>(S->bases, S->data + De.off, SCP, S->i_eta_w, S->i_lam_w, S->data + z.off, S->data + y.off, d); },
-                 [=](cudaStream_t q) { k_warm_zy_bwd<<<nblk(nZ, 256), 256, 0, q>>>(S->bases, SCP, S->i_eta_w, S->data + z.off, S->data + y.off, S->grad + z.off, S->grad + y.off, S->grad + De.off, d); },
+    T.push_back({[=](cudaStream_t q) { lk(k_warm_zy, nblk(nZ, 256), 256, 0, q, S->bases, S->data + De.off, SCP, S->i_eta_w, S->i_lam_w, S->data + z.off, S->data + y.off, d); },
+                 [=](cudaStream_t q) { lk(k_warm_zy_bwd, nblk(nZ, 256), 256, 0, q, S->bases, SCP, S->i_eta_w, S->data + z.off, S->data + y.off, S->grad + z.off, S->grad + y.off, S->grad + De.off, d); },
                  "warm_zy"});
     Buf zy = B.alloc(nZY);
     op_mask_scale(z, y, zy, "warm_mask");
@@ -288,8 +301,8 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         if (!have_dual) { al = B.alloc(nZ); be = B.alloc(nZ); }      // zero duals (model.jl:338): arenas are zero-filled, never written
         {
             const Buf zc = z, yc = y, fxc = fx, alc = al, bec = be;
-            T.push_back({[=](cudaStream_t q) { k_zy_update<<<nblk(nZ, 256), 256, 0, q>>>(S->data + zc.off, S->data + yc.off, S->data + gz.off, S->data + gy.off, S->data + fxc.off, S->data + alc.off, S->data + bec.off, SCP, i_eta, i_lam, i_rho, S->data + zn.off, S->data + yn.off, d); },
-                         [=](cudaStream_t q) { k_zy_update_bwd<<<nblk(nZ, 256), 256, 0, q>>>(S->data + zc.off, S->data + yc.off, S->data + gz.off, S->data + gy.off, S->data + fxc.off, S->data + alc.off, S->data + bec.off, SCP, i_eta, i_lam, i_rho, S->data + zn.off, S->data + yn.off, S->grad + zn.off, S->grad + yn.off, S->grad + zc.off, S->grad + yc.off, S->grad + gz.off, S->grad + gy.off, S->grad + fxc.off, S->grad + alc.off, S->grad + bec.off, DSCP, d); },
+            T.push_back({[=](cudaStream_t q) { lk(k_zy_update, nblk(nZ, 256), 256, 0, q, S->data + zc.off, S->data + yc.off, S->data + gz.off, S->data + gy.off, S->data + fxc.off, S->data + alc.off, S->data + bec.off, SCP, i_eta, i_lam, i_rho, S->data + zn.off, S->data + yn.off, d); },
+                         [=](cudaStream_t q) { lk(k_zy_update_bwd, nblk(nZ, 256), 256, 0, q, S->data + zc.off, S->data + yc.off, S->data + gz.off, S->data + gy.off, S->data + fxc.off, S->data + alc.off, S->data + bec.off, SCP, i_eta, i_lam, i_rho, S->data + zn.off, S->data + yn.off, S->grad + zn.off, S->grad + yn.off, S->grad + zc.off, S->grad + yc.off, S->grad + gz.off, S->grad + gy.off, S->grad + fxc.off, S->grad + alc.off, S->grad + bec.off, DSCP, d); },
                          "zy_update"});
         }
         z = zn; y = yn;
@@ -297,8 +310,8 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         op_mask_scale(z, y, zy2, "mask_scale");
         {
             const Buf fxc = fx, alc = al, bec = be;
-            T.push_back({[=](cudaStream_t q) { k_d_build<<<nblk(nZY, 256), 256, 0, q>>>(S->data + fxc.off, S->data + zy2.off, S->data + alc.off, S->data + bec.off, S->data + dd.off, d); },
-                         [=](cudaStream_t q) { k_d_build_bwd<<<nblk(nZY, 256), 256, 0, q>>>(S->grad + dd.off, S->grad + fxc.off, S->grad + zy2.off, S->grad + alc.off, S->grad + bec.off, d); },
+            T.push_back({[=](cudaStream_t q) { lk(k_d_build, nblk(nZY, 256), 256, 0, q, S->data + fxc.off, S->data + zy2.off, S->data + alc.off, S->data + bec.off, S->data + dd.off, d); },
+                         [=](cudaStream_t q) { lk(k_d_build_bwd, nblk(nZY, 256), 256, 0, q, S->grad + dd.off, S->grad + fxc.off, S->grad + zy2.off, S->grad + alc.off, S->grad + bec.off, d); },
                          "d_build"});
         }
         { const int gl = B.n_lists++; op_corr2d(dd, Fe, 0, g, gl, "corr2d"); op_topq(&x, g, i_om, -1.f, 1, xn, gl, "topq"); }
@@ -309,8 +322,8 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         if (n + 1 < d.npx) {      // the duals after the last pass are never read (model.jl:356 returns Z, Y, X)
             Buf an = B.alloc(nZ), bn = B.alloc(nZ);
             const Buf alc = al, bec = be, fxc = fx, zc = z, yc = y;
-            T.push_back({[=](cudaStream_t q) { k_dual<<<nblk(nZ, 256), 256, 0, q>>>(S->data + alc.off, S->data + bec.off, S->data + fxc.off, S->data + zc.off, S->data + yc.off, S->data + an.off, S->data + bn.off, d); },
-                         [=](cudaStream_t q) { k_dual_bwd<<<nblk(nZ, 256), 256, 0, q>>>(S->grad + an.off, S->grad + bn.off, S->grad + alc.off, S->grad + bec.off, S->grad + fxc.off, S->grad + zc.off, S->grad + yc.off, d); },
+            T.push_back({[=](cudaStream_t q) { lk(k_dual, nblk(nZ, 256), 256, 0, q, S->data + alc.off, S->data + bec.off, S->data + fxc.off, S->data + zc.off, S->data + yc.off, S->data + an.off, S->data + bn.off, d); },
+                         [=](cudaStream_t q) { lk(k_dual_bwd, nblk(nZ, 256), 256, 0, q, S->grad + an.off, S->grad + bn.off, S->grad + alc.off, S->grad + bec.off, S->grad + fxc.off, S->grad + zc.off, S->grad + yc.off, d); },
                          "dual"});
             al = an; be = bn;
         }
@@ -335,8 +348,8 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         op_dgrad(z, y, rec, +1.f, Gm, "df_dgrad");                      // R = sumZD + sumYRD + S  ('+S': model.jl:282-285)
         {
             const Buf Dcc = Dc; const int64_t gsc = Dgs;
-            T.push_back({[=](cudaStream_t q) { k_d_update<<<nblk((int64_t)d.G * d.fl * d.M, 128), 128, 0, q>>>(S->data + Dcc.off, gsc, S->data + Gm.off, SCP, i_mu, S->data + Dn.off, d); },
-                         [=](cudaStream_t q) { k_d_update_bwd<<<nblk((int64_t)d.G * d.fl * d.M, 128), 128, 0, q>>>(S->data + Dcc.off, gsc, S->data + Gm.off, SCP, i_mu, S->data + Dn.off, S->grad + Dn.off, S->grad + Dcc.off, gsc, S->grad + Gm.off, DSCP, d); },
+            T.push_back({[=](cudaStream_t q) { lk(k_d_update, nblk((int64_t)d.G * d.fl * d.M, 128), 128, 0, q, S->data + Dcc.off, gsc, S->data + Gm.off, SCP, i_mu, S->data + Dn.off, d); },
+                         [=](cudaStream_t q) { lk(k_d_update_bwd, nblk((int64_t)d.G * d.fl * d.M, 128), 128, 0, q, S->data + Dcc.off, gsc, S->data + Gm.off, SCP, i_mu, S->data + Dn.off, S->grad + Dn.off, S->grad + Dcc.off, gsc, S->grad + Gm.off, DSCP, d); },
                          "d_update"});
         }
         Dc = Dn; Dgs = nD;
@@ -346,15 +359,15 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         op_tconv(x, Fc, Fgs, fxc, "df_tconv");
         {
             const Buf th = theta; const bool ht = have_theta;
-            T.push_back({[=](cudaStream_t q) { k_sub3<<<nblk(nZY, 256), 256, 0, q>>>(S->data + fxc.off, S->data + zyF.off, ht ? S->data + th.off : nullptr, -1.f, S->data + e.off, nZY); },
-                         [=](cudaStream_t q) { k_sub3_bwd<<<nblk(nZY, 256), 256, 0, q>>>(S->grad + e.off, S->grad + fxc.off, S->grad + zyF.off, ht ? S->grad + th.off : nullptr, -1.f, nZY); },
+            T.push_back({[=](cudaStream_t q) { lk(k_sub3, nblk(nZY, 256), 256, 0, q, S->data + fxc.off, S->data + zyF.off, ht ? S->data + th.off : nullptr, -1.f, S->data + e.off, nZY); },
+                         [=](cudaStream_t q) { lk(k_sub3_bwd, nblk(nZY, 256), 256, 0, q, S->grad + e.off, S->grad + fxc.off, S->grad + zyF.off, ht ? S->grad + th.off : nullptr, -1.f, nZY); },
                          "e_build"});
         }
         op_fgrad(e, x, Fg, "df_fgrad");
         {
             const Buf Fcc = Fc; const int64_t gsc = Fgs;
-            T.push_back({[=](cudaStream_t q) { k_f_update<<<d.G * d.K, 256, 0, q>>>(S->data + Fcc.off, gsc, S->data + Fg.off, SCP, i_kap, i_kaps, S->data + Fn.off, S->data + nrm.off, d); },
-                         [=](cudaStream_t q) { k_f_update_bwd<<<d.G * d.K, 256, 0, q>>>(S->data + Fn.off, S->data + nrm.off, S->data + Fg.off, SCP, i_kap, i_kaps, S->grad + Fn.off, S->grad + Fcc.off, gsc, S->grad + Fg.off, DSCP, d); },
+            T.push_back({[=](cudaStream_t q) { lk(k_f_update, d.G * d.K, 256, 0, q, S->data + Fcc.off, gsc, S->data + Fg.off, SCP, i_kap, i_kaps, S->data + Fn.off, S->data + nrm.off, d); },
+                         [=](cudaStream_t q) { lk(k_f_update_bwd, d.G * d.K, 256, 0, q, S->data + Fn.off, S->data + nrm.off, S->data + Fg.off, SCP, i_kap, i_kaps, S->grad + Fn.off, S->grad + Fcc.off, gsc, S->grad + Fg.off, DSCP, d); },
                          "f_update"});
         }
         Fc = Fn; Fgs = nF;
@@ -364,8 +377,8 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
             Buf fx2 = B.alloc(nZY), thn = B.alloc(nZY);
             op_tconv(x, Fc, Fgs, fx2, "theta_tconv");
             const Buf th = theta; const bool ht = have_theta;
-            T.push_back({[=](cudaStream_t q) { k_sub3<<<nblk(nZY, 256), 256, 0, q>>>(S->data + fx2.off, S->data + zyF.off, ht ? S->data + th.off : nullptr, +1.f, S->data + thn.off, nZY); },
-                         [=](cudaStream_t q) { k_sub3_bwd<<<nblk(nZY, 256), 256, 0, q>>>(S->grad + thn.off, S->grad + fx2.off, S->grad + zyF.off, ht ? S->grad + th.off : nullptr, +1.f, nZY); },
+            T.push_back({[=](cudaStream_t q) { lk(k_sub3, nblk(nZY, 256), 256, 0, q, S->data + fx2.off, S->data + zyF.off, ht ? S->data + th.off : nullptr, +1.f, S->data + thn.off, nZY); },
+                         [=](cudaStream_t q) { lk(k_sub3_bwd, nblk(nZY, 256), 256, 0, q, S->grad + thn.off, S->grad + fx2.off, S->grad + zyF.off, ht ? S->grad + th.off : nullptr, +1.f, nZY); },
                          "theta"});
             theta = thn; have_theta = true;
         }
@@ -377,8 +390,8 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
     op_tconv(x, Fc, Fgs, fxL, "loss_tconv");
     {
         const Buf ls = s->loss;
-        T.push_back({[=](cudaStream_t q) { k_loss<<<d.G, 1024, 0, q>>>(S->data + recL.off, S->bases, S->data + fxL.off, S->data + zyF.off, S->data + ls.off, d); },
-                     [=](cudaStream_t q) { k_loss_bwd<<<nblk(std::max(nS, nZY), 256), 256, 0, q>>>(S->data + recL.off, S->bases, S->data + fxL.off, S->data + zyF.off, 1.f / (float)d.G, S->grad + recL.off, S->grad + fxL.off, S->grad + zyF.off, d); },
+        T.push_back({[=](cudaStream_t q) { lk(k_loss, d.G, 1024, 0, q, S->data + recL.off, S->bases, S->data + fxL.off, S->data + zyF.off, S->data + ls.off, d); },
+                     [=](cudaStream_t q) { lk(k_loss_bwd, nblk(std::max(nS, nZY), 256), 256, 0, q, S->data + recL.off, S->bases, S->data + fxL.off, S->data + zyF.off, 1.f / (float)d.G, S->grad + recL.off, S->grad + fxL.off, S->grad + zyF.off, d); },
                      "loss"});
     }
     s->arena = B.cursor; s->bits_n = B.bit_cursor; s->n_lists = B.n_lists;
@@ -401,7 +414,7 @@ static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
     MB_CUDA(ctx, cudaMalloc(&s->lidx, (size_t)std::max(1, s->n_lists) * s->d.NS * LIST_CAP * 2));
     MB_CUDA(ctx, cudaMalloc(&s->lval, (size_t)std::max(1, s->n_lists) * s->d.NS * LIST_CAP * 4));
     MB_CUDA(ctx, cudaMemset(s->lcnt, 0, (size_t)std::max(1, s->n_lists) * s->d.NS * 4));
-    if (s->mask_cap <= MS_MAXV * 512) MB_CUDA(ctx, cudaFuncSetAttribute(k_mask_scale_c, cudaFuncAttributeMaxDynamicSharedMemorySize, s->mask_cap * 4));
+    if (s->mask_cap <= MS_MAXV * 512) MB_CUDA(ctx, cudaFuncSetAttribute(k_mask_scale_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (s->mask_cap + 2 * MS_BINS + MS_CAND) * 4));
     MB_CUDA(ctx, cudaFuncSetAttribute(k_mask_scale_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<int64_t>(2 * (int64_t)s->d.B * s->d.c * s->d.M, 49152) * 4));
     MB_CUDA(ctx, cudaFuncSetAttribute(k_topq_s, cudaFuncAttributeMaxDynamicSharedMemorySize, s->d.l * s->d.K * 4));
     if (s->tensor) {
@@ -535,7 +548,7 @@ static void run_op(mb200_csc* s, Op& op, bool fwd, cudaStream_t q) {
 
 static void enqueue_step(mb200_csc* s, const uint32_t* words, int64_t rowwords, const int64_t* idx_dev, bool backward, cudaStream_t q) {
     const CscDims d = s->d;
-    k_unpack_bases<<<nblk((int64_t)d.NS * d.Lb, 256), 256, 0, q>>>(words, rowwords, idx_dev, s->bases, d);
+    lk(k_unpack_bases, nblk((int64_t)d.NS * d.Lb, 256), 256, 0, q, words, rowwords, idx_dev, s->bases, d);
     for (auto& op : s->tape) run_op(s, op, true, q);
     if (backward) {
         cudaMemsetAsync(s->grad, 0, s->arena * 4, q);
@@ -552,14 +565,19 @@ static int launch_step(mb200_ctx* ctx, mb200_csc* s, const uint32_t* words, int6
             if (s->graph) { cudaGraphDestroy(s->graph); s->graph = nullptr; }
             MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             MB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            const int64_t c0 = g_lk_count;
             enqueue_step(s, words, rowwords, idx_dev, true, ctx->stream);
+            s->graph_kernels = g_lk_count - c0;                  // kernel nodes of the captured step
             MB_CUDA(ctx, cudaStreamEndCapture(ctx->stream, &s->graph));
             MB_CUDA(ctx, cudaGraphInstantiate(&s->gexec, s->graph, 0));
             s->graph_ok = true; s->graph_words = words; s->graph_rowwords = rowwords;
         }
         MB_CUDA(ctx, cudaGraphLaunch(s->gexec, ctx->stream));
+        ctx->launches[T_CSC] += s->graph_kernels;
     } else {
+        const int64_t c0 = g_lk_count;
         enqueue_step(s, words, rowwords, idx_dev, false, ctx->stream);
+        ctx->launches[T_CSC] += g_lk_count - c0;
     }
     MB_CUDA(ctx, cudaGetLastError());
     return MB200_OK;
@@ -599,21 +617,6 @@ static int run_step_host(mb200_ctx* ctx, mb200_csc* s, const uint8_t* ascii, int
     return launch_step(ctx, s, s->batch_words, rw, s->idx_identity_dev, backward);
 }
 
-static int64_t tape_launches(const mb200_csc* s, bool backward) {
-    // counted once by running the tape on a capture-free dry pass is overkill; kernels per op are fixed:
-    int64_t n = 1;
-    for (auto& op : s->tape) {
-        if (op.kind) continue;
-        const std::string nm = op.name;
-        const int f = nm == "prep" ? 10 : 1;
-        int b = 1;
-        if (nm == "prep") b = 9;
-        else if (nm.find("recon") != std::string::npos || nm.find("corr_sig") != std::string::npos || nm.find("dgrad") != std::string::npos ||
-                 nm.find("corr2d") != std::string::npos || nm.find("tconv") != std::string::npos || nm.find("fgrad") != std::string::npos) b = 2;
-        n += f + (backward ? b : 0);
-    }
-    return n;
-}
 
 // loss (and gradient) of n_groups batches.  seq_idx: n_groups*batch_size indices into seqs.
 // loss_out: n_groups*3 floats {total, reconstruction, syntax} per group; grads: n_trainable floats = mean over groups (or NULL).
@@ -627,7 +630,6 @@ extern "C" int32_t mb200_csc_loss_grad(mb200_ctx* ctx, mb200_csc* s, const mb200
     int rc = run_step(ctx, s, seqs, seq_idx, true);
     if (rc) return rc;
     tm.end(tc);
-    ctx->launches[T_CSC] += tape_launches(s, true);
     const int td = tm.begin(T_D2H);
     if (loss_out) MB_CUDA(ctx, cudaMemcpyAsync(loss_out, s->data + s->loss.off, (size_t)s->d.G * 3 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (grads) MB_CUDA(ctx, cudaMemcpyAsync(grads, s->g_raw, (size_t)s->n_train * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -643,7 +645,6 @@ extern "C" int32_t mb200_csc_step_begin(mb200_ctx* ctx, mb200_csc* s, const mb20
     if (!ctx || !s || !seqs || !seq_idx) return MB200_E_INVALID;
     if (s->xyz_only) MB_FAIL(ctx, MB200_E_INVALID, "csc: handle was created forward_only");
     MB_CUDA(ctx, cudaSetDevice(ctx->device));
-    ctx->launches[T_CSC] += tape_launches(s, true);
     return run_step(ctx, s, seqs, seq_idx, true);
 }
 
@@ -655,7 +656,6 @@ extern "C" int32_t mb200_csc_step_begin_host(mb200_ctx* ctx, mb200_csc* s, const
     if (!ctx || !s || !ascii_rows) return MB200_E_INVALID;
     if (s->xyz_only) MB_FAIL(ctx, MB200_E_INVALID, "csc: handle was created forward_only");
     MB_CUDA(ctx, cudaSetDevice(ctx->device));
-    ctx->launches[T_CSC] += tape_launches(s, true);
     return run_step_host(ctx, s, ascii_rows, n_rows, true);
 }
 
@@ -665,10 +665,10 @@ extern "C" int32_t mb200_csc_adabelief_step(mb200_ctx* ctx, mb200_csc* s, float 
     MB_CUDA(ctx, cudaSetDevice(ctx->device));
     s->step_count += 1;
     const float c1 = 1.f - powf(beta1, (float)s->step_count), c2 = 1.f - powf(beta2, (float)s->step_count);
-    k_adabelief<<<nblk(s->n_train, 256), 256, 0, ctx->stream>>>(s->p_raw, s->g_raw, s->mt, s->st, eta, beta1, beta2, eps * eps, c1, c2, (int)s->n_train);
+    lk(k_adabelief, nblk(s->n_train, 256), 256, 0, ctx->stream, s->p_raw, s->g_raw, s->mt, s->st, eta, beta1, beta2, eps * eps, c1, c2, (int)s->n_train);
     float* d_l1 = s->data + s->loss.off + (size_t)s->d.G * 3;       // slot right after the per-group losses
     MB_CUDA(ctx, cudaMemsetAsync(d_l1, 0, 4, ctx->stream));
-    k_l1_F<<<s->d.K, 256, 0, ctx->stream>>>(s->p_raw + s->off_F, d_l1, s->d);
+    lk(k_l1_F, s->d.K, 256, 0, ctx->stream, s->p_raw + s->off_F, d_l1, s->d);
     ctx->launches[T_CSC] += 2;
     MB_CUDA(ctx, cudaMemcpyAsync(s->host_out, s->data + s->loss.off, ((size_t)s->d.G * 3 + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -691,12 +691,38 @@ extern "C" int32_t mb200_csc_get_buffer(mb200_ctx* ctx, mb200_csc* s, const char
     return MB200_OK;
 }
 
+// the batch-median mask alone (create_ZY_mask + cat_ZY, model.jl:194-210) on host arrays z,y [G][B*c][M] -> zy [G][B*c][2M], med [G]:
+// runs the very kernel the step uses for this handle's shape, so order-statistic corner cases can be checked in isolation
+extern "C" int32_t mb200_csc_median_mask(mb200_ctx* ctx, mb200_csc* s, const float* z, const float* y, float* zy_out, float* med_out) {
+    if (!ctx || !s || !z || !y || !zy_out || !med_out) return MB200_E_INVALID;
+    const CscDims d = s->d;
+    MB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nZ = (size_t)d.NS * d.c * d.M;
+    float* buf = nullptr;
+    MB_CUDA(ctx, cudaMalloc(&buf, (4 * nZ + d.G) * 4));
+    float *dz = buf, *dy = buf + nZ, *dzy = buf + 2 * nZ, *dmed = buf + 4 * nZ;
+    cudaMemcpyAsync(dz, z, nZ * 4, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(dy, y, nZ * 4, cudaMemcpyHostToDevice, ctx->stream);
+    const bool ms_cluster = s->mask_cap <= MS_MAXV * 512 && d.G < 32;
+    const int ms_cap1 = (int)std::min<int64_t>(2 * (int64_t)d.B * d.c * d.M, 49152);
+    if (ms_cluster) lk(k_mask_scale_c, d.G * CL, MS_THREADS, ((size_t)s->mask_cap + 2 * MS_BINS + MS_CAND) * 4, ctx->stream, dz, dy, dzy, dmed, s->mask_cap, d);
+    else lk(k_mask_scale_s, d.G, 1024, (size_t)ms_cap1 * 4, ctx->stream, dz, dy, dzy, dmed, ms_cap1, d);
+    cudaMemcpyAsync(zy_out, dzy, 2 * nZ * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(med_out, dmed, (size_t)d.G * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(buf);
+    MB_CUDA(ctx, e);
+    return MB200_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // code retrieval (inference/_1_code_retrieval.jl:33-56): forward-only ADMM_XYZ over consecutive groups of batch_size
 // sequences; non-zeros of X as (position, fil, seq, Float16 mag), ordered by seq, fil, position.
 // ---------------------------------------------------------------------------------------------
 #define CODE_SLOTS 96
 __global__ void __launch_bounds__(128) k_emit_codes(const float* __restrict__ x, int64_t seq0, mb200_code* __restrict__ slots, int32_t* __restrict__ counts, CscDims d) {
+    PDL_SYNC();
     // one warp per sequence walks (fil, position) in order and compacts entries > 0 with ballots
     const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -744,11 +770,12 @@ extern "C" int32_t mb200_csc_codes(mb200_ctx* ctx, mb200_csc* s, const mb200_seq
         MB_CUDA(ctx, cudaMemcpyAsync(s->idx_dev, s->idx_pinned, (size_t)d.NS * 8, cudaMemcpyHostToDevice, ctx->stream));
         const int tc = tm.begin(T_CSC);
         // forward-only: run ops up to the last XYZ pass (a forward_only handle holds exactly those)
-        k_unpack_bases<<<nblk((int64_t)d.NS * d.Lb, 256), 256, 0, ctx->stream>>>(seqs->words, seqs->rowwords, s->idx_dev, s->bases, d);
+        const int64_t c0 = g_lk_count;
+        lk(k_unpack_bases, nblk((int64_t)d.NS * d.Lb, 256), 256, 0, ctx->stream, seqs->words, seqs->rowwords, s->idx_dev, s->bases, d);
         for (auto& op : s->tape) { if (op.kind) break; op.fwd(ctx->stream); if (std::string(op.name) == "df_mask") break; }
-        k_emit_codes<<<nblk((int64_t)d.NS * 32, 128), 128, 0, ctx->stream>>>(s->data + s->named["x"].off, first_seq + s0, d_slots, d_cnt, d);
+        lk(k_emit_codes, nblk((int64_t)d.NS * 32, 128), 128, 0, ctx->stream, s->data + s->named["x"].off, first_seq + s0, d_slots, d_cnt, d);
+        ctx->launches[T_CSC] += g_lk_count - c0;
         tm.end(tc);
-        ctx->launches[T_CSC] += tape_launches(s, false) + 1;
         MB_CUDA(ctx, cudaGetLastError());
         const int td = tm.begin(T_D2H);
         MB_CUDA(ctx, cudaMemcpyAsync(h_cnt.data(), d_cnt, (size_t)d.NS * 4, cudaMemcpyDeviceToHost, ctx->stream));

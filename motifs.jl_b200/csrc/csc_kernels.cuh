@@ -19,6 +19,9 @@ struct CscDims {
 };
 
 #define FULLMASK 0xffffffffu
+// Programmatic dependent launch (optional, MB200_PDL=1): every kernel of the step waits for the full completion (and memory
+// flush) of its predecessor before touching memory.  A no-op for a kernel launched without the attribute.
+#define PDL_SYNC() asm volatile("griddepcontrol.wait;" ::: "memory")
 __device__ __forceinline__ float warp_sum(float v) {
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
@@ -44,7 +47,7 @@ __device__ __forceinline__ float block_sum(float v) {
 // reverse-complement filter D[4(fl-1-j) + 3 - s[p+j]][m].  One thread per (n,p,m).
 __global__ void __launch_bounds__(256) k_warm_zy(const uint8_t* __restrict__ bases, const float* __restrict__ D,
                                                  const float* __restrict__ sc, int i_eta, int i_lam,
-                                                 float* __restrict__ z, float* __restrict__ y, CscDims d) {
+                                                 float* __restrict__ z, float* __restrict__ y, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.c * d.M) return;
     const int m = (int)(t % d.M);
@@ -66,7 +69,7 @@ __global__ void __launch_bounds__(256) k_warm_zy(const uint8_t* __restrict__ bas
 __global__ void __launch_bounds__(256) k_warm_zy_bwd(const uint8_t* __restrict__ bases, const float* __restrict__ sc, int i_eta,
                                                      const float* __restrict__ z, const float* __restrict__ y,
                                                      const float* __restrict__ dz, const float* __restrict__ dy,
-                                                     float* __restrict__ dD, CscDims d) {
+                                                     float* __restrict__ dD, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.c * d.M) return;
     const int m = (int)(t % d.M);
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(256) k_warm_zy_bwd(const uint8_t* __restrict__
 // (model.jl:238-239, 276-277, 313-314).  One warp per (n,t), lanes over m.
 __global__ void __launch_bounds__(256) k_recon(const float* __restrict__ ca, const float* __restrict__ cb,
                                                const float* __restrict__ filt, int64_t filt_gs,
-                                               float* __restrict__ out, int accumulate, CscDims d) {
+                                               float* __restrict__ out, int accumulate, CscDims d) { PDL_SYNC();
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wid >= (int64_t)d.NS * d.L4) return;
@@ -137,7 +140,7 @@ __device__ __forceinline__ float sig_at(const float* __restrict__ sig, const uin
 // (model.jl:240-241 z_grad/y_grad data terms).  One thread per (n,p,m).
 __global__ void __launch_bounds__(256) k_corr_sig(const float* __restrict__ sig, const uint8_t* __restrict__ bases, float sgn,
                                                   const float* __restrict__ filt, int64_t filt_gs,
-                                                  float* __restrict__ oa, float* __restrict__ ob, int accumulate, CscDims d) {
+                                                  float* __restrict__ oa, float* __restrict__ ob, int accumulate, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.c * d.M) return;
     const int m = (int)(t % d.M);
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(256) k_corr_sig(const float* __restrict__ sig,
 // (tau,m).  When the output is shared by all groups (out_gs == 0) contributions are added atomically.
 __global__ void __launch_bounds__(256) k_dgrad(const float* __restrict__ ca, const float* __restrict__ cb,
                                                const float* __restrict__ sig, const uint8_t* __restrict__ bases, float sgn,
-                                               float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) {
+                                               float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) { PDL_SYNC();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= d.f_len * d.M) return;
     const int g = blockIdx.y;
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(256) k_dgrad(const float* __restrict__ ca, con
 // =============================================================================================
 // U2 "corr2d": out[n,i,k] (+)= sum_{a<h} sum_{j<2M} A[n,i+a,j] F[a][j][k]   (model.jl:214,251). One thread per (n,i,k).
 __global__ void __launch_bounds__(128) k_corr2d(const float* __restrict__ A, const float* __restrict__ filt, int64_t filt_gs,
-                                                float* __restrict__ out, int accumulate, CscDims d) {
+                                                float* __restrict__ out, int accumulate, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.l * d.K) return;
     const int k = (int)(t % d.K);
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(128) k_corr2d(const float* __restrict__ A, con
 // U1 "tconv": out[n,i,j] (+)= sum_a sum_k x[n,i-a,k] F[a][j][k], 0 <= i-a < l   (model.jl:229,263,294,316,370).
 // One thread per (n,i,j); x holds few non-zeros (top-q), so zero rows are skipped (warp-uniform test).
 __global__ void __launch_bounds__(128) k_tconv(const float* __restrict__ x, const float* __restrict__ filt, int64_t filt_gs,
-                                               float* __restrict__ out, int accumulate, CscDims d) {
+                                               float* __restrict__ out, int accumulate, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.c * d.M2) return;
     const int j = (int)(t % d.M2);
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(128) k_tconv(const float* __restrict__ x, cons
 
 // U3 "fgrad": of[g][a][j][k] (+)= sum_{n in g} sum_{i<l} A[n,a+i,j] x[n,i,k]   (model.jl:292-302). grid.y = group.
 __global__ void __launch_bounds__(128) k_fgrad(const float* __restrict__ A, const float* __restrict__ x,
-                                               float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) {
+                                               float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) { PDL_SYNC();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= d.h * d.M2 * d.K) return;
     const int g = blockIdx.y;
@@ -255,7 +258,7 @@ __global__ void __launch_bounds__(256) k_zy_update(const float* __restrict__ z, 
                                                    const float* __restrict__ gz, const float* __restrict__ gy,
                                                    const float* __restrict__ fx, const float* __restrict__ al, const float* __restrict__ be,
                                                    const float* __restrict__ sc, int i_eta, int i_lam, int i_rho,
-                                                   float* __restrict__ zn, float* __restrict__ yn, CscDims d) {
+                                                   float* __restrict__ zn, float* __restrict__ yn, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.c * d.M) return;
     const int m = (int)(t % d.M);
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(256) k_zy_update_bwd(const float* __restrict__
                                                        const float* __restrict__ dzn, const float* __restrict__ dyn,
                                                        float* __restrict__ dz, float* __restrict__ dy, float* __restrict__ dgz, float* __restrict__ dgy,
                                                        float* __restrict__ dfx, float* __restrict__ dal, float* __restrict__ dbe,
-                                                       float* __restrict__ dsc, CscDims d) {
+                                                       float* __restrict__ dsc, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float s_eta = 0.f, s_lam = 0.f, s_rho = 0.f;
     if (t < (int64_t)d.NS * d.c * d.M) {
@@ -315,7 +318,7 @@ __device__ __forceinline__ float zy_elem(const float* __restrict__ z, const floa
     return j < d.M ? z[np * d.M + j] : y[np * d.M + (j - d.M)];
 }
 __global__ void __launch_bounds__(1024) k_mask_scale(const float* __restrict__ z, const float* __restrict__ y,
-                                                     float* __restrict__ zy, float* __restrict__ med_out, CscDims d) {
+                                                     float* __restrict__ zy, float* __restrict__ med_out, CscDims d) { PDL_SYNC();
     __shared__ unsigned int hist[256];
     __shared__ unsigned int s_prefix, s_rank, s_cnt;
     __shared__ float s_med;
@@ -385,7 +388,7 @@ __global__ void __launch_bounds__(1024) k_mask_scale(const float* __restrict__ z
     }
 }
 __global__ void __launch_bounds__(256) k_mask_scale_bwd(const float* __restrict__ z, const float* __restrict__ y, const float* __restrict__ med,
-                                                        const float* __restrict__ dzy, float* __restrict__ dz, float* __restrict__ dy, CscDims d) {
+                                                        const float* __restrict__ dzy, float* __restrict__ dz, float* __restrict__ dy, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.c * d.M2) return;
     const int j = (int)(t % d.M2);
@@ -397,7 +400,7 @@ __global__ void __launch_bounds__(256) k_mask_scale_bwd(const float* __restrict_
 
 // A9 input: dd = fx - (zy' - [alpha beta])   (model.jl:248-250)
 __global__ void __launch_bounds__(256) k_d_build(const float* __restrict__ fx, const float* __restrict__ zy, const float* __restrict__ al,
-                                                 const float* __restrict__ be, float* __restrict__ dd, CscDims d) {
+                                                 const float* __restrict__ be, float* __restrict__ dd, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.c * d.M2) return;
     const int j = (int)(t % d.M2);
@@ -406,7 +409,7 @@ __global__ void __launch_bounds__(256) k_d_build(const float* __restrict__ fx, c
     dd[t] = fx[t] - (zy[t] - ab);
 }
 __global__ void __launch_bounds__(256) k_d_build_bwd(const float* __restrict__ ddd, float* __restrict__ dfx, float* __restrict__ dzy,
-                                                     float* __restrict__ dal, float* __restrict__ dbe, CscDims d) {
+                                                     float* __restrict__ dal, float* __restrict__ dbe, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.c * d.M2) return;
     const int j = (int)(t % d.M2);
@@ -421,7 +424,7 @@ __global__ void __launch_bounds__(256) k_d_build_bwd(const float* __restrict__ d
 __device__ __forceinline__ unsigned int fkey(float v) { unsigned int b = __float_as_uint(v); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
 __device__ __forceinline__ float fkey_inv(unsigned int k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 __global__ void __launch_bounds__(256) k_topq(const float* __restrict__ xprev, const float* __restrict__ g, const float* __restrict__ sc, int i_om,
-                                              float coef, float* __restrict__ xout, uint8_t* __restrict__ bit, float* __restrict__ vq_out, CscDims d) {
+                                              float coef, float* __restrict__ xout, uint8_t* __restrict__ bit, float* __restrict__ vq_out, CscDims d) { PDL_SYNC();
     __shared__ unsigned int hist[256];
     __shared__ unsigned int s_prefix, s_rank;
     const int64_t n = blockIdx.x;
@@ -459,7 +462,7 @@ __global__ void __launch_bounds__(256) k_topq(const float* __restrict__ xprev, c
 }
 __global__ void __launch_bounds__(256) k_topq_bwd(const uint8_t* __restrict__ bit, const float* __restrict__ g, const float* __restrict__ sc, int i_om,
                                                   float coef, const float* __restrict__ dxout, float* __restrict__ dxprev, float* __restrict__ dg,
-                                                  float* __restrict__ dsc, int om_trainable, CscDims d) {
+                                                  float* __restrict__ dsc, int om_trainable, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float s = 0.f;
     if (t < (int64_t)d.NS * d.l * d.K) {
@@ -473,7 +476,7 @@ __global__ void __launch_bounds__(256) k_topq_bwd(const uint8_t* __restrict__ bi
 
 // dual update (model.jl:265-266): an = al + fx[:, :M] - z ; bn = be + fx[:, M:] - y
 __global__ void __launch_bounds__(256) k_dual(const float* __restrict__ al, const float* __restrict__ be, const float* __restrict__ fx,
-                                              const float* __restrict__ z, const float* __restrict__ y, float* __restrict__ an, float* __restrict__ bn, CscDims d) {
+                                              const float* __restrict__ z, const float* __restrict__ y, float* __restrict__ an, float* __restrict__ bn, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.c * d.M) return;
     const int m = (int)(t % d.M);
@@ -482,7 +485,7 @@ __global__ void __launch_bounds__(256) k_dual(const float* __restrict__ al, cons
     bn[t] = (be ? be[t] : 0.f) + fx[np * d.M2 + d.M + m] - y[t];
 }
 __global__ void __launch_bounds__(256) k_dual_bwd(const float* __restrict__ dan, const float* __restrict__ dbn, float* __restrict__ dal, float* __restrict__ dbe,
-                                                  float* __restrict__ dfx, float* __restrict__ dz, float* __restrict__ dy, CscDims d) {
+                                                  float* __restrict__ dfx, float* __restrict__ dz, float* __restrict__ dy, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.c * d.M) return;
     const int m = (int)(t % d.M);
@@ -495,13 +498,13 @@ __global__ void __launch_bounds__(256) k_dual_bwd(const float* __restrict__ dan,
 
 // out = a - b - (c ? c : 0)   over [NS][c][2M]   (e = fx - (zy + theta), model.jl:294; theta' = theta + fx - zy, :370 as out = fx - zy + theta)
 __global__ void __launch_bounds__(256) k_sub3(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c3, float csign,
-                                              float* __restrict__ out, int64_t n) {
+                                              float* __restrict__ out, int64_t n) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     out[t] = a[t] - b[t] + (c3 ? csign * c3[t] : 0.f);
 }
 __global__ void __launch_bounds__(256) k_sub3_bwd(const float* __restrict__ dout, float* __restrict__ da, float* __restrict__ db, float* __restrict__ dc3,
-                                                  float csign, int64_t n) {
+                                                  float csign, int64_t n) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const float g = dout[t];
@@ -511,7 +514,7 @@ __global__ void __launch_bounds__(256) k_sub3_bwd(const float* __restrict__ dout
 
 // A10 update (model.jl:287-288): Dn[g][4j+a][m] = D exp(-mu G) / sum_a' (D exp(-mu G)).  One thread per (g,j,m).
 __global__ void __launch_bounds__(256) k_d_update(const float* __restrict__ D, int64_t D_gs, const float* __restrict__ G, const float* __restrict__ sc, int i_mu,
-                                                  float* __restrict__ Dn, CscDims d) {
+                                                  float* __restrict__ Dn, CscDims d) { PDL_SYNC();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= d.G * d.fl * d.M) return;
     const int m = t % d.M;
@@ -528,7 +531,7 @@ __global__ void __launch_bounds__(256) k_d_update(const float* __restrict__ D, i
 }
 __global__ void __launch_bounds__(256) k_d_update_bwd(const float* __restrict__ D, int64_t D_gs, const float* __restrict__ G, const float* __restrict__ sc, int i_mu,
                                                       const float* __restrict__ Dn, const float* __restrict__ dDn,
-                                                      float* __restrict__ dD, int64_t dD_gs, float* __restrict__ dG, float* __restrict__ dsc, CscDims d) {
+                                                      float* __restrict__ dD, int64_t dD_gs, float* __restrict__ dG, float* __restrict__ dsc, CscDims d) { PDL_SYNC();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     float s_mu = 0.f;
     if (t < d.G * d.fl * d.M) {
@@ -558,7 +561,7 @@ __global__ void __launch_bounds__(256) k_d_update_bwd(const float* __restrict__ 
 
 // A11 update (model.jl:304-308): Fu = relu(F - kap*Fg - kap*kaps) ; Fn[:,:,k] = Fu[:,:,k] / ||Fu[:,:,k]||_2.  One block per (g,k).
 __global__ void __launch_bounds__(256) k_f_update(const float* __restrict__ F, int64_t F_gs, const float* __restrict__ Fg, const float* __restrict__ sc,
-                                                  int i_kap, int i_kaps, float* __restrict__ Fn, float* __restrict__ nrm, CscDims d) {
+                                                  int i_kap, int i_kaps, float* __restrict__ Fn, float* __restrict__ nrm, CscDims d) { PDL_SYNC();
     __shared__ float s_n;
     const int k = blockIdx.x % d.K, g = blockIdx.x / d.K;
     const float kap = sc[i_kap], kaps = sc[i_kaps];
@@ -581,7 +584,7 @@ __global__ void __launch_bounds__(256) k_f_update(const float* __restrict__ F, i
 }
 __global__ void __launch_bounds__(256) k_f_update_bwd(const float* __restrict__ Fn, const float* __restrict__ nrm, const float* __restrict__ Fg,
                                                       const float* __restrict__ sc, int i_kap, int i_kaps, const float* __restrict__ dFn,
-                                                      float* __restrict__ dF, int64_t dF_gs, float* __restrict__ dFg, float* __restrict__ dsc, CscDims d) {
+                                                      float* __restrict__ dF, int64_t dF_gs, float* __restrict__ dFg, float* __restrict__ dsc, CscDims d) { PDL_SYNC();
     __shared__ float s_dot;
     const int k = blockIdx.x % d.K, g = blockIdx.x / d.K;
     const float kap = sc[i_kap], kaps = sc[i_kaps];
@@ -612,7 +615,7 @@ __global__ void __launch_bounds__(256) k_f_update_bwd(const float* __restrict__ 
 
 // A12 (model.jl:310-325): loss[g] = (1/B) (sum (recon - S)^2 + sum (fx - zy)^2).  One block per group.
 __global__ void __launch_bounds__(1024) k_loss(const float* __restrict__ recon, const uint8_t* __restrict__ bases, const float* __restrict__ fx,
-                                               const float* __restrict__ zy, float* __restrict__ loss, CscDims d) {
+                                               const float* __restrict__ zy, float* __restrict__ loss, CscDims d) { PDL_SYNC();
     const int g = blockIdx.x;
     float a = 0.f, b = 0.f;
     const int64_t n0 = (int64_t)g * d.B;
@@ -629,7 +632,7 @@ __global__ void __launch_bounds__(1024) k_loss(const float* __restrict__ recon, 
 // seeds the adjoints: d loss_total / d loss[g] = wgt (1/G for the mean over groups)
 __global__ void __launch_bounds__(256) k_loss_bwd(const float* __restrict__ recon, const uint8_t* __restrict__ bases, const float* __restrict__ fx,
                                                   const float* __restrict__ zy, float wgt, float* __restrict__ drecon, float* __restrict__ dfx,
-                                                  float* __restrict__ dzy, CscDims d) {
+                                                  float* __restrict__ dzy, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const float s = 2.f * wgt / (float)d.B;
     if (t < (int64_t)d.NS * d.L4) drecon[t] += s * sig_at(recon, bases, -1.f, t / d.L4, (int)(t % d.L4), d);
@@ -640,16 +643,20 @@ __global__ void __launch_bounds__(256) k_loss_bwd(const float* __restrict__ reco
 // parameter preparation (model.jl:139-169) and its adjoint; raw parameter vector in Flux.params order
 // =============================================================================================
 // scalars: eff = raw^2
-__global__ void k_prep_scalars(const float* __restrict__ raw, float* __restrict__ eff, int n) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) eff[t] = raw[t] * raw[t];
+// the eight scalar arrays sit in separate places of the raw parameter vector: one launch squares them all (warp w = segment w)
+struct ScalarSegs { int raw_off[8], eff_idx[8], n[8], nseg; };
+__global__ void __launch_bounds__(256) k_prep_scalars(const float* __restrict__ raw, float* __restrict__ eff, ScalarSegs sg) { PDL_SYNC();
+    const int w = threadIdx.x >> 5;
+    if (w >= sg.nseg) return;
+    for (int i = threadIdx.x & 31; i < sg.n[w]; i += 32) { const float r = raw[sg.raw_off[w] + i]; eff[sg.eff_idx[w] + i] = r * r; }
 }
-__global__ void k_prep_scalars_bwd(const float* __restrict__ raw, const float* __restrict__ deff, float* __restrict__ draw, int n) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) draw[t] += 2.f * raw[t] * deff[t];
+__global__ void __launch_bounds__(256) k_prep_scalars_bwd(const float* __restrict__ raw, const float* __restrict__ deff, float* __restrict__ draw, ScalarSegs sg) { PDL_SYNC();
+    const int w = threadIdx.x >> 5;
+    if (w >= sg.nseg) return;
+    for (int i = threadIdx.x & 31; i < sg.n[w]; i += 32) draw[sg.raw_off[w] + i] += 2.f * raw[sg.raw_off[w] + i] * deff[sg.eff_idx[w] + i];
 }
 // D: raw is Julia (32,1,M) column-major = raw[m*32 + 4j + a]; eff[(4j+a)*M + m] = (raw^2 + 1e-3) / sum_a'(...)
-__global__ void k_prep_D(const float* __restrict__ raw, float* __restrict__ eff, CscDims d) {
+__global__ void k_prep_D(const float* __restrict__ raw, float* __restrict__ eff, CscDims d) { PDL_SYNC();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= d.fl * d.M) return;
     const int m = t % d.M, j = t / d.M;
@@ -659,7 +666,7 @@ __global__ void k_prep_D(const float* __restrict__ raw, float* __restrict__ eff,
     #pragma unroll
     for (int a = 0; a < 4; ++a) eff[(4 * j + a) * d.M + m] = u[a] / s;
 }
-__global__ void k_prep_D_bwd(const float* __restrict__ raw, const float* __restrict__ eff, const float* __restrict__ deff, float* __restrict__ draw, CscDims d) {
+__global__ void k_prep_D_bwd(const float* __restrict__ raw, const float* __restrict__ eff, const float* __restrict__ deff, float* __restrict__ draw, CscDims d) { PDL_SYNC();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= d.fl * d.M) return;
     const int m = t % d.M, j = t / d.M;
@@ -673,7 +680,7 @@ __global__ void k_prep_D_bwd(const float* __restrict__ raw, const float* __restr
     }
 }
 // F: raw is Julia (h,2M,1,K) column-major = raw[(k*2M + j)*h + a]; eff[(a*2M + j)*K + k] = raw^2 / sqrt(sum_{a,j} raw^4). One block per k.
-__global__ void __launch_bounds__(256) k_prep_F(const float* __restrict__ raw, float* __restrict__ eff, float* __restrict__ nrm, CscDims d) {
+__global__ void __launch_bounds__(256) k_prep_F(const float* __restrict__ raw, float* __restrict__ eff, float* __restrict__ nrm, CscDims d) { PDL_SYNC();
     __shared__ float s_n;
     const int k = blockIdx.x;
     const int HJ = d.h * d.M2;
@@ -691,7 +698,7 @@ __global__ void __launch_bounds__(256) k_prep_F(const float* __restrict__ raw, f
     }
 }
 __global__ void __launch_bounds__(256) k_prep_F_bwd(const float* __restrict__ raw, const float* __restrict__ eff, const float* __restrict__ nrm,
-                                                    const float* __restrict__ deff, float* __restrict__ draw, CscDims d) {
+                                                    const float* __restrict__ deff, float* __restrict__ draw, CscDims d) { PDL_SYNC();
     __shared__ float s_dot;
     const int k = blockIdx.x;
     const int HJ = d.h * d.M2;
@@ -716,7 +723,7 @@ __global__ void __launch_bounds__(256) k_prep_F_bwd(const float* __restrict__ ra
 
 // unpack the selected sequences' bases from the 2-bit store: bases[n][p] for n in idx
 __global__ void __launch_bounds__(256) k_unpack_bases(const uint32_t* __restrict__ words, int64_t rowwords, const int64_t* __restrict__ idx,
-                                                      uint8_t* __restrict__ bases, CscDims d) {
+                                                      uint8_t* __restrict__ bases, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.Lb) return;
     const int p = (int)(t % d.Lb);
@@ -727,7 +734,7 @@ __global__ void __launch_bounds__(256) k_unpack_bases(const uint32_t* __restrict
 
 // AdaBelief (Flux 0.14.6 Optimise.AdaBelief, restated; see oracle/csc_oracle.py) over the trainable vector, fp32.
 __global__ void __launch_bounds__(256) k_adabelief(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mt, float* __restrict__ st,
-                                                   float eta, float b1, float b2, float eps2, float c1, float c2, int n) {
+                                                   float eta, float b1, float b2, float eps2, float c1, float c2, int n) { PDL_SYNC();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const float gr = g[t];
@@ -738,7 +745,7 @@ __global__ void __launch_bounds__(256) k_adabelief(float* __restrict__ p, const 
     p[t] -= eta * m / c1 / (sqrtf(s / c2) + eps2);
 }
 // l1 = sum |prep_syntax_filters(F)| (train.jl:47): per k sum(r^2)/sqrt(sum r^4), summed over k.  One block per k, atomics into out.
-__global__ void __launch_bounds__(256) k_l1_F(const float* __restrict__ raw, float* __restrict__ out, CscDims d) {
+__global__ void __launch_bounds__(256) k_l1_F(const float* __restrict__ raw, float* __restrict__ out, CscDims d) { PDL_SYNC();
     const int k = blockIdx.x;
     const int HJ = d.h * d.M2;
     float s2 = 0.f, s4 = 0.f;
@@ -790,7 +797,7 @@ __device__ __forceinline__ void hist_add(unsigned int* hist, bool active, unsign
 // ROWS rows; partial sums are combined by warp shuffles and a small shared-memory reduction (fixed order).
 template <int KK, int ROWS>
 __global__ void __launch_bounds__(128) k_corr2d_w(const float* __restrict__ A, const float* __restrict__ filt, int64_t filt_gs,
-                                                  float* __restrict__ out, int accumulate, CscDims d) {
+                                                  float* __restrict__ out, int accumulate, CscDims d) { PDL_SYNC();
     __shared__ float s_part[4][ROWS * KK];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tiles = (d.l + ROWS - 1) / ROWS;
@@ -839,7 +846,7 @@ __global__ void __launch_bounds__(128) k_corr2d_w(const float* __restrict__ A, c
 // T3, one block per (group, tau): 16 reduction phases x 64 filter slots, deterministic shared-memory reduction.
 __global__ void __launch_bounds__(1024) k_dgrad_b(const float* __restrict__ ca, const float* __restrict__ cb,
                                                   const float* __restrict__ sig, const uint8_t* __restrict__ bases, float sgn,
-                                                  float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) {
+                                                  float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) { PDL_SYNC();
     __shared__ float s_red[16][64];
     const int tau = blockIdx.x, g = blockIdx.y;
     const int m = threadIdx.x & 63, ph = threadIdx.x >> 6;
@@ -887,7 +894,7 @@ __device__ __forceinline__ int block_excl_scan256(int cnt, int* total) {
 // non-zero list (entry = flat index i*K+k, value) written for the sparse consumers.
 __global__ void __launch_bounds__(256) k_topq_s(const float* __restrict__ xprev, const float* __restrict__ g, const float* __restrict__ sc, int i_om,
                                                 float coef, float* __restrict__ xout, uint8_t* __restrict__ bit,
-                                                int32_t* __restrict__ lcnt, uint16_t* __restrict__ lidx, float* __restrict__ lval, CscDims d) {
+                                                int32_t* __restrict__ lcnt, uint16_t* __restrict__ lidx, float* __restrict__ lval, CscDims d) { PDL_SYNC();
     extern __shared__ float s_v[];
     __shared__ unsigned int hist[256];
     __shared__ unsigned int s_prefix, s_rank;
@@ -940,7 +947,7 @@ __global__ void __launch_bounds__(256) k_topq_s(const float* __restrict__ xprev,
 __global__ void __launch_bounds__(256) k_topq_s_bwd(const uint8_t* __restrict__ bit, const float* __restrict__ g, const float* __restrict__ sc, int i_om,
                                                     float coef, const float* __restrict__ dxout, float* __restrict__ dxprev, float* __restrict__ dg,
                                                     float* __restrict__ dsc, int om_trainable,
-                                                    int32_t* __restrict__ lcnt, uint16_t* __restrict__ lidx, float* __restrict__ lval, CscDims d) {
+                                                    int32_t* __restrict__ lcnt, uint16_t* __restrict__ lidx, float* __restrict__ lval, CscDims d) { PDL_SYNC();
     const int64_t n = blockIdx.x;
     const int E = d.l * d.K;
     const float om = coef * sc[i_om];
@@ -969,7 +976,7 @@ __global__ void __launch_bounds__(256) k_topq_s_bwd(const uint8_t* __restrict__ 
 // U1 with the x operand given as a list: one block per (n, i), threads over j.
 __global__ void __launch_bounds__(128) k_tconv_l(const float* __restrict__ x, const int32_t* __restrict__ lcnt, const uint16_t* __restrict__ lidx,
                                                  const float* __restrict__ lval, const float* __restrict__ filt, int64_t filt_gs,
-                                                 float* __restrict__ out, int accumulate, CscDims d) {
+                                                 float* __restrict__ out, int accumulate, CscDims d) { PDL_SYNC();
     __shared__ int s_i[LIST_CAP], s_k[LIST_CAP];
     __shared__ float s_v[LIST_CAP];
     const int64_t n = blockIdx.x / d.c;
@@ -1010,7 +1017,7 @@ __global__ void __launch_bounds__(128) k_tconv_l(const float* __restrict__ x, co
 // order (sequence, position) by the first warp and every thread accumulates one j over them.
 __global__ void __launch_bounds__(128) k_fgrad_l(const float* __restrict__ A, const float* __restrict__ x, const int32_t* __restrict__ lcnt,
                                                  const uint16_t* __restrict__ lidx, const float* __restrict__ lval,
-                                                 float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) {
+                                                 float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) { PDL_SYNC();
     __shared__ int s_n[256], s_i[256];
     __shared__ float s_v[256];
     __shared__ int s_cnt, s_dense;
@@ -1074,7 +1081,7 @@ __global__ void __launch_bounds__(128) k_fgrad_l(const float* __restrict__ A, co
 // A4 with the positive entries of the group compacted into shared memory (cap floats of dynamic smem); falls back to
 // re-reading global memory in every pass when there are more positives than fit.
 __global__ void __launch_bounds__(1024) k_mask_scale_s(const float* __restrict__ z, const float* __restrict__ y,
-                                                       float* __restrict__ zy, float* __restrict__ med_out, int cap, CscDims d) {
+                                                       float* __restrict__ zy, float* __restrict__ med_out, int cap, CscDims d) { PDL_SYNC();
     extern __shared__ float s_pos[];
     __shared__ unsigned int hist[256];
     __shared__ unsigned int s_prefix, s_rank, s_cnt, s_min;
@@ -1180,7 +1187,7 @@ namespace cg = cooperative_groups;
 // land in CTA 0's shared memory and are summed there in rank order.
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256) k_dgrad_c(const float* __restrict__ ca, const float* __restrict__ cb,
                                                                             const float* __restrict__ sig, const uint8_t* __restrict__ bases, float sgn,
-                                                                            float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) {
+                                                                            float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) { PDL_SYNC();
     __shared__ float s_red[4][64];
     __shared__ float s_all[CL][64];
     cg::cluster_group cluster = cg::this_cluster();
@@ -1218,15 +1225,52 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256) k_dgrad_c(cons
     }
 }
 
-// A4 on a cluster: every CTA compacts the positive entries of its slice of rows into its own shared memory; the radix
-// histograms are combined in CTA 0 through DSMEM atomics; the mask is applied by all 8 CTAs.
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(512) k_mask_scale_c(const float* __restrict__ z, const float* __restrict__ y,
-                                                                                 float* __restrict__ zy, float* __restrict__ med_out, CscDims d) {
-    extern __shared__ float s_pos[];
-    __shared__ unsigned int hist[256];
-    __shared__ unsigned int ghist[256];           // meaningful in CTA 0
-    __shared__ unsigned int ctl[8];               // CTA 0: [0] prefix, [1] rank, [2] total positives, [3] count <= v1, [4] min bits > v1
-    __shared__ unsigned int s_lcnt, s_b0, s_b1;
+// A4 on a cluster.  Every CTA keeps its slice of (z,y) in registers and its positive entries in shared memory.  The median
+// of the positives is found with one fine radix level in the common case: a 4096-bin histogram of bits 30..19 is built
+// locally, its non-empty bins are added into ALL eight CTAs' merged histograms through DSMEM, and after one cluster barrier
+// every CTA locates the median's bin redundantly.  The few hundred entries of that bin are then broadcast the same way and the
+// remaining bits are resolved inside each CTA (block-local radix passes), so no result has to be published: two full
+// cluster barriers per call instead of one or two per radix byte.  Degenerate inputs (more than MS_CAND entries in the
+// bin, e.g. many equal values) take further 12-bit cluster levels first.
+#define MS_BINS 4096
+#define MS_CAND 2048
+#define MS_THREADS 1024
+// rank search in an nb-bin histogram (nb <= 8 * blockDim.x) by the whole block; res[0]=bin, res[1]=count below, res[2]=count in
+// bin, res[3]=total; median_rank: rank = lower middle of the total.  Needs hist complete and visible (caller syncs before); ends with a __syncthreads.
+__device__ __forceinline__ void block_find_bin(const unsigned int* hist, int nb, unsigned int rank, bool median_rank, unsigned int* wsum, unsigned int* res) {
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5, nw = blockDim.x >> 5;
+    const int per = (nb + blockDim.x - 1) / blockDim.x;            // <= 8
+    unsigned int h[8], sum = 0;
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) { const int bi = t * per + i; h[i] = (i < per && bi < nb) ? hist[bi] : 0u; sum += h[i]; }
+    unsigned int inc = sum;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(FULLMASK, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    unsigned int base = 0, total = 0;
+    for (int i = 0; i < nw; ++i) { const unsigned int x = wsum[i]; if (i < w) base += x; total += x; }
+    const unsigned int exc = base + inc - sum;
+    if (median_rank) rank = total == 0 ? 0xffffffffu : ((total & 1u) ? total / 2 : total / 2 - 1);   // lower middle entry
+    if (rank >= exc && rank < exc + sum) {
+        unsigned int c0 = exc; int bi = 0;
+        #pragma unroll
+        for (; bi < 7; ++bi) { if (c0 + h[bi] > rank) break; c0 += h[bi]; }
+        res[0] = (unsigned int)(t * per + bi); res[1] = c0; res[2] = h[bi];
+    }
+    if (t == 0) res[3] = total;
+    __syncthreads();
+}
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(MS_THREADS) k_mask_scale_c(const float* __restrict__ z, const float* __restrict__ y,
+                                                                                 float* __restrict__ zy, float* __restrict__ med_out, int cap, CscDims d) { PDL_SYNC();
+    extern __shared__ float s_dyn[];
+    float* s_pos = s_dyn;                                                  // [cap] this CTA's slice: z rows, then y rows
+    unsigned int* lhist = reinterpret_cast<unsigned int*>(s_dyn + cap);   // [MS_BINS] local histogram; later scratch
+    unsigned int* mhist = lhist + MS_BINS;                                 // [MS_BINS] merged histogram (remote atomics land here)
+    float* cand = reinterpret_cast<float*>(mhist + MS_BINS);               // [MS_CAND] merged candidates (remote stores land here)
+    __shared__ unsigned int ctl[2];               // [0] candidates reserved so far, [1] min bits of the entries above the bin
+    __shared__ unsigned int s_ncand, s_lmin, s_base[CL], wsum[32], res[4];
     cg::cluster_group cluster = cg::this_cluster();
     const int r = (int)cluster.block_rank();
     const int g = blockIdx.x / CL;
@@ -1237,96 +1281,143 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(512) k_mask_scale_c
     const float* zg = z + ((int64_t)g * rows_total + row0) * d.M;
     const float* yg = y + ((int64_t)g * rows_total + row0) * d.M;
     const int EZ = (row1 - row0) * d.M;
-    unsigned int* ghist0 = cluster.map_shared_rank(ghist, 0);
-    unsigned int* ctl0 = cluster.map_shared_rank(ctl, 0);
-    if (threadIdx.x == 0) s_lcnt = 0;
-    if (r == 0) { if (threadIdx.x < 256) ghist[threadIdx.x] = 0; if (threadIdx.x < 8) ctl[threadIdx.x] = threadIdx.x == 4 ? 0x7f800000u : 0u; }
+    for (int i = threadIdx.x; i < 2 * MS_BINS; i += blockDim.x) lhist[i] = 0;      // lhist and mhist are adjacent
+    if (threadIdx.x == 0) { s_ncand = 0; s_lmin = 0x7f800000u; ctl[0] = 0; ctl[1] = 0x7f800000u; }
     __syncthreads();
-    // 1. this thread's share of the slice goes to registers with all loads in flight at once (the slice is read from
-    //    global memory exactly once: the same registers feed the compaction and the final masking)
-    float v[MS_MAXV];
-    #pragma unroll
-    for (int it = 0; it < MS_MAXV; ++it) {
-        const int e = it * (int)blockDim.x + threadIdx.x;
-        v[it] = e < EZ ? zg[e] : (e < 2 * EZ ? yg[e - EZ] : 0.f);
-    }
-    #pragma unroll
-    for (int it = 0; it < MS_MAXV; ++it) {
-        if (it * (int)blockDim.x < 2 * EZ) {                       // block-uniform
-            const bool pos = v[it] > 0.f;
-            const unsigned mk = __ballot_sync(FULLMASK, pos);
-            unsigned base = 0;
-            if (lane == 0 && mk) base = atomicAdd(&s_lcnt, __popc(mk));
-            base = __shfl_sync(FULLMASK, base, 0);
-            if (pos) s_pos[base + __popc(mk & ((1u << lane) - 1u))] = v[it];
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");         // my shared memory is ready for remote adds
+    // 1. the slice is read from global memory once into shared memory (z rows then y rows).  Plain loops, not unrolled register
+    //    arrays: this kernel runs a few times per step from a cold instruction cache, and with 6280 SASS instructions its run
+    //    time was instruction fetch (ncu: 7-9 of 16 warps stalled on no_instruction)
+    const int E2 = 2 * EZ;
+    #pragma unroll 8
+    for (int e = threadIdx.x; e < E2; e += blockDim.x) s_pos[e] = e < EZ ? zg[e] : yg[e - EZ];
+    __syncthreads();
+    const unsigned int lpos = (unsigned int)E2;
+    // 2. cluster radix levels: bits 30..19, 18..7, 6..0
+    unsigned int prefix = 0, pmask = 0, krank = 0, npos = 0, cnt = 0;
+    int shift = 19, nb = MS_BINS;
+    bool first = true, resolved = false;
+    for (int lvl = 0; lvl < 3; ++lvl) {
+        if (!first) {                                              // rare: clear both histograms, everybody before anybody adds
+            for (int i = threadIdx.x; i < 2 * MS_BINS; i += blockDim.x) lhist[i] = 0;
+            __syncthreads();
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
         }
-    }
-    __syncthreads();
-    const unsigned int lpos = s_lcnt;
-    cluster.sync();                                              // CTA 0's control block is initialised
-    if (threadIdx.x == 0 && lpos) atomicAdd(&ctl0[2], lpos);
-    cluster.sync();
-    if (threadIdx.x == 0) s_b0 = ctl0[2];
-    __syncthreads();
-    const unsigned int npos = s_b0;
-    float med = -INFINITY;
-    if (npos > 0) {                                              // cluster-uniform
-        const unsigned int k1 = (npos & 1u) ? npos / 2 : npos / 2 - 1;
-        if (r == 0 && threadIdx.x == 0) { ctl[0] = 0; ctl[1] = k1; }
-        unsigned int prefix = 0;
-        for (int shift = 24; shift >= 0; shift -= 8) {
-            if (threadIdx.x < 256) hist[threadIdx.x] = 0;
-            __syncthreads();
-            const unsigned int pmask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
-            for (unsigned e0 = 0; e0 < lpos; e0 += blockDim.x) {
-                const unsigned e = e0 + threadIdx.x;
-                const unsigned int b = e < lpos ? __float_as_uint(s_pos[e]) : 0u;
-                hist_add(hist, e < lpos && (b & pmask) == prefix, (b >> shift) & 255u);
+        for (unsigned e0 = 0; e0 < lpos; e0 += blockDim.x) {
+            const unsigned e = e0 + threadIdx.x;
+            const float f = e < lpos ? s_pos[e] : 0.f;
+            const unsigned int b = __float_as_uint(f);
+            if (f > 0.f && (b & pmask) == prefix) atomicAdd(&lhist[(b >> shift) & (unsigned)(nb - 1)], 1u);
+        }
+        __syncthreads();
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");       // every CTA's mhist is zeroed
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+            const unsigned int c = lhist[i];
+            if (c) {
+                #pragma unroll
+                for (int q = 0; q < CL; ++q) atomicAdd(cluster.map_shared_rank(&mhist[i], (r + q) & (CL - 1)), c);
             }
-            __syncthreads();
-            if (threadIdx.x < 256 && hist[threadIdx.x]) atomicAdd(&ghist0[threadIdx.x], hist[threadIdx.x]);
-            cluster.sync();
-            if (r == 0) {
-                if (threadIdx.x < 32) {
-                    int bin; unsigned int below;
-                    find_bin(ghist, ctl[1], &bin, &below);
-                    __syncwarp();
-                    if (threadIdx.x == 0) { ctl[1] -= below; ctl[0] = prefix | ((unsigned int)bin << shift); }
+        }
+        cluster.sync();                                            // merged histogram complete in every CTA
+        block_find_bin(mhist, nb, krank, first, wsum, res);
+        if (first) {
+            npos = res[3];
+            if (npos == 0) break;
+            krank = (npos & 1u) ? npos / 2 : npos / 2 - 1;
+            first = false;
+        }
+        const unsigned int bin = res[0];
+        krank -= res[1]; cnt = res[2];
+        prefix |= bin << shift; pmask |= (unsigned)(nb - 1) << shift;
+        __syncthreads();                                           // res is reused
+        if (cnt <= MS_CAND) break;
+        if (shift == 0) { resolved = true; break; }                // all 31 bits fixed: every entry of the bin is the same value
+        if (shift == 19) { shift = 7; nb = MS_BINS; } else { shift = 0; nb = 128; }
+    }
+    float med = -INFINITY;
+    if (npos > 0) {                                                // cluster-uniform
+        // 3. broadcast the bin's entries (and the smallest entry above the bin) to every CTA
+        unsigned int* lc = lhist;                                  // local candidate list (lhist is no longer needed)
+        unsigned int mn = 0x7f800000u;
+        for (unsigned e0 = 0; e0 < lpos; e0 += blockDim.x) {
+            const unsigned e = e0 + threadIdx.x;
+            const float f = e < lpos ? s_pos[e] : 0.f;
+            const unsigned int b = __float_as_uint(f);
+            const bool in = f > 0.f && (b & pmask) == prefix;
+            if (f > 0.f && (b & pmask) > prefix) mn = min(mn, b);
+            if (!resolved) {
+                const unsigned mk = __ballot_sync(FULLMASK, in);
+                unsigned base = 0;
+                if (lane == 0 && mk) base = atomicAdd(&s_ncand, __popc(mk));
+                base = __shfl_sync(FULLMASK, base, 0);
+                if (in) lc[base + __popc(mk & ((1u << lane) - 1u))] = b;
+            }
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(FULLMASK, mn, o));
+        if (lane == 0 && mn != 0x7f800000u) atomicMin(&s_lmin, mn);
+        __syncthreads();
+        const unsigned int nc = s_ncand;
+        if (threadIdx.x < CL) {
+            const int dst = threadIdx.x;
+            if (nc) s_base[dst] = atomicAdd(cluster.map_shared_rank(&ctl[0], dst), nc);
+            if (s_lmin != 0x7f800000u) atomicMin(cluster.map_shared_rank(&ctl[1], dst), s_lmin);
+        }
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < nc * CL; i += blockDim.x) {
+            const int dst = (int)(i / nc); const unsigned j = i - dst * nc;
+            cluster.map_shared_rank(cand, dst)[s_base[dst] + j] = __uint_as_float(lc[j]);
+        }
+        cluster.sync();                                            // candidates complete in every CTA; nothing remote after this
+        // 4. block-local radix passes over the remaining low bits of the candidates
+        const unsigned int kin = krank;                            // ascending rank of the median entry inside the bin
+        unsigned int v1b = prefix;
+        if (!resolved) {
+            unsigned int lowfix = 0, lowmask = 0;
+            int rem = shift;
+            while (rem > 0) {
+                const int nbits = rem < 10 ? rem : 10, sh = rem - nbits, nbin = 1 << nbits;
+                for (int i = threadIdx.x; i < nbin; i += blockDim.x) lhist[i] = 0;
+                __syncthreads();
+                for (unsigned e0 = 0; e0 < cnt; e0 += blockDim.x) {
+                    const unsigned e = e0 + threadIdx.x;
+                    const unsigned int b = e < cnt ? __float_as_uint(cand[e]) : 0u;
+                    hist_add(lhist, e < cnt && (b & lowmask) == lowfix, (b >> sh) & (unsigned)(nbin - 1));
                 }
                 __syncthreads();
-                if (threadIdx.x < 256) ghist[threadIdx.x] = 0;
+                block_find_bin(lhist, nbin, krank, false, wsum, res);
+                lowfix |= res[0] << sh; lowmask |= (unsigned)(nbin - 1) << sh; krank -= res[1];
+                __syncthreads();
+                rem = sh;
             }
-            cluster.sync();
-            if (threadIdx.x == 0) s_b0 = ctl0[0];
-            __syncthreads();
-            prefix = s_b0;
+            v1b |= lowfix;
         }
-        const float v1 = __uint_as_float(prefix);
+        const float v1 = __uint_as_float(v1b);
         if (npos & 1u) med = v1;
         else {
-            unsigned int le = 0, mn = 0x7f800000u;
-            for (unsigned e = threadIdx.x; e < lpos; e += blockDim.x) { const float v = s_pos[e]; if (v <= v1) ++le; else mn = min(mn, __float_as_uint(v)); }
+            // second middle value = entry of ascending rank kin+1: a copy of v1, else the next candidate, else the smallest entry above the bin
+            unsigned int le = 0, mn2 = 0x7f800000u;
+            if (!resolved)
+                for (unsigned e = threadIdx.x; e < cnt; e += blockDim.x) { const unsigned int b = __float_as_uint(cand[e]); if (b <= v1b) ++le; else mn2 = min(mn2, b); }
             #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { le += __shfl_xor_sync(FULLMASK, le, o); mn = min(mn, __shfl_xor_sync(FULLMASK, mn, o)); }
-            if (lane == 0) { if (le) atomicAdd(&ctl0[3], le); atomicMin(&ctl0[4], mn); }
-            cluster.sync();
-            if (threadIdx.x == 0) { s_b0 = ctl0[3]; s_b1 = ctl0[4]; }
+            for (int o = 16; o > 0; o >>= 1) { le += __shfl_xor_sync(FULLMASK, le, o); mn2 = min(mn2, __shfl_xor_sync(FULLMASK, mn2, o)); }
+            if (threadIdx.x == 0) { res[0] = 0; res[1] = 0x7f800000u; }
             __syncthreads();
-            const float v2 = (s_b0 >= k1 + 2) ? v1 : __uint_as_float(s_b1);
-            med = v1 * 0.5f + v2 * 0.5f;                         // Statistics.middle(a, b) = a/2 + b/2
+            if (lane == 0) { if (le) atomicAdd(&res[0], le); atomicMin(&res[1], mn2); }
+            __syncthreads();
+            const unsigned int le_all = resolved ? cnt : res[0];
+            const unsigned int v2b = (le_all >= kin + 2) ? v1b : (res[1] != 0x7f800000u ? res[1] : ctl[1]);
+            med = v1 * 0.5f + __uint_as_float(v2b) * 0.5f;       // Statistics.middle(a, b) = a/2 + b/2
         }
     }
     if (r == 0 && threadIdx.x == 0) med_out[g] = med;
-    // 2. apply the mask to the CTA's slice from the registers
+    // 5. apply the mask to the CTA's slice
     float* og = zy + ((int64_t)g * rows_total + row0) * d.M2;
-    #pragma unroll
-    for (int it = 0; it < MS_MAXV; ++it) {
-        const int e = it * (int)blockDim.x + threadIdx.x;
-        if (e < 2 * EZ) {
-            const int ee = e < EZ ? e : e - EZ;
-            const int np = ee / d.M, m = ee - np * d.M;
-            og[(int64_t)np * d.M2 + (e < EZ ? 0 : d.M) + m] = v[it] >= med ? d.mf * v[it] : 0.f;
-        }
+    #pragma unroll 2
+    for (int e = threadIdx.x; e < E2; e += blockDim.x) {
+        const int ee = e < EZ ? e : e - EZ;
+        const int np = ee / d.M, m = ee - np * d.M;
+        const float f = s_pos[e];
+        og[(int64_t)np * d.M2 + (e < EZ ? 0 : d.M) + m] = f >= med ? d.mf * f : 0.f;
     }
-    cluster.sync();                                              // CTA 0's shared memory must outlive every remote access
 }

@@ -31,14 +31,14 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t da, uint64
 }
 
 // operand preparation: A fp32 [rows][2M] -> bf16 [rows + pad][104]; F fp32 [h][2M][K] -> bf16 [h][TC_CH][TC_N][8]
-__global__ void __launch_bounds__(256) k_tc_prep_A(const float* __restrict__ A, __nv_bfloat16* __restrict__ Ab, int64_t rows, int M2, int ld) {
+__global__ void __launch_bounds__(256) k_tc_prep_A(const float* __restrict__ A, __nv_bfloat16* __restrict__ Ab, int64_t rows, int M2, int ld) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rows * ld) return;
     const int j = (int)(t % ld);
     const int64_t r = t / ld;
     Ab[t] = __float2bfloat16_rn(j < M2 ? A[r * M2 + j] : 0.f);
 }
-__global__ void __launch_bounds__(256) k_tc_prep_F(const float* __restrict__ F, __nv_bfloat16* __restrict__ Fb, int h, int M2, int K) {
+__global__ void __launch_bounds__(256) k_tc_prep_F(const float* __restrict__ F, __nv_bfloat16* __restrict__ Fb, int h, int M2, int K) { PDL_SYNC();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= h * TC_CH * TC_N * 8) return;
     const int e = t & 7, n = (t >> 3) % TC_N, ch = (t / (8 * TC_N)) % TC_CH, a = t / (8 * TC_N * TC_CH);
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) k_tc_prep_F(const float* __restrict__ F, 
 
 // One CTA = 128 threads; persistent over row tiles.  Thread 0 issues the MMAs; all four warps drain TMEM.
 __global__ void __launch_bounds__(128, 1) k_corr2d_tc(const __nv_bfloat16* __restrict__ Ab, const __nv_bfloat16* __restrict__ Fb,
-                                                      float* __restrict__ out, int64_t rows_total, int ntiles, int ld, CscDims d) {
+                                                      float* __restrict__ out, int64_t rows_total, int ntiles, int ld, CscDims d) { PDL_SYNC();
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     const int R = TC_M + d.h - 1;                               // staged rows per tile
     uint8_t* sA = tc_smem;                                      // [TC_CH][R][16 B]
@@ -160,7 +160,7 @@ __device__ __forceinline__ void tc_bar_wait(uint32_t bar, uint32_t parity) {
 }
 
 __global__ void __launch_bounds__(192, 1) k_corr2d_tc2(const __grid_constant__ CUtensorMap tmapA, const __nv_bfloat16* __restrict__ Fb,
-                                                       float* __restrict__ out, int64_t rows_total, int ntiles, CscDims d) {
+                                                       float* __restrict__ out, int64_t rows_total, int ntiles, CscDims d) { PDL_SYNC();
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     const int R = TC_M + d.h - 1;
     const uint32_t stage_bytes = (uint32_t)(((size_t)TC_CH * R * 16 + 1023) & ~(size_t)1023);

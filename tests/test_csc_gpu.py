@@ -179,3 +179,57 @@ def test_tensor_core_code_retrieval_within_stated_bf16_tolerance(ctx):
     rel = np.array([abs(m1[k] - m0[k]) / max(abs(m0[k]), 1e-6) for k in common])
     assert np.quantile(rel, 0.99) <= 5e-2
     ref.free(); tc.free(); seqs.free()
+
+
+def _median_mask_ref(z, y, mf):
+    """create_ZY_mask + cat_ZY, model.jl:194-210, per group in numpy (Statistics.median: middle(a,b) = a/2 + b/2)."""
+    G = z.shape[0]
+    zy = np.concatenate([z, y], axis=2)
+    out = np.zeros_like(zy); med = np.zeros(G, np.float32)
+    for g in range(G):
+        pos = np.sort(zy[g][zy[g] > 0])
+        if len(pos) == 0:
+            med[g] = -np.inf
+        elif len(pos) % 2:
+            med[g] = pos[len(pos) // 2]
+        else:
+            med[g] = np.float32(pos[len(pos) // 2 - 1] * np.float32(0.5) + pos[len(pos) // 2] * np.float32(0.5))
+        out[g] = np.where(zy[g] >= med[g], np.float32(mf) * zy[g], np.float32(0))
+    return out, med
+
+
+@pytest.mark.parametrize("G", [1, 3, 40])          # 1,3: one 8-CTA cluster per group; 40: one CTA per group
+def test_median_mask_order_statistic_corner_cases(ctx, G):
+    hp = mdl.Hyperparam()
+    Lb = 100
+    m = mb._lib.CscModel(ctx, hp, Lb, n_groups=G, forward_only=True)
+    rows, M = hp.batch_size * (Lb - hp.filter_len + 1), hp.M
+    rng = np.random.default_rng(G)
+    n = rows * M
+
+    def case(kind):
+        if kind == "relu_normal":                        # the usual shape: about half the entries positive
+            v = rng.standard_normal((2, G, n)).astype(np.float32)
+        elif kind == "few_distinct":                     # thousands of copies of 5 values: every radix level is exercised
+            v = rng.choice(np.array([-1, 0, 0.25, 0.5, 0.5000001, 3, 7], np.float32), size=(2, G, n))
+        elif kind == "all_equal":
+            v = np.full((2, G, n), 1.25, np.float32)
+        elif kind == "narrow":                           # > MS_CAND entries share the top 12 bits, differ in the low mantissa bits
+            v = (1.0 + rng.integers(0, 4000, size=(2, G, n)) * 2.0 ** -23).astype(np.float32)
+        elif kind == "odd_count":
+            v = -np.ones((2, G, n), np.float32); v[0, :, :7] = np.arange(1, 8, dtype=np.float32)[None]
+        elif kind == "even_two_bins":                    # the two middle entries fall into different histogram bins
+            v = -np.ones((2, G, n), np.float32); v[0, :, :4] = np.array([0.1, 0.2, 900.0, 1000.0], np.float32)[None]
+        elif kind == "no_positive":
+            v = -np.abs(rng.standard_normal((2, G, n))).astype(np.float32)
+        elif kind == "tiny_and_huge":
+            v = np.exp(rng.uniform(-60, 60, size=(2, G, n))).astype(np.float32) * rng.choice(np.array([-1, 1], np.float32), size=(2, G, n))
+        return v[0].reshape(G, rows, M), v[1].reshape(G, rows, M)
+
+    for kind in ("relu_normal", "few_distinct", "all_equal", "narrow", "odd_count", "even_two_bins", "no_positive", "tiny_and_huge"):
+        z, y = case(kind)
+        zy, med = m.median_mask(z, y)
+        rzy, rmed = _median_mask_ref(z, y, hp.magnifying_factor)
+        assert np.array_equal(med, rmed), (kind, med[:4], rmed[:4])
+        assert np.array_equal(zy, rzy), kind
+    m.free()
