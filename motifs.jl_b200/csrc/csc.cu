@@ -73,6 +73,7 @@ struct mb200_csc {
     bool tensor = false;                                 // forward-only handle using the tcgen05 BF16 path for corr2d
     __nv_bfloat16 *tc_A = nullptr, *tc_F = nullptr; int tc_tiles = 0, tc_ld = 104; size_t tc_smem = 0, tc_smem2 = 0;
     CUtensorMap tc_map; bool tc_pipelined = false;
+    bool tc_grouped = false; size_t tc_smem3 = 0; int64_t tc_arows = 0;      // tap-grouped kernel (k_corr2d_tc3)
     cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr; bool graph_ok = false;
     const uint32_t* graph_words = nullptr; int64_t graph_rowwords = 0;
 };
@@ -148,7 +149,8 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
                          lk(k_prep_scalars, 1, 256, 0, q, S->p_raw, S->data + sc.off, S->segs);
                          lk(k_prep_D, nblk(d.fl * d.M, 128), 128, 0, q, S->p_raw + S->off_D, S->data + De.off, d);
                          lk(k_prep_F, d.K, 256, 0, q, S->p_raw + S->off_F, S->data + Fe.off, S->data + Fn0.off, d);
-                         if (S->tensor) lk(k_tc_prep_F, nblk((int64_t)d.h * TC_CH * TC_N * 8, 256), 256, 0, q, S->data + Fe.off, S->tc_F, d.h, d.M2, d.K);
+                         if (S->tensor && S->tc_grouped) lk(k_tc_prep_F3, nblk((int64_t)d.h * TC_CH * d.K * 8, 256), 256, 0, q, S->data + Fe.off, S->tc_F, d.h, d.M2, d.K);
+                         else if (S->tensor) lk(k_tc_prep_F, nblk((int64_t)d.h * TC_CH * TC_N * 8, 256), 256, 0, q, S->data + Fe.off, S->tc_F, d.h, d.M2, d.K);
                      },
                      [=](cudaStream_t q) {
                          ScalarSegs tr = S->segs; tr.nseg = 7;      // the warm-up scalars (segment 7) are not trained
@@ -171,6 +173,11 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
     auto run_corr2d = [=](const float* A, const float* filt, int64_t gs, float* out, int acc, cudaStream_t q) {
         if (S->tensor && gs == 0 && !acc) {
             const int64_t rows = (int64_t)d.NS * d.c;
+            if (S->tc_grouped) {
+                lk(k_tc_prep_A3, nblk(rows * (TC_CH - 1), 256), 256, 0, q, A, S->tc_A, rows, S->tc_arows, d.M2);
+                lk(k_corr2d_tc3<24, 3>, std::min(S->tc_tiles, S->ctx->sm_count), TC3_THREADS, S->tc_smem3, q, S->tc_A, S->tc_arows, S->tc_F, out, rows, S->tc_tiles, d);
+                return;
+            }
             lk(k_tc_prep_A, nblk(rows * S->tc_ld, 256), 256, 0, q, A, S->tc_A, rows, d.M2, S->tc_ld);
             if (S->tc_pipelined) lk(k_corr2d_tc2, std::min(S->tc_tiles, S->ctx->sm_count), 192, S->tc_smem2, q, S->tc_map, S->tc_F, out, rows, S->tc_tiles, d);
             else lk(k_corr2d_tc, std::min(S->tc_tiles, S->ctx->sm_count), 128, S->tc_smem, q, S->tc_A, S->tc_F, out, rows, S->tc_tiles, S->tc_ld, d);
@@ -419,18 +426,26 @@ static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
     MB_CUDA(ctx, cudaFuncSetAttribute(k_topq_s, cudaFuncAttributeMaxDynamicSharedMemorySize, s->d.l * s->d.K * 4));
     if (s->tensor) {
         const int64_t rows = (int64_t)s->d.NS * s->d.c;
-        s->tc_tiles = (int)((rows + TC_M - 1) / TC_M);
-        const size_t arows = (size_t)s->tc_tiles * TC_M + s->d.h + 8;
+        const char* np = getenv("MB200_TC_NO_PIPELINE");
+        const char* ng = getenv("MB200_TC_NO_GROUPING");
+        const bool pipelined = !(np && np[0] == '1');
+        s->tc_grouped = pipelined && !(ng && ng[0] == '1') && s->d.h == 3 * TC_J && s->d.K == 24;      // the instantiated shape <K = 24, h/4 = 3>
+        const int step = s->tc_grouped ? TC_VALID : TC_M;                 // output rows per tile
+        const int R = s->tc_grouped ? TC_M + s->d.h - TC_J : TC_M + s->d.h - 1;
+        s->tc_tiles = (int)((rows + step - 1) / step);
+        const size_t arows = (size_t)rows + 2 * TC_M + s->d.h + 8;        // every variant's last tile stays inside the zero padding
+        s->tc_arows = (int64_t)arows;
         MB_CUDA(ctx, cudaMalloc(&s->tc_A, arows * s->tc_ld * 2));
         MB_CUDA(ctx, cudaMemset(s->tc_A, 0, arows * s->tc_ld * 2));
         MB_CUDA(ctx, cudaMalloc(&s->tc_F, (size_t)s->d.h * TC_CH * TC_N * 8 * 2));
-        const int R = TC_M + s->d.h - 1;
         s->tc_smem = (((size_t)TC_CH * R * 16 + 127) & ~(size_t)127) + (size_t)s->d.h * TC_CH * TC_N * 16;
         MB_CUDA(ctx, cudaFuncSetAttribute(k_corr2d_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tc_smem));
         s->tc_smem2 = 2 * ((((size_t)TC_CH * R * 16) + 1023) & ~(size_t)1023) + (size_t)s->d.h * TC_CH * TC_N * 16;
         MB_CUDA(ctx, cudaFuncSetAttribute(k_corr2d_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tc_smem2));
-        const char* np = getenv("MB200_TC_NO_PIPELINE");
-        s->tc_pipelined = !(np && np[0] == '1') && tc_make_tmap(&s->tc_map, s->tc_A, arows, s->tc_ld, R) == 0;
+        s->tc_smem3 = TC3_STAGES * ((((size_t)TC_CH * R * 16) + 1023) & ~(size_t)1023) + (size_t)s->d.h * TC_CH * s->d.K * 16 + 4 * 3 * (TC_J - 1) * (TC_J - 1) * 24 * 4;
+        MB_CUDA(ctx, cudaFuncSetAttribute(k_corr2d_tc3<24, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tc_smem3));
+        s->tc_pipelined = pipelined && tc_make_tmap(&s->tc_map, s->tc_A, arows, s->tc_ld, R) == 0;
+        if (!s->tc_pipelined) { s->tc_grouped = false; s->tc_tiles = (int)((rows + TC_M - 1) / TC_M); }
     }
     MB_CUDA(ctx, cudaStreamCreateWithFlags(&s->aux, cudaStreamNonBlocking));
     MB_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
