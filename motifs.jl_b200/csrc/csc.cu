@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "csc_kernels.cuh"
 #include "tc_corr2d.cuh"
+#include "csc_batched.cuh"
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
@@ -73,7 +74,8 @@ struct mb200_csc {
     bool tensor = false;                                 // forward-only handle using the tcgen05 BF16 path for corr2d
     __nv_bfloat16 *tc_A = nullptr, *tc_F = nullptr; int tc_tiles = 0, tc_ld = 104; size_t tc_smem = 0, tc_smem2 = 0;
     CUtensorMap tc_map; bool tc_pipelined = false;
-    bool tc_grouped = false; size_t tc_smem3 = 0; int64_t tc_arows = 0;      // tap-grouped kernel (k_corr2d_tc3)
+    bool tc_grouped = false; size_t tc_smem3 = 0; int64_t tc_arows = 0;
+    bool batched = false; float* Ft_scratch = nullptr;      // one-CTA-per-sequence kernels (csc_batched.cuh) for many-group shapes      // tap-grouped kernel (k_corr2d_tc3)
     cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr; bool graph_ok = false;
     const uint32_t* graph_words = nullptr; int64_t graph_rowwords = 0;
 };
@@ -186,12 +188,27 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         if (fastK) lk(k_corr2d_w<24, 4>, d.NS * ((d.l + 3) / 4), 128, 0, q, A, filt, gs, out, acc, d);
         else lk(k_corr2d, nblk(nX, 128), 128, 0, q, A, filt, gs, out, acc, d);
     };
+    // D-layer forms: per-output kernels for a single reference batch, one CTA per sequence when the launch holds many groups
+    const bool batched = S->batched;
+    const size_t smem_rb = recon_b_smem(d), smem_cb = corr_sig_b_smem(d), smem_tb = (size_t)d.c * d.M2 * 4;
+    auto run_recon = [=](const float* ca, const float* cb, const float* filt, int64_t gs, float* out, int acc, cudaStream_t q) {
+        if (batched) lk(k_recon_b, d.NS, RB_THREADS, smem_rb, q, ca, cb, filt, gs, out, acc, d);
+        else lk(k_recon, nblk(nS * 32, 256), 256, 0, q, ca, cb, filt, gs, out, acc, d);
+    };
+    auto run_corr_sig = [=](const float* sig, float sgn, const float* filt, int64_t gs, float* oa, float* ob, int acc, cudaStream_t q) {
+        if (batched) lk(k_corr_sig_b, d.NS, RB_THREADS, smem_cb, q, sig, S->bases, sgn, filt, gs, oa, ob, acc, d);
+        else lk(k_corr_sig, nblk(nZ, 256), 256, 0, q, sig, S->bases, sgn, filt, gs, oa, ob, acc, d);
+    };
     auto run_dgrad = [=](const float* ca, const float* cb, const float* sig, float sgn, float* of, int64_t ogs, int acc, cudaStream_t q) {
         if (fastM) lk(k_dgrad_c, dim3(d.f_len * CL, d.G), 256, 0, q, ca, cb, sig, S->bases, sgn, of, ogs, acc, d);
         else lk(k_dgrad, dim3(nblk(nD, 128), d.G), 128, 0, q, ca, cb, sig, S->bases, sgn, of, ogs, acc, d);
     };
     auto run_tconv = [=](const float* x, int L, const float* filt, int64_t gs, float* out, int acc, cudaStream_t q) {
-        lk(k_tconv_l, d.NS * d.c, 128, 0, q, x, LCNT(L), LIDX(L), LVAL(L), filt, gs, out, acc, d);
+        if (batched) {
+            const int Gf = gs ? d.G : 1;
+            lk(k_transpose_F, nblk((int64_t)Gf * nF, 256), 256, 0, q, filt, gs, S->Ft_scratch, Gf, d);
+            lk(k_tconv_b, d.NS, RB_THREADS, smem_tb, q, x, LCNT(L), LIDX(L), LVAL(L), (const float*)S->Ft_scratch, gs ? nF : (int64_t)0, out, acc, d);
+        } else lk(k_tconv_l, d.NS * d.c, 128, 0, q, x, LCNT(L), LIDX(L), LVAL(L), filt, gs, out, acc, d);
     };
     auto run_fgrad = [=](const float* A, const float* x, int L, float* of, int64_t ogs, int acc, cudaStream_t q) {
         lk(k_fgrad_l, dim3(d.K, d.h, d.G), 128, 0, q, A, x, LCNT(L), LIDX(L), LVAL(L), of, ogs, acc, d);
@@ -206,18 +223,18 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
     };
     std::map<size_t, int> xlist;                 // buffer offset of an x tensor -> list of its data
     auto op_recon = [&](Buf ca, Buf cb, Buf filt, int64_t gs, Buf out, const char* nm) {
-        T.push_back({[=](cudaStream_t q) { lk(k_recon, nblk(nS * 32, 256), 256, 0, q, S->data + ca.off, S->data + cb.off, S->data + filt.off, gs, S->data + out.off, 0, d); },
+        T.push_back({[=](cudaStream_t q) { run_recon(S->data + ca.off, S->data + cb.off, S->data + filt.off, gs, S->data + out.off, 0, q); },
                      [=](cudaStream_t q) {
                          // d ca, d cb: corr_sig form with signal = d out ; d filt: dgrad form with signal = d out
-                         par2(q, [=](cudaStream_t r) { lk(k_corr_sig, nblk(nZ, 256), 256, 0, r, S->grad + out.off, S->bases, 0.f, S->data + filt.off, gs, S->grad + ca.off, S->grad + cb.off, 1, d); },
+                         par2(q, [=](cudaStream_t r) { run_corr_sig(S->grad + out.off, 0.f, S->data + filt.off, gs, S->grad + ca.off, S->grad + cb.off, 1, r); },
                                  [=](cudaStream_t r) { run_dgrad(S->data + ca.off, S->data + cb.off, S->grad + out.off, 0.f, S->grad + filt.off, gs, 1, r); });
                      },
                      nm});
     };
     auto op_corr_sig = [&](Buf sig, float sgn, Buf filt, int64_t gs, Buf oa, Buf ob, const char* nm) {
-        T.push_back({[=](cudaStream_t q) { lk(k_corr_sig, nblk(nZ, 256), 256, 0, q, S->data + sig.off, S->bases, sgn, S->data + filt.off, gs, S->data + oa.off, S->data + ob.off, 0, d); },
+        T.push_back({[=](cudaStream_t q) { run_corr_sig(S->data + sig.off, sgn, S->data + filt.off, gs, S->data + oa.off, S->data + ob.off, 0, q); },
                      [=](cudaStream_t q) {
-                         par2(q, [=](cudaStream_t r) { lk(k_recon, nblk(nS * 32, 256), 256, 0, r, S->grad + oa.off, S->grad + ob.off, S->data + filt.off, gs, S->grad + sig.off, 1, d); },
+                         par2(q, [=](cudaStream_t r) { run_recon(S->grad + oa.off, S->grad + ob.off, S->data + filt.off, gs, S->grad + sig.off, 1, r); },
                                  [=](cudaStream_t r) { run_dgrad(S->grad + oa.off, S->grad + ob.off, S->data + sig.off, sgn, S->grad + filt.off, gs, 1, r); });
                      },
                      nm});
@@ -226,8 +243,8 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         T.push_back({[=](cudaStream_t q) { run_dgrad(S->data + ca.off, S->data + cb.off, S->data + sig.off, sgn, S->data + outG.off, nD, 0, q); },
                      [=](cudaStream_t q) {
                          // d ca, d cb: corr_sig with filter = dG (per group) ; d sig: recon with filter = dG
-                         par2(q, [=](cudaStream_t r) { lk(k_corr_sig, nblk(nZ, 256), 256, 0, r, S->data + sig.off, S->bases, sgn, S->grad + outG.off, nD, S->grad + ca.off, S->grad + cb.off, 1, d); },
-                                 [=](cudaStream_t r) { lk(k_recon, nblk(nS * 32, 256), 256, 0, r, S->data + ca.off, S->data + cb.off, S->grad + outG.off, nD, S->grad + sig.off, 1, d); });
+                         par2(q, [=](cudaStream_t r) { run_corr_sig(S->data + sig.off, sgn, S->grad + outG.off, nD, S->grad + ca.off, S->grad + cb.off, 1, r); },
+                                 [=](cudaStream_t r) { run_recon(S->data + ca.off, S->data + cb.off, S->grad + outG.off, nD, S->grad + sig.off, 1, r); });
                      },
                      nm});
     };
@@ -268,6 +285,7 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         const int ms_cap1 = (int)std::min<int64_t>(2 * (int64_t)d.B * d.c * d.M, 49152);
         T.push_back({[=](cudaStream_t q) {
                          if (ms_cluster) lk(k_mask_scale_c, d.G * CL, MS_THREADS, ((size_t)mask_cap + 2 * MS_BINS + MS_CAND) * 4, q, S->data + z.off, S->data + y.off, S->data + zy.off, S->data + med.off, mask_cap, d);
+                         else if (S->batched) lk(k_mask_scale_g, d.G, MG_THREADS, 0, q, S->data + z.off, S->data + y.off, S->data + zy.off, S->data + med.off, d);
                          else lk(k_mask_scale_s, d.G, 1024, (size_t)ms_cap1 * 4, q, S->data + z.off, S->data + y.off, S->data + zy.off, S->data + med.off, ms_cap1, d);
                      },
                      [=](cudaStream_t q) { lk(k_mask_scale_bwd, nblk(nZY, 256), 256, 0, q, S->data + z.off, S->data + y.off, S->data + med.off, S->grad + zy.off, S->grad + z.off, S->grad + y.off, d); },
@@ -416,6 +434,12 @@ static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
     MB_CUDA(ctx, cudaMalloc(&s->data, s->arena * 4));
     MB_CUDA(ctx, cudaMemset(s->data, 0, s->arena * 4));
     if (!s->xyz_only) { MB_CUDA(ctx, cudaMalloc(&s->grad, s->arena * 4)); MB_CUDA(ctx, cudaMemset(s->grad, 0, s->arena * 4)); }
+    if (s->batched) {
+        MB_CUDA(ctx, cudaMalloc(&s->Ft_scratch, (size_t)s->d.G * s->d.h * s->d.M2 * s->d.K * 4));
+        MB_CUDA(ctx, cudaFuncSetAttribute(k_recon_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)recon_b_smem(s->d)));
+        MB_CUDA(ctx, cudaFuncSetAttribute(k_corr_sig_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_sig_b_smem(s->d)));
+        MB_CUDA(ctx, cudaFuncSetAttribute(k_tconv_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)s->d.c * s->d.M2 * 4)));
+    }
     MB_CUDA(ctx, cudaMalloc(&s->bits, std::max<size_t>(s->bits_n, 16)));
     MB_CUDA(ctx, cudaMalloc(&s->lcnt, (size_t)std::max(1, s->n_lists) * s->d.NS * 4));
     MB_CUDA(ctx, cudaMalloc(&s->lidx, (size_t)std::max(1, s->n_lists) * s->d.NS * LIST_CAP * 2));
@@ -491,6 +515,11 @@ extern "C" int32_t mb200_csc_create(mb200_ctx* ctx, const mb200_hparams* hp, int
     s->off_lam = o; o += d.npx; s->off_kaps = o; o += d.npd; s->off_eta = o; o += d.npx; s->off_om = o; o += d.npx; s->off_kap = o; o += d.npd;
     s->off_D = o; o += (int64_t)d.f_len * d.M; s->off_F = o; o += (int64_t)d.h * d.M2 * d.K; s->off_rho = o; o += d.npx; s->off_mu = o; o += d.npd;
     s->n_train = o; s->off_warm = o; o += 3; s->n_total = o;
+    {   // one CTA per sequence pays off once the launch holds enough sequences to fill the machine (MB200_BATCHED_MIN_G overrides)
+        const char* e = getenv("MB200_BATCHED_MIN_G");
+        const int min_g = e ? atoi(e) : 8;       // measured break-even on B200 (Lb = 100): 8 groups = 48 CTAs
+        s->batched = d.G >= min_g && d.f_len == 32 && recon_b_smem(d) <= 200 * 1024 && (size_t)d.c * d.M2 * 4 <= 200 * 1024;
+    }
     build_tape(s, s->xyz_only);
     int rc = csc_alloc(ctx, s);
     if (rc) { delete s; return rc; }
@@ -505,7 +534,7 @@ extern "C" int32_t mb200_csc_destroy(mb200_ctx* ctx, mb200_csc* s) {
     if (s->graph) cudaGraphDestroy(s->graph);
     if (s->aux) cudaStreamDestroy(s->aux);
     if (s->ev_fork) { cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_join); cudaEventDestroy(s->ev_fork2); cudaEventDestroy(s->ev_join2); }
-    cudaFree(s->p_raw); cudaFree(s->g_raw); cudaFree(s->mt); cudaFree(s->st); cudaFree(s->data); cudaFree(s->grad); cudaFree(s->bits); cudaFree(s->lcnt); cudaFree(s->lidx); cudaFree(s->lval); cudaFree(s->tc_A); cudaFree(s->tc_F);
+    cudaFree(s->p_raw); cudaFree(s->g_raw); cudaFree(s->mt); cudaFree(s->st); cudaFree(s->data); cudaFree(s->grad); cudaFree(s->bits); cudaFree(s->lcnt); cudaFree(s->lidx); cudaFree(s->lval); cudaFree(s->tc_A); cudaFree(s->tc_F); cudaFree(s->Ft_scratch);
     cudaFree(s->bases); cudaFree(s->idx_dev); cudaFreeHost(s->idx_pinned); cudaFree(s->idx_identity_dev); cudaFree(s->batch_words); cudaFreeHost(s->batch_pinned); cudaFreeHost(s->host_out);
     delete s;
     return MB200_OK;
@@ -721,6 +750,7 @@ extern "C" int32_t mb200_csc_median_mask(mb200_ctx* ctx, mb200_csc* s, const flo
     const bool ms_cluster = s->mask_cap <= MS_MAXV * 512 && d.G < 32;
     const int ms_cap1 = (int)std::min<int64_t>(2 * (int64_t)d.B * d.c * d.M, 49152);
     if (ms_cluster) lk(k_mask_scale_c, d.G * CL, MS_THREADS, ((size_t)s->mask_cap + 2 * MS_BINS + MS_CAND) * 4, ctx->stream, dz, dy, dzy, dmed, s->mask_cap, d);
+    else if (s->batched) lk(k_mask_scale_g, d.G, MG_THREADS, 0, ctx->stream, dz, dy, dzy, dmed, d);
     else lk(k_mask_scale_s, d.G, 1024, (size_t)ms_cap1 * 4, ctx->stream, dz, dy, dzy, dmed, ms_cap1, d);
     cudaMemcpyAsync(zy_out, dzy, 2 * nZ * 4, cudaMemcpyDeviceToHost, ctx->stream);
     cudaMemcpyAsync(med_out, dmed, (size_t)d.G * 4, cudaMemcpyDeviceToHost, ctx->stream);

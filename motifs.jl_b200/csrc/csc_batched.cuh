@@ -1,0 +1,336 @@
+// Batched-shape variants of the three D/F-layer forms that dominate code retrieval and many-group steps.
+//
+// The kernels in csc_kernels.cuh are laid out for ONE reference batch (6 sequences): one warp or one block per output
+// element, so that a 6-sequence step exposes enough parallelism to hide latency.  With hundreds of groups per launch that
+// layout re-reads every operand row from L1/L2 once per output that touches it (k_recon: each (n,p) row of Z,Y 32 times;
+// ncu, 500 groups: k_recon 1.36 ms, k_tconv_l 1.03 ms, k_corr_sig 0.55 ms of a 3.4 ms pass).  Here one CTA owns one sequence,
+// stages its operands in shared memory once and works on register tiles:
+//   k_recon_b     T1  U[p][k] = sum_m a[p][m] F[k][m] + b[p][m] F[f_len-1-k][m]  (a [c x 2M].[2M x 32] product, 4x4 register
+//                     tiles), then the overlap-add  out[t] = sum_{p} U[p][t-4p]                       (model.jl:238-239,276-277,313-314)
+//   k_corr_sig_b  T2  oa[p][m] = sum_k r[4p+k] F[k][m], ob[p][m] = sum_k r[4p+k] F[f_len-1-k][m]      (model.jl:240-241)
+//   k_tconv_b     U1  fx[i+a][j] += x[i][k] F[a][j][k] over the sequence's non-zero codes, scattered into a shared-memory tile
+//                     in list order (the same order of additions per output as k_tconv_l)              (model.jl:229,263,294,316,370)
+// Same operands, same results up to fp32 summation order (tests compare both layouts).
+#pragma once
+#include "csc_kernels.cuh"
+
+#define RB_THREADS 256
+
+// dynamic shared memory: a,b [cpad][M] | FT, FrT [M][32] | U [cpad][33]
+__global__ void __launch_bounds__(RB_THREADS) k_recon_b(const float* __restrict__ ca, const float* __restrict__ cb,
+                                                        const float* __restrict__ filt, int64_t filt_gs,
+                                                        float* __restrict__ out, int accumulate, CscDims d) { PDL_SYNC();
+    extern __shared__ __align__(16) float rb_smem[];
+    const int cpad = (d.c + 3) & ~3;
+    float* sa = rb_smem;                          // [cpad][M]
+    float* sb = sa + cpad * d.M;
+    float* sFT = sb + cpad * d.M;                 // [M][32]: sFT[m][k] = F[k][m]
+    float* sFr = sFT + d.M * 32;                  // [M][32]: sFr[m][k] = F[f_len-1-k][m]
+    float* sU = sFr + d.M * 32;                   // [cpad][33]
+    const int64_t n = blockIdx.x;
+    const float* F = filt + (n / d.B) * filt_gs;
+    const float* za = ca + n * d.c * d.M;
+    const float* zb = cb + n * d.c * d.M;
+    const int E = d.c * d.M;
+    for (int e = threadIdx.x; e < cpad * d.M; e += RB_THREADS) { sa[e] = e < E ? za[e] : 0.f; sb[e] = e < E ? zb[e] : 0.f; }
+    for (int e = threadIdx.x; e < d.f_len * d.M; e += RB_THREADS) {
+        const int k = e / d.M, m = e - k * d.M;
+        const float f = F[e];
+        sFT[m * 32 + k] = f; sFr[m * 32 + (d.f_len - 1 - k)] = f;
+    }
+    __syncthreads();
+    // register tiles: 4 positions x 4 taps; a warp holds 4 position tiles x 8 tap tiles, so every operand load is one wavefront
+    const int ntile = (cpad >> 2) * 8;
+    for (int tile = threadIdx.x; tile < ntile; tile += RB_THREADS) {
+        const int pt = tile >> 3, kt = tile & 7;
+        const float* a0 = sa + (pt * 4) * d.M;
+        const float* b0 = sb + (pt * 4) * d.M;
+        float u[4][4];
+        #pragma unroll
+        for (int i = 0; i < 4; ++i)
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) u[i][j] = 0.f;
+        #pragma unroll 2
+        for (int m = 0; m < d.M; ++m) {
+            const float4 f = *reinterpret_cast<const float4*>(sFT + m * 32 + kt * 4);
+            const float4 g = *reinterpret_cast<const float4*>(sFr + m * 32 + kt * 4);
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float av = a0[i * d.M + m], bv = b0[i * d.M + m];
+                u[i][0] += av * f.x + bv * g.x; u[i][1] += av * f.y + bv * g.y;
+                u[i][2] += av * f.z + bv * g.z; u[i][3] += av * f.w + bv * g.w;
+            }
+        }
+        #pragma unroll
+        for (int i = 0; i < 4; ++i)
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) sU[(pt * 4 + i) * 33 + kt * 4 + j] = u[i][j];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < d.L4; t += RB_THREADS) {
+        const int p_hi = min(d.c - 1, t >> 2);
+        const int p_lo = max(0, (t - d.f_len + 4) >> 2);
+        float acc = 0.f;
+        for (int p = p_lo; p <= p_hi; ++p) acc += sU[p * 33 + (t - 4 * p)];
+        float* o = out + n * d.L4 + t;
+        if (accumulate) *o += acc; else *o = acc;
+    }
+}
+static inline size_t recon_b_smem(const CscDims& d) {
+    const size_t cpad = (size_t)((d.c + 3) & ~3);
+    return (2 * cpad * d.M + 2 * (size_t)d.M * 32 + cpad * 33) * 4;
+}
+
+// dynamic shared memory: r [L4 + f_len] | F [f_len][Mp], Mp = M rounded up to a multiple of 4
+__global__ void __launch_bounds__(RB_THREADS) k_corr_sig_b(const float* __restrict__ sig, const uint8_t* __restrict__ bases, float sgn,
+                                                           const float* __restrict__ filt, int64_t filt_gs,
+                                                           float* __restrict__ oa, float* __restrict__ ob, int accumulate, CscDims d) { PDL_SYNC();
+    extern __shared__ __align__(16) float rb_smem[];
+    const int Mp = (d.M + 3) & ~3;
+    const int rlen = (d.L4 + d.f_len + 3) & ~3;
+    float* sr = rb_smem;                          // [rlen] signal with the one-hot folded in, zero tail
+    float* sF = sr + rlen;                        // [f_len][Mp]
+    const int64_t n = blockIdx.x;
+    const float* F = filt + (n / d.B) * filt_gs;
+    for (int t = threadIdx.x; t < rlen; t += RB_THREADS) sr[t] = t < d.L4 ? sig_at(sig, bases, sgn, n, t, d) : 0.f;
+    for (int e = threadIdx.x; e < d.f_len * Mp; e += RB_THREADS) {
+        const int k = e / Mp, m = e - k * Mp;
+        sF[e] = m < d.M ? F[k * d.M + m] : 0.f;
+    }
+    __syncthreads();
+    const int cpad = (d.c + 3) & ~3, mt_n = Mp >> 2;
+    const int ntile = (cpad >> 2) * mt_n;
+    for (int tile = threadIdx.x; tile < ntile; tile += RB_THREADS) {
+        const int pt = tile / mt_n, mt = tile - pt * mt_n;
+        float a[4][4], b[4][4];
+        #pragma unroll
+        for (int i = 0; i < 4; ++i)
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) { a[i][j] = 0.f; b[i][j] = 0.f; }
+        const float* r0 = sr + 16 * pt;            // position p = 4pt+i reads r[4p + k] = r0[4i + k]
+        #pragma unroll 4
+        for (int k = 0; k < d.f_len; ++k) {
+            const float4 f = *reinterpret_cast<const float4*>(sF + k * Mp + mt * 4);
+            const float4 g = *reinterpret_cast<const float4*>(sF + (d.f_len - 1 - k) * Mp + mt * 4);
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float rv = r0[4 * i + k];
+                a[i][0] += rv * f.x; a[i][1] += rv * f.y; a[i][2] += rv * f.z; a[i][3] += rv * f.w;
+                b[i][0] += rv * g.x; b[i][1] += rv * g.y; b[i][2] += rv * g.z; b[i][3] += rv * g.w;
+            }
+        }
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int p = pt * 4 + i;
+            if (p >= d.c) continue;
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = mt * 4 + j;
+                if (m >= d.M) continue;
+                const int64_t o = (n * d.c + p) * d.M + m;
+                if (accumulate) { oa[o] += a[i][j]; ob[o] += b[i][j]; } else { oa[o] = a[i][j]; ob[o] = b[i][j]; }
+            }
+        }
+    }
+}
+static inline size_t corr_sig_b_smem(const CscDims& d) {
+    const size_t Mp = (size_t)((d.M + 3) & ~3), rlen = (size_t)((d.L4 + d.f_len + 3) & ~3);
+    return (rlen + (size_t)d.f_len * Mp) * 4;
+}
+
+// F [h][2M][K] -> Ft [K][h*2M] (per group when gs != 0): the tap rows of one syntax filter become contiguous
+__global__ void __launch_bounds__(256) k_transpose_F(const float* __restrict__ F, int64_t gs, float* __restrict__ Ft, int G, CscDims d) { PDL_SYNC();
+    const int hj = d.h * d.M2;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)G * hj * d.K) return;
+    const int k = (int)(t % d.K);
+    const int64_t r = t / d.K;
+    const int e = (int)(r % hj);
+    const int64_t g = r / hj;
+    Ft[(g * d.K + k) * hj + e] = F[g * gs + (int64_t)e * d.K + k];
+}
+
+// dynamic shared memory: tile [c][2M].  Ft as written by k_transpose_F (ft_gs = K*h*2M per group, or 0 when shared).
+__global__ void __launch_bounds__(RB_THREADS) k_tconv_b(const float* __restrict__ x, const int32_t* __restrict__ lcnt, const uint16_t* __restrict__ lidx,
+                                                        const float* __restrict__ lval, const float* __restrict__ Ft, int64_t ft_gs,
+                                                        float* __restrict__ out, int accumulate, CscDims d) { PDL_SYNC();
+    extern __shared__ __align__(16) float rb_smem[];
+    float* tile = rb_smem;
+    __shared__ int s_i[LIST_CAP], s_k[LIST_CAP];
+    __shared__ float s_v[LIST_CAP];
+    const int64_t n = blockIdx.x;
+    const float* FT = Ft + (n / d.B) * ft_gs;
+    const int hj = d.h * d.M2, E = d.c * d.M2;
+    const int cnt = lcnt[n];
+    for (int e = threadIdx.x; e < E; e += RB_THREADS) tile[e] = 0.f;
+    if (cnt <= LIST_CAP && threadIdx.x < cnt) {
+        const int e = lidx[n * LIST_CAP + threadIdx.x];
+        s_i[threadIdx.x] = e / d.K; s_k[threadIdx.x] = e % d.K; s_v[threadIdx.x] = lval[n * LIST_CAP + threadIdx.x];
+    }
+    __syncthreads();
+    if (cnt <= LIST_CAP) {
+        // rows i..i+h-1 of the tile are one contiguous window of h*2M floats: window[e] += v * Ft[k][e]
+        for (int q = 0; q < cnt; ++q) {
+            float* w = tile + s_i[q] * d.M2;
+            const float* f = FT + (int64_t)s_k[q] * hj;
+            const float v = s_v[q];
+            for (int e = threadIdx.x; e < hj; e += RB_THREADS) w[e] += v * f[e];
+            __syncthreads();                       // the next code's window overlaps this one with other threads
+        }
+    } else {                                       // more than LIST_CAP non-zeros: walk x itself in the same (position, filter) order
+        const float* xr = x + n * d.l * d.K;
+        for (int q = 0; q < d.l * d.K; ++q) {
+            const float v = xr[q];
+            if (v == 0.f) continue;                // block-uniform
+            float* w = tile + (q / d.K) * d.M2;
+            const float* f = FT + (int64_t)(q % d.K) * hj;
+            for (int e = threadIdx.x; e < hj; e += RB_THREADS) w[e] += v * f[e];
+            __syncthreads();
+        }
+    }
+    float* o = out + n * E;
+    for (int e = threadIdx.x; e < E; e += RB_THREADS) { if (accumulate) o[e] += tile[e]; else o[e] = tile[e]; }
+}
+
+// A4 for many groups: one CTA per group, the same order-statistic scheme as k_mask_scale_c (one 4096-bin level on bits 30..19,
+// then the few hundred entries of the median's bin resolved in shared memory) but with the group's 2*B*c*M values re-read from
+// L2 in each of the three sweeps instead of being held in shared memory: 24 KB of shared memory per CTA, two CTAs per SM, and
+// no cap on the group size.  (k_mask_scale_s keeps up to 49 152 positives in shared memory and runs four 8-bit radix passes over
+// them with one CTA per SM: 304 us per 500 groups; this kernel: see profiles/.)
+#define MG_THREADS 1024
+__global__ void __launch_bounds__(MG_THREADS) k_mask_scale_g(const float* __restrict__ z, const float* __restrict__ y,
+                                                             float* __restrict__ zy, float* __restrict__ med_out, CscDims d) { PDL_SYNC();
+    __shared__ unsigned int hist[MS_BINS];
+    __shared__ float cand[MS_CAND];
+    __shared__ unsigned int s_ncand, s_min, wsum[32], res[4];
+    const int g = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int EZ = d.B * d.c * d.M;
+    const float* zg = z + (int64_t)g * EZ;
+    const float* yg = y + (int64_t)g * EZ;
+    const int E2 = 2 * EZ;
+    // 16-byte sweeps when a group's slab is a whole number of float4 (27 900 floats at Lb = 100): the sweeps are bound by loads in flight
+    const int VZ = (EZ & 3) ? 0 : EZ >> 2, V2 = 2 * VZ;
+    const float4* zg4 = reinterpret_cast<const float4*>(zg);
+    const float4* yg4 = reinterpret_cast<const float4*>(yg);
+    unsigned int prefix = 0, pmask = 0, krank = 0, npos = 0, cnt = 0;
+    int shift = 19, nb = MS_BINS;
+    bool first = true, resolved = false;
+    for (int lvl = 0; lvl < 3; ++lvl) {
+        for (int i = threadIdx.x; i < nb; i += MG_THREADS) hist[i] = 0;
+        if (threadIdx.x == 0) { s_ncand = 0; s_min = 0x7f800000u; }
+        __syncthreads();
+        #pragma unroll 4
+        for (int v = threadIdx.x; v < V2; v += MG_THREADS) {
+            const float4 f4 = v < VZ ? zg4[v] : yg4[v - VZ];
+            const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const unsigned int b = __float_as_uint(fv[i]);
+                if (fv[i] > 0.f && (b & pmask) == prefix) atomicAdd(&hist[(b >> shift) & (unsigned)(nb - 1)], 1u);
+            }
+        }
+        for (int e = 4 * V2 + threadIdx.x; e < E2; e += MG_THREADS) {          // group sizes that are not a multiple of 4: scalar sweep
+            const float f = e < EZ ? zg[e] : yg[e - EZ];
+            const unsigned int b = __float_as_uint(f);
+            if (f > 0.f && (b & pmask) == prefix) atomicAdd(&hist[(b >> shift) & (unsigned)(nb - 1)], 1u);
+        }
+        __syncthreads();
+        block_find_bin(hist, nb, krank, first, wsum, res);
+        if (first) {
+            npos = res[3];
+            if (npos == 0) break;
+            krank = (npos & 1u) ? npos / 2 : npos / 2 - 1;
+            first = false;
+        }
+        const unsigned int bin = res[0];
+        krank -= res[1]; cnt = res[2];
+        prefix |= bin << shift; pmask |= (unsigned)(nb - 1) << shift;
+        __syncthreads();
+        if (cnt <= MS_CAND) break;
+        if (shift == 0) { resolved = true; break; }
+        if (shift == 19) { shift = 7; nb = MS_BINS; } else { shift = 0; nb = 128; }
+    }
+    float med = -INFINITY;
+    if (npos > 0) {
+        // the bin's entries -> cand[], and the smallest entry above the bin
+        unsigned int mn = 0x7f800000u;
+        auto take = [&](float f) {                                  // candidates are rare (a few hundred of 55 800): plain atomics
+            const unsigned int b = __float_as_uint(f);
+            if (f > 0.f) {
+                if ((b & pmask) > prefix) mn = min(mn, b);
+                else if (!resolved && (b & pmask) == prefix) cand[atomicAdd(&s_ncand, 1u)] = f;
+            }
+        };
+        #pragma unroll 4
+        for (int v = threadIdx.x; v < V2; v += MG_THREADS) {
+            const float4 f4 = v < VZ ? zg4[v] : yg4[v - VZ];
+            take(f4.x); take(f4.y); take(f4.z); take(f4.w);
+        }
+        for (int e = 4 * V2 + threadIdx.x; e < E2; e += MG_THREADS) take(e < EZ ? zg[e] : yg[e - EZ]);
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(FULLMASK, mn, o));
+        if (lane == 0 && mn != 0x7f800000u) atomicMin(&s_min, mn);
+        __syncthreads();
+        const unsigned int kin = krank;
+        unsigned int v1b = prefix;
+        if (!resolved) {
+            unsigned int lowfix = 0, lowmask = 0;
+            int rem = shift;
+            while (rem > 0) {
+                const int nbits = rem < 10 ? rem : 10, sh = rem - nbits, nbin = 1 << nbits;
+                for (int i = threadIdx.x; i < nbin; i += MG_THREADS) hist[i] = 0;
+                __syncthreads();
+                for (unsigned e0 = 0; e0 < cnt; e0 += MG_THREADS) {
+                    const unsigned e = e0 + threadIdx.x;
+                    const unsigned int b = e < cnt ? __float_as_uint(cand[e]) : 0u;
+                    hist_add(hist, e < cnt && (b & lowmask) == lowfix, (b >> sh) & (unsigned)(nbin - 1));
+                }
+                __syncthreads();
+                block_find_bin(hist, nbin, krank, false, wsum, res);
+                lowfix |= res[0] << sh; lowmask |= (unsigned)(nbin - 1) << sh; krank -= res[1];
+                __syncthreads();
+                rem = sh;
+            }
+            v1b |= lowfix;
+        }
+        const float v1 = __uint_as_float(v1b);
+        if (npos & 1u) med = v1;
+        else {
+            unsigned int le = 0, mn2 = 0x7f800000u;
+            if (!resolved)
+                for (unsigned e = threadIdx.x; e < cnt; e += MG_THREADS) { const unsigned int b = __float_as_uint(cand[e]); if (b <= v1b) ++le; else mn2 = min(mn2, b); }
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { le += __shfl_xor_sync(FULLMASK, le, o); mn2 = min(mn2, __shfl_xor_sync(FULLMASK, mn2, o)); }
+            if (threadIdx.x == 0) { res[0] = 0; res[1] = 0x7f800000u; }
+            __syncthreads();
+            if (lane == 0) { if (le) atomicAdd(&res[0], le); atomicMin(&res[1], mn2); }
+            __syncthreads();
+            const unsigned int le_all = resolved ? cnt : res[0];
+            const unsigned int v2b = (le_all >= kin + 2) ? v1b : (res[1] != 0x7f800000u ? res[1] : s_min);
+            med = v1 * 0.5f + __uint_as_float(v2b) * 0.5f;       // Statistics.middle(a, b) = a/2 + b/2
+        }
+    }
+    if (threadIdx.x == 0) med_out[g] = med;
+    // zy[row][0..M) = masked z row, zy[row][M..2M) = masked y row
+    float* og = zy + (int64_t)g * d.B * d.c * d.M2;
+    #pragma unroll 4
+    for (int v = threadIdx.x; v < V2; v += MG_THREADS) {
+        const bool isz = v < VZ;
+        const float4 f4 = isz ? zg4[v] : yg4[v - VZ];
+        const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
+        const int e0 = 4 * (isz ? v : v - VZ);
+        int np = e0 / d.M, m = e0 - np * d.M;
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            og[(int64_t)np * d.M2 + (isz ? 0 : d.M) + m] = fv[i] >= med ? d.mf * fv[i] : 0.f;
+            if (++m == d.M) { m = 0; ++np; }
+        }
+    }
+    for (int e = 4 * V2 + threadIdx.x; e < E2; e += MG_THREADS) {
+        const int ee = e < EZ ? e : e - EZ;
+        const int np = ee / d.M, m = ee - np * d.M;
+        const float f = e < EZ ? zg[e] : yg[e - EZ];
+        og[(int64_t)np * d.M2 + (e < EZ ? 0 : d.M) + m] = f >= med ? d.mf * f : 0.f;
+    }
+}

@@ -234,3 +234,37 @@ def test_median_mask_order_statistic_corner_cases(ctx, G):
         assert np.array_equal(med, rmed), (kind, med[:4], rmed[:4])
         assert np.array_equal(zy, rzy), kind
     m.free()
+
+
+def test_batched_layout_matches_single_batch_layout(ctx):
+    """n_groups=40 selects the one-CTA-per-sequence kernels (csc_batched.cuh: recon, corr_sig, tconv in forward and reverse
+    pass); every group must reproduce what the single-batch kernels compute for it: loss to 1e-6 relative, gradient = mean of
+    the 40 single-group gradients to 1e-5 of its largest entry, and the same code records."""
+    G = 40
+    hp, ohp, a, seqs, flat = _setup(ctx, 6 * G, 100, 9)
+    mG = mb._lib.CscModel(ctx, hp, 100, n_groups=G)
+    m1 = mb._lib.CscModel(ctx, hp, 100)
+    mG.set_params(flat); m1.set_params(flat)
+    idx = np.random.default_rng(1).permutation(6 * G)
+    lossG, gG = mG.loss_grad(seqs, idx)
+    gs = []
+    for k in range(G):
+        l1, g1 = m1.loss_grad(seqs, idx[6 * k: 6 * k + 6])
+        assert lossG[k, 0] == pytest.approx(l1[0, 0], rel=1e-6), k
+        gs.append(g1)
+    gm = np.mean(gs, axis=0)
+    assert np.abs(gG - gm).max() <= 1e-5 * np.abs(gm).max()
+    # forward-only: codes of a 40-group launch vs 40 launches of one group
+    fG = mb._lib.CscModel(ctx, hp, 100, n_groups=G, forward_only=True)
+    f1 = mb._lib.CscModel(ctx, hp, 100, n_groups=1, forward_only=True)
+    fG.set_params(flat); f1.set_params(flat)
+    cG = fG.codes(seqs)
+    c1 = np.concatenate([f1.codes(seqs, first_seq=6 * k, n_seqs=6) for k in range(G)])
+    assert len(cG) == len(c1)
+    for f in ("position", "fil", "seq"):
+        assert np.array_equal(cG[f], c1[f]), f
+    dm = np.abs(cG["mag_f16"].view(np.float16).astype(np.float32) - c1["mag_f16"].view(np.float16).astype(np.float32))
+    assert (dm <= 2e-6).mean() >= 0.99
+    for m in (mG, m1, fG, f1):
+        m.free()
+    seqs.free()
