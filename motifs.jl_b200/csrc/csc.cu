@@ -185,7 +185,8 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
             else lk(k_corr2d_tc, std::min(S->tc_tiles, S->ctx->sm_count), 128, S->tc_smem, q, S->tc_A, S->tc_F, out, rows, S->tc_tiles, S->tc_ld, d);
             return;
         }
-        if (fastK) lk(k_corr2d_w<24, 4>, d.NS * ((d.l + 3) / 4), 128, 0, q, A, filt, gs, out, acc, d);
+        if (S->batched && d.G >= 32 && fastK && d.M2 * 24 <= 5 * 4 * C2B_THREADS)      // one CTA per sequence wins from ~190 sequences up (measured) lk(k_corr2d_b<24>, d.NS, C2B_THREADS, corr2d_b_smem(d, 24), q, A, filt, gs, out, acc, d);
+        else if (fastK) lk(k_corr2d_w<24, 4>, d.NS * ((d.l + 3) / 4), 128, 0, q, A, filt, gs, out, acc, d);
         else lk(k_corr2d, nblk(nX, 128), 128, 0, q, A, filt, gs, out, acc, d);
     };
     // D-layer forms: per-output kernels for a single reference batch, one CTA per sequence when the launch holds many groups
@@ -439,6 +440,7 @@ static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
         MB_CUDA(ctx, cudaFuncSetAttribute(k_recon_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)recon_b_smem(s->d)));
         MB_CUDA(ctx, cudaFuncSetAttribute(k_corr_sig_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_sig_b_smem(s->d)));
         MB_CUDA(ctx, cudaFuncSetAttribute(k_tconv_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)s->d.c * s->d.M2 * 4)));
+        MB_CUDA(ctx, cudaFuncSetAttribute(k_corr2d_b<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr2d_b_smem(s->d, 24)));
     }
     MB_CUDA(ctx, cudaMalloc(&s->bits, std::max<size_t>(s->bits_n, 16)));
     MB_CUDA(ctx, cudaMalloc(&s->lcnt, (size_t)std::max(1, s->n_lists) * s->d.NS * 4));

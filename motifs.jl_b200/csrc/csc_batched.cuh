@@ -334,3 +334,87 @@ __global__ void __launch_bounds__(MG_THREADS) k_mask_scale_g(const float* __rest
         og[(int64_t)np * d.M2 + (e < EZ ? 0 : d.M) + m] = f >= med ? d.mf * f : 0.f;
     }
 }
+
+// U2 "corr2d" for many groups, fp32: out[n,i,k] (+)= sum_{a<h} sum_{j<2M} A[n,i+a,j] F[a][j][k]   (model.jl:214,251)
+// One CTA per sequence.  The sequence's rows (c x 2M, row stride 2M+1 so that the row tiles of a warp fall into different banks)
+// stay in shared memory; F is streamed one window offset at a time (2M x K floats, double-buffered through registers).
+// Register tiles of 4 rows x 8 filters: per (a, j) a thread issues 4 broadcast row loads + 2 LDS.128 for 32 FMAs.
+#define C2B_THREADS 128
+template <int KK>
+__global__ void __launch_bounds__(C2B_THREADS) k_corr2d_b(const float* __restrict__ A, const float* __restrict__ filt, int64_t filt_gs,
+                                                          float* __restrict__ out, int accumulate, CscDims d) { PDL_SYNC();
+    extern __shared__ __align__(16) float rb_smem[];
+    constexpr int KT = KK / 8;                                  // filter tiles of 8
+    const int rt_n = (d.l + 3) >> 2;                            // row tiles of 4
+    const int rows_pad = rt_n * 4 + d.h - 1;                    // rows a tile may touch
+    const int ldA = d.M2 + 1;
+    float* sA = rb_smem;                                        // [rows_pad][ldA]
+    float* sF = sA + ((rows_pad * ldA + 3) & ~3);               // [2][2M*KK]
+    const int64_t n = blockIdx.x;
+    const float* F = filt + (n / d.B) * filt_gs;
+    const float* a_src = A + n * d.c * d.M2;
+    const int fsz = d.M2 * KK, fv = fsz >> 2;                   // floats / float4 per window offset
+    for (int e = threadIdx.x; e < rows_pad * d.M2; e += C2B_THREADS) {
+        const int r = e / d.M2, j = e - r * d.M2;
+        sA[r * ldA + j] = r < d.c ? a_src[e] : 0.f;
+    }
+    const int ntile = rt_n * KT;
+    for (int t0 = 0; t0 < ntile; t0 += C2B_THREADS) {
+        const int tile = t0 + threadIdx.x;
+        const bool live = tile < ntile;
+        const int rt = live ? tile / KT : 0, kt = live ? tile - rt * KT : 0;
+        float acc[4][8];
+        #pragma unroll
+        for (int r = 0; r < 4; ++r)
+            #pragma unroll
+            for (int k = 0; k < 8; ++k) acc[r][k] = 0.f;
+        __syncthreads();                                        // sA filled / previous round done with sF
+        for (int v = threadIdx.x; v < fv; v += C2B_THREADS) reinterpret_cast<float4*>(sF)[v] = reinterpret_cast<const float4*>(F)[v];
+        __syncthreads();
+        for (int a = 0; a < d.h; ++a) {
+            float4 pre[5];                                      // next offset's F slice (2M*KK/4 = 600 float4 over 128 threads)
+            const bool more = a + 1 < d.h;
+            if (more) {
+                const float4* src = reinterpret_cast<const float4*>(F + (int64_t)(a + 1) * fsz);
+                #pragma unroll
+                for (int u = 0; u < 5; ++u) { const int v = threadIdx.x + u * C2B_THREADS; if (v < fv) pre[u] = src[v]; }
+            }
+            if (live) {
+                const float* f0 = sF + (a & 1) * fsz + kt * 8;
+                const float* a0 = sA + (rt * 4 + a) * ldA;
+                #pragma unroll 4
+                for (int j = 0; j < d.M2; ++j) {
+                    const float4 fa = *reinterpret_cast<const float4*>(f0 + j * KK);
+                    const float4 fb = *reinterpret_cast<const float4*>(f0 + j * KK + 4);
+                    #pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float av = a0[r * ldA + j];
+                        acc[r][0] += av * fa.x; acc[r][1] += av * fa.y; acc[r][2] += av * fa.z; acc[r][3] += av * fa.w;
+                        acc[r][4] += av * fb.x; acc[r][5] += av * fb.y; acc[r][6] += av * fb.z; acc[r][7] += av * fb.w;
+                    }
+                }
+            }
+            if (more) {
+                float4* dst = reinterpret_cast<float4*>(sF + ((a + 1) & 1) * fsz);
+                #pragma unroll
+                for (int u = 0; u < 5; ++u) { const int v = threadIdx.x + u * C2B_THREADS; if (v < fv) dst[v] = pre[u]; }
+            }
+            __syncthreads();
+        }
+        if (live) {
+            #pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int i = rt * 4 + r;
+                if (i >= d.l) continue;
+                float4* o = reinterpret_cast<float4*>(out + (n * d.l + i) * KK + kt * 8);
+                float4 v0 = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]), v1 = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+                if (accumulate) { const float4 p0 = o[0], p1 = o[1]; v0.x += p0.x; v0.y += p0.y; v0.z += p0.z; v0.w += p0.w; v1.x += p1.x; v1.y += p1.y; v1.z += p1.z; v1.w += p1.w; }
+                o[0] = v0; o[1] = v1;
+            }
+        }
+    }
+}
+static inline size_t corr2d_b_smem(const CscDims& d, int KK) {
+    const size_t rows_pad = (size_t)(((d.l + 3) >> 2) * 4 + d.h - 1);
+    return (((rows_pad * (d.M2 + 1) + 3) & ~(size_t)3) + 2 * (size_t)d.M2 * KK) * 4;
+}
