@@ -185,7 +185,8 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
             else lk(k_corr2d_tc, std::min(S->tc_tiles, S->ctx->sm_count), 128, S->tc_smem, q, S->tc_A, S->tc_F, out, rows, S->tc_tiles, S->tc_ld, d);
             return;
         }
-        if (S->batched && d.G >= 32 && fastK && d.M2 * 24 <= 5 * 4 * C2B_THREADS)      // one CTA per sequence wins from ~190 sequences up (measured) lk(k_corr2d_b<24>, d.NS, C2B_THREADS, corr2d_b_smem(d, 24), q, A, filt, gs, out, acc, d);
+        // one CTA per sequence wins from ~190 sequences up (measured)
+        if (S->batched && d.G >= 32 && fastK && d.M2 * 24 <= 5 * 4 * C2B_THREADS) lk(k_corr2d_b<24>, d.NS, C2B_THREADS, corr2d_b_smem(d, 24), q, A, filt, gs, out, acc, d);
         else if (fastK) lk(k_corr2d_w<24, 4>, d.NS * ((d.l + 3) / 4), 128, 0, q, A, filt, gs, out, acc, d);
         else lk(k_corr2d, nblk(nX, 128), 128, 0, q, A, filt, gs, out, acc, d);
     };
