@@ -181,6 +181,33 @@ typedef struct { uint32_t motif, seq, pos, comp; } mb200_site;   /* 0-based; com
 int32_t mb200_count_matrices(mb200_ctx* ctx, const mb200_seqs* seqs, const mb200_site* sites, int64_t n_sites,
                              const int64_t* lens, int32_t K, int32_t maxlen, uint32_t* counts);
 
+/* ---- code components -> triplet dictionary: replaces get_scanning_range_of_filtered_code_components, enumerate_triplets /
+ *      insert_H! (inference/_2_enumerate.jl:25-65) and the key counting of get_words / get_enriched_keys
+ *      (inference/_3_make_pfms.jl:3-26).  A key is f1 | f2<<8 | f3<<16 | d12<<24 | d13<<40 with 1-based filter ids (the fields of
+ *      the reference's NamedTuple key).  The dictionary itself stays on the device; the host asks for the keys above a count and
+ *      then for the values of the keys it selected.                                                   */
+typedef struct mb200_triplets mb200_triplets;
+typedef struct { uint64_t key; uint32_t count, reserved; uint64_t first; } mb200_key_count;   /* first = rank of the key's first insertion */
+typedef struct { uint32_t key_index, range_index, position, reserved; uint64_t order; } mb200_triplet_value;
+/* position/fil/seq: the filtered stored_code_components in the order code retrieval returns them (0-based fields, seq
+ * ascending).  Builds the sequence ranges exactly like _2_enumerate.jl:25-35 (a range closes when seq != cur_seq, cur_seq counts
+ * up by one per closed range, the last range is never closed), sorts every range by position (stable) and counts every
+ * triplet's key.  n_ranges / n_triplets may be NULL.                                                    */
+int32_t mb200_triplets_create(mb200_ctx* ctx, const uint16_t* position, const uint16_t* fil, const uint32_t* seq, int64_t n_codes,
+                              mb200_triplets** out, int64_t* n_ranges, int64_t* n_triplets);
+int32_t mb200_triplets_destroy(mb200_ctx* ctx, mb200_triplets* t);
+/* the ranges as 0-based half-open [start, stop) index pairs into the code arrays (n_ranges entries each) */
+int32_t mb200_triplets_ranges(mb200_ctx* ctx, const mb200_triplets* t, int32_t* start, int32_t* stop);
+/* keys with more than min_count values, in no particular order, each with its count and the rank of its first insertion
+ * (ascending `first` = the reference Dictionary's iteration order).  *n = how many there are; at most cap are written. */
+int32_t mb200_triplets_frequent(mb200_ctx* ctx, mb200_triplets* t, uint32_t min_count, mb200_key_count* out, int64_t cap, int64_t* n);
+/* the dictionary values of `keys` (a subset of the last mb200_triplets_frequent result): one record per value with
+ * key_index = index into keys, range_index = 1-based index of the sequence range (what insert_H! stores as seq_num),
+ * position = 1-based position of the triplet's first component; ascending `order` within a key = insertion order.
+ * *n = how many records there are; at most cap are written.                                             */
+int32_t mb200_triplets_values(mb200_ctx* ctx, mb200_triplets* t, const uint64_t* keys, int64_t n_keys, mb200_triplet_value* out,
+                              int64_t cap, int64_t* n);
+
 #ifdef __cplusplus
 }
 #endif

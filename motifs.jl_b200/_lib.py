@@ -34,6 +34,9 @@ assert HIT_DTYPE.itemsize == 16
 SITE_DTYPE = np.dtype([("motif", "<u4"), ("seq", "<u4"), ("pos", "<u4"), ("comp", "<u4")])
 CODE_DTYPE = np.dtype([("position", "<u2"), ("fil", "<u2"), ("seq", "<u4"), ("mag_f16", "<u2"), ("_pad", "<u2")])
 assert CODE_DTYPE.itemsize == 12
+KEYCOUNT_DTYPE = np.dtype([("key", "<u8"), ("count", "<u4"), ("reserved", "<u4"), ("first", "<u8")])
+TRIPVAL_DTYPE = np.dtype([("key_index", "<u4"), ("range_index", "<u4"), ("position", "<u4"), ("reserved", "<u4"), ("order", "<u8")])
+assert KEYCOUNT_DTYPE.itemsize == 24 and TRIPVAL_DTYPE.itemsize == 24
 
 
 class HParams(C.Structure):
@@ -86,6 +89,11 @@ def load():
         "mb200_csc_median_mask": (i32, [p, p, p, p, p, p]),
         "mb200_csc_codes": (i32, [p, p, p, i64, i64, p, i64, C.POINTER(i64)]),
         "mb200_count_matrices": (i32, [p, p, p, i64, p, i32, i32, p]),
+        "mb200_triplets_create": (i32, [p, p, p, p, i64, p, p, p]),
+        "mb200_triplets_destroy": (i32, [p, p]),
+        "mb200_triplets_ranges": (i32, [p, p, p, p]),
+        "mb200_triplets_frequent": (i32, [p, p, C.c_uint32, p, i64, p]),
+        "mb200_triplets_values": (i32, [p, p, p, i64, p, i64, p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -356,3 +364,61 @@ class CscModel:
         n = C.c_int64()
         self.ctx._check(self.ctx._lib.mb200_csc_codes(self.ctx._h, self._h, seqs._h, int(first_seq), int(n_seqs), _ptr(out), cap, C.byref(n)))
         return out[: n.value]
+
+
+class Triplets:
+    """mb200_triplets: the triplet dictionary of one set of filtered code components, resident on the device
+    (enumerate_triplets / insert_H!, inference/_2_enumerate.jl:25-65)."""
+
+    def __init__(self, ctx: "Context", codes):
+        self.ctx = ctx
+        pos = np.ascontiguousarray(codes["position"], np.uint16)
+        fil = np.ascontiguousarray(codes["fil"], np.uint16)
+        seq = np.ascontiguousarray(codes["seq"], np.uint32)
+        h, nr, nt = C.c_void_p(), C.c_int64(), C.c_int64()
+        ctx._check(ctx._lib.mb200_triplets_create(ctx._h, _ptr(pos), _ptr(fil), _ptr(seq), len(pos), C.byref(h), C.byref(nr), C.byref(nt)))
+        self._h, self.n_ranges, self.n_triplets = h, nr.value, nt.value
+
+    def ranges(self):
+        a, b = np.zeros(self.n_ranges, np.int32), np.zeros(self.n_ranges, np.int32)
+        self.ctx._check(self.ctx._lib.mb200_triplets_ranges(self.ctx._h, self._h, _ptr(a), _ptr(b)))
+        return a, b
+
+    def frequent(self, min_count: int):
+        """keys with more than min_count values, sorted by first insertion: structured array (key, count, first)."""
+        n = C.c_int64()
+        self.ctx._check(self.ctx._lib.mb200_triplets_frequent(self.ctx._h, self._h, int(min_count), None, 0, C.byref(n)))
+        out = np.zeros(n.value, KEYCOUNT_DTYPE)
+        if n.value:
+            self.ctx._check(self.ctx._lib.mb200_triplets_frequent(self.ctx._h, self._h, int(min_count), _ptr(out), n.value, C.byref(n)))
+        return out[np.argsort(out["first"], kind="stable")]
+
+    def values(self, keys, total=None):
+        """dictionary values of `keys` in insertion order: list of (n, 2) int64 arrays (range index, position), both 1-based."""
+        keys = np.ascontiguousarray(keys, np.uint64)
+        if len(keys) == 0:
+            return []
+        cap = int(total) if total is not None else 1 << 20
+        while True:
+            out = np.zeros(max(cap, 1), TRIPVAL_DTYPE)
+            n = C.c_int64()
+            self.ctx._check(self.ctx._lib.mb200_triplets_values(self.ctx._h, self._h, _ptr(keys), len(keys), _ptr(out), cap, C.byref(n)))
+            if n.value <= cap:
+                break
+            cap = n.value
+        out = out[: n.value]
+        out = out[np.lexsort((out["order"], out["key_index"]))]
+        cuts = np.searchsorted(out["key_index"], np.arange(len(keys) + 1))
+        vals = np.stack([out["range_index"].astype(np.int64), out["position"].astype(np.int64)], axis=1)
+        return [vals[cuts[i]: cuts[i + 1]] for i in range(len(keys))]
+
+    def free(self):
+        if self._h:
+            self.ctx._lib.mb200_triplets_destroy(self.ctx._h, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

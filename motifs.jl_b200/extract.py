@@ -8,8 +8,10 @@
   posdicts2countmats                          inference/_h6_positions2countmat.jl:26-37 -> GPU
   run_thru (the in-scope stages)              inference/_g1_obtain_coutmats.jl:131-173
 
-The triplet enumeration is vectorised numpy on the host for now (a GPU sort-by-key of the packed 64-bit keys is the planned
-replacement); count-matrix accumulation runs on the GPU.  Everything is 1-based like the reference at this level.
+The triplet enumeration and key counting run on the GPU (csrc/triplets.cu: hash table of packed 64-bit keys, mb200_triplets_*);
+run_thru uses that path.  `enumerate_triplets` / `get_enriched_keys` below are the same stage as plain numpy on explicit
+dictionaries: the form the tests compare the GPU path and the literal oracle with, not what run_thru executes.  Count-matrix
+accumulation runs on the GPU.  Everything is 1-based like the reference at this level.
 OUT OF SCOPE and therefore NOT applied by run_thru here: merge_H / trim_H, expansions_ms!,
 alignment_merge!, merge_to_remove_redundancy!, trim_cmats, merge_count_matrices — small sequential CPU heuristics.
 """
@@ -107,6 +109,26 @@ def get_enriched_keys(H, max_word_combinations=num_pfms2process, dec=-5, count_f
     return enriched or []
 
 
+def enumerate_triplets_gpu(ctx, codes):
+    """enumerate_triplets on the device (mb200_triplets_create): ranges, per-range stable sort by position, one hash-table count
+    per triplet key.  Returns the device-resident dictionary (`_lib.Triplets`); .ranges() gives the reference's ranges."""
+    return _lib.Triplets(ctx, codes)
+
+
+def get_enriched_keys_gpu(t, max_word_combinations=num_pfms2process, dec=-5, count_from=cover_more_than, count_to=cover_at_least):
+    """get_enriched_keys (_3_make_pfms.jl:13-26) on the device dictionary: every candidate list of the reference's loop is a subset
+    of {count > count_to}, so one compaction of those keys (with their first-insertion rank = Dictionary order) serves the whole
+    loop.  Returns a structured array (key, count, first) in the order the reference returns its keys."""
+    cand = t.frequent(count_to)
+    enriched = cand[:0]
+    for count in range(count_from, count_to - 1, dec):
+        enriched = cand[cand["count"] > count]
+        if len(enriched) > max_word_combinations:
+            top = enriched[np.argsort(-enriched["count"].astype(np.int64), kind="stable")]     # sort(length.(q), rev=true): stable
+            return top[:num_pfms2process]
+    return enriched
+
+
 def sites_from_H(H, keys, hp, range_to_seq=None):
     """(motif, seq, pos, comp) records of the enriched keys, 0-based, for the GPU count-matrix kernel."""
     rec = []
@@ -144,16 +166,19 @@ def posdicts2countmats(ms: Motifs, data):
 
 def run_thru(data, cdl, hp, ln, projs, this_bg, quantiles=(0.75, 0.65, 0.5, 0.45, 0.35, 0.25, 0.15, 0.05), codes=None):
     """run_thru (_g1_obtain_coutmats.jl:131-173), in-scope stages: code retrieval (GPU) -> per quantile: filter, ranges, triplet
-    enumeration, enriched keys -> merged dictionary (earlier quantiles win, like Dictionaries.merge's left-to-right update) ->
+    enumeration and key counting (GPU, csrc/triplets.cu), enriched keys -> merged dictionary (earlier quantiles win, like Dictionaries.merge's left-to-right update) ->
     count matrices (GPU) -> countmats2motifs.  Returns None when no key is enriched (:162-163)."""
     from .model import code_retrieval
     codes = code_retrieval(data, cdl, hp) if codes is None else codes
     merged = {}
     for q in quantiles:
         cf = filter_code_components_using_quantile(codes, q)
-        H = enumerate_triplets(cf, get_scanning_range_of_filtered_code_components(cf), hp)
-        for k in get_enriched_keys(H, max_word_combinations=1000):
-            merged[k] = H[k]                                       # merge(a, b): b's value replaces a's for equal keys
+        t = enumerate_triplets_gpu(data.ctx, cf)
+        ek = get_enriched_keys_gpu(t, max_word_combinations=1000)
+        if len(ek):
+            for k, v in zip(ek["key"].tolist(), t.values(ek["key"], total=int(ek["count"].sum()))):
+                merged[k] = v                                      # merge(a, b): b's value replaces a's for equal keys
+        t.free()
     if not merged:
         return None
     keys = list(merged.keys())
