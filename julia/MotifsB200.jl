@@ -107,4 +107,47 @@ function code_retrieval(ctx, m, seqs, N::Integer, batch_size::Integer)
     [(position=c.position + 0x0001, fil=c.fil + 0x0001, seq=c.seq + 0x00000001, mag=c.mag) for c in view(out, 1:cnt[])]
 end
 
+# replaces get_scanning_range_of_filtered_code_components + enumerate_triplets (inference/_2_enumerate.jl:25-65) and the key
+# counting of get_enriched_keys (inference/_3_make_pfms.jl:3-26).  `codes` = the filtered stored_code_components (1-based fields).
+struct KeyCount; key::UInt64; count::UInt32; reserved::UInt32; first::UInt64; end
+struct TripletValue; key_index::UInt32; range_index::UInt32; position::UInt32; reserved::UInt32; order::UInt64; end
+unpack_key(k::UInt64, h) = (f1=Int(k & 0xff), f2=Int((k >> 8) & 0xff), f3=Int((k >> 16) & 0xff), d12=Int((k >> 24) & 0xffff),
+                            d13=Int((k >> 40) & 0xffff), len=Int((k >> 40) & 0xffff) + h)
+function triplets_create(ctx, codes)
+    pos = UInt16[c.position - 1 for c in codes]; fil = UInt16[c.fil - 1 for c in codes]; seq = UInt32[c.seq - 1 for c in codes]
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve pos fil seq check(ctx, ccall((:mb200_triplets_create, lib), Int32,
+        (Ptr{Cvoid}, Ptr{UInt16}, Ptr{UInt16}, Ptr{UInt32}, Int64, Ref{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Int64}), ctx, pos, fil, seq, length(pos), h, C_NULL, C_NULL))
+    h[]
+end
+triplets_destroy(ctx, t) = ccall((:mb200_triplets_destroy, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), ctx, t)
+# keys with more than `min_count` values in Dictionary (first-insertion) order
+function triplets_frequent(ctx, t, min_count::Integer)
+    n = Ref{Int64}(0)
+    check(ctx, ccall((:mb200_triplets_frequent, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, UInt32, Ptr{KeyCount}, Int64, Ref{Int64}), ctx, t, min_count, C_NULL, 0, n))
+    out = Vector{KeyCount}(undef, n[])
+    GC.@preserve out check(ctx, ccall((:mb200_triplets_frequent, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, UInt32, Ptr{KeyCount}, Int64, Ref{Int64}), ctx, t, min_count, out, n[], n))
+    sort!(out, by = x -> x.first)
+end
+# get_enriched_keys(H; max_word_combinations, dec=-5, count_from=cover_more_than, count_to=cover_at_least) on the device dictionary
+function get_enriched_keys(ctx, t; max_word_combinations=500, dec=-5, count_from=200, count_to=10, num_pfms2process=500)
+    cand = triplets_frequent(ctx, t, count_to); enriched = KeyCount[]
+    for count = count_from:dec:count_to
+        enriched = filter(x -> x.count > count, cand)
+        length(enriched) > max_word_combinations && return sort(enriched, by = x -> x.count, rev = true)[1:num_pfms2process]
+    end
+    enriched
+end
+# H[k] for the selected keys: Vector of [(seq_num = range index, pos)] in insertion order, as insert_H! builds them
+function triplets_values(ctx, t, keys::Vector{KeyCount})
+    ks = UInt64[k.key for k in keys]; total = sum(Int(k.count) for k in keys; init = 0)
+    out = Vector{TripletValue}(undef, max(total, 1)); n = Ref{Int64}(0)
+    GC.@preserve ks out check(ctx, ccall((:mb200_triplets_values, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{UInt64}, Int64, Ptr{TripletValue}, Int64, Ref{Int64}), ctx, t, ks, length(ks), out, total, n))
+    recs = sort!(view(out, 1:n[]), by = v -> (v.key_index, v.order))
+    H = [Tuple{Int,Int}[] for _ in keys]
+    for v in recs push!(H[v.key_index + 1], (Int(v.range_index), Int(v.position))) end
+    H
+end
+
 end # module
