@@ -195,7 +195,7 @@ def bench_scan(args, ctx, torch, dist, world, rank, local, dev, stream):
         return reduce_counts(c)
 
     def step_e2e():
-        s2 = ctx.seqs_from_host_ptr(ascii_host.data_ptr(), n_local, Lb)     # H2D of this step's input + pack
+        s2 = ctx.seqs_from_host_ptr(ascii_host.data_ptr(), n_local, Lb, wait=False)     # H2D of this step's input + pack, overlapping the scan
         _, c = ctx.scan(s2, pw, lens, thr, want_hits=False, want_counts=True)
         s2.free()
         return reduce_counts(c)

@@ -57,7 +57,14 @@ int32_t     mb200_last_timing(const mb200_ctx* ctx, float* out_ms8, int64_t* lau
 /* ascii: N rows of Lb bytes, row-major, upper or lower case. */
 int32_t mb200_seqs_from_ascii(mb200_ctx* ctx, const uint8_t* ascii, int64_t N, int64_t Lb,
                               mb200_seqs** out);
-/* same, but `ascii_dev` is a device pointer on ctx's device (no host copy). */
+/* same, but returns at once: the H2D copies and pack kernels are queued on a copy stream of the ctx in 64 MB chunks, and
+ * mb200_scan starts on the first sequences while later chunks are still in flight (every other consumer, and
+ * mb200_seqs_wait, first waits for the whole upload).  `ascii` must stay valid — and should be pinned — until the first scan
+ * of these sequences or mb200_seqs_wait has returned; that call also reports MB200_E_BAD_SEQUENCE.          */
+int32_t mb200_seqs_from_ascii_async(mb200_ctx* ctx, const uint8_t* ascii, int64_t N, int64_t Lb,
+                                    mb200_seqs** out);
+int32_t mb200_seqs_wait(mb200_ctx* ctx, mb200_seqs* seqs);
+/* same as mb200_seqs_from_ascii, but `ascii_dev` is a device pointer on ctx's device (no host copy). */
 int32_t mb200_seqs_from_device_ascii(mb200_ctx* ctx, const void* ascii_dev, int64_t N, int64_t Lb,
                                      mb200_seqs** out);
 /* onehot: the reference's data_matrix (helpers.jl:123-139, fasta.jl:75): Float32, column-major

@@ -39,6 +39,15 @@ function upload_onehot(ctx, data_matrix::Array{Float32})
     h[]
 end
 free_seqs(ctx, s) = ccall((:mb200_seqs_free, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), ctx, s)
+# raw reads (N rows of L ASCII bytes, as read_fasta leaves them after uppercase.(...)): no one-hot detour.  async=true returns at once;
+# keep `ascii` alive (GC.@preserve) until the first gpu_scan of these sequences or wait_seqs has returned.
+function upload_ascii(ctx, ascii::Matrix{UInt8}; async=false)          # size(ascii) == (L, N): one column per read
+    h = Ref{Ptr{Cvoid}}(C_NULL); L, N = size(ascii)
+    rc = async ? ccall((:mb200_seqs_from_ascii_async, lib), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int64, Int64, Ref{Ptr{Cvoid}}), ctx, ascii, N, L, h) :
+                 ccall((:mb200_seqs_from_ascii, lib), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int64, Int64, Ref{Ptr{Cvoid}}), ctx, ascii, N, L, h)
+    check(ctx, rc); h[]
+end
+wait_seqs(ctx, s) = check(ctx, ccall((:mb200_seqs_wait, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), ctx, s))
 
 # replaces get_pos_scores_arr + gpu_scan (inference/_h3_1_alignment.jl:57-99).  `pwms` is the (K,4,maxlen) Float16 array the
 # reference builds at :65-69 with rc=false; thresh === nothing gives the reference's "score > 0" scan.

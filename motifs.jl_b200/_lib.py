@@ -67,6 +67,8 @@ def load():
         "mb200_set_stream": (i32, [p, p]),
         "mb200_last_timing": (i32, [p, p, p]),
         "mb200_seqs_from_ascii": (i32, [p, p, i64, i64, C.POINTER(p)]),
+        "mb200_seqs_from_ascii_async": (i32, [p, p, i64, i64, C.POINTER(p)]),
+        "mb200_seqs_wait": (i32, [p, p]),
         "mb200_seqs_from_device_ascii": (i32, [p, p, i64, i64, C.POINTER(p)]),
         "mb200_seqs_from_onehot_f32": (i32, [p, p, i64, i64, C.POINTER(p)]),
         "mb200_seqs_free": (i32, [p, p]),
@@ -152,10 +154,13 @@ class Context:
         self._check(self._lib.mb200_seqs_from_ascii(self._h, _ptr(a), a.shape[0], a.shape[1], C.byref(h)))
         return Sequences(self, h, a.shape[0], a.shape[1])
 
-    def seqs_from_host_ptr(self, ptr: int, N: int, Lb: int) -> "Sequences":
-        """ASCII rows at a raw host address (e.g. a pinned torch tensor's data_ptr())."""
+    def seqs_from_host_ptr(self, ptr: int, N: int, Lb: int, wait: bool = True) -> "Sequences":
+        """ASCII rows at a raw host address (e.g. a pinned torch tensor's data_ptr()).  wait=False: the upload is queued on the
+        ctx's copy stream and overlaps the first scan of these sequences (mb200_seqs_from_ascii_async); the caller keeps the host
+        buffer alive until that scan or Sequences.wait() has returned."""
         h = C.c_void_p()
-        self._check(self._lib.mb200_seqs_from_ascii(self._h, C.c_void_p(ptr), N, Lb, C.byref(h)))
+        fn = self._lib.mb200_seqs_from_ascii if wait else self._lib.mb200_seqs_from_ascii_async
+        self._check(fn(self._h, C.c_void_p(ptr), N, Lb, C.byref(h)))
         return Sequences(self, h, N, Lb)
 
     def seqs_from_device_ptr(self, ptr: int, N: int, Lb: int) -> "Sequences":
@@ -250,6 +255,10 @@ class Sequences:
         out = np.zeros((self.N, self.words_per_seq), np.uint32)
         self.ctx._check(self.ctx._lib.mb200_seqs_download(self.ctx._h, self._h, _ptr(out), out.size))
         return out
+
+    def wait(self):
+        """block until an asynchronous upload has finished (raises MB200Error on symbols other than A,C,G,T)."""
+        self.ctx._check(self.ctx._lib.mb200_seqs_wait(self.ctx._h, self._h))
 
     def free(self):
         if self._h and self.ctx._h:

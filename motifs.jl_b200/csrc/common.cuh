@@ -16,6 +16,7 @@ struct mb200_ctx {
     size_t smem_optin = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;            // stream every kernel of this ctx is launched on
+    cudaStream_t copy_stream = nullptr;       // uploads of mb200_seqs_from_ascii_async (created on first use)
     std::string err;
     // timing of the last call
     float ms[T_N] = {0};
@@ -32,7 +33,13 @@ struct mb200_seqs {
     int64_t rowwords = 0;        // uint32 words per sequence = ceil(Lb/16)
     uint32_t* words = nullptr;   // device, N*rowwords (+ zeroed tail pad of PAD_WORDS)
     int device = 0;
+    // asynchronous upload (mb200_seqs_from_ascii_async): rows [0, ready_end[i]) are packed once ready[i] has fired
+    bool pending = false;
+    std::vector<cudaEvent_t> ready; std::vector<int64_t> ready_end;
+    uint8_t* stage = nullptr;    // own staging buffers + bad-symbol counter, freed by mb_seqs_finish
+    cudaStream_t copy_stream = nullptr;
 };
+int mb_seqs_finish(mb200_ctx* ctx, mb200_seqs* s);      // waits for a pending upload, frees its staging; MB200_E_BAD_SEQUENCE if a symbol was not A,C,G,T
 static const int64_t SEQ_PAD_WORDS = 64;
 
 #define MB_FAIL(ctx, code, ...) do { char _b[512]; snprintf(_b, sizeof _b, __VA_ARGS__); \

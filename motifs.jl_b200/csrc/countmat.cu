@@ -33,6 +33,7 @@ extern "C" int32_t mb200_count_matrices(mb200_ctx* ctx, const mb200_seqs* seqs, 
     if (!ctx) return MB200_E_INVALID;
     if (!seqs || !lens || !counts || K <= 0 || maxlen <= 0 || n_sites < 0 || (n_sites > 0 && !sites)) MB_FAIL(ctx, MB200_E_INVALID, "count_matrices: bad arguments");
     MB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (seqs->pending) { const int rc = mb_seqs_finish(ctx, const_cast<mb200_seqs*>(seqs)); if (rc) return rc; }
     mb_reset_timing(ctx);
     std::vector<int32_t> h_lens(K);
     for (int k = 0; k < K; ++k) {

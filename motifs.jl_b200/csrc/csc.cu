@@ -633,6 +633,7 @@ static int launch_step(mb200_ctx* ctx, mb200_csc* s, const uint32_t* words, int6
 static int run_step(mb200_ctx* ctx, mb200_csc* s, const mb200_seqs* seqs, const int64_t* seq_idx, bool backward) {
     const CscDims d = s->d;
     if (seqs->Lb != d.Lb) MB_FAIL(ctx, MB200_E_INVALID, "csc: model built for Lb=%d, sequences have Lb=%lld", d.Lb, (long long)seqs->Lb);
+    if (seqs->pending) { const int rc = mb_seqs_finish(ctx, const_cast<mb200_seqs*>(seqs)); if (rc) return rc; }
     int64_t* slot = s->idx_pinned + (size_t)(s->ring++ % IDX_RING) * d.NS;
     for (int i = 0; i < d.NS; ++i) {
         if (seq_idx[i] < 0 || seq_idx[i] >= seqs->N) MB_FAIL(ctx, MB200_E_INVALID, "csc: sequence index %lld out of range", (long long)seq_idx[i]);
@@ -801,6 +802,7 @@ extern "C" int32_t mb200_csc_codes(mb200_ctx* ctx, mb200_csc* s, const mb200_seq
     if (!ctx || !s || !seqs || !n_out) return MB200_E_INVALID;
     const CscDims d = s->d;
     if (seqs->Lb != d.Lb) MB_FAIL(ctx, MB200_E_INVALID, "csc: model built for Lb=%d, sequences have Lb=%lld", d.Lb, (long long)seqs->Lb);
+    if (seqs->pending) { const int rc = mb_seqs_finish(ctx, const_cast<mb200_seqs*>(seqs)); if (rc) return rc; }
     if (first_seq < 0 || n_seqs < 0 || first_seq + n_seqs > seqs->N || n_seqs % d.B) MB_FAIL(ctx, MB200_E_INVALID, "csc_codes: range must be whole batches inside the data");
     MB_CUDA(ctx, cudaSetDevice(ctx->device));
     mb_reset_timing(ctx);

@@ -33,6 +33,7 @@ extern "C" int32_t mb200_destroy(mb200_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     for (int i = 0; i < 8; ++i) if (ctx->bufs[i]) cudaFree(ctx->bufs[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return MB200_OK;

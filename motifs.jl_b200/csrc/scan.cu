@@ -909,8 +909,17 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
     int64_t hits_written = 0, hits_needed = 0;
     std::vector<int64_t> h_rng(grid + 1);
     int64_t last_nchunks = -1;
+    size_t next_ready = 0;                                         // chunks of a pending asynchronous upload this scan has waited for
     for (int64_t s0 = 0; s0 < N; s0 += seqs_per_batch) {
         const int64_t ns = std::min(seqs_per_batch, N - s0);
+        if (seqs->pending) {
+            // a batch may start as soon as the chunks holding its sequences are packed (the kernel reads a few words past its last
+            // sequence: in bounds, and whatever they hold only reaches positions that are masked out)
+            while (next_ready < seqs->ready.size() && (next_ready == 0 || seqs->ready_end[next_ready - 1] < s0 + ns)) {
+                MB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, seqs->ready[next_ready], 0));
+                ++next_ready;
+            }
+        }
         const int64_t nchunks = ns * (int64_t)W16;
         const int64_t ntiles = tiles_of(nchunks);
         if (nchunks != last_nchunks) {
@@ -1033,6 +1042,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
     tm.end(t_total);
     MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     tm.collect();
+    if (seqs->pending) { rc = mb_seqs_finish(ctx, const_cast<mb200_seqs*>(seqs)); if (rc) return rc; }      // the upload has completed: report bad symbols
     if (n_hits) *n_hits = hits_needed;
     if (want_hits && hits_needed > hits_cap)
         MB_FAIL(ctx, MB200_E_HITS_OVERFLOW, "scan: %lld hits, capacity %lld", (long long)hits_needed, (long long)hits_cap);

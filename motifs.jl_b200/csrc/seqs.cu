@@ -169,9 +169,68 @@ extern "C" int32_t mb200_seqs_from_onehot_f32(mb200_ctx* ctx, const float* oneho
     return pack_common(ctx, onehot, true, true, N, Lb, out);
 }
 
+// Asynchronous upload: H2D copies (64 MB chunks, two staging buffers) and pack kernels are queued on the ctx's copy stream and the
+// call returns; an event per chunk tells mb200_scan which sequences are ready, so the scan of the first batch starts while later
+// chunks are still crossing PCIe.  The host buffer must stay valid (and should be pinned) until the first scan of these sequences
+// or mb200_seqs_wait has returned.
+extern "C" int32_t mb200_seqs_from_ascii_async(mb200_ctx* ctx, const uint8_t* ascii, int64_t N, int64_t Lb, mb200_seqs** out) {
+    if (!ctx) return MB200_E_INVALID;
+    if (!ascii && N > 0) MB_FAIL(ctx, MB200_E_INVALID, "seqs: null input");
+    int rc = seqs_alloc(ctx, N, Lb, out);
+    if (rc) return rc;
+    mb200_seqs* s = *out;
+    if (N == 0) return MB200_OK;
+    if (!ctx->copy_stream && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { mb200_seqs_free(ctx, s); *out = nullptr; MB_FAIL(ctx, MB200_E_CUDA, "seqs: cannot create the copy stream"); }
+    const size_t chunk_bytes = (size_t)64 << 20;
+    const int64_t rows_per_chunk = std::min<int64_t>(N, (int64_t)std::max<size_t>(1, chunk_bytes / (size_t)Lb));
+    const size_t buf = ((size_t)rows_per_chunk * (size_t)Lb + 255) & ~(size_t)255;
+    if (cudaMalloc(&s->stage, 256 + 2 * buf) != cudaSuccess) { cudaGetLastError(); mb200_seqs_free(ctx, s); *out = nullptr; MB_FAIL(ctx, MB200_E_NOMEM, "seqs: staging allocation failed"); }
+    cudaStream_t q = ctx->copy_stream;
+    s->copy_stream = q; s->pending = true;
+    unsigned int* d_bad = (unsigned int*)s->stage;
+    cudaError_t e = cudaMemsetAsync(d_bad, 0, 4, q);
+    // the tail pad was zeroed on ctx->stream by seqs_alloc: order the copy stream after it
+    cudaEvent_t ev0; cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming); cudaEventRecord(ev0, ctx->stream); cudaStreamWaitEvent(q, ev0, 0); cudaEventDestroy(ev0);
+    int b = 0;
+    for (int64_t n0 = 0; n0 < N && e == cudaSuccess; n0 += rows_per_chunk, b ^= 1) {
+        const int64_t nr = std::min(rows_per_chunk, N - n0);
+        uint8_t* d_stage = s->stage + 256 + (size_t)b * buf;
+        e = cudaMemcpyAsync(d_stage, ascii + (size_t)n0 * (size_t)Lb, (size_t)nr * (size_t)Lb, cudaMemcpyHostToDevice, q);
+        const int64_t threads = nr * s->rowwords;
+        pack_ascii_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, q>>>(d_stage, n0, nr, Lb, s->rowwords, s->words, d_bad);
+        cudaEvent_t ev;
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e == cudaSuccess) { e = cudaEventRecord(ev, q); s->ready.push_back(ev); s->ready_end.push_back(n0 + nr); }
+        ctx->launches[T_PACK] += 1;
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { mb200_seqs_free(ctx, s); *out = nullptr; MB_FAIL(ctx, MB200_E_CUDA, "seqs: %s", cudaGetErrorString(e)); }
+    return MB200_OK;
+}
+
+int mb_seqs_finish(mb200_ctx* ctx, mb200_seqs* s) {
+    if (!s->pending) return MB200_OK;
+    cudaError_t e = cudaStreamSynchronize(s->copy_stream);
+    unsigned int h_bad = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&h_bad, s->stage, 4, cudaMemcpyDeviceToHost);
+    for (auto ev : s->ready) cudaEventDestroy(ev);
+    s->ready.clear(); s->ready_end.clear();
+    cudaFree(s->stage); s->stage = nullptr; s->pending = false;
+    if (e != cudaSuccess) MB_FAIL(ctx, MB200_E_CUDA, "seqs: upload failed: %s", cudaGetErrorString(e));
+    if (h_bad) MB_FAIL(ctx, MB200_E_BAD_SEQUENCE, "%u words contain a symbol that is not A,C,G,T", h_bad);
+    return MB200_OK;
+}
+
+extern "C" int32_t mb200_seqs_wait(mb200_ctx* ctx, mb200_seqs* s) {
+    if (!ctx || !s) return MB200_E_INVALID;
+    MB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return mb_seqs_finish(ctx, s);
+}
+
 extern "C" int32_t mb200_seqs_free(mb200_ctx* ctx, mb200_seqs* s) {
     if (!s) return MB200_E_INVALID;
     if (ctx) cudaSetDevice(ctx->device);
+    if (s->pending) { cudaStreamSynchronize(s->copy_stream); for (auto ev : s->ready) cudaEventDestroy(ev); cudaFree(s->stage); s->pending = false; }
     if (s->words) cudaFree(s->words);
     delete s;
     return MB200_OK;
@@ -187,6 +246,7 @@ extern "C" int32_t mb200_seqs_shape(const mb200_seqs* s, int64_t* N, int64_t* Lb
 
 extern "C" int32_t mb200_seqs_download(mb200_ctx* ctx, const mb200_seqs* s, uint32_t* out_words, int64_t n_words) {
     if (!ctx || !s || !out_words) return MB200_E_INVALID;
+    if (s->pending) { const int rc = mb_seqs_finish(ctx, const_cast<mb200_seqs*>(s)); if (rc) return rc; }
     if (n_words != s->N * s->rowwords) MB_FAIL(ctx, MB200_E_INVALID, "download: expected %lld words", (long long)(s->N * s->rowwords));
     MB_CUDA(ctx, cudaSetDevice(ctx->device));
     MB_CUDA(ctx, cudaMemcpyAsync(out_words, s->words, (size_t)n_words * 4, cudaMemcpyDeviceToHost, ctx->stream));

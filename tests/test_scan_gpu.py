@@ -283,3 +283,34 @@ def test_empty_and_degenerate_inputs(ctx):
     with pytest.raises(mb.MB200Error) as e:
         ctx.seqs_from_onehot(onehot)
     assert e.value.code == mb._lib.E_BAD_SEQUENCE
+
+
+def test_asynchronous_upload_overlapping_the_scan(ctx):
+    """mb200_seqs_from_ascii_async: the scan may start on the first chunks while later ones are still being copied; results are
+    those of the blocking upload (1.2 M x 200 bp = 240 MB = four 64 MB chunks, several scan batches), bad symbols are reported by
+    the first consumer."""
+    N, Lb = 1_200_000, 200
+    a = synth.random_ascii(N, Lb, 11)
+    ms = synth.motifs_from_count_matrices(synth.random_count_matrices(40, 8, 30, 3))
+    pw, lens = so.pack_pwms(ms.pwms)
+    thr = synth.stated_thresholds(ms, 0.6)
+    s1 = ctx.seqs_from_ascii(a)
+    _, c1 = ctx.scan(s1, pw, lens, thr, want_hits=False, want_counts=True)
+    s2 = ctx.seqs_from_host_ptr(a.ctypes.data, N, Lb, wait=False)
+    _, c2 = ctx.scan(s2, pw, lens, thr, want_hits=False, want_counts=True)
+    assert np.array_equal(c1, c2)
+    assert np.array_equal(s1.download(), s2.download())
+    s3 = ctx.seqs_from_host_ptr(a.ctypes.data, N, Lb, wait=False)           # no scan: wait() completes it
+    s3.wait()
+    assert np.array_equal(s3.download(), s1.download())
+    for s in (s1, s2, s3):
+        s.free()
+    b = a[:5000].copy()
+    b[4321, 77] = ord("N")
+    s4 = ctx.seqs_from_host_ptr(b.ctypes.data, 5000, Lb, wait=False)
+    with pytest.raises(mb.MB200Error) as e:
+        ctx.scan(s4, pw, lens, thr, want_hits=False, want_counts=True)
+    assert e.value.code == mb._lib.E_BAD_SEQUENCE
+    s4.free()
+    s5 = ctx.seqs_from_host_ptr(b.ctypes.data, 5000, Lb, wait=False)
+    s5.free()                                                               # freeing a pending upload is safe
