@@ -268,3 +268,29 @@ def test_batched_layout_matches_single_batch_layout(ctx):
     for m in (mG, m1, fG, f1):
         m.free()
     seqs.free()
+
+
+@pytest.mark.parametrize("hpd,Lb,G", [
+    (dict(filter_len=4, M=5, h=3, K=4, q=3, batch_size=3, num_pass_xyz=2, num_pass_df=2), 31, 1),      # tiny, every generic kernel
+    (dict(filter_len=6, M=70, h=5, K=10, q=7, batch_size=4, num_pass_xyz=3, num_pass_df=2), 60, 1),    # M > 64, K != 24, f_len = 24
+    (dict(filter_len=8, M=20, h=12, K=24, q=16, batch_size=2, num_pass_xyz=2, num_pass_df=1), 50, 12), # batched kernels, odd sizes
+])
+def test_non_default_hyperparameters_match_oracle(ctx, hpd, Lb, G):
+    """shapes other than the reference's defaults take the generic kernels (k_corr2d, k_dgrad, ...) or the batched ones with other
+    tile counts: same bar as the default shape."""
+    hp = mdl.Hyperparam(**hpd)
+    hp_, ohp, a, seqs, flat = _setup(ctx, hp.batch_size * G + 5, Lb, 17, hp=hp)
+    m = mb._lib.CscModel(ctx, hp, Lb, n_groups=G)
+    m.set_params(flat)
+    assert m.n_trainable == co.n_params(ohp)
+    idx = np.random.default_rng(3).permutation(hp.batch_size * G + 5)[: hp.batch_size * G]
+    loss, g = m.loss_grad(seqs, idx)
+    og_sum = np.zeros_like(g, dtype=np.float64)
+    codes = so.ascii_to_codes(a)
+    for k in range(G):
+        oloss, og, aux = co.loss_and_grad(codes[idx[k * hp.batch_size:(k + 1) * hp.batch_size]], flat, ohp)
+        assert loss[k, 0] == pytest.approx(oloss, rel=1e-5), k
+        og_sum += og[: m.n_trainable]
+    og_mean = og_sum / G
+    assert np.abs(g - og_mean).max() <= 2e-4 * np.abs(og_mean).max()
+    m.free(); seqs.free()
