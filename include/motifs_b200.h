@@ -188,6 +188,13 @@ typedef struct { uint32_t motif, seq, pos, comp; } mb200_site;   /* 0-based; com
 int32_t mb200_count_matrices(mb200_ctx* ctx, const mb200_seqs* seqs, const mb200_site* sites, int64_t n_sites,
                              const int64_t* lens, int32_t K, int32_t maxlen, uint32_t* counts);
 
+/* ---- score threshold from a p-value: replaces pvalue2score (inference/_h2_Touzet.jl:170-187, with min_score_range, round_pwm,
+ *      best_score / worst_score, create_Q, find_largest_alpha :1-168).  Host-side Float64 DP, bit-identical to the reference's
+ *      order of additions.  pwm: 4 x m row-major (row = base A,C,G,T); bg: 4 background frequencies; eps: granularity (1e-1 in
+ *      _0_const.jl).  *found = 0 when no score qualifies (the reference returns `nothing`).                  */
+int32_t mb200_pvalue2score(mb200_ctx* ctx, const double* pwm, int32_t m, double pval, double eps, const double* bg,
+                           double* score, int32_t* found);
+
 /* ---- code components -> triplet dictionary: replaces get_scanning_range_of_filtered_code_components, enumerate_triplets /
  *      insert_H! (inference/_2_enumerate.jl:25-65) and the key counting of get_words / get_enriched_keys
  *      (inference/_3_make_pfms.jl:3-26).  A key is f1 | f2<<8 | f3<<16 | d12<<24 | d13<<40 with 1-based filter ids (the fields of

@@ -159,4 +159,15 @@ function triplets_values(ctx, t, keys::Vector{KeyCount})
     H
 end
 
+# Drop-in for pvalue2score (inference/_h2_Touzet.jl:170-187): returns `nothing` when no score qualifies.
+function pvalue2score(pwm::AbstractMatrix, pval::Real, eps::Real=1e-1; bg=[.25, .25, .25, .25])
+    rowmajor = collect(Float64, permutedims(pwm))            # C side reads 4 x m row-major = Julia (m,4) column-major
+    bg64 = collect(Float64, bg); score = Ref{Float64}(0.0); found = Ref{Int32}(0)
+    rc = GC.@preserve rowmajor bg64 ccall((:mb200_pvalue2score, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int32, Float64, Float64, Ptr{Float64}, Ref{Float64}, Ref{Int32}),
+        C_NULL, rowmajor, size(pwm, 2), pval, eps, bg64, score, found)
+    rc == 0 || error("mb200_pvalue2score failed ($rc)")
+    return found[] == 0 ? nothing : score[]
+end
+
 end # module

@@ -91,6 +91,7 @@ def load():
         "mb200_csc_median_mask": (i32, [p, p, p, p, p, p]),
         "mb200_csc_codes": (i32, [p, p, p, i64, i64, p, i64, C.POINTER(i64)]),
         "mb200_count_matrices": (i32, [p, p, p, i64, p, i32, i32, p]),
+        "mb200_pvalue2score": (i32, [p, p, i32, C.c_double, C.c_double, p, p, p]),
         "mb200_triplets_create": (i32, [p, p, p, p, i64, p, p, p]),
         "mb200_triplets_destroy": (i32, [p, p]),
         "mb200_triplets_ranges": (i32, [p, p, p, p]),
@@ -373,6 +374,20 @@ class CscModel:
         n = C.c_int64()
         self.ctx._check(self.ctx._lib.mb200_csc_codes(self.ctx._h, self._h, seqs._h, int(first_seq), int(n_seqs), _ptr(out), cap, C.byref(n)))
         return out[: n.value]
+
+
+def pvalue2score(ctx: "Context", pwm, pval, eps, bg):
+    """mb200_pvalue2score: Touzet p-value -> score of a (4, m) PWM segment in Float64; None when no score qualifies."""
+    p = np.ascontiguousarray(pwm, np.float64)
+    b = np.ascontiguousarray(bg, np.float64)
+    score, found = C.c_double(), C.c_int32()
+    if ctx is None:                                     # host arithmetic only: usable without a context
+        rc = load().mb200_pvalue2score(None, _ptr(p), p.shape[1], float(pval), float(eps), _ptr(b), C.byref(score), C.byref(found))
+        if rc != 0:
+            raise ValueError(f"mb200_pvalue2score failed ({rc})")
+    else:
+        ctx._check(ctx._lib.mb200_pvalue2score(ctx._h, _ptr(p), p.shape[1], float(pval), float(eps), _ptr(b), C.byref(score), C.byref(found)))
+    return score.value if found.value else None
 
 
 class Triplets:

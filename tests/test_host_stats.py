@@ -27,6 +27,25 @@ def test_pvalue2score_bitwise(seed):
             assert inf.pvalue2score(p, pval, bg=bg) == st.pvalue2score(p, pval, bg=bg)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_library_pvalue2score_bitwise(seed):
+    """mb200_pvalue2score (csrc/touzet.cu, host arithmetic, no device) against the oracle: identical Float64 bits, incl. -Inf
+    entries, a non-uniform background, and the `nothing` case."""
+    from motifs_jl_b200 import _lib
+    ms = synth.motifs_from_count_matrices(synth.random_count_matrices(4, 2, 15, seed))
+    bgs = (np.full(4, 0.25, np.float32), np.array([0.31, 0.19, 0.21, 0.29], np.float32))
+    for p in ms.pwms:
+        for pval in (3e-4, 1e-4, 1e-2, 0.0, 1.0):
+            for bg in bgs:
+                assert _lib.pvalue2score(None, p, pval, 1e-1, bg) == st.pvalue2score(p, pval, bg=bg)
+    p = np.array(ms.pwms[0], np.float16).copy()
+    p[2, 1] = -np.inf
+    assert _lib.pvalue2score(None, p, 3e-4, 1e-1, bgs[0]) == st.pvalue2score(p, 3e-4, bg=bgs[0])
+    assert _lib.pvalue2score(None, p, 0.5, 1e-2, bgs[1]) == st.pvalue2score(p, 0.5, eps=1e-2, bg=bgs[1])
+    with pytest.raises(ValueError):
+        _lib.pvalue2score(None, p, 1.5, 1e-1, bgs[0])
+
+
 def test_fisher_right_vs_scipy():
     rng = np.random.default_rng(0)
     for _ in range(200):
