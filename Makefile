@@ -5,6 +5,9 @@ PKG       := motifs.jl_b200
 CSRC      := $(PKG)/csrc
 LIB       := $(PKG)/lib/libmotifs_b200.so
 NVFLAGS   := -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xcompiler -Wall
+ifdef TCS_PROFILE
+NVFLAGS   += -DTCS_PROFILE=1
+endif
 CU        := $(wildcard $(CSRC)/*.cu)
 HDR       := $(wildcard $(CSRC)/*.cuh) include/motifs_b200.h
 

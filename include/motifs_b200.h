@@ -94,6 +94,7 @@ typedef struct {
 #define MB200_SCAN_RC           0x2u   /* score with reverse(pwm)        (rc=true pass)       */
 #define MB200_SCAN_WANT_HITS    0x4u
 #define MB200_SCAN_WANT_COUNTS  0x8u
+#define MB200_SCAN_NO_TENSOR    0x10u  /* thresholded scans: keep the SIMT kernel (default: tcgen05 pre-filter + exact re-scoring, same hit sets) */
 
 /* pwms_f16 : Float16 bits, Julia column-major (K,4,maxlen) exactly as built at
  *            _h3_1_alignment.jl:66-69 with rc=false (element (k,a,ind) at k + K*(a + 4*ind));
@@ -111,6 +112,9 @@ int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs,
                    const uint16_t* pwms_f16, const int64_t* lens, int32_t K, int32_t maxlen,
                    const uint16_t* thresh_f16, uint32_t flags,
                    mb200_hit* hits, int64_t hits_cap, int64_t* n_hits, int64_t* counts);
+/* which kernel family the last mb200_scan of this ctx used: 0 = scan_kernel (SIMT), 1 = tcgen05 pre-filter + exact re-scoring
+ * (thresholded scans, default), 2 = started on the tensor-core path and fell back to scan_kernel (candidate list overflow). */
+int32_t mb200_scan_last_path(const mb200_ctx* ctx);
 
 /* Score histogram of the unthresholded scan (hits = score > 0): hist[k*32768 + b] = number of hits of motif k whose Float16
  * score has the 15-bit pattern b (positive halves order like their bit patterns).  Replaces the hit lists as the input of the

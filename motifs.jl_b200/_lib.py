@@ -24,7 +24,7 @@ class MB200Error(RuntimeError):
 
 
 OK, E_INVALID, E_CUDA, E_NOMEM, E_BAD_SEQUENCE, E_HITS_OVERFLOW, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
-SCAN_FWD, SCAN_RC, SCAN_WANT_HITS, SCAN_WANT_COUNTS = 1, 2, 4, 8
+SCAN_FWD, SCAN_RC, SCAN_WANT_HITS, SCAN_WANT_COUNTS, SCAN_NO_TENSOR = 1, 2, 4, 8, 16
 MAX_MOTIF_LEN = 64
 
 HIT_DTYPE = np.dtype([("seq", "<u4"), ("pos", "<u4"), ("motif", "<u2"), ("score_f16", "<u2"),
@@ -75,6 +75,7 @@ def load():
         "mb200_seqs_shape": (i32, [p, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
         "mb200_seqs_download": (i32, [p, p, p, i64]),
         "mb200_scan": (i32, [p, p, p, p, i32, i32, p, C.c_uint32, p, i64, C.POINTER(i64), p]),
+        "mb200_scan_last_path": (i32, [p]),
         "mb200_scan_hist": (i32, [p, p, p, p, i32, i32, C.c_uint32, p]),
         "mb200_csc_create": (i32, [p, C.POINTER(HParams), i64, i32, i32, C.POINTER(p)]),
         "mb200_csc_destroy": (i32, [p, p]),
@@ -182,9 +183,10 @@ class Context:
 
     # ---- scan --------------------------------------------------------------------------------
     def scan(self, seqs: "Sequences", pwms_f16: np.ndarray, lens, thresh_f16=None, *, fwd=True, rc=True,
-             want_hits=True, want_counts=True, hits_cap=None):
+             want_hits=True, want_counts=True, hits_cap=None, tensor=True):
         """pwms_f16: (K, 4, maxlen) array in Julia memory order, i.e. numpy shape (maxlen, 4, K) C-order
-        holding float16 (or uint16 bits).  Returns (hits structured array | None, counts (K,4) int64 | None)."""
+        holding float16 (or uint16 bits).  Returns (hits structured array | None, counts (K,4) int64 | None).
+        tensor=False keeps a thresholded scan on the SIMT kernel (MB200_SCAN_NO_TENSOR); results are identical either way."""
         pw = np.ascontiguousarray(pwms_f16)
         if pw.dtype == np.float16:
             pw = pw.view(np.uint16)
@@ -202,7 +204,7 @@ class Context:
             if th.dtype != np.uint16 or th.shape != (K,):
                 raise ValueError("thresh_f16 must be K float16/uint16 values")
         flags = (SCAN_FWD if fwd else 0) | (SCAN_RC if rc else 0) | (SCAN_WANT_HITS if want_hits else 0) | \
-                (SCAN_WANT_COUNTS if want_counts else 0)
+                (SCAN_WANT_COUNTS if want_counts else 0) | (0 if tensor else SCAN_NO_TENSOR)
         counts = np.zeros((K, 4), np.int64) if want_counts else None
         n_hits = C.c_int64(0)
         cap = int(hits_cap) if hits_cap is not None else (1 << 16)
@@ -217,6 +219,12 @@ class Context:
             self._check(rc_)
             break
         return (hits[: n_hits.value] if want_hits else None), counts
+
+
+def scan_last_path(ctx: "Context") -> int:
+    """0: the last mb200_scan ran scan_kernel (SIMT), 1: tensor-core pre-filter + exact re-scoring, 2: started on the tensor-core
+    path and fell back (candidate list overflow)."""
+    return int(ctx._lib.mb200_scan_last_path(ctx._h))
 
 
 def count_matrices(ctx: "Context", seqs: "Sequences", sites, lens):

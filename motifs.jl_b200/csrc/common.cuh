@@ -24,8 +24,10 @@ struct mb200_ctx {
     cudaEvent_t ev[2 * T_N] = {nullptr};      // start/stop per slot
     // grow-only device buffers reused across calls (slot 0 = generic scratch)
     void* scratch = nullptr; size_t scratch_bytes = 0;
-    void* bufs[8] = {nullptr}; size_t buf_bytes[8] = {0};
+    void* bufs[12] = {nullptr}; size_t buf_bytes[12] = {0};
     void* pinned = nullptr;  size_t pinned_bytes = 0;
+    int last_scan_path = 0;                   // mb200_scan_last_path
+    size_t mask_clean_bytes = 0;              // leading bytes of bufs[2] (hit masks) known to be zero (tensor-core scan path)
 };
 
 struct mb200_seqs {

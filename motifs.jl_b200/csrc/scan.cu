@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
+#include <cmath>
 
 #define GROUP_MOTIFS 16                // motifs per warp pass
 #define GROUP_SLOTS 32                 // (motif, strand) slots = lanes
@@ -373,29 +374,24 @@ __device__ __forceinline__ uint32_t dilate32(uint32_t u, int len) {
     return r;
 }
 
-__global__ void __launch_bounds__(256) count_kernel(const uint32_t* __restrict__ mask, int64_t nseq, int32_t W, int32_t K2pad,
-                                                    const int32_t* __restrict__ pair2motif, const int32_t* __restrict__ pairlen,
-                                                    unsigned long long* __restrict__ counts, uint32_t* __restrict__ unit_cnt, int32_t K) {
-    const int32_t P = K2pad / 2;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nseq * P) return;
-    const int64_t n = t / P;
-    const int32_t m2 = (int32_t)(t - n * P);
-    const int32_t k = pair2motif[m2];
-    if (k < 0) return;
-    const int32_t len = pairlen[m2];
-    const uint2* mp = reinterpret_cast<const uint2*>(mask) + (n * W) * (int64_t)P + m2;
+// counts of one (sequence, motif) unit from its W mask words of both strands; CLEAR: leave the words zero behind (the tensor-core
+// path keeps the mask buffer all-zero between batches instead of clearing 8 GB per batch)
+template <bool CLEAR>
+__device__ __forceinline__ void count_unit(uint32_t* __restrict__ mask, int64_t n, int32_t m2, int32_t W, int32_t P, int32_t k, int32_t len,
+                                           unsigned long long* __restrict__ counts, uint32_t* __restrict__ unit_cnt, int32_t K) {
+    uint2* mp = reinterpret_cast<uint2*>(mask) + (n * W) * (int64_t)P + m2;
     uint32_t nf = 0, nr = 0, uq = 0, cov = 0;
     int32_t cu = 0;             // positions < cu are covered by earlier hits
     int32_t p1 = -1, p2 = -1;   // largest / second largest distinct start position
     bool dup = false;           // p1 hit on both strands
     for (int32_t w = 0; w < W; ++w) {
-        const uint2 fr = __ldg(mp + (int64_t)w * P);
+        const uint2 fr = CLEAR ? mp[(int64_t)w * P] : __ldg(mp + (int64_t)w * P);
         const uint32_t f = fr.x, r = fr.y, U = f | r;
         const int32_t base = w * 32;
         const int32_t cb = cu - base;
         uint32_t cm = cb >= 32 ? 0xffffffffu : (cb > 0 ? ((1u << cb) - 1u) : 0u);
         if (U) {
+            if (CLEAR) mp[(int64_t)w * P] = make_uint2(0u, 0u);
             nf += __popc(f); nr += __popc(r); uq += __popc(U);
             cm |= dilate32(U, len);
             const int32_t hi = 31 - __clz(U);
@@ -419,6 +415,34 @@ __global__ void __launch_bounds__(256) count_kernel(const uint32_t* __restrict__
         atomicAdd(&counts[k * 4 + 1], (unsigned long long)uq);
         atomicAdd(&counts[k * 4 + 2], (unsigned long long)covq);
         atomicAdd(&counts[k * 4 + 3], (unsigned long long)cov);
+    }
+}
+
+__global__ void __launch_bounds__(256) count_kernel(const uint32_t* __restrict__ mask, int64_t nseq, int32_t W, int32_t K2pad,
+                                                    const int32_t* __restrict__ pair2motif, const int32_t* __restrict__ pairlen,
+                                                    unsigned long long* __restrict__ counts, uint32_t* __restrict__ unit_cnt, int32_t K) {
+    const int32_t P = K2pad / 2;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nseq * P) return;
+    const int64_t n = t / P;
+    const int32_t m2 = (int32_t)(t - n * P);
+    const int32_t k = pair2motif[m2];
+    if (k < 0) return;
+    count_unit<false>(const_cast<uint32_t*>(mask), n, m2, W, P, k, pairlen[m2], counts, unit_cnt, K);
+}
+
+// Sparse form for the tensor-core path: one thread per (sequence, motif) unit that received at least one hit (the verifier lists
+// them); all other units have no hits and contribute nothing.  Clears the words it reads.
+__global__ void __launch_bounds__(256) count_listed_kernel(uint32_t* __restrict__ mask, const uint32_t* __restrict__ units, const unsigned long long* __restrict__ n_units,
+                                                           int32_t W, int32_t K2pad, const int32_t* __restrict__ pair2motif, const int32_t* __restrict__ pairlen,
+                                                           unsigned long long* __restrict__ counts) {
+    const int32_t P = K2pad / 2;
+    const unsigned long long total = *n_units;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t g = units[i];
+        const int64_t n = g / (uint32_t)P;
+        const int32_t m2 = (int32_t)(g - (uint32_t)n * (uint32_t)P);
+        count_unit<true>(mask, n, m2, W, P, pair2motif[m2], pairlen[m2], counts, nullptr, 0);
     }
 }
 
@@ -671,6 +695,164 @@ struct ScanPlan {
     int minlen = 0;
 };
 
+#include "scan_tc.cuh"
+
+// ---- host side of the tensor-core pre-filter (scan_tc.cuh) ------------------------------------------------------------
+static inline uint16_t float_to_h16(float f) { __half h = __float2half_rn(f); __half_raw r = h; return r.x; }
+static inline uint16_t h16_nextup(uint16_t h) { if (h == 0x8000u) return 0x0001u; return (h & 0x8000u) ? (uint16_t)(h - 1) : (uint16_t)(h + 1); }
+// smallest Float16 >= x (|x| well inside the Float16 range)
+static inline uint16_t h16_round_up(double x) {
+    uint16_t h = float_to_h16((float)x);
+    while ((double)h16_to_float(h) < x) h = h16_nextup(h);
+    return h;
+}
+// E with |Float16 running sum - real sum| <= E for every path through the columns w[j][0..3] whose Float16 running sum ends above t.
+//   U_j = fl16(U_{j-1} + max_b w[j][b])  bounds every partial sum from above (rounding is monotone);
+//   for paths ending above t:  s_{j-1} >= L_{j-1} = L_j - max_b w[j][b] - u*B_j,  L_n = t,  B_j = max(|L_j|, |U_j|) >= |s_j|;
+//   each add errs by at most u*|s_j|, u = 2^-11 (results in the subnormal range are exact).  Returns false when U_n <= t (no hit possible).
+static bool tc_error_bound(const std::vector<double>& w, int n, double t, double* E_out) {
+    const double u = 1.0 / 2048.0;
+    std::vector<double> U(n + 1, 0.0), mx(n + 1, 0.0);
+    for (int j = 1; j <= n; ++j) {
+        double m = w[(size_t)(j - 1) * 4];
+        for (int b = 1; b < 4; ++b) m = std::max(m, w[(size_t)(j - 1) * 4 + b]);
+        mx[j] = m;
+        U[j] = (double)h16_to_float(float_to_h16((float)(U[j - 1] + m)));     // the sum of two halves is exact in float: one rounding
+    }
+    if (!(U[n] > t)) return false;
+    double L = t, E = 0.0;
+    for (int j = n; j >= 1; --j) {
+        const double B = std::max(std::fabs(L), std::fabs(U[j]));
+        E += u * B;
+        L = L - mx[j] - u * B;
+    }
+    *E_out = E * 1.001 + 1e-6;
+    return true;
+}
+
+// CTAs of the grid over slot blocks in proportion to cost (clocks per tile); every block gets at least one.
+static bool tc_assign_ctas(std::vector<TcBlock>& blocks, const std::vector<double>& cost, int grid) {
+    const int nblocks = (int)blocks.size();
+    if (nblocks > grid) return false;
+    double csum = 0; for (double c : cost) csum += c;
+    std::vector<int> n(nblocks);
+    int used = 0;
+    for (int bi = 0; bi < nblocks; ++bi) { n[bi] = std::max(1, (int)(grid * cost[bi] / csum)); used += n[bi]; }
+    while (used > grid) {                                         // take from the block with the least cost per CTA
+        int w = -1;
+        for (int bi = 0; bi < nblocks; ++bi) if (n[bi] > 1 && (w < 0 || cost[bi] / n[bi] < cost[w] / n[w])) w = bi;
+        if (w < 0) return false;
+        --n[w]; --used;
+    }
+    while (used < grid) {                                         // give to the block with the most cost per CTA
+        int w = 0;
+        for (int bi = 1; bi < nblocks; ++bi) if (cost[bi] / n[bi] > cost[w] / n[w]) w = bi;
+        ++n[w]; ++used;
+    }
+    int c0 = 0;
+    for (int bi = 0; bi < nblocks; ++bi) { blocks[bi].cta0 = c0; blocks[bi].nctas = n[bi]; c0 += n[bi]; }
+    return true;
+}
+
+struct TcPlan {
+    std::vector<uint8_t> blob;
+    std::vector<TcBlock> blocks;
+    std::vector<TcSlot> slots;
+    int max_kchunks = 0;
+};
+
+// false: this call is not eligible for the tensor-core path (the caller keeps scan_kernel).
+static bool build_tc_plan(const ScanPlan& P, const uint16_t* pwms, const int64_t* lens, int K, const uint16_t* thresh, uint32_t flags,
+                          int64_t Lb, int grid, TcPlan& T) {
+    if (!thresh || !P.lblocks.empty()) return false;
+    const int nslots = (P.K2pad + TCS_N - 1) / TCS_N * TCS_N;
+    const int nblocks = nslots / TCS_N;
+    if (nblocks > grid) return false;
+    auto pw = [&](int k, int a, int ind) -> uint16_t { return pwms[(size_t)k + (size_t)K * ((size_t)a + 4 * (size_t)ind)]; };
+    TcSlot off; memset(&off, 0, sizeof off); off.motif = -1; off.thr = 0x7C00u;
+    T.slots.assign(nslots, off);
+    std::vector<std::vector<uint16_t>> col0(nslots);              // per slot: the B entries [len][4] (column 0 already holds w - T')
+    std::vector<int> blen(nblocks, 0);
+    for (int k = 0; k < K; ++k) {
+        const int len = (int)lens[k];
+        if (len > MB200_MAX_MOTIF_LEN) return false;
+        bool neg_inf = false;
+        for (int j = 0; j < len; ++j)
+            for (int b = 0; b < 4; ++b) {
+                const uint16_t v = pw(k, b, j);
+                if (h16_nonfinite(v)) { if (v == 0xFC00u) neg_inf = true; else return false; }     // +Inf / NaN entries: leave it to scan_kernel
+            }
+        const uint16_t raw = thresh[k];
+        if (h16_nonfinite(raw) && (raw & 0x03FFu)) continue;       // NaN threshold: never a hit
+        if (raw == 0x7C00u) continue;                              // +Inf threshold: never a hit
+        const uint16_t tb = h16_to_float(raw) > 0.f ? raw : (uint16_t)0;
+        const double t = (double)h16_to_float(tb);
+        if (neg_inf) continue;                                     // a -Inf entry makes every window -Inf or NaN (0 * -Inf): never a hit
+        for (int strand = 0; strand < 2; ++strand) {
+            if (!(flags & (strand ? MB200_SCAN_RC : MB200_SCAN_FWD))) continue;
+            const int slot = P.em[k].slot + strand;
+            std::vector<double> w((size_t)len * 4);
+            double A = 0.0;
+            for (int j = 0; j < len; ++j) {
+                double am = 0.0;
+                for (int b = 0; b < 4; ++b) {
+                    const uint16_t v = strand ? pw(k, 3 - b, len - 1 - j) : pw(k, b, j);
+                    w[(size_t)j * 4 + b] = (double)h16_to_float(v);
+                    am = std::max(am, std::fabs(w[(size_t)j * 4 + b]));
+                }
+                A += am;
+            }
+            double E = 0.0;
+            if (!tc_error_bound(w, len, t, &E)) continue;          // the best window cannot exceed the threshold
+            // FP32 accumulation in the tensor core (operands exact, possibly truncating adds, subnormal operands possibly flushed)
+            const double eps32 = (A + std::fabs(t) + E) * (1.0 / 8192.0) + len * 6.2e-5;
+            const double Tp = t - E - eps32;
+            if (A + std::fabs(Tp) > 30000.0) return false;
+            TcSlot sl; memset(&sl, 0, sizeof sl);
+            sl.motif = k; sl.strand = strand; sl.len = len; sl.npos = (int32_t)std::max<int64_t>(0, Lb - len + 1); sl.thr = tb;
+            T.slots[slot] = sl;
+            std::vector<uint16_t>& c = col0[slot];
+            c.resize((size_t)len * 4);
+            for (int j = 0; j < len; ++j)
+                for (int b = 0; b < 4; ++b) {
+                    const uint16_t v = strand ? pw(k, 3 - b, len - 1 - j) : pw(k, b, j);
+                    c[(size_t)j * 4 + b] = j == 0 ? h16_round_up(w[b] - Tp) : v;          // D > 0  <=>  real sum > T' (or a little less)
+                }
+            blen[slot / TCS_N] = std::max(blen[slot / TCS_N], len);
+        }
+    }
+    // B operands: [block][kchunk][256 slots][8 halves]; half e of chunk c = column 2c + e/4, base e%4
+    size_t total = 0;
+    std::vector<double> cost(nblocks);
+    for (int bi = 0; bi < nblocks; ++bi) {
+        TcBlock tb; memset(&tb, 0, sizeof tb);
+        int kc = (std::max(blen[bi], 1) + 1) / 2;
+        kc = std::max(2, (kc + 1) & ~1);
+        tb.kchunks = kc; tb.slot0 = bi * TCS_N; tb.b_off = (int64_t)total;
+        total += (size_t)kc * TCS_N * 16;
+        T.max_kchunks = std::max(T.max_kchunks, kc);
+        cost[bi] = std::max(kc * 64.0, 600.0) + 100.0;              // MMA clocks (128 per K=16 step) or the epilogue, whichever binds
+        T.blocks.push_back(tb);
+    }
+    T.blob.assign(total, 0);
+    for (int bi = 0; bi < nblocks; ++bi) {
+        uint16_t* Bm = reinterpret_cast<uint16_t*>(T.blob.data() + T.blocks[bi].b_off);
+        for (int sidx = 0; sidx < TCS_N; ++sidx) {
+            const int slot = bi * TCS_N + sidx;
+            const std::vector<uint16_t>& c = col0[slot];
+            if (c.empty()) {                                       // disabled slot: D = -1 everywhere
+                for (int b = 0; b < 4; ++b) Bm[((size_t)0 * TCS_N + sidx) * 8 + b] = 0xBC00u;
+                T.slots[slot].npos = 0;
+                continue;
+            }
+            const int len = (int)c.size() / 4;
+            for (int j = 0; j < len; ++j)
+                for (int b = 0; b < 4; ++b) Bm[((size_t)(j >> 1) * TCS_N + sidx) * 8 + 4 * (j & 1) + b] = c[(size_t)j * 4 + b];
+        }
+    }
+    return tc_assign_ctas(T.blocks, cost, grid);
+}
+
 static int build_plan(mb200_ctx* ctx, const uint16_t* pwms, const int64_t* lens, int K, int maxlen, const uint16_t* thresh,
                       uint32_t flags, int64_t Lb, size_t table_budget, double gather_frac, ScanPlan& P) {
     P.K = K;
@@ -829,6 +1011,13 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
     if (gather_warps <= 0 || gather_warps >= SCAN_THREADS / 32) { gather_frac = gather_warps <= 0 ? 0.0 : 1.0; gather_warps = 8; }
     int rc = build_plan(ctx, pwms_f16, lens, K, maxlen, thresh_f16, flags, Lb, table_budget, gather_frac, P);
     if (rc) return rc;
+    // Thresholded scans take the tensor-core pre-filter + exact verification (scan_tc.cuh) unless the caller or the inputs rule
+    // it out; the hit masks, and everything derived from them, are identical either way.
+    TcPlan TP;
+    bool use_tc = !(flags & MB200_SCAN_NO_TENSOR) && !hist && Lb < (1ll << 31);
+    if (const char* e = getenv("MB200_SCAN_TC")) use_tc = use_tc && atoi(e) != 0;
+    if (use_tc) use_tc = build_tc_plan(P, pwms_f16, lens, K, thresh_f16, flags, Lb, ctx->sm_count, TP);
+    ctx->last_scan_path = 0;
     const int64_t npos_max = Lb - P.minlen + 1;
     if (N == 0 || npos_max <= 0) return MB200_OK;       // nothing can be scored
     const int64_t W64 = (npos_max + 31) / 32;                      // 32-position mask words per sequence
@@ -865,6 +1054,39 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
     int64_t seqs_per_batch = std::max<int64_t>(1, (int64_t)(mask_budget / mask_bytes_per_seq));
     if (seqs_per_batch > N) seqs_per_batch = N;
     if ((double)seqs_per_batch * W > 2.0e9) seqs_per_batch = std::max<int64_t>(1, (int64_t)(2.0e9 / W));
+    if (use_tc && (double)seqs_per_batch * (double)Lb > 2.0e9) seqs_per_batch = std::max<int64_t>(1, (int64_t)(2.0e9 / (double)Lb));   // 32-bit virtual positions
+    // tensor-core path: plan (B operands, blocks, slots) in buf 8, candidate list + counters in buf 9
+    const unsigned long long tc_cap = (unsigned long long)32 << 20;
+    const bool tc_sparse = !want_hits && !hist && W <= 4096;        // counts only: count the units the verifier lists, never walk (or clear) the whole mask
+    size_t tc_off_blocks = 0, tc_off_slots = 0, tc_smem = 0;
+    uint8_t* d_tc = nullptr; unsigned long long* d_tc_list = nullptr; unsigned long long* d_tc_ctr = nullptr;     // ctr: [0] reserved, [1] overflow, [2] candidates, [3] hits, [4] listed units, [8..] clocks per CTA
+    uint32_t* d_tc_ulist = nullptr; uint32_t* d_tc_ubits = nullptr; unsigned long long tc_stat_cand = 0, tc_stat_hits = 0;
+    if (use_tc) {
+        tc_off_blocks = (TP.blob.size() + 255) & ~(size_t)255;
+        tc_off_slots = tc_off_blocks + ((TP.blocks.size() * sizeof(TcBlock) + 255) & ~(size_t)255);
+        const size_t tc_bytes = tc_off_slots + TP.slots.size() * sizeof(TcSlot);
+        rc = mb_ensure_buf(ctx, 8, tc_bytes); if (rc) return rc;
+        rc = mb_ensure_buf(ctx, 9, (size_t)tc_cap * 8 + (size_t)(8 + 2 * ctx->sm_count) * 8 + 256); if (rc) return rc;
+        d_tc = (uint8_t*)ctx->bufs[8];
+        d_tc_list = (unsigned long long*)ctx->bufs[9];
+        d_tc_ctr = d_tc_list + tc_cap;
+        // (sequence, motif) units with hits: list + bitmap (buf 10), for the sparse counting kernel
+        const size_t ubits_bytes = (((size_t)seqs_per_batch * (size_t)(P.K2pad / 2) + 31) / 32) * 4 + 256;
+        rc = mb_ensure_buf(ctx, 10, (size_t)tc_cap * 4 + ubits_bytes); if (rc) return rc;
+        d_tc_ulist = (uint32_t*)ctx->bufs[10];
+        d_tc_ubits = d_tc_ulist + tc_cap;
+        std::vector<uint8_t> h_tc(tc_bytes, 0);
+        memcpy(h_tc.data(), TP.blob.data(), TP.blob.size());
+        memcpy(h_tc.data() + tc_off_blocks, TP.blocks.data(), TP.blocks.size() * sizeof(TcBlock));
+        memcpy(h_tc.data() + tc_off_slots, TP.slots.data(), TP.slots.size() * sizeof(TcSlot));
+        MB_CUDA(ctx, cudaMemcpyAsync(d_tc, h_tc.data(), tc_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        MB_CUDA(ctx, cudaMemsetAsync(d_tc_ctr, 0, (size_t)(8 + 2 * ctx->sm_count) * 8, ctx->stream));
+        MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));           // h_tc goes out of scope
+        // at least half of the shared memory: one CTA per SM (each CTA allocates all 512 TMEM columns)
+        tc_smem = std::max<size_t>((size_t)TCS_STAGES * TCS_STAGE_BYTES + (size_t)TP.max_kchunks * TCS_N * 16, (size_t)120 * 1024);
+        if (tc_smem > ctx->smem_optin) use_tc = false;
+        else MB_CUDA(ctx, cudaFuncSetAttribute(k_scan_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+    }
     rc = mb_ensure_buf(ctx, 2, (size_t)seqs_per_batch * mask_bytes_per_seq); if (rc) return rc;
     uint32_t* d_mask = (uint32_t*)ctx->bufs[2];
     uint32_t* d_unit_cnt = nullptr; unsigned long long* d_unit_off = nullptr; unsigned long long* d_bsum = nullptr;
@@ -952,12 +1174,75 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
         a.tile_chunks = tile_chunks; a.ntiles = ntiles; a.tile_cap_words = tile_cap_words; a.blob_cap_bytes = blob_cap;
         a.cta_range = d_rng; a.gather_warps = gather_warps;
         int t1 = tm.begin(T_SCAN);
+        bool tc_done = false;
+        if (use_tc) {
+            const size_t need = (size_t)ns * mask_bytes_per_seq;
+            if (ctx->mask_clean_bytes < need) {                      // the buffer is kept all-zero between tensor-core batches (count_listed_kernel clears what it reads)
+                MB_CUDA(ctx, cudaMemsetAsync(d_mask, 0, need, ctx->stream));
+                ctx->mask_clean_bytes = need;
+            }
+            MB_CUDA(ctx, cudaMemsetAsync(d_tc_ctr, 0, 64, ctx->stream));
+            if (tc_sparse) MB_CUDA(ctx, cudaMemsetAsync(d_tc_ubits, 0, (((size_t)ns * (size_t)(P.K2pad / 2) + 31) / 32) * 4, ctx->stream));
+            TcArgs ta;
+            ta.seqw = seqs->words; ta.rowwords = rowwords; ta.seq0 = s0;
+            ta.Lb = (uint32_t)Lb; ta.vtotal = (uint32_t)(ns * Lb);
+            ta.blob = d_tc; ta.blocks = (const TcBlock*)(d_tc + tc_off_blocks); ta.nblocks = (int32_t)TP.blocks.size();
+            ta.slots = (const TcSlot*)(d_tc + tc_off_slots);
+            ta.list = d_tc_list; ta.cap = tc_cap; ta.gcount = d_tc_ctr; ta.overflow = (uint32_t*)(d_tc_ctr + 1);
+            ta.ntiles = (int32_t)((ns * Lb + 255) / 256);
+            ta.clocks = (long long*)(d_tc_ctr + 8);
+            ta.dbg = nullptr;
+#if TCS_PROFILE
+            static long long* d_dbg = nullptr;
+            if (getenv("MB200_SCAN_TC_DEBUG")) { if (!d_dbg) cudaMalloc(&d_dbg, 148 * 8 * 8 * 2); cudaMemset(d_dbg, 0, 148 * 8 * 8); ta.dbg = d_dbg; }
+#endif
+            k_scan_tc<<<grid, TCS_THREADS, tc_smem, ctx->stream>>>(ta);
+            k_scan_tc_verify<<<grid * 8, 256, 0, ctx->stream>>>(d_tc_list, d_tc_ctr, tc_cap, ta.slots, (const EmitMotif*)(d_plan + off_em), d_plan + off_blob,
+                                                                 seqs->words, rowwords, s0, (uint32_t)Lb, W, P.K2pad, d_mask, d_tc_ctr + 2,
+                                                                 tc_sparse ? d_tc_ubits : nullptr, d_tc_ulist, d_tc_ctr + 4);
+            ctx->launches[T_SCAN] += 2;
+            MB_CUDA(ctx, cudaGetLastError());
+            std::vector<unsigned long long> h_ctr(8 + 2 * (size_t)grid, 0);
+            MB_CUDA(ctx, cudaMemcpyAsync(h_ctr.data(), d_tc_ctr, h_ctr.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+#if TCS_PROFILE
+            if (ta.dbg && s0 == 0) {
+                std::vector<long long> h(148 * 8);
+                cudaMemcpy(h.data(), ta.dbg, 148 * 8 * 8, cudaMemcpyDeviceToHost);
+                for (int c = 0; c < grid; c += 1)
+                    fprintf(stderr, "[tcdbg] cta %3d blk %lld tiles %lld | mma total %9lld wait_full %9lld wait_acc %9lld | epi total %9lld wait %9lld | prod wait %9lld\n", c, h[c * 8 + 6], h[c * 8 + 7],
+                            h[c * 8 + 0], h[c * 8 + 1], h[c * 8 + 2], h[c * 8 + 4], h[c * 8 + 3], h[c * 8 + 5]);
+            }
+#endif
+            if (!h_ctr[1] && s0 + ns < N) {
+                // re-balance the CTAs over the slot blocks with the clocks per tile this batch measured (the epilogue's share depends on
+                // the candidate density of the block, which no static model knows)
+                std::vector<double> cost(TP.blocks.size(), 0.0);
+                bool ok = true;
+                for (size_t bi = 0; bi < TP.blocks.size(); ++bi) {
+                    double clk = 0, tiles = 0;
+                    for (int c = TP.blocks[bi].cta0; c < TP.blocks[bi].cta0 + TP.blocks[bi].nctas; ++c) { clk += (double)h_ctr[8 + 2 * c]; tiles += (double)h_ctr[8 + 2 * c + 1]; }
+                    if (tiles <= 0 || clk <= 0) { ok = false; break; }
+                    cost[bi] = clk / tiles;
+                }
+                if (ok && tc_assign_ctas(TP.blocks, cost, grid))
+                    MB_CUDA(ctx, cudaMemcpyAsync(d_tc + tc_off_blocks, TP.blocks.data(), TP.blocks.size() * sizeof(TcBlock), cudaMemcpyHostToDevice, ctx->stream));
+            }
+            tc_stat_cand += h_ctr[2]; tc_stat_hits += h_ctr[3];
+            ctx->mask_clean_bytes = 0;                               // the verifier has set bits (re-established below when the sparse count clears them)
+            if (h_ctr[1]) { use_tc = false; ctx->last_scan_path = 2; }   // candidate list overflowed (thresholds too permissive): this and later batches take scan_kernel
+            else { tc_done = true; if (ctx->last_scan_path == 0) ctx->last_scan_path = 1; }
+        }
+        if (tc_done) { /* masks are complete */ }
+        else {
+        ctx->mask_clean_bytes = 0;
         if (!P.mblocks.empty()) { scan_kernel<<<grid, SCAN_THREADS, smem_bytes, ctx->stream>>>(a); ctx->launches[T_SCAN] += 1; }
         if (!P.lblocks.empty()) {
             const int64_t warps = ns * (int64_t)P.lblocks.size() * GROUP_SLOTS;
             scan_long_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, ctx->stream>>>(seqs->words, rowwords, s0, ns, W, P.K2pad, d_plan + off_blob,
                                                                                         (const MBlock*)(d_plan + off_lb), (int32_t)P.lblocks.size(), d_mask);
             ctx->launches[T_SCAN] += 1;
+        }
         }
         tm.end(t1);
         MB_CUDA(ctx, cudaGetLastError());
@@ -980,6 +1265,11 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
             count_long_c<<<(unsigned)((ns * Pp + 255) / 256), 256, 0, ctx->stream>>>(ns, Pp, (const int32_t*)(d_plan + off_p2m), (const int32_t*)(d_plan + off_plen),
                 (const unsigned long long*)(lb + o_top1), (const unsigned long long*)(lb + o_top2), (const unsigned int*)(lb + o_dup), (const unsigned int*)(lb + o_nh), d_counts);
             ctx->launches[T_COUNT] += 3;
+        } else if (tc_done && tc_sparse) {
+            count_listed_kernel<<<grid * 8, 256, 0, ctx->stream>>>(d_mask, d_tc_ulist, d_tc_ctr + 4, W, P.K2pad, (const int32_t*)(d_plan + off_p2m),
+                                                                    (const int32_t*)(d_plan + off_plen), d_counts);
+            ctx->launches[T_COUNT] += 1;
+            ctx->mask_clean_bytes = (size_t)ns * mask_bytes_per_seq;   // every word with a bit belongs to a listed unit and was cleared
         } else {
             const int64_t cthreads = ns * Pp;
             count_kernel<<<(unsigned)((cthreads + 255) / 256), 256, 0, ctx->stream>>>(d_mask, ns, W, P.K2pad, (const int32_t*)(d_plan + off_p2m),
@@ -1042,6 +1332,10 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
     tm.end(t_total);
     MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     tm.collect();
+    if (d_tc_ctr && getenv("MB200_SCAN_TC_STATS")) {
+        fprintf(stderr, "[mb200] tensor-core scan: %s, candidates %llu, hits %llu, scan %.3f ms, count %.3f ms\n", use_tc ? "used" : "fell back", tc_stat_cand, tc_stat_hits,
+                ctx->ms[T_SCAN], ctx->ms[T_COUNT]);
+    }
     if (seqs->pending) { rc = mb_seqs_finish(ctx, const_cast<mb200_seqs*>(seqs)); if (rc) return rc; }      // the upload has completed: report bad symbols
     if (n_hits) *n_hits = hits_needed;
     if (want_hits && hits_needed > hits_cap)
@@ -1054,6 +1348,8 @@ extern "C" int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs, const uint
                               int64_t* n_hits, int64_t* counts) {
     return scan_impl(ctx, seqs, pwms_f16, lens, K, maxlen, thresh_f16, flags, hits, hits_cap, n_hits, counts, nullptr);
 }
+
+extern "C" int32_t mb200_scan_last_path(const mb200_ctx* ctx) { return ctx ? ctx->last_scan_path : MB200_E_INVALID; }
 
 // hist: K * 32768 uint32, hist[k][b] = number of hits (score > 0, both requested strands) whose Float16 score has bit pattern b.
 extern "C" int32_t mb200_scan_hist(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t* pwms_f16, const int64_t* lens, int32_t K,

@@ -1,0 +1,390 @@
+// Tensor-core pre-filter for the thresholded PWM scan (tcgen05.mma kind::f16, accumulators in TMEM) + exact verification.
+//
+// What it replaces: the same reference functions as scan_kernel (greedy_search! _h3_1_alignment.jl:18-36 followed by
+// filter_position_by_best_thresh! _s2_filter_pos_w_scores.jl:116-125), for the case the fused-threshold callers use
+// (thresh given).  The reference's score is a LEFT-TO-RIGHT Float16 running sum; a GEMM cannot reproduce its rounding, so the
+// GEMM is only a FILTER and every position it lets through is re-scored with the sequential Float16 adds:
+//
+//   1. k_scan_tc: D[v, s] = sum_{j,b} onehot(base[v+j])[b] * W_s[j][b]   (FP16 operands, exact products, FP32 accumulation)
+//      for every start position v of the batch and every (motif, strand) slot s, with the slot's pre-filter threshold T'_s
+//      folded into column 0 of W_s (rounded up), so that "D > 0" is the candidate test.  T'_s = t_s - E_s - eps32 where E_s bounds
+//      |Float16 running sum - real sum| over all paths whose Float16 score exceeds t_s (tc_error_bound below: U_j = the Float16
+//      running sum of column maxima bounds every partial sum from above by monotonicity of rounding, a backward recursion bounds
+//      the partial sums of hit paths from below, each add errs by at most 2^-11 |partial sum|).  Hence every true hit is a
+//      candidate; candidates (a few 1e-4 of all cells at the usual thresholds) go to a list in HBM.
+//   2. k_scan_tc_verify: one thread per candidate re-computes the sequential Float16 score (same table, same adds as
+//      emit_kernel) and sets the bit of the hit mask when score > thresh.  The masks then feed count / emit / hist unchanged, so
+//      hit sets are bit-identical to scan_kernel's (tests/test_scan_gpu.py runs both paths on the same inputs).
+//
+// Operand layout (the im2col matrix is never materialised): a tile is 128 start positions of one parity, v = v0 + par + 2m.
+// Its one-hot stream in shared memory holds one 16-byte chunk per base PAIR (2 bases x {A,C,G,T} halves); row m of the A operand
+// is the stream from chunk m on, so in the canonical K-major no-swizzle UMMA layout (core matrix = 8 rows x 16 B, rows 16 B
+// apart) the operand of K-chunk c is the same stream advanced by c*16 B.  Two copies ("planes", the second shifted by one chunk)
+// give the two K-chunks of one K=16 MMA at LBO = plane stride; SBO = 128 B.  B = W'[K chunk][256 slots][8 halves] stays resident.
+// One CTA per SM owns one block of 256 slots; warp 0 builds streams (from the 2-bit words in L2), one lane of warp 1 issues
+// kchunks/2 MMAs of 128x256x16 per tile, warps 2-9 (two groups, one per TMEM accumulator) drain 32-column chunks with
+// tcgen05.ld, take a 3-input max tree and only look at individual columns when some lane saw a positive value.
+#pragma once
+
+#define TCS_M 128
+#define TCS_N 256                          // slots per block = accumulator columns
+#define TCS_STREAM 160                     // 16-byte chunks per stream plane: 128 rows + up to 32 K-chunks
+#define TCS_PLANE_BYTES (TCS_STREAM * 16)
+#define TCS_STAGE_BYTES (4 * TCS_PLANE_BYTES)   // one tile: {even, odd} x {plane 0, plane 1}
+#define TCS_STAGES 4
+#define TCS_THREADS 352
+#define TCS_RESERVE 256                    // candidate records reserved per global atomic
+#define TCS_MAX_KCHUNKS 32                 // 64 columns x 4 bases / 8
+#ifndef TCS_PROFILE
+#define TCS_PROFILE 0                      // 1: per-role wait clocks in TcArgs::dbg (printed with MB200_SCAN_TC_DEBUG=1)
+#endif
+#if TCS_PROFILE
+#define TCS_PROF(...) __VA_ARGS__
+#else
+#define TCS_PROF(...)
+#endif
+
+struct TcBlock {
+    int64_t b_off;                         // byte offset of the block's B operand in the TC blob
+    int32_t kchunks;                       // 16-byte K chunks (8 halves = 2 PWM columns), even
+    int32_t slot0;                         // first global slot
+    int32_t cta0, nctas;                   // CTAs [cta0, cta0 + nctas) work on this block
+};
+struct TcSlot {                            // per global slot, for the epilogue (npos) and the verifier
+    int32_t motif;                         // original motif index, -1: disabled
+    int32_t strand, len, npos;
+    uint32_t thr;                          // Float16 bits of max(thresh, 0)
+    int32_t pad[3];
+};
+struct TcArgs {
+    const uint32_t* seqw; int64_t rowwords; int64_t seq0;
+    uint32_t Lb; uint32_t vtotal;          // virtual positions of the batch: v = n_local * Lb + p
+    const uint8_t* blob; const TcBlock* blocks; int32_t nblocks;
+    const TcSlot* slots;
+    unsigned long long* list; unsigned long long cap; unsigned long long* gcount;   // candidate list, its capacity, reserved records
+    uint32_t* overflow;
+    int32_t ntiles;                        // tiles of 256 positions (2 units each)
+    long long* clocks;                     // [grid][2]: clocks the MMA lane spent on its tiles, tiles done (feeds the host's re-balancing of CTAs over blocks)
+    long long* dbg;                        // TCS_PROFILE builds: [grid][8] wait clocks per role
+};
+
+__device__ __forceinline__ uint64_t tcs_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tcs_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tcs_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done, spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && ++spins > (1u << 26)) __trap();             // never hang the device on a lost completion
+    } while (!done);
+}
+__device__ __forceinline__ float tcs_max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// 16-byte one-hot chunk of a base pair: halves {A,C,G,T} of b0 then of b1, 1.0 = 0x3C00
+__device__ __forceinline__ uint4 tcs_onehot(uint32_t b0, uint32_t b1) {
+    uint4 r;
+    r.x = b0 < 2 ? 0x3C00u << (16 * b0) : 0u;
+    r.y = b0 >= 2 ? 0x3C00u << (16 * (b0 - 2)) : 0u;
+    r.z = b1 < 2 ? 0x3C00u << (16 * b1) : 0u;
+    r.w = b1 >= 2 ? 0x3C00u << (16 * (b1 - 2)) : 0u;
+    return r;
+}
+__device__ __forceinline__ uint32_t tcs_base(const TcArgs& a, uint32_t v) {
+    if (v >= a.vtotal) return 0u;
+    const uint32_t n = v / a.Lb, p = v - n * a.Lb;
+    const uint32_t w = __ldg(a.seqw + (a.seq0 + n) * a.rowwords + (p >> 4));
+    return (w >> ((p & 15) * 2)) & 3u;
+}
+
+// A warp's slice of the candidate list is used up: pad it with empty records and reserve the next one (one global atomic per
+// TCS_RESERVE records).  ~0: the list is full, the host falls back to scan_kernel for this batch.
+__device__ __noinline__ unsigned long long tcs_reserve(unsigned long long* list, unsigned long long* gcount, unsigned long long cap, uint32_t* overflow,
+                                                       int lane, unsigned long long cur, unsigned long long end) {
+    for (unsigned long long i = cur + lane; i < end; i += 32) list[i] = ~0ull;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(gcount, (unsigned long long)TCS_RESERVE);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base + TCS_RESERVE > cap) {
+        if (lane == 0) atomicExch(overflow, 1u);
+        return ~0ull;
+    }
+    return base;
+}
+
+#define TCS_LDTM32(U, TADDR)                                                                                                                   \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
+                 : "=r"(U[0]), "=r"(U[1]), "=r"(U[2]), "=r"(U[3]), "=r"(U[4]), "=r"(U[5]), "=r"(U[6]), "=r"(U[7]), "=r"(U[8]), "=r"(U[9]), "=r"(U[10]),           \
+                   "=r"(U[11]), "=r"(U[12]), "=r"(U[13]), "=r"(U[14]), "=r"(U[15]), "=r"(U[16]), "=r"(U[17]), "=r"(U[18]), "=r"(U[19]), "=r"(U[20]),      \
+                   "=r"(U[21]), "=r"(U[22]), "=r"(U[23]), "=r"(U[24]), "=r"(U[25]), "=r"(U[26]), "=r"(U[27]), "=r"(U[28]), "=r"(U[29]), "=r"(U[30]), "=r"(U[31]) \
+                 : "r"(TADDR) : "memory")
+
+// max of 32 accumulator values as four independent chains (latency, not issue, bounds the epilogue)
+__device__ __forceinline__ float tcs_max32(const uint32_t (&u)[32]) {
+    float m[4];
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        m[k] = tcs_max3(__uint_as_float(u[8 * k]), __uint_as_float(u[8 * k + 1]), __uint_as_float(u[8 * k + 2]));
+        m[k] = tcs_max3(m[k], __uint_as_float(u[8 * k + 3]), __uint_as_float(u[8 * k + 4]));
+        m[k] = tcs_max3(m[k], __uint_as_float(u[8 * k + 5]), __uint_as_float(u[8 * k + 6]));
+    }
+    return fmaxf(tcs_max3(m[0], m[1], m[2]), tcs_max3(m[3], __uint_as_float(u[7]), tcs_max3(__uint_as_float(u[15]), __uint_as_float(u[23]), __uint_as_float(u[31]))));
+}
+// bit c set when column c is positive (D > 0  <=>  its bits as a signed integer are > 0)
+__device__ __forceinline__ uint32_t tcs_posbits(const uint32_t (&u)[32]) {
+    uint32_t b = 0;
+    #pragma unroll
+    for (int c = 0; c < 32; ++c) b |= ((int32_t)u[c] > 0 ? 1u : 0u) << c;
+    return b;
+}
+
+// Some lane of the warp has a positive column among these 64 (two chunks): append (slot, position) records of every positive
+// column.  Windows that run past the end of their sequence are left to the verifier (it knows the motif length).
+__device__ __noinline__ void tcs_append(unsigned long long* list, unsigned long long* gcount, unsigned long long cap, uint32_t* overflow, int lane,
+                                        uint32_t bits0, uint32_t bits1, uint32_t slot_base, uint32_t v, unsigned long long* cur_end, uint32_t* dead) {
+    if (*dead) return;
+    const uint32_t cnt = __popc(bits0) + __popc(bits1);
+    uint32_t incl = cnt;                                                                 // inclusive prefix sum over lanes
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long cur = cur_end[0], end = cur_end[1];
+    if (cur + total > end) {
+        if (total > TCS_RESERVE) { if (lane == 0) atomicExch(overflow, 1u); *dead = 1u; return; }     // cannot happen: 32 lanes x 64 columns > 256 only at absurd densities
+        cur = tcs_reserve(list, gcount, cap, overflow, lane, cur, end);
+        if (cur == ~0ull) { *dead = 1u; cur_end[0] = cur_end[1] = 0; return; }
+        end = cur + TCS_RESERVE;
+    }
+    unsigned long long o = cur + (incl - cnt);
+    while (bits0) { const int c = __ffs(bits0) - 1; bits0 &= bits0 - 1; list[o++] = ((unsigned long long)(slot_base + c) << 32) | v; }
+    while (bits1) { const int c = __ffs(bits1) - 1; bits1 &= bits1 - 1; list[o++] = ((unsigned long long)(slot_base + 32 + c) << 32) | v; }
+    cur_end[0] = cur + total; cur_end[1] = end;
+}
+
+// Work item = one tile of 256 consecutive virtual start positions: parity 0 (even offsets) accumulates in TMEM columns [0,256),
+// parity 1 in [256,512).  Warps: 0 and 10 build the one-hot streams of alternate tiles, one lane of warp 1 issues the MMAs,
+// warps 2-5 drain parity (warp-2)/4 = 0, warps 6-9 parity 1.
+__global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
+    extern __shared__ __align__(1024) uint8_t tcs_smem[];
+    uint8_t* sA = tcs_smem;                                              // [TCS_STAGES][2 parities][2 planes][TCS_STREAM][16 B]
+    uint8_t* sB = tcs_smem + TCS_STAGES * TCS_STAGE_BYTES;               // [kchunks][256][16 B]
+    __shared__ __align__(8) uint64_t s_bars[2 * TCS_STAGES + 5];         // full[S], empty[S], accfull[2], accempty[2], B landed
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    auto bar = [&](int i) { return (uint32_t)__cvta_generic_to_shared(&s_bars[i]); };
+
+    // which slot block does this CTA serve
+    int bi = 0;
+    for (int i = 0; i < a.nblocks; ++i) if ((int)blockIdx.x >= a.blocks[i].cta0) bi = i;
+    const TcBlock blk = a.blocks[bi];
+    const int rank = (int)blockIdx.x - blk.cta0;
+    if (rank >= blk.nctas) return;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2 * TCS_STAGES + 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(i)) : "memory");
+        for (int i = 2 * TCS_STAGES + 2; i < 2 * TCS_STAGES + 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" :: "r"(bar(i)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(2 * TCS_STAGES + 4)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&s_tmem)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // the last chunk of every shifted plane is never written by the producers (and never needed): keep it zero
+    for (int i = tid; i < TCS_STAGES * 2; i += blockDim.x)
+        *reinterpret_cast<uint4*>(sA + (size_t)i * (2 * TCS_PLANE_BYTES) + TCS_PLANE_BYTES + (TCS_STREAM - 1) * 16) = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    const uint32_t sA_addr = (uint32_t)__cvta_generic_to_shared(sA), sB_addr = (uint32_t)__cvta_generic_to_shared(sB);
+    // instruction descriptor: D = F32 (1<<4), A = B = F16 (format 0), both K-major, N>>3 at bit 17, M>>4 at bit 24
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(TCS_N >> 3) << 17) | ((uint32_t)(TCS_M >> 4) << 24);
+
+    if (warp == 0 || warp == 10) {
+        // ---- producers: bases v0 .. v0+319 of the tile -> even stream E[m] = (b[2m], b[2m+1]), odd stream O[m] = (b[2m+1], b[2m+2]),
+        //      each stored twice (plane 1 = plane 0 shifted by one chunk) ----
+        const int pw = warp == 0 ? 0 : 1;
+        TCS_PROF(long long w_prod = 0;)
+        int it = 0;
+        for (int tile = rank; tile < a.ntiles; tile += blk.nctas, ++it) {
+            if ((it & 1) != pw) continue;
+            const int st = it % TCS_STAGES; const uint32_t ph = (it / TCS_STAGES) & 1;
+            uint32_t v = (uint32_t)tile * 256u + 2u * lane;
+            uint32_t n = v / a.Lb, p = v - n * a.Lb;
+            const uint32_t* row = a.seqw + (a.seq0 + n) * a.rowwords;
+            uint32_t b0[TCS_STREAM / 32], b1[TCS_STREAM / 32];
+            #pragma unroll
+            for (int i = 0; i < TCS_STREAM / 32; ++i) {
+                uint32_t w0 = 0, w1 = 0;
+                const bool second_in_row = p + 1 < a.Lb;
+                const uint32_t p1 = second_in_row ? p + 1 : 0u;
+                const uint32_t* row1 = second_in_row ? row : row + a.rowwords;
+                if (v < a.vtotal) w0 = __ldg(row + (p >> 4));
+                if (v + 1 < a.vtotal) w1 = __ldg(row1 + (p1 >> 4));
+                b0[i] = (w0 >> ((p & 15) * 2)) & 3u;
+                b1[i] = (w1 >> ((p1 & 15) * 2)) & 3u;
+                v += 64; p += 64;
+                while (p >= a.Lb) { p -= a.Lb; row += a.rowwords; }
+            }
+            TCS_PROF(const long long t0 = clock64();)
+            tcs_wait(bar(TCS_STAGES + st), ph ^ 1);                                      // stage free
+            TCS_PROF(w_prod += clock64() - t0;)
+            uint8_t* e0 = sA + (size_t)st * TCS_STAGE_BYTES;                             // even: plane 0, plane 1; odd: plane 0, plane 1
+            uint8_t* o0 = e0 + 2 * TCS_PLANE_BYTES;
+            #pragma unroll
+            for (int i = 0; i < TCS_STREAM / 32; ++i) {
+                const uint32_t m = lane + 32 * i;
+                uint32_t b2 = __shfl_down_sync(0xffffffffu, b0[i], 1);
+                const uint32_t nxt = __shfl_sync(0xffffffffu, i + 1 < TCS_STREAM / 32 ? b0[(i + 1) % (TCS_STREAM / 32)] : 0u, 0);
+                if (lane == 31) b2 = nxt;
+                const uint4 ev = tcs_onehot(b0[i], b1[i]);
+                const uint4 od = tcs_onehot(b1[i], b2);
+                *reinterpret_cast<uint4*>(e0 + m * 16) = ev;
+                *reinterpret_cast<uint4*>(o0 + m * 16) = od;
+                if (m > 0) {
+                    *reinterpret_cast<uint4*>(e0 + TCS_PLANE_BYTES + (m - 1) * 16) = ev;
+                    *reinterpret_cast<uint4*>(o0 + TCS_PLANE_BYTES + (m - 1) * 16) = od;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                 // generic-proxy writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar(st)) : "memory");
+        }
+        TCS_PROF(if (a.dbg && warp == 0 && lane == 0) a.dbg[blockIdx.x * 8 + 5] = w_prod;)
+    } else if (warp == 1) {
+        if (lane == 0) {
+            {   // the block's B operand, resident for the whole kernel
+                const uint32_t b_bytes = (uint32_t)blk.kchunks * TCS_N * 16;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar(2 * TCS_STAGES + 4)), "r"(b_bytes) : "memory");
+                for (uint32_t o = 0; o < b_bytes; o += 32768u) {
+                    const uint32_t nb = min(32768u, b_bytes - o);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 :: "r"(sB_addr + o), "l"(a.blob + blk.b_off + o), "r"(nb), "r"(bar(2 * TCS_STAGES + 4)) : "memory");
+                }
+                tcs_wait(bar(2 * TCS_STAGES + 4), 0);
+            }
+            const int kpairs = blk.kchunks >> 1;
+            const uint64_t db0 = tcs_desc(sB_addr, TCS_N * 16, 128);
+            TCS_PROF(long long w_full = 0; long long w_acc = 0;)
+            const long long t_start = clock64();
+            int it = 0;
+            for (int tile = rank; tile < a.ntiles; tile += blk.nctas, ++it) {
+                const int st = it % TCS_STAGES; const uint32_t ph = (it / TCS_STAGES) & 1;
+                const uint32_t aph = it & 1;
+                TCS_PROF(long long t0 = clock64();)
+                tcs_wait(bar(st), ph);                                                   // streams built
+                TCS_PROF(w_full += clock64() - t0;)
+                #pragma unroll
+                for (int par = 0; par < 2; ++par) {
+                    TCS_PROF(t0 = clock64();)
+                    tcs_wait(bar(2 * TCS_STAGES + 2 + par), aph ^ 1);                    // accumulator drained
+                    TCS_PROF(w_acc += clock64() - t0;)
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t da0 = tcs_desc(sA_addr + st * TCS_STAGE_BYTES + par * 2 * TCS_PLANE_BYTES, TCS_PLANE_BYTES, 128);
+                    for (int t = 0; t < kpairs; ++t)
+                        tcs_mma(tmem + par * TCS_N, da0 + (uint64_t)(2 * t), db0 + (uint64_t)(2 * t * TCS_N), idesc, t ? 1u : 0u);
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar(2 * TCS_STAGES + par)) : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar(TCS_STAGES + st)) : "memory");
+            }
+            if (a.clocks) { a.clocks[blockIdx.x * 2] = clock64() - t_start; a.clocks[blockIdx.x * 2 + 1] = it; }
+            TCS_PROF(if (a.dbg) { a.dbg[blockIdx.x * 8 + 0] = clock64() - t_start; a.dbg[blockIdx.x * 8 + 1] = w_full; a.dbg[blockIdx.x * 8 + 2] = w_acc; a.dbg[blockIdx.x * 8 + 6] = bi; a.dbg[blockIdx.x * 8 + 7] = it; })
+        }
+    } else {
+        // ---- epilogue: two groups of four warps (one per TMEM lane quarter), group `par` drains accumulator `par` of every tile ----
+        const int q = warp & 3;
+        const int par = (warp - 2) >> 2;
+        unsigned long long cur_end[2] = {0, 0};                                          // this warp's reserved slice of the candidate list
+        uint32_t dead = 0;                                                               // list capacity exhausted
+        TCS_PROF(long long w_epi = 0; const long long t_start = clock64();)
+        int it = 0;
+        for (int tile = rank; tile < a.ntiles; tile += blk.nctas, ++it) {
+            const uint32_t v = (uint32_t)tile * 256u + (uint32_t)par + 2u * (uint32_t)(q * 32 + lane);
+            const bool inb = v < a.vtotal;
+            TCS_PROF(const long long t0 = clock64();)
+            tcs_wait(bar(2 * TCS_STAGES + par), it & 1);
+            TCS_PROF(w_epi += clock64() - t0;)
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // four rounds of 64 columns, software pipelined: the next round's tcgen05.ld is in flight while this round is reduced
+            const uint32_t taddr = tmem + par * TCS_N + ((uint32_t)(q * 32) << 16);
+            uint32_t ua0[32], ua1[32], ub0[32], ub1[32];
+            TCS_LDTM32(ua0, taddr); TCS_LDTM32(ua1, taddr + 32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            #define TCS_ROUND(CUR0, CUR1, NXT0, NXT1, R)                                                                            \
+            {                                                                                                                         \
+                if ((R) < 3) { TCS_LDTM32(NXT0, taddr + ((R) + 1) * 64); TCS_LDTM32(NXT1, taddr + ((R) + 1) * 64 + 32); }          \
+                const bool pos = inb && fmaxf(tcs_max32(CUR0), tcs_max32(CUR1)) > 0.f;                                                \
+                if (__any_sync(0xffffffffu, pos)) {      /* about one round in ten at the usual thresholds */                       \
+                    const uint32_t bits0 = pos ? tcs_posbits(CUR0) : 0u, bits1 = pos ? tcs_posbits(CUR1) : 0u;                        \
+                    tcs_append(a.list, a.gcount, a.cap, a.overflow, lane, bits0, bits1, (uint32_t)(blk.slot0 + (R) * 64), v, cur_end, &dead); \
+                }                                                                                                                     \
+                if ((R) < 3) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");                                           \
+            }
+            TCS_ROUND(ua0, ua1, ub0, ub1, 0)
+            TCS_ROUND(ub0, ub1, ua0, ua1, 1)
+            TCS_ROUND(ua0, ua1, ub0, ub1, 2)
+            TCS_ROUND(ub0, ub1, ua0, ua1, 3)
+            #undef TCS_ROUND
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar(2 * TCS_STAGES + 2 + par)) : "memory");    // accumulator may be overwritten
+        }
+        for (unsigned long long i = cur_end[0] + lane; i < cur_end[1]; i += 32) a.list[i] = ~0ull;
+        TCS_PROF(if (a.dbg && warp == 2 && lane == 0) { a.dbg[blockIdx.x * 8 + 3] = w_epi; a.dbg[blockIdx.x * 8 + 4] = clock64() - t_start; })
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(512) : "memory");
+}
+
+// Exact re-scoring of the candidates: the sequential Float16 adds of greedy_search!, then score > thresh sets the mask bit.
+__global__ void __launch_bounds__(256) k_scan_tc_verify(const unsigned long long* __restrict__ list, const unsigned long long* __restrict__ gcount,
+                                                        unsigned long long cap, const TcSlot* __restrict__ slots, const EmitMotif* __restrict__ em,
+                                                        const uint8_t* __restrict__ blob, const uint32_t* __restrict__ seqw, int64_t rowwords, int64_t seq0,
+                                                        uint32_t Lb, int32_t W, int32_t K2pad, uint32_t* __restrict__ mask, unsigned long long* __restrict__ stats,
+                                                        uint32_t* __restrict__ unit_bits, uint32_t* __restrict__ unit_list, unsigned long long* __restrict__ n_units) {
+    const unsigned long long total = min(*gcount, cap);
+    unsigned int n_cand = 0, n_hit = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long rec = list[i];
+        if (rec == ~0ull) continue;
+        const uint32_t slot = (uint32_t)(rec >> 32), v = (uint32_t)rec;
+        const uint32_t n = v / Lb, p = v - n * Lb;
+        const TcSlot sl = slots[slot];
+        if ((int32_t)p >= sl.npos) continue;                                              // the window runs past the end of its sequence (or the slot is disabled)
+        const EmitMotif m = em[sl.motif];
+        const uint8_t* tab = blob + m.tab_off + sl.strand * m.strand_stride;
+        const uint32_t* srow = seqw + (seq0 + n) * rowwords;
+        __half s = __ushort_as_half((unsigned short)0);
+        for (int32_t j = 0; j < sl.len; ++j) {
+            const uint32_t qq = p + j;
+            const uint32_t base = (__ldg(srow + (qq >> 4)) >> ((qq & 15) * 2)) & 3u;
+            s = __hadd(s, *reinterpret_cast<const __half*>(tab + (int64_t)j * m.col_stride + base * m.base_stride));
+        }
+        ++n_cand;
+        if (__hgt(s, __ushort_as_half((unsigned short)sl.thr))) {
+            atomicOr(&mask[((int64_t)n * W + (p >> 5)) * (int64_t)K2pad + slot], 1u << (p & 31));
+            ++n_hit;
+            if (unit_bits) {                                                              // first hit of this (sequence, motif) unit: list it for count_listed_kernel
+                const uint32_t g = n * (uint32_t)(K2pad >> 1) + (slot >> 1);
+                const uint32_t bit = 1u << (g & 31);
+                if (!(atomicOr(&unit_bits[g >> 5], bit) & bit)) unit_list[atomicAdd(n_units, 1ull)] = g;
+            }
+        }
+    }
+    if (stats) {
+        n_cand = __reduce_add_sync(0xffffffffu, n_cand);
+        n_hit = __reduce_add_sync(0xffffffffu, n_hit);
+        if ((threadIdx.x & 31) == 0 && n_cand) { atomicAdd(&stats[0], (unsigned long long)n_cand); atomicAdd(&stats[1], (unsigned long long)n_hit); }
+    }
+}

@@ -466,7 +466,7 @@ def filter_positions_scores_usecomp_fused_(ms: Motifs, data, bg):
     ms.score_thresh = np.zeros(K, f16)
     for i in range(K):
         with np.errstate(over="ignore"):
-            ms.score_thresh[i] = f16(get_best_thresh_hist(h_fg[i], h_bg[i], ms.effective_segments[i], ms.pwms[i], data.N * data.L, bg, ctx=data.ctx))
+            ms.score_thresh[i] = f16(get_best_thresh_hist(h_fg[i], h_bg[i], ms.effective_segments[i], ms.pwms[i], data.N * data.L, bg, ctx=data.seqs.ctx))
     return scan_counts(ms, data, thresh=ms.score_thresh), scan_counts(ms, data, bg=True, thresh=ms.score_thresh)
 
 

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import motifs_jl_b200 as mb
-from motifs_jl_b200 import inference, synth
+from motifs_jl_b200 import inference, synth, _lib
 from oracle import scan_oracle as so
 
 pytestmark = pytest.mark.gpu
@@ -24,8 +24,23 @@ def _check(ctx, ascii_rows, ms, thresh=None, strands=3):
     # counts-only call must agree with the hits call
     _, c2 = ctx.scan(seqs, pw, lens, thresh, fwd=bool(strands & 1), rc=bool(strands & 2), want_hits=False)
     assert np.array_equal(c2, ocounts)
+    if thresh is not None:
+        # the call above took the tensor-core pre-filter when eligible; the SIMT kernel must give the same hits and counts
+        h3, c3 = ctx.scan(seqs, pw, lens, thresh, fwd=bool(strands & 1), rc=bool(strands & 2), tensor=False)
+        assert _lib.scan_last_path(ctx) == 0
+        assert np.array_equal(c3, ocounts)
+        assert h3.tobytes() == hits.tobytes()
     seqs.free()
     return hits, counts
+
+
+def _tc_path(ctx, ascii_rows, ms, thresh, strands=3):
+    """path taken by a thresholded counts-only scan (1 = tensor-core pre-filter)"""
+    pw, lens = so.pack_pwms(ms.pwms)
+    seqs = ctx.seqs_from_ascii(ascii_rows)
+    ctx.scan(seqs, pw, lens, thresh, fwd=bool(strands & 1), rc=bool(strands & 2), want_hits=False)
+    seqs.free()
+    return _lib.scan_last_path(ctx)
 
 
 def test_pack_matches_layout(ctx):
@@ -314,3 +329,87 @@ def test_asynchronous_upload_overlapping_the_scan(ctx):
     s4.free()
     s5 = ctx.seqs_from_host_ptr(b.ctypes.data, 5000, Lb, wait=False)
     s5.free()                                                               # freeing a pending upload is safe
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Tensor-core pre-filter (csrc/scan_tc.cuh): every thresholded _check above already runs it next to the SIMT kernel and the
+# oracle.  The cases below aim at what could break a filter: scores that land exactly on the threshold, partial sums whose
+# Float16 rounding error is large, windows that straddle sequences and tiles, disabled slots, and the overflow fallback.
+# ---------------------------------------------------------------------------------------------------------------------
+def test_tensor_path_is_taken_and_exact_at_the_threshold(ctx):
+    a = synth.random_ascii(3000, 100, 71)
+    ms = synth.motifs_from_count_matrices(synth.random_count_matrices(150, 8, 40, 72))
+    thr = synth.stated_thresholds(ms, 0.5)
+    assert _tc_path(ctx, a, ms, thr) == 1
+    # thresholds equal to scores that occur: "score > thresh" must drop exactly those hits
+    pw, lens = so.pack_pwms(ms.pwms)
+    oh, _ = so.scan(pw, lens, so.ascii_to_codes(a), thr, 3)
+    thr2 = thr.copy()
+    for m in range(len(ms.pwms)):
+        sc = np.sort(oh[oh["motif"] == m]["score_f16"].view(np.float16))
+        if len(sc):
+            thr2[m] = sc[len(sc) // 2]
+    h, c = _check(ctx, a, ms, thr2)
+    assert 0 < len(h) < len(oh)
+
+
+@pytest.mark.parametrize("scale,seed", [(1.0, 81), (16.0, 82), (0.01, 83)])
+def test_tensor_path_large_and_tiny_magnitudes(ctx, scale, seed):
+    # entries up to +-250 (rounding error of a partial sum ~0.1 per add) and entries around 1e-2 (Float16 spacing effects differ)
+    a = synth.random_ascii(2000, 77, seed)
+    ms = synth.motifs_from_count_matrices(synth.random_count_matrices(70, 8, 40, seed + 100))
+    for p in ms.pwms:
+        p[:] = (p.astype(np.float32) * scale).astype(np.float16)
+    thr = synth.stated_thresholds(ms, 0.35)
+    assert _tc_path(ctx, a, ms, thr) == 1
+    _check(ctx, a, ms, thr)
+    _check(ctx, a, ms, thr, strands=1)
+    _check(ctx, a, ms, thr, strands=2)
+
+
+def test_tensor_path_short_sequences_and_tile_edges(ctx):
+    # sequences shorter than a 256-position tile, lengths that are not multiples of anything, motifs as long as the sequence
+    for Lb, N, seed in [(9, 5000, 91), (33, 999, 92), (64, 513, 93), (255, 40, 94), (257, 40, 95), (1000, 7, 96)]:
+        a = synth.random_ascii(N, Lb, seed)
+        ms = synth.motifs_from_count_matrices(synth.random_count_matrices(20, 1, min(64, Lb + 3), seed + 50))
+        thr = synth.stated_thresholds(ms, 0.4)
+        _check(ctx, a, ms, thr)
+
+
+def test_tensor_path_zero_threshold_and_disabled_slots(ctx):
+    a = synth.random_ascii(400, 120, 97)
+    ms = synth.motifs_from_count_matrices(synth.random_count_matrices(12, 8, 30, 98))
+    ms.pwms[1][2, 3] = np.float16(-np.inf)               # -Inf entry: the motif never hits
+    ms.pwms[4][:] = np.float16(-1.0)                     # best window below any threshold
+    thr = synth.stated_thresholds(ms, 0.5)
+    thr[2] = np.float16(np.nan)                          # NaN threshold: never a hit
+    thr[3] = np.float16(np.inf)
+    thr[5] = np.float16(0.0)
+    thr[6] = np.float16(-2.0)
+    thr[1] = np.float16(1.0)
+    thr[4] = np.float16(1.0)
+    assert _tc_path(ctx, a, ms, thr) == 1
+    h, c = _check(ctx, a, ms, thr)
+    assert c[1, 0] == 0 and c[2, 0] == 0 and c[3, 0] == 0 and c[4, 0] == 0 and c[5, 0] > 0
+    # +Inf / NaN entries are left to the SIMT kernel
+    ms.pwms[7][0, 5] = np.float16(np.inf)
+    assert _tc_path(ctx, a, ms, thr) == 0
+    _check(ctx, a, ms, thr)
+
+
+def test_tensor_path_candidate_overflow_falls_back(ctx):
+    # thresholds of zero on all-positive PWMs: every cell is a candidate; 33.5 M records overflow the list and the scan must
+    # finish on the SIMT kernel with the same counts
+    a = synth.random_ascii(20000, 200, 99)
+    ms = synth.motifs_from_count_matrices(synth.random_count_matrices(6, 8, 12, 100))
+    for p in ms.pwms:
+        p[:] = np.abs(p) + np.float16(0.01)
+    thr = np.zeros(6, np.float16)
+    pw, lens = so.pack_pwms(ms.pwms)
+    seqs = ctx.seqs_from_ascii(a)
+    _, c = ctx.scan(seqs, pw, lens, thr, want_hits=False)
+    assert _lib.scan_last_path(ctx) == 2
+    _, c0 = ctx.scan(seqs, pw, lens, thr, want_hits=False, tensor=False)
+    assert np.array_equal(c, c0)
+    assert c[0, 0] == 2 * 20000 * (200 - ms.lens[0] + 1)
+    seqs.free()
