@@ -212,11 +212,12 @@ def bench_scan(args, ctx, torch, dist, world, rank, local, dev, stream):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_scan = t_cnt = 0.0
         n_launch = nk = 0
+        timed.t_verify = 0.0
         e0.record(stream)
         for _ in range(steps):
             res = fn()
             t, l = ctx.last_timing()
-            t_scan += t["scan"]; t_cnt += t["count"]; nk += l["scan"]
+            t_scan += t["scan"]; t_cnt += t["count"]; nk += l["scan"]; timed.t_verify += t["emit"]
             n_launch += sum(l.values())
         e1.record(stream)
         barrier()
@@ -229,6 +230,9 @@ def bench_scan(args, ctx, torch, dist, world, rank, local, dev, stream):
     if rank == 0:
         sampler.start()
     ms_step, counts, t_scan, t_cnt, n_scan_launch, n_launch = timed(step_resident, args.steps, args.warmup)
+    t_verify = timed.t_verify
+    from motifs_jl_b200 import _lib as _mblib
+    scan_path = _mblib.scan_last_path(ctx)                                    # 1: tcgen05 pre-filter + exact re-scoring, 0: SIMT scan_kernel
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, counts2, *_ = timed(step_e2e, max(1, args.steps), 1)
     assert np.array_equal(counts, counts2)
@@ -265,6 +269,27 @@ def bench_scan(args, ctx, torch, dist, world, rank, local, dev, stream):
                                         "cells_per_s": cells_rate, "achieved": cells_rate / 1e12, "peak": alu_peak / 1e12, "unit": "Tcell/s",
                                         "frac": cells_rate / alu_peak, "peak_source": "148 SM x 4 sub-partitions x 512 cells / 28 clk x SM clock under load"}},
                "checks": {"counts_sum": [int(x) for x in counts.sum(axis=0)]}}
+        if scan_path == 1:
+            # dominant kernel: k_scan_tc (csrc/scan_tc.cuh), a one-hot GEMM on the tensor cores.  Algorithmic flops: 8 per PWM
+            # cell = 2 (multiply-add) x 4 (one-hot bases), cells = strands x N x sum_k (Lb - len_k + 1) len_k; the launch also computes the
+            # zero padding of K to the longest motif of a 256-slot block and the windows that straddle two sequences, which are not counted.
+            tf_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1413.0)))
+            flops_per_launch = 8.0 * cells_per_seq(lens, Lb) * n_local / launches_per_step
+            tf = flops_per_launch / (ms_per_launch * 1e-3) / 1e12
+            hbm = dict(out["roofline"]); hbm.pop("binding", None); hbm.pop("traffic", None); hbm["kernel"] = "k_scan_tc"
+            hbm["note"] = "algorithmic HBM bytes (0.25 B/bp + tables) over the same kernel time: the scan is not HBM bound (SURVEY §8d)"
+            out["roofline"] = {"bound": "tensor", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf / tf_peak,
+                               # ncu --set full of one launch (profiles/r01_scan_tc_ncu_full_summary.csv): dram read+write per launch
+                               "traffic": None,
+                               "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback",
+                               "kernel": "k_scan_tc", "ms_per_launch": ms_per_launch,
+                               "kernel_share_of_step": (t_scan / args.steps) / ms_step,
+                               "verify_kernel_share_of_step": (t_verify / args.steps) / ms_step,
+                               "count_kernel_share_of_step": (t_cnt / args.steps) / ms_step,
+                               "algorithmic_flops_per_launch": flops_per_launch,
+                               "note": "FP16 one-hot GEMM pre-filter (FP32 accumulate in TMEM), candidates re-scored with the reference's sequential Float16 adds: "
+                                       "hit sets identical to the SIMT kernel; cells/s below counts useful PWM cells only",
+                               "cells_per_s": cells_rate, "hbm": hbm}
         if world == 1 and not args.no_cpu_baseline:
             sample = ascii_host[: min(n_local, 20000)].numpy()
             rate, n, cores, dt = cpu_scan_rate(pw, lens, thr, sample, args.cpu_seconds)

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string>
 #include <vector>
+#include <utility>
 #include "../../include/motifs_b200.h"
 
 enum { T_PACK = 0, T_SCAN = 1, T_COUNT = 2, T_EMIT = 3, T_CSC = 4, T_H2D = 5, T_D2H = 6, T_TOTAL = 7, T_N = 8 };
@@ -27,6 +28,8 @@ struct mb200_ctx {
     void* bufs[12] = {nullptr}; size_t buf_bytes[12] = {0};
     void* pinned = nullptr;  size_t pinned_bytes = 0;
     int last_scan_path = 0;                   // mb200_scan_last_path
+    // freed sequence stores / staging buffers kept for the next upload (cudaMalloc + cudaFree of 0.5 GB cost 100s of ms per call)
+    std::vector<std::pair<void*, size_t>> pool; size_t pool_bytes = 0;
     size_t mask_clean_bytes = 0;              // leading bytes of bufs[2] (hit masks) known to be zero (tensor-core scan path)
 };
 
@@ -34,6 +37,7 @@ struct mb200_seqs {
     int64_t N = 0, Lb = 0;
     int64_t rowwords = 0;        // uint32 words per sequence = ceil(Lb/16)
     uint32_t* words = nullptr;   // device, N*rowwords (+ zeroed tail pad of PAD_WORDS)
+    size_t words_bytes = 0, stage_bytes = 0;   // block sizes as handed out by mb_pool_alloc
     int device = 0;
     // asynchronous upload (mb200_seqs_from_ascii_async): rows [0, ready_end[i]) are packed once ready[i] has fired
     bool pending = false;
@@ -71,4 +75,6 @@ struct MbTimers {
 int mb_ensure_scratch(mb200_ctx* ctx, size_t bytes);
 int mb_ensure_pinned(mb200_ctx* ctx, size_t bytes);
 int mb_ensure_buf(mb200_ctx* ctx, int slot, size_t bytes);
+void* mb_pool_alloc(mb200_ctx* ctx, size_t bytes, size_t* got);   // nullptr when out of memory; *got = size of the block handed out
+void mb_pool_free(mb200_ctx* ctx, void* p, size_t bytes);        // ctx may be NULL (plain cudaFree)
 static inline void mb_reset_timing(mb200_ctx* ctx) { for (int i = 0; i < T_N; ++i) { ctx->ms[i] = 0; ctx->launches[i] = 0; } }

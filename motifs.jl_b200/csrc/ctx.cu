@@ -1,5 +1,6 @@
 // Context management of libmotifs_b200 (C ABI in include/motifs_b200.h).
 #include "common.cuh"
+#include <algorithm>
 
 extern "C" int32_t mb200_version(void) { return 100; }
 
@@ -33,6 +34,7 @@ extern "C" int32_t mb200_destroy(mb200_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     for (int i = 0; i < 12; ++i) if (ctx->bufs[i]) cudaFree(ctx->bufs[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (auto& b : ctx->pool) cudaFree(b.first);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -90,4 +92,36 @@ int mb_ensure_buf(mb200_ctx* ctx, int slot, size_t bytes) {
     }
     ctx->buf_bytes[slot] = bytes;
     return MB200_OK;
+}
+
+
+// Small cache of device blocks for the sequence stores: a block is reused when it is at most 25 % (or 64 MB) larger than asked.
+void* mb_pool_alloc(mb200_ctx* ctx, size_t bytes, size_t* got) {
+    int best = -1;
+    for (int i = 0; i < (int)ctx->pool.size(); ++i) {
+        const size_t b = ctx->pool[i].second;
+        if (b >= bytes && b <= bytes + std::max<size_t>(bytes / 4, (size_t)64 << 20) && (best < 0 || b < ctx->pool[best].second)) best = i;
+    }
+    if (best >= 0) {
+        void* p = ctx->pool[best].first; *got = ctx->pool[best].second;
+        ctx->pool_bytes -= *got; ctx->pool.erase(ctx->pool.begin() + best);
+        return p;
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        for (auto& b : ctx->pool) cudaFree(b.first);               // give the cache back and retry once
+        ctx->pool.clear(); ctx->pool_bytes = 0;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    *got = bytes;
+    return p;
+}
+void mb_pool_free(mb200_ctx* ctx, void* p, size_t bytes) {
+    if (!p) return;
+    if (!ctx || bytes == 0) { cudaFree(p); return; }
+    ctx->pool.emplace_back(p, bytes); ctx->pool_bytes += bytes;
+    while (ctx->pool.size() > 6 || ctx->pool_bytes > ((size_t)12 << 30)) {       // oldest first
+        cudaFree(ctx->pool.front().first); ctx->pool_bytes -= ctx->pool.front().second; ctx->pool.erase(ctx->pool.begin());
+    }
 }

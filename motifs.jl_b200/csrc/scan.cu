@@ -758,7 +758,7 @@ struct TcPlan {
     std::vector<uint8_t> blob;
     std::vector<TcBlock> blocks;
     std::vector<TcSlot> slots;
-    int max_kchunks = 0;
+    size_t max_b_bytes = 0;                // largest B operand footprint of an entry
 };
 
 // false: this call is not eligible for the tensor-core path (the caller keeps scan_kernel).
@@ -823,20 +823,17 @@ static bool build_tc_plan(const ScanPlan& P, const uint16_t* pwms, const int64_t
     }
     // B operands: [block][kchunk][256 slots][8 halves]; half e of chunk c = column 2c + e/4, base e%4
     size_t total = 0;
-    std::vector<double> cost(nblocks);
+    std::vector<int> kcs(nblocks);
+    std::vector<int64_t> boff(nblocks);
     for (int bi = 0; bi < nblocks; ++bi) {
-        TcBlock tb; memset(&tb, 0, sizeof tb);
         int kc = (std::max(blen[bi], 1) + 1) / 2;
         kc = std::max(2, (kc + 1) & ~1);
-        tb.kchunks = kc; tb.slot0 = bi * TCS_N; tb.b_off = (int64_t)total;
+        kcs[bi] = kc; boff[bi] = (int64_t)total;
         total += (size_t)kc * TCS_N * 16;
-        T.max_kchunks = std::max(T.max_kchunks, kc);
-        cost[bi] = std::max(kc * 64.0, 600.0) + 100.0;              // MMA clocks (128 per K=16 step) or the epilogue, whichever binds
-        T.blocks.push_back(tb);
     }
     T.blob.assign(total, 0);
     for (int bi = 0; bi < nblocks; ++bi) {
-        uint16_t* Bm = reinterpret_cast<uint16_t*>(T.blob.data() + T.blocks[bi].b_off);
+        uint16_t* Bm = reinterpret_cast<uint16_t*>(T.blob.data() + boff[bi]);
         for (int sidx = 0; sidx < TCS_N; ++sidx) {
             const int slot = bi * TCS_N + sidx;
             const std::vector<uint16_t>& c = col0[slot];
@@ -849,6 +846,35 @@ static bool build_tc_plan(const ScanPlan& P, const uint16_t* pwms, const int64_t
             for (int j = 0; j < len; ++j)
                 for (int b = 0; b < 4; ++b) Bm[((size_t)(j >> 1) * TCS_N + sidx) * 8 + 4 * (j & 1) + b] = c[(size_t)j * 4 + b];
         }
+    }
+    // Work entries: the longest remaining block is paired with the shortest one while both B operands fit in shared memory (the short
+    // block's MMAs are shorter than the drain of a 128 x 256 accumulator, the long block's are longer: see k_scan_tc).  Initial cost in
+    // clocks per tile; scan_impl replaces it with measured clocks after the first batch.
+    std::vector<int> ord(nblocks);
+    for (int bi = 0; bi < nblocks; ++bi) ord[bi] = bi;
+    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return kcs[x] > kcs[y]; });
+    const double drain = 800.0;                                    // clocks to read one accumulator back (TMEM read bandwidth + barrier latencies)
+    const size_t b_budget = (size_t)200 * 1024 - (size_t)TCS_STAGES * TCS_STAGE_BYTES;
+    std::vector<double> cost;
+    int lo = 0, hi = nblocks - 1;
+    while (lo <= hi) {
+        TcBlock e; memset(&e, 0, sizeof e);
+        const int L = ord[lo];
+        e.b_off[0] = boff[L]; e.kchunks[0] = kcs[L]; e.slot0[0] = L * TCS_N; e.nsub = 1;
+        size_t bbytes = (size_t)kcs[L] * TCS_N * 16;
+        const bool no_pair = getenv("MB200_SCAN_TC_NOPAIR") != nullptr;
+        if (lo < hi && !no_pair && bbytes + (size_t)kcs[ord[hi]] * TCS_N * 16 <= b_budget) {
+            const int S = ord[hi];
+            e.b_off[1] = boff[S]; e.kchunks[1] = kcs[S]; e.slot0[1] = S * TCS_N; e.nsub = 2;
+            bbytes += (size_t)kcs[S] * TCS_N * 16;
+            cost.push_back(2.0 * std::max(kcs[L] * 64.0, drain) + 2.0 * std::max(kcs[S] * 64.0, drain) + 100.0);
+            --hi;
+        } else {
+            cost.push_back(2.0 * std::max(kcs[L] * 64.0, drain) + 100.0);
+        }
+        ++lo;
+        T.max_b_bytes = std::max(T.max_b_bytes, bbytes);
+        T.blocks.push_back(e);
     }
     return tc_assign_ctas(T.blocks, cost, grid);
 }
@@ -1083,7 +1109,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
         MB_CUDA(ctx, cudaMemsetAsync(d_tc_ctr, 0, (size_t)(8 + 2 * ctx->sm_count) * 8, ctx->stream));
         MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));           // h_tc goes out of scope
         // at least half of the shared memory: one CTA per SM (each CTA allocates all 512 TMEM columns)
-        tc_smem = std::max<size_t>((size_t)TCS_STAGES * TCS_STAGE_BYTES + (size_t)TP.max_kchunks * TCS_N * 16, (size_t)120 * 1024);
+        tc_smem = std::max<size_t>((size_t)TCS_STAGES * TCS_STAGE_BYTES + TP.max_b_bytes, (size_t)120 * 1024);
         if (tc_smem > ctx->smem_optin) use_tc = false;
         else MB_CUDA(ctx, cudaFuncSetAttribute(k_scan_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
     }
@@ -1173,7 +1199,6 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
         a.blob = d_plan + off_blob; a.mblocks = (const MBlock*)(d_plan + off_mb); a.n_mblocks = (int32_t)P.mblocks.size();
         a.tile_chunks = tile_chunks; a.ntiles = ntiles; a.tile_cap_words = tile_cap_words; a.blob_cap_bytes = blob_cap;
         a.cta_range = d_rng; a.gather_warps = gather_warps;
-        int t1 = tm.begin(T_SCAN);
         bool tc_done = false;
         if (use_tc) {
             const size_t need = (size_t)ns * mask_bytes_per_seq;
@@ -1196,17 +1221,21 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
             static long long* d_dbg = nullptr;
             if (getenv("MB200_SCAN_TC_DEBUG")) { if (!d_dbg) cudaMalloc(&d_dbg, 148 * 8 * 8 * 2); cudaMemset(d_dbg, 0, 148 * 8 * 8); ta.dbg = d_dbg; }
 #endif
+            const int t_tc = tm.begin(T_SCAN);
             k_scan_tc<<<grid, TCS_THREADS, tc_smem, ctx->stream>>>(ta);
+            tm.end(t_tc);
+            const int t_vf = tm.begin(T_EMIT);
             k_scan_tc_verify<<<grid * 8, 256, 0, ctx->stream>>>(d_tc_list, d_tc_ctr, tc_cap, ta.slots, (const EmitMotif*)(d_plan + off_em), d_plan + off_blob,
                                                                  seqs->words, rowwords, s0, (uint32_t)Lb, W, P.K2pad, d_mask, d_tc_ctr + 2,
                                                                  tc_sparse ? d_tc_ubits : nullptr, d_tc_ulist, d_tc_ctr + 4);
-            ctx->launches[T_SCAN] += 2;
+            tm.end(t_vf);
+            ctx->launches[T_SCAN] += 1; ctx->launches[T_EMIT] += 1;
             MB_CUDA(ctx, cudaGetLastError());
             std::vector<unsigned long long> h_ctr(8 + 2 * (size_t)grid, 0);
             MB_CUDA(ctx, cudaMemcpyAsync(h_ctr.data(), d_tc_ctr, h_ctr.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
             MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 #if TCS_PROFILE
-            if (ta.dbg && s0 == 0) {
+            if (ta.dbg && s0 / seqs_per_batch == atoi(getenv("MB200_SCAN_TC_DEBUG"))) {
                 std::vector<long long> h(148 * 8);
                 cudaMemcpy(h.data(), ta.dbg, 148 * 8 * 8, cudaMemcpyDeviceToHost);
                 for (int c = 0; c < grid; c += 1)
@@ -1235,6 +1264,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
         }
         if (tc_done) { /* masks are complete */ }
         else {
+        int t1 = tm.begin(T_SCAN);
         ctx->mask_clean_bytes = 0;
         if (!P.mblocks.empty()) { scan_kernel<<<grid, SCAN_THREADS, smem_bytes, ctx->stream>>>(a); ctx->launches[T_SCAN] += 1; }
         if (!P.lblocks.empty()) {
@@ -1243,8 +1273,8 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
                                                                                         (const MBlock*)(d_plan + off_lb), (int32_t)P.lblocks.size(), d_mask);
             ctx->launches[T_SCAN] += 1;
         }
-        }
         tm.end(t1);
+        }
         MB_CUDA(ctx, cudaGetLastError());
 
         int t2 = tm.begin(T_COUNT);

@@ -22,7 +22,7 @@
 // apart) the operand of K-chunk c is the same stream advanced by c*16 B.  Two copies ("planes", the second shifted by one chunk)
 // give the two K-chunks of one K=16 MMA at LBO = plane stride; SBO = 128 B.  B = W'[K chunk][256 slots][8 halves] stays resident.
 // One CTA per SM owns one block of 256 slots; warp 0 builds streams (from the 2-bit words in L2), one lane of warp 1 issues
-// kchunks/2 MMAs of 128x256x16 per tile, warps 2-9 (two groups, one per TMEM accumulator) drain 32-column chunks with
+// kchunks/2 MMAs of 128x256x16 per tile and parity, warps 2-17 (eight per TMEM accumulator) drain 32-column chunks with
 // tcgen05.ld, take a 3-input max tree and only look at individual columns when some lane saw a positive value.
 #pragma once
 
@@ -32,7 +32,7 @@
 #define TCS_PLANE_BYTES (TCS_STREAM * 16)
 #define TCS_STAGE_BYTES (4 * TCS_PLANE_BYTES)   // one tile: {even, odd} x {plane 0, plane 1}
 #define TCS_STAGES 4
-#define TCS_THREADS 352
+#define TCS_THREADS 608                    // warps: 0 and 18 producers, 1 MMA issue, 2-17 epilogue
 #define TCS_RESERVE 256                    // candidate records reserved per global atomic
 #define TCS_MAX_KCHUNKS 32                 // 64 columns x 4 bases / 8
 #ifndef TCS_PROFILE
@@ -44,11 +44,13 @@
 #define TCS_PROF(...)
 #endif
 
-struct TcBlock {
-    int64_t b_off;                         // byte offset of the block's B operand in the TC blob
-    int32_t kchunks;                       // 16-byte K chunks (8 halves = 2 PWM columns), even
-    int32_t slot0;                         // first global slot
-    int32_t cta0, nctas;                   // CTAs [cta0, cta0 + nctas) work on this block
+struct TcBlock {                           // what one CTA works on: one block of 256 slots, or a long and a short block paired
+    int64_t b_off[2];                      // byte offsets of the B operands in the TC blob
+    int32_t kchunks[2];                    // 16-byte K chunks (8 halves = 2 PWM columns), even
+    int32_t slot0[2];                      // first global slot
+    int32_t nsub;                          // 1, or 2: sub-block 0 (the longer one) accumulates in TMEM columns [0,256), sub-block 1 in [256,512)
+    int32_t cta0, nctas;                   // CTAs [cta0, cta0 + nctas) work on this entry
+    int32_t pad;
 };
 struct TcSlot {                            // per global slot, for the epilogue (npos) and the verifier
     int32_t motif;                         // original motif index, -1: disabled
@@ -142,7 +144,7 @@ __device__ __forceinline__ float tcs_max32(const uint32_t (&u)[32]) {
 __device__ __forceinline__ uint32_t tcs_posbits(const uint32_t (&u)[32]) {
     uint32_t b = 0;
     #pragma unroll
-    for (int c = 0; c < 32; ++c) b |= ((int32_t)u[c] > 0 ? 1u : 0u) << c;
+    for (int c = 31; c >= 0; --c) b = __funnelshift_l((uint32_t)(-(int32_t)u[c]), b, 1);       // shifts in the sign of -u: set exactly when (int)u > 0
     return b;
 }
 
@@ -169,13 +171,18 @@ __device__ __noinline__ void tcs_append(unsigned long long* list, unsigned long 
     cur_end[0] = cur + total; cur_end[1] = end;
 }
 
-// Work item = one tile of 256 consecutive virtual start positions: parity 0 (even offsets) accumulates in TMEM columns [0,256),
-// parity 1 in [256,512).  Warps: 0 and 10 build the one-hot streams of alternate tiles, one lane of warp 1 issues the MMAs,
-// warps 2-5 drain parity (warp-2)/4 = 0, warps 6-9 parity 1.
+// Work item = one tile of 256 consecutive virtual start positions = two parities (even / odd offsets) of 128 rows.
+// Single block: parity 0 accumulates in TMEM columns [0,256), parity 1 in [256,512).
+// Paired blocks (nsub = 2): draining 128 x 256 FP32 accumulators costs >= 512 clocks of TMEM read bandwidth, more than the MMA
+// time of a short block (K = 64: 512 clocks) and far less than that of a long one, so a long and a short block share the CTA
+// and the one-hot streams: unit order (long, p0) (short, p0) (long, p1) (short, p1), long -> accumulator 0, short -> accumulator 1;
+// the long block's accumulator drains under the short block's MMAs and vice versa.
+// Warps: 0 and 18 build the one-hot streams of alternate tiles, one lane of warp 1 issues the MMAs, warps 2-17 drain the
+// accumulators (8 warps each: 4 TMEM lane quarters x 2 column halves).
 __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
     extern __shared__ __align__(1024) uint8_t tcs_smem[];
     uint8_t* sA = tcs_smem;                                              // [TCS_STAGES][2 parities][2 planes][TCS_STREAM][16 B]
-    uint8_t* sB = tcs_smem + TCS_STAGES * TCS_STAGE_BYTES;               // [kchunks][256][16 B]
+    uint8_t* sB = tcs_smem + TCS_STAGES * TCS_STAGE_BYTES;               // per sub-block [kchunks][256][16 B]
     __shared__ __align__(8) uint64_t s_bars[2 * TCS_STAGES + 5];         // full[S], empty[S], accfull[2], accempty[2], B landed
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -190,7 +197,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
 
     if (tid == 0) {
         for (int i = 0; i < 2 * TCS_STAGES + 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(i)) : "memory");
-        for (int i = 2 * TCS_STAGES + 2; i < 2 * TCS_STAGES + 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" :: "r"(bar(i)) : "memory");
+        for (int i = 2 * TCS_STAGES + 2; i < 2 * TCS_STAGES + 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" :: "r"(bar(i)) : "memory");   // 8 epilogue warps per accumulator
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(2 * TCS_STAGES + 4)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -210,7 +217,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
     // instruction descriptor: D = F32 (1<<4), A = B = F16 (format 0), both K-major, N>>3 at bit 17, M>>4 at bit 24
     const uint32_t idesc = (1u << 4) | ((uint32_t)(TCS_N >> 3) << 17) | ((uint32_t)(TCS_M >> 4) << 24);
 
-    if (warp == 0 || warp == 10) {
+    if (warp == 0 || warp == TCS_THREADS / 32 - 1) {
         // ---- producers: bases v0 .. v0+319 of the tile -> even stream E[m] = (b[2m], b[2m+1]), odd stream O[m] = (b[2m+1], b[2m+2]),
         //      each stored twice (plane 1 = plane 0 shifted by one chunk) ----
         const int pw = warp == 0 ? 0 : 1;
@@ -263,37 +270,48 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
         TCS_PROF(if (a.dbg && warp == 0 && lane == 0) a.dbg[blockIdx.x * 8 + 5] = w_prod;)
     } else if (warp == 1) {
         if (lane == 0) {
-            {   // the block's B operand, resident for the whole kernel
-                const uint32_t b_bytes = (uint32_t)blk.kchunks * TCS_N * 16;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar(2 * TCS_STAGES + 4)), "r"(b_bytes) : "memory");
-                for (uint32_t o = 0; o < b_bytes; o += 32768u) {
-                    const uint32_t nb = min(32768u, b_bytes - o);
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 :: "r"(sB_addr + o), "l"(a.blob + blk.b_off + o), "r"(nb), "r"(bar(2 * TCS_STAGES + 4)) : "memory");
+            const uint32_t b_bytes0 = (uint32_t)blk.kchunks[0] * TCS_N * 16;
+            {   // the B operands, resident for the whole kernel
+                const uint32_t b_bytes1 = blk.nsub > 1 ? (uint32_t)blk.kchunks[1] * TCS_N * 16 : 0u;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar(2 * TCS_STAGES + 4)), "r"(b_bytes0 + b_bytes1) : "memory");
+                for (int sub = 0; sub < blk.nsub; ++sub) {
+                    const uint32_t nbytes = sub ? b_bytes1 : b_bytes0, dst = sB_addr + (sub ? b_bytes0 : 0u);
+                    for (uint32_t o = 0; o < nbytes; o += 32768u) {
+                        const uint32_t nb = min(32768u, nbytes - o);
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     :: "r"(dst + o), "l"(a.blob + blk.b_off[sub] + o), "r"(nb), "r"(bar(2 * TCS_STAGES + 4)) : "memory");
+                    }
                 }
                 tcs_wait(bar(2 * TCS_STAGES + 4), 0);
             }
-            const int kpairs = blk.kchunks >> 1;
-            const uint64_t db0 = tcs_desc(sB_addr, TCS_N * 16, 128);
+            const uint64_t dbA = tcs_desc(sB_addr, TCS_N * 16, 128), dbB = tcs_desc(sB_addr + b_bytes0, TCS_N * 16, 128);
+            const int kpA = blk.kchunks[0] >> 1, kpB = blk.kchunks[1] >> 1;
             TCS_PROF(long long w_full = 0; long long w_acc = 0;)
             const long long t_start = clock64();
+            uint32_t use0 = 0, use1 = 0;                                                 // completed uses of each accumulator
             int it = 0;
             for (int tile = rank; tile < a.ntiles; tile += blk.nctas, ++it) {
                 const int st = it % TCS_STAGES; const uint32_t ph = (it / TCS_STAGES) & 1;
-                const uint32_t aph = it & 1;
                 TCS_PROF(long long t0 = clock64();)
                 tcs_wait(bar(st), ph);                                                   // streams built
                 TCS_PROF(w_full += clock64() - t0;)
                 #pragma unroll
                 for (int par = 0; par < 2; ++par) {
-                    TCS_PROF(t0 = clock64();)
-                    tcs_wait(bar(2 * TCS_STAGES + 2 + par), aph ^ 1);                    // accumulator drained
-                    TCS_PROF(w_acc += clock64() - t0;)
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint64_t da0 = tcs_desc(sA_addr + st * TCS_STAGE_BYTES + par * 2 * TCS_PLANE_BYTES, TCS_PLANE_BYTES, 128);
-                    for (int t = 0; t < kpairs; ++t)
-                        tcs_mma(tmem + par * TCS_N, da0 + (uint64_t)(2 * t), db0 + (uint64_t)(2 * t * TCS_N), idesc, t ? 1u : 0u);
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar(2 * TCS_STAGES + par)) : "memory");
+                    for (int sub = 0; sub < blk.nsub; ++sub) {
+                        const int ac = blk.nsub > 1 ? sub : par;
+                        const uint32_t uses = ac ? use1 : use0;
+                        TCS_PROF(t0 = clock64();)
+                        tcs_wait(bar(2 * TCS_STAGES + 2 + ac), (uses & 1) ^ 1);          // accumulator drained
+                        TCS_PROF(w_acc += clock64() - t0;)
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint64_t da0 = tcs_desc(sA_addr + st * TCS_STAGE_BYTES + par * 2 * TCS_PLANE_BYTES, TCS_PLANE_BYTES, 128);
+                        const uint64_t dbs = sub ? dbB : dbA;
+                        const int kp = sub ? kpB : kpA;
+                        for (int t = 0; t < kp; ++t)
+                            tcs_mma(tmem + ac * TCS_N, da0 + (uint64_t)(2 * t), dbs + (uint64_t)(2 * t * TCS_N), idesc, t ? 1u : 0u);
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar(2 * TCS_STAGES + ac)) : "memory");
+                        if (ac) ++use1; else ++use0;
+                    }
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar(TCS_STAGES + st)) : "memory");
             }
@@ -301,43 +319,57 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
             TCS_PROF(if (a.dbg) { a.dbg[blockIdx.x * 8 + 0] = clock64() - t_start; a.dbg[blockIdx.x * 8 + 1] = w_full; a.dbg[blockIdx.x * 8 + 2] = w_acc; a.dbg[blockIdx.x * 8 + 6] = bi; a.dbg[blockIdx.x * 8 + 7] = it; })
         }
     } else {
-        // ---- epilogue: two groups of four warps (one per TMEM lane quarter), group `par` drains accumulator `par` of every tile ----
-        const int q = warp & 3;
-        const int par = (warp - 2) >> 2;
+        // ---- epilogue: 16 warps = {accumulator par} x {column half} x {TMEM lane quarter} ----
+        const int q = warp & 3;                                                          // TMEM lane quarter = warp id % 4
+        const int ac = ((warp - 2) >> 2) & 1;                                            // accumulator this warp drains
+        const int hf = (warp - 2) >> 3;                                                  // column half of the accumulator
         unsigned long long cur_end[2] = {0, 0};                                          // this warp's reserved slice of the candidate list
         uint32_t dead = 0;                                                               // list capacity exhausted
         TCS_PROF(long long w_epi = 0; const long long t_start = clock64();)
+        uint32_t uses = 0;
+        const int per_tile = blk.nsub > 1 ? 2 : 1;                                       // uses of this accumulator per tile
         int it = 0;
-        for (int tile = rank; tile < a.ntiles; tile += blk.nctas, ++it) {
+        for (int tile = rank; tile < a.ntiles; tile += blk.nctas, ++it)
+        for (int u2 = 0; u2 < per_tile; ++u2, ++uses) {
+            const int par = blk.nsub > 1 ? u2 : ac;
+            const int sub = blk.nsub > 1 ? ac : 0;
             const uint32_t v = (uint32_t)tile * 256u + (uint32_t)par + 2u * (uint32_t)(q * 32 + lane);
             const bool inb = v < a.vtotal;
             TCS_PROF(const long long t0 = clock64();)
-            tcs_wait(bar(2 * TCS_STAGES + par), it & 1);
+            tcs_wait(bar(2 * TCS_STAGES + ac), uses & 1);
             TCS_PROF(w_epi += clock64() - t0;)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // four rounds of 64 columns, software pipelined: the next round's tcgen05.ld is in flight while this round is reduced
-            const uint32_t taddr = tmem + par * TCS_N + ((uint32_t)(q * 32) << 16);
-            uint32_t ua0[32], ua1[32], ub0[32], ub1[32];
-            TCS_LDTM32(ua0, taddr); TCS_LDTM32(ua1, taddr + 32);
+            // this warp's 128 columns in four rounds of 32, software pipelined: the next round's tcgen05.ld is in flight while this
+            // round is reduced (the other three epilogue warps of the SM sub-partition fill the remaining latency)
+            const uint32_t taddr = tmem + ac * TCS_N + hf * (TCS_N / 2) + ((uint32_t)(q * 32) << 16);
+            uint32_t ua[32], ub[32];
+            TCS_LDTM32(ua, taddr);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            #define TCS_ROUND(CUR0, CUR1, NXT0, NXT1, R)                                                                            \
+            // the positive columns of a round are only recorded as a bit mask here; the list is written after the accumulator has been
+            // handed back to the MMA warp (the drain, not the appends, is on the tensor pipe's critical path)
+            uint32_t cb0 = 0, cb1 = 0, cb2 = 0, cb3 = 0, anyr = 0;
+            #define TCS_ROUND(CUR, NXT, R, CB)                                                                                      \
             {                                                                                                                         \
-                if ((R) < 3) { TCS_LDTM32(NXT0, taddr + ((R) + 1) * 64); TCS_LDTM32(NXT1, taddr + ((R) + 1) * 64 + 32); }          \
-                const bool pos = inb && fmaxf(tcs_max32(CUR0), tcs_max32(CUR1)) > 0.f;                                                \
-                if (__any_sync(0xffffffffu, pos)) {      /* about one round in ten at the usual thresholds */                       \
-                    const uint32_t bits0 = pos ? tcs_posbits(CUR0) : 0u, bits1 = pos ? tcs_posbits(CUR1) : 0u;                        \
-                    tcs_append(a.list, a.gcount, a.cap, a.overflow, lane, bits0, bits1, (uint32_t)(blk.slot0 + (R) * 64), v, cur_end, &dead); \
+                if ((R) < 3) { TCS_LDTM32(NXT, taddr + ((R) + 1) * 32); }                                                           \
+                const bool pos = inb && tcs_max32(CUR) > 0.f;                                                                         \
+                if (__any_sync(0xffffffffu, pos)) {      /* about one round in twenty at the usual thresholds */                    \
+                    CB = pos ? tcs_posbits(CUR) : 0u; anyr = 1u;                                                                      \
                 }                                                                                                                     \
                 if ((R) < 3) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");                                           \
             }
-            TCS_ROUND(ua0, ua1, ub0, ub1, 0)
-            TCS_ROUND(ub0, ub1, ua0, ua1, 1)
-            TCS_ROUND(ua0, ua1, ub0, ub1, 2)
-            TCS_ROUND(ub0, ub1, ua0, ua1, 3)
+            TCS_ROUND(ua, ub, 0, cb0)
+            TCS_ROUND(ub, ua, 1, cb1)
+            TCS_ROUND(ua, ub, 2, cb2)
+            TCS_ROUND(ub, ua, 3, cb3)
             #undef TCS_ROUND
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar(2 * TCS_STAGES + 2 + par)) : "memory");    // accumulator may be overwritten
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar(2 * TCS_STAGES + 2 + ac)) : "memory");    // accumulator may be overwritten
+            if (anyr) {                                                                   // warp-uniform
+                const uint32_t sb = (uint32_t)(blk.slot0[sub] + hf * (TCS_N / 2));
+                tcs_append(a.list, a.gcount, a.cap, a.overflow, lane, cb0, cb1, sb, v, cur_end, &dead);
+                if (__any_sync(0xffffffffu, (cb2 | cb3) != 0u)) tcs_append(a.list, a.gcount, a.cap, a.overflow, lane, cb2, cb3, sb + 64, v, cur_end, &dead);
+            }
         }
         for (unsigned long long i = cur_end[0] + lane; i < cur_end[1]; i += 32) a.list[i] = ~0ull;
         TCS_PROF(if (a.dbg && warp == 2 && lane == 0) { a.dbg[blockIdx.x * 8 + 3] = w_epi; a.dbg[blockIdx.x * 8 + 4] = clock64() - t_start; })

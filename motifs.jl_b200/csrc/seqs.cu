@@ -93,10 +93,11 @@ static int seqs_alloc(mb200_ctx* ctx, int64_t N, int64_t Lb, mb200_seqs** out) {
     mb200_seqs* s = new mb200_seqs();
     s->N = N; s->Lb = Lb; s->rowwords = (Lb + 15) / 16; s->device = ctx->device;
     size_t bytes = (size_t)(N * s->rowwords + SEQ_PAD_WORDS) * 4;
-    if (cudaMalloc(&s->words, bytes) != cudaSuccess) { cudaGetLastError(); delete s; MB_FAIL(ctx, MB200_E_NOMEM, "cudaMalloc(%zu) for sequences failed", bytes); }
+    s->words = (uint32_t*)mb_pool_alloc(ctx, bytes, &s->words_bytes);
+    if (!s->words) { delete s; MB_FAIL(ctx, MB200_E_NOMEM, "cudaMalloc(%zu) for sequences failed", bytes); }
     // zero the tail pad (the scan kernel reads a few words past the last sequence)
     cudaError_t e = cudaMemsetAsync(s->words + N * s->rowwords, 0, SEQ_PAD_WORDS * 4, ctx->stream);
-    if (e != cudaSuccess) { cudaFree(s->words); delete s; MB_FAIL(ctx, MB200_E_CUDA, "memset: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { mb_pool_free(ctx, s->words, s->words_bytes); delete s; MB_FAIL(ctx, MB200_E_CUDA, "memset: %s", cudaGetErrorString(e)); }
     *out = s;
     return MB200_OK;
 }
@@ -184,7 +185,8 @@ extern "C" int32_t mb200_seqs_from_ascii_async(mb200_ctx* ctx, const uint8_t* as
     const size_t chunk_bytes = (size_t)64 << 20;
     const int64_t rows_per_chunk = std::min<int64_t>(N, (int64_t)std::max<size_t>(1, chunk_bytes / (size_t)Lb));
     const size_t buf = ((size_t)rows_per_chunk * (size_t)Lb + 255) & ~(size_t)255;
-    if (cudaMalloc(&s->stage, 256 + 2 * buf) != cudaSuccess) { cudaGetLastError(); mb200_seqs_free(ctx, s); *out = nullptr; MB_FAIL(ctx, MB200_E_NOMEM, "seqs: staging allocation failed"); }
+    s->stage = (uint8_t*)mb_pool_alloc(ctx, 256 + 2 * buf, &s->stage_bytes);
+    if (!s->stage) { mb200_seqs_free(ctx, s); *out = nullptr; MB_FAIL(ctx, MB200_E_NOMEM, "seqs: staging allocation failed"); }
     cudaStream_t q = ctx->copy_stream;
     s->copy_stream = q; s->pending = true;
     unsigned int* d_bad = (unsigned int*)s->stage;
@@ -215,7 +217,7 @@ int mb_seqs_finish(mb200_ctx* ctx, mb200_seqs* s) {
     if (e == cudaSuccess) e = cudaMemcpy(&h_bad, s->stage, 4, cudaMemcpyDeviceToHost);
     for (auto ev : s->ready) cudaEventDestroy(ev);
     s->ready.clear(); s->ready_end.clear();
-    cudaFree(s->stage); s->stage = nullptr; s->pending = false;
+    mb_pool_free(ctx, s->stage, s->stage_bytes); s->stage = nullptr; s->pending = false;
     if (e != cudaSuccess) MB_FAIL(ctx, MB200_E_CUDA, "seqs: upload failed: %s", cudaGetErrorString(e));
     if (h_bad) MB_FAIL(ctx, MB200_E_BAD_SEQUENCE, "%u words contain a symbol that is not A,C,G,T", h_bad);
     return MB200_OK;
@@ -230,8 +232,8 @@ extern "C" int32_t mb200_seqs_wait(mb200_ctx* ctx, mb200_seqs* s) {
 extern "C" int32_t mb200_seqs_free(mb200_ctx* ctx, mb200_seqs* s) {
     if (!s) return MB200_E_INVALID;
     if (ctx) cudaSetDevice(ctx->device);
-    if (s->pending) { cudaStreamSynchronize(s->copy_stream); for (auto ev : s->ready) cudaEventDestroy(ev); cudaFree(s->stage); s->pending = false; }
-    if (s->words) cudaFree(s->words);
+    if (s->pending) { cudaStreamSynchronize(s->copy_stream); for (auto ev : s->ready) cudaEventDestroy(ev); mb_pool_free(ctx, s->stage, s->stage_bytes); s->pending = false; }
+    if (s->words) mb_pool_free(ctx, s->words, s->words_bytes);
     delete s;
     return MB200_OK;
 }
