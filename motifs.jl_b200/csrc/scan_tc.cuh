@@ -51,6 +51,9 @@ struct TcBlock {                           // what one CTA works on: one block o
     int32_t nsub;                          // 1, or 2: sub-block 0 (the longer one) accumulates in TMEM columns [0,256), sub-block 1 in [256,512)
     int32_t cta0, nctas;                   // CTAs [cta0, cta0 + nctas) work on this entry
     int32_t pad;
+    uint8_t c0[2][TCS_MAX_KCHUNKS / 2];    // per K=16 step t: first accumulator column / 16 with a motif longer than 4t columns.  Slots are
+                                           // sorted by length, so the step only multiplies columns [16 c0, 256): N shrinks along K instead
+                                           // of padding every motif to the longest of its block
 };
 struct TcSlot {                            // per global slot, for the epilogue (npos) and the verifier
     int32_t motif;                         // original motif index, -1: disabled
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
 
     if (tid == 0) {
         for (int i = 0; i < 2 * TCS_STAGES + 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(i)) : "memory");
-        for (int i = 2 * TCS_STAGES + 2; i < 2 * TCS_STAGES + 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" :: "r"(bar(i)) : "memory");   // 8 epilogue warps per accumulator
+        for (int i = 2 * TCS_STAGES + 2; i < 2 * TCS_STAGES + 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 16;" :: "r"(bar(i)) : "memory");   // all 16 epilogue warps drain every accumulator use
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(2 * TCS_STAGES + 4)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -214,8 +217,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
     const uint32_t sA_addr = (uint32_t)__cvta_generic_to_shared(sA), sB_addr = (uint32_t)__cvta_generic_to_shared(sB);
-    // instruction descriptor: D = F32 (1<<4), A = B = F16 (format 0), both K-major, N>>3 at bit 17, M>>4 at bit 24
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(TCS_N >> 3) << 17) | ((uint32_t)(TCS_M >> 4) << 24);
+    // instruction descriptor (built per MMA below): D = F32 (1<<4), A = B = F16 (format 0), both K-major, N>>3 at bit 17, M>>4 at bit 24
 
     if (warp == 0 || warp == TCS_THREADS / 32 - 1) {
         // ---- producers: bases v0 .. v0+319 of the tile -> even stream E[m] = (b[2m], b[2m+1]), odd stream O[m] = (b[2m+1], b[2m+2]),
@@ -307,8 +309,11 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
                         const uint64_t da0 = tcs_desc(sA_addr + st * TCS_STAGE_BYTES + par * 2 * TCS_PLANE_BYTES, TCS_PLANE_BYTES, 128);
                         const uint64_t dbs = sub ? dbB : dbA;
                         const int kp = sub ? kpB : kpA;
-                        for (int t = 0; t < kp; ++t)
-                            tcs_mma(tmem + ac * TCS_N, da0 + (uint64_t)(2 * t), dbs + (uint64_t)(2 * t * TCS_N), idesc, t ? 1u : 0u);
+                        for (int t = 0; t < kp; ++t) {
+                            const uint32_t c0 = (uint32_t)blk.c0[sub][t] * 16u;          // 0 for t = 0: the first step initialises all 256 columns
+                            const uint32_t idn = (1u << 4) | ((uint32_t)((TCS_N - c0) >> 3) << 17) | ((uint32_t)(TCS_M >> 4) << 24);
+                            tcs_mma(tmem + ac * TCS_N + c0, da0 + (uint64_t)(2 * t), dbs + (uint64_t)(2 * t * TCS_N + c0), idn, t ? 1u : 0u);
+                        }
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar(2 * TCS_STAGES + ac)) : "memory");
                         if (ac) ++use1; else ++use0;
                     }
@@ -319,56 +324,41 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
             TCS_PROF(if (a.dbg) { a.dbg[blockIdx.x * 8 + 0] = clock64() - t_start; a.dbg[blockIdx.x * 8 + 1] = w_full; a.dbg[blockIdx.x * 8 + 2] = w_acc; a.dbg[blockIdx.x * 8 + 6] = bi; a.dbg[blockIdx.x * 8 + 7] = it; })
         }
     } else {
-        // ---- epilogue: 16 warps = {accumulator par} x {column half} x {TMEM lane quarter} ----
+        // ---- epilogue: 16 warps = {TMEM lane quarter} x {64-column group}; every warp drains its 32 lanes x 64 columns of EVERY
+        //      accumulator use, in the MMA warp's order.  Both tcgen05.ld of a use are issued before the first wait: with four warps
+        //      per SM sub-partition that keeps ~32 KB of TMEM reads in flight (the loads, ~200 clocks of latency each, not the
+        //      reduction, bound the drain) ----
         const int q = warp & 3;                                                          // TMEM lane quarter = warp id % 4
-        const int ac = ((warp - 2) >> 2) & 1;                                            // accumulator this warp drains
-        const int hf = (warp - 2) >> 3;                                                  // column half of the accumulator
+        const int cg = (warp - 2) >> 2;                                                  // column group
         unsigned long long cur_end[2] = {0, 0};                                          // this warp's reserved slice of the candidate list
         uint32_t dead = 0;                                                               // list capacity exhausted
         TCS_PROF(long long w_epi = 0; const long long t_start = clock64();)
-        uint32_t uses = 0;
-        const int per_tile = blk.nsub > 1 ? 2 : 1;                                       // uses of this accumulator per tile
+        uint32_t use0 = 0, use1 = 0;                                                     // completed uses of each accumulator
         int it = 0;
         for (int tile = rank; tile < a.ntiles; tile += blk.nctas, ++it)
-        for (int u2 = 0; u2 < per_tile; ++u2, ++uses) {
-            const int par = blk.nsub > 1 ? u2 : ac;
-            const int sub = blk.nsub > 1 ? ac : 0;
+        for (int par = 0; par < 2; ++par)
+        for (int sub = 0; sub < blk.nsub; ++sub) {
+            const int ac = blk.nsub > 1 ? sub : par;
+            const uint32_t uses = ac ? use1 : use0;
+            if (ac) ++use1; else ++use0;
             const uint32_t v = (uint32_t)tile * 256u + (uint32_t)par + 2u * (uint32_t)(q * 32 + lane);
             const bool inb = v < a.vtotal;
             TCS_PROF(const long long t0 = clock64();)
             tcs_wait(bar(2 * TCS_STAGES + ac), uses & 1);
             TCS_PROF(w_epi += clock64() - t0;)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // this warp's 128 columns in four rounds of 32, software pipelined: the next round's tcgen05.ld is in flight while this
-            // round is reduced (the other three epilogue warps of the SM sub-partition fill the remaining latency)
-            const uint32_t taddr = tmem + ac * TCS_N + hf * (TCS_N / 2) + ((uint32_t)(q * 32) << 16);
+            const uint32_t taddr = tmem + ac * TCS_N + cg * 64 + ((uint32_t)(q * 32) << 16);
             uint32_t ua[32], ub[32];
             TCS_LDTM32(ua, taddr);
+            TCS_LDTM32(ub, taddr + 32);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            // the positive columns of a round are only recorded as a bit mask here; the list is written after the accumulator has been
-            // handed back to the MMA warp (the drain, not the appends, is on the tensor pipe's critical path)
-            uint32_t cb0 = 0, cb1 = 0, cb2 = 0, cb3 = 0, anyr = 0;
-            #define TCS_ROUND(CUR, NXT, R, CB)                                                                                      \
-            {                                                                                                                         \
-                if ((R) < 3) { TCS_LDTM32(NXT, taddr + ((R) + 1) * 32); }                                                           \
-                const bool pos = inb && tcs_max32(CUR) > 0.f;                                                                         \
-                if (__any_sync(0xffffffffu, pos)) {      /* about one round in twenty at the usual thresholds */                    \
-                    CB = pos ? tcs_posbits(CUR) : 0u; anyr = 1u;                                                                      \
-                }                                                                                                                     \
-                if ((R) < 3) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");                                           \
-            }
-            TCS_ROUND(ua, ub, 0, cb0)
-            TCS_ROUND(ub, ua, 1, cb1)
-            TCS_ROUND(ua, ub, 2, cb2)
-            TCS_ROUND(ub, ua, 3, cb3)
-            #undef TCS_ROUND
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar(2 * TCS_STAGES + 2 + ac)) : "memory");    // accumulator may be overwritten
-            if (anyr) {                                                                   // warp-uniform
-                const uint32_t sb = (uint32_t)(blk.slot0[sub] + hf * (TCS_N / 2));
-                tcs_append(a.list, a.gcount, a.cap, a.overflow, lane, cb0, cb1, sb, v, cur_end, &dead);
-                if (__any_sync(0xffffffffu, (cb2 | cb3) != 0u)) tcs_append(a.list, a.gcount, a.cap, a.overflow, lane, cb2, cb3, sb + 64, v, cur_end, &dead);
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar(2 * TCS_STAGES + 2 + ac)) : "memory");    // the values are in registers: the accumulator may be overwritten
+            const bool pos = inb && fmaxf(tcs_max32(ua), tcs_max32(ub)) > 0.f;
+            if (__any_sync(0xffffffffu, pos)) {          /* about one use in ten at the usual thresholds */
+                const uint32_t cb0 = pos ? tcs_posbits(ua) : 0u, cb1 = pos ? tcs_posbits(ub) : 0u;
+                tcs_append(a.list, a.gcount, a.cap, a.overflow, lane, cb0, cb1, (uint32_t)(blk.slot0[sub] + cg * 64), v, cur_end, &dead);
             }
         }
         for (unsigned long long i = cur_end[0] + lane; i < cur_end[1]; i += 32) a.list[i] = ~0ull;
