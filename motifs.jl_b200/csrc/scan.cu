@@ -847,19 +847,6 @@ static bool build_tc_plan(const ScanPlan& P, const uint16_t* pwms, const int64_t
                 for (int b = 0; b < 4; ++b) Bm[((size_t)(j >> 1) * TCS_N + sidx) * 8 + 4 * (j & 1) + b] = c[(size_t)j * 4 + b];
         }
     }
-    // per block and K=16 step t (PWM columns 4t .. 4t+3): first slot, rounded down to 16, whose motif is longer than 4t columns
-    std::vector<std::vector<uint8_t>> c0tab(nblocks, std::vector<uint8_t>(TCS_MAX_KCHUNKS / 2, 0));
-    for (int bi = 0; bi < nblocks; ++bi)
-        for (int t = 1; t < kcs[bi] / 2; ++t) {
-            int first = TCS_N - 16;
-            for (int sidx = 0; sidx < TCS_N; ++sidx)
-                if ((int)col0[bi * TCS_N + sidx].size() / 4 > 4 * t) { first = sidx; break; }
-            c0tab[bi][t] = (uint8_t)(std::min(first, TCS_N - 16) / 16);
-        }
-    // Measured (2 M x 200 bp, 500 PWMs): shrinking N along K executes 14 % fewer MMA flops but the scan gets 14 % SLOWER (67.7 -> 77.3 ms):
-    // every MMA re-reads its 4 KB A operand whatever N is, and the kernel already executes MMA flops at the chip's sustained rate
-    // (MEASURED_PEAKS.json).  Kept for experiments only.
-    if (!getenv("MB200_SCAN_TC_SHRINKN")) for (auto& v : c0tab) std::fill(v.begin(), v.end(), (uint8_t)0);
     // Work entries: blocks sorted by length are paired with their neighbour while both B operands fit in shared memory.  Each block
     // of a pair owns one accumulator, so an accumulator is drained (>= ~1000 clocks: TMEM read bandwidth + barrier latencies) under the
     // MMAs of the other block: two long blocks hide each other's drains completely and run at the MMA rate; two short blocks are
@@ -876,12 +863,10 @@ static bool build_tc_plan(const ScanPlan& P, const uint16_t* pwms, const int64_t
         TcBlock e; memset(&e, 0, sizeof e);
         const int L = ord[i];
         e.b_off[0] = boff[L]; e.kchunks[0] = kcs[L]; e.slot0[0] = L * TCS_N; e.nsub = 1;
-        memcpy(e.c0[0], c0tab[L].data(), TCS_MAX_KCHUNKS / 2);
         size_t bbytes = (size_t)kcs[L] * TCS_N * 16;
         if (i + 1 < nblocks && !no_pair && bbytes + (size_t)kcs[ord[i + 1]] * TCS_N * 16 <= b_budget) {
             const int S = ord[i + 1];
             e.b_off[1] = boff[S]; e.kchunks[1] = kcs[S]; e.slot0[1] = S * TCS_N; e.nsub = 2;
-            memcpy(e.c0[1], c0tab[S].data(), TCS_MAX_KCHUNKS / 2);
             bbytes += (size_t)kcs[S] * TCS_N * 16;
             cost.push_back(2.0 * std::max(kcs[L] * 64.0, drain) + 2.0 * std::max(kcs[S] * 64.0, drain) + 100.0);
             i += 2;

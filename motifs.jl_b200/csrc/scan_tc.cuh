@@ -51,9 +51,6 @@ struct TcBlock {                           // what one CTA works on: one block o
     int32_t nsub;                          // 1, or 2: sub-block 0 (the longer one) accumulates in TMEM columns [0,256), sub-block 1 in [256,512)
     int32_t cta0, nctas;                   // CTAs [cta0, cta0 + nctas) work on this entry
     int32_t pad;
-    uint8_t c0[2][TCS_MAX_KCHUNKS / 2];    // per K=16 step t: first accumulator column / 16 with a motif longer than 4t columns.  Slots are
-                                           // sorted by length, so the step only multiplies columns [16 c0, 256): N shrinks along K instead
-                                           // of padding every motif to the longest of its block
 };
 struct TcSlot {                            // per global slot, for the epilogue (npos) and the verifier
     int32_t motif;                         // original motif index, -1: disabled
@@ -77,9 +74,14 @@ __device__ __forceinline__ uint64_t tcs_desc(uint32_t smem_addr, uint32_t lbo_by
     // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
+// Issued by the whole (converged) MMA warp: one elected lane executes the instruction.  Keeping the warp converged lets the compiler
+// hold descriptors, TMEM address and instruction descriptor in uniform registers (no per-MMA R2UR/ELECT sequences).
 __device__ __forceinline__ void tcs_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xFFFFFFFF;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
                  :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tcs_commit(uint32_t bar) {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xFFFFFFFF;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" :: "r"(bar) : "memory");
 }
 __device__ __forceinline__ void tcs_wait(uint32_t bar, uint32_t parity) {
     uint32_t done, spins = 0;
@@ -174,6 +176,27 @@ __device__ __noinline__ void tcs_append(unsigned long long* list, unsigned long 
     cur_end[0] = cur + total; cur_end[1] = end;
 }
 
+// The K loop of one accumulator use, fully unrolled per trip count: with compile-time t the descriptors of step t are the first
+// ones plus constants (one uniform 64-bit add each).  A run-time loop costs ~26 dependent instructions per MMA in the single issuing
+// thread (ELECT + seven R2UR per MMA): ~180 clocks per 128-clock MMA, i.e. the issuing thread, not the tensor pipe, set the pace.
+template <int KP>
+__device__ __forceinline__ void tcs_issue_n(uint32_t tmem_d, uint64_t da0, uint64_t db0, uint32_t idesc) {
+    #pragma unroll
+    for (int t = 0; t < KP; ++t) tcs_mma(tmem_d, da0 + (uint64_t)(2 * t), db0 + (uint64_t)(2 * t * TCS_N), idesc, t ? 1u : 0u);
+}
+__device__ __forceinline__ void tcs_issue(int kp, uint32_t tmem_d, uint64_t da0, uint64_t db0, uint32_t idesc) {
+    switch (kp) {
+        case 1: tcs_issue_n<1>(tmem_d, da0, db0, idesc); break;   case 2: tcs_issue_n<2>(tmem_d, da0, db0, idesc); break;
+        case 3: tcs_issue_n<3>(tmem_d, da0, db0, idesc); break;   case 4: tcs_issue_n<4>(tmem_d, da0, db0, idesc); break;
+        case 5: tcs_issue_n<5>(tmem_d, da0, db0, idesc); break;   case 6: tcs_issue_n<6>(tmem_d, da0, db0, idesc); break;
+        case 7: tcs_issue_n<7>(tmem_d, da0, db0, idesc); break;   case 8: tcs_issue_n<8>(tmem_d, da0, db0, idesc); break;
+        case 9: tcs_issue_n<9>(tmem_d, da0, db0, idesc); break;   case 10: tcs_issue_n<10>(tmem_d, da0, db0, idesc); break;
+        case 11: tcs_issue_n<11>(tmem_d, da0, db0, idesc); break; case 12: tcs_issue_n<12>(tmem_d, da0, db0, idesc); break;
+        case 13: tcs_issue_n<13>(tmem_d, da0, db0, idesc); break; case 14: tcs_issue_n<14>(tmem_d, da0, db0, idesc); break;
+        case 15: tcs_issue_n<15>(tmem_d, da0, db0, idesc); break; default: tcs_issue_n<16>(tmem_d, da0, db0, idesc); break;
+    }
+}
+
 // Work item = one tile of 256 consecutive virtual start positions = two parities (even / odd offsets) of 128 rows.
 // Single block: parity 0 accumulates in TMEM columns [0,256), parity 1 in [256,512).
 // Paired blocks (nsub = 2): draining 128 x 256 FP32 accumulators costs >= 512 clocks of TMEM read bandwidth, more than the MMA
@@ -217,7 +240,8 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
     const uint32_t sA_addr = (uint32_t)__cvta_generic_to_shared(sA), sB_addr = (uint32_t)__cvta_generic_to_shared(sB);
-    // instruction descriptor (built per MMA below): D = F32 (1<<4), A = B = F16 (format 0), both K-major, N>>3 at bit 17, M>>4 at bit 24
+    // instruction descriptor: D = F32 (1<<4), A = B = F16 (format 0), both K-major, N>>3 at bit 17, M>>4 at bit 24
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(TCS_N >> 3) << 17) | ((uint32_t)(TCS_M >> 4) << 24);
 
     if (warp == 0 || warp == TCS_THREADS / 32 - 1) {
         // ---- producers: bases v0 .. v0+319 of the tile -> even stream E[m] = (b[2m], b[2m+1]), odd stream O[m] = (b[2m+1], b[2m+2]),
@@ -271,9 +295,9 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
         }
         TCS_PROF(if (a.dbg && warp == 0 && lane == 0) a.dbg[blockIdx.x * 8 + 5] = w_prod;)
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // ---- MMA warp: all 32 lanes run this code converged; tcs_mma / tcs_commit elect the issuing lane ----
             const uint32_t b_bytes0 = (uint32_t)blk.kchunks[0] * TCS_N * 16;
-            {   // the B operands, resident for the whole kernel
+            if (lane == 0) {   // the B operands, resident for the whole kernel
                 const uint32_t b_bytes1 = blk.nsub > 1 ? (uint32_t)blk.kchunks[1] * TCS_N * 16 : 0u;
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar(2 * TCS_STAGES + 4)), "r"(b_bytes0 + b_bytes1) : "memory");
                 for (int sub = 0; sub < blk.nsub; ++sub) {
@@ -284,8 +308,8 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
                                      :: "r"(dst + o), "l"(a.blob + blk.b_off[sub] + o), "r"(nb), "r"(bar(2 * TCS_STAGES + 4)) : "memory");
                     }
                 }
-                tcs_wait(bar(2 * TCS_STAGES + 4), 0);
             }
+            tcs_wait(bar(2 * TCS_STAGES + 4), 0);
             const uint64_t dbA = tcs_desc(sB_addr, TCS_N * 16, 128), dbB = tcs_desc(sB_addr + b_bytes0, TCS_N * 16, 128);
             const int kpA = blk.kchunks[0] >> 1, kpB = blk.kchunks[1] >> 1;
             TCS_PROF(long long w_full = 0; long long w_acc = 0;)
@@ -309,19 +333,15 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
                         const uint64_t da0 = tcs_desc(sA_addr + st * TCS_STAGE_BYTES + par * 2 * TCS_PLANE_BYTES, TCS_PLANE_BYTES, 128);
                         const uint64_t dbs = sub ? dbB : dbA;
                         const int kp = sub ? kpB : kpA;
-                        for (int t = 0; t < kp; ++t) {
-                            const uint32_t c0 = (uint32_t)blk.c0[sub][t] * 16u;          // 0 for t = 0: the first step initialises all 256 columns
-                            const uint32_t idn = (1u << 4) | ((uint32_t)((TCS_N - c0) >> 3) << 17) | ((uint32_t)(TCS_M >> 4) << 24);
-                            tcs_mma(tmem + ac * TCS_N + c0, da0 + (uint64_t)(2 * t), dbs + (uint64_t)(2 * t * TCS_N + c0), idn, t ? 1u : 0u);
-                        }
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar(2 * TCS_STAGES + ac)) : "memory");
+                        tcs_issue(kp, tmem + ac * TCS_N, da0, dbs, idesc);
+                        tcs_commit(bar(2 * TCS_STAGES + ac));
                         if (ac) ++use1; else ++use0;
                     }
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar(TCS_STAGES + st)) : "memory");
+                tcs_commit(bar(TCS_STAGES + st));
             }
-            if (a.clocks) { a.clocks[blockIdx.x * 2] = clock64() - t_start; a.clocks[blockIdx.x * 2 + 1] = it; }
-            TCS_PROF(if (a.dbg) { a.dbg[blockIdx.x * 8 + 0] = clock64() - t_start; a.dbg[blockIdx.x * 8 + 1] = w_full; a.dbg[blockIdx.x * 8 + 2] = w_acc; a.dbg[blockIdx.x * 8 + 6] = bi; a.dbg[blockIdx.x * 8 + 7] = it; })
+            if (a.clocks && lane == 0) { a.clocks[blockIdx.x * 2] = clock64() - t_start; a.clocks[blockIdx.x * 2 + 1] = it; }
+            TCS_PROF(if (a.dbg && lane == 0) { a.dbg[blockIdx.x * 8 + 0] = clock64() - t_start; a.dbg[blockIdx.x * 8 + 1] = w_full; a.dbg[blockIdx.x * 8 + 2] = w_acc; a.dbg[blockIdx.x * 8 + 6] = bi; a.dbg[blockIdx.x * 8 + 7] = it; })
         }
     } else {
         // ---- epilogue: 16 warps = {TMEM lane quarter} x {64-column group}; every warp drains its 32 lanes x 64 columns of EVERY
