@@ -159,10 +159,15 @@ __device__ __noinline__ void tcs_append(unsigned long long* list, unsigned long 
                                         uint32_t bits0, uint32_t bits1, uint32_t slot_base, uint32_t v, unsigned long long* cur_end, uint32_t* dead) {
     if (*dead) return;
     const uint32_t cnt = __popc(bits0) + __popc(bits1);
-    uint32_t incl = cnt;                                                                 // inclusive prefix sum over lanes
-    #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t who = __ballot_sync(0xffffffffu, cnt != 0u);
+    uint32_t incl = cnt, total;                                                          // inclusive prefix sum over lanes
+    if ((who & (who - 1u)) == 0u) {                                                      // the usual case: one lane has candidates
+        total = __shfl_sync(0xffffffffu, cnt, __ffs(who) - 1);
+    } else {
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        total = __shfl_sync(0xffffffffu, incl, 31);
+    }
     unsigned long long cur = cur_end[0], end = cur_end[1];
     if (cur + total > end) {
         if (total > TCS_RESERVE) { if (lane == 0) atomicExch(overflow, 1u); *dead = 1u; return; }     // cannot happen: 32 lanes x 64 columns > 256 only at absurd densities
@@ -375,9 +380,12 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar(2 * TCS_STAGES + 2 + ac)) : "memory");    // the values are in registers: the accumulator may be overwritten
-            const bool pos = inb && fmaxf(tcs_max32(ua), tcs_max32(ub)) > 0.f;
+            const float ma = tcs_max32(ua), mb = tcs_max32(ub);
+            const bool pos = inb && fmaxf(ma, mb) > 0.f;
             if (__any_sync(0xffffffffu, pos)) {          /* about one use in ten at the usual thresholds */
-                const uint32_t cb0 = pos ? tcs_posbits(ua) : 0u, cb1 = pos ? tcs_posbits(ub) : 0u;
+                uint32_t cb0 = 0u, cb1 = 0u;             // bit masks of the positive columns, only for the chunk(s) that have any
+                if (__any_sync(0xffffffffu, inb && ma > 0.f)) cb0 = pos ? tcs_posbits(ua) : 0u;
+                if (__any_sync(0xffffffffu, inb && mb > 0.f)) cb1 = pos ? tcs_posbits(ub) : 0u;
                 tcs_append(a.list, a.gcount, a.cap, a.overflow, lane, cb0, cb1, (uint32_t)(blk.slot0[sub] + cg * 64), v, cur_end, &dead);
             }
         }
