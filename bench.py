@@ -279,8 +279,9 @@ def bench_scan(args, ctx, torch, dist, world, rank, local, dev, stream):
             hbm = dict(out["roofline"]); hbm.pop("binding", None); hbm.pop("traffic", None); hbm["kernel"] = "k_scan_tc"
             hbm["note"] = "algorithmic HBM bytes (0.25 B/bp + tables) over the same kernel time: the scan is not HBM bound (SURVEY §8d)"
             out["roofline"] = {"bound": "tensor", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf / tf_peak,
-                               # ncu --set full of one launch (profiles/r01_scan_tc_ncu_full_summary.csv): dram read+write per launch
-                               "traffic": None,
+                               # ncu --set full of one launch (profiles/r01_scan_tc_ncu_full_summary.csv): dram read + write = 15.96 MB for
+                               # 291 271 sequences = 54.8 B per sequence (algorithmic: 50 B packed sequence + the tables once)
+                               "traffic": 54.8 * (n_local / launches_per_step) if (Lb == 200 and K == 500) else None,
                                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback",
                                "kernel": "k_scan_tc", "ms_per_launch": ms_per_launch,
                                "kernel_share_of_step": (t_scan / args.steps) / ms_step,
