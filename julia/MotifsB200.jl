@@ -18,6 +18,8 @@ struct HParams        # mb200_hparams = Hyperparam (model.jl:1-14)
 end
 
 const SCAN_FWD, SCAN_RC, SCAN_WANT_HITS, SCAN_WANT_COUNTS = UInt32(1), UInt32(2), UInt32(4), UInt32(8)
+const SCAN_NO_TENSOR = UInt32(16)      # thresholded scans: keep the SIMT kernel (default: tcgen05 pre-filter + exact re-scoring, same hit sets)
+scan_last_path(ctx) = ccall((:mb200_scan_last_path, lib), Int32, (Ptr{Cvoid},), ctx)   # 0 SIMT, 1 tensor-core path, 2 fell back
 
 check(ctx, rc) = rc == 0 || error("libmotifs_b200 ($rc): " * unsafe_string(ccall((:mb200_last_error, lib), Cstring, (Ptr{Cvoid},), ctx)))
 
