@@ -116,6 +116,14 @@ int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs,
  * (thresholded scans, default), 2 = started on the tensor-core path and fell back to scan_kernel (candidate list overflow). */
 int32_t mb200_scan_last_path(const mb200_ctx* ctx);
 
+/* Diagnostic, host arithmetic only (no ctx, no device): the error bound E and pre-filter threshold t' = t - E - eps32 the tensor-core
+ * path uses for one (motif, strand) slot, so that its guarantee "Float16 running sum > t  =>  real sum > t'" can be checked exhaustively
+ * on the CPU (tests/test_scan_prefilter_cpu.py).  cols_f16: len x 4 Float16 bits, row = PWM column in scoring order, entries {A,C,G,T};
+ * col0_f16 (4 values, may be NULL): column 0 of the B operand = entries of column 0 minus t', rounded up.  *possible = 0 when no window
+ * can exceed the threshold (the slot is disabled).  MB200_E_UNSUPPORTED for non-finite inputs (those calls use the SIMT kernel).       */
+int32_t mb200_scan_prefilter_bound(const uint16_t* cols_f16, int32_t len, uint16_t thresh_f16, double* E, double* t_prefilter,
+                                   uint16_t* col0_f16, int32_t* possible);
+
 /* Score histogram of the unthresholded scan (hits = score > 0): hist[k*32768 + b] = number of hits of motif k whose Float16
  * score has the 15-bit pattern b (positive halves order like their bit patterns).  Replaces the hit lists as the input of the
  * threshold sweep in get_best_thresh (inference/_s2_filter_pos_w_scores.jl:99-113) and of get_max_score / get_min_score

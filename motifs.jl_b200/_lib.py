@@ -76,6 +76,7 @@ def load():
         "mb200_seqs_download": (i32, [p, p, p, i64]),
         "mb200_scan": (i32, [p, p, p, p, i32, i32, p, C.c_uint32, p, i64, C.POINTER(i64), p]),
         "mb200_scan_last_path": (i32, [p]),
+        "mb200_scan_prefilter_bound": (i32, [p, i32, C.c_uint16, p, p, p, p]),
         "mb200_scan_hist": (i32, [p, p, p, p, i32, i32, C.c_uint32, p]),
         "mb200_csc_create": (i32, [p, C.POINTER(HParams), i64, i32, i32, C.POINTER(p)]),
         "mb200_csc_destroy": (i32, [p, p]),
@@ -225,6 +226,17 @@ def scan_last_path(ctx: "Context") -> int:
     """0: the last mb200_scan ran scan_kernel (SIMT), 1: tensor-core pre-filter + exact re-scoring, 2: started on the tensor-core
     path and fell back (candidate list overflow)."""
     return int(ctx._lib.mb200_scan_last_path(ctx._h))
+
+
+def scan_prefilter_bound(cols_f16, thresh_f16):
+    """mb200_scan_prefilter_bound: (E, t', column 0 of the B operand as float16[4], possible) for one slot; cols_f16: (len, 4)."""
+    c = np.ascontiguousarray(cols_f16, np.float16).view(np.uint16)
+    E, tp, ok = C.c_double(), C.c_double(), C.c_int32()
+    col0 = np.zeros(4, np.uint16)
+    rc = load().mb200_scan_prefilter_bound(_ptr(c), c.shape[0], int(np.float16(thresh_f16).view(np.uint16)), C.byref(E), C.byref(tp), _ptr(col0), C.byref(ok))
+    if rc != 0:
+        raise ValueError(f"mb200_scan_prefilter_bound failed ({rc})")
+    return E.value, tp.value, col0.view(np.float16), bool(ok.value)
 
 
 def count_matrices(ctx: "Context", seqs: "Sequences", sites, lens):

@@ -754,6 +754,16 @@ static bool tc_assign_ctas(std::vector<TcBlock>& blocks, const std::vector<doubl
     return true;
 }
 
+// Pre-filter threshold of one slot: T' = t - E - eps32, eps32 for the FP32 accumulation in the tensor core (operands exact, possibly
+// truncating adds, subnormal operands possibly flushed).  A = sum over columns of the largest |entry|.
+static bool tc_prefilter_threshold(const std::vector<double>& w, int len, double t, double A, double* E_out, double* Tp_out) {
+    double E = 0.0;
+    if (!tc_error_bound(w, len, t, &E)) return false;
+    const double eps32 = (A + std::fabs(t) + E) * (1.0 / 8192.0) + len * 6.2e-5;
+    *E_out = E; *Tp_out = t - E - eps32;
+    return true;
+}
+
 struct TcPlan {
     std::vector<uint8_t> blob;
     std::vector<TcBlock> blocks;
@@ -802,11 +812,8 @@ static bool build_tc_plan(const ScanPlan& P, const uint16_t* pwms, const int64_t
                 }
                 A += am;
             }
-            double E = 0.0;
-            if (!tc_error_bound(w, len, t, &E)) continue;          // the best window cannot exceed the threshold
-            // FP32 accumulation in the tensor core (operands exact, possibly truncating adds, subnormal operands possibly flushed)
-            const double eps32 = (A + std::fabs(t) + E) * (1.0 / 8192.0) + len * 6.2e-5;
-            const double Tp = t - E - eps32;
+            double E = 0.0, Tp = 0.0;
+            if (!tc_prefilter_threshold(w, len, t, A, &E, &Tp)) continue;       // the best window cannot exceed the threshold
             if (A + std::fabs(Tp) > 30000.0) return false;
             TcSlot sl; memset(&sl, 0, sizeof sl);
             sl.motif = k; sl.strand = strand; sl.len = len; sl.npos = (int32_t)std::max<int64_t>(0, Lb - len + 1); sl.thr = tb;
@@ -1378,6 +1385,30 @@ extern "C" int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs, const uint
                               int32_t maxlen, const uint16_t* thresh_f16, uint32_t flags, mb200_hit* hits, int64_t hits_cap,
                               int64_t* n_hits, int64_t* counts) {
     return scan_impl(ctx, seqs, pwms_f16, lens, K, maxlen, thresh_f16, flags, hits, hits_cap, n_hits, counts, nullptr);
+}
+
+// Diagnostic (host arithmetic only, ctx-free): the tensor-core pre-filter's error bound and threshold for one (motif, strand) slot.
+// cols_f16: len x 4 Float16 bit patterns, row = PWM column in scoring order, entries {A,C,G,T}; thresh_f16 as passed to mb200_scan.
+extern "C" int32_t mb200_scan_prefilter_bound(const uint16_t* cols_f16, int32_t len, uint16_t thresh_f16, double* E, double* t_prefilter,
+                                              uint16_t* col0_f16, int32_t* possible) {
+    if (!cols_f16 || len < 1 || len > MB200_MAX_MOTIF_LEN || !E || !t_prefilter || !possible) return MB200_E_INVALID;
+    std::vector<double> w((size_t)len * 4);
+    double A = 0.0;
+    for (int j = 0; j < len; ++j) {
+        double am = 0.0;
+        for (int b = 0; b < 4; ++b) {
+            if (h16_nonfinite(cols_f16[j * 4 + b])) return MB200_E_UNSUPPORTED;
+            w[(size_t)j * 4 + b] = (double)h16_to_float(cols_f16[j * 4 + b]);
+            am = std::max(am, std::fabs(w[(size_t)j * 4 + b]));
+        }
+        A += am;
+    }
+    if (h16_nonfinite(thresh_f16)) return MB200_E_UNSUPPORTED;
+    const double t = std::max(0.0, (double)h16_to_float(thresh_f16));
+    *E = 0.0; *t_prefilter = 0.0;
+    *possible = tc_prefilter_threshold(w, len, t, A, E, t_prefilter) ? 1 : 0;
+    if (*possible && col0_f16) for (int b = 0; b < 4; ++b) col0_f16[b] = h16_round_up(w[b] - *t_prefilter);      // what column 0 of the B operand holds
+    return MB200_OK;
 }
 
 extern "C" int32_t mb200_scan_last_path(const mb200_ctx* ctx) { return ctx ? ctx->last_scan_path : MB200_E_INVALID; }
