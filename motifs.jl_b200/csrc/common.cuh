@@ -18,6 +18,7 @@ struct mb200_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;            // stream every kernel of this ctx is launched on
     cudaStream_t copy_stream = nullptr;       // uploads of mb200_seqs_from_ascii_async (created on first use)
+    cudaStream_t aux_stream = nullptr;        // tensor-core scan: re-scoring + counting of batch i run here under the pre-filter of batch i+1
     std::string err;
     // timing of the last call
     float ms[T_N] = {0};
@@ -30,6 +31,7 @@ struct mb200_ctx {
     int last_scan_path = 0;                   // mb200_scan_last_path
     // freed sequence stores / staging buffers kept for the next upload (cudaMalloc + cudaFree of 0.5 GB cost 100s of ms per call)
     std::vector<std::pair<void*, size_t>> pool; size_t pool_bytes = 0;
+    std::vector<int32_t> tc_cost_sig; std::vector<double> tc_cost;   // tensor-core scan: measured clocks per tile of the last block structure
     size_t mask_clean_bytes = 0;              // leading bytes of bufs[2] (hit masks) known to be zero (tensor-core scan path)
 };
 
@@ -64,6 +66,11 @@ struct MbTimers {
         cudaEventRecord(s.a, ctx->stream); spans.push_back(s); return (int)spans.size() - 1;
     }
     void end(int id) { cudaEventRecord(spans[id].b, ctx->stream); }
+    int begin_on(int slot, cudaStream_t q) {
+        MbSpan s; s.slot = slot; cudaEventCreate(&s.a); cudaEventCreate(&s.b);
+        cudaEventRecord(s.a, q); spans.push_back(s); return (int)spans.size() - 1;
+    }
+    void end_on(int id, cudaStream_t q) { cudaEventRecord(spans[id].b, q); }
     void collect() {   // call after the stream was synchronised
         for (auto& s : spans) { float ms = 0; if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) ctx->ms[s.slot] += ms;
             cudaEventDestroy(s.a); cudaEventDestroy(s.b); }

@@ -36,6 +36,7 @@ extern "C" int32_t mb200_destroy(mb200_ctx* ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (auto& b : ctx->pool) cudaFree(b.first);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return MB200_OK;

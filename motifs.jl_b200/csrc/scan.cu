@@ -435,8 +435,9 @@ __global__ void __launch_bounds__(256) count_kernel(const uint32_t* __restrict__
 // them); all other units have no hits and contribute nothing.  Clears the words it reads.
 __global__ void __launch_bounds__(256) count_listed_kernel(uint32_t* __restrict__ mask, const uint32_t* __restrict__ units, const unsigned long long* __restrict__ n_units,
                                                            int32_t W, int32_t K2pad, const int32_t* __restrict__ pair2motif, const int32_t* __restrict__ pairlen,
-                                                           unsigned long long* __restrict__ counts) {
+                                                           unsigned long long* __restrict__ counts, const unsigned long long* __restrict__ overflow) {
     const int32_t P = K2pad / 2;
+    if (overflow && *overflow) return;                                                    // candidate list overflowed: the batch is re-run on scan_kernel
     const unsigned long long total = *n_units;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
         const uint32_t g = units[i];
@@ -769,6 +770,7 @@ struct TcPlan {
     std::vector<TcBlock> blocks;
     std::vector<TcSlot> slots;
     size_t max_b_bytes = 0;                // largest B operand footprint of an entry
+    std::vector<double> cost;              // clocks per tile of every entry (model, then measured)
 };
 
 // false: this call is not eligible for the tensor-core path (the caller keeps scan_kernel).
@@ -875,15 +877,18 @@ static bool build_tc_plan(const ScanPlan& P, const uint16_t* pwms, const int64_t
             const int S = ord[i + 1];
             e.b_off[1] = boff[S]; e.kchunks[1] = kcs[S]; e.slot0[1] = S * TCS_N; e.nsub = 2;
             bbytes += (size_t)kcs[S] * TCS_N * 16;
-            cost.push_back(2.0 * std::max(kcs[L] * 64.0, drain) + 2.0 * std::max(kcs[S] * 64.0, drain) + 100.0);
+            // measured on config 4 (profiles/r01_scan_tc_role_clocks.txt): 1.19 x the MMA clocks when the MMAs bind, ~4 drains of
+            // ~1150 clocks when they do not
+            cost.push_back(std::max(1.19 * 2.0 * (kcs[L] + kcs[S]) * 64.0, 4.0 * drain + 700.0));
             i += 2;
         } else {
-            cost.push_back(2.0 * std::max(kcs[L] * 64.0, drain) + 100.0);
+            cost.push_back(std::max(1.19 * 2.0 * kcs[L] * 64.0, 2.0 * drain + 350.0));
             i += 1;
         }
         T.max_b_bytes = std::max(T.max_b_bytes, bbytes);
         T.blocks.push_back(e);
     }
+    T.cost = cost;
     return tc_assign_ctas(T.blocks, cost, grid);
 }
 
@@ -1052,6 +1057,13 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
     if (const char* e = getenv("MB200_SCAN_TC")) use_tc = use_tc && atoi(e) != 0;
     if (use_tc) use_tc = build_tc_plan(P, pwms_f16, lens, K, thresh_f16, flags, Lb, ctx->sm_count, TP);
     ctx->last_scan_path = 0;
+    if (use_tc) {
+        // start from the clocks per tile measured by the previous scan of this ctx when it had the same block structure
+        std::vector<int32_t> sig;
+        for (auto& e : TP.blocks) { sig.push_back(e.nsub); sig.push_back(e.kchunks[0]); sig.push_back(e.kchunks[1]); }
+        if (sig == ctx->tc_cost_sig && ctx->tc_cost.size() == TP.blocks.size()) { TP.cost = ctx->tc_cost; tc_assign_ctas(TP.blocks, TP.cost, ctx->sm_count); }
+        else { ctx->tc_cost_sig = sig; ctx->tc_cost.clear(); }
+    }
     const int64_t npos_max = Lb - P.minlen + 1;
     if (N == 0 || npos_max <= 0) return MB200_OK;       // nothing can be scored
     const int64_t W64 = (npos_max + 31) / 32;                      // 32-position mask words per sequence
@@ -1090,9 +1102,9 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
     if ((double)seqs_per_batch * W > 2.0e9) seqs_per_batch = std::max<int64_t>(1, (int64_t)(2.0e9 / W));
     if (use_tc && (double)seqs_per_batch * (double)Lb > 2.0e9) seqs_per_batch = std::max<int64_t>(1, (int64_t)(2.0e9 / (double)Lb));   // 32-bit virtual positions
     // tensor-core path: plan (B operands, blocks, slots) in buf 8, candidate list + counters in buf 9
-    const unsigned long long tc_cap = (unsigned long long)32 << 20;
+    const unsigned long long tc_cap = (unsigned long long)24 << 20;      // candidate records per batch and buffer set
     const bool tc_sparse = !want_hits && !hist && W <= 4096;        // counts only: count the units the verifier lists, never walk (or clear) the whole mask
-    size_t tc_off_blocks = 0, tc_off_slots = 0, tc_smem = 0;
+    size_t tc_off_blocks = 0, tc_off_slots = 0, tc_smem = 0, tc_set_stride = 0, tc_uset_stride = 0;      // strides between the two buffer sets of the pipelined path
     uint8_t* d_tc = nullptr; unsigned long long* d_tc_list = nullptr; unsigned long long* d_tc_ctr = nullptr;     // ctr: [0] reserved, [1] overflow, [2] candidates, [3] hits, [4] listed units, [8..] clocks per CTA
     uint32_t* d_tc_ulist = nullptr; uint32_t* d_tc_ubits = nullptr; unsigned long long tc_stat_cand = 0, tc_stat_hits = 0;
     if (use_tc) {
@@ -1100,21 +1112,25 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
         tc_off_slots = tc_off_blocks + ((TP.blocks.size() * sizeof(TcBlock) + 255) & ~(size_t)255);
         const size_t tc_bytes = tc_off_slots + TP.slots.size() * sizeof(TcSlot);
         rc = mb_ensure_buf(ctx, 8, tc_bytes); if (rc) return rc;
-        rc = mb_ensure_buf(ctx, 9, (size_t)tc_cap * 8 + (size_t)(8 + 2 * ctx->sm_count) * 8 + 256); if (rc) return rc;
+        const size_t tc_set_bytes = (((size_t)tc_cap * 8 + (size_t)(8 + 2 * ctx->sm_count) * 8) + 255) & ~(size_t)255;     // list + counters
+        rc = mb_ensure_buf(ctx, 9, 2 * tc_set_bytes); if (rc) return rc;
         d_tc = (uint8_t*)ctx->bufs[8];
         d_tc_list = (unsigned long long*)ctx->bufs[9];
         d_tc_ctr = d_tc_list + tc_cap;
         // (sequence, motif) units with hits: list + bitmap (buf 10), for the sparse counting kernel
         const size_t ubits_bytes = (((size_t)seqs_per_batch * (size_t)(P.K2pad / 2) + 31) / 32) * 4 + 256;
-        rc = mb_ensure_buf(ctx, 10, (size_t)tc_cap * 4 + ubits_bytes); if (rc) return rc;
+        const size_t tc_uset_bytes = (((size_t)tc_cap * 4 + ubits_bytes) + 255) & ~(size_t)255;
+        rc = mb_ensure_buf(ctx, 10, 2 * tc_uset_bytes); if (rc) return rc;
         d_tc_ulist = (uint32_t*)ctx->bufs[10];
         d_tc_ubits = d_tc_ulist + tc_cap;
+        tc_set_stride = tc_set_bytes; tc_uset_stride = tc_uset_bytes;
         std::vector<uint8_t> h_tc(tc_bytes, 0);
         memcpy(h_tc.data(), TP.blob.data(), TP.blob.size());
         memcpy(h_tc.data() + tc_off_blocks, TP.blocks.data(), TP.blocks.size() * sizeof(TcBlock));
         memcpy(h_tc.data() + tc_off_slots, TP.slots.data(), TP.slots.size() * sizeof(TcSlot));
         MB_CUDA(ctx, cudaMemcpyAsync(d_tc, h_tc.data(), tc_bytes, cudaMemcpyHostToDevice, ctx->stream));
         MB_CUDA(ctx, cudaMemsetAsync(d_tc_ctr, 0, (size_t)(8 + 2 * ctx->sm_count) * 8, ctx->stream));
+        MB_CUDA(ctx, cudaMemsetAsync((uint8_t*)d_tc_ctr + tc_set_stride, 0, (size_t)(8 + 2 * ctx->sm_count) * 8, ctx->stream));
         MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));           // h_tc goes out of scope
         // at least half of the shared memory: one CTA per SM (each CTA allocates all 512 TMEM columns)
         tc_smem = std::max<size_t>((size_t)TCS_STAGES * TCS_STAGE_BYTES + TP.max_b_bytes, (size_t)120 * 1024);
@@ -1166,7 +1182,109 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
     std::vector<int64_t> h_rng(grid + 1);
     int64_t last_nchunks = -1;
     size_t next_ready = 0;                                         // chunks of a pending asynchronous upload this scan has waited for
-    for (int64_t s0 = 0; s0 < N; s0 += seqs_per_batch) {
+    std::vector<int64_t> todo;                                     // first sequences of the batches the loop below still has to do
+    for (int64_t s0 = 0; s0 < N; s0 += seqs_per_batch) todo.push_back(s0);
+
+    // ---- counts-only thresholded scans: pipelined tensor-core path.  The pre-filter of batch i+1 (ctx->stream) runs while batch i is
+    //      re-scored and counted on ctx->aux_stream; two sets of list / counter / unit buffers alternate.  The host looks at batch i's
+    //      counters (overflow, clocks for the re-balancing) while batch i+1 is already running, so the GPU never waits for it. ----
+    if (use_tc && tc_sparse) {
+        if (!ctx->aux_stream && cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess) MB_FAIL(ctx, MB200_E_CUDA, "scan: cannot create the auxiliary stream");
+        cudaStream_t aux = ctx->aux_stream;
+        const size_t nctr = 8 + 2 * (size_t)grid;
+        rc = mb_ensure_pinned(ctx, 2 * nctr * 8); if (rc) return rc;
+        unsigned long long* h_ctr2 = (unsigned long long*)ctx->pinned;
+        cudaEvent_t ev_tc[2], ev_aux[2];
+        for (int b = 0; b < 2; ++b) { cudaEventCreateWithFlags(&ev_tc[b], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_aux[b], cudaEventDisableTiming); }
+        const int nb = (int)todo.size();
+        std::vector<char> launched(nb, 0), failed(nb, 0);
+        bool overflowed = false;
+        // batch j's counters: statistics, overflow, measured clocks per tile -> CTA split of the next launch
+        auto process = [&](int j) -> int {
+            if (cudaEventSynchronize(ev_aux[j & 1]) != cudaSuccess) return MB200_E_CUDA;
+            const unsigned long long* h = h_ctr2 + (size_t)(j & 1) * nctr;
+            if (h[1]) { failed[j] = 1; overflowed = true; return MB200_OK; }
+            tc_stat_cand += h[2]; tc_stat_hits += h[3];
+            std::vector<double> cost(TP.blocks.size(), 0.0);
+            bool ok = true;
+            for (size_t bi = 0; bi < TP.blocks.size(); ++bi) {
+                double clk = 0, tiles = 0;
+                for (int c = TP.blocks[bi].cta0; c < TP.blocks[bi].cta0 + TP.blocks[bi].nctas; ++c) { clk += (double)h[8 + 2 * c]; tiles += (double)h[8 + 2 * c + 1]; }
+                if (tiles <= 0 || clk <= 0) { ok = false; break; }
+                cost[bi] = clk / tiles;
+            }
+            if (ok) ctx->tc_cost = cost;
+            if (ok && tc_assign_ctas(TP.blocks, cost, grid) &&
+                cudaMemcpyAsync(d_tc + tc_off_blocks, TP.blocks.data(), TP.blocks.size() * sizeof(TcBlock), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return MB200_E_CUDA;
+            return MB200_OK;
+        };
+        int i = 0;
+        for (; i < nb && !overflowed; ++i) {
+            const int64_t s0 = todo[i];
+            const int64_t ns = std::min(seqs_per_batch, N - s0);
+            if (seqs->pending) {
+                while (next_ready < seqs->ready.size() && (next_ready == 0 || seqs->ready_end[next_ready - 1] < s0 + ns)) {
+                    MB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, seqs->ready[next_ready], 0));
+                    ++next_ready;
+                }
+            }
+            const int b = i & 1;
+            unsigned long long* list_b = (unsigned long long*)((uint8_t*)d_tc_list + (size_t)b * tc_set_stride);
+            unsigned long long* ctr_b = list_b + tc_cap;
+            uint32_t* ulist_b = (uint32_t*)((uint8_t*)d_tc_ulist + (size_t)b * tc_uset_stride);
+            uint32_t* ubits_b = ulist_b + tc_cap;
+            const size_t need = (size_t)ns * mask_bytes_per_seq;
+            if (ctx->mask_clean_bytes < need) {
+                MB_CUDA(ctx, cudaMemsetAsync(d_mask, 0, need, ctx->stream));
+                ctx->mask_clean_bytes = need;
+            }
+            MB_CUDA(ctx, cudaMemsetAsync(ctr_b, 0, 64, ctx->stream));
+            TcArgs ta;
+            ta.seqw = seqs->words; ta.rowwords = rowwords; ta.seq0 = s0;
+            ta.Lb = (uint32_t)Lb; ta.vtotal = (uint32_t)(ns * Lb);
+            ta.blob = d_tc; ta.blocks = (const TcBlock*)(d_tc + tc_off_blocks); ta.nblocks = (int32_t)TP.blocks.size();
+            ta.slots = (const TcSlot*)(d_tc + tc_off_slots);
+            ta.list = list_b; ta.cap = tc_cap; ta.gcount = ctr_b; ta.overflow = (uint32_t*)(ctr_b + 1);
+            ta.ntiles = (int32_t)((ns * Lb + 255) / 256);
+            ta.clocks = (long long*)(ctr_b + 8);
+            ta.dbg = nullptr;
+            const int t_tc = tm.begin(T_SCAN);
+            k_scan_tc<<<grid, TCS_THREADS, tc_smem, ctx->stream>>>(ta);
+            tm.end(t_tc);
+            MB_CUDA(ctx, cudaGetLastError());
+            MB_CUDA(ctx, cudaEventRecord(ev_tc[b], ctx->stream));
+            MB_CUDA(ctx, cudaStreamWaitEvent(aux, ev_tc[b], 0));
+            MB_CUDA(ctx, cudaMemsetAsync(ubits_b, 0, (((size_t)ns * (size_t)(P.K2pad / 2) + 31) / 32) * 4, aux));
+            const int t_vf = tm.begin_on(T_EMIT, aux);
+            // 128-thread blocks: next to a k_scan_tc CTA (608 threads x 96 registers) an SM has ~7 K registers left
+            k_scan_tc_verify<<<grid * 16, 128, 0, aux>>>(list_b, ctr_b, tc_cap, ta.slots, (const EmitMotif*)(d_plan + off_em), d_plan + off_blob,
+                                                        seqs->words, rowwords, s0, (uint32_t)Lb, W, P.K2pad, d_mask, ctr_b + 2, ubits_b, ulist_b, ctr_b + 4);
+            tm.end_on(t_vf, aux);
+            const int t_ct = tm.begin_on(T_COUNT, aux);
+            count_listed_kernel<<<grid * 16, 128, 0, aux>>>(d_mask, ulist_b, ctr_b + 4, W, P.K2pad, (const int32_t*)(d_plan + off_p2m),
+                                                           (const int32_t*)(d_plan + off_plen), d_counts, ctr_b + 1);
+            tm.end_on(t_ct, aux);
+            MB_CUDA(ctx, cudaGetLastError());
+            MB_CUDA(ctx, cudaMemcpyAsync(h_ctr2 + (size_t)b * nctr, ctr_b, nctr * 8, cudaMemcpyDeviceToHost, aux));
+            MB_CUDA(ctx, cudaEventRecord(ev_aux[b], aux));
+            ctx->launches[T_SCAN] += 1; ctx->launches[T_EMIT] += 1; ctx->launches[T_COUNT] += 1;
+            launched[i] = 1;
+            if (i >= 1) { rc = process(i - 1); if (rc) return rc; }
+        }
+        const int n_launched = i;
+        // every batch but the last launched one was looked at inside the loop
+        if (n_launched > 0) { rc = process(n_launched - 1); if (rc) return rc; }
+        MB_CUDA(ctx, cudaStreamSynchronize(aux));
+        for (int b = 0; b < 2; ++b) { cudaEventDestroy(ev_tc[b]); cudaEventDestroy(ev_aux[b]); }
+        std::vector<int64_t> rest;
+        for (int j = 0; j < nb; ++j) if (!launched[j] || failed[j]) rest.push_back(todo[j]);
+        todo.swap(rest);
+        if (overflowed) { use_tc = false; ctx->last_scan_path = 2; ctx->mask_clean_bytes = 0; }     // a failed batch may have left bits behind (its count was skipped)
+        else ctx->last_scan_path = 1;
+    }
+
+    for (size_t ti = 0; ti < todo.size(); ++ti) {
+        const int64_t s0 = todo[ti];
         const int64_t ns = std::min(seqs_per_batch, N - s0);
         if (seqs->pending) {
             // a batch may start as soon as the chunks holding its sequences are packed (the kernel reads a few words past its last
@@ -1251,7 +1369,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
                             h[c * 8 + 0], h[c * 8 + 1], h[c * 8 + 2], h[c * 8 + 4], h[c * 8 + 3], h[c * 8 + 5]);
             }
 #endif
-            if (!h_ctr[1] && s0 + ns < N) {
+            if (!h_ctr[1]) {
                 // re-balance the CTAs over the slot blocks with the clocks per tile this batch measured (the epilogue's share depends on
                 // the candidate density of the block, which no static model knows)
                 std::vector<double> cost(TP.blocks.size(), 0.0);
@@ -1262,6 +1380,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
                     if (tiles <= 0 || clk <= 0) { ok = false; break; }
                     cost[bi] = clk / tiles;
                 }
+                if (ok) ctx->tc_cost = cost;
                 if (ok && tc_assign_ctas(TP.blocks, cost, grid))
                     MB_CUDA(ctx, cudaMemcpyAsync(d_tc + tc_off_blocks, TP.blocks.data(), TP.blocks.size() * sizeof(TcBlock), cudaMemcpyHostToDevice, ctx->stream));
             }
@@ -1305,7 +1424,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
             ctx->launches[T_COUNT] += 3;
         } else if (tc_done && tc_sparse) {
             count_listed_kernel<<<grid * 8, 256, 0, ctx->stream>>>(d_mask, d_tc_ulist, d_tc_ctr + 4, W, P.K2pad, (const int32_t*)(d_plan + off_p2m),
-                                                                    (const int32_t*)(d_plan + off_plen), d_counts);
+                                                                    (const int32_t*)(d_plan + off_plen), d_counts, nullptr);
             ctx->launches[T_COUNT] += 1;
             ctx->mask_clean_bytes = (size_t)ns * mask_bytes_per_seq;   // every word with a bit belongs to a listed unit and was cleared
         } else {

@@ -403,6 +403,7 @@ __global__ void __launch_bounds__(256) k_scan_tc_verify(const unsigned long long
                                                         const uint8_t* __restrict__ blob, const uint32_t* __restrict__ seqw, int64_t rowwords, int64_t seq0,
                                                         uint32_t Lb, int32_t W, int32_t K2pad, uint32_t* __restrict__ mask, unsigned long long* __restrict__ stats,
                                                         uint32_t* __restrict__ unit_bits, uint32_t* __restrict__ unit_list, unsigned long long* __restrict__ n_units) {
+    if (gcount[1]) return;                                                                // the list overflowed: this batch is re-run on scan_kernel
     const unsigned long long total = min(*gcount, cap);
     unsigned int n_cand = 0, n_hit = 0;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
