@@ -885,6 +885,12 @@ static bool build_tc_plan(const ScanPlan& P, const uint16_t* pwms, const int64_t
             cost.push_back(std::max(1.19 * 2.0 * kcs[L] * 64.0, 2.0 * drain + 350.0));
             i += 1;
         }
+        // Four 128-column accumulators (a drain then overlaps the MMAs of three other uses) were tried for the entries whose MMAs are
+        // shorter than the drain: measured 25 % SLOWER on config 4 (2 M x 200 bp: 75.9 -> 95.3 ms; all entries at 128 columns: 116.9 ms) —
+        // an N = 128 MMA re-reads the same 4 KB A operand for half the math and the operand fetch, not the math, then paces the pipe.
+        // Kept selectable for experiments only.
+        e.accw = 256;
+        if (const char* ev = getenv("MB200_SCAN_TC_ACCW")) { const int w = atoi(ev); if (w == 128 || w == 256) e.accw = w; }
         T.max_b_bytes = std::max(T.max_b_bytes, bbytes);
         T.blocks.push_back(e);
     }
@@ -1060,7 +1066,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
     if (use_tc) {
         // start from the clocks per tile measured by the previous scan of this ctx when it had the same block structure
         std::vector<int32_t> sig;
-        for (auto& e : TP.blocks) { sig.push_back(e.nsub); sig.push_back(e.kchunks[0]); sig.push_back(e.kchunks[1]); }
+        for (auto& e : TP.blocks) { sig.push_back(e.nsub); sig.push_back(e.kchunks[0]); sig.push_back(e.kchunks[1]); sig.push_back(e.accw); }
         if (sig == ctx->tc_cost_sig && ctx->tc_cost.size() == TP.blocks.size()) { TP.cost = ctx->tc_cost; tc_assign_ctas(TP.blocks, TP.cost, ctx->sm_count); }
         else { ctx->tc_cost_sig = sig; ctx->tc_cost.clear(); }
     }
