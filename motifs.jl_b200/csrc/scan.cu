@@ -697,6 +697,7 @@ struct ScanPlan {
 };
 
 #include "scan_tc.cuh"
+#include "scan_tc2.cuh"
 
 // ---- host side of the tensor-core pre-filter (scan_tc.cuh) ------------------------------------------------------------
 static inline uint16_t float_to_h16(float f) { __half h = __float2half_rn(f); __half_raw r = h; return r.x; }
@@ -752,6 +753,14 @@ static bool tc_assign_ctas(std::vector<TcBlock>& blocks, const std::vector<doubl
     }
     int c0 = 0;
     for (int bi = 0; bi < nblocks; ++bi) { blocks[bi].cta0 = c0; blocks[bi].nctas = n[bi]; c0 += n[bi]; }
+    return true;
+}
+
+// CTA-pair kernel (k_scan_tc2): entries get whole clusters of two CTAs
+static bool tc_assign(std::vector<TcBlock>& blocks, const std::vector<double>& cost, int grid, bool pair) {
+    if (!pair) return tc_assign_ctas(blocks, cost, grid);
+    if (!tc_assign_ctas(blocks, cost, grid / 2)) return false;
+    for (auto& b : blocks) { b.cta0 *= 2; b.nctas *= 2; }
     return true;
 }
 
@@ -1063,11 +1072,17 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
     if (const char* e = getenv("MB200_SCAN_TC")) use_tc = use_tc && atoi(e) != 0;
     if (use_tc) use_tc = build_tc_plan(P, pwms_f16, lens, K, thresh_f16, flags, Lb, ctx->sm_count, TP);
     ctx->last_scan_path = 0;
+    // CTA-pair kernel (scan_tc2.cuh, cta_group::2: half of B per CTA).  Correct (all parity tests pass with it) but measured NOT faster than
+    // k_scan_tc on config 4 (2 M x 200 bp: 79.5 ms vs 75.6-76.3 ms of kernel time on the same box), so it is opt-in: MB200_SCAN_TC_PAIR=1.
+    bool tc_pair = false;
+    if (const char* e = getenv("MB200_SCAN_TC_PAIR")) tc_pair = atoi(e) != 0 && use_tc && (ctx->sm_count % 2 == 0) && (int)TP.blocks.size() * 2 <= ctx->sm_count;
     if (use_tc) {
+        if (tc_pair && !tc_assign(TP.blocks, TP.cost, ctx->sm_count, true)) tc_pair = false;
         // start from the clocks per tile measured by the previous scan of this ctx when it had the same block structure
         std::vector<int32_t> sig;
         for (auto& e : TP.blocks) { sig.push_back(e.nsub); sig.push_back(e.kchunks[0]); sig.push_back(e.kchunks[1]); sig.push_back(e.accw); }
-        if (sig == ctx->tc_cost_sig && ctx->tc_cost.size() == TP.blocks.size()) { TP.cost = ctx->tc_cost; tc_assign_ctas(TP.blocks, TP.cost, ctx->sm_count); }
+        sig.push_back(tc_pair ? 2 : 1);
+        if (sig == ctx->tc_cost_sig && ctx->tc_cost.size() == TP.blocks.size()) { TP.cost = ctx->tc_cost; tc_assign(TP.blocks, TP.cost, ctx->sm_count, tc_pair); }
         else { ctx->tc_cost_sig = sig; ctx->tc_cost.clear(); }
     }
     const int64_t npos_max = Lb - P.minlen + 1;
@@ -1139,8 +1154,9 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
         MB_CUDA(ctx, cudaMemsetAsync((uint8_t*)d_tc_ctr + tc_set_stride, 0, (size_t)(8 + 2 * ctx->sm_count) * 8, ctx->stream));
         MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));           // h_tc goes out of scope
         // at least half of the shared memory: one CTA per SM (each CTA allocates all 512 TMEM columns)
-        tc_smem = std::max<size_t>((size_t)TCS_STAGES * TCS_STAGE_BYTES + TP.max_b_bytes, (size_t)120 * 1024);
+        tc_smem = std::max<size_t>((size_t)TCS_STAGES * TCS_STAGE_BYTES + (tc_pair ? TP.max_b_bytes / 2 : TP.max_b_bytes), (size_t)120 * 1024);
         if (tc_smem > ctx->smem_optin) use_tc = false;
+        else if (tc_pair) MB_CUDA(ctx, cudaFuncSetAttribute(k_scan_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
         else MB_CUDA(ctx, cudaFuncSetAttribute(k_scan_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
     }
     rc = mb_ensure_buf(ctx, 2, (size_t)seqs_per_batch * mask_bytes_per_seq); if (rc) return rc;
@@ -1220,7 +1236,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
                 cost[bi] = clk / tiles;
             }
             if (ok) ctx->tc_cost = cost;
-            if (ok && tc_assign_ctas(TP.blocks, cost, grid) &&
+            if (ok && tc_assign(TP.blocks, cost, grid, tc_pair) &&
                 cudaMemcpyAsync(d_tc + tc_off_blocks, TP.blocks.data(), TP.blocks.size() * sizeof(TcBlock), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return MB200_E_CUDA;
             return MB200_OK;
         };
@@ -1255,7 +1271,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
             ta.clocks = (long long*)(ctr_b + 8);
             ta.dbg = nullptr;
             const int t_tc = tm.begin(T_SCAN);
-            k_scan_tc<<<grid, TCS_THREADS, tc_smem, ctx->stream>>>(ta);
+            if (tc_pair) k_scan_tc2<<<grid, TCS_THREADS, tc_smem, ctx->stream>>>(ta); else k_scan_tc<<<grid, TCS_THREADS, tc_smem, ctx->stream>>>(ta);
             tm.end(t_tc);
             MB_CUDA(ctx, cudaGetLastError());
             MB_CUDA(ctx, cudaEventRecord(ev_tc[b], ctx->stream));
@@ -1354,7 +1370,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
             if (getenv("MB200_SCAN_TC_DEBUG")) { if (!d_dbg) cudaMalloc(&d_dbg, 148 * 8 * 8 * 2); cudaMemset(d_dbg, 0, 148 * 8 * 8); ta.dbg = d_dbg; }
 #endif
             const int t_tc = tm.begin(T_SCAN);
-            k_scan_tc<<<grid, TCS_THREADS, tc_smem, ctx->stream>>>(ta);
+            if (tc_pair) k_scan_tc2<<<grid, TCS_THREADS, tc_smem, ctx->stream>>>(ta); else k_scan_tc<<<grid, TCS_THREADS, tc_smem, ctx->stream>>>(ta);
             tm.end(t_tc);
             const int t_vf = tm.begin(T_EMIT);
             k_scan_tc_verify<<<grid * 8, 256, 0, ctx->stream>>>(d_tc_list, d_tc_ctr, tc_cap, ta.slots, (const EmitMotif*)(d_plan + off_em), d_plan + off_blob,
@@ -1387,7 +1403,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
                     cost[bi] = clk / tiles;
                 }
                 if (ok) ctx->tc_cost = cost;
-                if (ok && tc_assign_ctas(TP.blocks, cost, grid))
+                if (ok && tc_assign(TP.blocks, cost, grid, tc_pair))
                     MB_CUDA(ctx, cudaMemcpyAsync(d_tc + tc_off_blocks, TP.blocks.data(), TP.blocks.size() * sizeof(TcBlock), cudaMemcpyHostToDevice, ctx->stream));
             }
             tc_stat_cand += h_ctr[2]; tc_stat_hits += h_ctr[3];
