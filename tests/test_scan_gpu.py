@@ -413,3 +413,39 @@ def test_tensor_path_candidate_overflow_falls_back(ctx):
     assert np.array_equal(c, c0)
     assert c[0, 0] == 2 * 20000 * (200 - ms.lens[0] + 1)
     seqs.free()
+
+
+def test_tensor_path_multi_batch_equals_simt_at_scale(ctx):
+    """BASELINE config 4 shape at a size that takes three batches of the pipelined tensor-core path (two alternating buffer sets, CTA
+    re-balancing between batches, mask words cleared by the listed count): counts must equal the SIMT kernel's on the same sequences,
+    be additive over a split of the sequences, and equal the oracle's on a sample."""
+    N, Lb, K = 700_000, 200, 500
+    ms = synth.motifs_from_count_matrices(synth.random_count_matrices(K, 8, 40, 4))          # bench.py's motif set
+    thr = synth.stated_thresholds(ms, 0.7)
+    pw, lens = so.pack_pwms(ms.pwms)
+    a = synth.random_ascii(N, Lb, 123)
+    seqs = ctx.seqs_from_ascii(a)
+    _, c_tc = ctx.scan(seqs, pw, lens, thr, want_hits=False)
+    assert _lib.scan_last_path(ctx) == 1
+    _, c_tc2 = ctx.scan(seqs, pw, lens, thr, want_hits=False)                  # second call: cached CTA split, mask buffer reused as is
+    assert np.array_equal(c_tc, c_tc2)
+    _, c_simt = ctx.scan(seqs, pw, lens, thr, want_hits=False, tensor=False)
+    assert _lib.scan_last_path(ctx) == 0
+    assert np.array_equal(c_tc, c_simt)
+    _, c_tc3 = ctx.scan(seqs, pw, lens, thr, want_hits=False)                  # after the SIMT kernel dirtied the mask buffer
+    assert np.array_equal(c_tc, c_tc3)
+    seqs.free()
+    h = N // 2 + 12345
+    parts = []
+    for rows in (a[:h], a[h:]):
+        s = ctx.seqs_from_ascii(rows)
+        parts.append(ctx.scan(s, pw, lens, thr, want_hits=False)[1])
+        s.free()
+    assert np.array_equal(parts[0] + parts[1], c_tc)
+    sub = a[300_000:303_000]
+    s = ctx.seqs_from_ascii(sub)
+    _, c_sub = ctx.scan(s, pw, lens, thr, want_hits=False)
+    s.free()
+    _, oc = so.scan(pw, lens, so.ascii_to_codes(sub), thr, want_hits=False)
+    assert np.array_equal(c_sub, oc)
+    assert c_tc[:, 0].sum() > 0
