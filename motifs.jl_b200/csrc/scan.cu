@@ -899,6 +899,16 @@ static bool build_tc_plan(const ScanPlan& P, const uint16_t* pwms, const int64_t
         // an N = 128 MMA re-reads the same 4 KB A operand for half the math and the operand fetch, not the math, then paces the pipe.
         // Kept selectable for experiments only.
         e.accw = 256;
+        // ... except when the upper 128 slots of every block of the entry are padding (few motifs, e.g. BASELINE config 5 with 50 PWMs): with
+        // 128-column accumulators that half is skipped altogether
+        auto upper_empty = [&](int blkidx) { for (int sidx = TCS_N / 2; sidx < TCS_N; ++sidx) if (!col0[blkidx * TCS_N + sidx].empty()) return false; return true; };
+        e.nh[0] = e.nh[1] = 2;
+        {
+            bool all_empty = upper_empty(L);
+            if (e.nsub > 1) all_empty = all_empty && upper_empty((int)(e.slot0[1] / TCS_N));
+            // measured on config 5 (250 Mbp x 50 PWMs): 13.5 ms with the half skipped vs 12.3 ms with full 256-column MMAs — opt-in only
+            if (all_empty && getenv("MB200_SCAN_TC_HALF")) { e.accw = 128; e.nh[0] = e.nh[1] = 1; }
+        }
         if (const char* ev = getenv("MB200_SCAN_TC_ACCW")) { const int w = atoi(ev); if (w == 128 || w == 256) e.accw = w; }
         T.max_b_bytes = std::max(T.max_b_bytes, bbytes);
         T.blocks.push_back(e);

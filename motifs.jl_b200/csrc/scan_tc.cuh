@@ -50,8 +50,9 @@ struct TcBlock {                           // what one CTA works on: one block o
     int32_t slot0[2];                      // first global slot
     int32_t nsub;                          // 1, or 2: sub-block 0 (the longer one) accumulates in TMEM columns [0,256), sub-block 1 in [256,512)
     int32_t cta0, nctas;                   // CTAs [cta0, cta0 + nctas) work on this entry
-    int32_t accw;                          // accumulator width in TMEM columns: 256 (two accumulators) or 128 (four: entries whose MMAs are
-                                           // shorter than the drain of a 256-column accumulator keep three drains in flight per MMA)
+    int32_t accw;                          // accumulator width in TMEM columns: 256 (two accumulators) or 128 (four accumulators)
+    int32_t nh[2];                         // accw = 128: column halves of each sub-block that hold any enabled slot (1: the upper 128 slots are
+                                           // padding and are neither multiplied nor drained — scans with few motifs)
 };
 struct TcSlot {                            // per global slot, for the epilogue (npos) and the verifier
     int32_t motif;                         // original motif index, -1: disabled
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
                 #pragma unroll
                 for (int par = 0; par < 2; ++par) {
                     for (int sub = 0; sub < blk.nsub; ++sub)
-                    for (int h = 0; h < halves; ++h, ++u) {
+                    for (int h = 0; h < (halves > 1 ? blk.nh[sub] : 1); ++h, ++u) {
                         const uint32_t ac = u % (uint32_t)nacc, uses = u / (uint32_t)nacc;
                         TCS_PROF(t0 = clock64();)
                         tcs_wait(bar(2 * TCS_STAGES + 4 + ac), (uses & 1) ^ 1);          // accumulator drained
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
         for (int tile = rank; tile < a.ntiles; tile += blk.nctas, ++it)
         for (int par = 0; par < 2; ++par)
         for (int sub = 0; sub < blk.nsub; ++sub)
-        for (int h = 0; h < halves; ++h, ++u) {
+        for (int h = 0; h < (halves > 1 ? blk.nh[sub] : 1); ++h, ++u) {
             const uint32_t ac = u % (uint32_t)nacc, uses = u / (uint32_t)nacc;
             const uint32_t v = (uint32_t)tile * 256u + (uint32_t)par + 2u * (uint32_t)(q * 32 + lane);
             const bool inb = v < a.vtotal;
