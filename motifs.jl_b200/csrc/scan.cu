@@ -843,11 +843,17 @@ static bool build_tc_plan(const ScanPlan& P, const uint16_t* pwms, const int64_t
     size_t total = 0;
     std::vector<int> kcs(nblocks);
     std::vector<int64_t> boff(nblocks);
+    // Optional: B staged with the 128-byte swizzle (rows of 64 halves, K padded to whole rows) instead of the no-swizzle chunk planes (the
+    // layout A needs for its sliding window).  Parity-green, but measured slower on config 4 (2 M x 200 bp: 90.1 vs 85.6 ms per step on the
+    // same box; the padded rows also stop the two longest blocks from sharing a CTA), so the operand layout is not what limits the MMAs.
+    bool bswz = getenv("MB200_SCAN_TC_BSWZ") ? atoi(getenv("MB200_SCAN_TC_BSWZ")) != 0 : false;
+    if (const char* e = getenv("MB200_SCAN_TC_PAIR")) if (atoi(e) != 0) bswz = false;             // k_scan_tc2 stages half planes of the no-swizzle layout
+    auto bbytes_of = [&](int kc) { return bswz ? (size_t)((kc + 7) / 8) * TCS_N * 128 : (size_t)kc * TCS_N * 16; };
     for (int bi = 0; bi < nblocks; ++bi) {
         int kc = (std::max(blen[bi], 1) + 1) / 2;
         kc = std::max(2, (kc + 1) & ~1);
         kcs[bi] = kc; boff[bi] = (int64_t)total;
-        total += (size_t)kc * TCS_N * 16;
+        total += bbytes_of(kc);
     }
     T.blob.assign(total, 0);
     for (int bi = 0; bi < nblocks; ++bi) {
@@ -855,14 +861,19 @@ static bool build_tc_plan(const ScanPlan& P, const uint16_t* pwms, const int64_t
         for (int sidx = 0; sidx < TCS_N; ++sidx) {
             const int slot = bi * TCS_N + sidx;
             const std::vector<uint16_t>& c = col0[slot];
+            // position (in halves) of half e of K chunk ch of slot sidx
+            auto at = [&](int ch, int e) -> size_t {
+                if (!bswz) return ((size_t)ch * TCS_N + sidx) * 8 + e;
+                return ((size_t)(ch >> 3) * TCS_N + sidx) * 64 + (size_t)(((ch & 7) ^ (sidx & 7)) * 8) + e;
+            };
             if (c.empty()) {                                       // disabled slot: D = -1 everywhere
-                for (int b = 0; b < 4; ++b) Bm[((size_t)0 * TCS_N + sidx) * 8 + b] = 0xBC00u;
+                for (int b = 0; b < 4; ++b) Bm[at(0, b)] = 0xBC00u;
                 T.slots[slot].npos = 0;
                 continue;
             }
             const int len = (int)c.size() / 4;
             for (int j = 0; j < len; ++j)
-                for (int b = 0; b < 4; ++b) Bm[((size_t)(j >> 1) * TCS_N + sidx) * 8 + 4 * (j & 1) + b] = c[(size_t)j * 4 + b];
+                for (int b = 0; b < 4; ++b) Bm[at(j >> 1, 4 * (j & 1) + b)] = c[(size_t)j * 4 + b];
         }
     }
     // Work entries: blocks sorted by length are paired with their neighbour while both B operands fit in shared memory.  Each block
@@ -874,18 +885,19 @@ static bool build_tc_plan(const ScanPlan& P, const uint16_t* pwms, const int64_t
     for (int bi = 0; bi < nblocks; ++bi) ord[bi] = bi;
     std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return kcs[x] > kcs[y]; });
     const double drain = 1000.0;
-    const size_t b_budget = (size_t)200 * 1024 - (size_t)TCS_STAGES * TCS_STAGE_BYTES;
+    const size_t b_budget = (bswz ? (size_t)225 : (size_t)200) * 1024 - (size_t)TCS_STAGES * TCS_STAGE_BYTES;       // 227 KB per CTA minus static shared memory and the stages
     const bool no_pair = getenv("MB200_SCAN_TC_NOPAIR") != nullptr;
     std::vector<double> cost;
     for (int i = 0; i < nblocks;) {
         TcBlock e; memset(&e, 0, sizeof e);
         const int L = ord[i];
         e.b_off[0] = boff[L]; e.kchunks[0] = kcs[L]; e.slot0[0] = L * TCS_N; e.nsub = 1;
-        size_t bbytes = (size_t)kcs[L] * TCS_N * 16;
-        if (i + 1 < nblocks && !no_pair && bbytes + (size_t)kcs[ord[i + 1]] * TCS_N * 16 <= b_budget) {
+        size_t bbytes = bbytes_of(kcs[L]);
+        e.bswz = bswz ? 1 : 0;
+        if (i + 1 < nblocks && !no_pair && bbytes + bbytes_of(kcs[ord[i + 1]]) <= b_budget) {
             const int S = ord[i + 1];
             e.b_off[1] = boff[S]; e.kchunks[1] = kcs[S]; e.slot0[1] = S * TCS_N; e.nsub = 2;
-            bbytes += (size_t)kcs[S] * TCS_N * 16;
+            bbytes += bbytes_of(kcs[S]);
             // measured on config 4 (profiles/r01_scan_tc_role_clocks.txt): 1.19 x the MMA clocks when the MMAs bind, ~4 drains of
             // ~1150 clocks when they do not
             cost.push_back(std::max(1.19 * 2.0 * (kcs[L] + kcs[S]) * 64.0, 4.0 * drain + 700.0));
@@ -1090,7 +1102,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
         if (tc_pair && !tc_assign(TP.blocks, TP.cost, ctx->sm_count, true)) tc_pair = false;
         // start from the clocks per tile measured by the previous scan of this ctx when it had the same block structure
         std::vector<int32_t> sig;
-        for (auto& e : TP.blocks) { sig.push_back(e.nsub); sig.push_back(e.kchunks[0]); sig.push_back(e.kchunks[1]); sig.push_back(e.accw); }
+        for (auto& e : TP.blocks) { sig.push_back(e.nsub); sig.push_back(e.kchunks[0]); sig.push_back(e.kchunks[1]); sig.push_back(e.accw); sig.push_back(e.bswz); }
         sig.push_back(tc_pair ? 2 : 1);
         if (sig == ctx->tc_cost_sig && ctx->tc_cost.size() == TP.blocks.size()) { TP.cost = ctx->tc_cost; tc_assign(TP.blocks, TP.cost, ctx->sm_count, tc_pair); }
         else { ctx->tc_cost_sig = sig; ctx->tc_cost.clear(); }

@@ -51,6 +51,8 @@ struct TcBlock {                           // what one CTA works on: one block o
     int32_t nsub;                          // 1, or 2: sub-block 0 (the longer one) accumulates in TMEM columns [0,256), sub-block 1 in [256,512)
     int32_t cta0, nctas;                   // CTAs [cta0, cta0 + nctas) work on this entry
     int32_t accw;                          // accumulator width in TMEM columns: 256 (two accumulators) or 128 (four accumulators)
+    int32_t bswz;                          // 1: B operands are staged in the 128-byte-swizzled K-major layout ([K block of 64 halves][256 slots][128 B],
+                                           // 16-byte chunk c of slot n stored at chunk c ^ (n & 7)) instead of the no-swizzle chunk planes
     int32_t nh[2];                         // accw = 128: column halves of each sub-block that hold any enabled slot (1: the upper 128 slots are
                                            // padding and are neither multiplied nor drained — scans with few motifs)
 };
@@ -186,22 +188,35 @@ __device__ __noinline__ void tcs_append(unsigned long long* list, unsigned long 
 // The K loop of one accumulator use, fully unrolled per trip count: with compile-time t the descriptors of step t are the first
 // ones plus constants (one uniform 64-bit add each).  A run-time loop costs ~26 dependent instructions per MMA in the single issuing
 // thread (ELECT + seven R2UR per MMA): ~180 clocks per 128-clock MMA, i.e. the issuing thread, not the tensor pipe, set the pace.
-template <int KP>
+template <int KP, bool SWZ>
 __device__ __forceinline__ void tcs_issue_n(uint32_t tmem_d, uint64_t da0, uint64_t db0, uint32_t idesc) {
     #pragma unroll
-    for (int t = 0; t < KP; ++t) tcs_mma(tmem_d, da0 + (uint64_t)(2 * t), db0 + (uint64_t)(2 * t * TCS_N), idesc, t ? 1u : 0u);
-}
-__device__ __forceinline__ void tcs_issue(int kp, uint32_t tmem_d, uint64_t da0, uint64_t db0, uint32_t idesc) {
-    switch (kp) {
-        case 1: tcs_issue_n<1>(tmem_d, da0, db0, idesc); break;   case 2: tcs_issue_n<2>(tmem_d, da0, db0, idesc); break;
-        case 3: tcs_issue_n<3>(tmem_d, da0, db0, idesc); break;   case 4: tcs_issue_n<4>(tmem_d, da0, db0, idesc); break;
-        case 5: tcs_issue_n<5>(tmem_d, da0, db0, idesc); break;   case 6: tcs_issue_n<6>(tmem_d, da0, db0, idesc); break;
-        case 7: tcs_issue_n<7>(tmem_d, da0, db0, idesc); break;   case 8: tcs_issue_n<8>(tmem_d, da0, db0, idesc); break;
-        case 9: tcs_issue_n<9>(tmem_d, da0, db0, idesc); break;   case 10: tcs_issue_n<10>(tmem_d, da0, db0, idesc); break;
-        case 11: tcs_issue_n<11>(tmem_d, da0, db0, idesc); break; case 12: tcs_issue_n<12>(tmem_d, da0, db0, idesc); break;
-        case 13: tcs_issue_n<13>(tmem_d, da0, db0, idesc); break; case 14: tcs_issue_n<14>(tmem_d, da0, db0, idesc); break;
-        case 15: tcs_issue_n<15>(tmem_d, da0, db0, idesc); break; default: tcs_issue_n<16>(tmem_d, da0, db0, idesc); break;
+    for (int t = 0; t < KP; ++t) {
+        // K step t = chunks 2t, 2t+1.  no-swizzle: chunk planes of 256 x 16 B; swizzle-128B: 4 steps per 128-byte row, 32 B apart, then the
+        // next 32 KB K block (start-address field counts 16-byte units)
+        const uint64_t dboff = SWZ ? (uint64_t)((t >> 2) * ((TCS_N * 128) >> 4) + (t & 3) * 2) : (uint64_t)(2 * t * TCS_N);
+        tcs_mma(tmem_d, da0 + (uint64_t)(2 * t), db0 + dboff, idesc, t ? 1u : 0u);
     }
+}
+template <bool SWZ>
+__device__ __forceinline__ void tcs_issue_s(int kp, uint32_t tmem_d, uint64_t da0, uint64_t db0, uint32_t idesc) {
+    switch (kp) {
+        case 1: tcs_issue_n<1, SWZ>(tmem_d, da0, db0, idesc); break;   case 2: tcs_issue_n<2, SWZ>(tmem_d, da0, db0, idesc); break;
+        case 3: tcs_issue_n<3, SWZ>(tmem_d, da0, db0, idesc); break;   case 4: tcs_issue_n<4, SWZ>(tmem_d, da0, db0, idesc); break;
+        case 5: tcs_issue_n<5, SWZ>(tmem_d, da0, db0, idesc); break;   case 6: tcs_issue_n<6, SWZ>(tmem_d, da0, db0, idesc); break;
+        case 7: tcs_issue_n<7, SWZ>(tmem_d, da0, db0, idesc); break;   case 8: tcs_issue_n<8, SWZ>(tmem_d, da0, db0, idesc); break;
+        case 9: tcs_issue_n<9, SWZ>(tmem_d, da0, db0, idesc); break;   case 10: tcs_issue_n<10, SWZ>(tmem_d, da0, db0, idesc); break;
+        case 11: tcs_issue_n<11, SWZ>(tmem_d, da0, db0, idesc); break; case 12: tcs_issue_n<12, SWZ>(tmem_d, da0, db0, idesc); break;
+        case 13: tcs_issue_n<13, SWZ>(tmem_d, da0, db0, idesc); break; case 14: tcs_issue_n<14, SWZ>(tmem_d, da0, db0, idesc); break;
+        case 15: tcs_issue_n<15, SWZ>(tmem_d, da0, db0, idesc); break; default: tcs_issue_n<16, SWZ>(tmem_d, da0, db0, idesc); break;
+    }
+}
+__device__ __forceinline__ void tcs_issue(bool swz, int kp, uint32_t tmem_d, uint64_t da0, uint64_t db0, uint32_t idesc) {
+    if (swz) tcs_issue_s<true>(kp, tmem_d, da0, db0, idesc); else tcs_issue_s<false>(kp, tmem_d, da0, db0, idesc);
+}
+// UMMA shared-memory descriptor of a 128-byte-swizzled K-major operand: LBO unused (1), SBO = 1024 B (8 rows x 128 B), layout type 2
+__device__ __forceinline__ uint64_t tcs_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
 // Work item = one tile of 256 consecutive virtual start positions = two parities (even / odd offsets) of 128 rows.
@@ -304,9 +319,10 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
         TCS_PROF(if (a.dbg && warp == 0 && lane == 0) a.dbg[blockIdx.x * 8 + 5] = w_prod;)
     } else if (warp == 1) {
         {   // ---- MMA warp: all 32 lanes run this code converged; tcs_mma / tcs_commit elect the issuing lane ----
-            const uint32_t b_bytes0 = (uint32_t)blk.kchunks[0] * TCS_N * 16;
+            // bytes of a B operand: chunk planes, or whole 128-byte rows per K block of 8 chunks
+            const uint32_t b_bytes0 = blk.bswz ? (uint32_t)((blk.kchunks[0] + 7) / 8) * TCS_N * 128 : (uint32_t)blk.kchunks[0] * TCS_N * 16;
             if (lane == 0) {   // the B operands, resident for the whole kernel
-                const uint32_t b_bytes1 = blk.nsub > 1 ? (uint32_t)blk.kchunks[1] * TCS_N * 16 : 0u;
+                const uint32_t b_bytes1 = blk.nsub > 1 ? (blk.bswz ? (uint32_t)((blk.kchunks[1] + 7) / 8) * TCS_N * 128 : (uint32_t)blk.kchunks[1] * TCS_N * 16) : 0u;
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar(2 * TCS_STAGES + 8)), "r"(b_bytes0 + b_bytes1) : "memory");
                 for (int sub = 0; sub < blk.nsub; ++sub) {
                     const uint32_t nbytes = sub ? b_bytes1 : b_bytes0, dst = sB_addr + (sub ? b_bytes0 : 0u);
@@ -318,7 +334,8 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
                 }
             }
             tcs_wait(bar(2 * TCS_STAGES + 8), 0);
-            const uint64_t dbA = tcs_desc(sB_addr, TCS_N * 16, 128), dbB = tcs_desc(sB_addr + b_bytes0, TCS_N * 16, 128);
+            const uint64_t dbA = blk.bswz ? tcs_desc_sw128(sB_addr) : tcs_desc(sB_addr, TCS_N * 16, 128);
+            const uint64_t dbB = blk.bswz ? tcs_desc_sw128(sB_addr + b_bytes0) : tcs_desc(sB_addr + b_bytes0, TCS_N * 16, 128);
             const int kpA = blk.kchunks[0] >> 1, kpB = blk.kchunks[1] >> 1;
             TCS_PROF(long long w_full = 0; long long w_acc = 0;)
             const long long t_start = clock64();
@@ -339,9 +356,9 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
                         TCS_PROF(w_acc += clock64() - t0;)
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint64_t da0 = tcs_desc(sA_addr + st * TCS_STAGE_BYTES + par * 2 * TCS_PLANE_BYTES, TCS_PLANE_BYTES, 128);
-                        const uint64_t dbs = (sub ? dbB : dbA) + (uint64_t)(h * accw);   // B rows (slots) h*accw .. : 16 B per row and chunk
+                        const uint64_t dbs = (sub ? dbB : dbA) + (uint64_t)(h * accw * (blk.bswz ? 8 : 1));   // B rows (slots) h*accw .. : 16 (128) B per row
                         const int kp = sub ? kpB : kpA;
-                        tcs_issue(kp, tmem + ac * accw, da0, dbs, idesc);
+                        tcs_issue(blk.bswz != 0, kp, tmem + ac * accw, da0, dbs, idesc);
                         tcs_commit(bar(2 * TCS_STAGES + ac));
                     }
                 }
