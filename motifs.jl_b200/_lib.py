@@ -14,7 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "lib", "libmotifs_b200.so")
+    # MB200_LIBRARY: another build of the same ABI (A/B measurements of kernel changes on one box)
+    return os.environ.get("MB200_LIBRARY") or os.path.join(_HERE, "lib", "libmotifs_b200.so")
 
 
 class MB200Error(RuntimeError):

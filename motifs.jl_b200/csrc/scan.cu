@@ -843,12 +843,7 @@ static bool build_tc_plan(const ScanPlan& P, const uint16_t* pwms, const int64_t
     size_t total = 0;
     std::vector<int> kcs(nblocks);
     std::vector<int64_t> boff(nblocks);
-    // Optional: B staged with the 128-byte swizzle (rows of 64 halves, K padded to whole rows) instead of the no-swizzle chunk planes (the
-    // layout A needs for its sliding window).  Parity-green, but measured slower on config 4 (2 M x 200 bp: 90.1 vs 85.6 ms per step on the
-    // same box; the padded rows also stop the two longest blocks from sharing a CTA), so the operand layout is not what limits the MMAs.
-    bool bswz = getenv("MB200_SCAN_TC_BSWZ") ? atoi(getenv("MB200_SCAN_TC_BSWZ")) != 0 : false;
-    if (const char* e = getenv("MB200_SCAN_TC_PAIR")) if (atoi(e) != 0) bswz = false;             // k_scan_tc2 stages half planes of the no-swizzle layout
-    auto bbytes_of = [&](int kc) { return bswz ? (size_t)((kc + 7) / 8) * TCS_N * 128 : (size_t)kc * TCS_N * 16; };
+    auto bbytes_of = [&](int kc) { return (size_t)kc * TCS_N * 16; };
     for (int bi = 0; bi < nblocks; ++bi) {
         int kc = (std::max(blen[bi], 1) + 1) / 2;
         kc = std::max(2, (kc + 1) & ~1);
@@ -861,11 +856,7 @@ static bool build_tc_plan(const ScanPlan& P, const uint16_t* pwms, const int64_t
         for (int sidx = 0; sidx < TCS_N; ++sidx) {
             const int slot = bi * TCS_N + sidx;
             const std::vector<uint16_t>& c = col0[slot];
-            // position (in halves) of half e of K chunk ch of slot sidx
-            auto at = [&](int ch, int e) -> size_t {
-                if (!bswz) return ((size_t)ch * TCS_N + sidx) * 8 + e;
-                return ((size_t)(ch >> 3) * TCS_N + sidx) * 64 + (size_t)(((ch & 7) ^ (sidx & 7)) * 8) + e;
-            };
+            auto at = [&](int ch, int e) -> size_t { return ((size_t)ch * TCS_N + sidx) * 8 + e; };     // half e of K chunk ch of this slot
             if (c.empty()) {                                       // disabled slot: D = -1 everywhere
                 for (int b = 0; b < 4; ++b) Bm[at(0, b)] = 0xBC00u;
                 T.slots[slot].npos = 0;
@@ -885,7 +876,7 @@ static bool build_tc_plan(const ScanPlan& P, const uint16_t* pwms, const int64_t
     for (int bi = 0; bi < nblocks; ++bi) ord[bi] = bi;
     std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return kcs[x] > kcs[y]; });
     const double drain = 1000.0;
-    const size_t b_budget = (bswz ? (size_t)225 : (size_t)200) * 1024 - (size_t)TCS_STAGES * TCS_STAGE_BYTES;       // 227 KB per CTA minus static shared memory and the stages
+    const size_t b_budget = (size_t)200 * 1024 - (size_t)TCS_STAGES * TCS_STAGE_BYTES;
     const bool no_pair = getenv("MB200_SCAN_TC_NOPAIR") != nullptr;
     std::vector<double> cost;
     for (int i = 0; i < nblocks;) {
@@ -893,7 +884,6 @@ static bool build_tc_plan(const ScanPlan& P, const uint16_t* pwms, const int64_t
         const int L = ord[i];
         e.b_off[0] = boff[L]; e.kchunks[0] = kcs[L]; e.slot0[0] = L * TCS_N; e.nsub = 1;
         size_t bbytes = bbytes_of(kcs[L]);
-        e.bswz = bswz ? 1 : 0;
         if (i + 1 < nblocks && !no_pair && bbytes + bbytes_of(kcs[ord[i + 1]]) <= b_budget) {
             const int S = ord[i + 1];
             e.b_off[1] = boff[S]; e.kchunks[1] = kcs[S]; e.slot0[1] = S * TCS_N; e.nsub = 2;
@@ -906,22 +896,9 @@ static bool build_tc_plan(const ScanPlan& P, const uint16_t* pwms, const int64_t
             cost.push_back(std::max(1.19 * 2.0 * kcs[L] * 64.0, 2.0 * drain + 350.0));
             i += 1;
         }
-        // Four 128-column accumulators (a drain then overlaps the MMAs of three other uses) were tried for the entries whose MMAs are
-        // shorter than the drain: measured 25 % SLOWER on config 4 (2 M x 200 bp: 75.9 -> 95.3 ms; all entries at 128 columns: 116.9 ms) —
-        // an N = 128 MMA re-reads the same 4 KB A operand for half the math and the operand fetch, not the math, then paces the pipe.
-        // Kept selectable for experiments only.
-        e.accw = 256;
-        // ... except when the upper 128 slots of every block of the entry are padding (few motifs, e.g. BASELINE config 5 with 50 PWMs): with
-        // 128-column accumulators that half is skipped altogether
-        auto upper_empty = [&](int blkidx) { for (int sidx = TCS_N / 2; sidx < TCS_N; ++sidx) if (!col0[blkidx * TCS_N + sidx].empty()) return false; return true; };
-        e.nh[0] = e.nh[1] = 2;
-        {
-            bool all_empty = upper_empty(L);
-            if (e.nsub > 1) all_empty = all_empty && upper_empty((int)(e.slot0[1] / TCS_N));
-            // measured on config 5 (250 Mbp x 50 PWMs): 13.5 ms with the half skipped vs 12.3 ms with full 256-column MMAs — opt-in only
-            if (all_empty && getenv("MB200_SCAN_TC_HALF")) { e.accw = 128; e.nh[0] = e.nh[1] = 1; }
-        }
-        if (const char* ev = getenv("MB200_SCAN_TC_ACCW")) { const int w = atoi(ev); if (w == 128 || w == 256) e.accw = w; }
+        // Tried and removed (git history: 59d1900, 004a558, 1f9ca7b): four 128-column accumulators for short entries (25 %
+        // slower), skipping an all-padding upper column half (slower on config 5), B staged with the 128-byte swizzle (5 % slower).  The
+        // generic code paths they needed cost the production kernel 13 % (the MMA warp's instruction stream paces the tensor pipe).
         T.max_b_bytes = std::max(T.max_b_bytes, bbytes);
         T.blocks.push_back(e);
     }
@@ -1102,7 +1079,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
         if (tc_pair && !tc_assign(TP.blocks, TP.cost, ctx->sm_count, true)) tc_pair = false;
         // start from the clocks per tile measured by the previous scan of this ctx when it had the same block structure
         std::vector<int32_t> sig;
-        for (auto& e : TP.blocks) { sig.push_back(e.nsub); sig.push_back(e.kchunks[0]); sig.push_back(e.kchunks[1]); sig.push_back(e.accw); sig.push_back(e.bswz); }
+        for (auto& e : TP.blocks) { sig.push_back(e.nsub); sig.push_back(e.kchunks[0]); sig.push_back(e.kchunks[1]); }
         sig.push_back(tc_pair ? 2 : 1);
         if (sig == ctx->tc_cost_sig && ctx->tc_cost.size() == TP.blocks.size()) { TP.cost = ctx->tc_cost; tc_assign(TP.blocks, TP.cost, ctx->sm_count, tc_pair); }
         else { ctx->tc_cost_sig = sig; ctx->tc_cost.clear(); }

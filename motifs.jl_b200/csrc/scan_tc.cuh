@@ -50,11 +50,7 @@ struct TcBlock {                           // what one CTA works on: one block o
     int32_t slot0[2];                      // first global slot
     int32_t nsub;                          // 1, or 2: sub-block 0 (the longer one) accumulates in TMEM columns [0,256), sub-block 1 in [256,512)
     int32_t cta0, nctas;                   // CTAs [cta0, cta0 + nctas) work on this entry
-    int32_t accw;                          // accumulator width in TMEM columns: 256 (two accumulators) or 128 (four accumulators)
-    int32_t bswz;                          // 1: B operands are staged in the 128-byte-swizzled K-major layout ([K block of 64 halves][256 slots][128 B],
-                                           // 16-byte chunk c of slot n stored at chunk c ^ (n & 7)) instead of the no-swizzle chunk planes
-    int32_t nh[2];                         // accw = 128: column halves of each sub-block that hold any enabled slot (1: the upper 128 slots are
-                                           // padding and are neither multiplied nor drained — scans with few motifs)
+    int32_t pad;
 };
 struct TcSlot {                            // per global slot, for the epilogue (npos) and the verifier
     int32_t motif;                         // original motif index, -1: disabled
@@ -188,35 +184,22 @@ __device__ __noinline__ void tcs_append(unsigned long long* list, unsigned long 
 // The K loop of one accumulator use, fully unrolled per trip count: with compile-time t the descriptors of step t are the first
 // ones plus constants (one uniform 64-bit add each).  A run-time loop costs ~26 dependent instructions per MMA in the single issuing
 // thread (ELECT + seven R2UR per MMA): ~180 clocks per 128-clock MMA, i.e. the issuing thread, not the tensor pipe, set the pace.
-template <int KP, bool SWZ>
+template <int KP>
 __device__ __forceinline__ void tcs_issue_n(uint32_t tmem_d, uint64_t da0, uint64_t db0, uint32_t idesc) {
     #pragma unroll
-    for (int t = 0; t < KP; ++t) {
-        // K step t = chunks 2t, 2t+1.  no-swizzle: chunk planes of 256 x 16 B; swizzle-128B: 4 steps per 128-byte row, 32 B apart, then the
-        // next 32 KB K block (start-address field counts 16-byte units)
-        const uint64_t dboff = SWZ ? (uint64_t)((t >> 2) * ((TCS_N * 128) >> 4) + (t & 3) * 2) : (uint64_t)(2 * t * TCS_N);
-        tcs_mma(tmem_d, da0 + (uint64_t)(2 * t), db0 + dboff, idesc, t ? 1u : 0u);
-    }
+    for (int t = 0; t < KP; ++t) tcs_mma(tmem_d, da0 + (uint64_t)(2 * t), db0 + (uint64_t)(2 * t * TCS_N), idesc, t ? 1u : 0u);
 }
-template <bool SWZ>
-__device__ __forceinline__ void tcs_issue_s(int kp, uint32_t tmem_d, uint64_t da0, uint64_t db0, uint32_t idesc) {
+__device__ __forceinline__ void tcs_issue(int kp, uint32_t tmem_d, uint64_t da0, uint64_t db0, uint32_t idesc) {
     switch (kp) {
-        case 1: tcs_issue_n<1, SWZ>(tmem_d, da0, db0, idesc); break;   case 2: tcs_issue_n<2, SWZ>(tmem_d, da0, db0, idesc); break;
-        case 3: tcs_issue_n<3, SWZ>(tmem_d, da0, db0, idesc); break;   case 4: tcs_issue_n<4, SWZ>(tmem_d, da0, db0, idesc); break;
-        case 5: tcs_issue_n<5, SWZ>(tmem_d, da0, db0, idesc); break;   case 6: tcs_issue_n<6, SWZ>(tmem_d, da0, db0, idesc); break;
-        case 7: tcs_issue_n<7, SWZ>(tmem_d, da0, db0, idesc); break;   case 8: tcs_issue_n<8, SWZ>(tmem_d, da0, db0, idesc); break;
-        case 9: tcs_issue_n<9, SWZ>(tmem_d, da0, db0, idesc); break;   case 10: tcs_issue_n<10, SWZ>(tmem_d, da0, db0, idesc); break;
-        case 11: tcs_issue_n<11, SWZ>(tmem_d, da0, db0, idesc); break; case 12: tcs_issue_n<12, SWZ>(tmem_d, da0, db0, idesc); break;
-        case 13: tcs_issue_n<13, SWZ>(tmem_d, da0, db0, idesc); break; case 14: tcs_issue_n<14, SWZ>(tmem_d, da0, db0, idesc); break;
-        case 15: tcs_issue_n<15, SWZ>(tmem_d, da0, db0, idesc); break; default: tcs_issue_n<16, SWZ>(tmem_d, da0, db0, idesc); break;
+        case 1: tcs_issue_n<1>(tmem_d, da0, db0, idesc); break;   case 2: tcs_issue_n<2>(tmem_d, da0, db0, idesc); break;
+        case 3: tcs_issue_n<3>(tmem_d, da0, db0, idesc); break;   case 4: tcs_issue_n<4>(tmem_d, da0, db0, idesc); break;
+        case 5: tcs_issue_n<5>(tmem_d, da0, db0, idesc); break;   case 6: tcs_issue_n<6>(tmem_d, da0, db0, idesc); break;
+        case 7: tcs_issue_n<7>(tmem_d, da0, db0, idesc); break;   case 8: tcs_issue_n<8>(tmem_d, da0, db0, idesc); break;
+        case 9: tcs_issue_n<9>(tmem_d, da0, db0, idesc); break;   case 10: tcs_issue_n<10>(tmem_d, da0, db0, idesc); break;
+        case 11: tcs_issue_n<11>(tmem_d, da0, db0, idesc); break; case 12: tcs_issue_n<12>(tmem_d, da0, db0, idesc); break;
+        case 13: tcs_issue_n<13>(tmem_d, da0, db0, idesc); break; case 14: tcs_issue_n<14>(tmem_d, da0, db0, idesc); break;
+        case 15: tcs_issue_n<15>(tmem_d, da0, db0, idesc); break; default: tcs_issue_n<16>(tmem_d, da0, db0, idesc); break;
     }
-}
-__device__ __forceinline__ void tcs_issue(bool swz, int kp, uint32_t tmem_d, uint64_t da0, uint64_t db0, uint32_t idesc) {
-    if (swz) tcs_issue_s<true>(kp, tmem_d, da0, db0, idesc); else tcs_issue_s<false>(kp, tmem_d, da0, db0, idesc);
-}
-// UMMA shared-memory descriptor of a 128-byte-swizzled K-major operand: LBO unused (1), SBO = 1024 B (8 rows x 128 B), layout type 2
-__device__ __forceinline__ uint64_t tcs_desc_sw128(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
 // Work item = one tile of 256 consecutive virtual start positions = two parities (even / odd offsets) of 128 rows.
@@ -231,7 +214,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
     extern __shared__ __align__(1024) uint8_t tcs_smem[];
     uint8_t* sA = tcs_smem;                                              // [TCS_STAGES][2 parities][2 planes][TCS_STREAM][16 B]
     uint8_t* sB = tcs_smem + TCS_STAGES * TCS_STAGE_BYTES;               // per sub-block [kchunks][256][16 B]
-    __shared__ __align__(8) uint64_t s_bars[2 * TCS_STAGES + 9];         // full[S], empty[S], accfull[4], accempty[4], B landed
+    __shared__ __align__(8) uint64_t s_bars[2 * TCS_STAGES + 5];         // full[S], empty[S], accfull[2], accempty[2], B landed
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     auto bar = [&](int i) { return (uint32_t)__cvta_generic_to_shared(&s_bars[i]); };
@@ -244,9 +227,9 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
     if (rank >= blk.nctas) return;
 
     if (tid == 0) {
-        for (int i = 0; i < 2 * TCS_STAGES + 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(i)) : "memory");
-        for (int i = 2 * TCS_STAGES + 4; i < 2 * TCS_STAGES + 8; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 16;" :: "r"(bar(i)) : "memory");   // all 16 epilogue warps drain every accumulator use
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(2 * TCS_STAGES + 8)) : "memory");
+        for (int i = 0; i < 2 * TCS_STAGES + 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(i)) : "memory");
+        for (int i = 2 * TCS_STAGES + 2; i < 2 * TCS_STAGES + 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 16;" :: "r"(bar(i)) : "memory");   // all 16 epilogue warps drain every accumulator use
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(2 * TCS_STAGES + 4)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -263,8 +246,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
     const uint32_t tmem = s_tmem;
     const uint32_t sA_addr = (uint32_t)__cvta_generic_to_shared(sA), sB_addr = (uint32_t)__cvta_generic_to_shared(sB);
     // instruction descriptor: D = F32 (1<<4), A = B = F16 (format 0), both K-major, N>>3 at bit 17, M>>4 at bit 24
-    const int accw = blk.accw, nacc = 512 / blk.accw, halves = TCS_N / blk.accw;         // accumulators in TMEM, column halves per slot block
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(accw >> 3) << 17) | ((uint32_t)(TCS_M >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(TCS_N >> 3) << 17) | ((uint32_t)(TCS_M >> 4) << 24);
 
     if (warp == 0 || warp == TCS_THREADS / 32 - 1) {
         // ---- producers: bases v0 .. v0+319 of the tile -> even stream E[m] = (b[2m], b[2m+1]), odd stream O[m] = (b[2m+1], b[2m+2]),
@@ -319,27 +301,25 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
         TCS_PROF(if (a.dbg && warp == 0 && lane == 0) a.dbg[blockIdx.x * 8 + 5] = w_prod;)
     } else if (warp == 1) {
         {   // ---- MMA warp: all 32 lanes run this code converged; tcs_mma / tcs_commit elect the issuing lane ----
-            // bytes of a B operand: chunk planes, or whole 128-byte rows per K block of 8 chunks
-            const uint32_t b_bytes0 = blk.bswz ? (uint32_t)((blk.kchunks[0] + 7) / 8) * TCS_N * 128 : (uint32_t)blk.kchunks[0] * TCS_N * 16;
+            const uint32_t b_bytes0 = (uint32_t)blk.kchunks[0] * TCS_N * 16;
             if (lane == 0) {   // the B operands, resident for the whole kernel
-                const uint32_t b_bytes1 = blk.nsub > 1 ? (blk.bswz ? (uint32_t)((blk.kchunks[1] + 7) / 8) * TCS_N * 128 : (uint32_t)blk.kchunks[1] * TCS_N * 16) : 0u;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar(2 * TCS_STAGES + 8)), "r"(b_bytes0 + b_bytes1) : "memory");
+                const uint32_t b_bytes1 = blk.nsub > 1 ? (uint32_t)blk.kchunks[1] * TCS_N * 16 : 0u;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar(2 * TCS_STAGES + 4)), "r"(b_bytes0 + b_bytes1) : "memory");
                 for (int sub = 0; sub < blk.nsub; ++sub) {
                     const uint32_t nbytes = sub ? b_bytes1 : b_bytes0, dst = sB_addr + (sub ? b_bytes0 : 0u);
                     for (uint32_t o = 0; o < nbytes; o += 32768u) {
                         const uint32_t nb = min(32768u, nbytes - o);
                         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                     :: "r"(dst + o), "l"(a.blob + blk.b_off[sub] + o), "r"(nb), "r"(bar(2 * TCS_STAGES + 8)) : "memory");
+                                     :: "r"(dst + o), "l"(a.blob + blk.b_off[sub] + o), "r"(nb), "r"(bar(2 * TCS_STAGES + 4)) : "memory");
                     }
                 }
             }
-            tcs_wait(bar(2 * TCS_STAGES + 8), 0);
-            const uint64_t dbA = blk.bswz ? tcs_desc_sw128(sB_addr) : tcs_desc(sB_addr, TCS_N * 16, 128);
-            const uint64_t dbB = blk.bswz ? tcs_desc_sw128(sB_addr + b_bytes0) : tcs_desc(sB_addr + b_bytes0, TCS_N * 16, 128);
+            tcs_wait(bar(2 * TCS_STAGES + 4), 0);
+            const uint64_t dbA = tcs_desc(sB_addr, TCS_N * 16, 128), dbB = tcs_desc(sB_addr + b_bytes0, TCS_N * 16, 128);
             const int kpA = blk.kchunks[0] >> 1, kpB = blk.kchunks[1] >> 1;
             TCS_PROF(long long w_full = 0; long long w_acc = 0;)
             const long long t_start = clock64();
-            uint32_t u = 0;                                                              // accumulator uses so far: use u goes to accumulator u % nacc
+            uint32_t use0 = 0, use1 = 0;                                                 // completed uses of each accumulator
             int it = 0;
             for (int tile = rank; tile < a.ntiles; tile += blk.nctas, ++it) {
                 const int st = it % TCS_STAGES; const uint32_t ph = (it / TCS_STAGES) & 1;
@@ -348,18 +328,19 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
                 TCS_PROF(w_full += clock64() - t0;)
                 #pragma unroll
                 for (int par = 0; par < 2; ++par) {
-                    for (int sub = 0; sub < blk.nsub; ++sub)
-                    for (int h = 0; h < (halves > 1 ? blk.nh[sub] : 1); ++h, ++u) {
-                        const uint32_t ac = u % (uint32_t)nacc, uses = u / (uint32_t)nacc;
+                    for (int sub = 0; sub < blk.nsub; ++sub) {
+                        const int ac = blk.nsub > 1 ? sub : par;
+                        const uint32_t uses = ac ? use1 : use0;
                         TCS_PROF(t0 = clock64();)
-                        tcs_wait(bar(2 * TCS_STAGES + 4 + ac), (uses & 1) ^ 1);          // accumulator drained
+                        tcs_wait(bar(2 * TCS_STAGES + 2 + ac), (uses & 1) ^ 1);          // accumulator drained
                         TCS_PROF(w_acc += clock64() - t0;)
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint64_t da0 = tcs_desc(sA_addr + st * TCS_STAGE_BYTES + par * 2 * TCS_PLANE_BYTES, TCS_PLANE_BYTES, 128);
-                        const uint64_t dbs = (sub ? dbB : dbA) + (uint64_t)(h * accw * (blk.bswz ? 8 : 1));   // B rows (slots) h*accw .. : 16 (128) B per row
+                        const uint64_t dbs = sub ? dbB : dbA;
                         const int kp = sub ? kpB : kpA;
-                        tcs_issue(blk.bswz != 0, kp, tmem + ac * accw, da0, dbs, idesc);
+                        tcs_issue(kp, tmem + ac * TCS_N, da0, dbs, idesc);
                         tcs_commit(bar(2 * TCS_STAGES + ac));
+                        if (ac) ++use1; else ++use0;
                     }
                 }
                 tcs_commit(bar(TCS_STAGES + st));
@@ -377,39 +358,35 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
         unsigned long long cur_end[2] = {0, 0};                                          // this warp's reserved slice of the candidate list
         uint32_t dead = 0;                                                               // list capacity exhausted
         TCS_PROF(long long w_epi = 0; const long long t_start = clock64();)
-        const int wcols = accw / 4;                                                      // columns of an accumulator per warp: 64 or 32
-        uint32_t u = 0;
+        uint32_t use0 = 0, use1 = 0;                                                     // completed uses of each accumulator
         int it = 0;
         for (int tile = rank; tile < a.ntiles; tile += blk.nctas, ++it)
         for (int par = 0; par < 2; ++par)
-        for (int sub = 0; sub < blk.nsub; ++sub)
-        for (int h = 0; h < (halves > 1 ? blk.nh[sub] : 1); ++h, ++u) {
-            const uint32_t ac = u % (uint32_t)nacc, uses = u / (uint32_t)nacc;
+        for (int sub = 0; sub < blk.nsub; ++sub) {
+            const int ac = blk.nsub > 1 ? sub : par;
+            const uint32_t uses = ac ? use1 : use0;
+            if (ac) ++use1; else ++use0;
             const uint32_t v = (uint32_t)tile * 256u + (uint32_t)par + 2u * (uint32_t)(q * 32 + lane);
             const bool inb = v < a.vtotal;
             TCS_PROF(const long long t0 = clock64();)
             tcs_wait(bar(2 * TCS_STAGES + ac), uses & 1);
             TCS_PROF(w_epi += clock64() - t0;)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem + ac * accw + cg * wcols + ((uint32_t)(q * 32) << 16);
+            const uint32_t taddr = tmem + ac * TCS_N + cg * 64 + ((uint32_t)(q * 32) << 16);
             uint32_t ua[32], ub[32];
             TCS_LDTM32(ua, taddr);
-            if (wcols == 64) { TCS_LDTM32(ub, taddr + 32); }
-            else {
-                #pragma unroll
-                for (int i = 0; i < 32; ++i) ub[i] = 0xBF800000u;                        // -1.0f: never positive
-            }
+            TCS_LDTM32(ub, taddr + 32);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar(2 * TCS_STAGES + 4 + ac)) : "memory");    // the values are in registers: the accumulator may be overwritten
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar(2 * TCS_STAGES + 2 + ac)) : "memory");    // the values are in registers: the accumulator may be overwritten
             const float ma = tcs_max32(ua), mb = tcs_max32(ub);
             const bool pos = inb && fmaxf(ma, mb) > 0.f;
             if (__any_sync(0xffffffffu, pos)) {          /* about one use in ten at the usual thresholds */
                 uint32_t cb0 = 0u, cb1 = 0u;             // bit masks of the positive columns, only for the chunk(s) that have any
                 if (__any_sync(0xffffffffu, inb && ma > 0.f)) cb0 = pos ? tcs_posbits(ua) : 0u;
                 if (__any_sync(0xffffffffu, inb && mb > 0.f)) cb1 = pos ? tcs_posbits(ub) : 0u;
-                tcs_append(a.list, a.gcount, a.cap, a.overflow, lane, cb0, cb1, (uint32_t)(blk.slot0[sub] + h * accw + cg * wcols), v, cur_end, &dead);
+                tcs_append(a.list, a.gcount, a.cap, a.overflow, lane, cb0, cb1, (uint32_t)(blk.slot0[sub] + cg * 64), v, cur_end, &dead);
             }
         }
         for (unsigned long long i = cur_end[0] + lane; i < cur_end[1]; i += 32) a.list[i] = ~0ull;
