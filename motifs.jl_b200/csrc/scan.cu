@@ -788,7 +788,7 @@ static bool build_tc_plan(const ScanPlan& P, const uint16_t* pwms, const int64_t
     if (!thresh || !P.lblocks.empty()) return false;
     const int nslots = (P.K2pad + TCS_N - 1) / TCS_N * TCS_N;
     const int nblocks = nslots / TCS_N;
-    if (nblocks > grid) return false;
+    if (nblocks > grid || nblocks > TCS_MAX_ENTRIES) return false;
     auto pw = [&](int k, int a, int ind) -> uint16_t { return pwms[(size_t)k + (size_t)K * ((size_t)a + 4 * (size_t)ind)]; };
     TcSlot off; memset(&off, 0, sizeof off); off.motif = -1; off.thr = 0x7C00u;
     T.slots.assign(nslots, off);
@@ -1235,8 +1235,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
                 cost[bi] = clk / tiles;
             }
             if (ok) ctx->tc_cost = cost;
-            if (ok && tc_assign(TP.blocks, cost, grid, tc_pair) &&
-                cudaMemcpyAsync(d_tc + tc_off_blocks, TP.blocks.data(), TP.blocks.size() * sizeof(TcBlock), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return MB200_E_CUDA;
+            if (ok) tc_assign(TP.blocks, cost, grid, tc_pair);          // the next launch carries the new split in its parameters
             return MB200_OK;
         };
         int i = 0;
@@ -1263,7 +1262,8 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
             TcArgs ta;
             ta.seqw = seqs->words; ta.rowwords = rowwords; ta.seq0 = s0;
             ta.Lb = (uint32_t)Lb; ta.vtotal = (uint32_t)(ns * Lb);
-            ta.blob = d_tc; ta.blocks = (const TcBlock*)(d_tc + tc_off_blocks); ta.nblocks = (int32_t)TP.blocks.size();
+            ta.blob = d_tc; ta.nblocks = (int32_t)TP.blocks.size();
+            memset(ta.blocks, 0, sizeof ta.blocks); memcpy(ta.blocks, TP.blocks.data(), TP.blocks.size() * sizeof(TcBlock));
             ta.slots = (const TcSlot*)(d_tc + tc_off_slots);
             ta.list = list_b; ta.cap = tc_cap; ta.gcount = ctr_b; ta.overflow = (uint32_t*)(ctr_b + 1);
             ta.ntiles = (int32_t)((ns * Lb + 255) / 256);
@@ -1358,7 +1358,8 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
             TcArgs ta;
             ta.seqw = seqs->words; ta.rowwords = rowwords; ta.seq0 = s0;
             ta.Lb = (uint32_t)Lb; ta.vtotal = (uint32_t)(ns * Lb);
-            ta.blob = d_tc; ta.blocks = (const TcBlock*)(d_tc + tc_off_blocks); ta.nblocks = (int32_t)TP.blocks.size();
+            ta.blob = d_tc; ta.nblocks = (int32_t)TP.blocks.size();
+            memset(ta.blocks, 0, sizeof ta.blocks); memcpy(ta.blocks, TP.blocks.data(), TP.blocks.size() * sizeof(TcBlock));
             ta.slots = (const TcSlot*)(d_tc + tc_off_slots);
             ta.list = d_tc_list; ta.cap = tc_cap; ta.gcount = d_tc_ctr; ta.overflow = (uint32_t*)(d_tc_ctr + 1);
             ta.ntiles = (int32_t)((ns * Lb + 255) / 256);
@@ -1402,8 +1403,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
                     cost[bi] = clk / tiles;
                 }
                 if (ok) ctx->tc_cost = cost;
-                if (ok && tc_assign(TP.blocks, cost, grid, tc_pair))
-                    MB_CUDA(ctx, cudaMemcpyAsync(d_tc + tc_off_blocks, TP.blocks.data(), TP.blocks.size() * sizeof(TcBlock), cudaMemcpyHostToDevice, ctx->stream));
+                if (ok) tc_assign(TP.blocks, cost, grid, tc_pair);
             }
             tc_stat_cand += h_ctr[2]; tc_stat_hits += h_ctr[3];
             ctx->mask_clean_bytes = 0;                               // the verifier has set bits (re-established below when the sparse count clears them)

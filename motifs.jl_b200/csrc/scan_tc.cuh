@@ -35,6 +35,7 @@
 #define TCS_THREADS 608                    // warps: 0 and 18 producers, 1 MMA issue, 2-17 epilogue
 #define TCS_RESERVE 256                    // candidate records reserved per global atomic
 #define TCS_MAX_KCHUNKS 32                 // 64 columns x 4 bases / 8
+#define TCS_MAX_ENTRIES 16                 // work entries (single or paired slot blocks) per launch: up to 4096 motifs
 #ifndef TCS_PROFILE
 #define TCS_PROFILE 0                      // 1: per-role wait clocks in TcArgs::dbg (printed with MB200_SCAN_TC_DEBUG=1)
 #endif
@@ -61,7 +62,9 @@ struct TcSlot {                            // per global slot, for the epilogue 
 struct TcArgs {
     const uint32_t* seqw; int64_t rowwords; int64_t seq0;
     uint32_t Lb; uint32_t vtotal;          // virtual positions of the batch: v = n_local * Lb + p
-    const uint8_t* blob; const TcBlock* blocks; int32_t nblocks;
+    const uint8_t* blob; int32_t nblocks;
+    TcBlock blocks[TCS_MAX_ENTRIES];       // by value: kernel parameters live in the constant bank, so everything derived from an entry (trip
+                                           // counts, descriptors) is provably warp-uniform and stays in uniform registers
     const TcSlot* slots;
     unsigned long long* list; unsigned long long cap; unsigned long long* gcount;   // candidate list, its capacity, reserved records
     uint32_t* overflow;
