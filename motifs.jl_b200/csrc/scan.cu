@@ -435,7 +435,8 @@ __global__ void __launch_bounds__(256) count_kernel(const uint32_t* __restrict__
 // them); all other units have no hits and contribute nothing.  Clears the words it reads.
 __global__ void __launch_bounds__(256) count_listed_kernel(uint32_t* __restrict__ mask, const uint32_t* __restrict__ units, const unsigned long long* __restrict__ n_units,
                                                            int32_t W, int32_t K2pad, const int32_t* __restrict__ pair2motif, const int32_t* __restrict__ pairlen,
-                                                           unsigned long long* __restrict__ counts, const unsigned long long* __restrict__ overflow) {
+                                                           unsigned long long* __restrict__ counts, const unsigned long long* __restrict__ overflow,
+                                                           uint32_t* __restrict__ unit_cnt, int32_t K, int32_t clear) {
     const int32_t P = K2pad / 2;
     if (overflow && *overflow) return;                                                    // candidate list overflowed: the batch is re-run on scan_kernel
     const unsigned long long total = *n_units;
@@ -443,7 +444,21 @@ __global__ void __launch_bounds__(256) count_listed_kernel(uint32_t* __restrict_
         const uint32_t g = units[i];
         const int64_t n = g / (uint32_t)P;
         const int32_t m2 = (int32_t)(g - (uint32_t)n * (uint32_t)P);
-        count_unit<true>(mask, n, m2, W, P, pair2motif[m2], pairlen[m2], counts, nullptr, 0);
+        if (clear) count_unit<true>(mask, n, m2, W, P, pair2motif[m2], pairlen[m2], counts, unit_cnt, K);
+        else count_unit<false>(mask, n, m2, W, P, pair2motif[m2], pairlen[m2], counts, unit_cnt, K);     // the hit list is still to be emitted from these words
+    }
+}
+// after the hit list has been emitted: zero the mask words of the listed units so that the buffer is all-zero again
+__global__ void __launch_bounds__(256) clear_listed_kernel(uint32_t* __restrict__ mask, const uint32_t* __restrict__ units, const unsigned long long* __restrict__ n_units,
+                                                           int32_t W, int32_t K2pad) {
+    const int32_t P = K2pad / 2;
+    const unsigned long long total = *n_units * (unsigned long long)W;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t g = units[i / W];
+        const int32_t w = (int32_t)(i % W);
+        const int64_t n = g / (uint32_t)P;
+        const int32_t m2 = (int32_t)(g - (uint32_t)n * (uint32_t)P);
+        reinterpret_cast<uint2*>(mask)[((n * W) + w) * (int64_t)P + m2] = make_uint2(0u, 0u);
     }
 }
 
@@ -1124,6 +1139,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
     // tensor-core path: plan (B operands, blocks, slots) in buf 8, candidate list + counters in buf 9
     const unsigned long long tc_cap = (unsigned long long)24 << 20;      // candidate records per batch and buffer set
     const bool tc_sparse = !want_hits && !hist && W <= 4096;        // counts only: count the units the verifier lists, never walk (or clear) the whole mask
+    const bool tc_units = !hist && W <= 4096;                       // the verifier lists the (sequence, motif) units that received a hit (also for hit lists)
     size_t tc_off_blocks = 0, tc_off_slots = 0, tc_smem = 0, tc_set_stride = 0, tc_uset_stride = 0;      // strides between the two buffer sets of the pipelined path
     uint8_t* d_tc = nullptr; unsigned long long* d_tc_list = nullptr; unsigned long long* d_tc_ctr = nullptr;     // ctr: [0] reserved, [1] overflow, [2] candidates, [3] hits, [4] listed units, [8..] clocks per CTA
     uint32_t* d_tc_ulist = nullptr; uint32_t* d_tc_ubits = nullptr; unsigned long long tc_stat_cand = 0, tc_stat_hits = 0;
@@ -1283,7 +1299,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
             tm.end_on(t_vf, aux);
             const int t_ct = tm.begin_on(T_COUNT, aux);
             count_listed_kernel<<<grid * 16, 128, 0, aux>>>(d_mask, ulist_b, ctr_b + 4, W, P.K2pad, (const int32_t*)(d_plan + off_p2m),
-                                                           (const int32_t*)(d_plan + off_plen), d_counts, ctr_b + 1);
+                                                           (const int32_t*)(d_plan + off_plen), d_counts, ctr_b + 1, nullptr, 0, 1);
             tm.end_on(t_ct, aux);
             MB_CUDA(ctx, cudaGetLastError());
             MB_CUDA(ctx, cudaMemcpyAsync(h_ctr2 + (size_t)b * nctr, ctr_b, nctr * 8, cudaMemcpyDeviceToHost, aux));
@@ -1354,7 +1370,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
                 ctx->mask_clean_bytes = need;
             }
             MB_CUDA(ctx, cudaMemsetAsync(d_tc_ctr, 0, 64, ctx->stream));
-            if (tc_sparse) MB_CUDA(ctx, cudaMemsetAsync(d_tc_ubits, 0, (((size_t)ns * (size_t)(P.K2pad / 2) + 31) / 32) * 4, ctx->stream));
+            if (tc_units) MB_CUDA(ctx, cudaMemsetAsync(d_tc_ubits, 0, (((size_t)ns * (size_t)(P.K2pad / 2) + 31) / 32) * 4, ctx->stream));
             TcArgs ta;
             ta.seqw = seqs->words; ta.rowwords = rowwords; ta.seq0 = s0;
             ta.Lb = (uint32_t)Lb; ta.vtotal = (uint32_t)(ns * Lb);
@@ -1375,7 +1391,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
             const int t_vf = tm.begin(T_EMIT);
             k_scan_tc_verify<<<grid * 8, 256, 0, ctx->stream>>>(d_tc_list, d_tc_ctr, tc_cap, ta.slots, (const EmitMotif*)(d_plan + off_em), d_plan + off_blob,
                                                                  seqs->words, rowwords, s0, (uint32_t)Lb, W, P.K2pad, d_mask, d_tc_ctr + 2,
-                                                                 tc_sparse ? d_tc_ubits : nullptr, d_tc_ulist, d_tc_ctr + 4);
+                                                                 tc_units ? d_tc_ubits : nullptr, d_tc_ulist, d_tc_ctr + 4);
             tm.end(t_vf);
             ctx->launches[T_SCAN] += 1; ctx->launches[T_EMIT] += 1;
             MB_CUDA(ctx, cudaGetLastError());
@@ -1443,11 +1459,14 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
             count_long_c<<<(unsigned)((ns * Pp + 255) / 256), 256, 0, ctx->stream>>>(ns, Pp, (const int32_t*)(d_plan + off_p2m), (const int32_t*)(d_plan + off_plen),
                 (const unsigned long long*)(lb + o_top1), (const unsigned long long*)(lb + o_top2), (const unsigned int*)(lb + o_dup), (const unsigned int*)(lb + o_nh), d_counts);
             ctx->launches[T_COUNT] += 3;
-        } else if (tc_done && tc_sparse) {
+        } else if (tc_done && tc_units) {
+            // only the units the verifier listed have hits.  Counts-only: count and clear them.  With a hit list: the unit counts feed the
+            // prefix sum (zero elsewhere), the words stay until emit_kernel has read them and are cleared after that.
+            if (want_hits) MB_CUDA(ctx, cudaMemsetAsync(d_unit_cnt, 0, (size_t)ns * K * 2 * 4, ctx->stream));
             count_listed_kernel<<<grid * 8, 256, 0, ctx->stream>>>(d_mask, d_tc_ulist, d_tc_ctr + 4, W, P.K2pad, (const int32_t*)(d_plan + off_p2m),
-                                                                    (const int32_t*)(d_plan + off_plen), d_counts, nullptr);
+                                                                    (const int32_t*)(d_plan + off_plen), d_counts, nullptr, want_hits ? d_unit_cnt : nullptr, K, want_hits ? 0 : 1);
             ctx->launches[T_COUNT] += 1;
-            ctx->mask_clean_bytes = (size_t)ns * mask_bytes_per_seq;   // every word with a bit belongs to a listed unit and was cleared
+            if (!want_hits) ctx->mask_clean_bytes = (size_t)ns * mask_bytes_per_seq;   // every word with a bit belongs to a listed unit and was cleared
         } else {
             const int64_t cthreads = ns * Pp;
             count_kernel<<<(unsigned)((cthreads + 255) / 256), 256, 0, ctx->stream>>>(d_mask, ns, W, P.K2pad, (const int32_t*)(d_plan + off_p2m),
@@ -1494,6 +1513,11 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
                 tm.end(t5);
                 MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
                 hits_written += (int64_t)h_total;
+            }
+            if (tc_done && tc_units) {
+                clear_listed_kernel<<<grid * 8, 256, 0, ctx->stream>>>(d_mask, d_tc_ulist, d_tc_ctr + 4, W, P.K2pad);
+                ctx->launches[T_EMIT] += 1;
+                ctx->mask_clean_bytes = (size_t)ns * mask_bytes_per_seq;
             }
         }
     }

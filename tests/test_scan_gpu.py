@@ -434,6 +434,13 @@ def test_tensor_path_multi_batch_equals_simt_at_scale(ctx):
     assert np.array_equal(c_tc, c_simt)
     _, c_tc3 = ctx.scan(seqs, pw, lens, thr, want_hits=False)                  # after the SIMT kernel dirtied the mask buffer
     assert np.array_equal(c_tc, c_tc3)
+    # sorted hit lists over three batches: listed-unit counting, emit, clearing of the listed units between batches
+    h_tc, ch_tc = ctx.scan(seqs, pw, lens, thr, hits_cap=8_000_000)
+    assert _lib.scan_last_path(ctx) == 1 and np.array_equal(ch_tc, c_tc) and len(h_tc) == int(c_tc[:, 0].sum())
+    _, c_tc4 = ctx.scan(seqs, pw, lens, thr, want_hits=False)                  # the hit-list scan must leave the mask buffer clean
+    assert np.array_equal(c_tc, c_tc4)
+    h_simt, _ = ctx.scan(seqs, pw, lens, thr, hits_cap=8_000_000, tensor=False)
+    assert h_tc.tobytes() == h_simt.tobytes()
     seqs.free()
     h = N // 2 + 12345
     parts = []
