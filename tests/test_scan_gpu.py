@@ -456,3 +456,17 @@ def test_tensor_path_multi_batch_equals_simt_at_scale(ctx):
     _, oc = so.scan(pw, lens, so.ascii_to_codes(sub), thr, want_hits=False)
     assert np.array_equal(c_sub, oc)
     assert c_tc[:, 0].sum() > 0
+
+
+def test_tensor_path_many_motifs(ctx):
+    # 1100 motifs = 9 slot blocks (pairs of neighbouring blocks + one single entry); 2300 motifs exceed the 16 work entries a launch
+    # carries in its parameters and stay on the SIMT kernel
+    a = synth.random_ascii(300, 120, 201)
+    ms = synth.motifs_from_count_matrices(synth.random_count_matrices(1100, 6, 40, 202))
+    thr = synth.stated_thresholds(ms, 0.55)
+    assert _tc_path(ctx, a, ms, thr) == 1
+    _check(ctx, a, ms, thr)
+    ms2 = synth.motifs_from_count_matrices(synth.random_count_matrices(2300, 6, 30, 203))
+    thr2 = synth.stated_thresholds(ms2, 0.6)
+    assert _tc_path(ctx, a[:100], ms2, thr2) == 0
+    _check(ctx, a[:100], ms2, thr2)
