@@ -21,9 +21,10 @@
 // is the stream from chunk m on, so in the canonical K-major no-swizzle UMMA layout (core matrix = 8 rows x 16 B, rows 16 B
 // apart) the operand of K-chunk c is the same stream advanced by c*16 B.  Two copies ("planes", the second shifted by one chunk)
 // give the two K-chunks of one K=16 MMA at LBO = plane stride; SBO = 128 B.  B = W'[K chunk][256 slots][8 halves] stays resident.
-// One CTA per SM owns one block of 256 slots; warp 0 builds streams (from the 2-bit words in L2), one lane of warp 1 issues
-// kchunks/2 MMAs of 128x256x16 per tile and parity, warps 2-17 (eight per TMEM accumulator) drain 32-column chunks with
-// tcgen05.ld, take a 3-input max tree and only look at individual columns when some lane saw a positive value.
+// One CTA per SM owns one or two blocks of 256 slots; warps 0 and 18 build streams (from the 2-bit words in L2), warp 1 (converged, one
+// elected lane per instruction) issues kchunks/2 MMAs of 128x256x16 per tile, block and parity, warps 2-17 drain every accumulator use:
+// two tcgen05.ld of 32 lanes x 32 columns each, accumulator handed back, then a 3-input max tree; individual columns are looked at only
+// when some lane saw a positive value.  "tc_error_bound below" = tc_error_bound() in scan.cu (host).
 #pragma once
 
 #define TCS_M 128
