@@ -1285,6 +1285,13 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
             ta.ntiles = (int32_t)((ns * Lb + 255) / 256);
             ta.clocks = (long long*)(ctr_b + 8);
             ta.dbg = nullptr;
+#if TCS_PROFILE
+            static long long* d_dbg2 = nullptr;
+            if (getenv("MB200_SCAN_TC_DEBUG") && i == atoi(getenv("MB200_SCAN_TC_DEBUG"))) {
+                if (!d_dbg2) cudaMalloc(&d_dbg2, 148 * 8 * 8 * 2);
+                cudaMemsetAsync(d_dbg2, 0, 148 * 8 * 8, ctx->stream); ta.dbg = d_dbg2;
+            }
+#endif
             const int t_tc = tm.begin(T_SCAN);
             if (tc_pair) k_scan_tc2<<<grid, TCS_THREADS, tc_smem, ctx->stream>>>(ta); else k_scan_tc<<<grid, TCS_THREADS, tc_smem, ctx->stream>>>(ta);
             tm.end(t_tc);
@@ -1306,6 +1313,16 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
             MB_CUDA(ctx, cudaEventRecord(ev_aux[b], aux));
             ctx->launches[T_SCAN] += 1; ctx->launches[T_EMIT] += 1; ctx->launches[T_COUNT] += 1;
             launched[i] = 1;
+#if TCS_PROFILE
+            if (ta.dbg) {
+                std::vector<long long> h(148 * 8);
+                cudaStreamSynchronize(ctx->stream);
+                cudaMemcpy(h.data(), ta.dbg, 148 * 8 * 8, cudaMemcpyDeviceToHost);
+                for (int c = 0; c < grid; c += 1)
+                    fprintf(stderr, "[tcdbg] cta %3d blk %lld tiles %lld | mma total %9lld wait_full %9lld wait_acc %9lld | epi total %9lld wait %9lld | prod wait %9lld\n", c, h[c * 8 + 6], h[c * 8 + 7],
+                            h[c * 8 + 0], h[c * 8 + 1], h[c * 8 + 2], h[c * 8 + 4], h[c * 8 + 3], h[c * 8 + 5]);
+            }
+#endif
             if (i >= 1) { rc = process(i - 1); if (rc) return rc; }
         }
         const int n_launched = i;
