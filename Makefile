@@ -13,9 +13,16 @@ HDR       := $(wildcard $(CSRC)/*.cuh) include/motifs_b200.h
 
 all: $(LIB) oracle
 
-$(LIB): $(CU) $(HDR)
+OBJ       := $(patsubst $(CSRC)/%.cu,build/%.o,$(CU))
+
+# one object per translation unit (make -j compiles them in parallel); NCCL is bound at run time (csrc/comm.cu), so only libdl is linked
+build/%.o: $(CSRC)/%.cu $(HDR)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c -o $@ $<
+
+$(LIB): $(OBJ)
 	@mkdir -p $(PKG)/lib
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CU)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(OBJ) -ldl
 
 oracle: oracle/liboracle.so
 
@@ -23,9 +30,9 @@ oracle/liboracle.so: oracle/scan_oracle.c
 	$(CC) -O3 -march=x86-64-v3 -fopenmp -fPIC -shared -Wall -o $@ $< -lm
 
 ptxas-info:
-	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o /tmp/_mb200_info.so $(CU)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o /tmp/_mb200_info.so $(CU) -ldl
 
 clean:
-	rm -f $(LIB) oracle/liboracle.so
+	rm -rf $(LIB) oracle/liboracle.so build
 
 .PHONY: all oracle clean ptxas-info

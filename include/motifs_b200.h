@@ -31,6 +31,7 @@ extern "C" {
 #define MB200_E_BAD_SEQUENCE    -4   /* a byte that is not A,C,G,T (either case) / not one-hot */
 #define MB200_E_HITS_OVERFLOW   -5   /* hits_cap too small; *n_hits holds the required size */
 #define MB200_E_UNSUPPORTED     -6
+#define MB200_E_COMM            -7   /* NCCL missing or a collective failed (see mb200_last_error) */
 
 #define MB200_MAX_MOTIF_LEN     64   /* longest PWM the register-resident scan kernel scores; longer PWMs take a plain kernel */
 
@@ -50,6 +51,28 @@ int32_t     mb200_set_stream(mb200_ctx* ctx, void* cuda_stream);
  * out_ms[0]=pack, [1]=scan kernel, [2]=count kernel, [3]=emit (+prefix), [4]=csc step,
  * [5]=h2d copies, [6]=d2h copies, [7]=total of the call.  launches[i] = kernels launched. */
 int32_t     mb200_last_timing(const mb200_ctx* ctx, float* out_ms8, int64_t* launches8);
+
+/* ---- multi-GPU: one process per GPU, one NCCL communicator per ctx -------------------------
+ * The reference is single-GPU; SURVEY §8e shards the path over sequences: training averages the
+ * filter gradients with ONE all-reduce per step (the loop of train.jl:40-52), a scan sums the per-motif
+ * counts once (render.jl:70-85), code retrieval shards whole batches (_1_code_retrieval.jl:38-50).
+ * Rank 0 calls mb200_comm_unique_id and hands the 128 bytes to the other processes by whatever
+ * means the host has (Julia: Distributed / MPI / a file); every rank then calls mb200_comm_init
+ * (collective).  With a communicator:
+ *   - mb200_csc_adabelief_step averages the gradients over ranks before the update,
+ *   - mb200_csc_broadcast_params makes rank `root`'s parameters and optimiser state everybody's,
+ *   - mb200_scan / mb200_scan_hist with MB200_SCAN_REDUCE return counts / histograms summed over ranks,
+ *   - mb200_csc_codes_sharded decodes this rank's share of the batches and gathers all records.
+ * NCCL is loaded at run time (libnccl.so.2); without it mb200_comm_init returns MB200_E_COMM.   */
+#define MB200_COMM_ID_BYTES 128
+int32_t mb200_comm_unique_id(uint8_t* id_out /* MB200_COMM_ID_BYTES */);
+int32_t mb200_comm_init(mb200_ctx* ctx, const uint8_t* id, int32_t rank, int32_t world);
+int32_t mb200_comm_destroy(mb200_ctx* ctx);
+int32_t mb200_comm_info(const mb200_ctx* ctx, int32_t* rank, int32_t* world, int32_t* nccl_version);
+/* small host-buffer exchanges for the host loop (epoch seed, stop flag, record counts); blocking, collective */
+int32_t mb200_comm_broadcast(mb200_ctx* ctx, void* host_buf, int64_t bytes, int32_t root);
+int32_t mb200_comm_allreduce_i64(mb200_ctx* ctx, int64_t* host_buf, int64_t n);
+int32_t mb200_comm_allgather(mb200_ctx* ctx, const void* host_send, void* host_recv, int64_t bytes_per_rank);
 
 /* ---- sequences: replaces the one-hot Float32 arrays of loadfasta/fasta.jl:13-22 ------------
  * Sequences are stored 2 bit/base (A=0,C=1,G=2,T=3; same row order as helpers.jl:125-128),
@@ -76,6 +99,31 @@ int32_t mb200_seqs_shape(const mb200_seqs* s, int64_t* N, int64_t* Lb, int64_t* 
 /* copy the packed words back (N * words_per_seq uint32) — used by tests. */
 int32_t mb200_seqs_download(mb200_ctx* ctx, const mb200_seqs* s, uint32_t* out_words, int64_t n_words);
 
+/* ---- FASTA -> reads -> train/test split -> shuffled backgrounds: replaces reading / read_fasta
+ *      (loadfasta/helpers.jl:83-108), get_train_test_inds (:141-159), the seq_shuffle.(...; k) backgrounds and
+ *      est_1st_order_markov_bg of get_data_matrices (:206-245), get_data_bg (MOTIFs.jl:35-39).  The one-hot matrices of
+ *      fasta.jl:61-101 never exist: reads are uploaded once, split / shuffled / counted on the device.               */
+typedef struct mb200_fasta mb200_fasta;
+/* parse a FASTA file on the host: records split at '>', lines after the header joined, reads containing N/n dropped, at most
+ * max_entries kept (< 0: no cap; the reference uses 100 000), reads whose length differs from the first one dropped, upper-cased. */
+int32_t mb200_fasta_read(const char* path, int64_t max_entries, mb200_fasta** out, int64_t* N, int64_t* L);
+int32_t mb200_fasta_rows(const mb200_fasta* f, uint8_t* out_rows /* N*L bytes */);
+int32_t mb200_fasta_free(mb200_fasta* f);
+/* 0-based train / test indices: n_test = floor((1 - ratio) * n); shuffle != 0: randperm, test = sample without replacement,
+ * train = the remaining indices in randperm order; shuffle == 0: test = the last n_test indices.  train_idx / test_idx: room for n. */
+int32_t mb200_fasta_split(int64_t n, double train_test_split_ratio, int32_t shuffle, uint64_t seed,
+                          int64_t* train_idx, int64_t* test_idx, int64_t* n_train, int64_t* n_test);
+/* rows idx[0..n) of src as a new store (device gather) */
+int32_t mb200_seqs_gather(mb200_ctx* ctx, const mb200_seqs* src, const int64_t* idx, int64_t n, mb200_seqs** out);
+/* every sequence shuffled with its k-mer counts preserved exactly (k = 1: uniform permutation; k = 2..4: uniform random Eulerian
+ * walk through the (k-1)-mer graph, sequences up to 65 536 bp; k = 1 also for chromosome-scale sequences).  Sequence i draws from
+ * random stream first_stream + i of `seed`: shards shuffled on different GPUs equal the single-GPU result.          */
+int32_t mb200_seqs_shuffle(mb200_ctx* ctx, const mb200_seqs* src, int32_t k, uint64_t seed, int64_t first_stream, mb200_seqs** out);
+/* base_counts[4]: occurrences of A,C,G,T; transitions[16] (may be NULL): base a followed by base b within a sequence, [a*4+b] */
+int32_t mb200_seqs_base_counts(mb200_ctx* ctx, const mb200_seqs* seqs, int64_t* base_counts, int64_t* transitions);
+/* the stored reads as N rows of Lb ASCII bytes */
+int32_t mb200_seqs_to_ascii(mb200_ctx* ctx, const mb200_seqs* seqs, uint8_t* out_rows);
+
 /* ---- PWM scan: replaces greedy_search! + get_pos_scores_arr + gpu_scan
  *      (inference/_h3_1_alignment.jl:18-36, 57-87, 89-99), the threshold filter
  *      filter_position_by_best_thresh! (_s2_filter_pos_w_scores.jl:116-125) and the occurrence
@@ -94,6 +142,8 @@ typedef struct {
 #define MB200_SCAN_RC           0x2u   /* score with reverse(pwm)        (rc=true pass)       */
 #define MB200_SCAN_WANT_HITS    0x4u
 #define MB200_SCAN_WANT_COUNTS  0x8u
+#define MB200_SCAN_REDUCE       0x20u  /* counts (and mb200_scan_hist's histogram) are summed over the ranks of the ctx's communicator
+                                          before they are returned (one all-reduce per call; hit lists stay per rank)          */
 #define MB200_SCAN_NO_TENSOR    0x10u  /* thresholded scans: keep the SIMT kernel (default: tcgen05 pre-filter + exact re-scoring, same hit sets) */
 
 /* pwms_f16 : Float16 bits, Julia column-major (K,4,maxlen) exactly as built at
@@ -112,6 +162,9 @@ int32_t mb200_scan(mb200_ctx* ctx, const mb200_seqs* seqs,
                    const uint16_t* pwms_f16, const int64_t* lens, int32_t K, int32_t maxlen,
                    const uint16_t* thresh_f16, uint32_t flags,
                    mb200_hit* hits, int64_t hits_cap, int64_t* n_hits, int64_t* counts);
+/* After mb200_scan returned MB200_E_HITS_OVERFLOW (*n_hits = the size needed) the complete list is held by the library: fetch it
+ * here instead of scanning again.  The held list is dropped by the next mb200_scan of the ctx.                        */
+int32_t mb200_scan_take_hits(mb200_ctx* ctx, mb200_hit* hits, int64_t hits_cap, int64_t* n_hits);
 /* which kernel family the last mb200_scan of this ctx used: 0 = scan_kernel (SIMT), 1 = tcgen05 pre-filter + exact re-scoring
  * (thresholded scans, default), 2 = started on the tensor-core path and fell back to scan_kernel (candidate list overflow). */
 int32_t mb200_scan_last_path(const mb200_ctx* ctx);
@@ -160,6 +213,9 @@ int32_t mb200_csc_reset_optimizer(mb200_ctx* ctx, mb200_csc* csc);
 /* device addresses of the parameter and gradient vectors (n_total floats each), so that the host
  * framework can all-reduce gradients in place with one NCCL call per step.                      */
 int32_t mb200_csc_device_ptrs(const mb200_csc* csc, void** params_dev, void** grads_dev);
+/* data-parallel start: rank `root`'s parameters, AdaBelief state and step counter replace every rank's (collective; no-op
+ * without a communicator).                                                                        */
+int32_t mb200_csc_broadcast_params(mb200_ctx* ctx, mb200_csc* csc, int32_t root);
 /* loss and gradient of n_groups batches: seq_idx[n_groups*batch_size] indexes `seqs`.
  * loss_out: n_groups*3 floats {loss, reconstruction term, syntax term}; grads: n_trainable floats,
  * mean over groups (NULL to leave them on the device).                                          */
@@ -170,7 +226,8 @@ int32_t mb200_csc_step_begin(mb200_ctx* ctx, mb200_csc* csc, const mb200_seqs* s
 /* same for a batch handed over as host ASCII rows (n_groups*batch_size rows of Lb bytes): the per-step `S |> gpu` of train.jl:41 */
 int32_t mb200_csc_step_begin_host(mb200_ctx* ctx, mb200_csc* csc, const uint8_t* ascii_rows, int64_t n_rows);
 /* AdaBelief update (Flux.Optimise.AdaBelief defaults eta=1e-3, beta=(0.9,0.999), eps=1e-8) with the
- * gradients on the device; returns the mean loss of that step and l1 = sum|prep_syntax_filters(F)|
+ * gradients on the device — averaged over the ranks of the ctx's communicator first (ONE all-reduce of
+ * n_trainable floats per step) when there is one; returns the mean loss of that step and l1 = sum|prep_syntax_filters(F)|
  * (the early-stop statistic of train.jl:47-52).                                                  */
 int32_t mb200_csc_adabelief_step(mb200_ctx* ctx, mb200_csc* csc, float eta, float beta1, float beta2,
                                  float eps, float* loss_out, float* l1_F_out);
@@ -191,6 +248,13 @@ typedef struct {                 /* stored_code_component_t, inference/_0_const.
  * Records ordered by seq, fil, position.                                                        */
 int32_t mb200_csc_codes(mb200_ctx* ctx, mb200_csc* csc, const mb200_seqs* seqs, int64_t first_seq,
                         int64_t n_seqs, mb200_code* out, int64_t cap, int64_t* n_out);
+
+/* the same, sharded over the ranks of the ctx's communicator (mb200_comm_init): rank r decodes a contiguous range of whole
+ * batches, the records are all-gathered in rank order = ascending sequence order, so every rank receives exactly what a
+ * single-GPU mb200_csc_codes returns.  rank = world = -1 takes them from the communicator; explicit (rank, world) decode just
+ * that shard without any communication.  Every rank must hold the same `seqs`.                                 */
+int32_t mb200_csc_codes_sharded(mb200_ctx* ctx, mb200_csc* csc, const mb200_seqs* seqs, int64_t first_seq, int64_t n_seqs,
+                                int32_t rank, int32_t world, mb200_code* out, int64_t cap, int64_t* n_out);
 
 /* ---- positions -> count matrices: replaces posdicts2countmats / msa_add! (inference/_h6_positions2countmat.jl:7-54),
  *      obtain_count_matrices (_3_make_pfms.jl:28-46) and the counting half of enriched_keys2motifs

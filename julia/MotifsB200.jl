@@ -18,6 +18,7 @@ struct HParams        # mb200_hparams = Hyperparam (model.jl:1-14)
 end
 
 const SCAN_FWD, SCAN_RC, SCAN_WANT_HITS, SCAN_WANT_COUNTS = UInt32(1), UInt32(2), UInt32(4), UInt32(8)
+const SCAN_REDUCE = UInt32(32)         # counts / histograms summed over the ranks of the ctx's communicator inside the call
 const SCAN_NO_TENSOR = UInt32(16)      # thresholded scans: keep the SIMT kernel (default: tcgen05 pre-filter + exact re-scoring, same hit sets)
 scan_last_path(ctx) = ccall((:mb200_scan_last_path, lib), Int32, (Ptr{Cvoid},), ctx)   # 0 SIMT, 1 tensor-core path, 2 fell back
 
@@ -54,20 +55,23 @@ wait_seqs(ctx, s) = check(ctx, ccall((:mb200_seqs_wait, lib), Int32, (Ptr{Cvoid}
 # replaces get_pos_scores_arr + gpu_scan (inference/_h3_1_alignment.jl:57-99).  `pwms` is the (K,4,maxlen) Float16 array the
 # reference builds at :65-69 with rc=false; thresh === nothing gives the reference's "score > 0" scan.
 function gpu_scan(ctx, seqs, pwms::Array{Float16,3}, lens::Vector{Int64}; thresh::Union{Nothing,Vector{Float16}}=nothing,
-                  want_hits=true)
+                  want_hits=true, reduce=false)
     K, _, maxlen = size(pwms)
     counts = zeros(Int64, 4, K)                       # column k = (n_hits, unique starts, union_ranges coverage, true coverage)
     nhits = Ref{Int64}(0)
     flags = SCAN_FWD | SCAN_RC | SCAN_WANT_COUNTS | (want_hits ? SCAN_WANT_HITS : UInt32(0))
     cap = 1 << 16
     hits = Vector{Hit}(undef, want_hits ? cap : 0)
+    thr = thresh === nothing ? Float16[] : thresh      # kept alive (and unmoved) by GC.@preserve below
     while true
-        rc = GC.@preserve pwms lens hits counts ccall((:mb200_scan, lib), Int32,
+        # pointer(hits) is re-evaluated on every iteration: resize! below may move the buffer
+        rc = GC.@preserve pwms lens hits counts thr ccall((:mb200_scan, lib), Int32,
             (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float16}, Ptr{Int64}, Int32, Int32, Ptr{Float16}, UInt32, Ptr{Hit}, Int64, Ref{Int64}, Ptr{Int64}),
-            ctx, seqs, pwms, lens, K, maxlen, thresh === nothing ? C_NULL : pointer(thresh), flags,
-            want_hits ? pointer(hits) : C_NULL, want_hits ? cap : 0, nhits, counts)
-        if rc == -5 && want_hits                      # MB200_E_HITS_OVERFLOW: nhits[] is the exact size
-            cap = nhits[]; resize!(hits, cap); continue
+            ctx, seqs, pwms, lens, K, maxlen, thresh === nothing ? Ptr{Float16}(C_NULL) : pointer(thr), flags | (reduce ? SCAN_REDUCE : UInt32(0)),
+            want_hits ? pointer(hits) : Ptr{Hit}(C_NULL), want_hits ? cap : 0, nhits, counts)
+        if rc == -5 && want_hits                      # MB200_E_HITS_OVERFLOW: the library holds the complete list, nhits[] is its size
+            resize!(hits, nhits[])
+            rc = GC.@preserve hits ccall((:mb200_scan_take_hits, lib), Int32, (Ptr{Cvoid}, Ptr{Hit}, Int64, Ref{Int64}), ctx, hits, length(hits), nhits)
         end
         check(ctx, rc); break
     end
@@ -170,6 +174,131 @@ function pvalue2score(pwm::AbstractMatrix, pval::Real, eps::Real=1e-1; bg=[.25, 
         C_NULL, rowmajor, size(pwm, 2), pval, eps, bg64, score, found)
     rc == 0 || error("mb200_pvalue2score failed ($rc)")
     return found[] == 0 ? nothing : score[]
+end
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# multi-GPU: one Julia process per GPU (Distributed / MPI / plain `julia -p`), one NCCL communicator per ctx (csrc/comm.cu).
+# Rank 0 makes the id, the host ships the 128 bytes by its own means (e.g. `remotecall_fetch`), every rank calls comm_init.
+# After that train_step! averages the gradients over ranks inside mb200_csc_adabelief_step, gpu_scan(...; reduce=true) and
+# scan_hist(...; reduce=true) return sums over ranks, and code_retrieval(...; sharded=true) decodes 1/world of the batches per rank.
+# ------------------------------------------------------------------------------------------------------------------------------
+function comm_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    rc = GC.@preserve id ccall((:mb200_comm_unique_id, lib), Int32, (Ptr{UInt8},), id)
+    rc == 0 || error("mb200_comm_unique_id failed ($rc): libnccl.so.2 not loadable")
+    id
+end
+comm_init(ctx, id::Vector{UInt8}, rank::Integer, world::Integer) = GC.@preserve id check(ctx, ccall((:mb200_comm_init, lib), Int32,
+    (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32), ctx, id, rank, world))
+comm_destroy(ctx) = check(ctx, ccall((:mb200_comm_destroy, lib), Int32, (Ptr{Cvoid},), ctx))
+function comm_info(ctx)
+    r = Ref{Int32}(0); w = Ref{Int32}(1); v = Ref{Int32}(0)
+    check(ctx, ccall((:mb200_comm_info, lib), Int32, (Ptr{Cvoid}, Ref{Int32}, Ref{Int32}, Ref{Int32}), ctx, r, w, v))
+    (rank = Int(r[]), world = Int(w[]), nccl_version = Int(v[]))
+end
+# in-place broadcast of a bits-type array from `root` (epoch permutation seed, stop flag)
+comm_broadcast!(ctx, a::Array, root::Integer=0) = (GC.@preserve a check(ctx, ccall((:mb200_comm_broadcast, lib), Int32,
+    (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32), ctx, a, sizeof(a), root)); a)
+comm_allreduce!(ctx, a::Vector{Int64}) = (GC.@preserve a check(ctx, ccall((:mb200_comm_allreduce_i64, lib), Int32,
+    (Ptr{Cvoid}, Ptr{Int64}, Int64), ctx, a, length(a))); a)
+# start of data-parallel training: rank `root`'s weights and optimiser state become everybody's
+csc_broadcast_params(ctx, m, root::Integer=0) = check(ctx, ccall((:mb200_csc_broadcast_params, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32), ctx, m, root))
+# device addresses of the parameter / gradient vectors (for hosts that bring their own collective, e.g. NCCL.jl)
+function csc_device_ptrs(m)
+    p = Ref{Ptr{Cvoid}}(C_NULL); g = Ref{Ptr{Cvoid}}(C_NULL)
+    ccall((:mb200_csc_device_ptrs, lib), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Ref{Ptr{Cvoid}}), m, p, g) == 0 || error("mb200_csc_device_ptrs")
+    p[], g[]
+end
+# the per-step `S |> gpu` of train.jl:41 for hosts that keep the reads on the CPU: batch as L x 6 ASCII bytes (one column per read)
+function train_step_host!(ctx, m, ascii_batch::Matrix{UInt8}; eta=1f-3, beta=(0.9f0, 0.999f0), eps=1f-8)
+    GC.@preserve ascii_batch check(ctx, ccall((:mb200_csc_step_begin_host, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{UInt8}, Int64),
+                                              ctx, m, ascii_batch, size(ascii_batch, 2)))
+    loss = Ref{Float32}(0); l1 = Ref{Float32}(0)
+    check(ctx, ccall((:mb200_csc_adabelief_step, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Float32, Float32, Float32, Float32, Ref{Float32}, Ref{Float32}),
+                     ctx, m, eta, beta[1], beta[2], eps, loss, l1))
+    loss[], l1[]
+end
+# code_retrieval sharded over the communicator's ranks (every rank gets all records, ordered by seq like the single-GPU call)
+function code_retrieval_sharded(ctx, m, seqs, N::Integer, batch_size::Integer)
+    n = N - N % batch_size
+    cap = 64 * n; out = Vector{Code}(undef, cap); cnt = Ref{Int64}(0)
+    GC.@preserve out check(ctx, ccall((:mb200_csc_codes_sharded, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int32, Int32, Ptr{Code}, Int64, Ref{Int64}), ctx, m, seqs, 0, n, -1, -1, out, cap, cnt))
+    [(position=c.position + 0x0001, fil=c.fil + 0x0001, seq=c.seq + 0x00000001, mag=c.mag) for c in view(out, 1:cnt[])]
+end
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# seam S4 (SURVEY §8b): thresholds, filter, counts, Fisher without hit dictionaries
+# ------------------------------------------------------------------------------------------------------------------------------
+# (32768, K) histogram of the Float16 bit patterns of all hit scores (score > 0, both strands): the input of get_max_score /
+# get_min_score / the sweep of get_best_thresh (inference/_s2_filter_pos_w_scores.jl:11-36, 99-113)
+function scan_hist(ctx, seqs, pwms::Array{Float16,3}, lens::Vector{Int64}; reduce=false)
+    K, _, maxlen = size(pwms)
+    hist = zeros(UInt32, 32768, K)
+    GC.@preserve pwms lens hist check(ctx, ccall((:mb200_scan_hist, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float16}, Ptr{Int64}, Int32, Int32, UInt32, Ptr{UInt32}),
+        ctx, seqs, pwms, lens, K, maxlen, SCAN_FWD | SCAN_RC | (reduce ? SCAN_REDUCE : UInt32(0)), hist))
+    hist
+end
+# fused scan + filter_position_by_best_thresh! + get_uniq_counts + union_ranges coverage: (4, K) Int64, rows = hits, unique starts,
+# coverage as the reference computes it (_h4_overlap_ratio.jl:48-56), true coverage
+scan_counts(ctx, seqs, pwms, lens, thresh::Vector{Float16}; reduce=false) =
+    gpu_scan(ctx, seqs, pwms, lens; thresh=thresh, want_hits=false, reduce=reduce)[4]
+
+# get_best_thresh (_s2:90-114) from the two histograms.  `fisher(a, b)` is the host's right-tail test, e.g.
+#   (a, b) -> pvalue(FisherExactTest(a, asum - a, b, asum - b), tail=:right)        (HypothesisTests, as in the reference)
+function best_thresh_from_hist(h_fg::AbstractVector{UInt32}, h_bg::AbstractVector{UInt32}, eff_pos, pwm, bg, fisher;
+                               touzet_len=15, increment=Float16(0.5), pvalue_of=n -> (n <= 11 ? (n <= 9 ? 3e-4 : 1e-4) : 1e-4))
+    if any(length(r) < touzet_len for r in eff_pos)
+        best = 0.0
+        for r in eff_pos
+            (length(r) > touzet_len || length(r) <= 1) && continue
+            sub = view(pwm, :, r)
+            best += pvalue2score(sub, pvalue_of(size(sub, 2)); bg=bg)
+        end
+        return Float16(best)
+    end
+    nz = findall(i -> h_fg[i] + h_bg[i] > 0, 1:0x7C01)                 # positive finite halves and +Inf, ascending in value
+    isempty(nz) && return Float16(Inf)
+    min_score = reinterpret(Float16, UInt16(nz[1] - 1)); max_score = reinterpret(Float16, UInt16(nz[end] - 1))
+    tail_fg = reverse(cumsum(reverse(Int64.(h_fg)))); tail_bg = reverse(cumsum(reverse(Int64.(h_bg))))    # tail[b+1] = hits with pattern >= b
+    best_thresh, t, best_p = min_score, min_score, 1.0
+    while t < max_score
+        b = Int(reinterpret(UInt16, t))
+        a_, b_ = b + 2 <= 32768 ? tail_fg[b + 2] : 0, b + 2 <= 32768 ? tail_bg[b + 2] : 0      # scores strictly greater than t
+        p = fisher(a_, b_)
+        if p < best_p; best_p = p; best_thresh = t; end
+        t = Float16(t + increment)
+    end
+    best_thresh
+end
+
+# body of filter_positions_scores_usecomp!(ms, data, bg) (_s2_filter_pos_w_scores.jl:127-138) on the library: two histogram scans
+# give ms.score_thresh, two fused counting scans give the filtered occurrence counts (fg, bg) — no positions/scores dictionaries.
+function filter_positions_scores_usecomp!(ctx, ms, seqs_fg, seqs_bg, pwms, NL::Integer, bg, fisher)
+    h_fg = scan_hist(ctx, seqs_fg, pwms, ms.lens); h_bg = scan_hist(ctx, seqs_bg, pwms, ms.lens)
+    ms.score_thresh = [best_thresh_from_hist(view(h_fg, :, k), view(h_bg, :, k), ms.effective_segments[k], ms.pwms[k], bg,
+                                             (a, b) -> fisher(a, NL - a, b, NL - b)) for k in 1:length(ms.lens)]
+    scan_counts(ctx, seqs_fg, pwms, ms.lens, ms.score_thresh), scan_counts(ctx, seqs_bg, pwms, ms.lens, ms.score_thresh)
+end
+
+# body of pvec_from_test_data(ms, data) (render/pvec_calculations.jl:1-22): test-set scans filtered by ms.score_thresh, union
+# coverage (row 3), Fisher; returns (pvec, uniq_active_counts_test)
+function pvec_from_test_data(ctx, ms, seqs_test, seqs_bg_test, pwms, NL_test::Integer, fisher)
+    c = scan_counts(ctx, seqs_test, pwms, ms.lens, ms.score_thresh); cb = scan_counts(ctx, seqs_bg_test, pwms, ms.lens, ms.score_thresh)
+    pvec = [(c[3, k] == 0 && cb[3, k] == 0) ? 1.0 : fisher(c[3, k], NL_test - c[3, k], cb[3, k], NL_test - cb[3, k]) for k in 1:length(ms.lens)]
+    pvec, Float64.(c[2, :])
+end
+
+# positions -> count matrices: posdicts2countmats / msa_add! (inference/_h6_positions2countmat.jl:7-54).  sites: 0-based
+# (motif, seq, pos, comp) rows; returns Vector of 4 x len_k UInt32 matrices (add the 0.01 pseudo-count and convert on the host).
+struct Site; motif::UInt32; seq::UInt32; pos::UInt32; comp::UInt32; end
+function count_matrices(ctx, seqs, sites::Vector{Site}, lens::Vector{Int64})
+    K = length(lens); maxlen = Int(maximum(lens))
+    counts = zeros(UInt32, 4, maxlen, K)                               # C side: [(k*maxlen + col)*4 + base]
+    GC.@preserve sites lens counts check(ctx, ccall((:mb200_count_matrices, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Site}, Int64, Ptr{Int64}, Int32, Int32, Ptr{UInt32}), ctx, seqs, sites, length(sites), lens, K, maxlen, counts))
+    [counts[:, 1:lens[k], k] for k in 1:K]
 end
 
 end # module

@@ -24,8 +24,9 @@ class MB200Error(RuntimeError):
         self.code = code
 
 
-OK, E_INVALID, E_CUDA, E_NOMEM, E_BAD_SEQUENCE, E_HITS_OVERFLOW, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
-SCAN_FWD, SCAN_RC, SCAN_WANT_HITS, SCAN_WANT_COUNTS, SCAN_NO_TENSOR = 1, 2, 4, 8, 16
+OK, E_INVALID, E_CUDA, E_NOMEM, E_BAD_SEQUENCE, E_HITS_OVERFLOW, E_UNSUPPORTED, E_COMM = 0, -1, -2, -3, -4, -5, -6, -7
+SCAN_FWD, SCAN_RC, SCAN_WANT_HITS, SCAN_WANT_COUNTS, SCAN_NO_TENSOR, SCAN_REDUCE = 1, 2, 4, 8, 16, 32
+COMM_ID_BYTES = 128
 MAX_MOTIF_LEN = 64
 
 HIT_DTYPE = np.dtype([("seq", "<u4"), ("pos", "<u4"), ("motif", "<u2"), ("score_f16", "<u2"),
@@ -67,6 +68,13 @@ def load():
         "mb200_last_error": (C.c_char_p, [p]),
         "mb200_set_stream": (i32, [p, p]),
         "mb200_last_timing": (i32, [p, p, p]),
+        "mb200_comm_unique_id": (i32, [p]),
+        "mb200_comm_init": (i32, [p, p, i32, i32]),
+        "mb200_comm_destroy": (i32, [p]),
+        "mb200_comm_info": (i32, [p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+        "mb200_comm_broadcast": (i32, [p, p, i64, i32]),
+        "mb200_comm_allreduce_i64": (i32, [p, p, i64]),
+        "mb200_comm_allgather": (i32, [p, p, p, i64]),
         "mb200_seqs_from_ascii": (i32, [p, p, i64, i64, C.POINTER(p)]),
         "mb200_seqs_from_ascii_async": (i32, [p, p, i64, i64, C.POINTER(p)]),
         "mb200_seqs_wait": (i32, [p, p]),
@@ -75,7 +83,16 @@ def load():
         "mb200_seqs_free": (i32, [p, p]),
         "mb200_seqs_shape": (i32, [p, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
         "mb200_seqs_download": (i32, [p, p, p, i64]),
+        "mb200_fasta_read": (i32, [C.c_char_p, i64, C.POINTER(p), C.POINTER(i64), C.POINTER(i64)]),
+        "mb200_fasta_rows": (i32, [p, p]),
+        "mb200_fasta_free": (i32, [p]),
+        "mb200_fasta_split": (i32, [i64, C.c_double, i32, C.c_uint64, p, p, C.POINTER(i64), C.POINTER(i64)]),
+        "mb200_seqs_gather": (i32, [p, p, p, i64, C.POINTER(p)]),
+        "mb200_seqs_shuffle": (i32, [p, p, i32, C.c_uint64, i64, C.POINTER(p)]),
+        "mb200_seqs_base_counts": (i32, [p, p, p, p]),
+        "mb200_seqs_to_ascii": (i32, [p, p, p]),
         "mb200_scan": (i32, [p, p, p, p, i32, i32, p, C.c_uint32, p, i64, C.POINTER(i64), p]),
+        "mb200_scan_take_hits": (i32, [p, p, i64, C.POINTER(i64)]),
         "mb200_scan_last_path": (i32, [p]),
         "mb200_scan_prefilter_bound": (i32, [p, i32, C.c_uint16, p, p, p, p]),
         "mb200_scan_hist": (i32, [p, p, p, p, i32, i32, C.c_uint32, p]),
@@ -86,6 +103,8 @@ def load():
         "mb200_csc_get_params": (i32, [p, p, p, i64]),
         "mb200_csc_reset_optimizer": (i32, [p, p]),
         "mb200_csc_device_ptrs": (i32, [p, C.POINTER(p), C.POINTER(p)]),
+        "mb200_csc_broadcast_params": (i32, [p, p, i32]),
+        "mb200_csc_codes_sharded": (i32, [p, p, p, i64, i64, i32, i32, p, i64, C.POINTER(i64)]),
         "mb200_csc_loss_grad": (i32, [p, p, p, p, p, p]),
         "mb200_csc_step_begin": (i32, [p, p, p, p]),
         "mb200_csc_step_begin_host": (i32, [p, p, p, i64]),
@@ -149,6 +168,54 @@ class Context:
         names = ["pack", "scan", "count", "emit", "csc", "h2d", "d2h", "total"]
         return {k: float(v) for k, v in zip(names, ms)}, {k: int(v) for k, v in zip(names, n)}
 
+    # ---- multi-GPU (csrc/comm.cu): one NCCL communicator per ctx, created from a 128-byte id that rank 0 hands out --------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * COMM_ID_BYTES)()
+        rc = load().mb200_comm_unique_id(buf)
+        if rc != OK:
+            raise MB200Error(rc, "mb200_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        if len(unique_id) != COMM_ID_BYTES:
+            raise ValueError("unique_id must be 128 bytes (mb200_comm_unique_id)")
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        self._check(self._lib.mb200_comm_init(self._h, buf, int(rank), int(world)))
+
+    def comm_destroy(self):
+        self._check(self._lib.mb200_comm_destroy(self._h))
+
+    def comm_info(self):
+        r, w, v = C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(self._lib.mb200_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v)))
+        return r.value, w.value, v.value
+
+    @property
+    def rank(self):
+        return self.comm_info()[0]
+
+    @property
+    def world(self):
+        return self.comm_info()[1]
+
+    def comm_broadcast(self, arr: np.ndarray, root: int = 0) -> np.ndarray:
+        """in-place broadcast of a contiguous numpy array from `root` (blocking, collective)."""
+        assert arr.flags.c_contiguous
+        self._check(self._lib.mb200_comm_broadcast(self._h, _ptr(arr), arr.nbytes, int(root)))
+        return arr
+
+    def comm_allreduce_i64(self, arr: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(arr, np.int64)
+        self._check(self._lib.mb200_comm_allreduce_i64(self._h, _ptr(a), a.size))
+        return a
+
+    def comm_allgather(self, arr: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(arr)
+        out = np.zeros((self.world,) + a.shape, a.dtype)
+        self._check(self._lib.mb200_comm_allgather(self._h, _ptr(a), _ptr(out), a.nbytes))
+        return out
+
     # ---- sequences ---------------------------------------------------------------------------
     def seqs_from_ascii(self, ascii_rows: np.ndarray) -> "Sequences":
         a = np.ascontiguousarray(ascii_rows, dtype=np.uint8)
@@ -185,10 +252,11 @@ class Context:
 
     # ---- scan --------------------------------------------------------------------------------
     def scan(self, seqs: "Sequences", pwms_f16: np.ndarray, lens, thresh_f16=None, *, fwd=True, rc=True,
-             want_hits=True, want_counts=True, hits_cap=None, tensor=True):
+             want_hits=True, want_counts=True, hits_cap=None, tensor=True, reduce=False):
         """pwms_f16: (K, 4, maxlen) array in Julia memory order, i.e. numpy shape (maxlen, 4, K) C-order
         holding float16 (or uint16 bits).  Returns (hits structured array | None, counts (K,4) int64 | None).
-        tensor=False keeps a thresholded scan on the SIMT kernel (MB200_SCAN_NO_TENSOR); results are identical either way."""
+        tensor=False keeps a thresholded scan on the SIMT kernel (MB200_SCAN_NO_TENSOR); results are identical either way.
+        reduce=True: counts are summed over the ranks of the ctx's communicator inside the call (MB200_SCAN_REDUCE)."""
         pw = np.ascontiguousarray(pwms_f16)
         if pw.dtype == np.float16:
             pw = pw.view(np.uint16)
@@ -206,21 +274,45 @@ class Context:
             if th.dtype != np.uint16 or th.shape != (K,):
                 raise ValueError("thresh_f16 must be K float16/uint16 values")
         flags = (SCAN_FWD if fwd else 0) | (SCAN_RC if rc else 0) | (SCAN_WANT_HITS if want_hits else 0) | \
-                (SCAN_WANT_COUNTS if want_counts else 0) | (0 if tensor else SCAN_NO_TENSOR)
+                (SCAN_WANT_COUNTS if want_counts else 0) | (0 if tensor else SCAN_NO_TENSOR) | (SCAN_REDUCE if reduce else 0)
         counts = np.zeros((K, 4), np.int64) if want_counts else None
         n_hits = C.c_int64(0)
         cap = int(hits_cap) if hits_cap is not None else (1 << 16)
-        while True:
-            hits = np.zeros(cap if want_hits else 0, HIT_DTYPE)
-            rc_ = self._lib.mb200_scan(self._h, seqs._h, _ptr(pw), _ptr(ln), K, maxlen, _ptr(th), flags,
-                                       _ptr(hits) if want_hits else None, cap if want_hits else 0,
-                                       C.byref(n_hits), _ptr(counts))
-            if rc_ == E_HITS_OVERFLOW and hits_cap is None:
-                cap = int(n_hits.value)          # exact size reported by the library; retry once
-                continue
-            self._check(rc_)
-            break
+        hits = np.zeros(cap if want_hits else 0, HIT_DTYPE)
+        rc_ = self._lib.mb200_scan(self._h, seqs._h, _ptr(pw), _ptr(ln), K, maxlen, _ptr(th), flags,
+                                   _ptr(hits) if want_hits else None, cap if want_hits else 0,
+                                   C.byref(n_hits), _ptr(counts))
+        if rc_ == E_HITS_OVERFLOW and hits_cap is None:
+            # the library kept the complete list: fetch it instead of scanning again (counts are already final)
+            hits = np.zeros(int(n_hits.value), HIT_DTYPE)
+            rc_ = self._lib.mb200_scan_take_hits(self._h, _ptr(hits), len(hits), C.byref(n_hits))
+        self._check(rc_)
         return (hits[: n_hits.value] if want_hits else None), counts
+
+
+def fasta_read(path: str, max_entries: int = 100000) -> np.ndarray:
+    """mb200_fasta_read: (N, L) uint8 matrix of the reads the reference's read_fasta keeps (helpers.jl:83-108)."""
+    h, n, l = C.c_void_p(), C.c_int64(), C.c_int64()
+    rc = load().mb200_fasta_read(os.fsencode(path), int(max_entries), C.byref(h), C.byref(n), C.byref(l))
+    if rc != OK:
+        raise MB200Error(rc, f"mb200_fasta_read({path}) failed")
+    out = np.zeros((n.value, l.value), np.uint8)
+    try:
+        if out.size:
+            load().mb200_fasta_rows(h, _ptr(out))
+    finally:
+        load().mb200_fasta_free(h)
+    return out
+
+
+def fasta_split(n: int, ratio: float, shuffle: bool, seed: int):
+    """mb200_fasta_split: 0-based (train_idx, test_idx) following get_train_test_inds (helpers.jl:141-159)."""
+    tr, te = np.zeros(max(n, 1), np.int64), np.zeros(max(n, 1), np.int64)
+    ntr, nte = C.c_int64(), C.c_int64()
+    rc = load().mb200_fasta_split(int(n), float(ratio), int(bool(shuffle)), C.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(tr), _ptr(te), C.byref(ntr), C.byref(nte))
+    if rc != OK:
+        raise MB200Error(rc, "mb200_fasta_split failed")
+    return tr[: ntr.value].copy(), te[: nte.value].copy()
 
 
 def scan_last_path(ctx: "Context") -> int:
@@ -250,7 +342,7 @@ def count_matrices(ctx: "Context", seqs: "Sequences", sites, lens):
     return [out[k, : ln[k]].T.copy() for k in range(K)]
 
 
-def scan_hist(ctx: "Context", seqs: "Sequences", pwms_f16, lens, fwd=True, rc=True):
+def scan_hist(ctx: "Context", seqs: "Sequences", pwms_f16, lens, fwd=True, rc=True, reduce=False):
     """(K, 32768) uint32 histogram of the Float16 bit patterns of all hit scores (score > 0)."""
     pw = np.ascontiguousarray(pwms_f16)
     if pw.dtype == np.float16:
@@ -258,7 +350,7 @@ def scan_hist(ctx: "Context", seqs: "Sequences", pwms_f16, lens, fwd=True, rc=Tr
     maxlen, _, K = pw.shape
     ln = np.ascontiguousarray(lens, dtype=np.int64)
     out = np.zeros((K, 32768), np.uint32)
-    flags = (SCAN_FWD if fwd else 0) | (SCAN_RC if rc else 0)
+    flags = (SCAN_FWD if fwd else 0) | (SCAN_RC if rc else 0) | (SCAN_REDUCE if reduce else 0)
     ctx._check(ctx._lib.mb200_scan_hist(ctx._h, seqs._h, _ptr(pw), _ptr(ln), K, maxlen, flags, _ptr(out)))
     return out
 
@@ -276,6 +368,30 @@ class Sequences:
     def download(self) -> np.ndarray:
         out = np.zeros((self.N, self.words_per_seq), np.uint32)
         self.ctx._check(self.ctx._lib.mb200_seqs_download(self.ctx._h, self._h, _ptr(out), out.size))
+        return out
+
+    def gather(self, idx) -> "Sequences":
+        """rows idx of this store as a new store (device gather)."""
+        i = np.ascontiguousarray(idx, np.int64)
+        h = C.c_void_p()
+        self.ctx._check(self.ctx._lib.mb200_seqs_gather(self.ctx._h, self._h, _ptr(i), len(i), C.byref(h)))
+        return Sequences(self.ctx, h, len(i), self.Lb)
+
+    def shuffle(self, k: int, seed: int, first_stream: int = 0) -> "Sequences":
+        """seq_shuffle.(reads; k): k-mer-count-preserving shuffle of every sequence on the device, from a host seed."""
+        h = C.c_void_p()
+        self.ctx._check(self.ctx._lib.mb200_seqs_shuffle(self.ctx._h, self._h, int(k), C.c_uint64(int(seed) & (2 ** 64 - 1)), int(first_stream), C.byref(h)))
+        return Sequences(self.ctx, h, self.N, self.Lb)
+
+    def base_counts(self):
+        """(counts[4] of A,C,G,T, transitions[4,4] base a -> base b) as int64."""
+        c, t = np.zeros(4, np.int64), np.zeros((4, 4), np.int64)
+        self.ctx._check(self.ctx._lib.mb200_seqs_base_counts(self.ctx._h, self._h, _ptr(c), _ptr(t)))
+        return c, t
+
+    def to_ascii(self) -> np.ndarray:
+        out = np.zeros((self.N, self.Lb), np.uint8)
+        self.ctx._check(self.ctx._lib.mb200_seqs_to_ascii(self.ctx._h, self._h, _ptr(out)))
         return out
 
     def wait(self):
@@ -341,6 +457,10 @@ class CscModel:
         self.ctx._check(self.ctx._lib.mb200_csc_device_ptrs(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def broadcast_params(self, root: int = 0):
+        """rank `root`'s parameters + AdaBelief state become every rank's (collective; no-op without a communicator)."""
+        self.ctx._check(self.ctx._lib.mb200_csc_broadcast_params(self.ctx._h, self._h, int(root)))
+
     def loss_grad(self, seqs: "Sequences", seq_idx, want_grads=True):
         idx = np.ascontiguousarray(seq_idx, np.int64)
         if idx.size != self.batch:
@@ -386,14 +506,22 @@ class CscModel:
         self.ctx._check(self.ctx._lib.mb200_csc_median_mask(self.ctx._h, self._h, _ptr(z), _ptr(y), _ptr(zy), _ptr(med)))
         return zy, med
 
-    def codes(self, seqs: "Sequences", first_seq=0, n_seqs=None):
+    def codes(self, seqs: "Sequences", first_seq=0, n_seqs=None, shard=None):
+        """shard=None: this GPU decodes everything.  shard="comm": the ranks of the ctx's communicator each decode a contiguous
+        range of whole batches and all-gather the records (every rank returns the full result).  shard=(rank, world): only that
+        shard, no communication."""
         B = self.hp.batch_size
         if n_seqs is None:
             n_seqs = (seqs.N - first_seq) - (seqs.N - first_seq) % B          # DataLoader(partial=false)
         cap = max(1024, 64 * int(n_seqs))
         out = np.zeros(cap, CODE_DTYPE)
         n = C.c_int64()
-        self.ctx._check(self.ctx._lib.mb200_csc_codes(self.ctx._h, self._h, seqs._h, int(first_seq), int(n_seqs), _ptr(out), cap, C.byref(n)))
+        if shard is None:
+            self.ctx._check(self.ctx._lib.mb200_csc_codes(self.ctx._h, self._h, seqs._h, int(first_seq), int(n_seqs), _ptr(out), cap, C.byref(n)))
+        else:
+            r, w = (-1, -1) if shard == "comm" else shard
+            self.ctx._check(self.ctx._lib.mb200_csc_codes_sharded(self.ctx._h, self._h, seqs._h, int(first_seq), int(n_seqs), int(r), int(w),
+                                                                   _ptr(out), cap, C.byref(n)))
         return out[: n.value]
 
 

@@ -33,6 +33,9 @@ struct mb200_ctx {
     std::vector<std::pair<void*, size_t>> pool; size_t pool_bytes = 0;
     std::vector<int32_t> tc_cost_sig; std::vector<double> tc_cost;   // tensor-core scan: measured clocks per tile of the last block structure
     size_t mask_clean_bytes = 0;              // leading bytes of bufs[2] (hit masks) known to be zero (tensor-core scan path)
+    // multi-GPU (csrc/comm.cu): one NCCL communicator per ctx, created by mb200_comm_init; world == 1 without one
+    void* comm = nullptr; int rank = 0, world = 1;
+    std::vector<mb200_hit> held_hits;         // hit list of a scan whose caller buffer was too small (mb200_scan_take_hits)
 };
 
 struct mb200_seqs {
@@ -49,6 +52,7 @@ struct mb200_seqs {
 };
 int mb_seqs_finish(mb200_ctx* ctx, mb200_seqs* s);      // waits for a pending upload, frees its staging; MB200_E_BAD_SEQUENCE if a symbol was not A,C,G,T
 static const int64_t SEQ_PAD_WORDS = 64;
+int mb_seqs_alloc(mb200_ctx* ctx, int64_t N, int64_t Lb, mb200_seqs** out);   // empty store (tail pad zeroed on ctx->stream)
 
 #define MB_FAIL(ctx, code, ...) do { char _b[512]; snprintf(_b, sizeof _b, __VA_ARGS__); \
     if (ctx) (ctx)->err = _b; return (code); } while (0)
@@ -84,4 +88,10 @@ int mb_ensure_pinned(mb200_ctx* ctx, size_t bytes);
 int mb_ensure_buf(mb200_ctx* ctx, int slot, size_t bytes);
 void* mb_pool_alloc(mb200_ctx* ctx, size_t bytes, size_t* got);   // nullptr when out of memory; *got = size of the block handed out
 void mb_pool_free(mb200_ctx* ctx, void* p, size_t bytes);        // ctx may be NULL (plain cudaFree)
+// collectives on device buffers, enqueued on ctx->stream; no-ops without a communicator (csrc/comm.cu)
+int mb_comm_allreduce_f32(mb200_ctx* ctx, float* buf, size_t n, bool average);
+int mb_comm_allreduce_u64(mb200_ctx* ctx, unsigned long long* buf, size_t n);
+int mb_comm_allreduce_u32(mb200_ctx* ctx, unsigned int* buf, size_t n);
+int mb_comm_broadcast_bytes(mb200_ctx* ctx, void* buf, size_t bytes, int root);
+int mb_comm_allgather_bytes(mb200_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank);
 static inline void mb_reset_timing(mb200_ctx* ctx) { for (int i = 0; i < T_N; ++i) { ctx->ms[i] = 0; ctx->launches[i] = 0; } }

@@ -138,7 +138,7 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         s->segs.nseg = 8;
     }
     s->Deff = B.alloc(nD, "D0"); s->Feff = B.alloc(nF, "F0"); s->Fnrm0 = B.alloc(d.K);
-    s->loss = B.alloc((size_t)d.G * 3 + 4, "loss");
+    s->loss = B.alloc((size_t)d.G * 3 + 4 + d.K, "loss");       // per-group {loss, rec, syn}, then the K per-filter terms of l1(F)
     mb200_csc* S = s;
     auto& T = s->tape;
     T.clear();
@@ -492,7 +492,7 @@ static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
         for (int i = 0; i < s->d.NS; ++i) id[i] = i;
         MB_CUDA(ctx, cudaMemcpy(s->idx_identity_dev, id.data(), (size_t)s->d.NS * 8, cudaMemcpyHostToDevice));
     }
-    MB_CUDA(ctx, cudaMallocHost(&s->host_out, ((size_t)s->d.G * 3 + 8) * 4));
+    MB_CUDA(ctx, cudaMallocHost(&s->host_out, ((size_t)s->d.G * 3 + 8 + s->d.K) * 4));
     return MB200_OK;
 }
 
@@ -573,6 +573,22 @@ extern "C" int32_t mb200_csc_reset_optimizer(mb200_ctx* ctx, mb200_csc* s) {
     MB_CUDA(ctx, cudaMemsetAsync(s->mt, 0, (size_t)s->n_total * 4, ctx->stream));
     MB_CUDA(ctx, cudaMemsetAsync(s->st, 0, (size_t)s->n_total * 4, ctx->stream));
     s->step_count = 0;
+    return MB200_OK;
+}
+
+// rank `root`'s parameters, AdaBelief moments and step counter become everybody's (start of data-parallel training: replicas
+// that were initialised from different random streams would otherwise apply the averaged gradients to different weights)
+extern "C" int32_t mb200_csc_broadcast_params(mb200_ctx* ctx, mb200_csc* s, int32_t root) {
+    if (!ctx || !s) return MB200_E_INVALID;
+    if (!ctx->comm || ctx->world == 1) return MB200_OK;
+    if (root < 0 || root >= ctx->world) MB_FAIL(ctx, MB200_E_INVALID, "csc_broadcast_params: root %d of %d", root, ctx->world);
+    MB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = mb_comm_broadcast_bytes(ctx, s->p_raw, (size_t)s->n_total * 4, root); if (rc) return rc;
+    rc = mb_comm_broadcast_bytes(ctx, s->mt, (size_t)s->n_total * 4, root); if (rc) return rc;
+    rc = mb_comm_broadcast_bytes(ctx, s->st, (size_t)s->n_total * 4, root); if (rc) return rc;
+    int64_t sc = s->step_count;
+    rc = mb200_comm_broadcast(ctx, &sc, 8, root); if (rc) return rc;      // blocking: also drains the three broadcasts above
+    s->step_count = sc;
     return MB200_OK;
 }
 
@@ -711,17 +727,20 @@ extern "C" int32_t mb200_csc_adabelief_step(mb200_ctx* ctx, mb200_csc* s, float 
                                             float* loss_out, float* l1_F_out) {
     if (!ctx || !s) return MB200_E_INVALID;
     MB_CUDA(ctx, cudaSetDevice(ctx->device));
+    // data parallel: ONE all-reduce (average) of the n_train gradients per step, on the stream the reverse pass ran on
+    { const int rc = mb_comm_allreduce_f32(ctx, s->g_raw, (size_t)s->n_train, true); if (rc) return rc; }
     s->step_count += 1;
     const float c1 = 1.f - powf(beta1, (float)s->step_count), c2 = 1.f - powf(beta2, (float)s->step_count);
     lk(k_adabelief, nblk(s->n_train, 256), 256, 0, ctx->stream, s->p_raw, s->g_raw, s->mt, s->st, eta, beta1, beta2, eps * eps, c1, c2, (int)s->n_train);
-    float* d_l1 = s->data + s->loss.off + (size_t)s->d.G * 3;       // slot right after the per-group losses
-    MB_CUDA(ctx, cudaMemsetAsync(d_l1, 0, 4, ctx->stream));
+    // l1(F): one term per syntax filter, summed on the host in a fixed order — bit-identical on every rank, so that all ranks of a
+    // data-parallel run take the early-stop branch (train.jl:47-52) on the same step
+    float* d_l1 = s->data + s->loss.off + (size_t)s->d.G * 3;       // K slots right after the per-group losses
     lk(k_l1_F, s->d.K, 256, 0, ctx->stream, s->p_raw + s->off_F, d_l1, s->d);
     ctx->launches[T_CSC] += 2;
-    MB_CUDA(ctx, cudaMemcpyAsync(s->host_out, s->data + s->loss.off, ((size_t)s->d.G * 3 + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(ctx, cudaMemcpyAsync(s->host_out, s->data + s->loss.off, ((size_t)s->d.G * 3 + s->d.K) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (loss_out) { float m = 0.f; for (int g = 0; g < s->d.G; ++g) m += s->host_out[g * 3]; *loss_out = m / (float)s->d.G; }
-    if (l1_F_out) *l1_F_out = s->host_out[(size_t)s->d.G * 3];
+    if (l1_F_out) { float l1 = 0.f; for (int k = 0; k < s->d.K; ++k) l1 += s->host_out[(size_t)s->d.G * 3 + k]; *l1_F_out = l1; }
     return MB200_OK;
 }
 
@@ -797,8 +816,9 @@ __global__ void __launch_bounds__(128) k_emit_codes(const float* __restrict__ x,
     if (lane == 0) counts[n] = cnt;
 }
 
-extern "C" int32_t mb200_csc_codes(mb200_ctx* ctx, mb200_csc* s, const mb200_seqs* seqs, int64_t first_seq, int64_t n_seqs,
-                                   mb200_code* out, int64_t cap, int64_t* n_out) {
+// decodes [first_seq, first_seq + n_seqs); records go to `out` (up to cap) and, when given, are appended to `vec`
+static int32_t codes_impl(mb200_ctx* ctx, mb200_csc* s, const mb200_seqs* seqs, int64_t first_seq, int64_t n_seqs,
+                          mb200_code* out, int64_t cap, int64_t* n_out, std::vector<mb200_code>* vec) {
     if (!ctx || !s || !seqs || !n_out) return MB200_E_INVALID;
     const CscDims d = s->d;
     if (seqs->Lb != d.Lb) MB_FAIL(ctx, MB200_E_INVALID, "csc: model built for Lb=%d, sequences have Lb=%lld", d.Lb, (long long)seqs->Lb);
@@ -835,7 +855,8 @@ extern "C" int32_t mb200_csc_codes(mb200_ctx* ctx, mb200_csc* s, const mb200_seq
         for (int64_t i = 0; i < ns; ++i) {
             if (h_cnt[i] > CODE_SLOTS) MB_FAIL(ctx, MB200_E_UNSUPPORTED, "csc_codes: sequence %lld has %d non-zero codes (> %d slots)", (long long)(first_seq + s0 + i), h_cnt[i], CODE_SLOTS);
             for (int j = 0; j < h_cnt[i]; ++j) {
-                if (total < cap && out) out[total] = h_slots[(size_t)i * CODE_SLOTS + j]; else overflow = overflow || (total >= cap);
+                if (vec) vec->push_back(h_slots[(size_t)i * CODE_SLOTS + j]);
+                else if (total < cap && out) out[total] = h_slots[(size_t)i * CODE_SLOTS + j]; else overflow = overflow || (total >= cap);
                 ++total;
             }
         }
@@ -844,6 +865,50 @@ extern "C" int32_t mb200_csc_codes(mb200_ctx* ctx, mb200_csc* s, const mb200_seq
     MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     tm.collect();
     *n_out = total;
-    if (overflow || (total > cap)) MB_FAIL(ctx, MB200_E_HITS_OVERFLOW, "csc_codes: %lld records, capacity %lld", (long long)total, (long long)cap);
+    if (!vec && (overflow || (total > cap))) MB_FAIL(ctx, MB200_E_HITS_OVERFLOW, "csc_codes: %lld records, capacity %lld", (long long)total, (long long)cap);
+    return MB200_OK;
+}
+
+extern "C" int32_t mb200_csc_codes(mb200_ctx* ctx, mb200_csc* s, const mb200_seqs* seqs, int64_t first_seq, int64_t n_seqs,
+                                   mb200_code* out, int64_t cap, int64_t* n_out) {
+    return codes_impl(ctx, s, seqs, first_seq, n_seqs, out, cap, n_out, nullptr);
+}
+
+// Code retrieval sharded over the ranks of the ctx's communicator (third bullet): the batches of batch_size consecutive
+// sequences are independent (_1_code_retrieval.jl:38-50), so rank r decodes a contiguous range of whole batches and the records are
+// all-gathered in rank order — which is ascending sequence order, i.e. exactly the single-GPU result.  `rank`/`world` < 0: take them
+// from the communicator; explicit values with no communicator decode just that shard (no gather; used to test the split on one GPU).
+extern "C" int32_t mb200_csc_codes_sharded(mb200_ctx* ctx, mb200_csc* s, const mb200_seqs* seqs, int64_t first_seq, int64_t n_seqs,
+                                           int32_t rank, int32_t world, mb200_code* out, int64_t cap, int64_t* n_out) {
+    if (!ctx || !s || !seqs || !n_out) return MB200_E_INVALID;
+    const bool gather = rank < 0 || world < 0;
+    if (gather) { rank = ctx->rank; world = ctx->world; }
+    if (world < 1 || rank >= world) MB_FAIL(ctx, MB200_E_INVALID, "csc_codes_sharded: rank %d of %d", rank, world);
+    const int B = s->d.B;
+    if (n_seqs < 0 || n_seqs % B) MB_FAIL(ctx, MB200_E_INVALID, "csc_codes: range must be whole batches inside the data");
+    const int64_t groups = n_seqs / B;
+    const int64_t g_lo = groups * rank / world, g_hi = groups * (rank + 1) / world;
+    std::vector<mb200_code> mine;
+    int64_t n_mine = 0;
+    int rc = codes_impl(ctx, s, seqs, first_seq + g_lo * B, (g_hi - g_lo) * B, nullptr, 0, &n_mine, &mine);
+    if (rc) return rc;
+    if (!gather || world == 1) {
+        *n_out = n_mine;
+        if (n_mine > cap) MB_FAIL(ctx, MB200_E_HITS_OVERFLOW, "csc_codes: %lld records, capacity %lld", (long long)n_mine, (long long)cap);
+        if (n_mine) memcpy(out, mine.data(), (size_t)n_mine * sizeof(mb200_code));
+        return MB200_OK;
+    }
+    std::vector<int64_t> cnt(world, 0);
+    rc = mb200_comm_allgather(ctx, &n_mine, cnt.data(), 8); if (rc) return rc;
+    int64_t total = 0, mx = 0;
+    for (int r = 0; r < world; ++r) { total += cnt[r]; mx = std::max(mx, cnt[r]); }
+    *n_out = total;
+    // every rank takes part in the gather even when its own `out` is too small (the collective must not dead-lock)
+    std::vector<mb200_code> all((size_t)mx * world);
+    mine.resize((size_t)mx);
+    if (mx) { rc = mb200_comm_allgather(ctx, mine.data(), all.data(), mx * (int64_t)sizeof(mb200_code)); if (rc) return rc; }
+    if (total > cap) MB_FAIL(ctx, MB200_E_HITS_OVERFLOW, "csc_codes: %lld records, capacity %lld", (long long)total, (long long)cap);
+    int64_t o = 0;
+    for (int r = 0; r < world; ++r) { if (cnt[r]) memcpy(out + o, all.data() + (size_t)r * mx, (size_t)cnt[r] * sizeof(mb200_code)); o += cnt[r]; }
     return MB200_OK;
 }

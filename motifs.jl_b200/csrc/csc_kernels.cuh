@@ -744,14 +744,15 @@ __global__ void __launch_bounds__(256) k_adabelief(float* __restrict__ p, const 
     mt[t] = m; st[t] = s;
     p[t] -= eta * m / c1 / (sqrtf(s / c2) + eps2);
 }
-// l1 = sum |prep_syntax_filters(F)| (train.jl:47): per k sum(r^2)/sqrt(sum r^4), summed over k.  One block per k, atomics into out.
+// l1 = sum |prep_syntax_filters(F)| (train.jl:47): per k sum(r^2)/sqrt(sum r^4).  One block per k writes its term to out[k]; the host
+// adds the K terms in index order (no atomics: the statistic is bit-identical across data-parallel ranks).
 __global__ void __launch_bounds__(256) k_l1_F(const float* __restrict__ raw, float* __restrict__ out, CscDims d) { PDL_SYNC();
     const int k = blockIdx.x;
     const int HJ = d.h * d.M2;
     float s2 = 0.f, s4 = 0.f;
     for (int e = threadIdx.x; e < HJ; e += blockDim.x) { const float r = raw[(int64_t)k * HJ + e]; const float u = r * r; s2 += u; s4 += u * u; }
     s2 = block_sum(s2); s4 = block_sum(s4);
-    if (threadIdx.x == 0) atomicAdd(out, s2 / sqrtf(s4));
+    if (threadIdx.x == 0) out[k] = s2 / sqrtf(s4);
 }
 
 // =============================================================================================

@@ -31,6 +31,7 @@ extern "C" int32_t mb200_create(mb200_ctx** out, int32_t device_id) {
 extern "C" int32_t mb200_destroy(mb200_ctx* ctx) {
     if (!ctx) return MB200_E_INVALID;
     cudaSetDevice(ctx->device);
+    mb200_comm_destroy(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     for (int i = 0; i < 12; ++i) if (ctx->bufs[i]) cudaFree(ctx->bufs[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

@@ -1064,6 +1064,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
     MB_CUDA(ctx, cudaSetDevice(ctx->device));
     mb_reset_timing(ctx);
     if (n_hits) *n_hits = 0;
+    ctx->held_hits.clear(); ctx->held_hits.shrink_to_fit();
     if (counts) memset(counts, 0, sizeof(int64_t) * 4 * (size_t)K);
     if (hist) memset(hist, 0, (size_t)K * HIST_BINS * 4);
 
@@ -1100,7 +1101,20 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
         else { ctx->tc_cost_sig = sig; ctx->tc_cost.clear(); }
     }
     const int64_t npos_max = Lb - P.minlen + 1;
-    if (N == 0 || npos_max <= 0) return MB200_OK;       // nothing can be scored
+    const bool reduce = (flags & MB200_SCAN_REDUCE) != 0 && ctx->world > 1;
+    if (N == 0 || npos_max <= 0) {                      // nothing can be scored on this rank; it still takes part in the reduction
+        if (reduce && (want_counts || hist)) {
+            const size_t nb = hist ? (size_t)K * HIST_BINS * 4 : (size_t)K * 4 * 8;
+            rc = mb_ensure_scratch(ctx, nb); if (rc) return rc;
+            MB_CUDA(ctx, cudaMemsetAsync(ctx->scratch, 0, nb, ctx->stream));
+            if (want_counts) { rc = mb_comm_allreduce_u64(ctx, (unsigned long long*)ctx->scratch, (size_t)K * 4); if (rc) return rc;
+                               MB_CUDA(ctx, cudaMemcpyAsync(counts, ctx->scratch, (size_t)K * 4 * 8, cudaMemcpyDeviceToHost, ctx->stream)); }
+            if (hist) { rc = mb_comm_allreduce_u32(ctx, (unsigned int*)ctx->scratch, (size_t)K * HIST_BINS); if (rc) return rc;
+                        MB_CUDA(ctx, cudaMemcpyAsync(hist, ctx->scratch, (size_t)K * HIST_BINS * 4, cudaMemcpyDeviceToHost, ctx->stream)); }
+            MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        return MB200_OK;
+    }
     const int64_t W64 = (npos_max + 31) / 32;                      // 32-position mask words per sequence
     if (W64 > 0x1fffffff) MB_FAIL(ctx, MB200_E_UNSUPPORTED, "sequence too long");
     const int32_t W = (int32_t)W64;
@@ -1231,8 +1245,12 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
         const size_t nctr = 8 + 2 * (size_t)grid;
         rc = mb_ensure_pinned(ctx, 2 * nctr * 8); if (rc) return rc;
         unsigned long long* h_ctr2 = (unsigned long long*)ctx->pinned;
-        cudaEvent_t ev_tc[2], ev_aux[2];
-        for (int b = 0; b < 2; ++b) { cudaEventCreateWithFlags(&ev_tc[b], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_aux[b], cudaEventDisableTiming); }
+        struct EvGuard {                                            // the events are destroyed on every way out of this block (error returns included)
+            cudaEvent_t tc[2] = {nullptr, nullptr}, aux[2] = {nullptr, nullptr};
+            ~EvGuard() { for (int b = 0; b < 2; ++b) { if (tc[b]) cudaEventDestroy(tc[b]); if (aux[b]) cudaEventDestroy(aux[b]); } }
+        } evg;
+        cudaEvent_t* ev_tc = evg.tc; cudaEvent_t* ev_aux = evg.aux;
+        for (int b = 0; b < 2; ++b) { MB_CUDA(ctx, cudaEventCreateWithFlags(&ev_tc[b], cudaEventDisableTiming)); MB_CUDA(ctx, cudaEventCreateWithFlags(&ev_aux[b], cudaEventDisableTiming)); }
         const int nb = (int)todo.size();
         std::vector<char> launched(nb, 0), failed(nb, 0);
         bool overflowed = false;
@@ -1329,7 +1347,6 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
         // every batch but the last launched one was looked at inside the loop
         if (n_launched > 0) { rc = process(n_launched - 1); if (rc) return rc; }
         MB_CUDA(ctx, cudaStreamSynchronize(aux));
-        for (int b = 0; b < 2; ++b) { cudaEventDestroy(ev_tc[b]); cudaEventDestroy(ev_aux[b]); }
         std::vector<int64_t> rest;
         for (int j = 0; j < nb; ++j) if (!launched[j] || failed[j]) rest.push_back(todo[j]);
         todo.swap(rest);
@@ -1515,7 +1532,11 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
             MB_CUDA(ctx, cudaMemcpyAsync(&h_total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
             MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             hits_needed += (int64_t)h_total;
-            if (h_total && hits_needed <= hits_cap) {
+            // a list that outgrows the caller's buffer is kept in the ctx (host memory) and handed over by mb200_scan_take_hits:
+            // the caller's retry does not pay for the scan, count and prefix kernels a second time
+            const bool spill = hits_needed > hits_cap;
+            if (spill && ctx->held_hits.empty() && hits_written) ctx->held_hits.assign(hits, hits + hits_written);
+            if (h_total) {
                 rc = mb_ensure_buf(ctx, 4, (size_t)h_total * sizeof(mb200_hit)); if (rc) return rc;
                 mb200_hit* d_hits = (mb200_hit*)ctx->bufs[4];
                 int t4 = tm.begin(T_EMIT);
@@ -1526,7 +1547,9 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
                 ctx->launches[T_EMIT] += 1;
                 MB_CUDA(ctx, cudaGetLastError());
                 int t5 = tm.begin(T_D2H);
-                MB_CUDA(ctx, cudaMemcpyAsync(hits + hits_written, d_hits, (size_t)h_total * sizeof(mb200_hit), cudaMemcpyDeviceToHost, ctx->stream));
+                mb200_hit* dst = hits + hits_written;
+                if (spill) { ctx->held_hits.resize((size_t)hits_written + (size_t)h_total); dst = ctx->held_hits.data() + hits_written; }
+                MB_CUDA(ctx, cudaMemcpyAsync(dst, d_hits, (size_t)h_total * sizeof(mb200_hit), cudaMemcpyDeviceToHost, ctx->stream));
                 tm.end(t5);
                 MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
                 hits_written += (int64_t)h_total;
@@ -1537,6 +1560,10 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
                 ctx->mask_clean_bytes = (size_t)ns * mask_bytes_per_seq;
             }
         }
+    }
+    if (reduce) {                                       // one all-reduce per scan: K x 4 counts, or the K x 32768 histogram
+        if (want_counts) { rc = mb_comm_allreduce_u64(ctx, d_counts, (size_t)K * 4); if (rc) return rc; }
+        if (hist) { rc = mb_comm_allreduce_u32(ctx, d_hist, (size_t)K * HIST_BINS); if (rc) return rc; }
     }
     if (hist) {
         int t8 = tm.begin(T_D2H);
@@ -1592,6 +1619,17 @@ extern "C" int32_t mb200_scan_prefilter_bound(const uint16_t* cols_f16, int32_t 
     return MB200_OK;
 }
 
+// the complete hit list of the last mb200_scan of this ctx that returned MB200_E_HITS_OVERFLOW (kept on the host by the library)
+extern "C" int32_t mb200_scan_take_hits(mb200_ctx* ctx, mb200_hit* hits, int64_t hits_cap, int64_t* n_hits) {
+    if (!ctx || !n_hits) return MB200_E_INVALID;
+    *n_hits = (int64_t)ctx->held_hits.size();
+    if (*n_hits == 0) MB_FAIL(ctx, MB200_E_INVALID, "scan_take_hits: no overflowed hit list is held");
+    if (hits_cap < *n_hits || !hits) MB_FAIL(ctx, MB200_E_HITS_OVERFLOW, "scan_take_hits: %lld hits, capacity %lld", (long long)*n_hits, (long long)hits_cap);
+    memcpy(hits, ctx->held_hits.data(), (size_t)*n_hits * sizeof(mb200_hit));
+    ctx->held_hits.clear(); ctx->held_hits.shrink_to_fit();
+    return MB200_OK;
+}
+
 extern "C" int32_t mb200_scan_last_path(const mb200_ctx* ctx) { return ctx ? ctx->last_scan_path : MB200_E_INVALID; }
 
 // hist: K * 32768 uint32, hist[k][b] = number of hits (score > 0, both requested strands) whose Float16 score has bit pattern b.
@@ -1599,6 +1637,6 @@ extern "C" int32_t mb200_scan_hist(mb200_ctx* ctx, const mb200_seqs* seqs, const
                                    int32_t maxlen, uint32_t flags, uint32_t* hist) {
     if (!ctx) return MB200_E_INVALID;
     if (!hist) MB_FAIL(ctx, MB200_E_INVALID, "scan_hist: null histogram");
-    const uint32_t f = (flags & (MB200_SCAN_FWD | MB200_SCAN_RC));
+    const uint32_t f = (flags & (MB200_SCAN_FWD | MB200_SCAN_RC | MB200_SCAN_REDUCE));
     return scan_impl(ctx, seqs, pwms_f16, lens, K, maxlen, nullptr, f, nullptr, 0, nullptr, nullptr, hist);
 }

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) pack_onehot_kernel(const float4* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
-static int seqs_alloc(mb200_ctx* ctx, int64_t N, int64_t Lb, mb200_seqs** out) {
+int mb_seqs_alloc(mb200_ctx* ctx, int64_t N, int64_t Lb, mb200_seqs** out) {
     if (!ctx || !out || N < 0 || Lb <= 0) MB_FAIL(ctx, MB200_E_INVALID, "seqs: bad N=%lld Lb=%lld", (long long)N, (long long)Lb);
     MB_CUDA(ctx, cudaSetDevice(ctx->device));
     mb200_seqs* s = new mb200_seqs();
@@ -105,9 +105,12 @@ static int seqs_alloc(mb200_ctx* ctx, int64_t N, int64_t Lb, mb200_seqs** out) {
 static int pack_common(mb200_ctx* ctx, const void* src, bool src_on_host, bool onehot, int64_t N, int64_t Lb, mb200_seqs** out) {
     if (!src && N > 0) MB_FAIL(ctx, MB200_E_INVALID, "seqs: null input");
     mb_reset_timing(ctx);
-    int rc = seqs_alloc(ctx, N, Lb, out);
+    int rc = mb_seqs_alloc(ctx, N, Lb, out);
     if (rc) return rc;
     mb200_seqs* s = *out;
+    // from here on a failure must hand the (partly packed) store back: the callers drop the handle on error
+#define PC_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { mb200_seqs_free(ctx, s); *out = nullptr; \
+    MB_FAIL(ctx, MB200_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); } } while (0)
     MbTimers tm(ctx);
     int t_total = tm.begin(T_TOTAL);
     const size_t bytes_per_row = onehot ? (size_t)Lb * 16 : (size_t)Lb;
@@ -120,13 +123,13 @@ static int pack_common(mb200_ctx* ctx, const void* src, bool src_on_host, bool o
     if (rc) { mb200_seqs_free(ctx, s); *out = nullptr; return rc; }
     unsigned int* d_bad = (unsigned int*)ctx->scratch;
     uint8_t* d_stage = (uint8_t*)ctx->scratch + 256;
-    MB_CUDA(ctx, cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
+    PC_CUDA(cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
     for (int64_t n0 = 0; n0 < N; n0 += rows_per_chunk) {
         int64_t nr = std::min(rows_per_chunk, N - n0);
         const uint8_t* dsrc;
         if (src_on_host) {
             int th = tm.begin(T_H2D);
-            MB_CUDA(ctx, cudaMemcpyAsync(d_stage, (const uint8_t*)src + (size_t)n0 * bytes_per_row, (size_t)nr * bytes_per_row,
+            PC_CUDA(cudaMemcpyAsync(d_stage, (const uint8_t*)src + (size_t)n0 * bytes_per_row, (size_t)nr * bytes_per_row,
                                          cudaMemcpyHostToDevice, ctx->stream));
             tm.end(th);
             dsrc = d_stage;
@@ -143,12 +146,12 @@ static int pack_common(mb200_ctx* ctx, const void* src, bool src_on_host, bool o
         }
         tm.end(tp);
         ctx->launches[T_PACK] += 1;
-        MB_CUDA(ctx, cudaGetLastError());
+        PC_CUDA(cudaGetLastError());
     }
     unsigned int h_bad = 0;
-    MB_CUDA(ctx, cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PC_CUDA(cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
     tm.end(t_total);
-    MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PC_CUDA(cudaStreamSynchronize(ctx->stream));
     tm.collect();
     if (h_bad) {
         mb200_seqs_free(ctx, s); *out = nullptr;
@@ -156,6 +159,7 @@ static int pack_common(mb200_ctx* ctx, const void* src, bool src_on_host, bool o
     }
     return MB200_OK;
 }
+#undef PC_CUDA
 
 extern "C" int32_t mb200_seqs_from_ascii(mb200_ctx* ctx, const uint8_t* ascii, int64_t N, int64_t Lb, mb200_seqs** out) {
     if (!ctx) return MB200_E_INVALID;
@@ -177,7 +181,7 @@ extern "C" int32_t mb200_seqs_from_onehot_f32(mb200_ctx* ctx, const float* oneho
 extern "C" int32_t mb200_seqs_from_ascii_async(mb200_ctx* ctx, const uint8_t* ascii, int64_t N, int64_t Lb, mb200_seqs** out) {
     if (!ctx) return MB200_E_INVALID;
     if (!ascii && N > 0) MB_FAIL(ctx, MB200_E_INVALID, "seqs: null input");
-    int rc = seqs_alloc(ctx, N, Lb, out);
+    int rc = mb_seqs_alloc(ctx, N, Lb, out);
     if (rc) return rc;
     mb200_seqs* s = *out;
     if (N == 0) return MB200_OK;

@@ -161,7 +161,8 @@ def posdicts2countmats(ms: Motifs, data):
             s["motif"], s["seq"], s["pos"], s["comp"] = m, n - 1, np.asarray(pos) - 1, np.asarray(ms.use_comp[m][n])
             rec.append(s)
     sites = np.concatenate(rec) if rec else np.zeros(0, _lib.SITE_DTYPE)
-    return [c.astype(np.float32).astype(np.float16) for c in _lib.count_matrices(data.ctx, data.seqs, sites, ms.lens)]
+    # msa_add!(...; ps=0.01, return_count_mat=true) returns `msa .+ ps` (Float32 counts + the Float64 literal 0.01), then Float16
+    return [(c.astype(np.float32).astype(np.float64) + 0.01).astype(np.float16) for c in _lib.count_matrices(data.ctx, data.seqs, sites, ms.lens)]
 
 
 def run_thru(data, cdl, hp, ln, projs, this_bg, quantiles=(0.75, 0.65, 0.5, 0.45, 0.35, 0.25, 0.15, 0.05), codes=None):

@@ -15,7 +15,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from ._lib import CscModel, Context, Sequences  # noqa: F401
-from . import parallel
+from . import parallel  # noqa: F401
 
 
 @dataclass
@@ -132,44 +132,37 @@ def train_ucdl(data, num_epochs=None, l1_loss_thresh=np.float32(95.0), rng: np.r
     """train_ucdl (train.jl:13-57): DataLoader(batch 6, shuffle, partial=false) -> loss + gradient -> AdaBelief ->
     early stop on l1(F) < 95.  Returns (cdl, hp, len, projs=None, model).
 
-    Data parallel (one process per GPU): every rank draws the same epoch permutation, takes its own batch(es) of 6
-    from each global step, and the gradients are averaged with ONE all-reduce per step; with one rank
-    and groups_per_rank=1 this is exactly the reference's step sequence."""
-    import torch
-    import torch.distributed as dist
+    Data parallel (one process per GPU, communicator on the ctx: parallel.init_comm): rank 0's parameters and its epoch
+    permutations are broadcast, every rank takes its own batch(es) of 6 from each global step, and the gradients are averaged
+    with ONE all-reduce per step inside the library.  The early-stop statistic is computed from bit-identical
+    parameters in a fixed order, so all ranks leave the loop on the same step.  With one rank and groups_per_rank=1 this is
+    exactly the reference's step sequence."""
     hp = Hyperparam()
     ln = length_info.of(hp, data)
     rng = rng or np.random.default_rng()
     cdl = cdl or ucdl(hp, rng)
     seqs = data.seqs
-    model = CscModel(seqs.ctx, hp, data.L, n_groups=groups_per_rank)
+    ctx = seqs.ctx
+    rank, world, _ = ctx.comm_info()
+    model = CscModel(ctx, hp, data.L, n_groups=groups_per_rank)
     model.set_params(cdl.flat)
-    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-    rank = dist.get_rank() if world > 1 else 0
-    grad_view, stream_cm = None, None
     if world > 1:
-        # the library launches on a torch-owned side stream so that NCCL (which orders itself against torch's current
-        # stream) sees the reverse pass finish before the all-reduce and the optimiser waits for the all-reduce
-        dev = torch.device("cuda", seqs.ctx.device)
-        side = torch.cuda.Stream(device=dev)
-        seqs.ctx.set_stream(side.cuda_stream)
-        stream_cm = torch.cuda.stream(side)
-        stream_cm.__enter__()
-        _, gptr = model.device_ptrs()
-        grad_view = torch.as_tensor(_DevArray(gptr, model.n_total), device=dev)
+        # nothing guarantees that the callers seeded their generators alike: rank 0's weights and shuffles are everybody's
+        model.broadcast_params(0)
+        seed = np.array([rng.integers(0, 2 ** 62)], np.int64)
+        ctx.comm_broadcast(seed, 0)
+        rng = np.random.default_rng(int(seed[0]))
     num_epochs = setup_num_epochs(data.N) if num_epochs is None else num_epochs
     per_step = hp.batch_size * groups_per_rank * world
     steps_per_epoch = data.N // per_step
     step, stop = 0, False
     for epoch in range(1, num_epochs + 1):
-        perm = rng.permutation(data.N)                                   # shuffle=true; identical on every rank (same rng seed)
+        perm = rng.permutation(data.N)                                   # shuffle=true; identical on every rank (broadcast seed)
         for it in range(steps_per_epoch):
             lo = it * per_step + rank * hp.batch_size * groups_per_rank
             idx = perm[lo: lo + hp.batch_size * groups_per_rank]
             model.step_begin(seqs, idx)
-            if world > 1:
-                parallel.all_reduce_mean_(grad_view)                     # ONE all-reduce of 30 433 fp32 per step
-            loss, l1 = model.adabelief_step()
+            loss, l1 = model.adabelief_step()                            # averages the 30 433 gradients over ranks first (one all-reduce)
             step += 1
             if on_step is not None:
                 on_step(step, loss, l1)
@@ -183,10 +176,6 @@ def train_ucdl(data, num_epochs=None, l1_loss_thresh=np.float32(95.0), rng: np.r
         if verbose:
             print(f"Epoch: {epoch} completed")                           # train.jl:55
     cdl.flat[:] = model.get_params()
-    if stream_cm is not None:
-        torch.cuda.current_stream().synchronize()
-        stream_cm.__exit__(None, None, None)
-        seqs.ctx.set_stream(None)
     return cdl, hp, ln, None, model
 
 
@@ -199,13 +188,15 @@ class _DevArray:
 
 def code_retrieval(data, cdl: ucdl, hp: Hyperparam, model: CscModel | None = None, groups_per_call: int = 512, tensor_cores: bool = False):
     """code_retrieval (_1_code_retrieval.jl:33-56) -> structured array (position, fil, seq, mag_f16), 0-based, ordered by
-    seq, fil, position.  groups_per_call batches of 6 are decoded per kernel sequence (they are independent)."""
+    seq, fil, position.  groups_per_call batches of 6 are decoded per kernel sequence (they are independent); with a
+    communicator on the ctx the batches are sharded over the ranks and the records all-gathered."""
     seqs = data.seqs
-    n_groups = max(1, min(groups_per_call, data.N // hp.batch_size))
+    world = seqs.ctx.world
+    n_groups = max(1, min(groups_per_call, -(-(data.N // hp.batch_size) // world)))
     # tensor_cores=True routes the dense syntax-filter contraction through the tcgen05/TMEM BF16 kernel (stated tolerance, not the
     # fp32 parity path)
     m = CscModel(seqs.ctx, hp, data.L, n_groups=n_groups, forward_only=True, tensor_cores=tensor_cores)
     m.set_params(cdl.flat)
-    out = m.codes(seqs)
+    out = m.codes(seqs, shard="comm" if world > 1 else None)
     m.free()
     return out

@@ -52,3 +52,15 @@ def count_matrix(codes, seq1, pos1, comp, length):
         oh[win, np.arange(length)] = 1
         cm += oh[::-1, ::-1] if c else oh
     return cm
+
+
+def posdicts2countmats(codes, positions, use_comp, lens):
+    """posdicts2countmats(ms, data_matrix) (_h6_positions2countmat.jl:26-37): per motif msa_add!(...; return_count_mat=true) =
+    Float32 window sums .+ 0.01 (a Float64 literal), converted to Float16 (float_type_retrieval).  positions[m]: {seq1: [pos1...]}."""
+    out = []
+    for m, L in enumerate(lens):
+        seq1 = [n for n, ps in positions[m].items() for _ in ps]
+        pos1 = [p for ps in positions[m].values() for p in ps]
+        comp = [c for cs in use_comp[m].values() for c in cs]
+        out.append((count_matrix(codes, seq1, pos1, comp, int(L)).astype(np.float64) + 0.01).astype(np.float16))
+    return out
