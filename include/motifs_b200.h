@@ -210,6 +210,8 @@ int32_t mb200_csc_n_params(const mb200_csc* csc, int64_t* n_trainable, int64_t* 
 int32_t mb200_csc_set_params(mb200_ctx* ctx, mb200_csc* csc, const float* p, int64_t n_total);
 int32_t mb200_csc_get_params(mb200_ctx* ctx, mb200_csc* csc, float* p, int64_t n_total);
 int32_t mb200_csc_reset_optimizer(mb200_ctx* ctx, mb200_csc* csc);
+/* the n_trainable gradients currently on the device (local after step_begin, rank-averaged after adabelief_step) */
+int32_t mb200_csc_get_grads(mb200_ctx* ctx, mb200_csc* csc, float* g, int64_t n_trainable);
 /* device addresses of the parameter and gradient vectors (n_total floats each), so that the host
  * framework can all-reduce gradients in place with one NCCL call per step.                      */
 int32_t mb200_csc_device_ptrs(const mb200_csc* csc, void** params_dev, void** grads_dev);

@@ -102,6 +102,7 @@ def load():
         "mb200_csc_set_params": (i32, [p, p, p, i64]),
         "mb200_csc_get_params": (i32, [p, p, p, i64]),
         "mb200_csc_reset_optimizer": (i32, [p, p]),
+        "mb200_csc_get_grads": (i32, [p, p, p, i64]),
         "mb200_csc_device_ptrs": (i32, [p, C.POINTER(p), C.POINTER(p)]),
         "mb200_csc_broadcast_params": (i32, [p, p, i32]),
         "mb200_csc_codes_sharded": (i32, [p, p, p, i64, i64, i32, i32, p, i64, C.POINTER(i64)]),
@@ -447,6 +448,11 @@ class CscModel:
     def get_params(self):
         a = np.zeros(self.n_total, np.float32)
         self.ctx._check(self.ctx._lib.mb200_csc_get_params(self.ctx._h, self._h, _ptr(a), a.size))
+        return a
+
+    def get_grads(self):
+        a = np.zeros(self.n_trainable, np.float32)
+        self.ctx._check(self.ctx._lib.mb200_csc_get_grads(self.ctx._h, self._h, _ptr(a), a.size))
         return a
 
     def reset_optimizer(self):

@@ -72,9 +72,8 @@ struct mb200_csc {
     int i_lam0, i_kaps0, i_eta0, i_om0, i_kap0, i_rho0, i_mu0, i_lam_w, i_eta_w, i_om_w;
     bool xyz_only = false;
     bool tensor = false;                                 // forward-only handle using the tcgen05 BF16 path for corr2d
-    __nv_bfloat16 *tc_A = nullptr, *tc_F = nullptr; int tc_tiles = 0, tc_ld = 104; size_t tc_smem = 0, tc_smem2 = 0;
-    CUtensorMap tc_map; bool tc_pipelined = false;
-    bool tc_grouped = false; size_t tc_smem3 = 0; int64_t tc_arows = 0;
+    __nv_bfloat16 *tc_A = nullptr, *tc_F = nullptr; int tc_tiles = 0, tc_ld = 104;
+    size_t tc_smem3 = 0; int64_t tc_arows = 0;
     bool batched = false; float* Ft_scratch = nullptr;      // one-CTA-per-sequence kernels (csc_batched.cuh) for many-group shapes      // tap-grouped kernel (k_corr2d_tc3)
     cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr; bool graph_ok = false;
     const uint32_t* graph_words = nullptr; int64_t graph_rowwords = 0;
@@ -151,8 +150,7 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
                          lk(k_prep_scalars, 1, 256, 0, q, S->p_raw, S->data + sc.off, S->segs);
                          lk(k_prep_D, nblk(d.fl * d.M, 128), 128, 0, q, S->p_raw + S->off_D, S->data + De.off, d);
                          lk(k_prep_F, d.K, 256, 0, q, S->p_raw + S->off_F, S->data + Fe.off, S->data + Fn0.off, d);
-                         if (S->tensor && S->tc_grouped) lk(k_tc_prep_F3, nblk((int64_t)d.h * TC_CH * d.K * 8, 256), 256, 0, q, S->data + Fe.off, S->tc_F, d.h, d.M2, d.K);
-                         else if (S->tensor) lk(k_tc_prep_F, nblk((int64_t)d.h * TC_CH * TC_N * 8, 256), 256, 0, q, S->data + Fe.off, S->tc_F, d.h, d.M2, d.K);
+                         if (S->tensor) lk(k_tc_prep_F3, nblk((int64_t)d.h * TC_CH * d.K * 8, 256), 256, 0, q, S->data + Fe.off, S->tc_F, d.h, d.M2, d.K);
                      },
                      [=](cudaStream_t q) {
                          ScalarSegs tr = S->segs; tr.nseg = 7;      // the warm-up scalars (segment 7) are not trained
@@ -175,14 +173,8 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
     auto run_corr2d = [=](const float* A, const float* filt, int64_t gs, float* out, int acc, cudaStream_t q) {
         if (S->tensor && gs == 0 && !acc) {
             const int64_t rows = (int64_t)d.NS * d.c;
-            if (S->tc_grouped) {
-                lk(k_tc_prep_A3, nblk(rows * (TC_CH - 1), 256), 256, 0, q, A, S->tc_A, rows, S->tc_arows, d.M2);
-                lk(k_corr2d_tc3<24, 3>, std::min(S->tc_tiles, S->ctx->sm_count), TC3_THREADS, S->tc_smem3, q, S->tc_A, S->tc_arows, S->tc_F, out, rows, S->tc_tiles, d);
-                return;
-            }
-            lk(k_tc_prep_A, nblk(rows * S->tc_ld, 256), 256, 0, q, A, S->tc_A, rows, d.M2, S->tc_ld);
-            if (S->tc_pipelined) lk(k_corr2d_tc2, std::min(S->tc_tiles, S->ctx->sm_count), 192, S->tc_smem2, q, S->tc_map, S->tc_F, out, rows, S->tc_tiles, d);
-            else lk(k_corr2d_tc, std::min(S->tc_tiles, S->ctx->sm_count), 128, S->tc_smem, q, S->tc_A, S->tc_F, out, rows, S->tc_tiles, S->tc_ld, d);
+            lk(k_tc_prep_A3, nblk(rows * (TC_CH - 1), 256), 256, 0, q, A, S->tc_A, rows, S->tc_arows, d.M2);
+            lk(k_corr2d_tc3<24, 3>, std::min(S->tc_tiles, S->ctx->sm_count), TC3_THREADS, S->tc_smem3, q, S->tc_A, S->tc_arows, S->tc_F, out, rows, S->tc_tiles, d);
             return;
         }
         // one CTA per sequence wins from ~190 sequences up (measured)
@@ -453,26 +445,16 @@ static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
     MB_CUDA(ctx, cudaFuncSetAttribute(k_topq_s, cudaFuncAttributeMaxDynamicSharedMemorySize, s->d.l * s->d.K * 4));
     if (s->tensor) {
         const int64_t rows = (int64_t)s->d.NS * s->d.c;
-        const char* np = getenv("MB200_TC_NO_PIPELINE");
-        const char* ng = getenv("MB200_TC_NO_GROUPING");
-        const bool pipelined = !(np && np[0] == '1');
-        s->tc_grouped = pipelined && !(ng && ng[0] == '1') && s->d.h == 3 * TC_J && s->d.K == 24;      // the instantiated shape <K = 24, h/4 = 3>
-        const int step = s->tc_grouped ? TC_VALID : TC_M;                 // output rows per tile
-        const int R = s->tc_grouped ? TC_M + s->d.h - TC_J : TC_M + s->d.h - 1;
-        s->tc_tiles = (int)((rows + step - 1) / step);
-        const size_t arows = (size_t)rows + 2 * TC_M + s->d.h + 8;        // every variant's last tile stays inside the zero padding
+        // the tap-grouped kernel k_corr2d_tc3<K = 24, h/4 = 3> (tc_corr2d.cuh) is the one instantiated shape
+        const int R = TC_M + s->d.h - TC_J;
+        s->tc_tiles = (int)((rows + TC_VALID - 1) / TC_VALID);
+        const size_t arows = (size_t)rows + 2 * TC_M + s->d.h + 8;        // the last tile stays inside the zero padding
         s->tc_arows = (int64_t)arows;
         MB_CUDA(ctx, cudaMalloc(&s->tc_A, arows * s->tc_ld * 2));
         MB_CUDA(ctx, cudaMemset(s->tc_A, 0, arows * s->tc_ld * 2));
         MB_CUDA(ctx, cudaMalloc(&s->tc_F, (size_t)s->d.h * TC_CH * TC_N * 8 * 2));
-        s->tc_smem = (((size_t)TC_CH * R * 16 + 127) & ~(size_t)127) + (size_t)s->d.h * TC_CH * TC_N * 16;
-        MB_CUDA(ctx, cudaFuncSetAttribute(k_corr2d_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tc_smem));
-        s->tc_smem2 = 2 * ((((size_t)TC_CH * R * 16) + 1023) & ~(size_t)1023) + (size_t)s->d.h * TC_CH * TC_N * 16;
-        MB_CUDA(ctx, cudaFuncSetAttribute(k_corr2d_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tc_smem2));
         s->tc_smem3 = TC3_STAGES * ((((size_t)TC_CH * R * 16) + 1023) & ~(size_t)1023) + (size_t)s->d.h * TC_CH * s->d.K * 16 + 4 * 3 * (TC_J - 1) * (TC_J - 1) * 24 * 4;
         MB_CUDA(ctx, cudaFuncSetAttribute(k_corr2d_tc3<24, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tc_smem3));
-        s->tc_pipelined = pipelined && tc_make_tmap(&s->tc_map, s->tc_A, arows, s->tc_ld, R) == 0;
-        if (!s->tc_pipelined) { s->tc_grouped = false; s->tc_tiles = (int)((rows + TC_M - 1) / TC_M); }
     }
     MB_CUDA(ctx, cudaStreamCreateWithFlags(&s->aux, cudaStreamNonBlocking));
     MB_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
@@ -508,7 +490,7 @@ extern "C" int32_t mb200_csc_create(mb200_ctx* ctx, const mb200_hparams* hp, int
     mb200_csc* s = new mb200_csc();
     s->ctx = ctx; s->hp = *hp; s->xyz_only = forward_only != 0;
     s->tensor = forward_only == 2;
-    if (s->tensor && (hp->K > TC_N || 2 * hp->M > (TC_CH - 1) * 8)) { delete s; MB_FAIL(ctx, MB200_E_UNSUPPORTED, "csc: the tensor-core path needs K <= %d and 2M <= %d", TC_N, (TC_CH - 1) * 8); }
+    if (s->tensor && (hp->K != 24 || hp->h != 3 * TC_J || 2 * hp->M > (TC_CH - 1) * 8)) { delete s; MB_FAIL(ctx, MB200_E_UNSUPPORTED, "csc: the tensor-core path is built for K = 24, h = %d and 2M <= %d", 3 * TC_J, (TC_CH - 1) * 8); }
     CscDims& d = s->d;
     d.B = hp->batch_size; d.G = n_groups; d.NS = d.B * d.G; d.Lb = (int)Lb; d.L4 = 4 * (int)Lb; d.c = (int)c; d.l = (int)l;
     d.M = hp->M; d.M2 = 2 * hp->M; d.K = hp->K; d.h = hp->h; d.q = hp->q; d.fl = hp->filter_len; d.f_len = 4 * hp->filter_len;
@@ -564,6 +546,17 @@ extern "C" int32_t mb200_csc_get_params(mb200_ctx* ctx, mb200_csc* s, float* p, 
     if (n != s->n_total) MB_FAIL(ctx, MB200_E_INVALID, "csc: expected %lld parameters", (long long)s->n_total);
     MB_CUDA(ctx, cudaSetDevice(ctx->device));
     MB_CUDA(ctx, cudaMemcpyAsync(p, s->p_raw, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MB200_OK;
+}
+
+// the gradient vector as it currently sits on the device: local gradients after mb200_csc_step_begin, the rank-averaged ones after
+// mb200_csc_adabelief_step of a ctx with a communicator (tests and bench.py check "all-reduced == mean of the per-rank gradients")
+extern "C" int32_t mb200_csc_get_grads(mb200_ctx* ctx, mb200_csc* s, float* g, int64_t n) {
+    if (!ctx || !s || !g) return MB200_E_INVALID;
+    if (n != s->n_train) MB_FAIL(ctx, MB200_E_INVALID, "csc: expected %lld gradients", (long long)s->n_train);
+    MB_CUDA(ctx, cudaSetDevice(ctx->device));
+    MB_CUDA(ctx, cudaMemcpyAsync(g, s->g_raw, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MB200_OK;
 }

@@ -43,7 +43,7 @@ struct __align__(16) GroupMeta {
     int32_t len;                       // columns to run (longest motif of the group)
     int32_t tab_off;                   // byte offset of the group's table inside the motif block
     int32_t npos_max;                  // max over npos[]: position blocks starting at or beyond it have nothing to score
-    int32_t type;                      // 0: PRMT mapping (lane = slot), 1: gather mapping (lane = position), see scan_kernel
+    int32_t reserved;
     int32_t npos[GROUP_MOTIFS];        // valid start positions per motif (Lb - len_k + 1, >= 0)
     uint16_t thr[GROUP_SLOTS];         // Float16 bits per slot: max(thresh, 0), +Inf for a disabled strand / padding
 };                                     // 144 bytes
@@ -54,7 +54,7 @@ struct MBlock {
     int32_t blob_bytes;                // multiple of 16
     int32_t tab_bytes;                 // bytes of tables (metas follow)
     int32_t g0, ng;                    // global group range
-    int32_t cost, n_gather;            // n_gather: groups of this block scored with the gather mapping
+    int32_t cost, reserved;
 };
 
 struct ScanArgs {
@@ -63,7 +63,6 @@ struct ScanArgs {
     uint32_t* mask; int32_t K2pad;
     const uint8_t* blob; const MBlock* mblocks; int32_t n_mblocks;
     int32_t tile_chunks; int64_t ntiles; int32_t tile_cap_words; int32_t blob_cap_bytes;
-    int32_t gather_warps;              // warps of a CTA that run the gather mapping when a motif block holds both types
     const int64_t* cta_range;          // [gridDim.x + 1] pair ranges (pair = mblock * ntiles + tile)
 };
 
@@ -102,26 +101,6 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
     return v;
 }
 __device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-// gather mapping, one PWM column for 8 motifs x 2 strands: two 16 B table reads selected by the lane's base, eight adds
-__device__ __forceinline__ void gather_column(uint32_t tab_col, uint32_t b32, __half2 (&acc)[8]) {
-    const uint4 v0 = lds128(tab_col + b32);
-    const uint4 v1 = lds128(tab_col + b32 + 16);
-    acc[0] = __hadd2(acc[0], as_h2(v0.x)); acc[1] = __hadd2(acc[1], as_h2(v0.y));
-    acc[2] = __hadd2(acc[2], as_h2(v0.z)); acc[3] = __hadd2(acc[3], as_h2(v0.w));
-    acc[4] = __hadd2(acc[4], as_h2(v1.x)); acc[5] = __hadd2(acc[5], as_h2(v1.y));
-    acc[6] = __hadd2(acc[6], as_h2(v1.z)); acc[7] = __hadd2(acc[7], as_h2(v1.w));
-}
-#define GATHER_SEGMENT(XS, J0)                                                          \
-    _Pragma("unroll") for (int jj = 0; jj < 16; ++jj) {                                 \
-        if ((J0) + jj >= len) goto gather_done;                                         \
-        const uint32_t b32 = (((XS) >> (2 * jj)) & 3u) << 5;                            \
-        gather_column(tab + ((J0) + jj) * 128, b32, acc);                               \
-    }
 // first packed word of position block `pb` of sequence n (16 bases per word, so a block starts on a word)
 __device__ __forceinline__ int64_t block_word(int64_t gq, int32_t W16, int64_t rowwords, int64_t* n_out, int32_t* pb_out) {
     int64_t n = gq / W16;
@@ -138,14 +117,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a)
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tile1 + a.tile_cap_words);     // [0],[1] tiles, [2] blob
     int32_t* s_ticket = reinterpret_cast<int32_t*>(s_bar + 3);                     // next position block of the current tile
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int64_t q_lo = a.cta_range[blockIdx.x], q_hi = a.cta_range[blockIdx.x + 1];
     if (q_lo >= q_hi) return;
 
     const uint32_t bar0 = smem_u32(&s_bar[0]), bar1 = smem_u32(&s_bar[1]), bar2 = smem_u32(&s_bar[2]);
     if (threadIdx.x == 0) {
         mbar_init(bar0, 1); mbar_init(bar1, 1); mbar_init(bar2, 1);
-        s_ticket[0] = 0; s_ticket[1] = 0;
+        s_ticket[0] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -191,69 +170,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a)
         const uint32_t* s_tile = buf ? s_tile1 : s_tile0;
         const GroupMeta* s_meta = reinterpret_cast<const GroupMeta*>(s_blob + mbk.tab_bytes);
         const uint32_t blob_base = smem_u32(s_blob);
-        // Two mappings share the CTA: the gather mapping is bound by the shared-memory port, the PRMT mapping by
-        // the ALU pipe, so running them side by side on disjoint motif groups uses both.  A motif block that holds only one type
-        // is processed by all warps with that mapping.
-        const bool has_a = mbk.n_gather > 0, has_b = mbk.n_gather < mbk.ng;
-        const bool gather_role = has_a && (!has_b || warp < a.gather_warps);
-
-        if (gather_role) {
-            // ---- gather mapping: a warp takes 32 consecutive start positions (= one mask word); lane = position ----
-            const int32_t nchunk32 = cnt >> 1;
-            for (;;) {
-                int32_t i = 0;
-                if (lane == 0) i = atomicAdd(s_ticket, 1);
-                i = __shfl_sync(0xffffffffu, i, 0);
-                if (i >= nchunk32) break;
-                int64_t n; int32_t pb;
-                const int64_t lq = first + 2 * (int64_t)i;
-                const int64_t w0i = block_word(a.chunk0 + lq, a.W, a.rowwords, &n, &pb) - lo4;
-                const int32_t pos = pb * POS_BLOCK + lane;
-                const uint32_t* wp = s_tile + w0i + (lane >> 4);
-                const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
-                const uint32_t sh = (lane & 15) * 2;
-                const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
-                const uint32_t x2 = __funnelshift_r(w2, w3, sh), x3 = __funnelshift_r(w3, w4, sh);
-                uint32_t* mrow = a.mask + (lq >> 1) * (int64_t)a.K2pad + (int64_t)mbk.g0 * GROUP_SLOTS;
-                for (int32_t g = 0; g < mbk.ng; ++g) {
-                    const GroupMeta* gm = s_meta + g;
-                    if (gm->type != 1) continue;
-                    if (pb * POS_BLOCK >= gm->npos_max) {
-                        mrow[g * GROUP_SLOTS + lane] = 0u;
-                        continue;
-                    }
-                    const int32_t len = gm->len;
-                    #pragma unroll 1
-                    for (int hh = 0; hh < 2; ++hh) {              // two 8-motif halves of the 16-motif group
-                        const uint32_t tab = blob_base + gm->tab_off + hh * (len * 128);
-                        __half2 acc[8];
-                        #pragma unroll
-                        for (int k = 0; k < 8; ++k) acc[k] = as_h2(0u);
-                        GATHER_SEGMENT(x0, 0)
-                        GATHER_SEGMENT(x1, 16)
-                        GATHER_SEGMENT(x2, 32)
-                        GATHER_SEGMENT(x3, 48)
-                    gather_done:
-                        uint32_t myword = 0;
-                        #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const uint32_t t2 = *reinterpret_cast<const uint32_t*>(&gm->thr[(hh * 8 + k) * 2]);
-                            const uint32_t m = __hgt2_mask(acc[k], as_h2(t2));
-                            const bool valid = pos < gm->npos[hh * 8 + k];
-                            const uint32_t bf = __ballot_sync(0xffffffffu, valid && (m & 0xFFFFu));
-                            const uint32_t br = __ballot_sync(0xffffffffu, valid && (m >> 16));
-                            if (lane == 2 * k) myword = bf;
-                            if (lane == 2 * k + 1) myword = br;
-                        }
-                        if (lane < 16) mrow[g * GROUP_SLOTS + hh * 16 + lane] = myword;
-                    }
-                }
-            }
-        } else if (has_b) {
         const uint32_t tab_base = blob_base + lane * 8;
         for (;;) {
             int32_t i = 0;
-            if (lane == 0) i = atomicAdd(s_ticket + 1, 1);
+            if (lane == 0) i = atomicAdd(s_ticket, 1);
             i = __shfl_sync(0xffffffffu, i, 0);
             if (i >= cnt) break;
             int64_t n; int32_t pb;
@@ -285,7 +205,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a)
 
             for (int32_t g = 0; g < mbk.ng; ++g) {
                 const GroupMeta* gm = s_meta + g;
-                if (gm->type != 0) continue;
                 if (p0 >= gm->npos_max) {                     // warp-uniform: no valid start position in this block
                     mrow[(g * GROUP_SLOTS + lane) * 2] = 0;
                     continue;
@@ -320,9 +239,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a)
                 mrow[(g * GROUP_SLOTS + lane) * 2] = (uint16_t)bits;
             }
         }
-        }
         __syncthreads();      // tile buffer `buf` and (possibly) the blob may be overwritten next
-        if (threadIdx.x == 0) { s_ticket[0] = 0; s_ticket[1] = 0; }
+        if (threadIdx.x == 0) s_ticket[0] = 0;
         __syncthreads();
     }
 }
@@ -712,7 +630,6 @@ struct ScanPlan {
 };
 
 #include "scan_tc.cuh"
-#include "scan_tc2.cuh"
 
 // ---- host side of the tensor-core pre-filter (scan_tc.cuh) ------------------------------------------------------------
 static inline uint16_t float_to_h16(float f) { __half h = __float2half_rn(f); __half_raw r = h; return r.x; }
@@ -768,14 +685,6 @@ static bool tc_assign_ctas(std::vector<TcBlock>& blocks, const std::vector<doubl
     }
     int c0 = 0;
     for (int bi = 0; bi < nblocks; ++bi) { blocks[bi].cta0 = c0; blocks[bi].nctas = n[bi]; c0 += n[bi]; }
-    return true;
-}
-
-// CTA-pair kernel (k_scan_tc2): entries get whole clusters of two CTAs
-static bool tc_assign(std::vector<TcBlock>& blocks, const std::vector<double>& cost, int grid, bool pair) {
-    if (!pair) return tc_assign_ctas(blocks, cost, grid);
-    if (!tc_assign_ctas(blocks, cost, grid / 2)) return false;
-    for (auto& b : blocks) { b.cta0 *= 2; b.nctas *= 2; }
     return true;
 }
 
@@ -892,14 +801,13 @@ static bool build_tc_plan(const ScanPlan& P, const uint16_t* pwms, const int64_t
     std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return kcs[x] > kcs[y]; });
     const double drain = 1000.0;
     const size_t b_budget = (size_t)200 * 1024 - (size_t)TCS_STAGES * TCS_STAGE_BYTES;
-    const bool no_pair = getenv("MB200_SCAN_TC_NOPAIR") != nullptr;
     std::vector<double> cost;
     for (int i = 0; i < nblocks;) {
         TcBlock e; memset(&e, 0, sizeof e);
         const int L = ord[i];
         e.b_off[0] = boff[L]; e.kchunks[0] = kcs[L]; e.slot0[0] = L * TCS_N; e.nsub = 1;
         size_t bbytes = bbytes_of(kcs[L]);
-        if (i + 1 < nblocks && !no_pair && bbytes + bbytes_of(kcs[ord[i + 1]]) <= b_budget) {
+        if (i + 1 < nblocks && bbytes + bbytes_of(kcs[ord[i + 1]]) <= b_budget) {
             const int S = ord[i + 1];
             e.b_off[1] = boff[S]; e.kchunks[1] = kcs[S]; e.slot0[1] = S * TCS_N; e.nsub = 2;
             bbytes += bbytes_of(kcs[S]);
@@ -922,7 +830,7 @@ static bool build_tc_plan(const ScanPlan& P, const uint16_t* pwms, const int64_t
 }
 
 static int build_plan(mb200_ctx* ctx, const uint16_t* pwms, const int64_t* lens, int K, int maxlen, const uint16_t* thresh,
-                      uint32_t flags, int64_t Lb, size_t table_budget, double gather_frac, ScanPlan& P) {
+                      uint32_t flags, int64_t Lb, size_t table_budget, ScanPlan& P) {
     P.K = K;
     std::vector<int> order(K);
     for (int k = 0; k < K; ++k) {
@@ -961,15 +869,6 @@ static int build_plan(mb200_ctx* ctx, const uint16_t* pwms, const int64_t* lens,
             MB_FAIL(ctx, MB200_E_UNSUPPORTED, "a single motif group needs %d B of shared memory", mb.blob_bytes);
         P.mblocks.push_back(mb);
     }
-    // mapping per group: shared-memory-gather (type 1) or PRMT (type 0), balanced by column count inside every block
-    std::vector<int> gtype(P.ngroups, 0);
-    for (auto& mb : P.mblocks) {
-        double ca = 0, cb = 0;
-        for (int gg = mb.g0; gg < mb.g0 + mb.ng; ++gg) {
-            const bool to_a = gather_frac > 0 && (ca + glen[gg]) <= gather_frac * (ca + cb + glen[gg]) + 1e-9;
-            if (to_a) { gtype[gg] = 1; ca += glen[gg]; mb.n_gather += 1; } else cb += glen[gg];
-        }
-    }
     for (int gl = g_long; gl < P.ngroups; ++gl) {
         MBlock mb; memset(&mb, 0, sizeof mb);
         mb.g0 = gl; mb.ng = 1; mb.tab_bytes = glen[gl] * COL_BYTES; mb.cost = glen[gl];
@@ -992,7 +891,7 @@ static int build_plan(mb200_ctx* ctx, const uint16_t* pwms, const int64_t* lens,
         for (int gi = 0; gi < mb.ng; ++gi) {
             const int gg = mb.g0 + gi;
             GroupMeta gm; memset(&gm, 0, sizeof gm);
-            gm.len = glen[gg]; gm.tab_off = toff; gm.type = gtype[gg];
+            gm.len = glen[gg]; gm.tab_off = toff;
             uint16_t* T = reinterpret_cast<uint16_t*>(tabs + toff);   // [col][slot][base]
             for (int i = 0; i < GROUP_MOTIFS; ++i) {
                 const int idx = gg * GROUP_MOTIFS + i;
@@ -1015,10 +914,9 @@ static int build_plan(mb200_ctx* ctx, const uint16_t* pwms, const int64_t* lens,
                     P.pairlen[gg * GROUP_MOTIFS + i] = len;
                     P.em[k].slot = gg * GROUP_SLOTS + i * 2;
                     P.em[k].len = len;
-                    const bool ga = gtype[gg] == 1;
-                    // gather layout: two halves of 8 motifs, each [col][base][8 motifs x 2 strands]; PRMT layout: [col][slot][base]
-                    P.em[k].tab_off = mb.blob_off + toff + (ga ? (int64_t)(i / 8) * glen[gg] * 128 + (i % 8) * 4 : (int64_t)i * 16);
-                    P.em[k].col_stride = ga ? 128 : COL_BYTES; P.em[k].base_stride = ga ? 32 : 2; P.em[k].strand_stride = ga ? 2 : 8;
+                    // table layout [col][slot][base]
+                    P.em[k].tab_off = mb.blob_off + toff + (int64_t)i * 16;
+                    P.em[k].col_stride = COL_BYTES; P.em[k].base_stride = 2; P.em[k].strand_stride = 8;
                     for (int j = 0; j < len; ++j) {
                         int nf_f = 0;
                         for (int a2 = 0; a2 < 4; ++a2) nf_f += h16_nonfinite(pw(k, a2, j));
@@ -1027,16 +925,14 @@ static int build_plan(mb200_ctx* ctx, const uint16_t* pwms, const int64_t* lens,
                             // in the reference's sum (greedy_search! adds pwm*x for all four a).
                             const uint16_t v = pw(k, b, j);
                             const uint16_t ef = (nf_f - (int)h16_nonfinite(v)) > 0 ? (uint16_t)0x7E00u : v;
-                            if (ga) T[(size_t)(i / 8) * glen[gg] * 64 + ((size_t)j * 4 + b) * 16 + (i % 8) * 2 + 0] = ef;
-                            else T[((size_t)j * GROUP_SLOTS + i * 2 + 0) * 4 + b] = ef;
+                            T[((size_t)j * GROUP_SLOTS + i * 2 + 0) * 4 + b] = ef;
                             // reverse(pwm): rc[a][j] = pwm[3-a][len-1-j]; its column j mirrors forward column len-1-j
                             const int jr = len - 1 - j;
                             const uint16_t vr = pw(k, 3 - b, jr);
                             int nf_r = 0;
                             for (int a2 = 0; a2 < 4; ++a2) nf_r += h16_nonfinite(pw(k, a2, jr));
                             const uint16_t er = (nf_r - (int)h16_nonfinite(vr)) > 0 ? (uint16_t)0x7E00u : vr;
-                            if (ga) T[(size_t)(i / 8) * glen[gg] * 64 + ((size_t)j * 4 + b) * 16 + (i % 8) * 2 + 1] = er;
-                            else T[((size_t)j * GROUP_SLOTS + i * 2 + 1) * 4 + b] = er;
+                            T[((size_t)j * GROUP_SLOTS + i * 2 + 1) * 4 + b] = er;
                         }
                     }
                 }
@@ -1071,33 +967,19 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
     const int64_t N = seqs->N, Lb = seqs->Lb, rowwords = seqs->rowwords;
     const size_t table_budget = 160 * 1024;
     ScanPlan P;
-    // split of the motif groups between the two mappings of scan_kernel and of the warps between them (tunable for experiments)
-    // Measured (profiles/r01_scan_mapping_sweep.txt): the PRMT mapping alone is fastest; mixing in gather warps lowers throughput
-    // (both mappings also compete for issue slots and the FP16 pipes), so the default uses the PRMT mapping for every group.
-    double gather_frac = 0.0; int gather_warps = 8;
-    if (const char* e = getenv("MB200_SCAN_GATHER_FRAC")) gather_frac = atof(e);
-    if (const char* e = getenv("MB200_SCAN_GATHER_WARPS")) gather_warps = atoi(e);
-    if (gather_warps <= 0 || gather_warps >= SCAN_THREADS / 32) { gather_frac = gather_warps <= 0 ? 0.0 : 1.0; gather_warps = 8; }
-    int rc = build_plan(ctx, pwms_f16, lens, K, maxlen, thresh_f16, flags, Lb, table_budget, gather_frac, P);
+    int rc = build_plan(ctx, pwms_f16, lens, K, maxlen, thresh_f16, flags, Lb, table_budget, P);
     if (rc) return rc;
     // Thresholded scans take the tensor-core pre-filter + exact verification (scan_tc.cuh) unless the caller or the inputs rule
     // it out; the hit masks, and everything derived from them, are identical either way.
     TcPlan TP;
     bool use_tc = !(flags & MB200_SCAN_NO_TENSOR) && !hist && Lb < (1ll << 31);
-    if (const char* e = getenv("MB200_SCAN_TC")) use_tc = use_tc && atoi(e) != 0;
     if (use_tc) use_tc = build_tc_plan(P, pwms_f16, lens, K, thresh_f16, flags, Lb, ctx->sm_count, TP);
     ctx->last_scan_path = 0;
-    // CTA-pair kernel (scan_tc2.cuh, cta_group::2: half of B per CTA).  Correct (all parity tests pass with it) but measured NOT faster than
-    // k_scan_tc on config 4 (2 M x 200 bp: 79.5 ms vs 75.6-76.3 ms of kernel time on the same box), so it is opt-in: MB200_SCAN_TC_PAIR=1.
-    bool tc_pair = false;
-    if (const char* e = getenv("MB200_SCAN_TC_PAIR")) tc_pair = atoi(e) != 0 && use_tc && (ctx->sm_count % 2 == 0) && (int)TP.blocks.size() * 2 <= ctx->sm_count;
     if (use_tc) {
-        if (tc_pair && !tc_assign(TP.blocks, TP.cost, ctx->sm_count, true)) tc_pair = false;
         // start from the clocks per tile measured by the previous scan of this ctx when it had the same block structure
         std::vector<int32_t> sig;
         for (auto& e : TP.blocks) { sig.push_back(e.nsub); sig.push_back(e.kchunks[0]); sig.push_back(e.kchunks[1]); }
-        sig.push_back(tc_pair ? 2 : 1);
-        if (sig == ctx->tc_cost_sig && ctx->tc_cost.size() == TP.blocks.size()) { TP.cost = ctx->tc_cost; tc_assign(TP.blocks, TP.cost, ctx->sm_count, tc_pair); }
+        if (sig == ctx->tc_cost_sig && ctx->tc_cost.size() == TP.blocks.size()) { TP.cost = ctx->tc_cost; tc_assign_ctas(TP.blocks, TP.cost, ctx->sm_count); }
         else { ctx->tc_cost_sig = sig; ctx->tc_cost.clear(); }
     }
     const int64_t npos_max = Lb - P.minlen + 1;
@@ -1183,9 +1065,8 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
         MB_CUDA(ctx, cudaMemsetAsync((uint8_t*)d_tc_ctr + tc_set_stride, 0, (size_t)(8 + 2 * ctx->sm_count) * 8, ctx->stream));
         MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));           // h_tc goes out of scope
         // at least half of the shared memory: one CTA per SM (each CTA allocates all 512 TMEM columns)
-        tc_smem = std::max<size_t>((size_t)TCS_STAGES * TCS_STAGE_BYTES + (tc_pair ? TP.max_b_bytes / 2 : TP.max_b_bytes), (size_t)120 * 1024);
+        tc_smem = std::max<size_t>((size_t)TCS_STAGES * TCS_STAGE_BYTES + TP.max_b_bytes, (size_t)120 * 1024);
         if (tc_smem > ctx->smem_optin) use_tc = false;
-        else if (tc_pair) MB_CUDA(ctx, cudaFuncSetAttribute(k_scan_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
         else MB_CUDA(ctx, cudaFuncSetAttribute(k_scan_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
     }
     rc = mb_ensure_buf(ctx, 2, (size_t)seqs_per_batch * mask_bytes_per_seq); if (rc) return rc;
@@ -1269,7 +1150,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
                 cost[bi] = clk / tiles;
             }
             if (ok) ctx->tc_cost = cost;
-            if (ok) tc_assign(TP.blocks, cost, grid, tc_pair);          // the next launch carries the new split in its parameters
+            if (ok) tc_assign_ctas(TP.blocks, cost, grid);          // the next launch carries the new split in its parameters
             return MB200_OK;
         };
         int i = 0;
@@ -1306,12 +1187,12 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
 #if TCS_PROFILE
             static long long* d_dbg2 = nullptr;
             if (getenv("MB200_SCAN_TC_DEBUG") && i == atoi(getenv("MB200_SCAN_TC_DEBUG"))) {
-                if (!d_dbg2) cudaMalloc(&d_dbg2, 148 * 8 * 8 * 2);
-                cudaMemsetAsync(d_dbg2, 0, 148 * 8 * 8, ctx->stream); ta.dbg = d_dbg2;
+                if (!d_dbg2) MB_CUDA(ctx, cudaMalloc(&d_dbg2, (size_t)grid * 8 * 8));
+                MB_CUDA(ctx, cudaMemsetAsync(d_dbg2, 0, (size_t)grid * 8 * 8, ctx->stream)); ta.dbg = d_dbg2;
             }
 #endif
             const int t_tc = tm.begin(T_SCAN);
-            if (tc_pair) k_scan_tc2<<<grid, TCS_THREADS, tc_smem, ctx->stream>>>(ta); else k_scan_tc<<<grid, TCS_THREADS, tc_smem, ctx->stream>>>(ta);
+            k_scan_tc<<<grid, TCS_THREADS, tc_smem, ctx->stream>>>(ta);
             tm.end(t_tc);
             MB_CUDA(ctx, cudaGetLastError());
             MB_CUDA(ctx, cudaEventRecord(ev_tc[b], ctx->stream));
@@ -1333,9 +1214,9 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
             launched[i] = 1;
 #if TCS_PROFILE
             if (ta.dbg) {
-                std::vector<long long> h(148 * 8);
+                std::vector<long long> h((size_t)grid * 8);
                 cudaStreamSynchronize(ctx->stream);
-                cudaMemcpy(h.data(), ta.dbg, 148 * 8 * 8, cudaMemcpyDeviceToHost);
+                cudaMemcpy(h.data(), ta.dbg, (size_t)grid * 8 * 8, cudaMemcpyDeviceToHost);
                 for (int c = 0; c < grid; c += 1)
                     fprintf(stderr, "[tcdbg] cta %3d blk %lld tiles %lld | mma total %9lld wait_full %9lld wait_acc %9lld | epi total %9lld wait %9lld | prod wait %9lld\n", c, h[c * 8 + 6], h[c * 8 + 7],
                             h[c * 8 + 0], h[c * 8 + 1], h[c * 8 + 2], h[c * 8 + 4], h[c * 8 + 3], h[c * 8 + 5]);
@@ -1395,7 +1276,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
         a.mask = d_mask; a.K2pad = P.K2pad;
         a.blob = d_plan + off_blob; a.mblocks = (const MBlock*)(d_plan + off_mb); a.n_mblocks = (int32_t)P.mblocks.size();
         a.tile_chunks = tile_chunks; a.ntiles = ntiles; a.tile_cap_words = tile_cap_words; a.blob_cap_bytes = blob_cap;
-        a.cta_range = d_rng; a.gather_warps = gather_warps;
+        a.cta_range = d_rng;
         bool tc_done = false;
         if (use_tc) {
             const size_t need = (size_t)ns * mask_bytes_per_seq;
@@ -1417,10 +1298,10 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
             ta.dbg = nullptr;
 #if TCS_PROFILE
             static long long* d_dbg = nullptr;
-            if (getenv("MB200_SCAN_TC_DEBUG")) { if (!d_dbg) cudaMalloc(&d_dbg, 148 * 8 * 8 * 2); cudaMemset(d_dbg, 0, 148 * 8 * 8); ta.dbg = d_dbg; }
+            if (getenv("MB200_SCAN_TC_DEBUG")) { if (!d_dbg) MB_CUDA(ctx, cudaMalloc(&d_dbg, (size_t)grid * 8 * 8)); MB_CUDA(ctx, cudaMemset(d_dbg, 0, (size_t)grid * 8 * 8)); ta.dbg = d_dbg; }
 #endif
             const int t_tc = tm.begin(T_SCAN);
-            if (tc_pair) k_scan_tc2<<<grid, TCS_THREADS, tc_smem, ctx->stream>>>(ta); else k_scan_tc<<<grid, TCS_THREADS, tc_smem, ctx->stream>>>(ta);
+            k_scan_tc<<<grid, TCS_THREADS, tc_smem, ctx->stream>>>(ta);
             tm.end(t_tc);
             const int t_vf = tm.begin(T_EMIT);
             k_scan_tc_verify<<<grid * 8, 256, 0, ctx->stream>>>(d_tc_list, d_tc_ctr, tc_cap, ta.slots, (const EmitMotif*)(d_plan + off_em), d_plan + off_blob,
@@ -1434,8 +1315,8 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
             MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 #if TCS_PROFILE
             if (ta.dbg && s0 / seqs_per_batch == atoi(getenv("MB200_SCAN_TC_DEBUG"))) {
-                std::vector<long long> h(148 * 8);
-                cudaMemcpy(h.data(), ta.dbg, 148 * 8 * 8, cudaMemcpyDeviceToHost);
+                std::vector<long long> h((size_t)grid * 8);
+                cudaMemcpy(h.data(), ta.dbg, (size_t)grid * 8 * 8, cudaMemcpyDeviceToHost);
                 for (int c = 0; c < grid; c += 1)
                     fprintf(stderr, "[tcdbg] cta %3d blk %lld tiles %lld | mma total %9lld wait_full %9lld wait_acc %9lld | epi total %9lld wait %9lld | prod wait %9lld\n", c, h[c * 8 + 6], h[c * 8 + 7],
                             h[c * 8 + 0], h[c * 8 + 1], h[c * 8 + 2], h[c * 8 + 4], h[c * 8 + 3], h[c * 8 + 5]);
@@ -1453,7 +1334,7 @@ static int32_t scan_impl(mb200_ctx* ctx, const mb200_seqs* seqs, const uint16_t*
                     cost[bi] = clk / tiles;
                 }
                 if (ok) ctx->tc_cost = cost;
-                if (ok) tc_assign(TP.blocks, cost, grid, tc_pair);
+                if (ok) tc_assign_ctas(TP.blocks, cost, grid);
             }
             tc_stat_cand += h_ctr[2]; tc_stat_hits += h_ctr[3];
             ctx->mask_clean_bytes = 0;                               // the verifier has set bits (re-established below when the sparse count clears them)

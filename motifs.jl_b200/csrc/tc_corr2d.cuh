@@ -30,126 +30,6 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t da, uint64
                  :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// operand preparation: A fp32 [rows][2M] -> bf16 [rows + pad][104]; F fp32 [h][2M][K] -> bf16 [h][TC_CH][TC_N][8]
-__global__ void __launch_bounds__(256) k_tc_prep_A(const float* __restrict__ A, __nv_bfloat16* __restrict__ Ab, int64_t rows, int M2, int ld) { PDL_SYNC();
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= rows * ld) return;
-    const int j = (int)(t % ld);
-    const int64_t r = t / ld;
-    Ab[t] = __float2bfloat16_rn(j < M2 ? A[r * M2 + j] : 0.f);
-}
-__global__ void __launch_bounds__(256) k_tc_prep_F(const float* __restrict__ F, __nv_bfloat16* __restrict__ Fb, int h, int M2, int K) { PDL_SYNC();
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= h * TC_CH * TC_N * 8) return;
-    const int e = t & 7, n = (t >> 3) % TC_N, ch = (t / (8 * TC_N)) % TC_CH, a = t / (8 * TC_N * TC_CH);
-    const int j = ch * 8 + e;
-    Fb[t] = __float2bfloat16_rn((j < M2 && n < K) ? F[((int64_t)a * M2 + j) * K + n] : 0.f);
-}
-
-// One CTA = 128 threads; persistent over row tiles.  Thread 0 issues the MMAs; all four warps drain TMEM.
-__global__ void __launch_bounds__(128, 1) k_corr2d_tc(const __nv_bfloat16* __restrict__ Ab, const __nv_bfloat16* __restrict__ Fb,
-                                                      float* __restrict__ out, int64_t rows_total, int ntiles, int ld, CscDims d) { PDL_SYNC();
-    extern __shared__ __align__(1024) uint8_t tc_smem[];
-    const int R = TC_M + d.h - 1;                               // staged rows per tile
-    uint8_t* sA = tc_smem;                                      // [TC_CH][R][16 B]
-    uint8_t* sB = tc_smem + (((size_t)TC_CH * R * 16 + 127) & ~(size_t)127);        // [h][TC_CH][TC_N][16 B]
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint32_t s_tmem;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
-
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&s_tmem)), "n"(TC_N) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    // resident B operand (all of F, 12 x 14 x 32 x 16 B = 84 KB) and the zero chunk of A
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(Fb);
-        uint4* dst = reinterpret_cast<uint4*>(sB);
-        for (int i = tid; i < d.h * TC_CH * TC_N; i += 128) dst[i] = src[i];
-        uint4* z = reinterpret_cast<uint4*>(sA + (size_t)(TC_CH - 1) * R * 16);
-        for (int i = tid; i < R; i += 128) z[i] = make_uint4(0, 0, 0, 0);
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = s_tmem;
-    const uint32_t sA_addr = (uint32_t)__cvta_generic_to_shared(sA), sB_addr = (uint32_t)__cvta_generic_to_shared(sB);
-    // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=F32 (1<<4), A=BF16 (1<<7), B=BF16 (1<<10), both K-major,
-    // N>>3 at bit 17, M>>4 at bit 24
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-    uint32_t phase = 0;
-    const int nch = TC_CH - 1;                                  // data chunks per row (13)
-
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t r0 = (int64_t)tile * TC_M;
-        // stage rows r0 .. r0+R-1 as [chunk][row][16 B] (rows past the end of the buffer are zero padding in Ab)
-        for (int i = tid; i < R * nch; i += 128) {
-            const int row = i / nch, ch = i - row * nch;
-            const uint4 v = *reinterpret_cast<const uint4*>(Ab + (r0 + row) * ld + ch * 8);
-            *reinterpret_cast<uint4*>(sA + ((size_t)ch * R + row) * 16) = v;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t acc = 0;
-            for (int a = 0; a < d.h; ++a)
-                for (int t = 0; t < TC_CH / 2; ++t) {            // K = 16 per MMA = two 16-byte chunks
-                    const uint64_t da = tc_desc(sA_addr + ((uint32_t)(2 * t) * R + a) * 16, (uint32_t)R * 16, 128);
-                    const uint64_t db = tc_desc(sB_addr + ((uint32_t)(a * TC_CH + 2 * t) * TC_N) * 16, TC_N * 16, 128);
-                    tc_mma_bf16(tmem, da, db, idesc, acc);
-                    acc = 1;
-                }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
-        }
-        {   // wait for the accumulator
-            uint32_t done, spins = 0;
-            do {
-                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                             : "=r"(done) : "r"(bar), "r"(phase) : "memory");
-                if (!done && ++spins > (1u << 24)) __trap();         // never hang the device on a lost completion
-            } while (!done);
-            phase ^= 1;
-        }
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t v[32];
-        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-                       "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-                       "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                     : "r"(taddr) : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const int64_t r = r0 + warp * 32 + lane;                 // TMEM lane = output row of the tile
-        if (r < rows_total) {
-            const int64_t n = r / d.c;
-            const int i = (int)(r - n * d.c);
-            if (i < d.l) {                                       // rows i >= l are windows that run into the next sequence
-                float* o = out + (n * d.l + i) * d.K;
-                for (int k = 0; k < d.K; ++k) o[k] = __uint_as_float(v[k]);
-            }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                                         // TMEM and sA are reused by the next tile
-    }
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(TC_N) : "memory");
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Warp-specialised, double-buffered version of the same kernel (the one the tape launches):
-//   warp 0     producer : one 3-D TMA box copy (cp.async.bulk.tensor) per tile drops rows r0..r0+R-1 straight into the
-//                         [chunk][row][16 B] layout (tensor dims = {8 columns, rows, 13 chunks}, strides {208 B, 16 B})
-//   warp 1     MMA      : one lane issues the 84 tcgen05.mma of a tile, then commits to "stage free" and "accumulator full"
-//   warps 2-5  epilogue : tcgen05.ld of their TMEM lane quarter, store, release the accumulator
-// Two shared-memory stages and two 32-column TMEM accumulators let tile t+1 load and multiply while tile t drains.
-// ---------------------------------------------------------------------------------------------------------------------
-#include <cuda.h>
-
 __device__ __forceinline__ void tc_bar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done, spins = 0;
     do {
@@ -157,127 +37,6 @@ __device__ __forceinline__ void tc_bar_wait(uint32_t bar, uint32_t parity) {
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (!done && ++spins > (1u << 24)) __trap();             // never hang the device on a lost completion
     } while (!done);
-}
-
-__global__ void __launch_bounds__(192, 1) k_corr2d_tc2(const __grid_constant__ CUtensorMap tmapA, const __nv_bfloat16* __restrict__ Fb,
-                                                       float* __restrict__ out, int64_t rows_total, int ntiles, CscDims d) { PDL_SYNC();
-    extern __shared__ __align__(1024) uint8_t tc_smem[];
-    const int R = TC_M + d.h - 1;
-    const uint32_t stage_bytes = (uint32_t)(((size_t)TC_CH * R * 16 + 1023) & ~(size_t)1023);
-    uint8_t* sA0 = tc_smem;
-    uint8_t* sB = tc_smem + 2 * (size_t)stage_bytes;
-    __shared__ __align__(8) uint64_t s_bars[8];                   // full[2], empty[2], accfull[2], accempty[2]
-    __shared__ uint32_t s_tmem;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    auto bar = [&](int i) { return (uint32_t)__cvta_generic_to_shared(&s_bars[i]); };
-
-    if (tid == 0) {
-        for (int i = 0; i < 6; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(i)) : "memory");
-        for (int i = 6; i < 8; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" :: "r"(bar(i)) : "memory");   // 4 epilogue warps
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&s_tmem)), "n"(2 * TC_N) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    {   // resident B operand and the zero chunk of both A stages
-        const uint4* src = reinterpret_cast<const uint4*>(Fb);
-        uint4* dst = reinterpret_cast<uint4*>(sB);
-        for (int i = tid; i < d.h * TC_CH * TC_N; i += blockDim.x) dst[i] = src[i];
-        for (int st = 0; st < 2; ++st) {
-            uint4* z = reinterpret_cast<uint4*>(sA0 + (size_t)st * stage_bytes + (size_t)(TC_CH - 1) * R * 16);
-            for (int i = tid; i < R; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
-        }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = s_tmem;
-    const uint32_t sA_addr = (uint32_t)__cvta_generic_to_shared(sA0), sB_addr = (uint32_t)__cvta_generic_to_shared(sB);
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-    const uint32_t tx_bytes = (uint32_t)(TC_CH - 1) * R * 16;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            int it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
-                tc_bar_wait(bar(2 + st), ph ^ 1);                                        // stage free
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar(st)), "r"(tx_bytes) : "memory");
-                const int32_t c0 = 0, c1 = tile * TC_M, c2 = 0;
-                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                             :: "r"(sA_addr + st * stage_bytes), "l"(&tmapA), "r"(c0), "r"(c1), "r"(c2), "r"(bar(st)) : "memory");
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            int it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
-                tc_bar_wait(bar(st), ph);                                                // operands landed
-                tc_bar_wait(bar(6 + st), ph ^ 1);                                        // accumulator drained
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_base = sA_addr + st * stage_bytes;
-                uint32_t acc = 0;
-                for (int a = 0; a < d.h; ++a)
-                    for (int t = 0; t < TC_CH / 2; ++t) {
-                        const uint64_t da = tc_desc(a_base + ((uint32_t)(2 * t) * R + a) * 16, (uint32_t)R * 16, 128);
-                        const uint64_t db = tc_desc(sB_addr + ((uint32_t)(a * TC_CH + 2 * t) * TC_N) * 16, TC_N * 16, 128);
-                        tc_mma_bf16(tmem + st * TC_N, da, db, idesc, acc);
-                        acc = 1;
-                    }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar(2 + st)) : "memory");
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar(4 + st)) : "memory");
-            }
-        }
-    } else {
-        const int q = warp & 3;                                                           // TMEM lane quarter this warp may read
-        int it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
-            tc_bar_wait(bar(4 + st), ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t v[32];
-            const uint32_t taddr = tmem + st * TC_N + ((uint32_t)(q * 32) << 16);
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-                           "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-                           "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                         : "r"(taddr) : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar(6 + st)) : "memory");    // accumulator may be overwritten
-            const int64_t r = (int64_t)tile * TC_M + q * 32 + lane;
-            if (r < rows_total) {
-                const int64_t n = r / d.c;
-                const int i = (int)(r - n * d.c);
-                if (i < d.l) {
-                    float* o = out + (n * d.l + i) * d.K;
-                    for (int k = 0; k < d.K; ++k) o[k] = __uint_as_float(v[k]);
-                }
-            }
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(2 * TC_N) : "memory");
-}
-
-// host: tensor map of the BF16 row buffer viewed as {8 columns, rows, 13 chunks}
-typedef CUresult (*tc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static inline int tc_make_tmap(CUtensorMap* tm, void* base, uint64_t rows_alloc, int ld, int R) {
-    void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -1;
-    const cuuint64_t gdim[3] = {8, rows_alloc, (cuuint64_t)(TC_CH - 1)};
-    const cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, 16};
-    const cuuint32_t box[3] = {8, (cuuint32_t)R, (cuuint32_t)(TC_CH - 1)};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = ((tc_encode_fn)fn)(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

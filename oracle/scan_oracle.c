@@ -111,13 +111,15 @@ static inline int is_hit(f16 s, const uint16_t* thresh, int k) {
 /* union_ranges / push_ranges! (inference/_h4_overlap_ratio.jl:40-56) restated literally on
  * [start, stop] pairs.  `for i in eachindex(@view ranges[2:end])` runs i = 1..n-1 but indexes the
  * UNSLICED sorted array, so ranges[1] is merged with itself and ranges[n] is never visited.     */
-static int64_t union_ranges_total(int64_t* starts, int n, int len) {
+static int cmp_i64(const void* a, const void* b) { const int64_t x = *(const int64_t*)a, y = *(const int64_t*)b; return (x > y) - (x < y); }
+static int64_t union_ranges_total(int64_t* starts, int64_t n, int len) {
     if (n == 0) return 0;
     /* sort(ranges, by = x->x[1]) — stable; all ranges have the same length so stability is moot */
-    for (int i = 1; i < n; ++i) { int64_t v = starts[i]; int j = i - 1; while (j >= 0 && starts[j] > v) { starts[j + 1] = starts[j]; --j; } starts[j + 1] = v; }
+    if (n <= 64) { for (int64_t i = 1; i < n; ++i) { int64_t v = starts[i]; int64_t j = i - 1; while (j >= 0 && starts[j] > v) { starts[j + 1] = starts[j]; --j; } starts[j + 1] = v; } }
+    else qsort(starts, (size_t)n, sizeof(int64_t), cmp_i64);
     int64_t total = 0;
     int64_t cur_s = starts[0], cur_e = starts[0] + len - 1;        /* _ranges_ = [ranges[1]] */
-    for (int i = 1; i <= n - 1; ++i) {                              /* i in eachindex(view) = 1..n-1 */
+    for (int64_t i = 1; i <= n - 1; ++i) {                          /* i in eachindex(view) = 1..n-1 */
         const int64_t rs = starts[i - 1], re = starts[i - 1] + len - 1;   /* ranges[i] (1-based) */
         if (cur_e >= rs) { cur_e = re; }                            /* _ranges_[end] = _ranges_[end][1]:ranges[i][end] */
         else { total += cur_e - cur_s + 1; cur_s = rs; cur_e = re; }       /* push!(_ranges_, ranges[i]) */
@@ -126,9 +128,9 @@ static int64_t union_ranges_total(int64_t* starts, int n, int len) {
     return total;                                                   /* get_total_occupied_positions (:71-79) */
 }
 
-static int64_t true_union_total(const int64_t* sorted_starts, int n, int len) {
+static int64_t true_union_total(const int64_t* sorted_starts, int64_t n, int len) {
     int64_t total = 0, cu = -1;   /* cu = last covered position */
-    for (int i = 0; i < n; ++i) {
+    for (int64_t i = 0; i < n; ++i) {
         int64_t s = sorted_starts[i], e = s + len - 1;
         if (s > cu) total += len; else if (e > cu) total += e - cu;
         if (e > cu) cu = e;
@@ -152,36 +154,43 @@ int64_t oracle_scan(const uint16_t* pwms, const int64_t* lens, int K, int maxlen
     int64_t* per_seq = (int64_t*)calloc((size_t)N + 1, sizeof(int64_t));
     int64_t* cnt = counts ? (int64_t*)calloc((size_t)K * 4, sizeof(int64_t)) : NULL;
 
-    /* pass 1: count hits per sequence (for placement) and accumulate counts */
+    /* pass 1: count hits per sequence (for placement) and accumulate counts.  Work items are (sequence, motif) pairs so that one
+     * chromosome-length sequence still uses every thread; all sums are integers, hence independent of the schedule. */
+    const int64_t items = N * (int64_t)K;
     #pragma omp parallel
     {
         int64_t* local = cnt ? (int64_t*)calloc((size_t)K * 4, sizeof(int64_t)) : NULL;
-        int64_t* pos_buf = (int64_t*)malloc(sizeof(int64_t) * 2 * (size_t)(Lb + 1));
-        int64_t* tmp = (int64_t*)malloc(sizeof(int64_t) * 2 * (size_t)(Lb + 1));
-        #pragma omp for schedule(dynamic, 64)
-        for (int64_t n = 0; n < N; ++n) {
+        size_t cap = (size_t)(2 * (Lb + 1) < (1 << 20) ? 2 * (Lb + 1) : (1 << 20));      /* grows on demand (thresholded scans of long sequences are sparse) */
+        int64_t* pos_buf = (int64_t*)malloc(sizeof(int64_t) * cap);
+        int64_t* tmp = (int64_t*)malloc(sizeof(int64_t) * cap);
+        #pragma omp for schedule(dynamic, 16)
+        for (int64_t it = 0; it < items; ++it) {
+            const int64_t n = it / K;
+            const int k = (int)(it - n * K);
             const uint8_t* b = bases + n * Lb;
-            int64_t nh_seq = 0;
-            for (int k = 0; k < K; ++k) {
-                const int len = tabs[k].len;
-                int np = 0;
-                for (int rc = 0; rc < 2; ++rc) {
-                    if (!((strands >> rc) & 1)) continue;
-                    for (int64_t l = 0; l + len <= Lb; ++l)
-                        if (is_hit(score_tab(&tabs[k], rc, b, l), thresh, k)) pos_buf[np++] = l;
-                }
-                nh_seq += np;
-                if (local && np) {
-                    /* positions[m][n] = forward hits then rc hits */
-                    memcpy(tmp, pos_buf, sizeof(int64_t) * (size_t)np);
-                    local[k * 4 + 0] += np;
-                    local[k * 4 + 2] += union_ranges_total(tmp, np, len);      /* sorts tmp */
-                    int uq = 0; for (int i = 0; i < np; ++i) if (i == 0 || tmp[i] != tmp[i - 1]) ++uq;
-                    local[k * 4 + 1] += uq;                                    /* unique(positions) */
-                    local[k * 4 + 3] += true_union_total(tmp, np, len);
-                }
+            const int len = tabs[k].len;
+            int64_t np = 0;
+            for (int rc = 0; rc < 2; ++rc) {
+                if (!((strands >> rc) & 1)) continue;
+                for (int64_t l = 0; l + len <= Lb; ++l)
+                    if (is_hit(score_tab(&tabs[k], rc, b, l), thresh, k)) {
+                        if ((size_t)np == cap) { cap *= 2; pos_buf = (int64_t*)realloc(pos_buf, sizeof(int64_t) * cap); tmp = (int64_t*)realloc(tmp, sizeof(int64_t) * cap); }
+                        pos_buf[np++] = l;
+                    }
             }
-            per_seq[n + 1] = nh_seq;
+            if (np) {
+                #pragma omp atomic
+                per_seq[n + 1] += np;
+            }
+            if (local && np) {
+                /* positions[m][n] = forward hits then rc hits */
+                memcpy(tmp, pos_buf, sizeof(int64_t) * (size_t)np);
+                local[k * 4 + 0] += np;
+                local[k * 4 + 2] += union_ranges_total(tmp, np, len);      /* sorts tmp */
+                int64_t uq = 0; for (int64_t i = 0; i < np; ++i) if (i == 0 || tmp[i] != tmp[i - 1]) ++uq;
+                local[k * 4 + 1] += uq;                                    /* unique(positions) */
+                local[k * 4 + 3] += true_union_total(tmp, np, len);
+            }
         }
         if (local) {
             #pragma omp critical
@@ -232,3 +241,9 @@ uint16_t oracle_score_tab(const uint16_t* pwms, const int64_t* lens, int K, int 
 uint16_t oracle_score_literal(const uint16_t* pwms, const int64_t* lens, int K, int k, int rc, const uint8_t* bases, int64_t l) {
     return h2bits(score_literal(pwms, K, k, (int)lens[k], rc, bases, l));
 }
+
+/* thread control for the timed CPU baseline: torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently make the
+ * "all host cores" reference arm single-threaded */
+#include <omp.h>
+void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int oracle_max_threads(void) { return omp_get_max_threads(); }

@@ -31,8 +31,18 @@ def lib():
         for f in (L.oracle_score_tab, L.oracle_score_literal):
             f.restype = C.c_uint16
             f.argtypes = [p, p, i32, i32, i32, p, i64]
+        L.oracle_set_threads.restype = None
+        L.oracle_set_threads.argtypes = [i32]
+        L.oracle_max_threads.restype = i32
+        L.oracle_max_threads.argtypes = []
         _lib = L
     return _lib
+
+
+def set_threads(n: int) -> int:
+    """OpenMP threads of the C oracle (torchrun exports OMP_NUM_THREADS=1); returns what OpenMP will use."""
+    lib().oracle_set_threads(int(n))
+    return int(lib().oracle_max_threads())
 
 
 def _p(a):

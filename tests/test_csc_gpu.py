@@ -294,3 +294,29 @@ def test_non_default_hyperparameters_match_oracle(ctx, hpd, Lb, G):
     og_mean = og_sum / G
     assert np.abs(g - og_mean).max() <= 2e-4 * np.abs(og_mean).max()
     m.free(); seqs.free()
+
+
+def test_per_step_parity_on_training_steps_1_2_3_1000(ctx):
+    """per-step loss / gradient parity against the oracle on optimiser steps 1, 2, 3 and 1000 of a real training
+    run (train.jl:40-46).  'Per step' = the oracle evaluates the SAME batch at the parameters the library holds before that step, so the
+    check covers the parameter regions training actually reaches (sparser F, sharper D), not only the initialisation."""
+    hp, ohp, a, seqs, flat = _setup(ctx, 2000, 100, 2)
+    codes = so.ascii_to_codes(a)
+    m = mb._lib.CscModel(ctx, hp, 100)
+    m.set_params(flat)
+    n = m.n_trainable
+    rng = np.random.default_rng(0)
+    losses = {}
+    for step in range(1, 1001):
+        idx = rng.permutation(2000)[:6]
+        if step in (1, 2, 3, 1000):
+            p = m.get_params()
+            loss, g = m.loss_grad(seqs, idx)
+            oloss, og, _ = co.loss_and_grad(codes[idx], p, ohp)
+            assert loss[0, 0] == pytest.approx(oloss, rel=1e-5), step
+            assert np.abs(g - og[:n]).max() <= 2e-4 * np.abs(og[:n]).max(), step
+            losses[step] = float(loss[0, 0])
+        m.step_begin(seqs, idx)
+        m.adabelief_step()
+    assert losses[1000] < losses[1]                                          # and the run did train
+    m.free(); seqs.free()

@@ -69,8 +69,8 @@ def test_shuffle_long_sequence_is_a_permutation(ctx):
 
 
 def test_overflowing_hit_list_is_held_not_rescanned(ctx):
-    a = synth.planted_gapped(400, 100, 2)
-    ms = synth.motifs_from_count_matrices(synth.random_count_matrices(6, 8, 20, 1))
+    a = synth.planted_gapped(4000, 100, 2)
+    ms = synth.motifs_from_count_matrices(synth.random_count_matrices(40, 8, 20, 1))
     pw, lens = inference.pack_pwms(ms), ms.lens
     seqs = ctx.seqs_from_ascii(a)
     hits, counts = ctx.scan(seqs, pw, lens)                             # default capacity 65 536 < number of hits: one scan + take_hits
