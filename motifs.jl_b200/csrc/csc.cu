@@ -14,6 +14,7 @@
 #include "csc_kernels.cuh"
 #include "tc_corr2d.cuh"
 #include "csc_batched.cuh"
+#include "csc_fused.cuh"
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
@@ -77,6 +78,12 @@ struct mb200_csc {
     bool batched = false; float* Ft_scratch = nullptr;      // one-CTA-per-sequence kernels (csc_batched.cuh) for many-group shapes      // tap-grouped kernel (k_corr2d_tc3)
     cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr; bool graph_ok = false;
     const uint32_t* graph_words = nullptr; int64_t graph_rowwords = 0;
+    // fused persistent forward kernel (csc_fused.cuh): plan = arena offsets of the tape's buffers, sync area, eligibility
+    FzPlan fz{}; bool fused = false, no_fused = false; size_t fz_smem = 0; int fz_nmed = 0;
+    uint8_t* fz_sync = nullptr; size_t fz_sync_bytes = 0, fz_zero_bytes = 0; FzBufs fzb{};
+    bool fused_bwd = false; size_t fzb_smem = 0; FzBwd fzw{}; float* fz_bwd_buf = nullptr; unsigned int* fz_err_host = nullptr;
+    size_t op_xyz_begin = 0, op_xyz_end = 0;                // tape ops of the ADMM_XYZ passes: [begin, end)
+    Buf zero_al{}, zero_be{};
 };
 
 namespace {
@@ -271,7 +278,7 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
     };
     const int mask_cap = 2 * ((d.B * d.c + CL - 1) / CL) * d.M;      // floats of dynamic smem per CTA: its slice of rows, z and y
     s->mask_cap = mask_cap;
-    auto op_mask_scale = [&](Buf z, Buf y, Buf zy, const char* nm) {
+    auto op_mask_scale = [&](Buf z, Buf y, Buf zy, const char* nm) -> Buf {
         Buf med = B.alloc(d.G);
         // one 8-CTA cluster per group minimises latency (training, few groups); with many groups (batched code retrieval) one CTA per
         // group fills the machine better: 148 groups in flight instead of 18 clusters
@@ -284,11 +291,14 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
                      },
                      [=](cudaStream_t q) { lk(k_mask_scale_bwd, nblk(nZY, 256), 256, 0, q, S->data + z.off, S->data + y.off, S->data + med.off, S->grad + zy.off, S->grad + z.off, S->grad + y.off, d); },
                      nm});
+        return med;
     };
     // returns nothing; registers the data list of xout; `glist` = list id for d g (allocated by the caller)
+    size_t last_bo = 0; int last_xl = 0;
     auto op_topq = [&](const Buf* xprev, Buf g, int i_om, float coef, int om_train, Buf xout, int glist, const char* nm) {
         const size_t bo = B.bit_cursor; B.bit_cursor += (size_t)nX;
         const int xl = B.n_lists++;
+        last_bo = bo; last_xl = xl;
         xlist[xout.off] = xl;
         const bool hp_ = xprev != nullptr; const Buf xp = hp_ ? *xprev : Buf{};
         const size_t smem = (size_t)d.l * d.K * 4;
@@ -303,21 +313,33 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
                  [=](cudaStream_t q) { lk(k_warm_zy_bwd, nblk(nZ, 256), 256, 0, q, S->bases, SCP, S->i_eta_w, S->data + z.off, S->data + y.off, S->grad + z.off, S->grad + y.off, S->grad + De.off, d); },
                  "warm_zy"});
     Buf zy = B.alloc(nZY);
-    op_mask_scale(z, y, zy, "warm_mask");
+    FzPlan& FP = s->fz;
+    memset(&FP, 0, sizeof FP);
+    FP.npx = d.npx; FP.npd = d.npd; FP.i_eta_w = s->i_eta_w; FP.i_lam_w = s->i_lam_w; FP.i_om_w = s->i_om_w; FP.forward_only = xyz_only ? 1 : 0;
+    FP.sc = (int64_t)sc.off; FP.De = (int64_t)De.off; FP.Fe = (int64_t)Fe.off; FP.z0 = (int64_t)z.off; FP.y0 = (int64_t)y.off; FP.zy0 = (int64_t)zy.off;
+    FP.med0 = (int64_t)op_mask_scale(z, y, zy, "warm_mask").off;
     Buf g0 = B.alloc(nX), x = B.alloc(nX);
     { const int gl = B.n_lists++; op_corr2d(zy, Fe, 0, g0, gl, "warm_corr2d"); op_topq(nullptr, g0, s->i_om_w, 1.f, 0, x, gl, "warm_topq"); }
+    FP.g0 = (int64_t)g0.off; FP.x0 = (int64_t)x.off; FP.bits0 = (int64_t)last_bo; FP.xl0 = last_xl;
+    int cur_xl = last_xl;
     Buf fx = B.alloc(nZY);
+    FP.fx0 = (int64_t)fx.off;
     op_tconv(x, Fe, 0, fx, "warm_tconv");
     Buf al{}, be{};
     bool have_dual = false;
 
     // ---- ADMM_XYZ passes (model.jl:256-268, 347-355) ---------------------------------------------
+    s->op_xyz_begin = T.size();
     for (int n = 0; n < d.npx; ++n) {
         const int i_eta = s->i_eta0 + n, i_lam = s->i_lam0 + n, i_rho = s->i_rho0 + n, i_om = s->i_om0 + n;
         Buf rec = B.alloc(nS), gz = B.alloc(nZ), gy = B.alloc(nZ), zn = B.alloc(nZ), yn = B.alloc(nZ);
         op_recon(z, y, De, 0, rec, "recon");
         op_corr_sig(rec, -1.f, De, 0, gz, gy, "corr_sig");
         if (!have_dual) { al = B.alloc(nZ); be = B.alloc(nZ); }      // zero duals (model.jl:338): arenas are zero-filled, never written
+        FzPass* XP = n < FZ_MAXPX ? &FP.px[n] : nullptr;
+        if (XP) { XP->z_in = (int64_t)z.off; XP->y_in = (int64_t)y.off; XP->fx_in = (int64_t)fx.off; XP->al_in = (int64_t)al.off; XP->be_in = (int64_t)be.off;
+                  XP->rec = (int64_t)rec.off; XP->gz = (int64_t)gz.off; XP->gy = (int64_t)gy.off; XP->z_out = (int64_t)zn.off; XP->y_out = (int64_t)yn.off;
+                  XP->i_eta = i_eta; XP->i_lam = i_lam; XP->i_rho = i_rho; XP->i_om = i_om; XP->x_in = (int64_t)x.off; XP->xl_in = cur_xl; XP->al_out = -1; XP->be_out = -1; }
         {
             const Buf zc = z, yc = y, fxc = fx, alc = al, bec = be;
             T.push_back({[=](cudaStream_t q) { lk(k_zy_update, nblk(nZ, 256), 256, 0, q, S->data + zc.off, S->data + yc.off, S->data + gz.off, S->data + gy.off, S->data + fxc.off, S->data + alc.off, S->data + bec.off, SCP, i_eta, i_lam, i_rho, S->data + zn.off, S->data + yn.off, d); },
@@ -326,7 +348,7 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         }
         z = zn; y = yn;
         Buf zy2 = B.alloc(nZY), dd = B.alloc(nZY), g = B.alloc(nX), xn = B.alloc(nX), fxn = B.alloc(nZY);
-        op_mask_scale(z, y, zy2, "mask_scale");
+        { const Buf md = op_mask_scale(z, y, zy2, "mask_scale"); if (XP) XP->med = (int64_t)md.off; }
         {
             const Buf fxc = fx, alc = al, bec = be;
             T.push_back({[=](cudaStream_t q) { lk(k_d_build, nblk(nZY, 256), 256, 0, q, S->data + fxc.off, S->data + zy2.off, S->data + alc.off, S->data + bec.off, S->data + dd.off, d); },
@@ -336,6 +358,8 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         { const int gl = B.n_lists++; op_corr2d(dd, Fe, 0, g, gl, "corr2d"); op_topq(&x, g, i_om, -1.f, 1, xn, gl, "topq"); }
         s->named["g_last"] = g;
         x = xn;
+        if (XP) { XP->dd = (int64_t)dd.off; XP->g = (int64_t)g.off; XP->x_out = (int64_t)xn.off; XP->bits = (int64_t)last_bo; XP->xl_out = last_xl; XP->fx_out = (int64_t)fxn.off; }
+        cur_xl = last_xl;
         op_tconv(x, Fe, 0, fxn, "tconv");
         fx = fxn;
         if (n + 1 < d.npx) {      // the duals after the last pass are never read (model.jl:356 returns Z, Y, X)
@@ -345,15 +369,18 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
                          [=](cudaStream_t q) { lk(k_dual_bwd, nblk(nZ, 256), 256, 0, q, S->grad + an.off, S->grad + bn.off, S->grad + alc.off, S->grad + bec.off, S->grad + fxc.off, S->grad + zc.off, S->grad + yc.off, d); },
                          "dual"});
             al = an; be = bn;
+            if (XP) { XP->al_out = (int64_t)an.off; XP->be_out = (int64_t)bn.off; }
         }
         have_dual = true;
     }
+    s->op_xyz_end = T.size();
     s->named["z"] = z; s->named["y"] = y; s->named["x"] = x;
     if (xyz_only) { s->arena = B.cursor; s->bits_n = B.bit_cursor; s->n_lists = B.n_lists; return; }
 
     // ---- ADMM_DF (model.jl:362-373) ---------------------------------------------------------------
     Buf zyF = B.alloc(nZY, "zy");
-    op_mask_scale(z, y, zyF, "df_mask");
+    FP.zyF = (int64_t)zyF.off;
+    FP.medF = (int64_t)op_mask_scale(z, y, zyF, "df_mask").off;
     Buf Dc = De, Fc = Fe; int64_t Dgs = 0, Fgs = 0;
     Buf theta{}; bool have_theta = false;
     for (int n = 0; n < d.npd; ++n) {
@@ -363,6 +390,9 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         T.push_back({nullptr, nullptr, "fork", 0, 1});
         const size_t d_chain_begin = T.size();
         Buf rec = B.alloc(nS), Gm = B.alloc((size_t)d.G * nD), Dn = B.alloc((size_t)d.G * nD);
+        FzDf* YP = n < FZ_MAXPD ? &FP.df[n] : nullptr;
+        if (YP) { YP->D_in = (int64_t)Dc.off; YP->D_in_gs = (int32_t)Dgs; YP->F_in = (int64_t)Fc.off; YP->F_in_gs = (int32_t)Fgs; YP->rec = (int64_t)rec.off; YP->Gm = (int64_t)Gm.off;
+                  YP->Dn = (int64_t)Dn.off; YP->i_mu = i_mu; YP->i_kap = i_kap; YP->i_kaps = i_kaps; }
         op_recon(z, y, Dc, Dgs, rec, "df_recon");
         op_dgrad(z, y, rec, +1.f, Gm, "df_dgrad");                      // R = sumZD + sumYRD + S  ('+S': model.jl:282-285)
         {
@@ -375,6 +405,7 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         for (size_t ti = d_chain_begin; ti < T.size(); ++ti) T[ti].branch = 1;
         // update_F
         Buf fxc = B.alloc(nZY), e = B.alloc(nZY), Fg = B.alloc((size_t)d.G * nF), Fn = B.alloc((size_t)d.G * nF), nrm = B.alloc((size_t)d.G * d.K);
+        if (YP) { YP->e = (int64_t)e.off; YP->Fg = (int64_t)Fg.off; YP->Fn = (int64_t)Fn.off; YP->nrm = (int64_t)nrm.off; }
         op_tconv(x, Fc, Fgs, fxc, "df_tconv");
         {
             const Buf th = theta; const bool ht = have_theta;
@@ -400,11 +431,13 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
                          [=](cudaStream_t q) { lk(k_sub3_bwd, nblk(nZY, 256), 256, 0, q, S->grad + thn.off, S->grad + fx2.off, S->grad + zyF.off, ht ? S->grad + th.off : nullptr, +1.f, nZY); },
                          "theta"});
             theta = thn; have_theta = true;
+            if (YP) { YP->thn = (int64_t)thn.off; YP->has_theta_out = 1; }
         }
     }
     s->named["D"] = Dc; s->named["F"] = Fc;
     // ---- loss (model.jl:310-325) ------------------------------------------------------------------
     Buf recL = B.alloc(nS), fxL = B.alloc(nZY);
+    FP.recL = (int64_t)recL.off; FP.fxL = (int64_t)fxL.off; FP.loss = (int64_t)s->loss.off;
     op_recon(z, y, Dc, Dgs, recL, "loss_recon");
     op_tconv(x, Fc, Fgs, fxL, "loss_tconv");
     {
@@ -456,6 +489,60 @@ static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
         s->tc_smem3 = TC3_STAGES * ((((size_t)TC_CH * R * 16) + 1023) & ~(size_t)1023) + (size_t)s->d.h * TC_CH * s->d.K * 16 + 4 * 3 * (TC_J - 1) * (TC_J - 1) * 24 * 4;
         MB_CUDA(ctx, cudaFuncSetAttribute(k_corr2d_tc3<24, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tc_smem3));
     }
+    // ---- fused persistent forward kernel (csc_fused.cuh): the reference's own shapes, all clusters co-resident ----
+    {
+        const CscDims& d = s->d;
+        s->fused = false;
+        s->fz_smem = fz::fz_smem_bytes(d.Lb);
+        s->fz_nmed = d.npx + 2;
+        const bool shape_ok = d.M == FZ_M && d.K == FZ_K && d.h == FZ_H && d.fl == FZ_FL && d.npx <= FZ_MAXPX && d.npd <= FZ_MAXPD &&
+                              d.B * LIST_CAP <= FZ_THREADS && d.B * FZ_CL >= FZ_K && d.c >= FZ_CL && d.l >= 1 && fz::fz_rows(d.c) <= 32;
+        if (!s->no_fused && !s->tensor && shape_ok && s->fz_smem <= ctx->smem_optin) {
+            cudaError_t e = cudaFuncSetAttribute(k_csc_fused_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->fz_smem);
+            int nclus = 0;
+            if (e == cudaSuccess) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)(d.NS * FZ_CL)); cfg.blockDim = dim3(FZ_THREADS); cfg.dynamicSmemBytes = s->fz_smem;
+                e = cudaOccupancyMaxActiveClusters(&nclus, k_csc_fused_fwd, &cfg);
+            }
+            if (e != cudaSuccess) { cudaGetLastError(); nclus = 0; }
+            s->fused = nclus >= d.NS;                      // every cluster must be resident: the kernel synchronises across them
+        }
+        if (s->fused) {
+            const size_t nmed = (size_t)s->fz_nmed, G = (size_t)d.G;
+            const size_t o_bar = 0, o_ctl = 256 + ((G * 4 + 255) & ~(size_t)255), o_hist = o_ctl + ((G * nmed * 16 + 255) & ~(size_t)255);
+            const size_t o_cand = o_hist + G * nmed * FZ_NHIST * FZ_BINS * 4;
+            const size_t o_part = o_cand + G * nmed * FZ_CAND * 4;
+            s->fz_zero_bytes = o_cand;
+            s->fz_sync_bytes = o_part + G * (size_t)d.B * FZ_CL * FZ_PART * 4;
+            MB_CUDA(ctx, cudaMalloc(&s->fz_sync, s->fz_sync_bytes));
+            MB_CUDA(ctx, cudaMemset(s->fz_sync, 0, s->fz_sync_bytes));
+            FzBufs& b = s->fzb;
+            b.data = s->data; b.bits = s->bits; b.lcnt = s->lcnt; b.lidx = s->lidx; b.lval = s->lval; b.bases = s->bases;
+            b.bar = (unsigned int*)(s->fz_sync + o_bar); b.cctl = (unsigned int*)(s->fz_sync + o_ctl); b.hist = (unsigned int*)(s->fz_sync + o_hist);
+            b.cand = (float*)(s->fz_sync + o_cand); b.part = (float*)(s->fz_sync + o_part);
+            // reverse pass of the XYZ passes as one kernel (training handles only)
+            s->fzb_smem = fz::fzb_smem_bytes(d.Lb);
+            if (!s->xyz_only && s->fzb_smem <= ctx->smem_optin &&
+                cudaFuncSetAttribute(k_csc_fused_bwd_xyz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->fzb_smem) == cudaSuccess) {
+                int nclus = 0;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)(d.NS * FZ_CL)); cfg.blockDim = dim3(FZ_THREADS); cfg.dynamicSmemBytes = s->fzb_smem;
+                if (cudaOccupancyMaxActiveClusters(&nclus, k_csc_fused_bwd_xyz, &cfg) != cudaSuccess) { cudaGetLastError(); nclus = 0; }
+                s->fused_bwd = nclus >= d.NS;
+            }
+            if (s->fused_bwd) {
+                const size_t nF = (size_t)d.h * d.M2 * d.K, nD = (size_t)d.f_len * d.M;
+                const size_t n_dFp = G * (size_t)d.B * FZ_CL * nF, n_xch = (size_t)d.NS * FZ_KCAP, n_gsum = G * (nF + nD + 64);
+                MB_CUDA(ctx, cudaMalloc(&s->fz_bwd_buf, (n_dFp + n_xch + n_gsum + 64) * 4));
+                MB_CUDA(ctx, cudaMemset(s->fz_bwd_buf, 0, (n_dFp + n_xch + n_gsum + 64) * 4));
+                s->fzw.grad = s->grad; s->fzw.dFp = s->fz_bwd_buf; s->fzw.xch = s->fz_bwd_buf + n_dFp; s->fzw.gsum = s->fzw.xch + n_xch;
+                s->fzw.err = (unsigned int*)(s->fzw.gsum + n_gsum);
+                MB_CUDA(ctx, cudaMallocHost(&s->fz_err_host, 64));
+                *s->fz_err_host = 0;
+            }
+        }
+    }
     MB_CUDA(ctx, cudaStreamCreateWithFlags(&s->aux, cudaStreamNonBlocking));
     MB_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
     MB_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
@@ -488,6 +575,8 @@ extern "C" int32_t mb200_csc_create(mb200_ctx* ctx, const mb200_hparams* hp, int
     if (l < 1 || (int64_t)l * hp->K < hp->q) MB_FAIL(ctx, MB200_E_INVALID, "csc: sequence length %lld too short for filter_len %d, h %d, q %d", (long long)Lb, hp->filter_len, hp->h, hp->q);
     MB_CUDA(ctx, cudaSetDevice(ctx->device));
     mb200_csc* s = new mb200_csc();
+    s->no_fused = (forward_only & 0x100) != 0;            // MB200_CSC_NO_FUSED: keep the kernel-per-op tape (A/B tests of the fused step)
+    forward_only &= 0xff;
     s->ctx = ctx; s->hp = *hp; s->xyz_only = forward_only != 0;
     s->tensor = forward_only == 2;
     if (s->tensor && (hp->K != 24 || hp->h != 3 * TC_J || 2 * hp->M > (TC_CH - 1) * 8)) { delete s; MB_FAIL(ctx, MB200_E_UNSUPPORTED, "csc: the tensor-core path is built for K = 24, h = %d and 2M <= %d", 3 * TC_J, (TC_CH - 1) * 8); }
@@ -519,7 +608,7 @@ extern "C" int32_t mb200_csc_destroy(mb200_ctx* ctx, mb200_csc* s) {
     if (s->graph) cudaGraphDestroy(s->graph);
     if (s->aux) cudaStreamDestroy(s->aux);
     if (s->ev_fork) { cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_join); cudaEventDestroy(s->ev_fork2); cudaEventDestroy(s->ev_join2); }
-    cudaFree(s->p_raw); cudaFree(s->g_raw); cudaFree(s->mt); cudaFree(s->st); cudaFree(s->data); cudaFree(s->grad); cudaFree(s->bits); cudaFree(s->lcnt); cudaFree(s->lidx); cudaFree(s->lval); cudaFree(s->tc_A); cudaFree(s->tc_F); cudaFree(s->Ft_scratch);
+    cudaFree(s->p_raw); cudaFree(s->g_raw); cudaFree(s->mt); cudaFree(s->st); cudaFree(s->data); cudaFree(s->grad); cudaFree(s->bits); cudaFree(s->lcnt); cudaFree(s->lidx); cudaFree(s->lval); cudaFree(s->tc_A); cudaFree(s->tc_F); cudaFree(s->Ft_scratch); cudaFree(s->fz_sync); cudaFree(s->fz_bwd_buf); if (s->fz_err_host) cudaFreeHost(s->fz_err_host);
     cudaFree(s->bases); cudaFree(s->idx_dev); cudaFreeHost(s->idx_pinned); cudaFree(s->idx_identity_dev); cudaFree(s->batch_words); cudaFreeHost(s->batch_pinned); cudaFreeHost(s->host_out);
     delete s;
     return MB200_OK;
@@ -605,11 +694,45 @@ static void run_op(mb200_csc* s, Op& op, bool fwd, cudaStream_t q) {
 static void enqueue_step(mb200_csc* s, const uint32_t* words, int64_t rowwords, const int64_t* idx_dev, bool backward, cudaStream_t q) {
     const CscDims d = s->d;
     lk(k_unpack_bases, nblk((int64_t)d.NS * d.Lb, 256), 256, 0, q, words, rowwords, idx_dev, s->bases, d);
+    if (s->fused) {
+        // parameter preparation (three small kernels), then the whole forward pass as ONE persistent cooperative kernel
+        s->tape[0].fwd(q);
+        cudaMemsetAsync(s->fz_sync, 0, s->fz_zero_bytes, q);
+        s->fzb.bases = s->bases; s->fzb.data = s->data; s->fzb.bits = s->bits; s->fzb.lcnt = s->lcnt; s->fzb.lidx = s->lidx; s->fzb.lval = s->lval;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(d.NS * FZ_CL)); cfg.blockDim = dim3(FZ_THREADS); cfg.dynamicSmemBytes = s->fz_smem; cfg.stream = q;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, k_csc_fused_fwd, s->fz, s->fzb, d);
+        ++g_lk_count;
+    } else
     for (auto& op : s->tape) run_op(s, op, true, q);
     if (backward) {
         cudaMemsetAsync(s->grad, 0, s->arena * 4, q);
         cudaMemsetAsync(s->g_raw, 0, (size_t)s->n_total * 4, q);
-        for (auto it = s->tape.rbegin(); it != s->tape.rend(); ++it) run_op(s, *it, false, q);
+        for (size_t i = s->tape.size(); i-- > 0;) {
+            if (s->fused_bwd && i >= s->op_xyz_begin && i < s->op_xyz_end) {
+                if (i + 1 == s->op_xyz_end) {
+                    // the reverse pass of all ADMM_XYZ passes as ONE persistent kernel: reads the adjoints the DF / loss ops left for the final
+                    // z, y, x, hands d z0, d y0, d fx0, d x0 to the warm-up ops, and adds its share of dD, dF, d scalars
+                    cudaMemsetAsync(s->fz_sync, 0, 256, q);                     // barrier counters
+                    s->fzw.grad = s->grad;
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3((unsigned)(d.NS * FZ_CL)); cfg.blockDim = dim3(FZ_THREADS); cfg.dynamicSmemBytes = s->fzb_smem; cfg.stream = q;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+                    cfg.attrs = at; cfg.numAttrs = 1;
+                    cudaLaunchKernelEx(&cfg, k_csc_fused_bwd_xyz, s->fz, s->fzb, s->fzw, d);
+                    const int nF = d.h * d.M2 * d.K, nD = d.f_len * d.M, nsc = 3 * d.npx + d.npx + 3 * d.npd + 3;
+                    lk(k_csc_fused_finish, nblk(nF + nD + 64, 256), 256, 0, q, (const float*)s->fzw.gsum, d.G, nF, nD, nsc,
+                       s->grad + s->Feff.off, s->grad + s->Deff.off, s->grad + s->sc.off);
+                    ++g_lk_count;
+                }
+                continue;
+            }
+            run_op(s, s->tape[i], false, q);
+        }
     }
 }
 
@@ -675,6 +798,17 @@ static int run_step_host(mb200_ctx* ctx, mb200_csc* s, const uint8_t* ascii, int
 }
 
 
+// the fused reverse pass handles top-q supports of up to FZ_KCAP entries per sequence (q = 32 plus exact ties) and code lists of up to
+// LIST_CAP entries; a degenerate step (e.g. an all-zero code tensor, where every entry ties at the threshold) is reported, not approximated
+static int fused_check(mb200_ctx* ctx, mb200_csc* s) {
+    if (!s->fused_bwd || !s->fz_err_host || *s->fz_err_host == 0) return MB200_OK;
+    const unsigned int e = *s->fz_err_host;
+    *s->fz_err_host = 0;
+    cudaMemsetAsync(s->fzw.err, 0, 4, ctx->stream);
+    MB_FAIL(ctx, MB200_E_UNSUPPORTED, "csc: the fused reverse pass met a degenerate top-q support (flag %u: more than %d kept entries or more than %d codes in a sequence); "
+            "create the handle with MB200_CSC_NO_FUSED for such inputs", e, FZ_KCAP, LIST_CAP);
+}
+
 // loss (and gradient) of n_groups batches.  seq_idx: n_groups*batch_size indices into seqs.
 // loss_out: n_groups*3 floats {total, reconstruction, syntax} per group; grads: n_trainable floats = mean over groups (or NULL).
 extern "C" int32_t mb200_csc_loss_grad(mb200_ctx* ctx, mb200_csc* s, const mb200_seqs* seqs, const int64_t* seq_idx, float* loss_out, float* grads) {
@@ -690,10 +824,11 @@ extern "C" int32_t mb200_csc_loss_grad(mb200_ctx* ctx, mb200_csc* s, const mb200
     const int td = tm.begin(T_D2H);
     if (loss_out) MB_CUDA(ctx, cudaMemcpyAsync(loss_out, s->data + s->loss.off, (size_t)s->d.G * 3 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (grads) MB_CUDA(ctx, cudaMemcpyAsync(grads, s->g_raw, (size_t)s->n_train * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (s->fused_bwd) MB_CUDA(ctx, cudaMemcpyAsync(s->fz_err_host, s->fzw.err, 4, cudaMemcpyDeviceToHost, ctx->stream));
     tm.end(td); tm.end(tt);
     MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     tm.collect();
-    return MB200_OK;
+    return fused_check(ctx, s);
 }
 
 // forward + reverse pass only; gradients stay on the device (mb200_csc_device_ptrs) so that the host framework can
@@ -731,7 +866,9 @@ extern "C" int32_t mb200_csc_adabelief_step(mb200_ctx* ctx, mb200_csc* s, float 
     lk(k_l1_F, s->d.K, 256, 0, ctx->stream, s->p_raw + s->off_F, d_l1, s->d);
     ctx->launches[T_CSC] += 2;
     MB_CUDA(ctx, cudaMemcpyAsync(s->host_out, s->data + s->loss.off, ((size_t)s->d.G * 3 + s->d.K) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (s->fused_bwd) MB_CUDA(ctx, cudaMemcpyAsync(s->fz_err_host, s->fzw.err, 4, cudaMemcpyDeviceToHost, ctx->stream));
     MB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    { const int rc = fused_check(ctx, s); if (rc) return rc; }
     if (loss_out) { float m = 0.f; for (int g = 0; g < s->d.G; ++g) m += s->host_out[g * 3]; *loss_out = m / (float)s->d.G; }
     if (l1_F_out) { float l1 = 0.f; for (int k = 0; k < s->d.K; ++k) l1 += s->host_out[(size_t)s->d.G * 3 + k]; *l1_F_out = l1; }
     return MB200_OK;

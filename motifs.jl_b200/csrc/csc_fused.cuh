@@ -1,0 +1,1238 @@
+// The unrolled CSC network as ONE persistent kernel (forward pass) for the reference's own step shape: a batch of 6 sequences.
+//
+// Reference: model.jl:330-395 (ADMM_XYZ, ADMM_DF, forward_pass_return_loss), restated in position space.
+// The tape of csc.cu runs the same arithmetic as ~95 kernels of 2-25 us whose time is L2 round trips and launch gaps: six
+// sequences cannot fill 148 SMs.  Here a sequence is owned by a CLUSTER of 8 CTAs (CTA r owns a contiguous range of its c = Lb-7
+// positions) and a whole pass is computed without leaving the kernel:
+//   * per-sequence chains (recon -> corr_sig -> zy update, d build -> corr2d -> top-q -> tconv -> dual) need no barrier at all except
+//     one cluster barrier for the per-sequence top-q: what a CTA needs from its neighbours (a halo of 7 or 11 positions) it
+//     RECOMPUTES from tensors the neighbours published in global memory before the last barrier, instead of waiting for them;
+//   * only the batch-wide statistics cross sequences: the median of the batch (two barriers over the group's 48 CTAs: merged
+//     4096-bin histogram, then the median bin's candidates), the batch sums of the D and F gradients of ADMM_DF, the loss;
+//   * the syntax filters F (115 KB), the dictionary D and the CTA's rows of z, y, alpha, beta, fx, theta stay in shared memory
+//     across passes; every intermediate the reverse pass needs is also written to the tape's arena (fire-and-forget stores).
+// Barriers over a group are counters in global memory (all CTAs are co-resident: cooperative launch); every sum that crosses
+// CTAs is taken in a fixed order, so the step is deterministic.
+#pragma once
+#include "csc_kernels.cuh"
+#include <cooperative_groups.h>
+
+#define FZ_THREADS 512
+#define FZ_CL 8                   // CTAs per sequence = cluster size
+#define FZ_M 50
+#define FZ_M2 100
+#define FZ_K 24
+#define FZ_H 12
+#define FZ_FL 8
+#define FZ_FLEN 32
+#define FZ_MAXPX 8
+#define FZ_MAXPD 4
+#define FZ_NHIST 3                // histogram levels a median call may use (bits 30..19, 18..7, 6..0)
+#define FZ_BINS 4096
+#define FZ_CAND 2048
+
+struct FzPass {                   // arena offsets (floats) of one ADMM_XYZ pass
+    int64_t z_in, y_in, fx_in, al_in, be_in, rec, gz, gy, z_out, y_out, med, dd, g, x_in, x_out, fx_out, al_out, be_out, bits;
+    int32_t xl_in, xl_out, i_eta, i_lam, i_rho, i_om;
+};
+struct FzDf {                     // one ADMM_DF pass; D_in/F_in have group stride 0 in pass 0 (the prepared filters)
+    int64_t D_in, F_in, rec, Gm, Dn, e, Fg, Fn, nrm, thn;
+    int32_t D_in_gs, F_in_gs, i_mu, i_kap, i_kaps, has_theta_out;
+};
+struct FzPlan {
+    int32_t npx, npd, i_eta_w, i_lam_w, i_om_w, xl0, forward_only, pad0;
+    int64_t sc, De, Fe, z0, y0, med0, zy0, g0, x0, fx0, bits0;
+    FzPass px[FZ_MAXPX];
+    int64_t zyF, medF, recL, fxL, loss;
+    FzDf df[FZ_MAXPD];
+};
+struct FzBufs {
+    float* data;                  // the tape's arena
+    uint8_t* bits;
+    int32_t* lcnt; uint16_t* lidx; float* lval;      // code lists [list][NS][LIST_CAP]
+    const uint8_t* bases;         // [NS][Lb]
+    unsigned int* bar;            // [G] barrier counters (zeroed before the launch)
+    unsigned int* hist;           // [G][nmed][FZ_NHIST][FZ_BINS] merged histograms (zeroed before the launch)
+    float* cand;                  // [G][nmed][FZ_CAND]
+    unsigned int* cctl;           // [G][nmed][4]: candidates reserved, ~min bits above the bin
+    float* part;                  // [G][48][FZ_PART] per-CTA partial sums
+};
+#define FZ_PART 2048              // floats of partial-sum space per CTA (D gradient 1600, loss 2, ...)
+
+// FZ_PROFILE builds (make FZ_PROFILE=1): thread 0 of CTA 0 accumulates clock64() per phase and prints the table at the end
+#ifdef FZ_PROFILE
+#define FZ_TDECL long long fz_t0 = clock64(), fz_acc[16] = {0}
+#define FZ_T(id) do { if (threadIdx.x == 0) { const long long t = clock64(); fz_acc[id] += t - fz_t0; fz_t0 = t; } } while (0)
+#else
+#define FZ_TDECL
+#define FZ_T(id)
+#endif
+
+namespace fz {
+namespace cg = cooperative_groups;
+
+struct Ctx {
+    int n, r, g, gidx, ng, ncl;   // sequence, cluster rank, group, CTA index inside the group, CTAs per group, clusters per group
+    int p0, p1, nr;               // own code rows [p0, p1)
+    int i0, i1, ni;               // own x rows [i0, i1)
+    int q1;                       // own base positions [p0, q1) for the signal (q1 = p1, the last CTA also takes the tail up to Lb)
+    unsigned int epoch;           // barrier arrivals expected so far
+    unsigned int* bar;
+    long long tbar, tb1, tb2, tb3; int nbar;     // FZ_PROFILE: clocks thread 0 spent inside group barriers (fence, arrive+poll, fence)
+};
+
+__device__ __forceinline__ unsigned int ld_relaxed(const unsigned int* p) {
+    unsigned int v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+// barrier over the CTAs of one group; global writes before it are visible to every CTA of the group after it.  Hierarchical: the 8 CTAs
+// of a cluster meet at the hardware cluster barrier, only the cluster's rank-0 CTA arrives at / polls the counter in global memory (6
+// arrivals on one address instead of 48: same-address atomics serialise in L2), a second cluster barrier releases the others.
+// Ordering: every CTA publishes its writes with a gpu-scope fence before the first cluster barrier; the leader's fence after that barrier
+// is cumulative over them; readers fence after the second cluster barrier (and read other CTAs' data with ld.cg).
+__device__ __forceinline__ void group_barrier(Ctx& c) {
+    __syncthreads();
+    if (threadIdx.x == 0) __threadfence();
+    cg::this_cluster().sync();
+    if (c.r == 0 && threadIdx.x == 0) {
+#ifdef FZ_PROFILE
+        const long long tb0 = clock64();
+#endif
+        c.epoch += (unsigned int)c.ncl;
+        __threadfence();
+#ifdef FZ_PROFILE
+        const long long tb1 = clock64();
+#endif
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" :: "l"(c.bar) : "memory");
+        unsigned int spins = 0;
+        while (ld_relaxed(c.bar) < c.epoch) { if (++spins > (1u << 26)) __trap(); }      // never hang the device
+#ifdef FZ_PROFILE
+        const long long tb2 = clock64();
+#endif
+        __threadfence();
+#ifdef FZ_PROFILE
+        const long long tb3 = clock64();
+        c.tbar += tb3 - tb0; ++c.nbar; c.tb1 += tb1 - tb0; c.tb2 += tb2 - tb1; c.tb3 += tb3 - tb2;
+#endif
+    }
+    cg::this_cluster().sync();
+    if (threadIdx.x == 0) __threadfence();
+    __syncthreads();
+}
+__device__ __forceinline__ void cluster_barrier() { cg::this_cluster().sync(); }
+
+__device__ __forceinline__ float block_sum512(float v, float* s16) {      // fixed order; result in every thread
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) s16[w] = v;
+    __syncthreads();
+    float r = 0.f;
+    #pragma unroll
+    for (int i = 0; i < FZ_THREADS / 32; ++i) r += s16[i];
+    return r;
+}
+__device__ __forceinline__ int block_excl_scan512(int cnt, int* total, int* s_w /* 17 ints */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = cnt;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULLMASK, inc, o); if (lane >= o) inc += y; }
+    __syncthreads();
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) { int run = 0; for (int i = 0; i < 16; ++i) { const int t = s_w[i]; s_w[i] = run; run += t; } s_w[16] = run; }
+    __syncthreads();
+    *total = s_w[16];
+    return s_w[w] + inc - cnt;
+}
+
+// ---- shared-memory map (floats) --------------------------------------------------------------------------------------------
+struct Smem {
+    float *F, *D, *Dt, *Dr, *z, *y, *fx, *al, *be, *th, *zyF;   // persistent: filters (Dt/Dr: D as [tap][m][4] forward / reversed) and the CTA's rows of the state tensors
+    float *A;                                           // work tile: d / zy rows [i0, i1 + 11) x 100, or z,y halo rows for recon
+    float *sig;                                         // residual signal of base positions [p0, p1 + 7)
+    float *w;                                           // work area: corr2d partials / top-q values / histograms / candidates
+    float *gout;                                        // [ni][24] corr2d result of own rows
+    int *li; float *lv; int *lc;                        // current code list of the sequence: flat index, value, count
+    uint8_t* b;                                         // bases [p0 - 0, p1 + 7 + ...)
+    float* red;                                         // 32 floats of reduction scratch
+    int* iscr;                                          // 32 ints of scratch
+};
+__host__ __device__ inline int fz_rows(int c) { return (c + FZ_CL - 1) / FZ_CL; }
+__host__ __device__ inline size_t fz_work_floats(int Lb) {
+    const int c = Lb - FZ_FL + 1, l = c - FZ_H + 1;
+    size_t a = (size_t)6144 + 64;                       // corr2d partials (<= 512 threads x 12)
+    const size_t b = (size_t)l * FZ_K + 256;            // top-q values + the 256-bin radix histogram behind them
+    const size_t h = (size_t)FZ_BINS + FZ_CAND;         // median histogram + candidates
+    if (b > a) a = b;
+    if (h > a) a = h;
+    return a;
+}
+__host__ __device__ inline size_t fz_smem_bytes(int Lb) {
+    const int c = Lb - FZ_FL + 1, R = fz_rows(c);
+    size_t f = (size_t)FZ_H * FZ_M2 * FZ_K + 3 * FZ_FLEN * FZ_M;             // F, D, Dt, Dr
+    f += (size_t)R * (FZ_M * 4 + FZ_M2 * 3);                                // z y al be | fx th zyF
+    size_t A = (size_t)(R + FZ_H - 1) * FZ_M2, A2 = (size_t)2 * (R + 14) * FZ_M;
+    f += (A > A2 ? A : A2);
+    f += (size_t)4 * (R + 8);                                               // sig
+    f += fz_work_floats(Lb);
+    f += (size_t)R * FZ_K;                                                  // gout
+    f += 3 * LIST_CAP + 8;                                                  // list
+    f += 64;                                                                // red + iscr
+    return f * 4 + (size_t)(R + 16) + 64;                                   // + bases
+}
+
+__device__ __forceinline__ void carve(Smem& s, float* base, int R, int Lb) {
+    float* p = base;
+    s.F = p; p += FZ_H * FZ_M2 * FZ_K;
+    s.D = p; p += FZ_FLEN * FZ_M; s.Dt = p; p += FZ_FLEN * FZ_M; s.Dr = p; p += FZ_FLEN * FZ_M;
+    s.z = p; p += R * FZ_M; s.y = p; p += R * FZ_M; s.al = p; p += R * FZ_M; s.be = p; p += R * FZ_M;
+    s.fx = p; p += R * FZ_M2; s.th = p; p += R * FZ_M2; s.zyF = p; p += R * FZ_M2;
+    const size_t A = (size_t)(R + FZ_H - 1) * FZ_M2, A2 = (size_t)2 * (R + 14) * FZ_M;
+    s.A = p; p += (A > A2 ? A : A2);
+    s.sig = p; p += 4 * (R + 8);
+    s.w = p; p += fz_work_floats(Lb);
+    s.gout = p; p += R * FZ_K;
+    s.li = reinterpret_cast<int*>(p); p += LIST_CAP; s.lv = p; p += LIST_CAP; s.lc = reinterpret_cast<int*>(p); p += 8 + LIST_CAP;
+    s.red = p; p += 32; s.iscr = reinterpret_cast<int*>(p); p += 32;
+    s.b = reinterpret_cast<uint8_t*>(p);
+}
+
+// ---- batch median of the positive entries of (z, y) over the whole group; every CTA holds its rows in s.z / s.y -------------
+// (create_ZY_mask, model.jl:194-204; Statistics.median: mean of the two middle values for an even count; no positives: -inf = no mask)
+__device__ float group_median(Ctx& c, const Smem& s, const FzBufs& B, int mi, int nmed) {
+    unsigned int* lhist = reinterpret_cast<unsigned int*>(s.w);
+    float* cand = s.w + FZ_BINS;
+    unsigned int* wsum = reinterpret_cast<unsigned int*>(s.red);          // 32 uints
+    unsigned int* res = reinterpret_cast<unsigned int*>(s.iscr);          // 4 uints (+ scratch)
+    unsigned int* ghist0 = B.hist + ((size_t)c.g * nmed + mi) * FZ_NHIST * FZ_BINS;
+    float* gcand = B.cand + ((size_t)c.g * nmed + mi) * FZ_CAND;
+    unsigned int* gctl = B.cctl + ((size_t)c.g * nmed + mi) * 4;
+    const int nv = c.nr * FZ_M;
+    unsigned int prefix = 0, pmask = 0, krank = 0, npos = 0, cnt = 0;
+    int shift = 19, nb = FZ_BINS;
+    bool first = true, resolved = false;
+    for (int lvl = 0; lvl < FZ_NHIST; ++lvl) {
+        unsigned int* gh = ghist0 + (size_t)lvl * FZ_BINS;
+        for (int i = threadIdx.x; i < nb; i += FZ_THREADS) lhist[i] = 0;
+        __syncthreads();
+        for (int e = threadIdx.x; e < 2 * nv; e += FZ_THREADS) {
+            const float f = e < nv ? s.z[e] : s.y[e - nv];
+            const unsigned int b = __float_as_uint(f);
+            if (f > 0.f && (b & pmask) == prefix) atomicAdd(&lhist[(b >> shift) & (unsigned)(nb - 1)], 1u);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb; i += FZ_THREADS) { const unsigned int v = lhist[i]; if (v) atomicAdd(&gh[i], v); }
+        group_barrier(c);
+        for (int i = threadIdx.x; i < nb; i += FZ_THREADS) lhist[i] = __ldcg(&gh[i]);
+        __syncthreads();
+        block_find_bin(lhist, nb, krank, first, wsum, res);
+        if (first) {
+            npos = res[3];
+            if (npos == 0) break;
+            krank = (npos & 1u) ? npos / 2 : npos / 2 - 1;
+            first = false;
+        }
+        const unsigned int bin = res[0];
+        krank -= res[1]; cnt = res[2];
+        prefix |= bin << shift; pmask |= (unsigned)(nb - 1) << shift;
+        __syncthreads();
+        if (cnt <= FZ_CAND) break;
+        if (shift == 0) { resolved = true; break; }
+        if (shift == 19) { shift = 7; nb = FZ_BINS; } else { shift = 0; nb = 128; }
+    }
+    float med = -INFINITY;
+    if (npos > 0) {                                                        // group-uniform
+        // publish this CTA's entries of the median's bin, and the smallest entry above the bin
+        unsigned int* lc = lhist;                                          // local candidate bits
+        if (threadIdx.x == 0) { res[0] = 0; res[1] = 0; }
+        __syncthreads();
+        unsigned int mxinv = 0;                                            // max of ~bits = min of bits above the bin (0: none)
+        for (int e0 = 0; e0 < 2 * nv; e0 += FZ_THREADS) {
+            const int e = e0 + threadIdx.x;
+            const float f = e < 2 * nv ? (e < nv ? s.z[e] : s.y[e - nv]) : 0.f;
+            const unsigned int b = __float_as_uint(f);
+            if (f > 0.f && (b & pmask) > prefix) mxinv = max(mxinv, ~b);
+            if (!resolved && f > 0.f && (b & pmask) == prefix) lc[atomicAdd(&res[0], 1u)] = b;
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mxinv = max(mxinv, __shfl_xor_sync(FULLMASK, mxinv, o));
+        if ((threadIdx.x & 31) == 0 && mxinv) atomicMax(&res[1], mxinv);
+        __syncthreads();
+        const unsigned int nc = res[0];
+        if (threadIdx.x == 0) {
+            res[2] = nc ? atomicAdd(&gctl[0], nc) : 0u;
+            if (res[1]) atomicMax(&gctl[1], res[1]);
+        }
+        __syncthreads();
+        const unsigned int base = res[2];
+        for (unsigned int i = threadIdx.x; i < nc; i += FZ_THREADS) gcand[base + i] = __uint_as_float(lc[i]);
+        group_barrier(c);
+        const unsigned int above_inv = __ldcg(&gctl[1]);
+        if (!resolved) for (unsigned int i = threadIdx.x; i < cnt; i += FZ_THREADS) cand[i] = __ldcg(&gcand[i]);
+        __syncthreads();
+        const unsigned int kin = krank;
+        unsigned int v1b = prefix;
+        if (!resolved) {
+            unsigned int lowfix = 0, lowmask = 0;
+            int rem = shift;
+            while (rem > 0) {
+                const int nbits = rem < 10 ? rem : 10, sh = rem - nbits, nbin = 1 << nbits;
+                for (int i = threadIdx.x; i < nbin; i += FZ_THREADS) lhist[i] = 0;
+                __syncthreads();
+                for (unsigned e0 = 0; e0 < cnt; e0 += FZ_THREADS) {
+                    const unsigned e = e0 + threadIdx.x;
+                    const unsigned int b = e < cnt ? __float_as_uint(cand[e]) : 0u;
+                    hist_add(lhist, e < cnt && (b & lowmask) == lowfix, (b >> sh) & (unsigned)(nbin - 1));
+                }
+                __syncthreads();
+                block_find_bin(lhist, nbin, krank, false, wsum, res);
+                lowfix |= res[0] << sh; lowmask |= (unsigned)(nbin - 1) << sh; krank -= res[1];
+                __syncthreads();
+                rem = sh;
+            }
+            v1b |= lowfix;
+        }
+        const float v1 = __uint_as_float(v1b);
+        if (npos & 1u) med = v1;
+        else {
+            // second middle value: a copy of v1, else the next candidate, else the smallest entry above the bin
+            unsigned int le = 0, mn2 = 0x7f800000u;
+            if (!resolved)
+                for (unsigned e = threadIdx.x; e < cnt; e += FZ_THREADS) { const unsigned int b = __float_as_uint(cand[e]); if (b <= v1b) ++le; else mn2 = min(mn2, b); }
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { le += __shfl_xor_sync(FULLMASK, le, o); mn2 = min(mn2, __shfl_xor_sync(FULLMASK, mn2, o)); }
+            __syncthreads();
+            if (threadIdx.x == 0) { res[0] = 0; res[1] = 0x7f800000u; }
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) { if (le) atomicAdd(&res[0], le); atomicMin(&res[1], mn2); }
+            __syncthreads();
+            const unsigned int le_all = resolved ? cnt : res[0];
+            const unsigned int v2b = (le_all >= kin + 2) ? v1b : (res[1] != 0x7f800000u ? res[1] : ~above_inv);
+            med = v1 * 0.5f + __uint_as_float(v2b) * 0.5f;               // Statistics.middle(a, b) = a/2 + b/2
+            __syncthreads();
+        }
+    }
+    return med;
+}
+
+// ---- D layer ---------------------------------------------------------------------------------------------------------------
+// stage rows [lo, hi) of the sequence's z, y (global, [c][M]) into s.A as zh | yh (row-major [hi-lo][50] each)
+__device__ __forceinline__ void stage_zy_halo(const Smem& s, const float* zg, const float* yg, int lo, int hi) {
+    const int n = (hi - lo) * FZ_M;
+    float* zh = s.A; float* yh = s.A + n;
+    for (int e = threadIdx.x; e < n; e += FZ_THREADS) { zh[e] = __ldcg(zg + (size_t)lo * FZ_M + e); yh[e] = __ldcg(yg + (size_t)lo * FZ_M + e); }
+}
+// Dt[j][m][a] = D[4j+a][m], Dr[j][m][a] = D[31-4j-a][m]: the four nucleotide taps of a filter position as one 16-byte load
+__device__ __forceinline__ void build_Dt(const Smem& s) {
+    for (int o = threadIdx.x; o < FZ_FL * FZ_M; o += FZ_THREADS) {
+        const int j = o / FZ_M, m = o - j * FZ_M;
+        float4 f, r;
+        f.x = s.D[(4 * j + 0) * FZ_M + m]; f.y = s.D[(4 * j + 1) * FZ_M + m]; f.z = s.D[(4 * j + 2) * FZ_M + m]; f.w = s.D[(4 * j + 3) * FZ_M + m];
+        r.x = s.D[(31 - 4 * j) * FZ_M + m]; r.y = s.D[(30 - 4 * j) * FZ_M + m]; r.z = s.D[(29 - 4 * j) * FZ_M + m]; r.w = s.D[(28 - 4 * j) * FZ_M + m];
+        reinterpret_cast<float4*>(s.Dt)[o] = f; reinterpret_cast<float4*>(s.Dr)[o] = r;
+    }
+}
+// recon of base positions [q0, q1): rec[4q+a] = sum_{j<8} sum_m z[q-j][m] D[4j+a][m] + y[q-j][m] D[31-4j-a][m]  (model.jl:238-239,276-277,313-314)
+// from the staged rows [lo, hi); half a warp per base position, lanes over m, four taps per 16-byte filter load.  Writes
+// s.sig[t - 4 q0] = rec + sgn*S and, for own positions [wq0, wq1), rec to global (may be null)
+__device__ void recon_rows(const Ctx& c, const Smem& s, int lo, int hi, int q0, int q1, float sgn, float* rec_g, int wq0, int wq1, int Lb) {
+    const int sub = threadIdx.x & 15, hw = threadIdx.x >> 4;
+    const float* zh = s.A; const float* yh = s.A + (hi - lo) * FZ_M;
+    const int cc = Lb - FZ_FL + 1;
+    const float4* Dt4 = reinterpret_cast<const float4*>(s.Dt); const float4* Dr4 = reinterpret_cast<const float4*>(s.Dr);
+    for (int qb = q0; qb < q1; qb += FZ_THREADS / 16) {             // every lane runs the same number of trips (full-warp shuffles below)
+        const int q = qb + hw;
+        const bool live = q < q1;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        #pragma unroll
+        for (int j = 0; j < FZ_FL; ++j) {
+            const int p = q - j;
+            if (live && p >= 0 && p < cc) {
+                #pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int m = sub + 16 * i;
+                    if (m < FZ_M) {
+                        const float zv = zh[(p - lo) * FZ_M + m], yv = yh[(p - lo) * FZ_M + m];
+                        const float4 f = Dt4[j * FZ_M + m], r = Dr4[j * FZ_M + m];
+                        a0 += zv * f.x + yv * r.x; a1 += zv * f.y + yv * r.y; a2 += zv * f.z + yv * r.z; a3 += zv * f.w + yv * r.w;
+                    }
+                }
+            }
+        }
+        #pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(FULLMASK, a0, o); a1 += __shfl_xor_sync(FULLMASK, a1, o);
+            a2 += __shfl_xor_sync(FULLMASK, a2, o); a3 += __shfl_xor_sync(FULLMASK, a3, o);
+        }
+        if (live && sub == 0) {
+            if (rec_g && q >= wq0 && q < wq1) *reinterpret_cast<float4*>(rec_g + 4 * q) = make_float4(a0, a1, a2, a3);
+            float v[4] = {a0, a1, a2, a3};
+            if (sgn != 0.f) v[s.b[q - c.p0]] += sgn;
+            *reinterpret_cast<float4*>(s.sig + 4 * (q - q0)) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
+// ---- F layer ---------------------------------------------------------------------------------------------------------------
+// out[i][k] = sum_{a<12} sum_{j<100} A[i+a][j] F[a][j][k] for the CTA's ni rows; A rows [i0, i1+11) in s.A; result in s.gout
+__device__ void corr2d_rows(const Smem& s, const float* Fm, int ni) {
+    const int ntr = (ni + 2) / 3, ntile = ntr * 6;
+    const int nslice = ntile ? min(FZ_THREADS / ntile, 64) : 0;
+    const int tile = ntile ? threadIdx.x % ntile : 0, slice = ntile ? threadIdx.x / ntile : 0;
+    const int tr = tile / 6, kg = tile - tr * 6;
+    const int E = FZ_H * FZ_M2;
+    if (ntile && slice < nslice) {
+        float acc[3][4];
+        #pragma unroll
+        for (int r = 0; r < 3; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
+        const int e_lo = (int)((long long)E * slice / nslice), e_hi = (int)((long long)E * (slice + 1) / nslice);
+        const float* Ab = s.A + (3 * tr) * FZ_M2;                 // row (3tr + rr + a), column j  ->  Ab[rr*100 + e]   (e = a*100 + j)
+        #pragma unroll 4
+        for (int e = e_lo; e < e_hi; ++e) {
+            const float4 f = *reinterpret_cast<const float4*>(Fm + (size_t)e * FZ_K + 4 * kg);
+            #pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float av = Ab[r * FZ_M2 + e];
+                acc[r][0] += av * f.x; acc[r][1] += av * f.y; acc[r][2] += av * f.z; acc[r][3] += av * f.w;
+            }
+        }
+        float* dst = s.w + ((size_t)slice * (3 * ntr) + 3 * tr) * FZ_K + 4 * kg;
+        #pragma unroll
+        for (int r = 0; r < 3; ++r) *reinterpret_cast<float4*>(dst + r * FZ_K) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < ni * FZ_K; o += FZ_THREADS) {
+        float v = 0.f;
+        for (int sl = 0; sl < nslice; ++sl) v += s.w[(size_t)sl * (3 * ntr) * FZ_K + o];
+        s.gout[o] = v;
+    }
+    __syncthreads();
+}
+
+// out[i][j] = sum over a code list: v * F[i - iq][j][kq], 0 <= i - iq < 12, for own rows [p0, p1)   (model.jl:229,263,294,316,370).
+// cnt <= LIST_CAP: a warp first builds, per own row, the ordered list of the codes that reach it (offset of F[a][.][kq], value) in s.w;
+// then one thread per output (row, j) walks only those.  cnt <= lcap (a longer list held in li/lv): every output walks the whole list.
+// Otherwise (forward only: more codes than the list holds) the dense tensor xg is read from global.  out: [nr][100].  Uses s.w.
+__device__ void tconv_list(const Ctx& c, const Smem& s, const float* Fm, const int* li, const float* lv, int cnt, int lcap, const float* xg, int l, float* out) {
+    const int R = c.nr;
+    int* rcnt = reinterpret_cast<int*>(s.w); int* roff = rcnt + 32; float* rval = s.w + 32 + 32 * LIST_CAP;      // rows <= 32
+    if (cnt <= LIST_CAP) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int il = warp; il < R; il += FZ_THREADS / 32) {
+            const int i = c.p0 + il;
+            int run = 0;
+            for (int q0 = 0; q0 < cnt; q0 += 32) {
+                const int q = q0 + lane;
+                int a = -1, kq = 0; float v = 0.f;
+                if (q < cnt) { const int e = li[q], iq = e / FZ_K; kq = e - iq * FZ_K; a = i - iq; v = lv[q]; }
+                const bool hit = a >= 0 && a < FZ_H;
+                const unsigned mk = __ballot_sync(FULLMASK, hit);
+                if (hit) { const int o = run + __popc(mk & ((1u << lane) - 1u)); roff[il * LIST_CAP + o] = a * FZ_M2 * FZ_K + kq; rval[il * LIST_CAP + o] = v; }
+                run += __popc(mk);
+            }
+            if (lane == 0) rcnt[il] = run;
+        }
+        __syncthreads();
+        for (int o = threadIdx.x; o < R * FZ_M2; o += FZ_THREADS) {
+            const int il = o / FZ_M2, j = o - il * FZ_M2;
+            const int n = rcnt[il];
+            float acc = 0.f;
+            for (int q = 0; q < n; ++q) acc += rval[il * LIST_CAP + q] * Fm[roff[il * LIST_CAP + q] + j * FZ_K];
+            out[o] = acc;
+        }
+    } else if (cnt <= lcap) {
+        for (int o = threadIdx.x; o < R * FZ_M2; o += FZ_THREADS) {
+            const int il = o / FZ_M2, j = o - il * FZ_M2, i = c.p0 + il;
+            float acc = 0.f;
+            for (int q = 0; q < cnt; ++q) {
+                const int e = li[q], iq = e / FZ_K, kq = e - iq * FZ_K, a = i - iq;
+                if (a >= 0 && a < FZ_H) acc += lv[q] * Fm[((size_t)a * FZ_M2 + j) * FZ_K + kq];
+            }
+            out[o] = acc;
+        }
+    } else {
+        for (int o = threadIdx.x; o < R * FZ_M2; o += FZ_THREADS) {
+            const int il = o / FZ_M2, j = o - il * FZ_M2, i = c.p0 + il;
+            float acc = 0.f;
+            const int a_lo = max(0, i - l + 1), a_hi = min(FZ_H - 1, i);
+            for (int a = a_lo; a <= a_hi; ++a)
+                for (int k = 0; k < FZ_K; ++k) { const float xv = __ldcg(xg + (size_t)(i - a) * FZ_K + k); if (xv != 0.f) acc += xv * Fm[((size_t)a * FZ_M2 + j) * FZ_K + k]; }
+            out[o] = acc;
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void tconv_rows(const Ctx& c, const Smem& s, const float* Fm, const float* xg, int l, float* out) {
+    tconv_list(c, s, Fm, s.li, s.lv, s.lc[0], LIST_CAP, xg, l, out);
+}
+
+// per-sequence top-q (generate_bitmat / project_X, model.jl:181-192) on v = xprev + om * g over all l*K entries, redundantly in every CTA of
+// the cluster; writes own rows of x and the bitmap, rank 0 writes the ordered code list; leaves the list in s.li / s.lv / s.lc
+__device__ void topq_all(const Ctx& c, const Smem& s, const float* g_g, const float* xprev_g, bool have_prev, float om, int l, int q,
+                         float* xout_g, uint8_t* bits_g, int32_t* lcnt_g, uint16_t* lidx_g, float* lval_g) {
+    const int E = l * FZ_K;
+    float* sv = s.w;
+    unsigned int* hist = reinterpret_cast<unsigned int*>(s.w + E);        // fz_work_floats() reserves 256 bins behind the values
+    // values: previous codes come from the list when it is complete (cheaper than re-reading the dense tensor)
+    const int pcnt = have_prev ? s.lc[0] : 0;
+    if (have_prev && pcnt > LIST_CAP) { for (int e = threadIdx.x; e < E; e += FZ_THREADS) sv[e] = __ldcg(xprev_g + e) + om * __ldcg(g_g + e); }
+    else {
+        for (int e = threadIdx.x; e < E; e += FZ_THREADS) sv[e] = 0.f + om * __ldcg(g_g + e);
+        __syncthreads();
+        if (threadIdx.x < pcnt) { const int e = s.li[threadIdx.x]; sv[e] = s.lv[threadIdx.x] + om * __ldcg(g_g + e); }
+    }
+    unsigned int* ctl = reinterpret_cast<unsigned int*>(s.iscr);          // [0] prefix, [1] rank
+    if (threadIdx.x == 0) { ctl[0] = 0; ctl[1] = (unsigned int)(E - q); }
+    __syncthreads();
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+        __syncthreads();
+        const unsigned int prefix = ctl[0];
+        const unsigned int pmask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+        for (int e0 = 0; e0 < E; e0 += FZ_THREADS) {
+            const int e = e0 + threadIdx.x;
+            const unsigned int kk = e < E ? fkey(sv[e]) : 0u;
+            hist_add(hist, e < E && (kk & pmask) == prefix, (kk >> shift) & 255u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int bin; unsigned int below;
+            find_bin(hist, ctl[1], &bin, &below);
+            __syncwarp();
+            if (threadIdx.x == 0) { ctl[1] -= below; ctl[0] = prefix | ((unsigned int)bin << shift); }
+        }
+        __syncthreads();
+    }
+    const float vq = fkey_inv(ctl[0]);
+    __syncthreads();
+    // ordered list (flat index ascending): contiguous chunk per thread
+    const int per = (E + FZ_THREADS - 1) / FZ_THREADS;
+    const int e0 = threadIdx.x * per, e1 = min(E, e0 + per);
+    int cnt = 0;
+    for (int e = e0; e < e1; ++e) { const float v = sv[e]; cnt += (v >= vq && v != 0.f); }
+    int total;
+    int o = block_excl_scan512(cnt, &total, s.iscr + 8);
+    for (int e = e0; e < e1; ++e) {
+        const float v = sv[e];
+        if (v >= vq && v != 0.f) { if (o < LIST_CAP) { s.li[o] = e; s.lv[o] = v; } ++o; }
+    }
+    if (threadIdx.x == 0) s.lc[0] = total;
+    __syncthreads();
+    // own rows of the dense tensor + bitmap
+    for (int e = c.i0 * FZ_K + threadIdx.x; e < c.i1 * FZ_K; e += FZ_THREADS) {
+        const float v = sv[e]; const bool keep = v >= vq;
+        xout_g[e] = keep ? v : 0.f;
+        bits_g[e] = keep;
+    }
+    if (c.r == 0) {
+        if (threadIdx.x == 0) lcnt_g[0] = total;
+        if (threadIdx.x < min(total, LIST_CAP)) { lidx_g[threadIdx.x] = (uint16_t)s.li[threadIdx.x]; lval_g[threadIdx.x] = s.lv[threadIdx.x]; }
+    }
+    __syncthreads();
+}
+
+}  // namespace fz
+
+// =================================================================================================================================
+// forward kernel
+// =================================================================================================================================
+__global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_csc_fused_fwd(const FzPlan P, const FzBufs B, const CscDims d) {
+    using namespace fz;
+    extern __shared__ __align__(16) float fz_smem[];
+    const int Lb = d.Lb, cc = d.c, l = d.l;
+    const int R = fz_rows(cc);
+    Smem s; carve(s, fz_smem, R, Lb);
+    Ctx c;
+    c.n = blockIdx.x / FZ_CL; c.r = blockIdx.x % FZ_CL; c.g = c.n / d.B; c.gidx = (c.n % d.B) * FZ_CL + c.r; c.ng = d.B * FZ_CL; c.ncl = d.B;
+    c.p0 = min(cc, c.r * R); c.p1 = min(cc, c.p0 + R); c.nr = c.p1 - c.p0;
+    c.i0 = min(l, c.p0); c.i1 = min(l, c.p1); c.ni = c.i1 - c.i0;
+    c.q1 = (c.r == FZ_CL - 1) ? Lb : c.p1;
+    c.epoch = 0; c.bar = B.bar + c.g; c.tbar = 0; c.nbar = 0; c.tb1 = c.tb2 = c.tb3 = 0;
+    const int nmed = P.npx + 2;
+    float* const data = B.data;
+    const float* sc = data + P.sc;
+    const int64_t nZ = (int64_t)cc * FZ_M, nZY = (int64_t)cc * FZ_M2, nX = (int64_t)l * FZ_K, nS = (int64_t)4 * Lb;
+    const int64_t nD = FZ_FLEN * FZ_M, nF = (int64_t)FZ_H * FZ_M2 * FZ_K;
+    const float mf = d.mf;
+    FZ_TDECL;
+    // ---- prologue: filters and bases into shared memory --------------------------------------------------------------------
+    for (int e = threadIdx.x; e < (int)nF / 4; e += FZ_THREADS) reinterpret_cast<float4*>(s.F)[e] = __ldcg(reinterpret_cast<const float4*>(data + P.Fe) + e);
+    for (int e = threadIdx.x; e < (int)nD; e += FZ_THREADS) s.D[e] = __ldcg(data + P.De + e);
+    const int nb_own = min(Lb, c.p1 + 7 + FZ_FL) - c.p0;                       // bases [p0, ...) this CTA ever looks at
+    for (int e = threadIdx.x; e < nb_own; e += FZ_THREADS) s.b[e] = B.bases[(size_t)c.n * Lb + c.p0 + e];
+    for (int e = threadIdx.x; e < R * FZ_M2; e += FZ_THREADS) s.th[e] = 0.f;
+    if (threadIdx.x == 0) s.lc[0] = 0;
+    __syncthreads();
+    build_Dt(s);
+    __syncthreads();
+
+    FZ_T(0);
+    // per-sequence views of arena tensors
+#define SEQ_Z(off) (data + (off) + (int64_t)c.n * nZ)
+#define SEQ_ZY(off) (data + (off) + (int64_t)c.n * nZY)
+#define SEQ_X(off) (data + (off) + (int64_t)c.n * nX)
+#define SEQ_S(off) (data + (off) + (int64_t)c.n * nS)
+#define LCNT_(L) (B.lcnt + (size_t)(L) * d.NS + c.n)
+#define LIDX_(L) (B.lidx + ((size_t)(L) * d.NS + c.n) * LIST_CAP)
+#define LVAL_(L) (B.lval + ((size_t)(L) * d.NS + c.n) * LIST_CAP)
+
+    // ---- warm-up (model.jl:171-179, 224-232) -------------------------------------------------------------------------------
+    {
+        const float eta = sc[P.i_eta_w], lam = sc[P.i_lam_w];
+        float* zg = SEQ_Z(P.z0); float* yg = SEQ_Z(P.y0);
+        for (int o = threadIdx.x; o < c.nr * FZ_M; o += FZ_THREADS) {
+            const int pl = o / FZ_M, m = o - pl * FZ_M;
+            float uf = 0.f, ur = 0.f;
+            #pragma unroll
+            for (int j = 0; j < FZ_FL; ++j) {
+                const int b = s.b[pl + j];
+                uf += s.D[(4 * j + b) * FZ_M + m];
+                ur += s.D[(4 * (FZ_FL - 1 - j) + 3 - b) * FZ_M + m];
+            }
+            const float zv = fmaxf(eta * uf - lam * eta, 0.f), yv = fmaxf(eta * ur - lam * eta, 0.f);
+            s.z[o] = zv; s.y[o] = yv;
+            zg[(size_t)c.p0 * FZ_M + o] = zv; yg[(size_t)c.p0 * FZ_M + o] = yv;
+        }
+        for (int o = threadIdx.x; o < c.nr * FZ_M; o += FZ_THREADS) { s.al[o] = 0.f; s.be[o] = 0.f; }
+        for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) s.fx[o] = 0.f;
+        __syncthreads();
+    }
+    FZ_T(1);
+    // shared by warm-up and the passes: masked/scaled codes of rows [i0, i1 + 11) -> s.A (optionally d = fx - (zy' - [al be])), corr2d, top-q, tconv
+    auto x_chain = [&](int mi, int64_t z_off, int64_t y_off, int64_t med_off, bool with_d, int64_t fx_in, int64_t al_in, int64_t be_in, bool duals_zero,
+                       int64_t zy_out, int64_t dd_out, int64_t g_off, int64_t x_in, bool have_prev, int64_t x_out, int64_t bits_off, int xl_out, float om,
+                       int64_t fx_out) {
+        const float med = group_median(c, s, B, mi, nmed);
+        FZ_T(2);
+        if (c.gidx == 0 && threadIdx.x == 0) data[med_off + c.g] = med;
+        // A tile rows [i0, i1 + 11): own rows from shared memory, the rest recomputed from what the neighbours published
+        const int a_hi = min(cc, c.i1 + FZ_H - 1);
+        const float* zg = SEQ_Z(z_off); const float* yg = SEQ_Z(y_off);
+        const float* fxg = with_d ? SEQ_ZY(fx_in) : nullptr;
+        const float* alg = (with_d && !duals_zero) ? SEQ_Z(al_in) : nullptr; const float* beg = (with_d && !duals_zero) ? SEQ_Z(be_in) : nullptr;
+        if (c.ni > 0)
+        for (int o = threadIdx.x; o < (a_hi - c.i0) * FZ_M2; o += FZ_THREADS) {
+            const int rl = o / FZ_M2, j = o - rl * FZ_M2, row = c.i0 + rl;
+            const bool own = row < c.p1;
+            const int m = j < FZ_M ? j : j - FZ_M;
+            float v;
+            if (own) v = j < FZ_M ? s.z[(row - c.p0) * FZ_M + m] : s.y[(row - c.p0) * FZ_M + m];
+            else v = __ldcg((j < FZ_M ? zg : yg) + (size_t)row * FZ_M + m);
+            float zyv = v >= med ? mf * v : 0.f;
+            if (own && zy_out >= 0) SEQ_ZY(zy_out)[(size_t)row * FZ_M2 + j] = zyv;
+            if (with_d) {
+                float fxv, ab;
+                if (own) { fxv = s.fx[(row - c.p0) * FZ_M2 + j]; ab = j < FZ_M ? s.al[(row - c.p0) * FZ_M + m] : s.be[(row - c.p0) * FZ_M + m]; }
+                else { fxv = __ldcg(fxg + (size_t)row * FZ_M2 + j); ab = duals_zero ? 0.f : __ldcg((j < FZ_M ? alg : beg) + (size_t)row * FZ_M + m); }
+                zyv = fxv - (zyv - ab);
+                if (own && dd_out >= 0) SEQ_ZY(dd_out)[(size_t)row * FZ_M2 + j] = zyv;
+            }
+            s.A[o] = zyv;
+        }
+        // rows of zy / d that no x row reaches (i >= l) still belong to somebody's tape tensors
+        if (c.p1 > max(c.i1 + FZ_H - 1, c.p0) || c.ni == 0) {
+            const int r_lo = c.ni > 0 ? max(c.p0, a_hi) : c.p0;
+            for (int o = threadIdx.x + (r_lo - c.p0) * FZ_M2; o < c.nr * FZ_M2; o += FZ_THREADS) {
+                const int rl = o / FZ_M2, j = o - rl * FZ_M2, m = j < FZ_M ? j : j - FZ_M;
+                const float v = j < FZ_M ? s.z[rl * FZ_M + m] : s.y[rl * FZ_M + m];
+                float zyv = v >= med ? mf * v : 0.f;
+                if (zy_out >= 0) SEQ_ZY(zy_out)[(size_t)(c.p0 + rl) * FZ_M2 + j] = zyv;
+                if (with_d) { zyv = s.fx[o] - (zyv - (j < FZ_M ? s.al[rl * FZ_M + m] : s.be[rl * FZ_M + m])); if (dd_out >= 0) SEQ_ZY(dd_out)[(size_t)(c.p0 + rl) * FZ_M2 + j] = zyv; }
+            }
+        }
+        __syncthreads();
+        FZ_T(3);
+        corr2d_rows(s, s.F, c.ni);
+        FZ_T(4);
+        float* gg = SEQ_X(g_off);
+        for (int o = threadIdx.x; o < c.ni * FZ_K; o += FZ_THREADS) gg[(size_t)c.i0 * FZ_K + o] = s.gout[o];
+        cluster_barrier();                                     // the sequence's g is complete
+        FZ_T(5);
+        topq_all(c, s, gg, have_prev ? SEQ_X(x_in) : nullptr, have_prev, om, l, d.q, SEQ_X(x_out), B.bits + bits_off + (size_t)c.n * nX,
+                 LCNT_(xl_out), LIDX_(xl_out), LVAL_(xl_out));
+        FZ_T(6);
+        tconv_rows(c, s, s.F, SEQ_X(x_out), l, s.fx);
+        __syncthreads();
+        float* fo = SEQ_ZY(fx_out);
+        for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) fo[(size_t)c.p0 * FZ_M2 + o] = s.fx[o];
+        FZ_T(7);
+    };
+    x_chain(0, P.z0, P.y0, P.med0, false, 0, 0, 0, true, P.zy0, -1, P.g0, 0, false, P.x0, P.bits0, P.xl0, sc[P.i_om_w], P.fx0);
+
+    // ---- ADMM_XYZ passes (model.jl:256-268) --------------------------------------------------------------------------------
+    for (int n = 0; n < P.npx; ++n) {
+        const FzPass& X = P.px[n];
+        const float eta = sc[X.i_eta], lam = sc[X.i_lam], rho = sc[X.i_rho], om = sc[X.i_om];
+        // (1) recon of base positions [p0, p1 + 7) from rows [p0 - 7, p1 + 7) of the previous z, y; residual r = recon - S
+        {
+            const int lo = max(0, c.p0 - 7), hi = min(cc, c.p1 + 7);
+            const int q0 = c.p0, q1 = min(Lb, max(c.p1 + 7, c.q1));
+            if (c.nr > 0 || c.q1 > c.p0) {
+                stage_zy_halo(s, SEQ_Z(X.z_in), SEQ_Z(X.y_in), lo, hi);
+                __syncthreads();
+                FZ_T(10);
+                recon_rows(c, s, lo, hi, q0, q1, -1.f, SEQ_S(X.rec), c.p0, c.q1, Lb);
+            }
+            __syncthreads();
+        }
+        FZ_T(8);
+        // (2) corr_sig + ISTA step (model.jl:240-244); reads the old z, y, fx, alpha, beta rows held in shared memory
+        {
+            float* gzg = SEQ_Z(X.gz); float* gyg = SEQ_Z(X.gy); float* zo = SEQ_Z(X.z_out); float* yo = SEQ_Z(X.y_out);
+            for (int o = threadIdx.x; o < c.nr * FZ_M; o += FZ_THREADS) {
+                const int pl = o / FZ_M, m = o - pl * FZ_M;
+                float a = 0.f, b = 0.f;
+                #pragma unroll 8
+                for (int k = 0; k < FZ_FLEN; ++k) { const float r = s.sig[4 * pl + k]; a += r * s.D[k * FZ_M + m]; b += r * s.D[(FZ_FLEN - 1 - k) * FZ_M + m]; }
+                const float zv = s.z[o], yv = s.y[o];
+                const float lft = s.fx[pl * FZ_M2 + m], rgt = s.fx[pl * FZ_M2 + FZ_M + m];
+                const float zn = fmaxf(zv - eta * (a + rho * (zv - lft - s.al[o])) - lam * eta, 0.f);
+                const float yn = fmaxf(yv - eta * (b + rho * (yv - rgt - s.be[o])) - lam * eta, 0.f);
+                const size_t go = (size_t)c.p0 * FZ_M + o;
+                gzg[go] = a; gyg[go] = b; zo[go] = zn; yo[go] = yn;
+                s.z[o] = zn; s.y[o] = yn;
+            }
+            __syncthreads();
+        }
+        FZ_T(9);
+        // (3) mask, d, corr2d, top-q, tconv
+        x_chain(n + 1, X.z_out, X.y_out, X.med, true, X.fx_in, X.al_in, X.be_in, n == 0, -1, X.dd, X.g, X.x_in, true, X.x_out, X.bits, X.xl_out, -om, X.fx_out);
+        // (4) duals (model.jl:265-266); the duals after the last pass are never read
+        if (X.al_out >= 0) {
+            float* ao = SEQ_Z(X.al_out); float* bo = SEQ_Z(X.be_out);
+            for (int o = threadIdx.x; o < c.nr * FZ_M; o += FZ_THREADS) {
+                const int pl = o / FZ_M, m = o - pl * FZ_M;
+                const float an = s.al[o] + s.fx[pl * FZ_M2 + m] - s.z[o], bn = s.be[o] + s.fx[pl * FZ_M2 + FZ_M + m] - s.y[o];
+                s.al[o] = an; s.be[o] = bn;
+                ao[(size_t)c.p0 * FZ_M + o] = an; bo[(size_t)c.p0 * FZ_M + o] = bn;
+            }
+        }
+        __syncthreads();
+    }
+    FZ_T(10);
+    if (P.forward_only) return;
+
+    // ---- ADMM_DF (model.jl:362-373) ----------------------------------------------------------------------------------------
+    const FzPass& XL = P.px[P.npx - 1];
+    {
+        const float med = group_median(c, s, B, P.npx + 1, nmed);
+        if (c.gidx == 0 && threadIdx.x == 0) data[P.medF + c.g] = med;
+        float* zo = SEQ_ZY(P.zyF);
+        for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) {
+            const int rl = o / FZ_M2, j = o - rl * FZ_M2, m = j < FZ_M ? j : j - FZ_M;
+            const float v = j < FZ_M ? s.z[rl * FZ_M + m] : s.y[rl * FZ_M + m];
+            const float zyv = v >= med ? mf * v : 0.f;
+            s.zyF[o] = zyv; zo[(size_t)c.p0 * FZ_M2 + o] = zyv;
+        }
+        __syncthreads();
+    }
+    float* part = B.part + ((size_t)c.g * c.ng + c.gidx) * FZ_PART;
+    float* gpart = B.part + (size_t)c.g * c.ng * FZ_PART;
+    const int lo7 = max(0, c.p0 - 7), hi7 = min(cc, c.p1 + 7);
+    for (int n = 0; n < P.npd; ++n) {
+        const FzDf& Y = P.df[n];
+        const float mu = sc[Y.i_mu], kap = sc[Y.i_kap], kaps = sc[Y.i_kaps];
+        // D chain: recon with the current D, R = recon + S ('+S': model.jl:282-285), partial 32-lag gradient over own rows
+        {
+            stage_zy_halo(s, SEQ_Z(XL.z_out), SEQ_Z(XL.y_out), lo7, hi7);
+            __syncthreads();
+            recon_rows(c, s, lo7, hi7, c.p0, min(Lb, max(c.p1 + 7, c.q1)), +1.f, SEQ_S(Y.rec), c.p0, c.q1, Lb);
+            __syncthreads();
+            // G[tau][m] += z[p][m] R[4p + tau] + y[p][m] R[4p + 31 - tau]: thread (tau, m) over own rows, fixed order
+            for (int o = threadIdx.x; o < (int)nD; o += FZ_THREADS) {
+                const int tau = o / FZ_M, m = o - tau * FZ_M;
+                float acc = 0.f;
+                for (int pl = 0; pl < c.nr; ++pl) acc += s.z[pl * FZ_M + m] * s.sig[4 * pl + tau] + s.y[pl * FZ_M + m] * s.sig[4 * pl + FZ_FLEN - 1 - tau];
+                part[o] = acc;
+            }
+        }
+        FZ_T(11);
+        // F chain: e = fx(x, F) - (zyF + theta) on own rows (model.jl:294)
+        {
+            tconv_rows(c, s, s.F, SEQ_X(XL.x_out), l, s.A);
+            __syncthreads();
+            float* eg = SEQ_ZY(Y.e);
+            for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) eg[(size_t)c.p0 * FZ_M2 + o] = s.A[o] - s.zyF[o] - s.th[o];
+        }
+        FZ_T(12);
+        group_barrier(c);                                      // partial D gradients and e are published
+        // D update, redundantly in every CTA: G = sum of the group's partials in CTA order; D <- D exp(-mu G), renormalised (model.jl:287-288)
+        {
+            float* Gs = s.w;
+            for (int o = threadIdx.x; o < (int)nD; o += FZ_THREADS) {
+                float acc = 0.f;
+                for (int q = 0; q < c.ng; ++q) acc += __ldcg(gpart + (size_t)q * FZ_PART + o);
+                Gs[o] = acc;
+                if (c.gidx == 0) data[Y.Gm + (int64_t)c.g * nD + o] = acc;
+            }
+            __syncthreads();
+            for (int o = threadIdx.x; o < FZ_FL * FZ_M; o += FZ_THREADS) {
+                const int m = o % FZ_M, j = o / FZ_M;
+                float u[4], sum = 0.f;
+                #pragma unroll
+                for (int a = 0; a < 4; ++a) { const int e = (4 * j + a) * FZ_M + m; u[a] = s.D[e] * expf(-mu * Gs[e]); sum += u[a]; }
+                #pragma unroll
+                for (int a = 0; a < 4; ++a) { const int e = (4 * j + a) * FZ_M + m; const float v = u[a] / sum; s.D[e] = v; if (c.gidx == 0) data[Y.Dn + (int64_t)c.g * nD + e] = v; }
+            }
+            __syncthreads();
+            build_Dt(s);
+            __syncthreads();
+        }
+        FZ_T(13);
+        // F gradient + update for syntax filter k = gidx (model.jl:292-308): Fg[a][j][k] = sum_b sum_i e[b][a+i][j] x[b][i][k]
+        if (c.gidx < FZ_K) {
+            const int k = c.gidx;
+            int* sel_b = reinterpret_cast<int*>(s.A); int* sel_i = sel_b + 512; float* sel_v = reinterpret_cast<float*>(sel_i + 512);
+            int* cnt_p = s.iscr;
+            if (threadIdx.x == 0) { cnt_p[0] = 0; cnt_p[1] = 0; }
+            __syncthreads();
+            // gather the group's codes of filter k in (sequence, position) order: thread = (sequence b, slot q)
+            {
+                const int b = threadIdx.x / LIST_CAP, q = threadIdx.x - b * LIST_CAP;
+                bool hit = false; int e = 0; float v = 0.f;
+                if (b < d.B) {
+                    const int nn = c.g * d.B + b;
+                    const int cn = __ldcg(B.lcnt + (size_t)XL.xl_out * d.NS + nn);
+                    if (cn > LIST_CAP) cnt_p[1] = 1;
+                    else if (q < cn) { e = __ldcg(B.lidx + ((size_t)XL.xl_out * d.NS + nn) * LIST_CAP + q); hit = (e % FZ_K) == k; if (hit) v = __ldcg(B.lval + ((size_t)XL.xl_out * d.NS + nn) * LIST_CAP + q); }
+                }
+                int total;
+                const int o = block_excl_scan512(hit ? 1 : 0, &total, s.iscr + 8);
+                if (hit && o < 512) { sel_b[o] = b; sel_i[o] = e / FZ_K; sel_v[o] = v; }
+                if (threadIdx.x == 0) cnt_p[0] = total;
+            }
+            __syncthreads();
+            const bool dense = cnt_p[1] != 0 || cnt_p[0] > 512 || d.B * LIST_CAP > FZ_THREADS;
+            const int ns = cnt_p[0];
+            const float* Fin = data + Y.F_in + (int64_t)c.g * Y.F_in_gs;
+            float ss = 0.f;
+            float uu[3], gg[3];
+            #pragma unroll
+            for (int it = 0; it < 3; ++it) {
+                const int o = threadIdx.x + it * FZ_THREADS;           // o = a*100 + j
+                uu[it] = 0.f; gg[it] = 0.f;
+                if (o < FZ_H * FZ_M2) {
+                    const int a = o / FZ_M2, j = o - a * FZ_M2;
+                    float acc = 0.f;
+                    if (!dense) {
+                        for (int q = 0; q < ns; ++q) acc += sel_v[q] * __ldcg(data + Y.e + ((int64_t)(c.g * d.B + sel_b[q]) * cc + a + sel_i[q]) * FZ_M2 + j);
+                    } else {
+                        for (int b = 0; b < d.B; ++b)
+                            for (int i = 0; i < l; ++i) {
+                                const float xv = __ldcg(data + XL.x_out + ((int64_t)(c.g * d.B + b) * l + i) * FZ_K + k);
+                                if (xv != 0.f) acc += xv * __ldcg(data + Y.e + ((int64_t)(c.g * d.B + b) * cc + a + i) * FZ_M2 + j);
+                            }
+                    }
+                    gg[it] = acc;
+                    const float u = fmaxf(__ldcg(Fin + (size_t)o * FZ_K + k) - kap * acc - kap * kaps, 0.f);
+                    uu[it] = u; ss += u * u;
+                }
+            }
+            ss = block_sum512(ss, s.red);
+            const float nn = sqrtf(ss);
+            if (threadIdx.x == 0) data[Y.nrm + (int64_t)c.g * FZ_K + k] = nn;
+            #pragma unroll
+            for (int it = 0; it < 3; ++it) {
+                const int o = threadIdx.x + it * FZ_THREADS;
+                if (o < FZ_H * FZ_M2) {
+                    data[Y.Fg + (int64_t)c.g * nF + (size_t)o * FZ_K + k] = gg[it];
+                    data[Y.Fn + (int64_t)c.g * nF + (size_t)o * FZ_K + k] = uu[it] / nn;
+                }
+            }
+        }
+        FZ_T(14);
+        group_barrier(c);                                      // the updated F is published
+        for (int e = threadIdx.x; e < (int)nF / 4; e += FZ_THREADS) reinterpret_cast<float4*>(s.F)[e] = __ldcg(reinterpret_cast<const float4*>(data + Y.Fn + (int64_t)c.g * nF) + e);
+        __syncthreads();
+        // theta <- theta + fx(x, F_new) - zyF (model.jl:370), only needed by the next pass
+        if (Y.has_theta_out) {
+            tconv_rows(c, s, s.F, SEQ_X(XL.x_out), l, s.A);
+            __syncthreads();
+            float* tg = SEQ_ZY(Y.thn);
+            for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) { const float t = s.A[o] - s.zyF[o] + s.th[o]; s.th[o] = t; tg[(size_t)c.p0 * FZ_M2 + o] = t; }
+            __syncthreads();
+        }
+    }
+    FZ_T(15);
+    // ---- loss (model.jl:310-325) with the updated D, F -----------------------------------------------------------------------
+    {
+        stage_zy_halo(s, SEQ_Z(XL.z_out), SEQ_Z(XL.y_out), lo7, hi7);
+        __syncthreads();
+        recon_rows(c, s, lo7, hi7, c.p0, min(Lb, max(c.p1 + 7, c.q1)), -1.f, SEQ_S(P.recL), c.p0, c.q1, Lb);
+        __syncthreads();
+        float a = 0.f, b = 0.f;
+        for (int t = threadIdx.x; t < 4 * (c.q1 - c.p0); t += FZ_THREADS) { const float r = s.sig[t]; a += r * r; }
+        tconv_rows(c, s, s.F, SEQ_X(XL.x_out), l, s.A);
+        __syncthreads();
+        float* fg = SEQ_ZY(P.fxL);
+        for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) { const float v = s.A[o]; fg[(size_t)c.p0 * FZ_M2 + o] = v; const float dlt = v - s.zyF[o]; b += dlt * dlt; }
+        a = block_sum512(a, s.red);
+        b = block_sum512(b, s.red);
+        if (threadIdx.x == 0) { part[0] = a; part[1] = b; }
+        group_barrier(c);
+        if (c.gidx == 0 && threadIdx.x == 0) {
+            float sa = 0.f, sb = 0.f;
+            for (int q = 0; q < c.ng; ++q) { sa += __ldcg(gpart + (size_t)q * FZ_PART); sb += __ldcg(gpart + (size_t)q * FZ_PART + 1); }
+            data[P.loss + c.g * 3 + 0] = (sa + sb) / (float)d.B; data[P.loss + c.g * 3 + 1] = sa / (float)d.B; data[P.loss + c.g * 3 + 2] = sb / (float)d.B;
+        }
+    }
+#ifdef FZ_PROFILE
+    FZ_T(11);
+    {   // pure barrier latency: 16 back-to-back barriers with no work in between
+        const long long t0 = clock64();
+        for (int i = 0; i < 16; ++i) group_barrier(c);
+        const long long t1 = clock64();
+        for (int i = 0; i < 16; ++i) cluster_barrier();
+        const long long t2 = clock64();
+        if (blockIdx.x == 0 && threadIdx.x == 0) printf("[fz] back-to-back: group barrier %lld clk, cluster barrier %lld clk\n", (t1 - t0) / 16, (t2 - t1) / 16);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const char* nm[16] = {"prologue", "warm_zy", "median", "A tile", "corr2d", "g+cluster bar", "topq", "tconv+store", "recon", "corr_sig+zy", "stage zy halo", "DF D-chain+loss", "DF e", "barA+D update", "F update", "barB+F load+theta"};
+        long long tot = 0; for (int i = 0; i < 16; ++i) tot += fz_acc[i];
+        for (int i = 0; i < 16; ++i) printf("[fz] %-20s %9lld clk %5.1f%%\n", nm[i], fz_acc[i], 100.0 * fz_acc[i] / tot);
+        printf("[fz] total %lld clk; %d group barriers, %lld clk inside them (thread 0): fence %lld, arrive+poll %lld, fence %lld\n", tot, c.nbar, c.tbar, c.tb1, c.tb2, c.tb3);
+    }
+#endif
+#undef SEQ_Z
+#undef SEQ_ZY
+#undef SEQ_X
+#undef SEQ_S
+#undef LCNT_
+#undef LIDX_
+#undef LVAL_
+}
+
+// =================================================================================================================================
+// reverse pass of the ADMM_XYZ passes (the bulk of the step: 6 of the 9 unrolled passes) as one persistent kernel
+// =================================================================================================================================
+// Hand-derived adjoints of one_forward_step_XYZ (model.jl:256-268), same cluster-per-sequence layout as the forward kernel.  The
+// adjoint of a pass's outputs (z+, y+, x+, fx+, alpha+, beta+) is turned into the adjoint of its inputs; masks, top-q supports and the
+// zero duals are constants exactly where the reference uses @ignore.  Three cluster barriers per pass (halo exchanges of dfx+, of the
+// sparse dx values, of dgz/dgy) and no barrier across sequences: gradients of the shared parameters (D, F, the per-pass scalars) are
+// accumulated per CTA and summed once at the end in CTA order (deterministic).  The adjoint of x is only ever needed on the support the
+// top-q kept (model.jl:190 masks everything else), so the adjoint of fx = x (*) F is a handful of 1200-term dot products per sequence
+// instead of the dense contraction.
+#define FZ_KCAP 256               // kept entries per sequence the kernel handles (q = 32 plus ties); more raises the error flag
+
+struct FzBwd {                    // extra buffers of the reverse pass
+    float* grad;                  // the tape's adjoint arena (same offsets as data)
+    float* dFp;                   // [G][48][h*K*2M] per-CTA partial of dF, layout [a][k][j]
+    float* xch;                   // [NS][FZ_KCAP] exchange of the sparse dx values inside a cluster
+    float* gsum;                  // [G][nF + nD + 64] group sums: dF (layout [a][j][k]), dD, dsc
+    unsigned int* err;            // set when a sequence has more than FZ_KCAP kept entries / an overlong code list
+};
+
+namespace fz {
+
+struct SmemB {
+    float *F, *D, *Dt, *Dr;
+    float *dz, *dy, *dal, *dbe, *gzs, *gys, *zs, *ys;   // [R][50]
+    float *dfx;                                         // [R][100]
+    float *A;                                           // work tile (own rows [R][100] / halo staging)
+    float *sig, *sig2;                                  // drec and r = rec - S over base positions [p0, p1 + 7)
+    float *w;                                           // row lists of tconv
+    float *dDp, *dscp;                                  // partial dD [32][50], partial scalar gradients [64]
+    float *dxd;                                         // dense map [l][K] of the adjoint of the current x
+    int *kl; float *kv;                                 // kept entries (flat index) and their values
+    int *li2; float *lv2;                               // code list of x+ (from the tape)
+    int *istart;                                        // [R + 14] first list entry per position
+    float* red; int* iscr; uint8_t* b;
+};
+__host__ __device__ inline size_t fzb_smem_bytes(int Lb) {
+    const int c = Lb - FZ_FL + 1, l = c - FZ_H + 1, R = fz_rows(c);
+    size_t f = (size_t)FZ_H * FZ_M2 * FZ_K + 3 * FZ_FLEN * FZ_M;
+    f += (size_t)R * (FZ_M * 8 + FZ_M2);
+    const size_t A = (size_t)R * FZ_M2, A2 = (size_t)2 * (R + 14) * FZ_M;
+    f += (A > A2 ? A : A2);
+    f += (size_t)8 * (R + 8);
+    f += 32 + 64 * LIST_CAP;                              // row lists
+    f += FZ_FLEN * FZ_M + 64;
+    f += (size_t)l * FZ_K;
+    f += 2 * FZ_KCAP + 2 * LIST_CAP + (R + 16) + 64;
+    return f * 4 + (size_t)(R + 16) + 64;
+}
+__device__ __forceinline__ void carve_b(SmemB& s, float* base, int R, int Lb) {
+    const int c = Lb - FZ_FL + 1, l = c - FZ_H + 1;
+    float* p = base;
+    s.F = p; p += FZ_H * FZ_M2 * FZ_K;
+    s.D = p; p += FZ_FLEN * FZ_M; s.Dt = p; p += FZ_FLEN * FZ_M; s.Dr = p; p += FZ_FLEN * FZ_M;
+    s.dz = p; p += R * FZ_M; s.dy = p; p += R * FZ_M; s.dal = p; p += R * FZ_M; s.dbe = p; p += R * FZ_M;
+    s.gzs = p; p += R * FZ_M; s.gys = p; p += R * FZ_M; s.zs = p; p += R * FZ_M; s.ys = p; p += R * FZ_M;
+    s.dfx = p; p += R * FZ_M2;
+    const size_t A = (size_t)R * FZ_M2, A2 = (size_t)2 * (R + 14) * FZ_M;
+    s.A = p; p += (A > A2 ? A : A2);
+    s.sig = p; p += 4 * (R + 8); s.sig2 = p; p += 4 * (R + 8);
+    s.w = p; p += 32 + 64 * LIST_CAP;
+    s.dDp = p; p += FZ_FLEN * FZ_M; s.dscp = p; p += 64;
+    s.dxd = p; p += (size_t)l * FZ_K;
+    s.kl = reinterpret_cast<int*>(p); p += FZ_KCAP; s.kv = p; p += FZ_KCAP;
+    s.li2 = reinterpret_cast<int*>(p); p += LIST_CAP; s.lv2 = p; p += LIST_CAP;
+    s.istart = reinterpret_cast<int*>(p); p += R + 16;
+    s.red = p; p += 32; s.iscr = reinterpret_cast<int*>(p); p += 32;
+    s.b = reinterpret_cast<uint8_t*>(p);
+}
+
+// dFp[a][k][j] += sum over own rows r and list entries (i, k, v) with a = r - i in [0, 12): Arow[r][j] * v      (F_gradient, model.jl:292-302,
+// restricted to the CTA's rows; one thread per (a, j) walks its rows in order: no two threads share a target, the order is fixed)
+__device__ void fgrad_scatter(const Ctx& c, const float* Arow, const int* li, const float* lv, int cnt, int l, float* dFp, int* istart) {
+    // entries are ordered by flat index = (position, filter): first entry at or after every position of [p0 - 11, p1]
+    const int i_lo = c.p0 - (FZ_H - 1), npos = c.nr + FZ_H;
+    for (int t = threadIdx.x; t <= npos; t += FZ_THREADS) {
+        const int key = (i_lo + t) * FZ_K;
+        int lo = 0, hi = cnt;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (li[mid] < key) lo = mid + 1; else hi = mid; }
+        istart[t] = lo;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < FZ_H * FZ_M2; o += FZ_THREADS) {
+        const int a = o / FZ_M2, j = o - a * FZ_M2;
+        for (int pl = 0; pl < c.nr; ++pl) {
+            const int i = c.p0 + pl - a;
+            if (i < 0 || i >= l) continue;
+            const int t = i - i_lo;
+            const int q0 = istart[t], q1 = istart[t + 1];
+            if (q0 == q1) continue;
+            const float av = Arow[pl * FZ_M2 + j];
+            for (int q = q0; q < q1; ++q) { const int k = li[q] - i * FZ_K; dFp[(a * FZ_K + k) * FZ_M2 + j] += av * lv[q]; }
+        }
+    }
+    __syncthreads();
+}
+
+}  // namespace fz
+
+__global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_csc_fused_bwd_xyz(const FzPlan P, const FzBufs B, const FzBwd W, const CscDims d) {
+    using namespace fz;
+    extern __shared__ __align__(16) float fz_smem[];
+    const int Lb = d.Lb, cc = d.c, l = d.l;
+    const int R = fz_rows(cc);
+    SmemB s; carve_b(s, fz_smem, R, Lb);
+    Ctx c;
+    c.n = blockIdx.x / FZ_CL; c.r = blockIdx.x % FZ_CL; c.g = c.n / d.B; c.gidx = (c.n % d.B) * FZ_CL + c.r; c.ng = d.B * FZ_CL; c.ncl = d.B;
+    c.p0 = min(cc, c.r * R); c.p1 = min(cc, c.p0 + R); c.nr = c.p1 - c.p0;
+    c.i0 = min(l, c.p0); c.i1 = min(l, c.p1); c.ni = c.i1 - c.i0;
+    c.q1 = (c.r == FZ_CL - 1) ? Lb : c.p1;
+    c.epoch = 0; c.bar = B.bar + c.g; c.tbar = 0; c.nbar = 0; c.tb1 = c.tb2 = c.tb3 = 0;
+    float* const data = B.data; float* const grad = W.grad;
+    const float* sc = data + P.sc;
+    const int64_t nZ = (int64_t)cc * FZ_M, nZY = (int64_t)cc * FZ_M2, nX = (int64_t)l * FZ_K, nS = (int64_t)4 * Lb;
+    const int nD = FZ_FLEN * FZ_M, nF = FZ_H * FZ_M2 * FZ_K;
+    const float mf = d.mf;
+    const int E = l * FZ_K;
+    // Smem view that the shared device functions (recon_rows, tconv_list) expect
+    Smem sv; sv.F = s.F; sv.D = s.D; sv.Dt = s.Dt; sv.Dr = s.Dr; sv.A = s.A; sv.sig = s.sig; sv.w = s.w; sv.b = s.b; sv.red = s.red; sv.iscr = s.iscr;
+    sv.z = sv.y = sv.fx = sv.al = sv.be = sv.th = sv.zyF = sv.gout = nullptr; sv.li = s.kl; sv.lv = s.kv; sv.lc = nullptr;
+    float* dFp = W.dFp + ((size_t)c.g * c.ng + c.gidx) * nF;
+#define SEQ(off, per) ((off) + (int64_t)c.n * (per))
+    // ---- prologue ----------------------------------------------------------------------------------------------------------------
+    for (int e = threadIdx.x; e < nF / 4; e += FZ_THREADS) reinterpret_cast<float4*>(s.F)[e] = __ldcg(reinterpret_cast<const float4*>(data + P.Fe) + e);
+    for (int e = threadIdx.x; e < nD; e += FZ_THREADS) { s.D[e] = __ldcg(data + P.De + e); s.dDp[e] = 0.f; }
+    if (threadIdx.x < 64) s.dscp[threadIdx.x] = 0.f;
+    for (int e = threadIdx.x; e < nF / 4; e += FZ_THREADS) reinterpret_cast<float4*>(dFp)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int nb_own = min(Lb, c.p1 + 7 + FZ_FL) - c.p0;
+    for (int e = threadIdx.x; e < nb_own; e += FZ_THREADS) s.b[e] = B.bases[(size_t)c.n * Lb + c.p0 + e];
+    const FzPass& XL = P.px[P.npx - 1];
+    {   // adjoints handed over by the ops after the passes (DF, loss): dz, dy of the final codes, dx of the final x (dense)
+        const float* gz_ = grad + SEQ(XL.z_out, nZ) + (size_t)c.p0 * FZ_M; const float* gy_ = grad + SEQ(XL.y_out, nZ) + (size_t)c.p0 * FZ_M;
+        for (int o = threadIdx.x; o < c.nr * FZ_M; o += FZ_THREADS) { s.dz[o] = __ldcg(gz_ + o); s.dy[o] = __ldcg(gy_ + o); s.dal[o] = 0.f; s.dbe[o] = 0.f; }
+        for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) s.dfx[o] = 0.f;
+        const float* gx_ = grad + SEQ(XL.x_out, nX);
+        for (int e = threadIdx.x; e < E; e += FZ_THREADS) s.dxd[e] = __ldcg(gx_ + e);
+    }
+    __syncthreads();
+    build_Dt(sv);
+    __syncthreads();
+
+    for (int n = P.npx - 1; n >= 0; --n) {
+        const FzPass& X = P.px[n];
+        const float eta = sc[X.i_eta], lam = sc[X.i_lam], rho = sc[X.i_rho], om = sc[X.i_om];
+        // kept entries of x+ (the top-q bitmap of this pass), ordered by flat index; redundantly in every CTA of the cluster
+        int cnt;
+        {
+            const uint8_t* bits = B.bits + X.bits + (size_t)c.n * nX;
+            const int per = (E + FZ_THREADS - 1) / FZ_THREADS;
+            const int e0 = threadIdx.x * per, e1 = min(E, e0 + per);
+            int k = 0;
+            for (int e = e0; e < e1; ++e) k += bits[e] != 0;
+            int total;
+            int o = block_excl_scan512(k, &total, s.iscr + 8);
+            for (int e = e0; e < e1; ++e) if (bits[e] != 0) { if (o < FZ_KCAP) s.kl[o] = e; ++o; }
+            if (total > FZ_KCAP) { if (threadIdx.x == 0) atomicOr(W.err, 1u); total = FZ_KCAP; }
+            cnt = total;
+        }
+        // (i') duals: alpha+ = alpha + fx+_l - z+, beta+ likewise (model.jl:265-266); not computed by the last pass
+        if (X.al_out >= 0)
+            for (int o = threadIdx.x; o < c.nr * FZ_M; o += FZ_THREADS) {
+                const int pl = o / FZ_M, m = o - pl * FZ_M;
+                const float da = s.dal[o], db = s.dbe[o];
+                s.dfx[pl * FZ_M2 + m] += da; s.dfx[pl * FZ_M2 + FZ_M + m] += db; s.dz[o] -= da; s.dy[o] -= db;
+            }
+        __syncthreads();
+        float* dfx_g = grad + SEQ(X.fx_out, nZY);                 // scratch: the tape's slot of d fx+ (unused otherwise)
+        for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) dfx_g[(size_t)c.p0 * FZ_M2 + o] = s.dfx[o];
+        // code list of x+ from the tape (for the F gradient of fx+ = x+ (*) F)
+        int cnt2 = __ldcg(B.lcnt + (size_t)X.xl_out * d.NS + c.n);
+        if (cnt2 > LIST_CAP) { if (threadIdx.x == 0) atomicOr(W.err, 2u); cnt2 = LIST_CAP; }
+        if (threadIdx.x < cnt2) { s.li2[threadIdx.x] = __ldcg(B.lidx + ((size_t)X.xl_out * d.NS + c.n) * LIST_CAP + threadIdx.x); s.lv2[threadIdx.x] = __ldcg(B.lval + ((size_t)X.xl_out * d.NS + c.n) * LIST_CAP + threadIdx.x); }
+        cluster_barrier();                                        // #1: every CTA's rows of d fx+ are published
+        // (h') adjoint of fx+ = x+ (*) F on the kept support: entry q is taken by CTA q % 8, one warp per entry
+        {
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            float* xch = W.xch + (size_t)c.n * FZ_KCAP;
+            for (int q = c.r + FZ_CL * warp; q < cnt; q += FZ_CL * (FZ_THREADS / 32)) {
+                const int e = s.kl[q], i = e / FZ_K, k = e - i * FZ_K;
+                const float* rows = grad + SEQ(X.fx_out, nZY) + (size_t)i * FZ_M2;        // rows i .. i+11 are contiguous: 1200 floats
+                float acc = 0.f;
+                for (int t = lane; t < FZ_H * FZ_M2; t += 32) acc += __ldcg(rows + t) * s.F[(size_t)t * FZ_K + k];
+                acc = warp_sum(acc);
+                if (lane == 0) xch[q] = acc + s.dxd[e];
+            }
+        }
+        fgrad_scatter(c, s.dfx, s.li2, s.lv2, cnt2, l, dFp, s.istart);
+        cluster_barrier();                                        // #2: the sparse d x+ values are published
+        // (g') top-q adjoint (model.jl:190-192, 252-253): gr = d x+ on the kept support; d x = gr, d g = -omega gr, d omega = -sum gr g
+        {
+            const float* xch = W.xch + (size_t)c.n * FZ_KCAP;
+            const float* gg = data + SEQ(X.g, nX);
+            float som = 0.f;
+            for (int e = threadIdx.x; e < E; e += FZ_THREADS) s.dxd[e] = 0.f;
+            __syncthreads();
+            if (threadIdx.x < cnt) {
+                const float gr = __ldcg(xch + threadIdx.x);
+                const int e = s.kl[threadIdx.x];
+                s.dxd[e] = gr;
+                som = -gr * __ldcg(gg + e);
+                s.kv[threadIdx.x] = -om * gr;                      // the d g list shares the kept entries
+            }
+            som = block_sum512(som, s.red);
+            if (threadIdx.x == 0 && c.r == 0) s.dscp[X.i_om] += som;
+            __syncthreads();
+        }
+        // (f') adjoint of g = corr2d(dd, F): d dd = dg (*) F on own rows; dF += F_gradient(dd, dg)
+        tconv_list(c, sv, s.F, s.kl, s.kv, cnt, FZ_KCAP, nullptr, l, s.A);
+        {
+            const float* ddg = data + SEQ(X.dd, nZY) + (size_t)c.p0 * FZ_M2;
+            for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) s.dfx[o] = __ldcg(ddg + o);       // d fx+ is consumed: reuse its rows for dd
+            __syncthreads();
+            fgrad_scatter(c, s.dfx, s.kl, s.kv, cnt, l, dFp, s.istart);
+        }
+        // (e', d', c') d_build, mask, ISTA step (model.jl:248-250, 206-210, 240-244) on own rows
+        {
+            const float med = __ldcg(data + X.med + c.g);
+            const size_t ro = (size_t)c.p0 * FZ_M;
+            const float* zo = data + SEQ(X.z_out, nZ) + ro; const float* yo = data + SEQ(X.y_out, nZ) + ro;
+            const float* zi = data + SEQ(X.z_in, nZ) + ro; const float* yi = data + SEQ(X.y_in, nZ) + ro;
+            const float* gzd = data + SEQ(X.gz, nZ) + ro; const float* gyd = data + SEQ(X.gy, nZ) + ro;
+            const float* fxi = data + SEQ(X.fx_in, nZY) + (size_t)c.p0 * FZ_M2;
+            const float* ali = n > 0 ? data + SEQ(X.al_in, nZ) + ro : nullptr; const float* bei = n > 0 ? data + SEQ(X.be_in, nZ) + ro : nullptr;
+            float* dgz_g = grad + SEQ(X.gz, nZ) + ro; float* dgy_g = grad + SEQ(X.gy, nZ) + ro;
+            float s_eta = 0.f, s_lam = 0.f, s_rho = 0.f;
+            for (int o = threadIdx.x; o < c.nr * FZ_M; o += FZ_THREADS) {
+                const int pl = o / FZ_M, m = o - pl * FZ_M;
+                const float zov = __ldcg(zo + o), yov = __ldcg(yo + o), ziv = __ldcg(zi + o), yiv = __ldcg(yi + o);
+                const float gzv = __ldcg(gzd + o), gyv = __ldcg(gyd + o);
+                const float lft = __ldcg(fxi + pl * FZ_M2 + m), rgt = __ldcg(fxi + pl * FZ_M2 + FZ_M + m);
+                const float av = ali ? __ldcg(ali + o) : 0.f, bv = bei ? __ldcg(bei + o) : 0.f;
+                const float dl = s.A[pl * FZ_M2 + m], dr = s.A[pl * FZ_M2 + FZ_M + m];          // d dd
+                float dzo = s.dz[o], dyo = s.dy[o];
+                if (zov >= med) dzo += mf * (-dl);
+                if (yov >= med) dyo += mf * (-dr);
+                const float tz = zov > 0.f ? dzo : 0.f, ty = yov > 0.f ? dyo : 0.f;
+                const float ez = ziv - lft - av, ey = yiv - rgt - bv;
+                s.dz[o] = tz * (1.f - eta * rho); s.dy[o] = ty * (1.f - eta * rho);
+                const float dgz = -eta * tz, dgy = -eta * ty;
+                s.gzs[o] = dgz; s.gys[o] = dgy; dgz_g[o] = dgz; dgy_g[o] = dgy;
+                s.zs[o] = ziv; s.ys[o] = yiv;
+                s.dfx[pl * FZ_M2 + m] = dl + eta * rho * tz; s.dfx[pl * FZ_M2 + FZ_M + m] = dr + eta * rho * ty;
+                s.dal[o] += dl + eta * rho * tz; s.dbe[o] += dr + eta * rho * ty;
+                s_eta += tz * (-(gzv + rho * ez) - lam) + ty * (-(gyv + rho * ey) - lam);
+                s_lam += -eta * (tz + ty);
+                s_rho += -eta * (tz * ez + ty * ey);
+            }
+            s_eta = block_sum512(s_eta, s.red); s_lam = block_sum512(s_lam, s.red); s_rho = block_sum512(s_rho, s.red);
+            if (threadIdx.x == 0) { s.dscp[X.i_eta] += s_eta; s.dscp[X.i_lam] += s_lam; s.dscp[X.i_rho] += s_rho; }
+        }
+        cluster_barrier();                                        // #3: every CTA's rows of dgz, dgy are published
+        // (b') d rec = recon(dgz, dgy; D) over base positions [p0, p1 + 7) (halo rows recomputed from the neighbours' dgz, dgy); r = rec - S
+        {
+            const int lo = max(0, c.p0 - 7), hi = min(cc, c.p1 + 7);
+            const int q0 = c.p0, q1 = min(Lb, c.p1 + 7);
+            if (c.nr > 0) {
+                stage_zy_halo(sv, grad + SEQ(X.gz, nZ), grad + SEQ(X.gy, nZ), lo, hi);
+                const float* recg = data + SEQ(X.rec, nS);
+                for (int t = threadIdx.x; t < 4 * (q1 - q0); t += FZ_THREADS) {
+                    const int q = q0 + (t >> 2);
+                    s.sig2[t] = __ldcg(recg + 4 * q0 + t) - (s.b[q - c.p0] == (t & 3) ? 1.f : 0.f);
+                }
+                __syncthreads();
+                recon_rows(c, sv, lo, hi, q0, q1, 0.f, nullptr, 0, 0, Lb);
+            }
+            __syncthreads();
+        }
+        // dD += dgrad(dgz, dgy; r) + dgrad(z, y; d rec)  (32-lag gradient, model.jl:270-290 form) over own rows; then
+        // (a') dz += corr_sig(d rec; D), dy likewise
+        for (int o = threadIdx.x; o < nD; o += FZ_THREADS) {
+            const int tau = o / FZ_M, m = o - tau * FZ_M;
+            float acc = 0.f;
+            for (int pl = 0; pl < c.nr; ++pl)
+                acc += s.gzs[pl * FZ_M + m] * s.sig2[4 * pl + tau] + s.gys[pl * FZ_M + m] * s.sig2[4 * pl + FZ_FLEN - 1 - tau]
+                     + s.zs[pl * FZ_M + m] * s.sig[4 * pl + tau] + s.ys[pl * FZ_M + m] * s.sig[4 * pl + FZ_FLEN - 1 - tau];
+            s.dDp[o] += acc;
+        }
+        for (int o = threadIdx.x; o < c.nr * FZ_M; o += FZ_THREADS) {
+            const int pl = o / FZ_M, m = o - pl * FZ_M;
+            float a = 0.f, b = 0.f;
+            #pragma unroll 8
+            for (int k = 0; k < FZ_FLEN; ++k) { const float r = s.sig[4 * pl + k]; a += r * s.D[k * FZ_M + m]; b += r * s.D[(FZ_FLEN - 1 - k) * FZ_M + m]; }
+            s.dz[o] += a; s.dy[o] += b;
+        }
+        __syncthreads();
+    }
+    // ---- hand the adjoints of the warm-up outputs back to the tape: d z0, d y0, d fx0, d x0 -------------------------------------------
+    {
+        const FzPass& X0 = P.px[0];
+        float* gz_ = grad + SEQ(X0.z_in, nZ) + (size_t)c.p0 * FZ_M; float* gy_ = grad + SEQ(X0.y_in, nZ) + (size_t)c.p0 * FZ_M;
+        for (int o = threadIdx.x; o < c.nr * FZ_M; o += FZ_THREADS) { gz_[o] = s.dz[o]; gy_[o] = s.dy[o]; }
+        float* gf_ = grad + SEQ(X0.fx_in, nZY) + (size_t)c.p0 * FZ_M2;
+        for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) gf_[o] = s.dfx[o];
+        float* gx_ = grad + SEQ(X0.x_in, nX);
+        for (int e = c.i0 * FZ_K + threadIdx.x; e < c.i1 * FZ_K; e += FZ_THREADS) gx_[e] = s.dxd[e];
+    }
+    // ---- gradients of the shared parameters: per-CTA partials -> group sums in CTA order ------------------------------------------------
+    float* part = B.part + ((size_t)c.g * c.ng + c.gidx) * FZ_PART;
+    for (int o = threadIdx.x; o < nD; o += FZ_THREADS) part[o] = s.dDp[o];
+    if (threadIdx.x < 64) part[nD + threadIdx.x] = s.dscp[threadIdx.x];
+    group_barrier(c);
+    {
+        const float* gpart = B.part + (size_t)c.g * c.ng * FZ_PART;
+        const float* gF = W.dFp + (size_t)c.g * c.ng * nF;
+        float* gs = W.gsum + (size_t)c.g * (nF + nD + 64);
+        const int per = (nF + c.ng - 1) / c.ng;
+        for (int o = c.gidx * per + threadIdx.x; o < min(nF, (c.gidx + 1) * per); o += FZ_THREADS) {
+            const int k = o % FZ_K, aj = o / FZ_K, j = aj % FZ_M2, a = aj / FZ_M2;
+            const int po = (a * FZ_K + k) * FZ_M2 + j;
+            float acc = 0.f;
+            for (int q = 0; q < c.ng; ++q) acc += __ldcg(gF + (size_t)q * nF + po);
+            gs[o] = acc;
+        }
+        const int perd = (nD + 64 + c.ng - 1) / c.ng;
+        for (int o = c.gidx * perd + threadIdx.x; o < min(nD + 64, (c.gidx + 1) * perd); o += FZ_THREADS) {
+            float acc = 0.f;
+            for (int q = 0; q < c.ng; ++q) acc += __ldcg(gpart + (size_t)q * FZ_PART + o);
+            gs[nF + o] = acc;
+        }
+    }
+#undef SEQ
+}
+
+// adds the group sums of the fused reverse pass to the tape's adjoints of the prepared filters / scalars (deterministic: groups in order)
+__global__ void __launch_bounds__(256) k_csc_fused_finish(const float* __restrict__ gsum, int G, int nF, int nD, int nsc, float* __restrict__ gF, float* __restrict__ gD, float* __restrict__ gsc) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tot = nF + nD + 64;
+    if (o >= tot) return;
+    float acc = 0.f;
+    for (int g = 0; g < G; ++g) acc += gsum[(size_t)g * tot + o];
+    if (o < nF) gF[o] += acc;
+    else if (o < nF + nD) gD[o - nF] += acc;
+    else if (o - nF - nD < nsc) gsc[o - nF - nD] += acc;
+}

@@ -320,3 +320,27 @@ def test_per_step_parity_on_training_steps_1_2_3_1000(ctx):
         m.adabelief_step()
     assert losses[1000] < losses[1]                                          # and the run did train
     m.free(); seqs.free()
+
+
+@pytest.mark.parametrize("Lb,groups", [(100, 1), (200, 1), (64, 2), (100, 2)])
+def test_fused_forward_kernel_matches_the_tape(ctx, Lb, groups):
+    """csc_fused.cuh (one persistent cluster kernel for the forward pass) against the kernel-per-op tape (MB200_CSC_NO_FUSED): same
+    discrete results (top-q supports, i.e. the same median masks), values and gradients equal within fp32 summation order."""
+    hp, ohp, a, seqs, flat = _setup(ctx, 40, Lb, 21)
+    mf = mb._lib.CscModel(ctx, hp, Lb, n_groups=groups)
+    mt = mb._lib.CscModel(ctx, hp, Lb, n_groups=groups, fused=False)
+    mf.set_params(flat); mt.set_params(flat)
+    idx = np.random.default_rng(5).permutation(40)[:6 * groups]
+    lf, gf = mf.loss_grad(seqs, idx)
+    lt, gt = mt.loss_grad(seqs, idx)
+    assert np.allclose(lf, lt, rtol=2e-6)
+    B, c, l = hp.batch_size * groups, Lb - 7, Lb - 7 - 11
+    for name, n in (("x", B * l * hp.K), ("z", B * c * hp.M), ("y", B * c * hp.M), ("zy", B * c * hp.twoM), ("D", groups * 32 * hp.M), ("F", groups * hp.h * hp.twoM * hp.K)):
+        bf, bt = mf.get_buffer(name, n), mt.get_buffer(name, n)
+        assert np.array_equal(bf != 0, bt != 0), name
+        assert np.allclose(bf, bt, rtol=1e-4, atol=1e-6), name
+    assert np.abs(gf - gt).max() <= 2e-5 * np.abs(gt).max()
+    # deterministic: a second run of the same step returns the same bits
+    lf2, gf2 = mf.loss_grad(seqs, idx)
+    assert np.array_equal(lf, lf2)
+    mf.free(); mt.free(); seqs.free()
