@@ -533,7 +533,7 @@ static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
             }
             if (s->fused_bwd) {
                 const size_t nF = (size_t)d.h * d.M2 * d.K, nD = (size_t)d.f_len * d.M;
-                const size_t n_dFp = G * (size_t)d.B * FZ_CL * nF, n_xch = (size_t)d.NS * FZ_KCAP, n_gsum = G * (nF + nD + 64);
+                const size_t n_dFp = (size_t)d.NS * nF, n_xch = (size_t)d.NS * FZ_KCAP, n_gsum = G * (nF + nD + 64);
                 MB_CUDA(ctx, cudaMalloc(&s->fz_bwd_buf, (n_dFp + n_xch + n_gsum + 64) * 4));
                 MB_CUDA(ctx, cudaMemset(s->fz_bwd_buf, 0, (n_dFp + n_xch + n_gsum + 64) * 4));
                 s->fzw.grad = s->grad; s->fzw.dFp = s->fz_bwd_buf; s->fzw.xch = s->fz_bwd_buf + n_dFp; s->fzw.gsum = s->fzw.xch + n_xch;

@@ -916,7 +916,7 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
 
 struct FzBwd {                    // extra buffers of the reverse pass
     float* grad;                  // the tape's adjoint arena (same offsets as data)
-    float* dFp;                   // [G][48][h*K*2M] per-CTA partial of dF, layout [a][k][j]
+    float* dFp;                   // [NS][h*K][2M] per-sequence partial of dF, layout [a][k][j] (row t = a*K + k written by the cluster's CTA t % 8)
     float* xch;                   // [NS][FZ_KCAP] exchange of the sparse dx values inside a cluster
     float* gsum;                  // [G][nF + nD + 64] group sums: dF (layout [a][j][k]), dD, dsc
     unsigned int* err;            // set when a sequence has more than FZ_KCAP kept entries / an overlong code list
@@ -924,8 +924,10 @@ struct FzBwd {                    // extra buffers of the reverse pass
 
 namespace fz {
 
+#define FZ_NTGT ((FZ_H * FZ_K + FZ_CL - 1) / FZ_CL)      // dF targets (a, k) a CTA owns: t = a*K + k with t % 8 == rank
 struct SmemB {
     float *F, *D, *Dt, *Dr;
+    float *dFt;                                         // [FZ_NTGT][2M] this CTA's partial of dF for the targets it owns
     float *dz, *dy, *dal, *dbe, *gzs, *gys, *zs, *ys;   // [R][50]
     float *dfx;                                         // [R][100]
     float *A;                                           // work tile (own rows [R][100] / halo staging)
@@ -940,7 +942,7 @@ struct SmemB {
 };
 __host__ __device__ inline size_t fzb_smem_bytes(int Lb) {
     const int c = Lb - FZ_FL + 1, l = c - FZ_H + 1, R = fz_rows(c);
-    size_t f = (size_t)FZ_H * FZ_M2 * FZ_K + 3 * FZ_FLEN * FZ_M;
+    size_t f = (size_t)FZ_H * FZ_M2 * FZ_K + 3 * FZ_FLEN * FZ_M + (size_t)FZ_NTGT * FZ_M2;
     f += (size_t)R * (FZ_M * 8 + FZ_M2);
     const size_t A = (size_t)R * FZ_M2, A2 = (size_t)2 * (R + 14) * FZ_M;
     f += (A > A2 ? A : A2);
@@ -956,6 +958,7 @@ __device__ __forceinline__ void carve_b(SmemB& s, float* base, int R, int Lb) {
     float* p = base;
     s.F = p; p += FZ_H * FZ_M2 * FZ_K;
     s.D = p; p += FZ_FLEN * FZ_M; s.Dt = p; p += FZ_FLEN * FZ_M; s.Dr = p; p += FZ_FLEN * FZ_M;
+    s.dFt = p; p += FZ_NTGT * FZ_M2;
     s.dz = p; p += R * FZ_M; s.dy = p; p += R * FZ_M; s.dal = p; p += R * FZ_M; s.dbe = p; p += R * FZ_M;
     s.gzs = p; p += R * FZ_M; s.gys = p; p += R * FZ_M; s.zs = p; p += R * FZ_M; s.ys = p; p += R * FZ_M;
     s.dfx = p; p += R * FZ_M2;
@@ -999,6 +1002,53 @@ __device__ void fgrad_scatter(const Ctx& c, const float* Arow, const int* li, co
     __syncthreads();
 }
 
+// F_gradient (model.jl:292-302) of one sequence, balanced over its cluster whatever rows the codes sit in: dF[a][k][:] += sum over the list
+// entries (i, k, v) of v * A[i + a][:].  CTA r of the cluster owns the targets (a, k) with (a*K + k) % 8 == r; one warp per owned target
+// walks the list in order (fixed summation order), reads the rows of A from global memory (published before the preceding barrier) and
+// does ONE update of the CTA's shared-memory partial.  No two warps share a target, no atomics.
+__device__ void fgrad_targets(const Ctx& c, const float* Ag /* global [c][2M] of the sequence */, const int* li, const float* lv, int cnt, float* dFt) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t = c.r + FZ_CL * warp; t < FZ_H * FZ_K; t += FZ_CL * (FZ_THREADS / 32)) {
+        const int a = t / FZ_K, k = t - a * FZ_K;
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        bool any = false;
+        for (int q0 = 0; q0 < cnt; q0 += 32) {
+            const int q = q0 + lane;
+            int e = -1;
+            if (q < cnt) e = li[q];
+            const bool hit = e >= 0 && (e % FZ_K) == k;
+            unsigned mk = __ballot_sync(FULLMASK, hit);
+            while (mk) {
+                // up to four hits per trip: all their row loads are in flight together (an L2 round trip per hit would dominate otherwise)
+                float v[4]; const float* row[4];
+                #pragma unroll
+                for (int hh = 0; hh < 4; ++hh) {
+                    if (mk) {
+                        const int src = __ffs(mk) - 1; mk &= mk - 1;
+                        const int ee = __shfl_sync(FULLMASK, e, src);
+                        v[hh] = lv[q0 + src]; row[hh] = Ag + (size_t)(ee / FZ_K + a) * FZ_M2;
+                    } else { v[hh] = 0.f; row[hh] = Ag; }
+                }
+                float x0[4], x1[4], x2[4], x3[4];
+                #pragma unroll
+                for (int hh = 0; hh < 4; ++hh) {
+                    x0[hh] = __ldcg(row[hh] + lane); x1[hh] = __ldcg(row[hh] + 32 + lane); x2[hh] = __ldcg(row[hh] + 64 + lane);
+                    x3[hh] = lane < FZ_M2 - 96 ? __ldcg(row[hh] + 96 + lane) : 0.f;
+                }
+                #pragma unroll
+                for (int hh = 0; hh < 4; ++hh) { acc0 += v[hh] * x0[hh]; acc1 += v[hh] * x1[hh]; acc2 += v[hh] * x2[hh]; acc3 += v[hh] * x3[hh]; }
+                any = true;
+            }
+        }
+        if (any) {
+            float* dst = dFt + (size_t)(t / FZ_CL) * FZ_M2;
+            dst[lane] += acc0; dst[32 + lane] += acc1; dst[64 + lane] += acc2;
+            if (lane < FZ_M2 - 96) dst[96 + lane] += acc3;
+        }
+    }
+    __syncthreads();
+}
+
 }  // namespace fz
 
 __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_csc_fused_bwd_xyz(const FzPlan P, const FzBufs B, const FzBwd W, const CscDims d) {
@@ -1019,16 +1069,17 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
     const int nD = FZ_FLEN * FZ_M, nF = FZ_H * FZ_M2 * FZ_K;
     const float mf = d.mf;
     const int E = l * FZ_K;
+    FZ_TDECL;
     // Smem view that the shared device functions (recon_rows, tconv_list) expect
     Smem sv; sv.F = s.F; sv.D = s.D; sv.Dt = s.Dt; sv.Dr = s.Dr; sv.A = s.A; sv.sig = s.sig; sv.w = s.w; sv.b = s.b; sv.red = s.red; sv.iscr = s.iscr;
     sv.z = sv.y = sv.fx = sv.al = sv.be = sv.th = sv.zyF = sv.gout = nullptr; sv.li = s.kl; sv.lv = s.kv; sv.lc = nullptr;
-    float* dFp = W.dFp + ((size_t)c.g * c.ng + c.gidx) * nF;
+    float* dFp = s.dFt;                                           // partial dF of the targets this CTA owns, in shared memory
 #define SEQ(off, per) ((off) + (int64_t)c.n * (per))
     // ---- prologue ----------------------------------------------------------------------------------------------------------------
     for (int e = threadIdx.x; e < nF / 4; e += FZ_THREADS) reinterpret_cast<float4*>(s.F)[e] = __ldcg(reinterpret_cast<const float4*>(data + P.Fe) + e);
     for (int e = threadIdx.x; e < nD; e += FZ_THREADS) { s.D[e] = __ldcg(data + P.De + e); s.dDp[e] = 0.f; }
     if (threadIdx.x < 64) s.dscp[threadIdx.x] = 0.f;
-    for (int e = threadIdx.x; e < nF / 4; e += FZ_THREADS) reinterpret_cast<float4*>(dFp)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = threadIdx.x; e < FZ_NTGT * FZ_M2; e += FZ_THREADS) s.dFt[e] = 0.f;
     const int nb_own = min(Lb, c.p1 + 7 + FZ_FL) - c.p0;
     for (int e = threadIdx.x; e < nb_own; e += FZ_THREADS) s.b[e] = B.bases[(size_t)c.n * Lb + c.p0 + e];
     const FzPass& XL = P.px[P.npx - 1];
@@ -1043,23 +1094,30 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
     build_Dt(sv);
     __syncthreads();
 
+    FZ_T(0);
     for (int n = P.npx - 1; n >= 0; --n) {
         const FzPass& X = P.px[n];
         const float eta = sc[X.i_eta], lam = sc[X.i_lam], rho = sc[X.i_rho], om = sc[X.i_om];
         // kept entries of x+ (the top-q bitmap of this pass), ordered by flat index; redundantly in every CTA of the cluster
         int cnt;
         {
-            const uint8_t* bits = B.bits + X.bits + (size_t)c.n * nX;
-            const int per = (E + FZ_THREADS - 1) / FZ_THREADS;
-            const int e0 = threadIdx.x * per, e1 = min(E, e0 + per);
+            const uint32_t* bw = reinterpret_cast<const uint32_t*>(B.bits + X.bits + (size_t)c.n * nX);      // 4 flags per word (E is a multiple of 4)
+            const int nw = E >> 2;
+            const int per = (nw + FZ_THREADS - 1) / FZ_THREADS;
+            const int w0 = threadIdx.x * per, w1 = min(nw, w0 + per);
             int k = 0;
-            for (int e = e0; e < e1; ++e) k += bits[e] != 0;
+            for (int w = w0; w < w1; ++w) { const uint32_t v = bw[w]; k += ((v & 0xffu) != 0) + ((v & 0xff00u) != 0) + ((v & 0xff0000u) != 0) + ((v >> 24) != 0); }
             int total;
             int o = block_excl_scan512(k, &total, s.iscr + 8);
-            for (int e = e0; e < e1; ++e) if (bits[e] != 0) { if (o < FZ_KCAP) s.kl[o] = e; ++o; }
+            for (int w = w0; w < w1; ++w) {
+                const uint32_t v = bw[w];
+                #pragma unroll
+                for (int bb = 0; bb < 4; ++bb) if ((v >> (8 * bb)) & 0xffu) { if (o < FZ_KCAP) s.kl[o] = 4 * w + bb; ++o; }
+            }
             if (total > FZ_KCAP) { if (threadIdx.x == 0) atomicOr(W.err, 1u); total = FZ_KCAP; }
             cnt = total;
         }
+        FZ_T(1);
         // (i') duals: alpha+ = alpha + fx+_l - z+, beta+ likewise (model.jl:265-266); not computed by the last pass
         if (X.al_out >= 0)
             for (int o = threadIdx.x; o < c.nr * FZ_M; o += FZ_THREADS) {
@@ -1074,7 +1132,9 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
         int cnt2 = __ldcg(B.lcnt + (size_t)X.xl_out * d.NS + c.n);
         if (cnt2 > LIST_CAP) { if (threadIdx.x == 0) atomicOr(W.err, 2u); cnt2 = LIST_CAP; }
         if (threadIdx.x < cnt2) { s.li2[threadIdx.x] = __ldcg(B.lidx + ((size_t)X.xl_out * d.NS + c.n) * LIST_CAP + threadIdx.x); s.lv2[threadIdx.x] = __ldcg(B.lval + ((size_t)X.xl_out * d.NS + c.n) * LIST_CAP + threadIdx.x); }
+        FZ_T(2);
         cluster_barrier();                                        // #1: every CTA's rows of d fx+ are published
+        FZ_T(3);
         // (h') adjoint of fx+ = x+ (*) F on the kept support: entry q is taken by CTA q % 8, one warp per entry
         {
             const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1083,13 +1143,20 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
                 const int e = s.kl[q], i = e / FZ_K, k = e - i * FZ_K;
                 const float* rows = grad + SEQ(X.fx_out, nZY) + (size_t)i * FZ_M2;        // rows i .. i+11 are contiguous: 1200 floats
                 float acc = 0.f;
-                for (int t = lane; t < FZ_H * FZ_M2; t += 32) acc += __ldcg(rows + t) * s.F[(size_t)t * FZ_K + k];
+                float xr[38];
+                #pragma unroll
+                for (int u = 0; u < 38; ++u) { const int t = lane + 32 * u; xr[u] = t < FZ_H * FZ_M2 ? __ldcg(rows + t) : 0.f; }      // 1200 = 37.5 x 32
+                #pragma unroll
+                for (int u = 0; u < 38; ++u) { const int t = lane + 32 * u; if (t < FZ_H * FZ_M2) acc += xr[u] * s.F[(size_t)t * FZ_K + k]; }
                 acc = warp_sum(acc);
                 if (lane == 0) xch[q] = acc + s.dxd[e];
             }
         }
-        fgrad_scatter(c, s.dfx, s.li2, s.lv2, cnt2, l, dFp, s.istart);
+        FZ_T(4);
+        fgrad_targets(c, grad + SEQ(X.fx_out, nZY), s.li2, s.lv2, cnt2, dFp);
+        FZ_T(5);
         cluster_barrier();                                        // #2: the sparse d x+ values are published
+        FZ_T(6);
         // (g') top-q adjoint (model.jl:190-192, 252-253): gr = d x+ on the kept support; d x = gr, d g = -omega gr, d omega = -sum gr g
         {
             const float* xch = W.xch + (size_t)c.n * FZ_KCAP;
@@ -1108,14 +1175,12 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
             if (threadIdx.x == 0 && c.r == 0) s.dscp[X.i_om] += som;
             __syncthreads();
         }
+        FZ_T(7);
         // (f') adjoint of g = corr2d(dd, F): d dd = dg (*) F on own rows; dF += F_gradient(dd, dg)
         tconv_list(c, sv, s.F, s.kl, s.kv, cnt, FZ_KCAP, nullptr, l, s.A);
-        {
-            const float* ddg = data + SEQ(X.dd, nZY) + (size_t)c.p0 * FZ_M2;
-            for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) s.dfx[o] = __ldcg(ddg + o);       // d fx+ is consumed: reuse its rows for dd
-            __syncthreads();
-            fgrad_scatter(c, s.dfx, s.kl, s.kv, cnt, l, dFp, s.istart);
-        }
+        FZ_T(8);
+        fgrad_targets(c, data + SEQ(X.dd, nZY), s.kl, s.kv, cnt, dFp);
+        FZ_T(9);
         // (e', d', c') d_build, mask, ISTA step (model.jl:248-250, 206-210, 240-244) on own rows
         {
             const float med = __ldcg(data + X.med + c.g);
@@ -1152,7 +1217,9 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
             s_eta = block_sum512(s_eta, s.red); s_lam = block_sum512(s_lam, s.red); s_rho = block_sum512(s_rho, s.red);
             if (threadIdx.x == 0) { s.dscp[X.i_eta] += s_eta; s.dscp[X.i_lam] += s_lam; s.dscp[X.i_rho] += s_rho; }
         }
+        FZ_T(10);
         cluster_barrier();                                        // #3: every CTA's rows of dgz, dgy are published
+        FZ_T(11);
         // (b') d rec = recon(dgz, dgy; D) over base positions [p0, p1 + 7) (halo rows recomputed from the neighbours' dgz, dgy); r = rec - S
         {
             const int lo = max(0, c.p0 - 7), hi = min(cc, c.p1 + 7);
@@ -1169,16 +1236,31 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
             }
             __syncthreads();
         }
+        FZ_T(12);
         // dD += dgrad(dgz, dgy; r) + dgrad(z, y; d rec)  (32-lag gradient, model.jl:270-290 form) over own rows; then
         // (a') dz += corr_sig(d rec; D), dy likewise
-        for (int o = threadIdx.x; o < nD; o += FZ_THREADS) {
-            const int tau = o / FZ_M, m = o - tau * FZ_M;
-            float acc = 0.f;
-            for (int pl = 0; pl < c.nr; ++pl)
-                acc += s.gzs[pl * FZ_M + m] * s.sig2[4 * pl + tau] + s.gys[pl * FZ_M + m] * s.sig2[4 * pl + FZ_FLEN - 1 - tau]
-                     + s.zs[pl * FZ_M + m] * s.sig[4 * pl + tau] + s.ys[pl * FZ_M + m] * s.sig[4 * pl + FZ_FLEN - 1 - tau];
-            s.dDp[o] += acc;
+        for (int o = threadIdx.x; o < (FZ_FLEN / 4) * (FZ_M / 2); o += FZ_THREADS) {          // tile: taus 4tg..4tg+3 x filters 2mp, 2mp+1
+            const int tg = o / (FZ_M / 2), mp = o - tg * (FZ_M / 2);
+            float acc[4][2];
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.f;
+            for (int pl = 0; pl < c.nr; ++pl) {
+                const float2 gz2 = *reinterpret_cast<const float2*>(s.gzs + pl * FZ_M + 2 * mp), gy2 = *reinterpret_cast<const float2*>(s.gys + pl * FZ_M + 2 * mp);
+                const float2 z2 = *reinterpret_cast<const float2*>(s.zs + pl * FZ_M + 2 * mp), y2 = *reinterpret_cast<const float2*>(s.ys + pl * FZ_M + 2 * mp);
+                const float4 rf = *reinterpret_cast<const float4*>(s.sig2 + 4 * pl + 4 * tg), rr = *reinterpret_cast<const float4*>(s.sig2 + 4 * pl + FZ_FLEN - 4 - 4 * tg);
+                const float4 df = *reinterpret_cast<const float4*>(s.sig + 4 * pl + 4 * tg), dr = *reinterpret_cast<const float4*>(s.sig + 4 * pl + FZ_FLEN - 4 - 4 * tg);
+                // tau = 4tg + i reads r[4p + tau] (forward: .x .y .z .w) and r[4p + 31 - tau] (reversed block: .w .z .y .x)
+                const float f[4] = {rf.x, rf.y, rf.z, rf.w}, rv[4] = {rr.w, rr.z, rr.y, rr.x}, g[4] = {df.x, df.y, df.z, df.w}, gv[4] = {dr.w, dr.z, dr.y, dr.x};
+                #pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc[i][0] += gz2.x * f[i] + gy2.x * rv[i] + z2.x * g[i] + y2.x * gv[i];
+                    acc[i][1] += gz2.y * f[i] + gy2.y * rv[i] + z2.y * g[i] + y2.y * gv[i];
+                }
+            }
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) { s.dDp[(4 * tg + i) * FZ_M + 2 * mp] += acc[i][0]; s.dDp[(4 * tg + i) * FZ_M + 2 * mp + 1] += acc[i][1]; }
         }
+        FZ_T(13);
         for (int o = threadIdx.x; o < c.nr * FZ_M; o += FZ_THREADS) {
             const int pl = o / FZ_M, m = o - pl * FZ_M;
             float a = 0.f, b = 0.f;
@@ -1188,6 +1270,7 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
         }
         __syncthreads();
     }
+    FZ_T(14);
     // ---- hand the adjoints of the warm-up outputs back to the tape: d z0, d y0, d fx0, d x0 -------------------------------------------
     {
         const FzPass& X0 = P.px[0];
@@ -1202,26 +1285,42 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
     float* part = B.part + ((size_t)c.g * c.ng + c.gidx) * FZ_PART;
     for (int o = threadIdx.x; o < nD; o += FZ_THREADS) part[o] = s.dDp[o];
     if (threadIdx.x < 64) part[nD + threadIdx.x] = s.dscp[threadIdx.x];
+    for (int o = threadIdx.x; o < FZ_NTGT * FZ_M2; o += FZ_THREADS) {
+        const int lt = o / FZ_M2, t = lt * FZ_CL + c.r;
+        if (t < FZ_H * FZ_K) W.dFp[((size_t)c.n * (FZ_H * FZ_K) + t) * FZ_M2 + (o - lt * FZ_M2)] = s.dFt[o];
+    }
     group_barrier(c);
     {
         const float* gpart = B.part + (size_t)c.g * c.ng * FZ_PART;
-        const float* gF = W.dFp + (size_t)c.g * c.ng * nF;
+        const float* gF = W.dFp + (size_t)c.g * d.B * nF;            // [B sequences][a*K + k][j]
         float* gs = W.gsum + (size_t)c.g * (nF + nD + 64);
         const int per = (nF + c.ng - 1) / c.ng;
-        for (int o = c.gidx * per + threadIdx.x; o < min(nF, (c.gidx + 1) * per); o += FZ_THREADS) {
-            const int k = o % FZ_K, aj = o / FZ_K, j = aj % FZ_M2, a = aj / FZ_M2;
-            const int po = (a * FZ_K + k) * FZ_M2 + j;
+        for (int po = c.gidx * per + threadIdx.x; po < min(nF, (c.gidx + 1) * per); po += FZ_THREADS) {      // po = (a*K + k)*2M + j: coalesced reads
             float acc = 0.f;
-            for (int q = 0; q < c.ng; ++q) acc += __ldcg(gF + (size_t)q * nF + po);
-            gs[o] = acc;
+            for (int q = 0; q < d.B; ++q) acc += __ldcg(gF + (size_t)q * nF + po);
+            const int j = po % FZ_M2, ak = po / FZ_M2, k = ak % FZ_K, a = ak / FZ_K;
+            gs[(a * FZ_M2 + j) * FZ_K + k] = acc;
         }
         const int perd = (nD + 64 + c.ng - 1) / c.ng;
         for (int o = c.gidx * perd + threadIdx.x; o < min(nD + 64, (c.gidx + 1) * perd); o += FZ_THREADS) {
             float acc = 0.f;
+            #pragma unroll 8
             for (int q = 0; q < c.ng; ++q) acc += __ldcg(gpart + (size_t)q * FZ_PART + o);
             gs[nF + o] = acc;
         }
     }
+#ifdef FZ_PROFILE
+    FZ_T(15);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const char* nm[16] = {"prologue", "kept list", "duals+publish+list", "barrier 1", "sparse dx dots", "fgrad(dfx,x)", "barrier 2", "topq adjoint", "tconv(dg)", "fgrad(dd,dg)", "elementwise", "barrier 3", "recon(dgz)+r", "dgrad", "corr_sig(drec)", "epilogue"};
+        long long tot = 0; for (int i = 0; i < 16; ++i) tot += fz_acc[i];
+        for (int i = 0; i < 16; ++i) printf("[fzb] %-20s %9lld clk %5.1f%%\n", nm[i], fz_acc[i], 100.0 * fz_acc[i] / tot);
+        printf("[fzb] total %lld clk\n", tot);
+    }
+    if (blockIdx.x < 16 && threadIdx.x == 0)
+        printf("[fzb-cta %2d] dots %6lld fgrad1 %6lld b2 %6lld | topq %6lld tconv %6lld fgrad2 %6lld elem %6lld b3 %6lld | recon %6lld dgrad %6lld b1 %6lld kept %6lld duals %6lld\n", (int)blockIdx.x,
+               fz_acc[4], fz_acc[5], fz_acc[6], fz_acc[7], fz_acc[8], fz_acc[9], fz_acc[10], fz_acc[11], fz_acc[12], fz_acc[13], fz_acc[3], fz_acc[1], fz_acc[2]);
+#endif
 #undef SEQ
 }
 
