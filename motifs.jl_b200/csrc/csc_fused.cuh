@@ -67,6 +67,13 @@ struct FzBufs {
 #define FZ_TDECL
 #define FZ_T(id)
 #endif
+#ifdef FZ_PROFILE
+#define FZ_S0(c) do { if (threadIdx.x == 0) (c).subt = clock64(); } while (0)
+#define FZ_S(c, id) do { if (threadIdx.x == 0) { const long long t = clock64(); (c).sub[id] += t - (c).subt; (c).subt = t; } } while (0)
+#else
+#define FZ_S0(c)
+#define FZ_S(c, id)
+#endif
 
 namespace fz {
 namespace cg = cooperative_groups;
@@ -78,7 +85,7 @@ struct Ctx {
     int q1;                       // own base positions [p0, q1) for the signal (q1 = p1, the last CTA also takes the tail up to Lb)
     unsigned int epoch;           // barrier arrivals expected so far
     unsigned int* bar;
-    long long tbar, tb1, tb2, tb3; int nbar;     // FZ_PROFILE: clocks thread 0 spent inside group barriers (fence, arrive+poll, fence)
+    long long tbar, tb1, tb2, tb3; int nbar; long long sub[24]; long long subt;     // FZ_PROFILE: clocks thread 0 spent inside group barriers (fence, arrive+poll, fence)
 };
 
 __device__ __forceinline__ unsigned int ld_relaxed(const unsigned int* p) {
@@ -87,11 +94,9 @@ __device__ __forceinline__ unsigned int ld_relaxed(const unsigned int* p) {
 // barrier over the CTAs of one group; global writes before it are visible to every CTA of the group after it.  Hierarchical: the 8 CTAs
 // of a cluster meet at the hardware cluster barrier, only the cluster's rank-0 CTA arrives at / polls the counter in global memory (6
 // arrivals on one address instead of 48: same-address atomics serialise in L2), a second cluster barrier releases the others.
-// Ordering: every CTA publishes its writes with a gpu-scope fence before the first cluster barrier; the leader's fence after that barrier
-// is cumulative over them; readers fence after the second cluster barrier (and read other CTAs' data with ld.cg).
+// Ordering: the cluster barrier orders every CTA's writes before the leader's gpu-scope fence, which is cumulative over them; the leader's
+// acquire fence after the poll and the second cluster barrier order them before every reader (which reads other CTAs' data with ld.cg).
 __device__ __forceinline__ void group_barrier(Ctx& c) {
-    __syncthreads();
-    if (threadIdx.x == 0) __threadfence();
     cg::this_cluster().sync();
     if (c.r == 0 && threadIdx.x == 0) {
 #ifdef FZ_PROFILE
@@ -115,8 +120,6 @@ __device__ __forceinline__ void group_barrier(Ctx& c) {
 #endif
     }
     cg::this_cluster().sync();
-    if (threadIdx.x == 0) __threadfence();
-    __syncthreads();
 }
 __device__ __forceinline__ void cluster_barrier() { cg::this_cluster().sync(); }
 
@@ -161,7 +164,7 @@ __host__ __device__ inline int fz_rows(int c) { return (c + FZ_CL - 1) / FZ_CL; 
 __host__ __device__ inline size_t fz_work_floats(int Lb) {
     const int c = Lb - FZ_FL + 1, l = c - FZ_H + 1;
     size_t a = (size_t)6144 + 64;                       // corr2d partials (<= 512 threads x 12)
-    const size_t b = (size_t)l * FZ_K + 256;            // top-q values + the 256-bin radix histogram behind them
+    const size_t b = (size_t)l * FZ_K + 2048 + 64;      // top-q values + the 2048-bin histogram behind them
     const size_t h = (size_t)FZ_BINS + FZ_CAND;         // median histogram + candidates
     if (b > a) a = b;
     if (h > a) a = h;
@@ -211,9 +214,10 @@ __device__ float group_median(Ctx& c, const Smem& s, const FzBufs& B, int mi, in
     unsigned int prefix = 0, pmask = 0, krank = 0, npos = 0, cnt = 0;
     int shift = 19, nb = FZ_BINS;
     bool first = true, resolved = false;
+    FZ_S0(c);
     for (int lvl = 0; lvl < FZ_NHIST; ++lvl) {
         unsigned int* gh = ghist0 + (size_t)lvl * FZ_BINS;
-        for (int i = threadIdx.x; i < nb; i += FZ_THREADS) lhist[i] = 0;
+        for (int i = threadIdx.x; i < nb / 4; i += FZ_THREADS) reinterpret_cast<uint4*>(lhist)[i] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
         for (int e = threadIdx.x; e < 2 * nv; e += FZ_THREADS) {
             const float f = e < nv ? s.z[e] : s.y[e - nv];
@@ -221,10 +225,20 @@ __device__ float group_median(Ctx& c, const Smem& s, const FzBufs& B, int mi, in
             if (f > 0.f && (b & pmask) == prefix) atomicAdd(&lhist[(b >> shift) & (unsigned)(nb - 1)], 1u);
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < nb; i += FZ_THREADS) { const unsigned int v = lhist[i]; if (v) atomicAdd(&gh[i], v); }
+        FZ_S(c, 0);
+        for (int i = threadIdx.x; i < nb / 4; i += FZ_THREADS) {
+            const uint4 v = reinterpret_cast<const uint4*>(lhist)[i];
+            if (v.x) atomicAdd(&gh[4 * i], v.x);
+            if (v.y) atomicAdd(&gh[4 * i + 1], v.y);
+            if (v.z) atomicAdd(&gh[4 * i + 2], v.z);
+            if (v.w) atomicAdd(&gh[4 * i + 3], v.w);
+        }
+        FZ_S(c, 1);
         group_barrier(c);
-        for (int i = threadIdx.x; i < nb; i += FZ_THREADS) lhist[i] = __ldcg(&gh[i]);
+        FZ_S(c, 2);
+        for (int i = threadIdx.x; i < nb / 4; i += FZ_THREADS) reinterpret_cast<uint4*>(lhist)[i] = __ldcg(reinterpret_cast<const uint4*>(gh) + i);
         __syncthreads();
+        FZ_S(c, 3);
         block_find_bin(lhist, nb, krank, first, wsum, res);
         if (first) {
             npos = res[3];
@@ -240,6 +254,7 @@ __device__ float group_median(Ctx& c, const Smem& s, const FzBufs& B, int mi, in
         if (shift == 0) { resolved = true; break; }
         if (shift == 19) { shift = 7; nb = FZ_BINS; } else { shift = 0; nb = 128; }
     }
+    FZ_S(c, 4);
     float med = -INFINITY;
     if (npos > 0) {                                                        // group-uniform
         // publish this CTA's entries of the median's bin, and the smallest entry above the bin
@@ -266,8 +281,10 @@ __device__ float group_median(Ctx& c, const Smem& s, const FzBufs& B, int mi, in
         __syncthreads();
         const unsigned int base = res[2];
         for (unsigned int i = threadIdx.x; i < nc; i += FZ_THREADS) gcand[base + i] = __uint_as_float(lc[i]);
+        FZ_S(c, 5);
         group_barrier(c);
         const unsigned int above_inv = __ldcg(&gctl[1]);
+        FZ_S(c, 6);
         if (!resolved) for (unsigned int i = threadIdx.x; i < cnt; i += FZ_THREADS) cand[i] = __ldcg(&gcand[i]);
         __syncthreads();
         const unsigned int kin = krank;
@@ -292,6 +309,7 @@ __device__ float group_median(Ctx& c, const Smem& s, const FzBufs& B, int mi, in
             }
             v1b |= lowfix;
         }
+        FZ_S(c, 7);
         const float v1 = __uint_as_float(v1b);
         if (npos & 1u) med = v1;
         else {
@@ -312,6 +330,7 @@ __device__ float group_median(Ctx& c, const Smem& s, const FzBufs& B, int mi, in
             __syncthreads();
         }
     }
+    FZ_S(c, 8);
     return med;
 }
 
@@ -385,15 +404,23 @@ __device__ void corr2d_rows(const Smem& s, const float* Fm, int ni) {
         float acc[3][4];
         #pragma unroll
         for (int r = 0; r < 3; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
-        const int e_lo = (int)((long long)E * slice / nslice), e_hi = (int)((long long)E * (slice + 1) / nslice);
-        const float* Ab = s.A + (3 * tr) * FZ_M2;                 // row (3tr + rr + a), column j  ->  Ab[rr*100 + e]   (e = a*100 + j)
-        #pragma unroll 4
-        for (int e = e_lo; e < e_hi; ++e) {
-            const float4 f = *reinterpret_cast<const float4*>(Fm + (size_t)e * FZ_K + 4 * kg);
+        // slices are cut at multiples of 4 in e = a*100 + j: rows i..i+h-1 of A are one contiguous run in e, so four consecutive taps of a
+        // row are ONE 16-byte load (shared memory bandwidth, not the FMA pipe, bounds this loop)
+        const int e_lo = 4 * (int)((long long)(E / 4) * slice / nslice), e_hi = 4 * (int)((long long)(E / 4) * (slice + 1) / nslice);
+        const float* Ab = s.A + (3 * tr) * FZ_M2;                 // row (3tr + rr + a), column j  ->  Ab[rr*100 + e]
+        #pragma unroll 2
+        for (int e = e_lo; e < e_hi; e += 4) {
+            float4 av[3];
             #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const float av = Ab[r * FZ_M2 + e];
-                acc[r][0] += av * f.x; acc[r][1] += av * f.y; acc[r][2] += av * f.z; acc[r][3] += av * f.w;
+            for (int r = 0; r < 3; ++r) av[r] = *reinterpret_cast<const float4*>(Ab + r * FZ_M2 + e);
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 f = *reinterpret_cast<const float4*>(Fm + (size_t)(e + u) * FZ_K + 4 * kg);
+                #pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float a1 = u == 0 ? av[r].x : u == 1 ? av[r].y : u == 2 ? av[r].z : av[r].w;
+                    acc[r][0] += a1 * f.x; acc[r][1] += a1 * f.y; acc[r][2] += a1 * f.z; acc[r][3] += a1 * f.w;
+                }
             }
         }
         float* dst = s.w + ((size_t)slice * (3 * ntr) + 3 * tr) * FZ_K + 4 * kg;
@@ -468,10 +495,11 @@ __device__ __forceinline__ void tconv_rows(const Ctx& c, const Smem& s, const fl
 
 // per-sequence top-q (generate_bitmat / project_X, model.jl:181-192) on v = xprev + om * g over all l*K entries, redundantly in every CTA of
 // the cluster; writes own rows of x and the bitmap, rank 0 writes the ordered code list; leaves the list in s.li / s.lv / s.lc
-__device__ void topq_all(const Ctx& c, const Smem& s, const float* g_g, const float* xprev_g, bool have_prev, float om, int l, int q,
+__device__ void topq_all(Ctx& c, const Smem& s, const float* g_g, const float* xprev_g, bool have_prev, float om, int l, int q,
                          float* xout_g, uint8_t* bits_g, int32_t* lcnt_g, uint16_t* lidx_g, float* lval_g) {
     const int E = l * FZ_K;
     float* sv = s.w;
+    FZ_S0(c);
     unsigned int* hist = reinterpret_cast<unsigned int*>(s.w + E);        // fz_work_floats() reserves 256 bins behind the values
     // values: previous codes come from the list when it is complete (cheaper than re-reading the dense tensor)
     const int pcnt = have_prev ? s.lc[0] : 0;
@@ -481,28 +509,62 @@ __device__ void topq_all(const Ctx& c, const Smem& s, const float* g_g, const fl
         __syncthreads();
         if (threadIdx.x < pcnt) { const int e = s.li[threadIdx.x]; sv[e] = s.lv[threadIdx.x] + om * __ldcg(g_g + e); }
     }
-    unsigned int* ctl = reinterpret_cast<unsigned int*>(s.iscr);          // [0] prefix, [1] rank
-    if (threadIdx.x == 0) { ctl[0] = 0; ctl[1] = (unsigned int)(E - q); }
+    FZ_S(c, 10);
+    unsigned int* ctl = reinterpret_cast<unsigned int*>(s.iscr);          // [0] prefix / key of the q-th largest, [1] rank, [2] candidates
+    unsigned int* wsum = reinterpret_cast<unsigned int*>(s.red);
+    unsigned int* res = ctl + 4;
+    // one pass over a 2048-bin histogram of the top 11 key bits (sign, exponent, 2 mantissa bits): the bin of the q-th largest value holds a
+    // handful of entries, whose exact order is then settled by counting.  Many entries in that bin (ties): the byte-wise radix select below.
+    for (int i = threadIdx.x; i < 2048; i += FZ_THREADS) hist[i] = 0;
+    if (threadIdx.x == 0) { ctl[0] = 0; ctl[1] = (unsigned int)(E - q); ctl[2] = 0; }
     __syncthreads();
-    for (int shift = 24; shift >= 0; shift -= 8) {
-        if (threadIdx.x < 256) hist[threadIdx.x] = 0;
-        __syncthreads();
-        const unsigned int prefix = ctl[0];
-        const unsigned int pmask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+    for (int e0 = 0; e0 < E; e0 += FZ_THREADS) {
+        const int e = e0 + threadIdx.x;
+        const unsigned int kk = e < E ? fkey(sv[e]) : 0u;
+        hist_add(hist, e < E, kk >> 21);
+    }
+    __syncthreads();
+    FZ_S(c, 11);
+    block_find_bin(hist, 2048, (unsigned int)(E - q), false, wsum, res);
+    const unsigned int tbin = res[0], kr = (unsigned int)(E - q) - res[1], cntb = res[2];
+    __syncthreads();
+    FZ_S(c, 12);
+    if (cntb <= FZ_THREADS) {
+        unsigned int* cd = hist;                                            // the histogram is no longer needed
         for (int e0 = 0; e0 < E; e0 += FZ_THREADS) {
             const int e = e0 + threadIdx.x;
-            const unsigned int kk = e < E ? fkey(sv[e]) : 0u;
-            hist_add(hist, e < E && (kk & pmask) == prefix, (kk >> shift) & 255u);
+            if (e < E) { const unsigned int kk = fkey(sv[e]); if ((kk >> 21) == tbin) cd[atomicAdd(&ctl[2], 1u)] = kk; }
         }
         __syncthreads();
-        if (threadIdx.x < 32) {
-            int bin; unsigned int below;
-            find_bin(hist, ctl[1], &bin, &below);
-            __syncwarp();
-            if (threadIdx.x == 0) { ctl[1] -= below; ctl[0] = prefix | ((unsigned int)bin << shift); }
+        if (threadIdx.x < cntb) {
+            const unsigned int mine = cd[threadIdx.x];
+            unsigned int less = 0, eq = 0;
+            for (unsigned int i = 0; i < cntb; ++i) { const unsigned int o = cd[i]; less += o < mine; eq += o == mine; }
+            if (less <= kr && kr < less + eq) ctl[0] = mine;              // every thread holding that value writes the same bits
         }
         __syncthreads();
+    } else {
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+            __syncthreads();
+            const unsigned int prefix = ctl[0];
+            const unsigned int pmask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+            for (int e0 = 0; e0 < E; e0 += FZ_THREADS) {
+                const int e = e0 + threadIdx.x;
+                const unsigned int kk = e < E ? fkey(sv[e]) : 0u;
+                hist_add(hist, e < E && (kk & pmask) == prefix, (kk >> shift) & 255u);
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                int bin; unsigned int below;
+                find_bin(hist, ctl[1], &bin, &below);
+                __syncwarp();
+                if (threadIdx.x == 0) { ctl[1] -= below; ctl[0] = prefix | ((unsigned int)bin << shift); }
+            }
+            __syncthreads();
+        }
     }
+    FZ_S(c, 13);
     const float vq = fkey_inv(ctl[0]);
     __syncthreads();
     // ordered list (flat index ascending): contiguous chunk per thread
@@ -511,13 +573,14 @@ __device__ void topq_all(const Ctx& c, const Smem& s, const float* g_g, const fl
     int cnt = 0;
     for (int e = e0; e < e1; ++e) { const float v = sv[e]; cnt += (v >= vq && v != 0.f); }
     int total;
-    int o = block_excl_scan512(cnt, &total, s.iscr + 8);
+    int o = block_excl_scan512(cnt, &total, s.iscr + 12);
     for (int e = e0; e < e1; ++e) {
         const float v = sv[e];
         if (v >= vq && v != 0.f) { if (o < LIST_CAP) { s.li[o] = e; s.lv[o] = v; } ++o; }
     }
     if (threadIdx.x == 0) s.lc[0] = total;
     __syncthreads();
+    FZ_S(c, 14);
     // own rows of the dense tensor + bitmap
     for (int e = c.i0 * FZ_K + threadIdx.x; e < c.i1 * FZ_K; e += FZ_THREADS) {
         const float v = sv[e]; const bool keep = v >= vq;
@@ -529,6 +592,7 @@ __device__ void topq_all(const Ctx& c, const Smem& s, const float* g_g, const fl
         if (threadIdx.x < min(total, LIST_CAP)) { lidx_g[threadIdx.x] = (uint16_t)s.li[threadIdx.x]; lval_g[threadIdx.x] = s.lv[threadIdx.x]; }
     }
     __syncthreads();
+    FZ_S(c, 15);
 }
 
 }  // namespace fz
@@ -547,7 +611,7 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
     c.p0 = min(cc, c.r * R); c.p1 = min(cc, c.p0 + R); c.nr = c.p1 - c.p0;
     c.i0 = min(l, c.p0); c.i1 = min(l, c.p1); c.ni = c.i1 - c.i0;
     c.q1 = (c.r == FZ_CL - 1) ? Lb : c.p1;
-    c.epoch = 0; c.bar = B.bar + c.g; c.tbar = 0; c.nbar = 0; c.tb1 = c.tb2 = c.tb3 = 0;
+    c.epoch = 0; c.bar = B.bar + c.g; c.tbar = 0; c.nbar = 0; c.tb1 = c.tb2 = c.tb3 = 0; for (int i = 0; i < 24; ++i) c.sub[i] = 0; c.subt = 0;
     const int nmed = P.npx + 2;
     float* const data = B.data;
     const float* sc = data + P.sc;
@@ -734,17 +798,47 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
         const float mu = sc[Y.i_mu], kap = sc[Y.i_kap], kaps = sc[Y.i_kaps];
         // D chain: recon with the current D, R = recon + S ('+S': model.jl:282-285), partial 32-lag gradient over own rows
         {
+            FZ_S0(c);
             stage_zy_halo(s, SEQ_Z(XL.z_out), SEQ_Z(XL.y_out), lo7, hi7);
             __syncthreads();
             recon_rows(c, s, lo7, hi7, c.p0, min(Lb, max(c.p1 + 7, c.q1)), +1.f, SEQ_S(Y.rec), c.p0, c.q1, Lb);
             __syncthreads();
-            // G[tau][m] += z[p][m] R[4p + tau] + y[p][m] R[4p + 31 - tau]: thread (tau, m) over own rows, fixed order
-            for (int o = threadIdx.x; o < (int)nD; o += FZ_THREADS) {
-                const int tau = o / FZ_M, m = o - tau * FZ_M;
-                float acc = 0.f;
-                for (int pl = 0; pl < c.nr; ++pl) acc += s.z[pl * FZ_M + m] * s.sig[4 * pl + tau] + s.y[pl * FZ_M + m] * s.sig[4 * pl + FZ_FLEN - 1 - tau];
-                part[o] = acc;
+            // G[tau][m] += z[p][m] R[4p + tau] + y[p][m] R[4p + 31 - tau] over own rows: tile of 4 taus x 2 filters per thread (16-byte signal loads)
+            FZ_S(c, 16);
+            float* Gp = s.w;                                       // this CTA's partial [32][50]
+            for (int o = threadIdx.x; o < (FZ_FLEN / 4) * (FZ_M / 2); o += FZ_THREADS) {
+                const int tg = o / (FZ_M / 2), mp = o - tg * (FZ_M / 2);
+                float acc[4][2];
+                #pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.f;
+                for (int pl = 0; pl < c.nr; ++pl) {
+                    const float2 z2 = *reinterpret_cast<const float2*>(s.z + pl * FZ_M + 2 * mp), y2 = *reinterpret_cast<const float2*>(s.y + pl * FZ_M + 2 * mp);
+                    const float4 rf = *reinterpret_cast<const float4*>(s.sig + 4 * pl + 4 * tg), rr = *reinterpret_cast<const float4*>(s.sig + 4 * pl + FZ_FLEN - 4 - 4 * tg);
+                    const float f[4] = {rf.x, rf.y, rf.z, rf.w}, rv[4] = {rr.w, rr.z, rr.y, rr.x};
+                    #pragma unroll
+                    for (int i = 0; i < 4; ++i) { acc[i][0] += z2.x * f[i] + y2.x * rv[i]; acc[i][1] += z2.y * f[i] + y2.y * rv[i]; }
+                }
+                #pragma unroll
+                for (int i = 0; i < 4; ++i) { Gp[(4 * tg + i) * FZ_M + 2 * mp] = acc[i][0]; Gp[(4 * tg + i) * FZ_M + 2 * mp + 1] = acc[i][1]; }
             }
+            FZ_S(c, 17);
+            // sum over the cluster's 8 CTAs through distributed shared memory (rank order), one slice of 200 entries per CTA; the 6 cluster
+            // sums go through global memory
+            cluster_barrier();
+            {
+                cg::cluster_group cl = cg::this_cluster();
+                float* cpart = B.part + ((size_t)c.g * c.ng + (c.n % d.B) * FZ_CL) * FZ_PART;      // the cluster's slot (its rank-0 CTA's)
+                const int per = (int)nD / FZ_CL;
+                for (int o = threadIdx.x; o < per; o += FZ_THREADS) {
+                    const int e = c.r * per + o;
+                    float acc = 0.f;
+                    #pragma unroll
+                    for (int q = 0; q < FZ_CL; ++q) acc += cl.map_shared_rank(Gp, q)[e];
+                    cpart[e] = acc;
+                }
+            }
+            cluster_barrier();                                     // remote reads of this CTA's partial are done: s.w may be reused
+            FZ_S(c, 18);
         }
         FZ_T(11);
         // F chain: e = fx(x, F) - (zyF + theta) on own rows (model.jl:294)
@@ -760,8 +854,13 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
         {
             float* Gs = s.w;
             for (int o = threadIdx.x; o < (int)nD; o += FZ_THREADS) {
+                float v[8];
+                #pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = q < d.B ? __ldcg(gpart + (size_t)q * FZ_CL * FZ_PART + o) : 0.f;       // all loads in flight together
                 float acc = 0.f;
-                for (int q = 0; q < c.ng; ++q) acc += __ldcg(gpart + (size_t)q * FZ_PART + o);
+                #pragma unroll
+                for (int q = 0; q < 8; ++q) acc += v[q];
+                for (int q = 8; q < d.B; ++q) acc += __ldcg(gpart + (size_t)q * FZ_CL * FZ_PART + o);
                 Gs[o] = acc;
                 if (c.gidx == 0) data[Y.Gm + (int64_t)c.g * nD + o] = acc;
             }
@@ -815,7 +914,13 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
                     const int a = o / FZ_M2, j = o - a * FZ_M2;
                     float acc = 0.f;
                     if (!dense) {
-                        for (int q = 0; q < ns; ++q) acc += sel_v[q] * __ldcg(data + Y.e + ((int64_t)(c.g * d.B + sel_b[q]) * cc + a + sel_i[q]) * FZ_M2 + j);
+                        for (int q0 = 0; q0 < ns; q0 += 8) {                 // eight independent loads per trip (one L2 round trip, not eight)
+                            float ev[8];
+                            #pragma unroll
+                            for (int u = 0; u < 8; ++u) { const int q = min(q0 + u, ns - 1); ev[u] = __ldcg(data + Y.e + ((int64_t)(c.g * d.B + sel_b[q]) * cc + a + sel_i[q]) * FZ_M2 + j); }
+                            #pragma unroll
+                            for (int u = 0; u < 8; ++u) if (q0 + u < ns) acc += sel_v[q0 + u] * ev[u];
+                        }
                     } else {
                         for (int b = 0; b < d.B; ++b)
                             for (int i = 0; i < l; ++i) {
@@ -854,26 +959,36 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
         }
     }
     FZ_T(15);
+    FZ_S0(c);
     // ---- loss (model.jl:310-325) with the updated D, F -----------------------------------------------------------------------
     {
         stage_zy_halo(s, SEQ_Z(XL.z_out), SEQ_Z(XL.y_out), lo7, hi7);
         __syncthreads();
         recon_rows(c, s, lo7, hi7, c.p0, min(Lb, max(c.p1 + 7, c.q1)), -1.f, SEQ_S(P.recL), c.p0, c.q1, Lb);
         __syncthreads();
+        FZ_S(c, 19);
         float a = 0.f, b = 0.f;
         for (int t = threadIdx.x; t < 4 * (c.q1 - c.p0); t += FZ_THREADS) { const float r = s.sig[t]; a += r * r; }
         tconv_rows(c, s, s.F, SEQ_X(XL.x_out), l, s.A);
         __syncthreads();
         float* fg = SEQ_ZY(P.fxL);
         for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) { const float v = s.A[o]; fg[(size_t)c.p0 * FZ_M2 + o] = v; const float dlt = v - s.zyF[o]; b += dlt * dlt; }
+        FZ_S(c, 20);
         a = block_sum512(a, s.red);
         b = block_sum512(b, s.red);
+        FZ_S(c, 21);
         if (threadIdx.x == 0) { part[0] = a; part[1] = b; }
         group_barrier(c);
-        if (c.gidx == 0 && threadIdx.x == 0) {
-            float sa = 0.f, sb = 0.f;
-            for (int q = 0; q < c.ng; ++q) { sa += __ldcg(gpart + (size_t)q * FZ_PART); sb += __ldcg(gpart + (size_t)q * FZ_PART + 1); }
-            data[P.loss + c.g * 3 + 0] = (sa + sb) / (float)d.B; data[P.loss + c.g * 3 + 1] = sa / (float)d.B; data[P.loss + c.g * 3 + 2] = sb / (float)d.B;
+        FZ_S(c, 22);
+        if (c.gidx == 0) {
+            float* la = s.w; float* lb = s.w + 64;                 // one load per thread (a serial loop would pay an L2 round trip per term)
+            if (threadIdx.x < c.ng) { la[threadIdx.x] = __ldcg(gpart + (size_t)threadIdx.x * FZ_PART); lb[threadIdx.x] = __ldcg(gpart + (size_t)threadIdx.x * FZ_PART + 1); }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float sa = 0.f, sb = 0.f;
+                for (int q = 0; q < c.ng; ++q) { sa += la[q]; sb += lb[q]; }      // CTA order: deterministic
+                data[P.loss + c.g * 3 + 0] = (sa + sb) / (float)d.B; data[P.loss + c.g * 3 + 1] = sa / (float)d.B; data[P.loss + c.g * 3 + 2] = sb / (float)d.B;
+            }
         }
     }
 #ifdef FZ_PROFILE
@@ -890,6 +1005,10 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
         const char* nm[16] = {"prologue", "warm_zy", "median", "A tile", "corr2d", "g+cluster bar", "topq", "tconv+store", "recon", "corr_sig+zy", "stage zy halo", "DF D-chain+loss", "DF e", "barA+D update", "F update", "barB+F load+theta"};
         long long tot = 0; for (int i = 0; i < 16; ++i) tot += fz_acc[i];
         for (int i = 0; i < 16; ++i) printf("[fz] %-20s %9lld clk %5.1f%%\n", nm[i], fz_acc[i], 100.0 * fz_acc[i] / tot);
+        printf("[fz] median: hist %lld push %lld bar1 %lld pull %lld find %lld cand %lld bar2 %lld radix %lld v2 %lld | topq: values %lld hist %lld find %lld select %lld list %lld out %lld\n",
+               c.sub[0], c.sub[1], c.sub[2], c.sub[3], c.sub[4], c.sub[5], c.sub[6], c.sub[7], c.sub[8], c.sub[10], c.sub[11], c.sub[12], c.sub[13], c.sub[14], c.sub[15]);
+        printf("[fz] loss: recon %lld tconv+sum %lld blocksums %lld barrier %lld\n", c.sub[19], c.sub[20], c.sub[21], c.sub[22]);
+        printf("[fz] DF D-chain: stage+recon %lld Gp %lld cluster reduce %lld\n", c.sub[16], c.sub[17], c.sub[18]);
         printf("[fz] total %lld clk; %d group barriers, %lld clk inside them (thread 0): fence %lld, arrive+poll %lld, fence %lld\n", tot, c.nbar, c.tbar, c.tb1, c.tb2, c.tb3);
     }
 #endif
@@ -928,78 +1047,45 @@ namespace fz {
 struct SmemB {
     float *F, *D, *Dt, *Dr;
     float *dFt;                                         // [FZ_NTGT][2M] this CTA's partial of dF for the targets it owns
-    float *dz, *dy, *dal, *dbe, *gzs, *gys, *zs, *ys;   // [R][50]
+    float *dz, *dy, *dal, *dbe, *gzs, *gys;             // [R][50]
     float *dfx;                                         // [R][100]
     float *A;                                           // work tile (own rows [R][100] / halo staging)
     float *sig, *sig2;                                  // drec and r = rec - S over base positions [p0, p1 + 7)
     float *w;                                           // row lists of tconv
     float *dDp, *dscp;                                  // partial dD [32][50], partial scalar gradients [64]
-    float *dxd;                                         // dense map [l][K] of the adjoint of the current x
     int *kl; float *kv;                                 // kept entries (flat index) and their values
     int *li2; float *lv2;                               // code list of x+ (from the tape)
-    int *istart;                                        // [R + 14] first list entry per position
     float* red; int* iscr; uint8_t* b;
 };
 __host__ __device__ inline size_t fzb_smem_bytes(int Lb) {
-    const int c = Lb - FZ_FL + 1, l = c - FZ_H + 1, R = fz_rows(c);
+    const int c = Lb - FZ_FL + 1, R = fz_rows(c);
     size_t f = (size_t)FZ_H * FZ_M2 * FZ_K + 3 * FZ_FLEN * FZ_M + (size_t)FZ_NTGT * FZ_M2;
-    f += (size_t)R * (FZ_M * 8 + FZ_M2);
+    f += (size_t)R * (FZ_M * 6 + FZ_M2);
     const size_t A = (size_t)R * FZ_M2, A2 = (size_t)2 * (R + 14) * FZ_M;
     f += (A > A2 ? A : A2);
     f += (size_t)8 * (R + 8);
     f += 32 + 64 * LIST_CAP;                              // row lists
     f += FZ_FLEN * FZ_M + 64;
-    f += (size_t)l * FZ_K;
-    f += 2 * FZ_KCAP + 2 * LIST_CAP + (R + 16) + 64;
+    f += 2 * FZ_KCAP + 2 * LIST_CAP + 64;
     return f * 4 + (size_t)(R + 16) + 64;
 }
 __device__ __forceinline__ void carve_b(SmemB& s, float* base, int R, int Lb) {
-    const int c = Lb - FZ_FL + 1, l = c - FZ_H + 1;
     float* p = base;
     s.F = p; p += FZ_H * FZ_M2 * FZ_K;
     s.D = p; p += FZ_FLEN * FZ_M; s.Dt = p; p += FZ_FLEN * FZ_M; s.Dr = p; p += FZ_FLEN * FZ_M;
     s.dFt = p; p += FZ_NTGT * FZ_M2;
     s.dz = p; p += R * FZ_M; s.dy = p; p += R * FZ_M; s.dal = p; p += R * FZ_M; s.dbe = p; p += R * FZ_M;
-    s.gzs = p; p += R * FZ_M; s.gys = p; p += R * FZ_M; s.zs = p; p += R * FZ_M; s.ys = p; p += R * FZ_M;
+    s.gzs = p; p += R * FZ_M; s.gys = p; p += R * FZ_M;
     s.dfx = p; p += R * FZ_M2;
     const size_t A = (size_t)R * FZ_M2, A2 = (size_t)2 * (R + 14) * FZ_M;
     s.A = p; p += (A > A2 ? A : A2);
     s.sig = p; p += 4 * (R + 8); s.sig2 = p; p += 4 * (R + 8);
     s.w = p; p += 32 + 64 * LIST_CAP;
     s.dDp = p; p += FZ_FLEN * FZ_M; s.dscp = p; p += 64;
-    s.dxd = p; p += (size_t)l * FZ_K;
     s.kl = reinterpret_cast<int*>(p); p += FZ_KCAP; s.kv = p; p += FZ_KCAP;
     s.li2 = reinterpret_cast<int*>(p); p += LIST_CAP; s.lv2 = p; p += LIST_CAP;
-    s.istart = reinterpret_cast<int*>(p); p += R + 16;
     s.red = p; p += 32; s.iscr = reinterpret_cast<int*>(p); p += 32;
     s.b = reinterpret_cast<uint8_t*>(p);
-}
-
-// dFp[a][k][j] += sum over own rows r and list entries (i, k, v) with a = r - i in [0, 12): Arow[r][j] * v      (F_gradient, model.jl:292-302,
-// restricted to the CTA's rows; one thread per (a, j) walks its rows in order: no two threads share a target, the order is fixed)
-__device__ void fgrad_scatter(const Ctx& c, const float* Arow, const int* li, const float* lv, int cnt, int l, float* dFp, int* istart) {
-    // entries are ordered by flat index = (position, filter): first entry at or after every position of [p0 - 11, p1]
-    const int i_lo = c.p0 - (FZ_H - 1), npos = c.nr + FZ_H;
-    for (int t = threadIdx.x; t <= npos; t += FZ_THREADS) {
-        const int key = (i_lo + t) * FZ_K;
-        int lo = 0, hi = cnt;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (li[mid] < key) lo = mid + 1; else hi = mid; }
-        istart[t] = lo;
-    }
-    __syncthreads();
-    for (int o = threadIdx.x; o < FZ_H * FZ_M2; o += FZ_THREADS) {
-        const int a = o / FZ_M2, j = o - a * FZ_M2;
-        for (int pl = 0; pl < c.nr; ++pl) {
-            const int i = c.p0 + pl - a;
-            if (i < 0 || i >= l) continue;
-            const int t = i - i_lo;
-            const int q0 = istart[t], q1 = istart[t + 1];
-            if (q0 == q1) continue;
-            const float av = Arow[pl * FZ_M2 + j];
-            for (int q = q0; q < q1; ++q) { const int k = li[q] - i * FZ_K; dFp[(a * FZ_K + k) * FZ_M2 + j] += av * lv[q]; }
-        }
-    }
-    __syncthreads();
 }
 
 // F_gradient (model.jl:292-302) of one sequence, balanced over its cluster whatever rows the codes sit in: dF[a][k][:] += sum over the list
@@ -1062,7 +1148,7 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
     c.p0 = min(cc, c.r * R); c.p1 = min(cc, c.p0 + R); c.nr = c.p1 - c.p0;
     c.i0 = min(l, c.p0); c.i1 = min(l, c.p1); c.ni = c.i1 - c.i0;
     c.q1 = (c.r == FZ_CL - 1) ? Lb : c.p1;
-    c.epoch = 0; c.bar = B.bar + c.g; c.tbar = 0; c.nbar = 0; c.tb1 = c.tb2 = c.tb3 = 0;
+    c.epoch = 0; c.bar = B.bar + c.g; c.tbar = 0; c.nbar = 0; c.tb1 = c.tb2 = c.tb3 = 0; for (int i = 0; i < 24; ++i) c.sub[i] = 0; c.subt = 0;
     float* const data = B.data; float* const grad = W.grad;
     const float* sc = data + P.sc;
     const int64_t nZ = (int64_t)cc * FZ_M, nZY = (int64_t)cc * FZ_M2, nX = (int64_t)l * FZ_K, nS = (int64_t)4 * Lb;
@@ -1087,8 +1173,6 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
         const float* gz_ = grad + SEQ(XL.z_out, nZ) + (size_t)c.p0 * FZ_M; const float* gy_ = grad + SEQ(XL.y_out, nZ) + (size_t)c.p0 * FZ_M;
         for (int o = threadIdx.x; o < c.nr * FZ_M; o += FZ_THREADS) { s.dz[o] = __ldcg(gz_ + o); s.dy[o] = __ldcg(gy_ + o); s.dal[o] = 0.f; s.dbe[o] = 0.f; }
         for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) s.dfx[o] = 0.f;
-        const float* gx_ = grad + SEQ(XL.x_out, nX);
-        for (int e = threadIdx.x; e < E; e += FZ_THREADS) s.dxd[e] = __ldcg(gx_ + e);
     }
     __syncthreads();
     build_Dt(sv);
@@ -1149,7 +1233,7 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
                 #pragma unroll
                 for (int u = 0; u < 38; ++u) { const int t = lane + 32 * u; if (t < FZ_H * FZ_M2) acc += xr[u] * s.F[(size_t)t * FZ_K + k]; }
                 acc = warp_sum(acc);
-                if (lane == 0) xch[q] = acc + s.dxd[e];
+                if (lane == 0) xch[q] = acc + __ldcg(grad + SEQ(X.x_out, nX) + e);          // + what later consumers of x+ already left there
             }
         }
         FZ_T(4);
@@ -1162,12 +1246,11 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
             const float* xch = W.xch + (size_t)c.n * FZ_KCAP;
             const float* gg = data + SEQ(X.g, nX);
             float som = 0.f;
-            for (int e = threadIdx.x; e < E; e += FZ_THREADS) s.dxd[e] = 0.f;
-            __syncthreads();
+            float* gxin = grad + SEQ(X.x_in, nX);                  // d x of the pass's input: zero except on the kept support
             if (threadIdx.x < cnt) {
                 const float gr = __ldcg(xch + threadIdx.x);
                 const int e = s.kl[threadIdx.x];
-                s.dxd[e] = gr;
+                if (c.r == 0) gxin[e] = gr;
                 som = -gr * __ldcg(gg + e);
                 s.kv[threadIdx.x] = -om * gr;                      // the d g list shares the kept entries
             }
@@ -1207,7 +1290,6 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
                 s.dz[o] = tz * (1.f - eta * rho); s.dy[o] = ty * (1.f - eta * rho);
                 const float dgz = -eta * tz, dgy = -eta * ty;
                 s.gzs[o] = dgz; s.gys[o] = dgy; dgz_g[o] = dgz; dgy_g[o] = dgy;
-                s.zs[o] = ziv; s.ys[o] = yiv;
                 s.dfx[pl * FZ_M2 + m] = dl + eta * rho * tz; s.dfx[pl * FZ_M2 + FZ_M + m] = dr + eta * rho * ty;
                 s.dal[o] += dl + eta * rho * tz; s.dbe[o] += dr + eta * rho * ty;
                 s_eta += tz * (-(gzv + rho * ez) - lam) + ty * (-(gyv + rho * ey) - lam);
@@ -1235,6 +1317,10 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
                 recon_rows(c, sv, lo, hi, q0, q1, 0.f, nullptr, 0, 0, Lb);
             }
             __syncthreads();
+            // the pass's input codes (own rows) for dgrad(z, y; d rec): the halo staging area is free again
+            const float* zi = data + SEQ(X.z_in, nZ) + (size_t)c.p0 * FZ_M; const float* yi = data + SEQ(X.y_in, nZ) + (size_t)c.p0 * FZ_M;
+            for (int o = threadIdx.x; o < c.nr * FZ_M; o += FZ_THREADS) { s.A[o] = __ldcg(zi + o); s.A[R * FZ_M + o] = __ldcg(yi + o); }
+            __syncthreads();
         }
         FZ_T(12);
         // dD += dgrad(dgz, dgy; r) + dgrad(z, y; d rec)  (32-lag gradient, model.jl:270-290 form) over own rows; then
@@ -1246,7 +1332,7 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
             for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.f;
             for (int pl = 0; pl < c.nr; ++pl) {
                 const float2 gz2 = *reinterpret_cast<const float2*>(s.gzs + pl * FZ_M + 2 * mp), gy2 = *reinterpret_cast<const float2*>(s.gys + pl * FZ_M + 2 * mp);
-                const float2 z2 = *reinterpret_cast<const float2*>(s.zs + pl * FZ_M + 2 * mp), y2 = *reinterpret_cast<const float2*>(s.ys + pl * FZ_M + 2 * mp);
+                const float2 z2 = *reinterpret_cast<const float2*>(s.A + pl * FZ_M + 2 * mp), y2 = *reinterpret_cast<const float2*>(s.A + R * FZ_M + pl * FZ_M + 2 * mp);
                 const float4 rf = *reinterpret_cast<const float4*>(s.sig2 + 4 * pl + 4 * tg), rr = *reinterpret_cast<const float4*>(s.sig2 + 4 * pl + FZ_FLEN - 4 - 4 * tg);
                 const float4 df = *reinterpret_cast<const float4*>(s.sig + 4 * pl + 4 * tg), dr = *reinterpret_cast<const float4*>(s.sig + 4 * pl + FZ_FLEN - 4 - 4 * tg);
                 // tau = 4tg + i reads r[4p + tau] (forward: .x .y .z .w) and r[4p + 31 - tau] (reversed block: .w .z .y .x)
@@ -1278,8 +1364,6 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
         for (int o = threadIdx.x; o < c.nr * FZ_M; o += FZ_THREADS) { gz_[o] = s.dz[o]; gy_[o] = s.dy[o]; }
         float* gf_ = grad + SEQ(X0.fx_in, nZY) + (size_t)c.p0 * FZ_M2;
         for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) gf_[o] = s.dfx[o];
-        float* gx_ = grad + SEQ(X0.x_in, nX);
-        for (int e = c.i0 * FZ_K + threadIdx.x; e < c.i1 * FZ_K; e += FZ_THREADS) gx_[e] = s.dxd[e];
     }
     // ---- gradients of the shared parameters: per-CTA partials -> group sums in CTA order ------------------------------------------------
     float* part = B.part + ((size_t)c.g * c.ng + c.gidx) * FZ_PART;
