@@ -3,7 +3,8 @@ NVCC      ?= nvcc
 CC        := gcc
 PKG       := motifs.jl_b200
 CSRC      := $(PKG)/csrc
-LIB       := $(PKG)/lib/libmotifs_b200.so
+BUILD     ?= build
+LIB       ?= $(PKG)/lib/libmotifs_b200.so
 NVFLAGS   := -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xcompiler -Wall
 ifdef TCS_PROFILE
 NVFLAGS   += -DTCS_PROFILE=1
@@ -16,15 +17,15 @@ HDR       := $(wildcard $(CSRC)/*.cuh) include/motifs_b200.h
 
 all: $(LIB) oracle
 
-OBJ       := $(patsubst $(CSRC)/%.cu,build/%.o,$(CU))
+OBJ       := $(patsubst $(CSRC)/%.cu,$(BUILD)/%.o,$(CU))
 
 # one object per translation unit (make -j compiles them in parallel); NCCL is bound at run time (csrc/comm.cu), so only libdl is linked
-build/%.o: $(CSRC)/%.cu $(HDR)
-	@mkdir -p build
+$(BUILD)/%.o: $(CSRC)/%.cu $(HDR)
+	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 
 $(LIB): $(OBJ)
-	@mkdir -p $(PKG)/lib
+	@mkdir -p $(dir $(LIB))
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(OBJ) -ldl
 
 oracle: oracle/liboracle.so

@@ -200,6 +200,8 @@ typedef struct {                 /* Hyperparam, model.jl:1-14 (same defaults exp
  * with the fp32 path (stated tolerance in tests/test_csc_gpu.py), off by default.                  */
 #define MB200_CSC_NO_FUSED 0x100  /* OR into forward_only: keep the kernel-per-op tape instead of the fused persistent forward kernel
                                      (same results within fp32 summation order; for A/B measurements and tests)            */
+#define MB200_CSC_NO_FUSED_DF 0x200 /* OR into forward_only: the reverse pass of the loss and the ADMM_DF passes stays on the tape
+                                     (the forward kernel and the fused reverse pass of the ADMM_XYZ passes are kept)       */
 int32_t mb200_csc_create(mb200_ctx* ctx, const mb200_hparams* hp, int64_t Lb, int32_t n_groups,
                          int32_t forward_only, mb200_csc** out);
 int32_t mb200_csc_destroy(mb200_ctx* ctx, mb200_csc* csc);

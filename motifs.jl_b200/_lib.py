@@ -414,7 +414,7 @@ class Sequences:
 class CscModel:
     """mb200_csc: the unrolled CSC network for one (hyper-parameters, Lb, n_groups) shape on one device."""
 
-    def __init__(self, ctx: Context, hp, Lb: int, n_groups: int = 1, forward_only: bool = False, tensor_cores: bool = False, fused: bool = True):
+    def __init__(self, ctx: Context, hp, Lb: int, n_groups: int = 1, forward_only: bool = False, tensor_cores: bool = False, fused: bool = True, fused_df: bool = True):
         self.ctx = ctx
         self.hp = hp
         self.Lb, self.n_groups, self.forward_only = int(Lb), int(n_groups), bool(forward_only)
@@ -423,7 +423,7 @@ class CscModel:
         h = C.c_void_p()
         if tensor_cores and not forward_only:
             raise ValueError("the tensor-core path is forward-only (code retrieval)")
-        ctx._check(ctx._lib.mb200_csc_create(ctx._h, C.byref(chp), self.Lb, self.n_groups, (2 if tensor_cores else int(self.forward_only)) | (0 if fused else 0x100), C.byref(h)))
+        ctx._check(ctx._lib.mb200_csc_create(ctx._h, C.byref(chp), self.Lb, self.n_groups, (2 if tensor_cores else int(self.forward_only)) | (0 if fused else 0x100) | (0 if fused_df else 0x200), C.byref(h)))
         self._h = h
         nt, na = C.c_int64(), C.c_int64()
         ctx._check(ctx._lib.mb200_csc_n_params(self._h, C.byref(nt), C.byref(na)))

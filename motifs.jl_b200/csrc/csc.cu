@@ -82,6 +82,7 @@ struct mb200_csc {
     FzPlan fz{}; bool fused = false, no_fused = false; size_t fz_smem = 0; int fz_nmed = 0;
     uint8_t* fz_sync = nullptr; size_t fz_sync_bytes = 0, fz_zero_bytes = 0; FzBufs fzb{};
     bool fused_bwd = false; size_t fzb_smem = 0; FzBwd fzw{}; float* fz_bwd_buf = nullptr; unsigned int* fz_err_host = nullptr;
+    bool fused_bwd_df = false, no_fused_df = false; size_t fzd_smem = 0;      // loss + ADMM_DF reverse pass as one kernel (needs fused_bwd)
     size_t op_xyz_begin = 0, op_xyz_end = 0;                // tape ops of the ADMM_XYZ passes: [begin, end)
     Buf zero_al{}, zero_be{};
 };
@@ -533,13 +534,22 @@ static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
             }
             if (s->fused_bwd) {
                 const size_t nF = (size_t)d.h * d.M2 * d.K, nD = (size_t)d.f_len * d.M;
-                const size_t n_dFp = (size_t)d.NS * nF, n_xch = (size_t)d.NS * FZ_KCAP, n_gsum = G * (nF + nD + 64);
+                const size_t n_dFp = (size_t)d.NS * nF, n_xch = (size_t)d.NS * FZ_KCAP, n_gsum = 2 * G * (nF + nD + 64);      // second half: group sums of the DF reverse kernel
                 MB_CUDA(ctx, cudaMalloc(&s->fz_bwd_buf, (n_dFp + n_xch + n_gsum + 64) * 4));
                 MB_CUDA(ctx, cudaMemset(s->fz_bwd_buf, 0, (n_dFp + n_xch + n_gsum + 64) * 4));
                 s->fzw.grad = s->grad; s->fzw.dFp = s->fz_bwd_buf; s->fzw.xch = s->fz_bwd_buf + n_dFp; s->fzw.gsum = s->fzw.xch + n_xch;
                 s->fzw.err = (unsigned int*)(s->fzw.gsum + n_gsum);
                 MB_CUDA(ctx, cudaMallocHost(&s->fz_err_host, 64));
                 *s->fz_err_host = 0;
+                s->fzd_smem = fz::fzd_smem_bytes(d.Lb);
+                if (!s->no_fused_df && s->fzd_smem <= ctx->smem_optin &&
+                    cudaFuncSetAttribute(k_csc_fused_bwd_df, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->fzd_smem) == cudaSuccess) {
+                    int nclus = 0;
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3((unsigned)(d.NS * FZ_CL)); cfg.blockDim = dim3(FZ_THREADS); cfg.dynamicSmemBytes = s->fzd_smem;
+                    if (cudaOccupancyMaxActiveClusters(&nclus, k_csc_fused_bwd_df, &cfg) != cudaSuccess) { cudaGetLastError(); nclus = 0; }
+                    s->fused_bwd_df = nclus >= d.NS;
+                }
             }
         }
     }
@@ -576,6 +586,7 @@ extern "C" int32_t mb200_csc_create(mb200_ctx* ctx, const mb200_hparams* hp, int
     MB_CUDA(ctx, cudaSetDevice(ctx->device));
     mb200_csc* s = new mb200_csc();
     s->no_fused = (forward_only & 0x100) != 0;            // MB200_CSC_NO_FUSED: keep the kernel-per-op tape (A/B tests of the fused step)
+    s->no_fused_df = (forward_only & 0x200) != 0;         // MB200_CSC_NO_FUSED_DF: loss / ADMM_DF reverse pass on the tape (A/B tests)
     forward_only &= 0xff;
     s->ctx = ctx; s->hp = *hp; s->xyz_only = forward_only != 0;
     s->tensor = forward_only == 2;
@@ -712,6 +723,23 @@ static void enqueue_step(mb200_csc* s, const uint32_t* words, int64_t rowwords, 
         cudaMemsetAsync(s->grad, 0, s->arena * 4, q);
         cudaMemsetAsync(s->g_raw, 0, (size_t)s->n_total * 4, q);
         for (size_t i = s->tape.size(); i-- > 0;) {
+            if (s->fused_bwd_df && i >= s->op_xyz_end) {
+                if (i + 1 == s->tape.size()) {
+                    // loss, ADMM_DF passes and the final mask in reverse as ONE persistent kernel: leaves d z, d y, d x (kept support) of the
+                    // final codes for the XYZ kernel below and its share of dD, dF, d scalars in the second half of gsum
+                    cudaMemsetAsync(s->fz_sync, 0, 256, q);
+                    s->fzw.grad = s->grad;
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3((unsigned)(d.NS * FZ_CL)); cfg.blockDim = dim3(FZ_THREADS); cfg.dynamicSmemBytes = s->fzd_smem; cfg.stream = q;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+                    cfg.attrs = at; cfg.numAttrs = 1;
+                    float* gsum2 = s->fzw.gsum + (size_t)d.G * ((size_t)d.h * d.M2 * d.K + (size_t)d.f_len * d.M + 64);
+                    cudaLaunchKernelEx(&cfg, k_csc_fused_bwd_df, s->fz, s->fzb, s->fzw, gsum2, d);
+                    ++g_lk_count;
+                }
+                continue;
+            }
             if (s->fused_bwd && i >= s->op_xyz_begin && i < s->op_xyz_end) {
                 if (i + 1 == s->op_xyz_end) {
                     // the reverse pass of all ADMM_XYZ passes as ONE persistent kernel: reads the adjoints the DF / loss ops left for the final
@@ -725,7 +753,7 @@ static void enqueue_step(mb200_csc* s, const uint32_t* words, int64_t rowwords, 
                     cfg.attrs = at; cfg.numAttrs = 1;
                     cudaLaunchKernelEx(&cfg, k_csc_fused_bwd_xyz, s->fz, s->fzb, s->fzw, d);
                     const int nF = d.h * d.M2 * d.K, nD = d.f_len * d.M, nsc = 3 * d.npx + d.npx + 3 * d.npd + 3;
-                    lk(k_csc_fused_finish, nblk(nF + nD + 64, 256), 256, 0, q, (const float*)s->fzw.gsum, d.G, nF, nD, nsc,
+                    lk(k_csc_fused_finish, nblk(nF + nD + 64, 256), 256, 0, q, (const float*)s->fzw.gsum, s->fused_bwd_df ? 2 * d.G : d.G, nF, nD, nsc,
                        s->grad + s->Feff.off, s->grad + s->Deff.off, s->grad + s->sc.off);
                     ++g_lk_count;
                 }

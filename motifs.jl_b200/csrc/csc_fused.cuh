@@ -440,7 +440,9 @@ __device__ void corr2d_rows(const Smem& s, const float* Fm, int ni) {
 // cnt <= LIST_CAP: a warp first builds, per own row, the ordered list of the codes that reach it (offset of F[a][.][kq], value) in s.w;
 // then one thread per output (row, j) walks only those.  cnt <= lcap (a longer list held in li/lv): every output walks the whole list.
 // Otherwise (forward only: more codes than the list holds) the dense tensor xg is read from global.  out: [nr][100].  Uses s.w.
-__device__ void tconv_list(const Ctx& c, const Smem& s, const float* Fm, const int* li, const float* lv, int cnt, int lcap, const float* xg, int l, float* out) {
+// Filter element (a, j, k) sits at Fm[a*sa + j*sj + k*sk]: (2M*K, K, 1) for the [a][j][k] layout of F, (2M, 1, h*2M) for a k-major copy.
+__device__ void tconv_list(const Ctx& c, const Smem& s, const float* Fm, const int* li, const float* lv, int cnt, int lcap, const float* xg, int l, float* out,
+                           int sa = FZ_M2 * FZ_K, int sj = FZ_K, int sk = 1) {
     const int R = c.nr;
     int* rcnt = reinterpret_cast<int*>(s.w); int* roff = rcnt + 32; float* rval = s.w + 32 + 32 * LIST_CAP;      // rows <= 32
     if (cnt <= LIST_CAP) {
@@ -454,7 +456,7 @@ __device__ void tconv_list(const Ctx& c, const Smem& s, const float* Fm, const i
                 if (q < cnt) { const int e = li[q], iq = e / FZ_K; kq = e - iq * FZ_K; a = i - iq; v = lv[q]; }
                 const bool hit = a >= 0 && a < FZ_H;
                 const unsigned mk = __ballot_sync(FULLMASK, hit);
-                if (hit) { const int o = run + __popc(mk & ((1u << lane) - 1u)); roff[il * LIST_CAP + o] = a * FZ_M2 * FZ_K + kq; rval[il * LIST_CAP + o] = v; }
+                if (hit) { const int o = run + __popc(mk & ((1u << lane) - 1u)); roff[il * LIST_CAP + o] = a * sa + kq * sk; rval[il * LIST_CAP + o] = v; }
                 run += __popc(mk);
             }
             if (lane == 0) rcnt[il] = run;
@@ -464,7 +466,7 @@ __device__ void tconv_list(const Ctx& c, const Smem& s, const float* Fm, const i
             const int il = o / FZ_M2, j = o - il * FZ_M2;
             const int n = rcnt[il];
             float acc = 0.f;
-            for (int q = 0; q < n; ++q) acc += rval[il * LIST_CAP + q] * Fm[roff[il * LIST_CAP + q] + j * FZ_K];
+            for (int q = 0; q < n; ++q) acc += rval[il * LIST_CAP + q] * Fm[roff[il * LIST_CAP + q] + j * sj];
             out[o] = acc;
         }
     } else if (cnt <= lcap) {
@@ -473,7 +475,7 @@ __device__ void tconv_list(const Ctx& c, const Smem& s, const float* Fm, const i
             float acc = 0.f;
             for (int q = 0; q < cnt; ++q) {
                 const int e = li[q], iq = e / FZ_K, kq = e - iq * FZ_K, a = i - iq;
-                if (a >= 0 && a < FZ_H) acc += lv[q] * Fm[((size_t)a * FZ_M2 + j) * FZ_K + kq];
+                if (a >= 0 && a < FZ_H) acc += lv[q] * Fm[a * sa + j * sj + kq * sk];
             }
             out[o] = acc;
         }
@@ -483,7 +485,7 @@ __device__ void tconv_list(const Ctx& c, const Smem& s, const float* Fm, const i
             float acc = 0.f;
             const int a_lo = max(0, i - l + 1), a_hi = min(FZ_H - 1, i);
             for (int a = a_lo; a <= a_hi; ++a)
-                for (int k = 0; k < FZ_K; ++k) { const float xv = __ldcg(xg + (size_t)(i - a) * FZ_K + k); if (xv != 0.f) acc += xv * Fm[((size_t)a * FZ_M2 + j) * FZ_K + k]; }
+                for (int k = 0; k < FZ_K; ++k) { const float xv = __ldcg(xg + (size_t)(i - a) * FZ_K + k); if (xv != 0.f) acc += xv * Fm[a * sa + j * sj + k * sk]; }
             out[o] = acc;
         }
     }
@@ -1404,6 +1406,404 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
     if (blockIdx.x < 16 && threadIdx.x == 0)
         printf("[fzb-cta %2d] dots %6lld fgrad1 %6lld b2 %6lld | topq %6lld tconv %6lld fgrad2 %6lld elem %6lld b3 %6lld | recon %6lld dgrad %6lld b1 %6lld kept %6lld duals %6lld\n", (int)blockIdx.x,
                fz_acc[4], fz_acc[5], fz_acc[6], fz_acc[7], fz_acc[8], fz_acc[9], fz_acc[10], fz_acc[11], fz_acc[12], fz_acc[13], fz_acc[3], fz_acc[1], fz_acc[2]);
+#endif
+#undef SEQ
+}
+
+// =================================================================================================================================
+// reverse pass of everything after the ADMM_XYZ passes: loss, the ADMM_DF passes, the final mask (model.jl:310-325, 362-373, 206-210)
+// =================================================================================================================================
+// Same cluster-per-sequence layout.  Inputs are the tape tensors the forward kernel left (final z, y, code list, zy', and per DF pass
+// rec, G, D+, e, Fg, F+, ||.||); outputs are d z, d y of the final codes (own rows), d x on the support the last top-q kept (all the
+// XYZ reverse pass reads), and the group sums of d D0, d F0, d mu/kappa/kappa_s.  Per pass, in reverse: the adjoints of the two
+// GROUP-level updates need batch sums, so a pass costs two group barriers like its forward:
+//   B1: per-sequence partials of d F+ (owned targets, via dFp) and of d D+ (cluster sums, via part) are published
+//       -> d_update adjoint redundantly in every CTA (d D, d G, d mu); f_update adjoint of filter k in CTA k (d F kept there, d Fg published)
+//   B2: d Fg is published -> per sequence: u = tconv(x; d Fg) (adjoint of e), d x += corr2d(e; d Fg) + corr2d(w; F) on the kept support,
+//       d F += fgrad(w, x);  d rec = recon(z, y; d G), d z,y += corr_sig(rec + S; d G) + corr_sig(d rec; D), d D += dgrad(z, y; d rec).
+// fx(x, F_n) enters e_n and theta_n with opposite signs, so the adjoint w_n of that product is u_0 for the first pass, the adjoint of
+// theta_{n+1} for the middle passes and exactly zero for the last one (the tape adds and subtracts the same term there).
+namespace fz {
+
+struct SmemDf {
+    float *Dc, *dG, *Dt, *Dr, *dDg, *Gp;                // current D, d G, its two tap-major forms, group-level part of d D, this CTA's dgrad partial
+    float *sig, *sigB;                                  // recon output (d rec) / signal loaded from the tape (rec + S, or the loss residual)
+    float *zy;                                          // z | y rows [p0 - 7, p1 + 7) of the final codes (constant)
+    float *dzyF, *dth, *u;                              // [R][100]: adjoint of zy', of theta, tconv output
+    float *w;                                           // row lists of tconv
+    float *dFt;                                         // [FZ_NTGT][100] partial d F of the owned targets
+    float *duK;                                         // [h*2M] d F (group-level part) of the filter this CTA owns
+    float *dxv; int* kl; int* li2; float* lv2;          // d x on the kept support, kept entries, code list
+    float *dscp, *red; int* iscr;
+    float *dz, *dy;                                     // [R][50]
+    uint8_t* b;
+};
+__host__ __device__ inline size_t fzd_smem_bytes(int Lb) {
+    const int c = Lb - FZ_FL + 1, R = fz_rows(c);
+    size_t f = (size_t)6 * FZ_FLEN * FZ_M + (size_t)8 * (R + 8) + (size_t)2 * (R + 14) * FZ_M + (size_t)3 * R * FZ_M2;
+    f += 32 + 64 * LIST_CAP;
+    f += (size_t)FZ_NTGT * FZ_M2 + (size_t)FZ_H * FZ_M2 + 2 * FZ_KCAP + 2 * LIST_CAP + 64 + 32 + 32;
+    f += (size_t)2 * R * FZ_M + 8;
+    return f * 4 + (size_t)(R + 16) + 64;
+}
+__device__ __forceinline__ void carve_df(SmemDf& s, float* base, int R) {
+    float* p = base;
+    s.Dc = p; p += FZ_FLEN * FZ_M; s.dG = p; p += FZ_FLEN * FZ_M; s.Dt = p; p += FZ_FLEN * FZ_M; s.Dr = p; p += FZ_FLEN * FZ_M;
+    s.dDg = p; p += FZ_FLEN * FZ_M; s.Gp = p; p += FZ_FLEN * FZ_M;
+    s.sig = p; p += 4 * (R + 8); s.sigB = p; p += 4 * (R + 8);
+    s.zy = p; p += 2 * (R + 14) * FZ_M;
+    s.dzyF = p; p += R * FZ_M2; s.dth = p; p += R * FZ_M2; s.u = p; p += R * FZ_M2;
+    s.w = p; p += 32 + 64 * LIST_CAP;
+    s.dFt = p; p += FZ_NTGT * FZ_M2;
+    s.duK = p; p += FZ_H * FZ_M2;
+    s.dxv = p; p += FZ_KCAP; s.kl = reinterpret_cast<int*>(p); p += FZ_KCAP;
+    s.li2 = reinterpret_cast<int*>(p); p += LIST_CAP; s.lv2 = p; p += LIST_CAP;
+    s.dscp = p; p += 64; s.red = p; p += 32; s.iscr = reinterpret_cast<int*>(p); p += 32;
+    s.dz = p; p += R * FZ_M; s.dy = p; p += R * FZ_M;
+    p += 8;
+    s.b = reinterpret_cast<uint8_t*>(p);
+}
+
+// kept entries (flat index, ascending) of a top-q bitmap [E bytes]; the same list in every CTA of the cluster.  Returns the count (capped).
+__device__ int kept_from_bits(const uint8_t* bits, int E, int* kl, int* iscr, unsigned int* err) {
+    const uint32_t* bw = reinterpret_cast<const uint32_t*>(bits);
+    const int nw = E >> 2;
+    const int per = (nw + FZ_THREADS - 1) / FZ_THREADS;
+    const int w0 = threadIdx.x * per, w1 = min(nw, w0 + per);
+    int k = 0;
+    for (int w = w0; w < w1; ++w) { const uint32_t v = bw[w]; k += ((v & 0xffu) != 0) + ((v & 0xff00u) != 0) + ((v & 0xff0000u) != 0) + ((v >> 24) != 0); }
+    int total;
+    int o = block_excl_scan512(k, &total, iscr);
+    for (int w = w0; w < w1; ++w) {
+        const uint32_t v = bw[w];
+        #pragma unroll
+        for (int bb = 0; bb < 4; ++bb) if ((v >> (8 * bb)) & 0xffu) { if (o < FZ_KCAP) kl[o] = 4 * w + bb; ++o; }
+    }
+    if (total > FZ_KCAP) { if (threadIdx.x == 0) atomicOr(err, 1u); total = FZ_KCAP; }
+    __syncthreads();
+    return total;
+}
+
+// d x[e] += sum_{t < h*2M} rows[i*2M + t] * Fm[t*K + k] for the kept entries e = i*K + k this CTA owns (entry q -> CTA q % 8, one warp each)
+__device__ void dots_kept(const Ctx& c, const float* rows_g, const float* Fm, const int* kl, int cnt, float* dxv, int st = FZ_K, int sk = 1) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = c.r + FZ_CL * warp; q < cnt; q += FZ_CL * (FZ_THREADS / 32)) {
+        const int e = kl[q], i = e / FZ_K, k = e - i * FZ_K;
+        const float* rows = rows_g + (size_t)i * FZ_M2;
+        float xr[38], fr[38];
+        #pragma unroll
+        for (int u = 0; u < 38; ++u) { const int t = lane + 32 * u; xr[u] = t < FZ_H * FZ_M2 ? __ldcg(rows + t) : 0.f; }
+        #pragma unroll
+        for (int u = 0; u < 38; ++u) { const int t = lane + 32 * u; fr[u] = t < FZ_H * FZ_M2 ? __ldcg(Fm + (size_t)t * st + (size_t)k * sk) : 0.f; }
+        float acc = 0.f;
+        #pragma unroll
+        for (int u = 0; u < 38; ++u) acc += xr[u] * fr[u];
+        acc = warp_sum(acc);
+        if (lane == 0) dxv[q] += acc;
+    }
+    __syncthreads();
+}
+
+// own rows: d z,y += corr_sig(sig1; f1) (+ corr_sig(sig2; f2)) and this CTA's partial Gp = dgrad(z, y; sigG); signals cover base positions [p0, p1 + 7)
+__device__ void d_data_step(const Ctx& c, const float* zown, const float* yown, const float* sig1, const float* f1, const float* sig2, const float* f2,
+                            const float* sigG, float* Gp, float* dz, float* dy) {
+    const int nt = (FZ_FLEN / 4) * (FZ_M / 2);                     // 200 tiles of 4 taus x 2 filters
+    if ((int)threadIdx.x < nt) {
+        const int o = threadIdx.x, tg = o / (FZ_M / 2), mp = o - tg * (FZ_M / 2);
+        float acc[4][2];
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.f;
+        for (int pl = 0; pl < c.nr; ++pl) {
+            const float2 z2 = *reinterpret_cast<const float2*>(zown + pl * FZ_M + 2 * mp), y2 = *reinterpret_cast<const float2*>(yown + pl * FZ_M + 2 * mp);
+            const float4 rf = *reinterpret_cast<const float4*>(sigG + 4 * pl + 4 * tg), rr = *reinterpret_cast<const float4*>(sigG + 4 * pl + FZ_FLEN - 4 - 4 * tg);
+            const float f[4] = {rf.x, rf.y, rf.z, rf.w}, rv[4] = {rr.w, rr.z, rr.y, rr.x};
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) { acc[i][0] += z2.x * f[i] + y2.x * rv[i]; acc[i][1] += z2.y * f[i] + y2.y * rv[i]; }
+        }
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) { Gp[(4 * tg + i) * FZ_M + 2 * mp] = acc[i][0]; Gp[(4 * tg + i) * FZ_M + 2 * mp + 1] = acc[i][1]; }
+    } else {
+        for (int o = threadIdx.x - nt; o < c.nr * FZ_M; o += FZ_THREADS - nt) {
+            const int pl = o / FZ_M, m = o - pl * FZ_M;
+            float a = 0.f, b = 0.f;
+            #pragma unroll 8
+            for (int k = 0; k < FZ_FLEN; ++k) { const float r = sig1[4 * pl + k]; a += r * f1[k * FZ_M + m]; b += r * f1[(FZ_FLEN - 1 - k) * FZ_M + m]; }
+            if (sig2) {
+                #pragma unroll 8
+                for (int k = 0; k < FZ_FLEN; ++k) { const float r = sig2[4 * pl + k]; a += r * f2[k * FZ_M + m]; b += r * f2[(FZ_FLEN - 1 - k) * FZ_M + m]; }
+            }
+            dz[o] += a; dy[o] += b;
+        }
+    }
+    __syncthreads();
+}
+
+}  // namespace fz
+
+__global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_csc_fused_bwd_df(const FzPlan P, const FzBufs B, const FzBwd W, float* __restrict__ gsum2, const CscDims d) {
+    using namespace fz;
+    namespace cg = cooperative_groups;
+    extern __shared__ __align__(16) float fz_smem[];
+    const int Lb = d.Lb, cc = d.c, l = d.l;
+    const int R = fz_rows(cc);
+    SmemDf s; carve_df(s, fz_smem, R);
+    Ctx c;
+    c.n = blockIdx.x / FZ_CL; c.r = blockIdx.x % FZ_CL; c.g = c.n / d.B; c.gidx = (c.n % d.B) * FZ_CL + c.r; c.ng = d.B * FZ_CL; c.ncl = d.B;
+    c.p0 = min(cc, c.r * R); c.p1 = min(cc, c.p0 + R); c.nr = c.p1 - c.p0;
+    c.i0 = min(l, c.p0); c.i1 = min(l, c.p1); c.ni = c.i1 - c.i0;
+    c.q1 = (c.r == FZ_CL - 1) ? Lb : c.p1;
+    c.epoch = 0; c.bar = B.bar + c.g; c.tbar = 0; c.nbar = 0; c.tb1 = c.tb2 = c.tb3 = 0; for (int i = 0; i < 24; ++i) c.sub[i] = 0; c.subt = 0;
+    float* const data = B.data; float* const grad = W.grad;
+    const float* sc = data + P.sc;
+    const int64_t nZ = (int64_t)cc * FZ_M, nZY = (int64_t)cc * FZ_M2, nX = (int64_t)l * FZ_K, nS = (int64_t)4 * Lb;
+    const int nD = FZ_FLEN * FZ_M, nF = FZ_H * FZ_M2 * FZ_K, HJ = FZ_H * FZ_M2;
+    const float mf = d.mf;
+    FZ_TDECL;
+    Smem sv; sv.F = nullptr; sv.D = s.dG; sv.Dt = s.Dt; sv.Dr = s.Dr; sv.A = s.zy; sv.sig = s.sig; sv.w = s.w; sv.b = s.b; sv.red = s.red; sv.iscr = s.iscr;
+    sv.z = sv.y = sv.fx = sv.al = sv.be = sv.th = sv.zyF = sv.gout = nullptr; sv.li = s.li2; sv.lv = s.lv2; sv.lc = nullptr;
+#define SEQ(off, per) ((off) + (int64_t)c.n * (per))
+    const FzPass& XL = P.px[P.npx - 1];
+    const int lo7 = max(0, c.p0 - 7), hi7 = min(cc, c.p1 + 7);
+    const int q0 = c.p0, q1 = min(Lb, c.p1 + 7);
+    const int nq4 = c.nr > 0 ? 4 * (q1 - q0) : 0;
+    const float* zown = s.zy + (c.p0 - lo7) * FZ_M; const float* yown = s.zy + (hi7 - lo7) * FZ_M + (c.p0 - lo7) * FZ_M;
+    float* part = B.part + ((size_t)c.g * c.ng + c.gidx) * FZ_PART;
+    const float* gpart = B.part + (size_t)c.g * c.ng * FZ_PART;
+    float* cpart = B.part + ((size_t)c.g * c.ng + (c.n % d.B) * FZ_CL) * FZ_PART;            // the cluster's slot (its rank-0 CTA's)
+    cg::cluster_group cl = cg::this_cluster();
+    // sum of the cluster's dgrad partials through distributed shared memory (rank order) -> the cluster's slot; call between two cluster barriers
+    auto cluster_reduce_Gp = [&]() {
+        const int per = nD / FZ_CL;
+        for (int o = threadIdx.x; o < per; o += FZ_THREADS) {
+            const int e = c.r * per + o;
+            float acc = 0.f;
+            #pragma unroll
+            for (int q = 0; q < FZ_CL; ++q) acc += cl.map_shared_rank(s.Gp, q)[e];
+            cpart[e] = acc;
+        }
+    };
+    auto publish_dFt = [&]() {
+        for (int o = threadIdx.x; o < FZ_NTGT * FZ_M2; o += FZ_THREADS) {
+            const int lt = o / FZ_M2, t = lt * FZ_CL + c.r;
+            if (t < FZ_H * FZ_K) W.dFp[((size_t)c.n * (FZ_H * FZ_K) + t) * FZ_M2 + (o - lt * FZ_M2)] = s.dFt[o];
+        }
+    };
+    // ---- prologue ----------------------------------------------------------------------------------------------------------------
+    {
+        const int nb_own = min(Lb, c.p1 + 7 + FZ_FL) - c.p0;
+        for (int e = threadIdx.x; e < nb_own; e += FZ_THREADS) s.b[e] = B.bases[(size_t)c.n * Lb + c.p0 + e];
+        for (int o = threadIdx.x; o < R * FZ_M; o += FZ_THREADS) { s.dz[o] = 0.f; s.dy[o] = 0.f; }
+        for (int o = threadIdx.x; o < R * FZ_M2; o += FZ_THREADS) { s.dzyF[o] = 0.f; s.dth[o] = 0.f; }
+        for (int e = threadIdx.x; e < nD; e += FZ_THREADS) s.dDg[e] = 0.f;
+        for (int e = threadIdx.x; e < HJ; e += FZ_THREADS) s.duK[e] = 0.f;
+        if (threadIdx.x < 64) s.dscp[threadIdx.x] = 0.f;
+        if (threadIdx.x < FZ_KCAP) s.dxv[threadIdx.x] = 0.f;
+        if (hi7 > lo7) stage_zy_halo(sv, data + SEQ(XL.z_out, nZ), data + SEQ(XL.y_out, nZ), lo7, hi7);
+    }
+    int cnt2 = __ldcg(B.lcnt + (size_t)XL.xl_out * d.NS + c.n);
+    if (cnt2 > LIST_CAP) { if (threadIdx.x == 0) atomicOr(W.err, 2u); cnt2 = LIST_CAP; }
+    if ((int)threadIdx.x < cnt2) { s.li2[threadIdx.x] = __ldcg(B.lidx + ((size_t)XL.xl_out * d.NS + c.n) * LIST_CAP + threadIdx.x); s.lv2[threadIdx.x] = __ldcg(B.lval + ((size_t)XL.xl_out * d.NS + c.n) * LIST_CAP + threadIdx.x); }
+    const int cnt = kept_from_bits(B.bits + XL.bits + (size_t)c.n * nX, l * FZ_K, s.kl, s.iscr + 8, W.err);
+    FZ_T(0);
+    // ---- loss (model.jl:310-325): d recL = sw (recL - S), d fxL = sw (fxL - zy'), d zy' = -d fxL ------------------------------------------
+    {
+        const float sw = 2.f / ((float)d.G * (float)d.B);
+        const FzDf& YL = P.df[P.npd - 1];
+        for (int e = threadIdx.x; e < nD; e += FZ_THREADS) s.Dc[e] = __ldcg(data + YL.Dn + (int64_t)c.g * nD + e);
+        const float* recg = data + SEQ(P.recL, nS);
+        for (int t = threadIdx.x; t < nq4; t += FZ_THREADS) {
+            const int q = q0 + (t >> 2);
+            s.sigB[t] = sw * (__ldcg(recg + 4 * q0 + t) - (s.b[q - c.p0] == (t & 3) ? 1.f : 0.f));
+        }
+        const float* fg = data + SEQ(P.fxL, nZY) + (size_t)c.p0 * FZ_M2; const float* zyg = data + SEQ(P.zyF, nZY) + (size_t)c.p0 * FZ_M2;
+        float* scr = grad + SEQ(P.fxL, nZY) + (size_t)c.p0 * FZ_M2;
+        for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) { const float v = sw * (__ldcg(fg + o) - __ldcg(zyg + o)); s.dzyF[o] = -v; scr[o] = v; }
+        for (int o = threadIdx.x; o < FZ_NTGT * FZ_M2; o += FZ_THREADS) s.dFt[o] = 0.f;
+        __syncthreads();
+        d_data_step(c, zown, yown, s.sigB, s.Dc, nullptr, nullptr, s.sigB, s.Gp, s.dz, s.dy);
+        cluster_barrier();                                        // d fxL rows and the dgrad partials of the cluster are complete
+        cluster_reduce_Gp();
+        dots_kept(c, grad + SEQ(P.fxL, nZY), data + YL.Fn + (int64_t)c.g * nF, s.kl, cnt, s.dxv);
+        fgrad_targets(c, grad + SEQ(P.fxL, nZY), s.li2, s.lv2, cnt2, s.dFt);
+        publish_dFt();
+        cluster_barrier();                                        // remote reads of Gp are done
+    }
+    FZ_T(1);
+    // ---- ADMM_DF passes in reverse ---------------------------------------------------------------------------------------------------
+    for (int n = P.npd - 1; n >= 0; --n) {
+        const FzDf& Y = P.df[n];
+        const float mu = sc[Y.i_mu], kap = sc[Y.i_kap], kaps = sc[Y.i_kaps];
+        const bool has_partial = (n + 1 == P.npd) || (n + 1 <= P.npd - 2);      // some sequence-level term reached d F_{n+1}
+        const bool has_w = (n == 0) || (n <= P.npd - 2);
+        group_barrier(c);                                         // B1
+        FZ_T(2);
+        // d_update adjoint (model.jl:287-288), redundantly: d D+ = group-level part + the clusters' data terms
+        {
+            for (int o = threadIdx.x; o < nD; o += FZ_THREADS) {
+                float v[8];
+                #pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = q < d.B ? __ldcg(gpart + (size_t)q * FZ_CL * FZ_PART + o) : 0.f;
+                float acc = s.dDg[o];
+                #pragma unroll
+                for (int q = 0; q < 8; ++q) acc += v[q];
+                s.dDg[o] = acc;
+                s.Dc[o] = __ldcg(data + Y.D_in + (int64_t)c.g * Y.D_in_gs + o);
+            }
+            __syncthreads();
+            float s_mu = 0.f;
+            for (int o = threadIdx.x; o < FZ_FL * FZ_M; o += FZ_THREADS) {
+                const int m = o % FZ_M, j = o / FZ_M;
+                float Gv[4], ex[4], uu[4], dDn[4], ssum = 0.f, dot = 0.f;
+                #pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int e = (4 * j + a) * FZ_M + m;
+                    Gv[a] = __ldcg(data + Y.Gm + (int64_t)c.g * nD + e); ex[a] = expf(-mu * Gv[a]); uu[a] = s.Dc[e] * ex[a]; ssum += uu[a];
+                    dDn[a] = s.dDg[e]; dot += dDn[a] * __ldcg(data + Y.Dn + (int64_t)c.g * nD + e);
+                }
+                #pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int e = (4 * j + a) * FZ_M + m;
+                    const float du = (dDn[a] - dot) / ssum;
+                    s.dDg[e] = du * ex[a]; s.dG[e] = du * uu[a] * (-mu); s_mu += du * uu[a] * (-Gv[a]);
+                }
+            }
+            s_mu = block_sum512(s_mu, s.red);
+            if (threadIdx.x == 0 && c.gidx == 0) s.dscp[Y.i_mu] += s_mu;
+            __syncthreads();
+            build_Dt(sv);                                         // tap-major forms of d G for recon
+        }
+        FZ_T(3);
+        // f_update adjoint (model.jl:304-308) of filter k = gidx: d F+ = what this CTA kept + the sequences' partials; d Fg published
+        float* dFg_g = grad + Y.Fg + (int64_t)c.g * nF;           // scratch: the tape's adjoint slot of Fg
+        if (c.gidx < FZ_K) {
+            const int k = c.gidx;
+            float dFv[3], fnv[3], dot = 0.f;
+            #pragma unroll
+            for (int it = 0; it < 3; ++it) {
+                const int e = threadIdx.x + it * FZ_THREADS;
+                dFv[it] = 0.f; fnv[it] = 0.f;
+                if (e < HJ) {
+                    float acc = s.duK[e];
+                    if (has_partial) {
+                        const int a = e / FZ_M2, j = e - a * FZ_M2;
+                        float v[8];
+                        #pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = q < d.B ? __ldcg(W.dFp + ((size_t)(c.g * d.B + q) * (FZ_H * FZ_K) + a * FZ_K + k) * FZ_M2 + j) : 0.f;
+                        #pragma unroll
+                        for (int q = 0; q < 8; ++q) acc += v[q];
+                    }
+                    dFv[it] = acc; fnv[it] = __ldcg(data + Y.Fn + (int64_t)c.g * nF + (size_t)e * FZ_K + k);
+                    dot += acc * fnv[it];
+                }
+            }
+            dot = block_sum512(dot, s.red);
+            const float nn = __ldcg(data + Y.nrm + (int64_t)c.g * FZ_K + k);
+            float s_kap = 0.f, s_kaps = 0.f;
+            #pragma unroll
+            for (int it = 0; it < 3; ++it) {
+                const int e = threadIdx.x + it * FZ_THREADS;
+                if (e < HJ) {
+                    float du = 0.f;
+                    if (fnv[it] > 0.f) {
+                        du = (dFv[it] - dot * fnv[it]) / nn;
+                        s_kap += du * (-__ldcg(data + Y.Fg + (int64_t)c.g * nF + (size_t)e * FZ_K + k) - kaps);
+                        s_kaps += du * (-kap);
+                    }
+                    s.duK[e] = du;
+                    dFg_g[(size_t)k * HJ + e] = -kap * du;                 // k-major: a filter's 1200 entries are contiguous for the dots and the tconv below
+                }
+            }
+            s_kap = block_sum512(s_kap, s.red); s_kaps = block_sum512(s_kaps, s.red);
+            if (threadIdx.x == 0) { s.dscp[Y.i_kap] += s_kap; s.dscp[Y.i_kaps] += s_kaps; }
+        }
+        FZ_T(4);
+        group_barrier(c);                                         // B2: d Fg is published
+        FZ_T(5);
+        // D chain of the sequence: d rec = recon(z, y; d G); d z,y += corr_sig(rec + S; d G) + corr_sig(d rec; D); d D += dgrad(z, y; d rec)
+        {
+            const float* recg = data + SEQ(Y.rec, nS);
+            for (int t = threadIdx.x; t < nq4; t += FZ_THREADS) {
+                const int q = q0 + (t >> 2);
+                s.sigB[t] = __ldcg(recg + 4 * q0 + t) + (s.b[q - c.p0] == (t & 3) ? 1.f : 0.f);
+            }
+            if (c.nr > 0) recon_rows(c, sv, lo7, hi7, q0, q1, 0.f, nullptr, 0, 0, Lb);
+            __syncthreads();
+            d_data_step(c, zown, yown, s.sig, s.Dc, s.sigB, s.dG, s.sig, s.Gp, s.dz, s.dy);
+        }
+        FZ_T(6);
+        // F chain of the sequence
+        dots_kept(c, data + SEQ(Y.e, nZY), dFg_g, s.kl, cnt, s.dxv, 1, HJ);                // d x += corr2d(e; d Fg)
+        FZ_T(7);
+        tconv_list(c, sv, dFg_g, s.li2, s.lv2, cnt2, LIST_CAP, nullptr, l, s.u, FZ_M2, 1, HJ);      // u = d e = tconv(x; d Fg)
+        {
+            float* scr = grad + SEQ(Y.e, nZY) + (size_t)c.p0 * FZ_M2;
+            for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) {
+                const float uv = s.u[o], th_old = s.dth[o];
+                float dzy = s.dzyF[o] - uv;
+                if (n >= 1) { const float th_new = th_old - uv; s.dth[o] = th_new; dzy -= th_new; }
+                s.dzyF[o] = dzy;
+                if (has_w) scr[o] = n == 0 ? uv : th_old;
+            }
+            if (has_w) for (int o = threadIdx.x; o < FZ_NTGT * FZ_M2; o += FZ_THREADS) s.dFt[o] = 0.f;
+        }
+        FZ_T(8);
+        cluster_barrier();                                        // w rows and the dgrad partials of the cluster are complete
+        cluster_reduce_Gp();
+        if (has_w) {
+            dots_kept(c, grad + SEQ(Y.e, nZY), data + Y.F_in + (int64_t)c.g * Y.F_in_gs, s.kl, cnt, s.dxv);      // d x += corr2d(w; F)
+            fgrad_targets(c, grad + SEQ(Y.e, nZY), s.li2, s.lv2, cnt2, s.dFt);                               // d F += fgrad(w, x)
+            publish_dFt();
+        }
+        FZ_T(9);
+        cluster_barrier();
+    }
+    // ---- final mask (model.jl:206-210) and the hand-over to the XYZ reverse pass ----------------------------------------------------------
+    {
+        const float med = __ldcg(data + P.medF + c.g);
+        float* gz_ = grad + SEQ(XL.z_out, nZ) + (size_t)c.p0 * FZ_M; float* gy_ = grad + SEQ(XL.y_out, nZ) + (size_t)c.p0 * FZ_M;
+        for (int o = threadIdx.x; o < c.nr * FZ_M; o += FZ_THREADS) {
+            const int pl = o / FZ_M, m = o - pl * FZ_M;
+            const float zv = zown[o], yv = yown[o];
+            gz_[o] = s.dz[o] + (zv >= med ? mf * s.dzyF[pl * FZ_M2 + m] : 0.f);
+            gy_[o] = s.dy[o] + (yv >= med ? mf * s.dzyF[pl * FZ_M2 + FZ_M + m] : 0.f);
+        }
+        float* gx = grad + SEQ(XL.x_out, nX);
+        for (int q = threadIdx.x; q < cnt; q += FZ_THREADS) if ((q % FZ_CL) == c.r) gx[s.kl[q]] = s.dxv[q];
+        if (threadIdx.x < 64) part[nD + threadIdx.x] = s.dscp[threadIdx.x];
+    }
+    group_barrier(c);
+    {
+        float* gs = gsum2 + (size_t)c.g * (nF + nD + 64);
+        if (c.gidx < FZ_K) {                                      // d F0 column k = the group-level part + the sequences' fgrad(u_0, x)
+            const int k = c.gidx;
+            for (int e = threadIdx.x; e < HJ; e += FZ_THREADS) {
+                const int a = e / FZ_M2, j = e - a * FZ_M2;
+                float acc = s.duK[e];
+                for (int q = 0; q < d.B; ++q) acc += __ldcg(W.dFp + ((size_t)(c.g * d.B + q) * (FZ_H * FZ_K) + a * FZ_K + k) * FZ_M2 + j);
+                gs[(size_t)e * FZ_K + k] = acc;
+            }
+        }
+        if (c.gidx == c.ng - 1) {
+            for (int o = threadIdx.x; o < nD; o += FZ_THREADS) {
+                float acc = s.dDg[o];
+                for (int q = 0; q < d.B; ++q) acc += __ldcg(gpart + (size_t)q * FZ_CL * FZ_PART + o);
+                gs[nF + o] = acc;
+            }
+            if (threadIdx.x < 64) {
+                float acc = 0.f;
+                for (int q = 0; q < c.ng; ++q) acc += __ldcg(gpart + (size_t)q * FZ_PART + nD + threadIdx.x);
+                gs[nF + nD + threadIdx.x] = acc;
+            }
+        }
+    }
+#ifdef FZ_PROFILE
+    FZ_T(10);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const char* nm[11] = {"prologue", "loss", "B1", "d_update adj", "f_update adj", "B2", "D chain", "dots(e,dFg)", "tconv(dFg)+elem", "bar+dots(w)+fgrad", "epilogue"};
+        long long tot = 0; for (int i = 0; i < 11; ++i) tot += fz_acc[i];
+        for (int i = 0; i < 11; ++i) printf("[fzd] %-20s %9lld clk %5.1f%%\n", nm[i], fz_acc[i], 100.0 * fz_acc[i] / tot);
+        printf("[fzd] total %lld clk\n", tot);
+    }
 #endif
 #undef SEQ
 }
