@@ -752,11 +752,22 @@ static void enqueue_step(mb200_csc* s, const uint32_t* words, int64_t rowwords, 
                     at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
                     cfg.attrs = at; cfg.numAttrs = 1;
                     cudaLaunchKernelEx(&cfg, k_csc_fused_bwd_xyz, s->fz, s->fzb, s->fzw, d);
-                    const int nF = d.h * d.M2 * d.K, nD = d.f_len * d.M, nsc = 3 * d.npx + d.npx + 3 * d.npd + 3;
-                    lk(k_csc_fused_finish, nblk(nF + nD + 64, 256), 256, 0, q, (const float*)s->fzw.gsum, s->fused_bwd_df ? 2 * d.G : d.G, nF, nD, nsc,
-                       s->grad + s->Feff.off, s->grad + s->Deff.off, s->grad + s->sc.off);
                     ++g_lk_count;
+                    if (!s->fused_bwd_df) {              // A/B mode with the DF reverse pass on the tape: add the group sums to the tape's adjoints
+                        const int nF = d.h * d.M2 * d.K, nD = d.f_len * d.M, nsc = 3 * d.npx + d.npx + 3 * d.npd + 3;
+                        lk(k_csc_fused_finish, nblk(nF + nD + 64, 256), 256, 0, q, (const float*)s->fzw.gsum, d.G, nF, nD, nsc,
+                           s->grad + s->Feff.off, s->grad + s->Deff.off, s->grad + s->sc.off);
+                    }
                 }
+                continue;
+            }
+            if (s->fused_bwd && i >= 1 && i < s->op_xyz_begin) continue;       // the reverse pass of the warm-up is the tail of k_csc_fused_bwd_xyz
+            if (s->fused_bwd && s->fused_bwd_df && i == 0) {
+                // group sums of both reverse kernels -> adjoint of prep_params -> raw gradient vector, one kernel
+                ScalarSegs tr = s->segs; tr.nseg = 7;      // the warm-up scalars (segment 7) are not trained
+                lk(k_csc_fused_tail, d.K + 2, 256, 0, q, (const float*)s->fzw.gsum, 2 * d.G, (const float*)s->p_raw, s->off_D, s->off_F,
+                   (const float*)(s->data + s->Feff.off), (const float*)(s->data + s->Fnrm0.off), (const float*)(s->data + s->Deff.off),
+                   (const float*)(s->grad + s->Feff.off), (const float*)(s->grad + s->Deff.off), (const float*)(s->grad + s->sc.off), s->g_raw, tr, d);
                 continue;
             }
             run_op(s, s->tape[i], false, q);

@@ -1359,13 +1359,87 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
         __syncthreads();
     }
     FZ_T(14);
-    // ---- hand the adjoints of the warm-up outputs back to the tape: d z0, d y0, d fx0, d x0 -------------------------------------------
+    // ---- reverse pass of the warm-up (model.jl:224-232): fx0 = tconv(x0, F), x0 = top-q(om_w g0), g0 = corr2d(zy0', F), zy0' = mask(z0, y0),
+    //      (z0, y0) = relu(eta_w corr(S, D) - lam_w eta_w); the warm-up scalars are not trained ------------------------------------------------
     {
-        const FzPass& X0 = P.px[0];
-        float* gz_ = grad + SEQ(X0.z_in, nZ) + (size_t)c.p0 * FZ_M; float* gy_ = grad + SEQ(X0.y_in, nZ) + (size_t)c.p0 * FZ_M;
-        for (int o = threadIdx.x; o < c.nr * FZ_M; o += FZ_THREADS) { gz_[o] = s.dz[o]; gy_[o] = s.dy[o]; }
-        float* gf_ = grad + SEQ(X0.fx_in, nZY) + (size_t)c.p0 * FZ_M2;
-        for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) gf_[o] = s.dfx[o];
+        int cnt;
+        {   // kept entries of x0
+            const uint32_t* bw = reinterpret_cast<const uint32_t*>(B.bits + P.bits0 + (size_t)c.n * nX);
+            const int nw = E >> 2;
+            const int per = (nw + FZ_THREADS - 1) / FZ_THREADS;
+            const int w0 = threadIdx.x * per, w1 = min(nw, w0 + per);
+            int k = 0;
+            for (int w = w0; w < w1; ++w) { const uint32_t v = bw[w]; k += ((v & 0xffu) != 0) + ((v & 0xff00u) != 0) + ((v & 0xff0000u) != 0) + ((v >> 24) != 0); }
+            int total;
+            int o = block_excl_scan512(k, &total, s.iscr + 8);
+            for (int w = w0; w < w1; ++w) {
+                const uint32_t v = bw[w];
+                #pragma unroll
+                for (int bb = 0; bb < 4; ++bb) if ((v >> (8 * bb)) & 0xffu) { if (o < FZ_KCAP) s.kl[o] = 4 * w + bb; ++o; }
+            }
+            if (total > FZ_KCAP) { if (threadIdx.x == 0) atomicOr(W.err, 1u); total = FZ_KCAP; }
+            cnt = total;
+        }
+        float* dfx_g = grad + SEQ(P.fx0, nZY);                    // scratch: the tape's slot of d fx0
+        for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) dfx_g[(size_t)c.p0 * FZ_M2 + o] = s.dfx[o];
+        int cnt2 = __ldcg(B.lcnt + (size_t)P.xl0 * d.NS + c.n);
+        if (cnt2 > LIST_CAP) { if (threadIdx.x == 0) atomicOr(W.err, 2u); cnt2 = LIST_CAP; }
+        if (threadIdx.x < cnt2) { s.li2[threadIdx.x] = __ldcg(B.lidx + ((size_t)P.xl0 * d.NS + c.n) * LIST_CAP + threadIdx.x); s.lv2[threadIdx.x] = __ldcg(B.lval + ((size_t)P.xl0 * d.NS + c.n) * LIST_CAP + threadIdx.x); }
+        cluster_barrier();                                        // d fx0 rows (and the d x0 values pass 0 left) are published
+        {
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            float* xch = W.xch + (size_t)c.n * FZ_KCAP;
+            for (int q = c.r + FZ_CL * warp; q < cnt; q += FZ_CL * (FZ_THREADS / 32)) {
+                const int e = s.kl[q], i = e / FZ_K, k = e - i * FZ_K;
+                const float* rows = dfx_g + (size_t)i * FZ_M2;
+                float acc = 0.f;
+                float xr[38];
+                #pragma unroll
+                for (int u = 0; u < 38; ++u) { const int t = lane + 32 * u; xr[u] = t < FZ_H * FZ_M2 ? __ldcg(rows + t) : 0.f; }
+                #pragma unroll
+                for (int u = 0; u < 38; ++u) { const int t = lane + 32 * u; if (t < FZ_H * FZ_M2) acc += xr[u] * s.F[(size_t)t * FZ_K + k]; }
+                acc = warp_sum(acc);
+                if (lane == 0) xch[q] = acc + __ldcg(grad + SEQ(P.x0, nX) + e);
+            }
+        }
+        fgrad_targets(c, dfx_g, s.li2, s.lv2, cnt2, dFp);          // d F += fgrad(d fx0, x0)
+        cluster_barrier();                                        // the sparse d x0 values are published
+        {
+            const float om_w = sc[P.i_om_w];
+            const float* xch = W.xch + (size_t)c.n * FZ_KCAP;
+            if (threadIdx.x < cnt) s.kv[threadIdx.x] = om_w * __ldcg(xch + threadIdx.x);      // d g0 on the kept support
+            __syncthreads();
+        }
+        tconv_list(c, sv, s.F, s.kl, s.kv, cnt, FZ_KCAP, nullptr, l, s.A);                   // d zy0' = tconv(d g0; F) on own rows
+        fgrad_targets(c, data + SEQ(P.zy0, nZY), s.kl, s.kv, cnt, dFp);                     // d F += fgrad(zy0', d g0)
+        {
+            const float med = __ldcg(data + P.med0 + c.g), eta_w = sc[P.i_eta_w];
+            const float* z0 = data + SEQ(P.z0, nZ) + (size_t)c.p0 * FZ_M; const float* y0 = data + SEQ(P.y0, nZ) + (size_t)c.p0 * FZ_M;
+            for (int o = threadIdx.x; o < c.nr * FZ_M; o += FZ_THREADS) {
+                const int pl = o / FZ_M, m = o - pl * FZ_M;
+                const float zv = __ldcg(z0 + o), yv = __ldcg(y0 + o);
+                float dzv = s.dz[o], dyv = s.dy[o];
+                if (zv >= med) dzv += mf * s.A[pl * FZ_M2 + m];
+                if (yv >= med) dyv += mf * s.A[pl * FZ_M2 + FZ_M + m];
+                s.gzs[o] = zv > 0.f ? eta_w * dzv : 0.f;
+                s.gys[o] = yv > 0.f ? eta_w * dyv : 0.f;
+            }
+            __syncthreads();
+            // d D[4j + a][m] += sum over own rows p with base[p + j] == a of gz[p][m], + those with base[p + 7 - j] == 3 - a of gy[p][m]
+            // (the reverse-complement filter reads D[4(7 - j') + 3 - b]); one thread per (j, m), fixed order
+            for (int o = threadIdx.x; o < FZ_FL * FZ_M; o += FZ_THREADS) {
+                const int j = o / FZ_M, m = o - j * FZ_M;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                for (int pl = 0; pl < c.nr; ++pl) {
+                    const int bz = s.b[pl + j], by = 3 - (int)s.b[pl + FZ_FL - 1 - j];
+                    const float gz = s.gzs[pl * FZ_M + m], gy = s.gys[pl * FZ_M + m];
+                    a0 += (bz == 0 ? gz : 0.f) + (by == 0 ? gy : 0.f); a1 += (bz == 1 ? gz : 0.f) + (by == 1 ? gy : 0.f);
+                    a2 += (bz == 2 ? gz : 0.f) + (by == 2 ? gy : 0.f); a3 += (bz == 3 ? gz : 0.f) + (by == 3 ? gy : 0.f);
+                }
+                s.dDp[(4 * j + 0) * FZ_M + m] += a0; s.dDp[(4 * j + 1) * FZ_M + m] += a1; s.dDp[(4 * j + 2) * FZ_M + m] += a2; s.dDp[(4 * j + 3) * FZ_M + m] += a3;
+            }
+            __syncthreads();
+        }
     }
     // ---- gradients of the shared parameters: per-CTA partials -> group sums in CTA order ------------------------------------------------
     float* part = B.part + ((size_t)c.g * c.ng + c.gidx) * FZ_PART;
@@ -1819,3 +1893,67 @@ __global__ void __launch_bounds__(256) k_csc_fused_finish(const float* __restric
     else if (o < nF + nD) gD[o - nF] += acc;
     else if (o - nF - nD < nsc) gsc[o - nF - nD] += acc;
 }
+
+// Last kernel of the fully fused reverse pass: group sums of the two reverse kernels (gsum: [G2][nF + nD + 64]) + whatever already sits in the
+// adjoints of the prepared parameters, pushed through the adjoint of prep_params (model.jl:139-169: F = r^2 / ||r^2||_2 per syntax filter,
+// D = (r^2 + 1e-3) normalised over the four nucleotides, scalars squared) into the raw gradient vector.  Blocks 0..K-1: one syntax filter each;
+// block K: D; block K+1: the trained scalars.  Replaces k_csc_fused_finish + the three prep adjoint kernels of the tape.
+__global__ void __launch_bounds__(256) k_csc_fused_tail(const float* __restrict__ gsum, int G2, const float* __restrict__ raw, int64_t off_D, int64_t off_F,
+                                                        const float* __restrict__ Feff, const float* __restrict__ Fnrm, const float* __restrict__ Deff,
+                                                        const float* __restrict__ gFe, const float* __restrict__ gDe, const float* __restrict__ gsc,
+                                                        float* __restrict__ draw, ScalarSegs sg, CscDims d) {
+    __shared__ float s_de[FZ_H * FZ_M2];
+    __shared__ float s_dot;
+    const int nF = d.h * d.M2 * d.K, nD = d.f_len * d.M, tot = nF + nD + 64, HJ = d.h * d.M2;
+    if ((int)blockIdx.x < d.K) {
+        const int k = blockIdx.x;
+        float dot = 0.f;
+        for (int e = threadIdx.x; e < HJ; e += blockDim.x) {           // e = j*h + a in raw order
+            const int a = e % d.h, j = e / d.h;
+            const int64_t o = ((int64_t)a * d.M2 + j) * d.K + k;
+            float de = gFe[o];
+            for (int g = 0; g < G2; ++g) de += gsum[(size_t)g * tot + o];
+            s_de[e] = de; dot += de * Feff[o];
+        }
+        dot = block_sum(dot);
+        if (threadIdx.x == 0) s_dot = dot;
+        __syncthreads();
+        dot = s_dot;
+        const float nn = Fnrm[k];
+        for (int e = threadIdx.x; e < HJ; e += blockDim.x) {
+            const int a = e % d.h, j = e / d.h;
+            const int64_t o = ((int64_t)a * d.M2 + j) * d.K + k;
+            const float r = raw[off_F + (int64_t)k * HJ + e];
+            draw[off_F + (int64_t)k * HJ + e] += (s_de[e] - dot * Feff[o]) / nn * 2.f * r;
+        }
+    } else if ((int)blockIdx.x == d.K) {
+        for (int t = threadIdx.x; t < d.fl * d.M; t += blockDim.x) {
+            const int m = t % d.M, j = t / d.M;
+            float de[4], ssum = 0.f, dot = 0.f;
+            #pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int o = (4 * j + a) * d.M + m;
+                const float r = raw[off_D + m * d.f_len + 4 * j + a];
+                ssum += r * r + 0.001f;
+                float v = gDe[o];
+                for (int g = 0; g < G2; ++g) v += gsum[(size_t)g * tot + nF + o];
+                de[a] = v; dot += v * Deff[o];
+            }
+            #pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const float r = raw[off_D + m * d.f_len + 4 * j + a];
+                draw[off_D + m * d.f_len + 4 * j + a] += (de[a] - dot) / ssum * 2.f * r;
+            }
+        }
+    } else {
+        const int w = threadIdx.x >> 5;
+        if (w < sg.nseg)
+            for (int i = threadIdx.x & 31; i < sg.n[w]; i += 32) {
+                const int idx = sg.eff_idx[w] + i;
+                float de = gsc[idx];
+                for (int g = 0; g < G2; ++g) de += gsum[(size_t)g * tot + nF + nD + idx];
+                draw[sg.raw_off[w] + i] += 2.f * raw[sg.raw_off[w] + i] * de;
+            }
+    }
+}
+
