@@ -500,6 +500,11 @@ static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
                               d.B * LIST_CAP <= FZ_THREADS && d.B * FZ_CL >= FZ_K && d.c >= FZ_CL && d.l >= 1 && fz::fz_rows(d.c) <= 32;
         if (!s->no_fused && !s->tensor && shape_ok && s->fz_smem <= ctx->smem_optin) {
             cudaError_t e = cudaFuncSetAttribute(k_csc_fused_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->fz_smem);
+#if FZ_CL > 8
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_csc_fused_fwd, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_csc_fused_bwd_xyz, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_csc_fused_bwd_df, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+#endif
             int nclus = 0;
             if (e == cudaSuccess) {
                 cudaLaunchConfig_t cfg = {};

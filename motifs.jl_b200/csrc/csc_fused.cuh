@@ -2,12 +2,12 @@
 //
 // Reference: model.jl:330-395 (ADMM_XYZ, ADMM_DF, forward_pass_return_loss), restated in position space.
 // The tape of csc.cu runs the same arithmetic as ~95 kernels of 2-25 us whose time is L2 round trips and launch gaps: six
-// sequences cannot fill 148 SMs.  Here a sequence is owned by a CLUSTER of 8 CTAs (CTA r owns a contiguous range of its c = Lb-7
+// sequences cannot fill 148 SMs.  Here a sequence is owned by a CLUSTER of FZ_CL = 16 CTAs (CTA r owns a contiguous range of its c = Lb-7
 // positions) and a whole pass is computed without leaving the kernel:
 //   * per-sequence chains (recon -> corr_sig -> zy update, d build -> corr2d -> top-q -> tconv -> dual) need no barrier at all except
 //     one cluster barrier for the per-sequence top-q: what a CTA needs from its neighbours (a halo of 7 or 11 positions) it
 //     RECOMPUTES from tensors the neighbours published in global memory before the last barrier, instead of waiting for them;
-//   * only the batch-wide statistics cross sequences: the median of the batch (two barriers over the group's 48 CTAs: merged
+//   * only the batch-wide statistics cross sequences: the median of the batch (two barriers over the group's 96 CTAs: merged
 //     4096-bin histogram, then the median bin's candidates), the batch sums of the D and F gradients of ADMM_DF, the loss;
 //   * the syntax filters F (115 KB), the dictionary D and the CTA's rows of z, y, alpha, beta, fx, theta stay in shared memory
 //     across passes; every intermediate the reverse pass needs is also written to the tape's arena (fire-and-forget stores).
@@ -18,7 +18,9 @@
 #include <cooperative_groups.h>
 
 #define FZ_THREADS 512
-#define FZ_CL 8                   // CTAs per sequence = cluster size
+#ifndef FZ_CL
+#define FZ_CL 16                  // CTAs per sequence = cluster size.  16 is a non-portable cluster size (opt-in attribute, one cluster per GPC):
+#endif                            // measured 0.65 -> 0.59 ms per step against 8 (make FZ_CL=8 builds that variant); handles that cannot place it keep the tape
 #define FZ_M 50
 #define FZ_M2 100
 #define FZ_K 24
@@ -55,7 +57,7 @@ struct FzBufs {
     unsigned int* hist;           // [G][nmed][FZ_NHIST][FZ_BINS] merged histograms (zeroed before the launch)
     float* cand;                  // [G][nmed][FZ_CAND]
     unsigned int* cctl;           // [G][nmed][4]: candidates reserved, ~min bits above the bin
-    float* part;                  // [G][48][FZ_PART] per-CTA partial sums
+    float* part;                  // [G][B * FZ_CL][FZ_PART] per-CTA partial sums
 };
 #define FZ_PART 2048              // floats of partial-sum space per CTA (D gradient 1600, loss 2, ...)
 
@@ -91,9 +93,9 @@ struct Ctx {
 __device__ __forceinline__ unsigned int ld_relaxed(const unsigned int* p) {
     unsigned int v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
-// barrier over the CTAs of one group; global writes before it are visible to every CTA of the group after it.  Hierarchical: the 8 CTAs
+// barrier over the CTAs of one group; global writes before it are visible to every CTA of the group after it.  Hierarchical: the CTAs
 // of a cluster meet at the hardware cluster barrier, only the cluster's rank-0 CTA arrives at / polls the counter in global memory (6
-// arrivals on one address instead of 48: same-address atomics serialise in L2), a second cluster barrier releases the others.
+// arrivals on one address instead of 96: same-address atomics serialise in L2), a second cluster barrier releases the others.
 // Ordering: the cluster barrier orders every CTA's writes before the leader's gpu-scope fence, which is cumulative over them; the leader's
 // acquire fence after the poll and the second cluster barrier order them before every reader (which reads other CTAs' data with ld.cg).
 __device__ __forceinline__ void group_barrier(Ctx& c) {
@@ -824,7 +826,7 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
                 for (int i = 0; i < 4; ++i) { Gp[(4 * tg + i) * FZ_M + 2 * mp] = acc[i][0]; Gp[(4 * tg + i) * FZ_M + 2 * mp + 1] = acc[i][1]; }
             }
             FZ_S(c, 17);
-            // sum over the cluster's 8 CTAs through distributed shared memory (rank order), one slice of 200 entries per CTA; the 6 cluster
+            // sum over the CTAs of the cluster through distributed shared memory (rank order), one slice of 1600 / FZ_CL entries per CTA; the 6 cluster
             // sums go through global memory
             cluster_barrier();
             {
@@ -983,7 +985,7 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
         group_barrier(c);
         FZ_S(c, 22);
         if (c.gidx == 0) {
-            float* la = s.w; float* lb = s.w + 64;                 // one load per thread (a serial loop would pay an L2 round trip per term)
+            float* la = s.w; float* lb = s.w + 256;                 // one load per thread (a serial loop would pay an L2 round trip per term)
             if (threadIdx.x < c.ng) { la[threadIdx.x] = __ldcg(gpart + (size_t)threadIdx.x * FZ_PART); lb[threadIdx.x] = __ldcg(gpart + (size_t)threadIdx.x * FZ_PART + 1); }
             __syncthreads();
             if (threadIdx.x == 0) {
@@ -1037,7 +1039,7 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
 
 struct FzBwd {                    // extra buffers of the reverse pass
     float* grad;                  // the tape's adjoint arena (same offsets as data)
-    float* dFp;                   // [NS][h*K][2M] per-sequence partial of dF, layout [a][k][j] (row t = a*K + k written by the cluster's CTA t % 8)
+    float* dFp;                   // [NS][h*K][2M] per-sequence partial of dF, layout [a][k][j] (row t = a*K + k written by the cluster's CTA t % FZ_CL)
     float* xch;                   // [NS][FZ_KCAP] exchange of the sparse dx values inside a cluster
     float* gsum;                  // [G][nF + nD + 64] group sums: dF (layout [a][j][k]), dD, dsc
     unsigned int* err;            // set when a sequence has more than FZ_KCAP kept entries / an overlong code list
@@ -1045,7 +1047,7 @@ struct FzBwd {                    // extra buffers of the reverse pass
 
 namespace fz {
 
-#define FZ_NTGT ((FZ_H * FZ_K + FZ_CL - 1) / FZ_CL)      // dF targets (a, k) a CTA owns: t = a*K + k with t % 8 == rank
+#define FZ_NTGT ((FZ_H * FZ_K + FZ_CL - 1) / FZ_CL)      // dF targets (a, k) a CTA owns: t = a*K + k with t % FZ_CL == rank
 struct SmemB {
     float *F, *D, *Dt, *Dr;
     float *dFt;                                         // [FZ_NTGT][2M] this CTA's partial of dF for the targets it owns
@@ -1091,7 +1093,7 @@ __device__ __forceinline__ void carve_b(SmemB& s, float* base, int R, int Lb) {
 }
 
 // F_gradient (model.jl:292-302) of one sequence, balanced over its cluster whatever rows the codes sit in: dF[a][k][:] += sum over the list
-// entries (i, k, v) of v * A[i + a][:].  CTA r of the cluster owns the targets (a, k) with (a*K + k) % 8 == r; one warp per owned target
+// entries (i, k, v) of v * A[i + a][:].  CTA r of the cluster owns the targets (a, k) with (a*K + k) % FZ_CL == r; one warp per owned target
 // walks the list in order (fixed summation order), reads the rows of A from global memory (published before the preceding barrier) and
 // does ONE update of the CTA's shared-memory partial.  No two warps share a target, no atomics.
 __device__ void fgrad_targets(const Ctx& c, const float* Ag /* global [c][2M] of the sequence */, const int* li, const float* lv, int cnt, float* dFt) {
@@ -1221,7 +1223,7 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
         FZ_T(2);
         cluster_barrier();                                        // #1: every CTA's rows of d fx+ are published
         FZ_T(3);
-        // (h') adjoint of fx+ = x+ (*) F on the kept support: entry q is taken by CTA q % 8, one warp per entry
+        // (h') adjoint of fx+ = x+ (*) F on the kept support: entry q is taken by CTA q % FZ_CL, one warp per entry
         {
             const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
             float* xch = W.xch + (size_t)c.n * FZ_KCAP;
@@ -1558,7 +1560,7 @@ __device__ int kept_from_bits(const uint8_t* bits, int E, int* kl, int* iscr, un
     return total;
 }
 
-// d x[e] += sum_{t < h*2M} rows[i*2M + t] * Fm[t*K + k] for the kept entries e = i*K + k this CTA owns (entry q -> CTA q % 8, one warp each)
+// d x[e] += sum_{t < h*2M} rows[i*2M + t] * Fm[t*K + k] for the kept entries e = i*K + k this CTA owns (entry q -> CTA q % FZ_CL, one warp each)
 __device__ void dots_kept(const Ctx& c, const float* rows_g, const float* Fm, const int* kl, int cnt, float* dxv, int st = FZ_K, int sk = 1) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int q = c.r + FZ_CL * warp; q < cnt; q += FZ_CL * (FZ_THREADS / 32)) {
