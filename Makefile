@@ -9,6 +9,9 @@ NVFLAGS   := -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -X
 ifdef TCS_PROFILE
 NVFLAGS   += -DTCS_PROFILE=1
 endif
+ifdef EXTRA_DEFS
+NVFLAGS   += $(EXTRA_DEFS)
+endif
 ifdef FZ_CL
 NVFLAGS   += -DFZ_CL=$(FZ_CL)
 endif

@@ -707,72 +707,78 @@ static void run_op(mb200_csc* s, Op& op, bool fwd, cudaStream_t q) {
     if (fwd) op.fwd(qq); else op.bwd(qq);
 }
 
+// Invariant of the fused kernels' sync area (barrier counters of the three kernels, median histograms and controls): it is all-zero
+// whenever a step begins.  The fully fused training step restores that in its last kernel (k_csc_fused_tail); every other fused path
+// clears it with memset nodes after the last kernel that used it.  Likewise the adjoint arena: the fully fused step reads only the d x
+// slots from it before writing, and those are cleared by their reader (k_csc_fused_bwd_xyz), so it needs no memset per step.
+#define FZ_BAR_DF 21          // barrier counters: forward kernel [0, 21), DF reverse kernel [21, 42), XYZ reverse kernel [42, 63) (one per group)
+#define FZ_BAR_XYZ 42
+static void launch_fused(mb200_csc* s, int which, cudaStream_t q) {
+    const CscDims d = s->d;
+    FzBufs fb = s->fzb;
+    fb.bases = s->bases; fb.data = s->data; fb.bits = s->bits; fb.lcnt = s->lcnt; fb.lidx = s->lidx; fb.lval = s->lval;
+    s->fzw.grad = s->grad;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(d.NS * FZ_CL)); cfg.blockDim = dim3(FZ_THREADS); cfg.stream = q;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (which == 0) { cfg.dynamicSmemBytes = s->fz_smem; cudaLaunchKernelEx(&cfg, k_csc_fused_fwd, s->fz, fb, d); }
+    else if (which == 1) {
+        fb.bar += FZ_BAR_DF; cfg.dynamicSmemBytes = s->fzd_smem;
+        float* gsum2 = s->fzw.gsum + (size_t)d.G * ((size_t)d.h * d.M2 * d.K + (size_t)d.f_len * d.M + 64);
+        cudaLaunchKernelEx(&cfg, k_csc_fused_bwd_df, s->fz, fb, s->fzw, gsum2, d);
+    } else { fb.bar += FZ_BAR_XYZ; cfg.dynamicSmemBytes = s->fzb_smem; cudaLaunchKernelEx(&cfg, k_csc_fused_bwd_xyz, s->fz, fb, s->fzw, d); }
+    ++g_lk_count;
+}
+
 static void enqueue_step(mb200_csc* s, const uint32_t* words, int64_t rowwords, const int64_t* idx_dev, bool backward, cudaStream_t q) {
     const CscDims d = s->d;
-    lk(k_unpack_bases, nblk((int64_t)d.NS * d.Lb, 256), 256, 0, q, words, rowwords, idx_dev, s->bases, d);
+    const bool fused_all = backward && s->fused && s->fused_bwd && s->fused_bwd_df;
     if (s->fused) {
-        // parameter preparation (three small kernels), then the whole forward pass as ONE persistent cooperative kernel
-        s->tape[0].fwd(q);
-        cudaMemsetAsync(s->fz_sync, 0, s->fz_zero_bytes, q);
-        s->fzb.bases = s->bases; s->fzb.data = s->data; s->fzb.bits = s->bits; s->fzb.lcnt = s->lcnt; s->fzb.lidx = s->lidx; s->fzb.lval = s->lval;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(d.NS * FZ_CL)); cfg.blockDim = dim3(FZ_THREADS); cfg.dynamicSmemBytes = s->fz_smem; cfg.stream = q;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, k_csc_fused_fwd, s->fz, s->fzb, d);
-        ++g_lk_count;
-    } else
-    for (auto& op : s->tape) run_op(s, op, true, q);
+        // prep_params + unpacking of the batch in one kernel, then the whole forward pass as ONE persistent cooperative kernel
+        lk(k_csc_fused_head, d.K + 2 + (unsigned)std::min<int64_t>(8, ((int64_t)d.NS * d.Lb + 255) / 256), 256, 0, q, (const float*)s->p_raw, s->off_D, s->off_F,
+           s->data + s->Feff.off, s->data + s->Fnrm0.off, s->data + s->Deff.off, s->data + s->sc.off, s->segs, words, rowwords, idx_dev, s->bases, d);
+        launch_fused(s, 0, q);
+        if (!fused_all) cudaMemsetAsync(s->fz_sync, 0, s->fz_zero_bytes, q);
+    } else {
+        lk(k_unpack_bases, nblk((int64_t)d.NS * d.Lb, 256), 256, 0, q, words, rowwords, idx_dev, s->bases, d);
+        for (auto& op : s->tape) run_op(s, op, true, q);
+    }
     if (backward) {
-        cudaMemsetAsync(s->grad, 0, s->arena * 4, q);
-        cudaMemsetAsync(s->g_raw, 0, (size_t)s->n_total * 4, q);
+        if (!fused_all) {
+            cudaMemsetAsync(s->grad, 0, s->arena * 4, q);
+            cudaMemsetAsync(s->g_raw, 0, (size_t)s->n_total * 4, q);
+        }
         for (size_t i = s->tape.size(); i-- > 0;) {
             if (s->fused_bwd_df && i >= s->op_xyz_end) {
-                if (i + 1 == s->tape.size()) {
-                    // loss, ADMM_DF passes and the final mask in reverse as ONE persistent kernel: leaves d z, d y, d x (kept support) of the
-                    // final codes for the XYZ kernel below and its share of dD, dF, d scalars in the second half of gsum
-                    cudaMemsetAsync(s->fz_sync, 0, 256, q);
-                    s->fzw.grad = s->grad;
-                    cudaLaunchConfig_t cfg = {};
-                    cfg.gridDim = dim3((unsigned)(d.NS * FZ_CL)); cfg.blockDim = dim3(FZ_THREADS); cfg.dynamicSmemBytes = s->fzd_smem; cfg.stream = q;
-                    cudaLaunchAttribute at[1];
-                    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
-                    cfg.attrs = at; cfg.numAttrs = 1;
-                    float* gsum2 = s->fzw.gsum + (size_t)d.G * ((size_t)d.h * d.M2 * d.K + (size_t)d.f_len * d.M + 64);
-                    cudaLaunchKernelEx(&cfg, k_csc_fused_bwd_df, s->fz, s->fzb, s->fzw, gsum2, d);
-                    ++g_lk_count;
-                }
+                // loss, ADMM_DF passes and the final mask in reverse as ONE persistent kernel: leaves d z, d y, d x (kept support) of the
+                // final codes for the XYZ kernel below and its share of dD, dF, d scalars in the second half of gsum
+                if (i + 1 == s->tape.size()) launch_fused(s, 1, q);
                 continue;
             }
             if (s->fused_bwd && i >= s->op_xyz_begin && i < s->op_xyz_end) {
                 if (i + 1 == s->op_xyz_end) {
-                    // the reverse pass of all ADMM_XYZ passes as ONE persistent kernel: reads the adjoints the DF / loss ops left for the final
-                    // z, y, x, hands d z0, d y0, d fx0, d x0 to the warm-up ops, and adds its share of dD, dF, d scalars
-                    cudaMemsetAsync(s->fz_sync, 0, 256, q);                     // barrier counters
-                    s->fzw.grad = s->grad;
-                    cudaLaunchConfig_t cfg = {};
-                    cfg.gridDim = dim3((unsigned)(d.NS * FZ_CL)); cfg.blockDim = dim3(FZ_THREADS); cfg.dynamicSmemBytes = s->fzb_smem; cfg.stream = q;
-                    cudaLaunchAttribute at[1];
-                    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
-                    cfg.attrs = at; cfg.numAttrs = 1;
-                    cudaLaunchKernelEx(&cfg, k_csc_fused_bwd_xyz, s->fz, s->fzb, s->fzw, d);
-                    ++g_lk_count;
+                    // the reverse pass of all ADMM_XYZ passes and of the warm-up as ONE persistent kernel: reads the adjoints left for the final
+                    // z, y, x and adds its share of dD, dF, d scalars to gsum
+                    launch_fused(s, 2, q);
                     if (!s->fused_bwd_df) {              // A/B mode with the DF reverse pass on the tape: add the group sums to the tape's adjoints
                         const int nF = d.h * d.M2 * d.K, nD = d.f_len * d.M, nsc = 3 * d.npx + d.npx + 3 * d.npd + 3;
                         lk(k_csc_fused_finish, nblk(nF + nD + 64, 256), 256, 0, q, (const float*)s->fzw.gsum, d.G, nF, nD, nsc,
                            s->grad + s->Feff.off, s->grad + s->Deff.off, s->grad + s->sc.off);
                     }
+                    if (!fused_all) cudaMemsetAsync(s->fz_sync, 0, 256, q);
                 }
                 continue;
             }
             if (s->fused_bwd && i >= 1 && i < s->op_xyz_begin) continue;       // the reverse pass of the warm-up is the tail of k_csc_fused_bwd_xyz
-            if (s->fused_bwd && s->fused_bwd_df && i == 0) {
-                // group sums of both reverse kernels -> adjoint of prep_params -> raw gradient vector, one kernel
+            if (fused_all && i == 0) {
+                // group sums of both reverse kernels -> adjoint of prep_params -> raw gradient vector; also clears the sync area
                 ScalarSegs tr = s->segs; tr.nseg = 7;      // the warm-up scalars (segment 7) are not trained
-                lk(k_csc_fused_tail, d.K + 2, 256, 0, q, (const float*)s->fzw.gsum, 2 * d.G, (const float*)s->p_raw, s->off_D, s->off_F,
+                const int64_t z16 = (int64_t)(s->fz_zero_bytes / 16);
+                lk(k_csc_fused_tail, d.K + 2 + 16, 256, 0, q, (const float*)s->fzw.gsum, 2 * d.G, (const float*)s->p_raw, s->off_D, s->off_F,
                    (const float*)(s->data + s->Feff.off), (const float*)(s->data + s->Fnrm0.off), (const float*)(s->data + s->Deff.off),
-                   (const float*)(s->grad + s->Feff.off), (const float*)(s->grad + s->Deff.off), (const float*)(s->grad + s->sc.off), s->g_raw, tr, d);
+                   s->g_raw, tr, reinterpret_cast<uint4*>(s->fz_sync), z16, d);
                 continue;
             }
             run_op(s, s->tape[i], false, q);
@@ -849,6 +855,8 @@ static int fused_check(mb200_ctx* ctx, mb200_csc* s) {
     const unsigned int e = *s->fz_err_host;
     *s->fz_err_host = 0;
     cudaMemsetAsync(s->fzw.err, 0, 4, ctx->stream);
+    cudaMemsetAsync(s->grad, 0, s->arena * 4, ctx->stream);                 // the clamped lists may have left d x slots uncleared
+    cudaMemsetAsync(s->fz_sync, 0, s->fz_zero_bytes, ctx->stream);
     MB_FAIL(ctx, MB200_E_UNSUPPORTED, "csc: the fused reverse pass met a degenerate top-q support (flag %u: more than %d kept entries or more than %d codes in a sequence); "
             "create the handle with MB200_CSC_NO_FUSED for such inputs", e, FZ_KCAP, LIST_CAP);
 }

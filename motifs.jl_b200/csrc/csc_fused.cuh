@@ -29,9 +29,20 @@
 #define FZ_FLEN 32
 #define FZ_MAXPX 8
 #define FZ_MAXPD 4
-#define FZ_NHIST 3                // histogram levels a median call may use (bits 30..19, 18..7, 6..0)
+#define FZ_NHIST 4                // histogram levels a median call may use (window level, then bits 15..4, 3..0 or bits 30..19, 18..7, 6..0)
+#ifndef FZ_KLO
+#define FZ_KLO (103 << 7)         // window key = (float bits >> 16) - FZ_KLO: exponent field 103 (2^-24) .. 134 (2^8), 7 mantissa bits
+#endif
+#ifndef FZ_FORCE_GENERIC
+#define FZ_FORCE_GENERIC 0        // test builds: 1 sends every median through the plain prefix levels
+#endif
+#ifndef FZ_CNTSEL
+#define FZ_CNTSEL 512             // candidate sets up to this size are settled by counting (one candidate per thread), larger ones by radix passes
+#endif
 #define FZ_BINS 4096
+#ifndef FZ_CAND
 #define FZ_CAND 2048
+#endif
 
 struct FzPass {                   // arena offsets (floats) of one ADMM_XYZ pass
     int64_t z_in, y_in, fx_in, al_in, be_in, rec, gz, gy, z_out, y_out, med, dd, g, x_in, x_out, fx_out, al_out, be_out, bits;
@@ -214,9 +225,14 @@ __device__ float group_median(Ctx& c, const Smem& s, const FzBufs& B, int mi, in
     unsigned int* gctl = B.cctl + ((size_t)c.g * nmed + mi) * 4;
     const int nv = c.nr * FZ_M;
     unsigned int prefix = 0, pmask = 0, krank = 0, npos = 0, cnt = 0;
-    int shift = 19, nb = FZ_BINS;
-    bool first = true, resolved = false;
+    int shift = 16, nb = FZ_BINS;
+    bool first = true, resolved = false, window = true;
     FZ_S0(c);
+    // Level 0 bins the positives by WINDOW key: the top 16 bits (exponent + 7 mantissa bits) minus FZ_KLO, clamped to [0, 4095] -- 32 binades from
+    // 2^-24 at a relative bin width of 2^-7, so the median's bin holds ~1 % of the entries and its candidates settle the rest in one exchange.
+    // A median in an interior bin with few candidates (the usual case) is done after this level; an interior bin with many candidates (ties)
+    // goes on with bits 15..4 and 3..0 under the bin's 16-bit prefix; an edge bin (values outside the window) restarts with the plain prefix
+    // levels (bits 30..19, 18..7, 6..0) on the full rank.  Every decision is taken from the merged histogram: the same in every CTA.
     for (int lvl = 0; lvl < FZ_NHIST; ++lvl) {
         unsigned int* gh = ghist0 + (size_t)lvl * FZ_BINS;
         for (int i = threadIdx.x; i < nb / 4; i += FZ_THREADS) reinterpret_cast<uint4*>(lhist)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -224,7 +240,8 @@ __device__ float group_median(Ctx& c, const Smem& s, const FzBufs& B, int mi, in
         for (int e = threadIdx.x; e < 2 * nv; e += FZ_THREADS) {
             const float f = e < nv ? s.z[e] : s.y[e - nv];
             const unsigned int b = __float_as_uint(f);
-            if (f > 0.f && (b & pmask) == prefix) atomicAdd(&lhist[(b >> shift) & (unsigned)(nb - 1)], 1u);
+            if (window) { if (f > 0.f) atomicAdd(&lhist[min(max((int)(b >> 16) - FZ_KLO, 0), FZ_BINS - 1)], 1u); }
+            else if (f > 0.f && (b & pmask) == prefix) atomicAdd(&lhist[(b >> shift) & (unsigned)(nb - 1)], 1u);
         }
         __syncthreads();
         FZ_S(c, 0);
@@ -248,13 +265,23 @@ __device__ float group_median(Ctx& c, const Smem& s, const FzBufs& B, int mi, in
             krank = (npos & 1u) ? npos / 2 : npos / 2 - 1;
             first = false;
         }
-        const unsigned int bin = res[0];
-        krank -= res[1]; cnt = res[2];
-        prefix |= bin << shift; pmask |= (unsigned)(nb - 1) << shift;
+        const unsigned int bin = res[0], below = res[1], inbin = res[2];
         __syncthreads();
+        if (window) {
+            window = false;
+            if (bin >= 1u && bin <= (unsigned)(FZ_BINS - 2) && !FZ_FORCE_GENERIC) {
+                krank -= below; cnt = inbin;
+                prefix = (bin + (unsigned)FZ_KLO) << 16; pmask = 0xffff0000u; shift = 16;
+                if (cnt <= FZ_CAND) break;
+                shift = 4; nb = FZ_BINS;
+            } else { prefix = 0; pmask = 0; shift = 19; nb = FZ_BINS; cnt = npos; }      // krank stays the rank among all positives
+            continue;
+        }
+        krank -= below; cnt = inbin;
+        prefix |= bin << shift; pmask |= (unsigned)(nb - 1) << shift;
         if (cnt <= FZ_CAND) break;
         if (shift == 0) { resolved = true; break; }
-        if (shift == 19) { shift = 7; nb = FZ_BINS; } else { shift = 0; nb = 128; }
+        if (shift == 19) { shift = 7; nb = FZ_BINS; } else if (shift == 7) { shift = 0; nb = 128; } else { shift = 0; nb = 16; }
     }
     FZ_S(c, 4);
     float med = -INFINITY;
@@ -291,7 +318,27 @@ __device__ float group_median(Ctx& c, const Smem& s, const FzBufs& B, int mi, in
         __syncthreads();
         const unsigned int kin = krank;
         unsigned int v1b = prefix;
-        if (!resolved) {
+        // few candidates (the usual case with the window level: ~100): every thread ranks ONE candidate against all others (broadcast 16-byte
+        // reads); the thread that holds rank krank also knows how many entries are <= it and the next larger one
+        const bool cntsel = !resolved && cnt <= FZ_CNTSEL;
+        unsigned int cs_le = 0, cs_next = 0x7f800000u;
+        if (cntsel) {
+            for (unsigned int i = cnt + threadIdx.x; i < ((cnt + 3u) & ~3u); i += FZ_THREADS) cand[i] = __uint_as_float(0x7f800000u);      // pad: +inf ranks above everything
+            __syncthreads();
+            if (threadIdx.x < cnt) {
+                const unsigned int mine = __float_as_uint(cand[threadIdx.x]);
+                unsigned int less = 0, eq = 0, nxt = 0x7f800000u;
+                for (unsigned int j = 0; j < cnt; j += 4) {
+                    const float4 o4 = *reinterpret_cast<const float4*>(cand + j);
+                    const unsigned int o[4] = {__float_as_uint(o4.x), __float_as_uint(o4.y), __float_as_uint(o4.z), __float_as_uint(o4.w)};
+                    #pragma unroll
+                    for (int u = 0; u < 4; ++u) { less += o[u] < mine; eq += o[u] == mine; if (o[u] > mine) nxt = min(nxt, o[u]); }
+                }
+                if (less <= krank && krank < less + eq) { res[4] = mine; res[5] = less + eq; res[6] = nxt; }      // equal candidates write equal values
+            }
+            __syncthreads();
+            v1b = res[4]; cs_le = res[5]; cs_next = res[6];
+        } else if (!resolved) {
             unsigned int lowfix = 0, lowmask = 0;
             int rem = shift;
             while (rem > 0) {
@@ -317,7 +364,8 @@ __device__ float group_median(Ctx& c, const Smem& s, const FzBufs& B, int mi, in
         else {
             // second middle value: a copy of v1, else the next candidate, else the smallest entry above the bin
             unsigned int le = 0, mn2 = 0x7f800000u;
-            if (!resolved)
+            if (cntsel) { if (threadIdx.x == 0) { le = cs_le; mn2 = cs_next; } }
+            else if (!resolved)
                 for (unsigned e = threadIdx.x; e < cnt; e += FZ_THREADS) { const unsigned int b = __float_as_uint(cand[e]); if (b <= v1b) ++le; else mn2 = min(mn2, b); }
             #pragma unroll
             for (int o = 16; o > 0; o >>= 1) { le += __shfl_xor_sync(FULLMASK, le, o); mn2 = min(mn2, __shfl_xor_sync(FULLMASK, mn2, o)); }
@@ -1058,6 +1106,7 @@ struct SmemB {
     float *w;                                           // row lists of tconv
     float *dDp, *dscp;                                  // partial dD [32][50], partial scalar gradients [64]
     int *kl; float *kv;                                 // kept entries (flat index) and their values
+    int *klp;                                           // kept entries of the pass handled before (whose d x values this pass consumes and clears)
     int *li2; float *lv2;                               // code list of x+ (from the tape)
     float* red; int* iscr; uint8_t* b;
 };
@@ -1070,7 +1119,7 @@ __host__ __device__ inline size_t fzb_smem_bytes(int Lb) {
     f += (size_t)8 * (R + 8);
     f += 32 + 64 * LIST_CAP;                              // row lists
     f += FZ_FLEN * FZ_M + 64;
-    f += 2 * FZ_KCAP + 2 * LIST_CAP + 64;
+    f += 3 * FZ_KCAP + 2 * LIST_CAP + 64;
     return f * 4 + (size_t)(R + 16) + 64;
 }
 __device__ __forceinline__ void carve_b(SmemB& s, float* base, int R, int Lb) {
@@ -1086,7 +1135,7 @@ __device__ __forceinline__ void carve_b(SmemB& s, float* base, int R, int Lb) {
     s.sig = p; p += 4 * (R + 8); s.sig2 = p; p += 4 * (R + 8);
     s.w = p; p += 32 + 64 * LIST_CAP;
     s.dDp = p; p += FZ_FLEN * FZ_M; s.dscp = p; p += 64;
-    s.kl = reinterpret_cast<int*>(p); p += FZ_KCAP; s.kv = p; p += FZ_KCAP;
+    s.kl = reinterpret_cast<int*>(p); p += FZ_KCAP; s.kv = p; p += FZ_KCAP; s.klp = reinterpret_cast<int*>(p); p += FZ_KCAP;
     s.li2 = reinterpret_cast<int*>(p); p += LIST_CAP; s.lv2 = p; p += LIST_CAP;
     s.red = p; p += 32; s.iscr = reinterpret_cast<int*>(p); p += 32;
     s.b = reinterpret_cast<uint8_t*>(p);
@@ -1183,11 +1232,13 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
     __syncthreads();
 
     FZ_T(0);
+    int cnt_prev = 0;
     for (int n = P.npx - 1; n >= 0; --n) {
         const FzPass& X = P.px[n];
         const float eta = sc[X.i_eta], lam = sc[X.i_lam], rho = sc[X.i_rho], om = sc[X.i_om];
         // kept entries of x+ (the top-q bitmap of this pass), ordered by flat index; redundantly in every CTA of the cluster
         int cnt;
+        if (n != P.npx - 1) { if ((int)threadIdx.x < cnt_prev) s.klp[threadIdx.x] = s.kl[threadIdx.x]; __syncthreads(); }
         {
             const uint32_t* bw = reinterpret_cast<const uint32_t*>(B.bits + X.bits + (size_t)c.n * nX);      // 4 flags per word (E is a multiple of 4)
             const int nw = E >> 2;
@@ -1205,6 +1256,9 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
             if (total > FZ_KCAP) { if (threadIdx.x == 0) atomicOr(W.err, 1u); total = FZ_KCAP; }
             cnt = total;
         }
+        // the d x+ values this pass is about to read were written on the support of the pass handled before it (for the last pass: by the
+        // DF reverse kernel, on this pass's own support); they are cleared after the reads, so the adjoint arena never needs a memset
+        if (n == P.npx - 1) { __syncthreads(); if ((int)threadIdx.x < cnt) s.klp[threadIdx.x] = s.kl[threadIdx.x]; cnt_prev = cnt; }
         FZ_T(1);
         // (i') duals: alpha+ = alpha + fx+_l - z+, beta+ likewise (model.jl:265-266); not computed by the last pass
         if (X.al_out >= 0)
@@ -1244,6 +1298,8 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
         fgrad_targets(c, grad + SEQ(X.fx_out, nZY), s.li2, s.lv2, cnt2, dFp);
         FZ_T(5);
         cluster_barrier();                                        // #2: the sparse d x+ values are published
+        if (c.r == 1 % FZ_CL && (int)threadIdx.x < cnt_prev) grad[SEQ(X.x_out, nX) + s.klp[threadIdx.x]] = 0.f;      // consumed by every CTA before the barrier
+        cnt_prev = cnt;
         FZ_T(6);
         // (g') top-q adjoint (model.jl:190-192, 252-253): gr = d x+ on the kept support; d x = gr, d g = -omega gr, d omega = -sum gr g
         {
@@ -1365,6 +1421,8 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
     //      (z0, y0) = relu(eta_w corr(S, D) - lam_w eta_w); the warm-up scalars are not trained ------------------------------------------------
     {
         int cnt;
+        if ((int)threadIdx.x < cnt_prev) s.klp[threadIdx.x] = s.kl[threadIdx.x];
+        __syncthreads();
         {   // kept entries of x0
             const uint32_t* bw = reinterpret_cast<const uint32_t*>(B.bits + P.bits0 + (size_t)c.n * nX);
             const int nw = E >> 2;
@@ -1406,6 +1464,7 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
         }
         fgrad_targets(c, dfx_g, s.li2, s.lv2, cnt2, dFp);          // d F += fgrad(d fx0, x0)
         cluster_barrier();                                        // the sparse d x0 values are published
+        if (c.r == 1 % FZ_CL && (int)threadIdx.x < cnt_prev) grad[SEQ(P.x0, nX) + s.klp[threadIdx.x]] = 0.f;           // what pass 0 left there is consumed
         {
             const float om_w = sc[P.i_om_w];
             const float* xch = W.xch + (size_t)c.n * FZ_KCAP;
@@ -1896,14 +1955,14 @@ __global__ void __launch_bounds__(256) k_csc_fused_finish(const float* __restric
     else if (o - nF - nD < nsc) gsc[o - nF - nD] += acc;
 }
 
-// Last kernel of the fully fused reverse pass: group sums of the two reverse kernels (gsum: [G2][nF + nD + 64]) + whatever already sits in the
-// adjoints of the prepared parameters, pushed through the adjoint of prep_params (model.jl:139-169: F = r^2 / ||r^2||_2 per syntax filter,
-// D = (r^2 + 1e-3) normalised over the four nucleotides, scalars squared) into the raw gradient vector.  Blocks 0..K-1: one syntax filter each;
-// block K: D; block K+1: the trained scalars.  Replaces k_csc_fused_finish + the three prep adjoint kernels of the tape.
+// Last kernel of the fully fused reverse pass: group sums of the two reverse kernels (gsum: [G2][nF + nD + 64]) pushed through the adjoint of
+// prep_params (model.jl:139-169: F = r^2 / ||r^2||_2 per syntax filter, D = (r^2 + 1e-3) normalised over the four nucleotides, scalars
+// squared) into the raw gradient vector (assigned: the step has no other contributor).  Blocks 0..K-1: one syntax filter each; block K: D;
+// block K+1: the trained scalars; the remaining blocks clear the sync area (barrier counters, median histograms) for the next step.
+// Replaces k_csc_fused_finish, the three prep adjoint kernels of the tape and four memset nodes.
 __global__ void __launch_bounds__(256) k_csc_fused_tail(const float* __restrict__ gsum, int G2, const float* __restrict__ raw, int64_t off_D, int64_t off_F,
                                                         const float* __restrict__ Feff, const float* __restrict__ Fnrm, const float* __restrict__ Deff,
-                                                        const float* __restrict__ gFe, const float* __restrict__ gDe, const float* __restrict__ gsc,
-                                                        float* __restrict__ draw, ScalarSegs sg, CscDims d) {
+                                                        float* __restrict__ draw, ScalarSegs sg, uint4* __restrict__ zero_area, int64_t zero_n16, CscDims d) {
     __shared__ float s_de[FZ_H * FZ_M2];
     __shared__ float s_dot;
     const int nF = d.h * d.M2 * d.K, nD = d.f_len * d.M, tot = nF + nD + 64, HJ = d.h * d.M2;
@@ -1913,7 +1972,7 @@ __global__ void __launch_bounds__(256) k_csc_fused_tail(const float* __restrict_
         for (int e = threadIdx.x; e < HJ; e += blockDim.x) {           // e = j*h + a in raw order
             const int a = e % d.h, j = e / d.h;
             const int64_t o = ((int64_t)a * d.M2 + j) * d.K + k;
-            float de = gFe[o];
+            float de = 0.f;
             for (int g = 0; g < G2; ++g) de += gsum[(size_t)g * tot + o];
             s_de[e] = de; dot += de * Feff[o];
         }
@@ -1926,7 +1985,7 @@ __global__ void __launch_bounds__(256) k_csc_fused_tail(const float* __restrict_
             const int a = e % d.h, j = e / d.h;
             const int64_t o = ((int64_t)a * d.M2 + j) * d.K + k;
             const float r = raw[off_F + (int64_t)k * HJ + e];
-            draw[off_F + (int64_t)k * HJ + e] += (s_de[e] - dot * Feff[o]) / nn * 2.f * r;
+            draw[off_F + (int64_t)k * HJ + e] = (s_de[e] - dot * Feff[o]) / nn * 2.f * r;
         }
     } else if ((int)blockIdx.x == d.K) {
         for (int t = threadIdx.x; t < d.fl * d.M; t += blockDim.x) {
@@ -1937,25 +1996,68 @@ __global__ void __launch_bounds__(256) k_csc_fused_tail(const float* __restrict_
                 const int o = (4 * j + a) * d.M + m;
                 const float r = raw[off_D + m * d.f_len + 4 * j + a];
                 ssum += r * r + 0.001f;
-                float v = gDe[o];
+                float v = 0.f;
                 for (int g = 0; g < G2; ++g) v += gsum[(size_t)g * tot + nF + o];
                 de[a] = v; dot += v * Deff[o];
             }
             #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 const float r = raw[off_D + m * d.f_len + 4 * j + a];
-                draw[off_D + m * d.f_len + 4 * j + a] += (de[a] - dot) / ssum * 2.f * r;
+                draw[off_D + m * d.f_len + 4 * j + a] = (de[a] - dot) / ssum * 2.f * r;
             }
         }
-    } else {
+    } else if ((int)blockIdx.x == d.K + 1) {
         const int w = threadIdx.x >> 5;
         if (w < sg.nseg)
             for (int i = threadIdx.x & 31; i < sg.n[w]; i += 32) {
                 const int idx = sg.eff_idx[w] + i;
-                float de = gsc[idx];
+                float de = 0.f;
                 for (int g = 0; g < G2; ++g) de += gsum[(size_t)g * tot + nF + nD + idx];
-                draw[sg.raw_off[w] + i] += 2.f * raw[sg.raw_off[w] + i] * de;
+                draw[sg.raw_off[w] + i] = 2.f * raw[sg.raw_off[w] + i] * de;
             }
+    } else {
+        const int64_t nb = (int64_t)gridDim.x - (d.K + 2);
+        for (int64_t i = ((int64_t)blockIdx.x - (d.K + 2)) * blockDim.x + threadIdx.x; i < zero_n16; i += nb * blockDim.x) zero_area[i] = make_uint4(0u, 0u, 0u, 0u);
     }
 }
 
+// First kernel of the fused step: prep_params (model.jl:139-169) of the three parameter families and the 2-bit -> byte unpacking of the batch's
+// bases in one launch (blocks 0..K-1: syntax filters; K: D; K+1: scalars; the rest: bases).  Replaces four kernels of the tape.
+__global__ void __launch_bounds__(256) k_csc_fused_head(const float* __restrict__ raw, int64_t off_D, int64_t off_F, float* __restrict__ Feff, float* __restrict__ Fnrm,
+                                                        float* __restrict__ Deff, float* __restrict__ sceff, ScalarSegs sg,
+                                                        const uint32_t* __restrict__ words, int64_t rowwords, const int64_t* __restrict__ idx, uint8_t* __restrict__ bases, CscDims d) {
+    __shared__ float s_n;
+    const int HJ = d.h * d.M2;
+    if ((int)blockIdx.x < d.K) {
+        const int k = blockIdx.x;
+        float ss = 0.f;
+        for (int e = threadIdx.x; e < HJ; e += blockDim.x) { const float r = raw[off_F + (int64_t)k * HJ + e]; const float u = r * r; ss += u * u; }
+        ss = block_sum(ss);
+        if (threadIdx.x == 0) { s_n = sqrtf(ss); Fnrm[k] = s_n; }
+        __syncthreads();
+        for (int e = threadIdx.x; e < HJ; e += blockDim.x) {
+            const int a = e % d.h, j = e / d.h;
+            const float r = raw[off_F + (int64_t)k * HJ + e];
+            Feff[((int64_t)a * d.M2 + j) * d.K + k] = r * r / s_n;
+        }
+    } else if ((int)blockIdx.x == d.K) {
+        for (int t = threadIdx.x; t < d.fl * d.M; t += blockDim.x) {
+            const int m = t % d.M, j = t / d.M;
+            float u[4], ssum = 0.f;
+            #pragma unroll
+            for (int a = 0; a < 4; ++a) { const float r = raw[off_D + m * d.f_len + 4 * j + a]; u[a] = r * r + 0.001f; ssum += u[a]; }
+            #pragma unroll
+            for (int a = 0; a < 4; ++a) Deff[(4 * j + a) * d.M + m] = u[a] / ssum;
+        }
+    } else if ((int)blockIdx.x == d.K + 1) {
+        const int w = threadIdx.x >> 5;
+        if (w < sg.nseg)
+            for (int i = threadIdx.x & 31; i < sg.n[w]; i += 32) { const float r = raw[sg.raw_off[w] + i]; sceff[sg.eff_idx[w] + i] = r * r; }
+    } else {
+        const int64_t nb = (int64_t)gridDim.x - (d.K + 2), tot = (int64_t)d.NS * d.Lb;
+        for (int64_t t = ((int64_t)blockIdx.x - (d.K + 2)) * blockDim.x + threadIdx.x; t < tot; t += nb * blockDim.x) {
+            const int64_t n = t / d.Lb; const int p = (int)(t - n * d.Lb);
+            bases[t] = (uint8_t)((words[idx[n] * rowwords + (p >> 4)] >> (2 * (p & 15))) & 3u);
+        }
+    }
+}
