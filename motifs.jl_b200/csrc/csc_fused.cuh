@@ -284,6 +284,9 @@ __device__ float group_median(Ctx& c, const Smem& s, const FzBufs& B, int mi, in
         if (shift == 19) { shift = 7; nb = FZ_BINS; } else if (shift == 7) { shift = 0; nb = 128; } else { shift = 0; nb = 16; }
     }
     FZ_S(c, 4);
+#ifdef FZ_PROFILE
+    if (blockIdx.x == 0 && threadIdx.x == 0) printf("[fzm] median %d: %u positives, %u candidates, %d low bits open\n", mi, npos, cnt, shift);
+#endif
     float med = -INFINITY;
     if (npos > 0) {                                                        // group-uniform
         // publish this CTA's entries of the median's bin, and the smallest entry above the bin

@@ -1,6 +1,7 @@
 """Parity of the CUDA CSC network (through the C ABI) against the PyTorch-CPU oracle (oracle/csc_oracle.py).
-Tolerances (fp32 vs fp32, different summation orders): loss 1e-5 relative (north_star); gradients 2e-4 of the
-largest gradient entry; discrete results (top-q support of X) identical."""
+Tolerances (fp32 vs fp32, different summation orders): loss 1e-5 relative (north_star); gradients 2e-5 of the
+largest gradient entry and 1e-4 of each parameter block's largest entry (measured: <= 1e-6); discrete results
+(top-q support of X) identical."""
 import numpy as np
 import pytest
 
@@ -43,12 +44,12 @@ def test_loss_and_grad_match_oracle(ctx, Lb, seed):
     F = m.get_buffer("F", hp.h * hp.twoM * hp.K).reshape(hp.h, hp.twoM, hp.K)
     assert np.allclose(F, aux["F"].detach().numpy(), rtol=1e-4, atol=1e-7)
     scale = np.abs(og).max()
-    assert np.abs(g - og[: m.n_trainable]).max() <= 2e-4 * scale
+    assert np.abs(g - og[: m.n_trainable]).max() <= 2e-5 * scale
     # per-block relative error, so small blocks (scalars) are held to the same bar as F
     o = 0
     for name, n in co.param_sizes(ohp).items():
         blk, oblk = g[o:o + n], og[o:o + n]
-        assert np.abs(blk - oblk).max() <= 1e-3 * max(np.abs(oblk).max(), 1e-6), name
+        assert np.abs(blk - oblk).max() <= 1e-4 * max(np.abs(oblk).max(), 1e-6), name
         o += n
     m.free(); seqs.free()
 
@@ -357,3 +358,46 @@ def test_fused_forward_kernel_matches_the_tape(ctx, Lb, groups):
     lf2, gf2 = mf.loss_grad(seqs, idx)
     assert np.array_equal(lf, lf2)
     mf.free(); mt.free(); seqs.free()
+
+
+@pytest.mark.parametrize("Lb", [100, 200, 64])
+def test_fused_reverse_kernels_match_the_tape(ctx, Lb):
+    """The three step variants of one handle shape -- fully fused (7 kernels), fused forward + XYZ reverse with the loss / ADMM_DF reverse pass
+    on the tape (MB200_CSC_NO_FUSED_DF), and the kernel-per-op tape (MB200_CSC_NO_FUSED) -- give the same loss and, per parameter block,
+    gradients within 5e-6 of the block's largest entry (fp32 summation order is all that differs)."""
+    hp, ohp, a, seqs, flat = _setup(ctx, 40, Lb, 9)
+    idx = np.random.default_rng(3).permutation(40)[:6]
+    out = {}
+    for name, kw in (("fused", {}), ("tape_df", {"fused_df": False}), ("tape", {"fused": False})):
+        m = mb._lib.CscModel(ctx, hp, Lb, **kw)
+        m.set_params(flat)
+        out[name] = m.loss_grad(seqs, idx)
+        m.free()
+    for name in ("tape_df", "tape"):
+        assert out["fused"][0][0, 0] == pytest.approx(out[name][0][0, 0], rel=2e-6)
+        o = 0
+        for blk, n in co.param_sizes(ohp).items():
+            ref, new = out[name][1][o:o + n], out["fused"][1][o:o + n]
+            assert np.abs(new - ref).max() <= 5e-6 * max(np.abs(ref).max(), 1e-9), (name, blk)
+            o += n
+    seqs.free()
+
+
+def test_fused_step_leaves_its_scratch_clean(ctx):
+    """The fully fused step never clears its adjoint arena or sync area with memsets: the d x slots are cleared by their reader and the sync
+    area by the last kernel.  Gradients of the same batch must therefore be bit-identical whatever ran on the handle before (other batches,
+    optimiser steps with the parameters restored afterwards)."""
+    hp, ohp, a, seqs, flat = _setup(ctx, 60, 100, 4)
+    rng = np.random.default_rng(5)
+    m = mb._lib.CscModel(ctx, hp, 100)
+    m.set_params(flat)
+    idx = rng.permutation(60)[:6]
+    l0, g0 = m.loss_grad(seqs, idx)
+    for _ in range(5):
+        m.loss_grad(seqs, rng.permutation(60)[:6])
+    for _ in range(3):
+        m.step_begin(seqs, rng.permutation(60)[:6]); m.adabelief_step()
+    m.set_params(flat)
+    l1, g1 = m.loss_grad(seqs, idx)
+    assert np.array_equal(l0, l1) and np.array_equal(g0, g1)
+    m.free(); seqs.free()
