@@ -202,7 +202,9 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         else lk(k_corr_sig, nblk(nZ, 256), 256, 0, q, sig, S->bases, sgn, filt, gs, oa, ob, acc, d);
     };
     auto run_dgrad = [=](const float* ca, const float* cb, const float* sig, float sgn, float* of, int64_t ogs, int acc, cudaStream_t q) {
-        if (fastM) lk(k_dgrad_c, dim3(d.f_len * CL, d.G), 256, 0, q, ca, cb, sig, S->bases, sgn, of, ogs, acc, d);
+        // many groups: one CTA per group with a 4-lag x 2-filter register tile (the per-lag kernels re-read the codes 32 times)
+        if (batched && fastM && d.f_len == 32 && (d.M & 1) == 0 && (size_t)d.L4 * 4 <= S->ctx->smem_optin) lk(k_dgrad_g, dim3(d.G, DG_SLICES), DG_THREADS, (size_t)d.L4 * 4, q, ca, cb, sig, S->bases, sgn, of, ogs, acc, d);
+        else if (fastM) lk(k_dgrad_c, dim3(d.f_len * CL, d.G), 256, 0, q, ca, cb, sig, S->bases, sgn, of, ogs, acc, d);
         else lk(k_dgrad, dim3(nblk(nD, 128), d.G), 128, 0, q, ca, cb, sig, S->bases, sgn, of, ogs, acc, d);
     };
     auto run_tconv = [=](const float* x, int L, const float* filt, int64_t gs, float* out, int acc, cudaStream_t q) {
@@ -224,6 +226,11 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         cudaEventRecord(S->ev_join, S->aux); cudaStreamWaitEvent(q, S->ev_join, 0);
     };
     std::map<size_t, int> xlist;                 // buffer offset of an x tensor -> list of its data
+    std::map<size_t, size_t> xbits;              // buffer offset of an x tensor -> offset of the top-q bitmap that produced it
+    // the adjoint of a top-q output is only read on the kept support (k_topq_s_bwd masks it): ~32 dot products per sequence instead of the dense contraction
+    auto run_corr2d_kept = [=](const float* A, const float* filt, int64_t gs, size_t bo, float* out, int acc, cudaStream_t q) {
+        lk(k_corr2d_kept, d.NS, CK_THREADS, (size_t)d.l * d.K * 4, q, A, filt, gs, (const uint8_t*)(S->bits + bo), out, acc, d);
+    };
     auto op_recon = [&](Buf ca, Buf cb, Buf filt, int64_t gs, Buf out, const char* nm) {
         T.push_back({[=](cudaStream_t q) { run_recon(S->data + ca.off, S->data + cb.off, S->data + filt.off, gs, S->data + out.off, 0, q); },
                      [=](cudaStream_t q) {
@@ -261,19 +268,21 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
     };
     auto op_tconv = [&](Buf x, Buf filt, int64_t gs, Buf out, const char* nm) {
         const int xl = xlist.at(x.off);
+        const size_t xb = xbits.at(x.off);
         T.push_back({[=](cudaStream_t q) { run_tconv(S->data + x.off, xl, S->data + filt.off, gs, S->data + out.off, 0, q); },
                      [=](cudaStream_t q) {
-                         par2(q, [=](cudaStream_t r) { run_corr2d(S->grad + out.off, S->data + filt.off, gs, S->grad + x.off, 1, r); },
+                         par2(q, [=](cudaStream_t r) { run_corr2d_kept(S->grad + out.off, S->data + filt.off, gs, xb, S->grad + x.off, 1, r); },
                                  [=](cudaStream_t r) { run_fgrad(S->grad + out.off, S->data + x.off, xl, S->grad + filt.off, gs, 1, r); });
                      },
                      nm});
     };
     auto op_fgrad = [&](Buf A, Buf x, Buf outF, const char* nm) {                               // per-group output
         const int xl = xlist.at(x.off);
+        const size_t xb = xbits.at(x.off);
         T.push_back({[=](cudaStream_t q) { run_fgrad(S->data + A.off, S->data + x.off, xl, S->data + outF.off, nF, 0, q); },
                      [=](cudaStream_t q) {
                          par2(q, [=](cudaStream_t r) { run_tconv(S->data + x.off, xl, S->grad + outF.off, nF, S->grad + A.off, 1, r); },
-                                 [=](cudaStream_t r) { run_corr2d(S->data + A.off, S->grad + outF.off, nF, S->grad + x.off, 1, r); });
+                                 [=](cudaStream_t r) { run_corr2d_kept(S->data + A.off, S->grad + outF.off, nF, xb, S->grad + x.off, 1, r); });
                      },
                      nm});
     };
@@ -300,7 +309,7 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         const size_t bo = B.bit_cursor; B.bit_cursor += (size_t)nX;
         const int xl = B.n_lists++;
         last_bo = bo; last_xl = xl;
-        xlist[xout.off] = xl;
+        xlist[xout.off] = xl; xbits[xout.off] = bo;
         const bool hp_ = xprev != nullptr; const Buf xp = hp_ ? *xprev : Buf{};
         const size_t smem = (size_t)d.l * d.K * 4;
         T.push_back({[=](cudaStream_t q) { lk(k_topq_s, d.NS, 256, smem, q, hp_ ? S->data + xp.off : nullptr, S->data + g.off, SCP, i_om, coef, S->data + xout.off, S->bits + bo, LCNT(xl), LIDX(xl), LVAL(xl), d); },
@@ -311,7 +320,10 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
     // ---- warm-up (model.jl:224-232) --------------------------------------------------------------
     Buf z = B.alloc(nZ), y = B.alloc(nZ);
     T.push_back({[=](cudaStream_t q) { lk(k_warm_zy, nblk(nZ, 256), 256, 0, q, S->bases, S->data + De.off, SCP, S->i_eta_w, S->i_lam_w, S->data + z.off, S->data + y.off, d); },
-                 [=](cudaStream_t q) { lk(k_warm_zy_bwd, nblk(nZ, 256), 256, 0, q, S->bases, SCP, S->i_eta_w, S->data + z.off, S->data + y.off, S->grad + z.off, S->grad + y.off, S->grad + De.off, d); },
+                 [=](cudaStream_t q) {
+                     if (batched && d.fl * d.M <= 512 && d.M <= 64) lk(k_warm_zy_bwd_s, d.NS, 512, 0, q, S->bases, SCP, S->i_eta_w, S->data + z.off, S->data + y.off, S->grad + z.off, S->grad + y.off, S->grad + De.off, d);
+                     else lk(k_warm_zy_bwd, nblk(nZ, 256), 256, 0, q, S->bases, SCP, S->i_eta_w, S->data + z.off, S->data + y.off, S->grad + z.off, S->grad + y.off, S->grad + De.off, d);
+                 },
                  "warm_zy"});
     Buf zy = B.alloc(nZY);
     FzPlan& FP = s->fz;
@@ -477,6 +489,8 @@ static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
     if (s->mask_cap <= MS_MAXV * 512) MB_CUDA(ctx, cudaFuncSetAttribute(k_mask_scale_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (s->mask_cap + 2 * MS_BINS + MS_CAND) * 4));
     MB_CUDA(ctx, cudaFuncSetAttribute(k_mask_scale_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<int64_t>(2 * (int64_t)s->d.B * s->d.c * s->d.M, 49152) * 4));
     MB_CUDA(ctx, cudaFuncSetAttribute(k_topq_s, cudaFuncAttributeMaxDynamicSharedMemorySize, s->d.l * s->d.K * 4));
+    MB_CUDA(ctx, cudaFuncSetAttribute(k_corr2d_kept, cudaFuncAttributeMaxDynamicSharedMemorySize, s->d.l * s->d.K * 4));
+    if ((size_t)s->d.L4 * 4 <= ctx->smem_optin) MB_CUDA(ctx, cudaFuncSetAttribute(k_dgrad_g, cudaFuncAttributeMaxDynamicSharedMemorySize, s->d.L4 * 4));
     if (s->tensor) {
         const int64_t rows = (int64_t)s->d.NS * s->d.c;
         // the tap-grouped kernel k_corr2d_tc3<K = 24, h/4 = 3> (tc_corr2d.cuh) is the one instantiated shape

@@ -418,3 +418,154 @@ static inline size_t corr2d_b_smem(const CscDims& d, int KK) {
     const size_t rows_pad = (size_t)(((d.l + 3) >> 2) * 4 + d.h - 1);
     return (((rows_pad * (d.M2 + 1) + 3) & ~(size_t)3) + 2 * (size_t)d.M2 * KK) * 4;
 }
+
+// T3 "dgrad" for many-group launches: of[g][tau][m] (+)= sum_{n in g} sum_p ca[n,p,m] r[n,4p+tau] + cb[n,p,m] r[n,4p+31-tau]
+// (model.jl:270-290), one 4-CTA CLUSTER per group.  The per-tau kernels (k_dgrad_c / k_dgrad_b) re-read the codes once per lag: 32 x 30 MB of
+// traffic per launch at 64 groups x 200 bp (441 us).  Here a thread owns a tile of 4 lags x 2 filters, the sequence's signal (with the one-hot
+// input folded in) is staged in shared memory and the codes are read 8 times (once per lag group, through L1) instead of 32.  CTA s of the
+// cluster takes rows [s c/4, (s+1) c/4) of every sequence, its two thread halves alternate halves of those; the partial tiles are added in a
+// fixed order (halves, then cluster ranks through distributed shared memory).  f_len = 32, M even and <= 64.
+#define DG_THREADS 512
+#define DG_SLICES 4
+__global__ void __cluster_dims__(1, DG_SLICES, 1) __launch_bounds__(DG_THREADS) k_dgrad_g(const float* __restrict__ ca, const float* __restrict__ cb,
+                                                         const float* __restrict__ sig, const uint8_t* __restrict__ bases, float sgn,
+                                                         float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) { PDL_SYNC();
+    extern __shared__ __align__(16) float dg_r[];                  // [L4] signal of the current sequence
+    __shared__ float s_red[32 * 64];                               // the upper half's tile sums, then this CTA's tile sums
+    cg::cluster_group cluster = cg::this_cluster();
+    const int g = blockIdx.x, sl = blockIdx.y;
+    const int half = threadIdx.x >> 8, t = threadIdx.x & 255;
+    const int mpairs = d.M >> 1;
+    const bool active = t < 8 * mpairs;
+    const int tg = active ? t / mpairs : 0, mp = active ? t - tg * mpairs : 0;
+    const int per = (d.c + DG_SLICES - 1) / DG_SLICES;
+    const int s_lo = min(d.c, sl * per), s_hi = min(d.c, s_lo + per), p_mid = (s_lo + s_hi + 1) >> 1;
+    const int p_lo = half ? p_mid : s_lo, p_hi = half ? s_hi : p_mid;
+    float acc[4][2];
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.f;
+    for (int nl = 0; nl < d.B; ++nl) {
+        const int64_t n = (int64_t)g * d.B + nl;
+        __syncthreads();
+        for (int q = 4 * s_lo + threadIdx.x; q < min(d.L4, 4 * s_hi + 32); q += DG_THREADS) dg_r[q] = sig_at(sig, bases, sgn, n, q, d);
+        __syncthreads();
+        if (active) {
+            const float* za = ca + (n * d.c) * d.M + 2 * mp;
+            const float* yb = cb + (n * d.c) * d.M + 2 * mp;
+            for (int p0 = p_lo; p0 < p_hi; p0 += 8) {               // eight rows of codes in flight per thread
+                float2 z2[8], y2[8];
+                #pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int p = min(p0 + u, p_hi - 1);
+                    z2[u] = *reinterpret_cast<const float2*>(za + (int64_t)p * d.M); y2[u] = *reinterpret_cast<const float2*>(yb + (int64_t)p * d.M);
+                }
+                #pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int p = p0 + u;
+                    if (p < p_hi) {
+                        const float4 rf = *reinterpret_cast<const float4*>(dg_r + 4 * p + 4 * tg), rr = *reinterpret_cast<const float4*>(dg_r + 4 * p + 28 - 4 * tg);
+                        const float f[4] = {rf.x, rf.y, rf.z, rf.w}, rv[4] = {rr.w, rr.z, rr.y, rr.x};
+                        #pragma unroll
+                        for (int i = 0; i < 4; ++i) { acc[i][0] += z2[u].x * f[i] + y2[u].x * rv[i]; acc[i][1] += z2[u].y * f[i] + y2[u].y * rv[i]; }
+                    }
+                }
+            }
+        }
+    }
+    if (active && half) {
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) { s_red[(4 * tg + i) * 64 + 2 * mp] = acc[i][0]; s_red[(4 * tg + i) * 64 + 2 * mp + 1] = acc[i][1]; }
+    }
+    __syncthreads();
+    if (active && !half) {
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) { s_red[(4 * tg + i) * 64 + 2 * mp] += acc[i][0]; s_red[(4 * tg + i) * 64 + 2 * mp + 1] += acc[i][1]; }
+    }
+    cluster.sync();                                               // every CTA's tile sums are in its s_red
+    if (sl == 0 && active && !half) {
+        #pragma unroll
+        for (int i = 0; i < 4; ++i)
+            #pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int tau = 4 * tg + i, m = 2 * mp + u;
+                float v = 0.f;
+                #pragma unroll
+                for (int r = 0; r < DG_SLICES; ++r) v += cluster.map_shared_rank(s_red, r)[tau * 64 + m];
+                float* o = of + (int64_t)g * out_gs + tau * d.M + m;
+                if (out_gs == 0 && d.G > 1) atomicAdd(o, v);
+                else if (accumulate) *o += v; else *o = v;
+            }
+    }
+    cluster.sync();                                               // remote reads of s_red are done
+}
+
+// U2 "corr2d" restricted to the entries a top-q kept: out[n,i,k] (+)= sum_{a<h} sum_{j<2M} A[n,i+a,j] F[a][j][k] for (i,k) with bits[n][i*K+k] != 0.
+// Every corr2d of the reverse pass produces the adjoint of a top-q OUTPUT, and the top-q adjoint (model.jl:190) discards it outside the kept
+// support: ~32 dot products of h*2M terms per sequence instead of l*K (x 136 less work at Lb = 200).  One CTA per sequence, one warp per entry.
+#define CK_THREADS 256
+__global__ void __launch_bounds__(CK_THREADS) k_corr2d_kept(const float* __restrict__ A, const float* __restrict__ filt, int64_t filt_gs, const uint8_t* __restrict__ bits,
+                                                            float* __restrict__ out, int accumulate, CscDims d) { PDL_SYNC();
+    extern __shared__ int ck_list[];                               // [l*K] kept entries (any order: every entry is written by exactly one warp)
+    __shared__ int s_cnt;
+    const int64_t n = blockIdx.x;
+    const int E = d.l * d.K, HJ = d.h * d.M2;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const uint8_t* b = bits + n * E;
+    for (int e = threadIdx.x; e < E; e += CK_THREADS) if (b[e]) ck_list[atomicAdd(&s_cnt, 1)] = e;
+    __syncthreads();
+    const int cnt = s_cnt, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* F = filt + (n / d.B) * filt_gs;
+    for (int q = warp; q < cnt; q += CK_THREADS / 32) {
+        const int e = ck_list[q], i = e / d.K, k = e - i * d.K;
+        const float* rows = A + (n * d.c + i) * d.M2;              // rows i .. i+h-1 are contiguous
+        float acc = 0.f;
+        #pragma unroll 4
+        for (int t = lane; t < HJ; t += 32) acc += rows[t] * F[(int64_t)t * d.K + k];
+        acc = warp_sum(acc);
+        if (lane == 0) { float* o = out + n * E + e; if (accumulate) *o += acc; else *o = acc; }
+    }
+}
+
+
+// adjoint of the warm-up wrt D (k_warm_zy_bwd) for many-group launches: one CTA per sequence.  Chunks of 32 positions: all threads load
+// z, y, dz, dy of the chunk (every element once, all loads in flight) and leave gz, gy in shared memory; then one thread per (filter position j,
+// filter m) adds its four nucleotide rows over the chunk in registers (fixed order).  ONE atomic per (sequence, entry) at the end -- the
+// per-element kernel issues 16 float atomics per code entry onto 1600 addresses (0.5 ms at 64 groups x 200 bp).
+#define WZ_ROWS 32
+__global__ void __launch_bounds__(512) k_warm_zy_bwd_s(const uint8_t* __restrict__ bases, const float* __restrict__ sc, int i_eta,
+                                                        const float* __restrict__ z, const float* __restrict__ y,
+                                                        const float* __restrict__ dz, const float* __restrict__ dy, float* __restrict__ dD, CscDims d) { PDL_SYNC();
+    __shared__ float s_gz[WZ_ROWS * 64], s_gy[WZ_ROWS * 64];
+    const int64_t n = blockIdx.x;
+    const int t = threadIdx.x;
+    const bool active = t < d.fl * d.M;
+    const int j = active ? t / d.M : 0, m = active ? t - j * d.M : 0;
+    const float eta = sc[i_eta];
+    const uint8_t* s = bases + n * d.Lb;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int p0 = 0; p0 < d.c; p0 += WZ_ROWS) {
+        const int rows = min(WZ_ROWS, d.c - p0);
+        __syncthreads();
+        for (int e = t; e < rows * d.M; e += 512) {
+            const int64_t o = (n * d.c + p0) * d.M + e;
+            const int pl = e / d.M, mm = e - pl * d.M;
+            s_gz[pl * 64 + mm] = z[o] > 0.f ? eta * dz[o] : 0.f;
+            s_gy[pl * 64 + mm] = y[o] > 0.f ? eta * dy[o] : 0.f;
+        }
+        __syncthreads();
+        if (active)
+            for (int pl = 0; pl < rows; ++pl) {
+                const int p = p0 + pl;
+                const float gz = s_gz[pl * 64 + m], gy = s_gy[pl * 64 + m];
+                const int bz = s[p + j], by = 3 - (int)s[p + d.fl - 1 - j];          // z reads D[4j + b], y reads D[4(fl-1-j') + 3 - b] with j' = fl-1-j
+                a0 += (bz == 0 ? gz : 0.f) + (by == 0 ? gy : 0.f); a1 += (bz == 1 ? gz : 0.f) + (by == 1 ? gy : 0.f);
+                a2 += (bz == 2 ? gz : 0.f) + (by == 2 ? gy : 0.f); a3 += (bz == 3 ? gz : 0.f) + (by == 3 ? gy : 0.f);
+            }
+    }
+    if (!active) return;
+    if (a0 != 0.f) atomicAdd(&dD[(4 * j + 0) * d.M + m], a0);
+    if (a1 != 0.f) atomicAdd(&dD[(4 * j + 1) * d.M + m], a1);
+    if (a2 != 0.f) atomicAdd(&dD[(4 * j + 2) * d.M + m], a2);
+    if (a3 != 0.f) atomicAdd(&dD[(4 * j + 3) * d.M + m], a3);
+}
