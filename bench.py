@@ -162,10 +162,11 @@ def scan_config(args, n_touzet=None):
 
 
 def train_config(nseq, Lb, world, opt_steps, index, groups=1):
-    return {"workload": f"CSC training: {nseq} seqs x {Lb} bp (planted gapped motif), batch 6 per rank, "
+    return {"workload": f"CSC training: {nseq} seqs x {Lb} bp (planted gapped motif), {groups} batch(es) of 6 per rank and optimiser step, "
                         f"M=50 K=24 h=12 q=32, 6 XYZ + 3 DF passes, AdaBelief",
-            "baseline_config_index": index, "n_seqs": nseq, "seq_len": Lb, "global_batch": 6 * groups * world,
-            "optimizer_steps_per_bench_step": opt_steps, "parallelism": f"dp{world}", "l2": "working set (<20 MB) is L2 resident by design"}
+            "baseline_config_index": index, "n_seqs": nseq, "seq_len": Lb, "global_batch": 6 * groups * world, "groups_per_rank": groups,
+            "optimizer_steps_per_bench_step": opt_steps, "parallelism": f"dp{world}",
+            "l2": "working set (<20 MB) is L2 resident by design" if groups == 1 else "working set (~14 MB per group) exceeds L2: no flush needed"}
 
 
 def oracle_threads():
@@ -394,7 +395,7 @@ def flops_per_seq(Lb):
     return 3.0 * 2.0 * mac
 
 
-def bench_train(args, ctx, torch, dist, world, rank, local, dev, N, Lb, opt_steps, index, groups=1, e2e_leg=True, extras=True):
+def bench_train(args, ctx, torch, dist, world, rank, local, dev, N, Lb, opt_steps, index, groups=1, e2e_leg=True, extras=True, warm_mult=50):
     from motifs_jl_b200 import model as mdl, synth
     from motifs_jl_b200._lib import CscModel
     hp = mdl.Hyperparam()
@@ -442,7 +443,7 @@ def bench_train(args, ctx, torch, dist, world, rank, local, dev, N, Lb, opt_step
             checks["allreduced_grad_is_mean"] = bool(err <= 1e-6)
             p_all = ctx.comm_allgather(model.get_params())
             checks["params_identical_on_all_ranks"] = bool((p_all == p_all[0]).all())
-        for _ in range(min(args.warmup, 3) * 50):                         # >= 3 warm-up iterations of the step (graph capture included)
+        for _ in range(max(3, min(args.warmup, 3) * warm_mult)):          # >= 3 warm-up iterations of the step (graph capture included)
             opt_step()
         if world > 1:
             dist.barrier()
@@ -732,6 +733,11 @@ def main():
     if wl in ("all", "config3"):
         nested["config3_training"] = bench_train(args, ctx, torch, dist, world, rank, local, dev, args.c3_nseq, args.c3_seqlen, args.c3_steps, 2,
                                                  groups=args.c3_groups, e2e_leg=False, extras=False)
+    if wl == "all" and args.c3_groups == 1:
+        # the same data-parallel run with 64 reference batches per rank and optimiser step (global batch 384 x ranks): what the ranks are
+        # worth once a step carries enough work to fill a GPU (the many-group launch path of the library)
+        nested["config3_training_64groups"] = bench_train(args, ctx, torch, dist, world, rank, local, dev, args.c3_nseq, args.c3_seqlen, 10, 2,
+                                                          groups=64, e2e_leg=False, extras=False, warm_mult=3)
     if wl in ("all", "config5") and rank == 0:
         nested["config5_long_scan"] = bench_long_scan(args, ctx, torch, dev, stream)
     if world > 1:

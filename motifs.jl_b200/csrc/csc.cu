@@ -186,7 +186,10 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
             return;
         }
         // one CTA per sequence wins from ~190 sequences up (measured)
-        if (S->batched && d.G >= 32 && fastK && d.M2 * 24 <= 5 * 4 * C2B_THREADS) lk(k_corr2d_b<24>, d.NS, C2B_THREADS, corr2d_b_smem(d, 24), q, A, filt, gs, out, acc, d);
+        if (S->batched && d.G >= 32 && fastK && d.M2 * 24 <= C2B_PRE * 4 * 64) {
+            const int ntile = ((d.l + 3) / 4) * 3;            // 4-row x 8-filter register tiles of a sequence
+            lk(k_corr2d_b<24>, d.NS, std::min(C2B_THREADS, std::max(64, (ntile + 31) / 32 * 32)), corr2d_b_smem(d, 24), q, A, filt, gs, out, acc, d);
+        }
         else if (fastK) lk(k_corr2d_w<24, 4>, d.NS * ((d.l + 3) / 4), 128, 0, q, A, filt, gs, out, acc, d);
         else lk(k_corr2d, nblk(nX, 128), 128, 0, q, A, filt, gs, out, acc, d);
     };

@@ -339,7 +339,8 @@ __global__ void __launch_bounds__(MG_THREADS) k_mask_scale_g(const float* __rest
 // One CTA per sequence.  The sequence's rows (c x 2M, row stride 2M+1 so that the row tiles of a warp fall into different banks)
 // stay in shared memory; F is streamed one window offset at a time (2M x K floats, double-buffered through registers).
 // Register tiles of 4 rows x 8 filters: per (a, j) a thread issues 4 broadcast row loads + 2 LDS.128 for 32 FMAs.
-#define C2B_THREADS 128
+#define C2B_THREADS 256          // upper bound; launched with the number of register tiles rounded up to a warp (>= 64), so that one round covers the sequence
+#define C2B_PRE 10               // float4 of the next F slice a thread holds (600 float4 over >= 64 threads)
 template <int KK>
 __global__ void __launch_bounds__(C2B_THREADS) k_corr2d_b(const float* __restrict__ A, const float* __restrict__ filt, int64_t filt_gs,
                                                           float* __restrict__ out, int accumulate, CscDims d) { PDL_SYNC();
@@ -354,12 +355,12 @@ __global__ void __launch_bounds__(C2B_THREADS) k_corr2d_b(const float* __restric
     const float* F = filt + (n / d.B) * filt_gs;
     const float* a_src = A + n * d.c * d.M2;
     const int fsz = d.M2 * KK, fv = fsz >> 2;                   // floats / float4 per window offset
-    for (int e = threadIdx.x; e < rows_pad * d.M2; e += C2B_THREADS) {
+    for (int e = threadIdx.x; e < rows_pad * d.M2; e += blockDim.x) {
         const int r = e / d.M2, j = e - r * d.M2;
         sA[r * ldA + j] = r < d.c ? a_src[e] : 0.f;
     }
     const int ntile = rt_n * KT;
-    for (int t0 = 0; t0 < ntile; t0 += C2B_THREADS) {
+    for (int t0 = 0; t0 < ntile; t0 += blockDim.x) {
         const int tile = t0 + threadIdx.x;
         const bool live = tile < ntile;
         const int rt = live ? tile / KT : 0, kt = live ? tile - rt * KT : 0;
@@ -369,15 +370,15 @@ __global__ void __launch_bounds__(C2B_THREADS) k_corr2d_b(const float* __restric
             #pragma unroll
             for (int k = 0; k < 8; ++k) acc[r][k] = 0.f;
         __syncthreads();                                        // sA filled / previous round done with sF
-        for (int v = threadIdx.x; v < fv; v += C2B_THREADS) reinterpret_cast<float4*>(sF)[v] = reinterpret_cast<const float4*>(F)[v];
+        for (int v = threadIdx.x; v < fv; v += blockDim.x) reinterpret_cast<float4*>(sF)[v] = reinterpret_cast<const float4*>(F)[v];
         __syncthreads();
         for (int a = 0; a < d.h; ++a) {
-            float4 pre[5];                                      // next offset's F slice (2M*KK/4 = 600 float4 over 128 threads)
+            float4 pre[C2B_PRE];                                      // next offset's F slice (2M*KK/4 = 600 float4 over 128 threads)
             const bool more = a + 1 < d.h;
             if (more) {
                 const float4* src = reinterpret_cast<const float4*>(F + (int64_t)(a + 1) * fsz);
                 #pragma unroll
-                for (int u = 0; u < 5; ++u) { const int v = threadIdx.x + u * C2B_THREADS; if (v < fv) pre[u] = src[v]; }
+                for (int u = 0; u < C2B_PRE; ++u) { const int v = threadIdx.x + u * blockDim.x; if (v < fv) pre[u] = src[v]; }
             }
             if (live) {
                 const float* f0 = sF + (a & 1) * fsz + kt * 8;
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(C2B_THREADS) k_corr2d_b(const float* __restric
             if (more) {
                 float4* dst = reinterpret_cast<float4*>(sF + ((a + 1) & 1) * fsz);
                 #pragma unroll
-                for (int u = 0; u < 5; ++u) { const int v = threadIdx.x + u * C2B_THREADS; if (v < fv) dst[v] = pre[u]; }
+                for (int u = 0; u < C2B_PRE; ++u) { const int v = threadIdx.x + u * blockDim.x; if (v < fv) dst[v] = pre[u]; }
             }
             __syncthreads();
         }
