@@ -519,7 +519,46 @@ def bench_train(args, ctx, torch, dist, world, rank, local, dev, N, Lb, opt_step
                 rate, steps, cores, dt = cpu_train_rate(a[:2000], cdl.flat, args.cpu_seconds)
                 out["cpu_baseline"] = {"value": rate, "unit": "seq/s", "cores": cores, "kind": "port", "seconds": dt,
                                        "sample": f"{steps} optimiser steps of batch 6 (oracle/csc_oracle.py, PyTorch-CPU fp32 + autograd, {cores} threads)"}
+        p_trained = model.get_params()
         model.free()
+        if extras:
+            # code retrieval (inference/_1_code_retrieval.jl:33-56) over the training set with the parameters training just produced: 512 batches of
+            # 6 per launch sequence, fp32 (the parity path) and with the dense contraction on the tcgen05 BF16 kernel (stated tolerance); with a
+            # communicator the batches are sharded over the ranks and the records all-gathered
+            res = {}
+            for name, tc in (("fp32", False), ("tensor_cores_bf16", True)):
+                n_dec = n_train - n_train % hp.batch_size
+                G = max(1, min(512, -(-(n_dec // hp.batch_size) // world)))
+                mc = CscModel(ctx, hp, Lb, n_groups=G, forward_only=True, tensor_cores=tc)
+                mc.set_params(p_trained)
+                recs = mc.codes(seqs, shard="comm" if world > 1 else None)                    # warm-up (and the records for the comparison)
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record(side)
+                for _ in range(3):
+                    mc.codes(seqs, shard="comm" if world > 1 else None)
+                c1.record(side)
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                tc_ms = torch.tensor([c0.elapsed_time(c1) / 3], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(tc_ms, op=dist.ReduceOp.MAX)
+                res[name] = (recs, float(tc_ms.item()), n_dec)
+                mc.free()
+            if rank == 0:
+                r32, ms32, n_dec = res["fp32"]
+                rtc, mstc, _ = res["tensor_cores_bf16"]
+                key = lambda r: (r["seq"].astype(np.int64) * 65536 + r["fil"].astype(np.int64)) * 65536 + r["position"].astype(np.int64)
+                same = int(np.intersect1d(key(r32), key(rtc)).size)
+                out["code_retrieval"] = {"metric": "decoded_sequences_per_sec", "value": n_dec / (ms32 / 1e3), "unit": "seq/s", "ms": ms32,
+                                         "records": int(len(r32)), "dtype": "f32",
+                                         "sample": f"{n_dec} sequences x {Lb} bp, 6 ADMM_XYZ passes, {world} rank(s), records (position, fil, seq, Float16 magnitude) returned to the host",
+                                         "tensor_cores_bf16": {"value": n_dec / (mstc / 1e3), "unit": "seq/s", "ms": mstc, "records": int(len(rtc)),
+                                                               "records_also_in_fp32": same, "fraction_of_fp32_records": same / max(1, len(r32)),
+                                                               "note": "opt-in (tcgen05 kind::f16, BF16 operands): the top-q projection is discontinuous, so rounded operands move a few codes; the fp32 path is the parity path"}}
         # extra data point (NOT the headline): 16 independent batches of 6 per optimiser step on one GPU — the same arithmetic as
         # 16 data-parallel ranks (global batch 96, gradients averaged), i.e. a different optimisation trajectory than the reference's
         if extras and rank == 0 and world == 1:
