@@ -320,7 +320,11 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
             }
             tcs_wait(bar(2 * TCS_STAGES + 4), 0);
             const uint64_t dbA = tcs_desc(sB_addr, TCS_N * 16, 128), dbB = tcs_desc(sB_addr + b_bytes0, TCS_N * 16, 128);
+#ifdef TCS_EMULATE_HALF_K      // timing experiment only (results are wrong): half the MMAs per accumulator use = the MMA time an FP8 operand format would leave
+            const int kpA = max(1, blk.kchunks[0] >> 2), kpB = max(1, blk.kchunks[1] >> 2);
+#else
             const int kpA = blk.kchunks[0] >> 1, kpB = blk.kchunks[1] >> 1;
+#endif
             TCS_PROF(long long w_full = 0; long long w_acc = 0;)
             const long long t_start = clock64();
             uint32_t use0 = 0, use1 = 0;                                                 // completed uses of each accumulator
