@@ -382,8 +382,18 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_scan_tc(const TcArgs a) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem + ac * TCS_N + cg * 64 + ((uint32_t)(q * 32) << 16);
             uint32_t ua[32], ub[32];
+#ifdef TCS_EXPERIMENT_NO_DRAIN        // timing experiment only: the accumulator is handed back without being read (pure hand-off latency)
+            #pragma unroll
+            for (int i = 0; i < 32; ++i) ua[i] = 0x80000000u + taddr;
+#else
             TCS_LDTM32(ua, taddr);
+#endif
+#if defined(TCS_EXPERIMENT_HALF_DRAIN) || defined(TCS_EXPERIMENT_NO_DRAIN)      // timing experiment only (results are wrong): read half of the accumulator columns
+            #pragma unroll
+            for (int i = 0; i < 32; ++i) ub[i] = ua[i];
+#else
             TCS_LDTM32(ub, taddr + 32);
+#endif
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
