@@ -465,6 +465,8 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
     s->arena = B.cursor; s->bits_n = B.bit_cursor; s->n_lists = B.n_lists;
 }
 
+#define FZ_BAR_DF 21          // barrier counters: forward kernel [0, 21), DF reverse kernel [21, 42), XYZ reverse kernel [42, 63) (one per group)
+#define FZ_BAR_XYZ 42
 static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
     MB_CUDA(ctx, cudaMalloc(&s->p_raw, (size_t)s->n_total * 4));
     MB_CUDA(ctx, cudaMalloc(&s->g_raw, (size_t)s->n_total * 4));
@@ -514,7 +516,7 @@ static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
         s->fz_smem = fz::fz_smem_bytes(d.Lb);
         s->fz_nmed = d.npx + 2;
         const bool shape_ok = d.M == FZ_M && d.K == FZ_K && d.h == FZ_H && d.fl == FZ_FL && d.npx <= FZ_MAXPX && d.npd <= FZ_MAXPD &&
-                              d.B * LIST_CAP <= FZ_THREADS && d.B * FZ_CL >= FZ_K && d.c >= FZ_CL && d.l >= 1 && fz::fz_rows(d.c) <= 32;
+                              d.B * LIST_CAP <= FZ_THREADS && d.B * FZ_CL >= FZ_K && d.c >= FZ_CL && d.l >= 1 && fz::fz_rows(d.c) <= 32 && d.G <= FZ_BAR_DF;
         if (!s->no_fused && !s->tensor && shape_ok && s->fz_smem <= ctx->smem_optin) {
             cudaError_t e = cudaFuncSetAttribute(k_csc_fused_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->fz_smem);
 #if FZ_CL > 8
@@ -728,8 +730,6 @@ static void run_op(mb200_csc* s, Op& op, bool fwd, cudaStream_t q) {
 // whenever a step begins.  The fully fused training step restores that in its last kernel (k_csc_fused_tail); every other fused path
 // clears it with memset nodes after the last kernel that used it.  Likewise the adjoint arena: the fully fused step reads only the d x
 // slots from it before writing, and those are cleared by their reader (k_csc_fused_bwd_xyz), so it needs no memset per step.
-#define FZ_BAR_DF 21          // barrier counters: forward kernel [0, 21), DF reverse kernel [21, 42), XYZ reverse kernel [42, 63) (one per group)
-#define FZ_BAR_XYZ 42
 static void launch_fused(mb200_csc* s, int which, cudaStream_t q) {
     const CscDims d = s->d;
     FzBufs fb = s->fzb;
