@@ -285,7 +285,7 @@ __device__ float group_median(Ctx& c, const Smem& s, const FzBufs& B, int mi, in
     }
     FZ_S(c, 4);
 #ifdef FZ_PROFILE
-    if (blockIdx.x == 0 && threadIdx.x == 0) printf("[fzm] median %d: %u positives, %u candidates, %d low bits open\n", mi, npos, cnt, shift);
+    if (blockIdx.x == 0 && threadIdx.x == 0) printf("[fzm] median %d: %u positives, %u candidates, %d low bits open, window bin %d\n", mi, npos, cnt, shift, (int)(prefix >> 16) - FZ_KLO);
 #endif
     float med = -INFINITY;
     if (npos > 0) {                                                        // group-uniform
