@@ -89,10 +89,13 @@ function gpu_scan(ctx, seqs, pwms::Array{Float16,3}, lens::Vector{Int64}; thresh
 end
 
 # replaces the loop body of train_ucdl (train.jl:40-52): gradient(ps) do forward_pass_return_loss(...) end ; update! ; l1 test
-function csc_create(ctx, hp::HParams, L::Integer; n_groups=1, forward_only=false)
+# fused = false / fused_df = false keep the kernel-per-op tape for the whole step / for the reverse pass of the loss and the ADMM_DF passes
+# (MB200_CSC_NO_FUSED = 0x100, MB200_CSC_NO_FUSED_DF = 0x200: A/B measurements and cross-checks; same results within fp32 summation order)
+function csc_create(ctx, hp::HParams, L::Integer; n_groups=1, forward_only=false, tensor_cores=false, fused=true, fused_df=true)
     h = Ref{Ptr{Cvoid}}(C_NULL)
+    flags = Int32((tensor_cores ? 2 : (forward_only ? 1 : 0)) | (fused ? 0 : 0x100) | (fused_df ? 0 : 0x200))
     check(ctx, ccall((:mb200_csc_create, lib), Int32, (Ptr{Cvoid}, Ref{HParams}, Int64, Int32, Int32, Ref{Ptr{Cvoid}}),
-                     ctx, hp, L, n_groups, forward_only ? 1 : 0, h))
+                     ctx, hp, L, n_groups, flags, h))
     h[]
 end
 # flat = vcat(lambda_sparsity, kappa_sparsity, lambda_stepsize, omega_stepsize, kappa_stepsize, vec(D), vec(F), penalty_xyz, mu,
