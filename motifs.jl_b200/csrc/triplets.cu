@@ -30,7 +30,7 @@ struct mb200_triplets {
     uint16_t *pos_in = nullptr, *fil_in = nullptr;
     int32_t *rs = nullptr, *re = nullptr;
     int64_t* base = nullptr;                          // enumeration index of each range's first triplet
-    TrEntry* table = nullptr; uint64_t mask = 0;
+    TrEntry* table = nullptr; uint64_t mask = 0; size_t table_bytes = 0;      // block from the ctx cache (mb_pool_alloc)
     mb200_key_count* cand = nullptr; int64_t n_cand = 0; uint32_t cand_min = 0; bool have_cand = false;
     uint32_t* sel = nullptr;
     unsigned long long* counters = nullptr;           // [0] generic counter, [1] error flag
@@ -147,10 +147,13 @@ __global__ void __launch_bounds__(256) trip_mark_kernel(const TrEntry* __restric
     atomicAdd(&counters[1], 1ull);                            // not a key of this dictionary (or below the candidate threshold)
 }
 
-static void trip_free(mb200_triplets* t) {
+// the hash table (2 x the triplets, GBs at 20 000 sequences) comes from the ctx's block cache: run_thru builds one dictionary per quantile
+// (_g1_obtain_coutmats.jl:136-160), and cudaMalloc / cudaFree of a block that size cost ~30 ms each
+static void trip_free(mb200_ctx* ctx, mb200_triplets* t) {
     if (!t) return;
     cudaFree(t->pos); cudaFree(t->fil); cudaFree(t->pos_in); cudaFree(t->fil_in); cudaFree(t->rs); cudaFree(t->re); cudaFree(t->base);
-    cudaFree(t->table); cudaFree(t->cand); cudaFree(t->sel); cudaFree(t->counters);
+    if (t->table) mb_pool_free(ctx, t->table, t->table_bytes);
+    cudaFree(t->cand); cudaFree(t->sel); cudaFree(t->counters);
     delete t;
 }
 
@@ -174,7 +177,7 @@ extern "C" int32_t mb200_triplets_create(mb200_ctx* ctx, const uint16_t* positio
     std::vector<int64_t> h_base(t->n_ranges + 1, 0);
     for (int64_t r = 0; r < t->n_ranges; ++r) {
         const int64_t n = t->h_stop[r] - t->h_start[r];
-        if (n > TR_MAXN) { trip_free(t); MB_FAIL(ctx, MB200_E_UNSUPPORTED, "triplets: a range holds %lld code components (max %d)", (long long)n, TR_MAXN); }
+        if (n > TR_MAXN) { trip_free(ctx, t); MB_FAIL(ctx, MB200_E_UNSUPPORTED, "triplets: a range holds %lld code components (max %d)", (long long)n, TR_MAXN); }
         h_base[r + 1] = h_base[r] + (n >= 3 ? n * (n - 1) * (n - 2) / 6 : 0);
     }
     t->n_triplets = h_base[t->n_ranges];
@@ -182,15 +185,17 @@ extern "C" int32_t mb200_triplets_create(mb200_ctx* ctx, const uint16_t* positio
     if (n_triplets) *n_triplets = t->n_triplets;
     uint64_t cap = 1024;
     while (cap < 2 * (uint64_t)t->n_triplets && cap < (1ull << 31)) cap <<= 1;
-    if ((uint64_t)t->n_triplets > cap / 2 + cap / 4) { trip_free(t); MB_FAIL(ctx, MB200_E_UNSUPPORTED, "triplets: %lld triplets exceed the hash table", (long long)t->n_triplets); }
+    if ((uint64_t)t->n_triplets > cap / 2 + cap / 4) { trip_free(ctx, t); MB_FAIL(ctx, MB200_E_UNSUPPORTED, "triplets: %lld triplets exceed the hash table", (long long)t->n_triplets); }
     t->mask = cap - 1;
     const size_t nc = (size_t)std::max<int64_t>(n_codes, 1), nr = (size_t)std::max<int64_t>(t->n_ranges, 1);
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
     ok(cudaMalloc(&t->pos, nc * 2)); ok(cudaMalloc(&t->fil, nc * 2)); ok(cudaMalloc(&t->pos_in, nc * 2)); ok(cudaMalloc(&t->fil_in, nc * 2));
     ok(cudaMalloc(&t->rs, nr * 4)); ok(cudaMalloc(&t->re, nr * 4)); ok(cudaMalloc(&t->base, (nr + 1) * 8));
-    ok(cudaMalloc(&t->table, cap * sizeof(TrEntry))); ok(cudaMalloc(&t->counters, 16));
-    if (e != cudaSuccess) { trip_free(t); MB_FAIL(ctx, MB200_E_CUDA, "triplets: allocation failed: %s", cudaGetErrorString(e)); }
+    t->table = reinterpret_cast<TrEntry*>(mb_pool_alloc(ctx, cap * sizeof(TrEntry), &t->table_bytes));
+    if (!t->table) ok(cudaErrorMemoryAllocation);
+    ok(cudaMalloc(&t->counters, 16));
+    if (e != cudaSuccess) { trip_free(ctx, t); MB_FAIL(ctx, MB200_E_CUDA, "triplets: allocation failed: %s", cudaGetErrorString(e)); }
     cudaStream_t q = ctx->stream;
     ok(cudaMemsetAsync(t->table, 0, cap * sizeof(TrEntry), q));
     ok(cudaMemsetAsync(t->counters, 0, 16, q));
@@ -206,7 +211,7 @@ extern "C" int32_t mb200_triplets_create(mb200_ctx* ctx, const uint16_t* positio
         ok(cudaGetLastError());
     }
     ok(cudaStreamSynchronize(q));
-    if (e != cudaSuccess) { trip_free(t); MB_FAIL(ctx, MB200_E_CUDA, "triplets: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { trip_free(ctx, t); MB_FAIL(ctx, MB200_E_CUDA, "triplets: %s", cudaGetErrorString(e)); }
     *out = t;
     return MB200_OK;
 }
@@ -214,7 +219,7 @@ extern "C" int32_t mb200_triplets_create(mb200_ctx* ctx, const uint16_t* positio
 extern "C" int32_t mb200_triplets_destroy(mb200_ctx* ctx, mb200_triplets* t) {
     if (!t) return MB200_E_INVALID;
     if (ctx) cudaSetDevice(ctx->device);
-    trip_free(t);
+    trip_free(ctx, t);
     return MB200_OK;
 }
 

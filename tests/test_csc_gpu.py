@@ -131,8 +131,8 @@ def test_host_batch_step_equals_resident_step(ctx):
         idx = rng.permutation(30)[:6]
         m1.step_begin(seqs, idx); l1a = m1.adabelief_step()
         m2.step_begin_host(a[idx]); l1b = m2.adabelief_step()
-        assert l1a == pytest.approx(l1b, rel=1e-5)            # scalar-gradient reductions use float atomics: last-bit differences
-    assert np.allclose(m1.get_params(), m2.get_params(), rtol=0, atol=2e-6)
+        assert l1a == l1b                                     # the fused step has no atomics: every sum is taken in a fixed order
+    assert np.array_equal(m1.get_params(), m2.get_params())
     bad = a[:6].copy(); bad[2, 5] = ord("N")
     with pytest.raises(mb.MB200Error) as e:
         m2.step_begin_host(bad)
