@@ -104,6 +104,19 @@ struct Ctx {
 __device__ __forceinline__ unsigned int ld_relaxed(const unsigned int* p) {
     unsigned int v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
+// global (L2) -> shared copy of n4 float4 with U loads per thread in flight: the destination is a generic pointer, so the compiler will not move
+// a load above the previous iteration's store by itself, and a one-load-per-iteration loop pays one L2 round trip per 8 KB of the block
+template <int U>
+__device__ __forceinline__ void stage_f4(float4* dst, const float4* src, int n4) {
+    for (int e0 = 0; e0 < n4; e0 += U * FZ_THREADS) {
+        float4 v[U];
+        #pragma unroll
+        for (int u = 0; u < U; ++u) { const int e = e0 + u * FZ_THREADS + threadIdx.x; if (e < n4) v[u] = __ldcg(src + e); }
+        #pragma unroll
+        for (int u = 0; u < U; ++u) { const int e = e0 + u * FZ_THREADS + threadIdx.x; if (e < n4) dst[e] = v[u]; }
+    }
+}
+
 // barrier over the CTAs of one group; global writes before it are visible to every CTA of the group after it.  Hierarchical: the CTAs
 // of a cluster meet at the hardware cluster barrier, only the cluster's rank-0 CTA arrives at / polls the counter in global memory (6
 // arrivals on one address instead of 96: same-address atomics serialise in L2), a second cluster barrier releases the others.
@@ -284,7 +297,7 @@ __device__ float group_median(Ctx& c, const Smem& s, const FzBufs& B, int mi, in
         if (shift == 19) { shift = 7; nb = FZ_BINS; } else if (shift == 7) { shift = 0; nb = 128; } else { shift = 0; nb = 16; }
     }
     FZ_S(c, 4);
-#ifdef FZ_PROFILE
+#ifdef FZ_PROFILE_MEDIAN
     if (blockIdx.x == 0 && threadIdx.x == 0) printf("[fzm] median %d: %u positives, %u candidates, %d low bits open, window bin %d\n", mi, npos, cnt, shift, (int)(prefix >> 16) - FZ_KLO);
 #endif
     float med = -INFINITY;
@@ -675,7 +688,7 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
     const float mf = d.mf;
     FZ_TDECL;
     // ---- prologue: filters and bases into shared memory --------------------------------------------------------------------
-    for (int e = threadIdx.x; e < (int)nF / 4; e += FZ_THREADS) reinterpret_cast<float4*>(s.F)[e] = __ldcg(reinterpret_cast<const float4*>(data + P.Fe) + e);
+    stage_f4<8>(reinterpret_cast<float4*>(s.F), reinterpret_cast<const float4*>(data + P.Fe), (int)nF / 4);
     for (int e = threadIdx.x; e < (int)nD; e += FZ_THREADS) s.D[e] = __ldcg(data + P.De + e);
     const int nb_own = min(Lb, c.p1 + 7 + FZ_FL) - c.p0;                       // bases [p0, ...) this CTA ever looks at
     for (int e = threadIdx.x; e < nb_own; e += FZ_THREADS) s.b[e] = B.bases[(size_t)c.n * Lb + c.p0 + e];
@@ -1002,7 +1015,7 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
         }
         FZ_T(14);
         group_barrier(c);                                      // the updated F is published
-        for (int e = threadIdx.x; e < (int)nF / 4; e += FZ_THREADS) reinterpret_cast<float4*>(s.F)[e] = __ldcg(reinterpret_cast<const float4*>(data + Y.Fn + (int64_t)c.g * nF) + e);
+        stage_f4<8>(reinterpret_cast<float4*>(s.F), reinterpret_cast<const float4*>(data + Y.Fn + (int64_t)c.g * nF), (int)nF / 4);
         __syncthreads();
         // theta <- theta + fx(x, F_new) - zyF (model.jl:370), only needed by the next pass
         if (Y.has_theta_out) {
@@ -1218,7 +1231,7 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
     float* dFp = s.dFt;                                           // partial dF of the targets this CTA owns, in shared memory
 #define SEQ(off, per) ((off) + (int64_t)c.n * (per))
     // ---- prologue ----------------------------------------------------------------------------------------------------------------
-    for (int e = threadIdx.x; e < nF / 4; e += FZ_THREADS) reinterpret_cast<float4*>(s.F)[e] = __ldcg(reinterpret_cast<const float4*>(data + P.Fe) + e);
+    stage_f4<8>(reinterpret_cast<float4*>(s.F), reinterpret_cast<const float4*>(data + P.Fe), nF / 4);
     for (int e = threadIdx.x; e < nD; e += FZ_THREADS) { s.D[e] = __ldcg(data + P.De + e); s.dDp[e] = 0.f; }
     if (threadIdx.x < 64) s.dscp[threadIdx.x] = 0.f;
     for (int e = threadIdx.x; e < FZ_NTGT * FZ_M2; e += FZ_THREADS) s.dFt[e] = 0.f;
