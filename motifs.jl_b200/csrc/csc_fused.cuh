@@ -573,7 +573,13 @@ __device__ void topq_all(Ctx& c, const Smem& s, const float* g_g, const float* x
     const int pcnt = have_prev ? s.lc[0] : 0;
     if (have_prev && pcnt > LIST_CAP) { for (int e = threadIdx.x; e < E; e += FZ_THREADS) sv[e] = __ldcg(xprev_g + e) + om * __ldcg(g_g + e); }
     else {
-        for (int e = threadIdx.x; e < E; e += FZ_THREADS) sv[e] = 0.f + om * __ldcg(g_g + e);
+        for (int e0 = 0; e0 < E; e0 += 4 * FZ_THREADS) {                 // four loads per thread in flight (see stage_f4)
+            float gv[4];
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) { const int e = e0 + u * FZ_THREADS + threadIdx.x; gv[u] = e < E ? __ldcg(g_g + e) : 0.f; }
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) { const int e = e0 + u * FZ_THREADS + threadIdx.x; if (e < E) sv[e] = 0.f + om * gv[u]; }
+        }
         __syncthreads();
         if (threadIdx.x < pcnt) { const int e = s.li[threadIdx.x]; sv[e] = s.lv[threadIdx.x] + om * __ldcg(g_g + e); }
     }
@@ -743,23 +749,41 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
         const float* fxg = with_d ? SEQ_ZY(fx_in) : nullptr;
         const float* alg = (with_d && !duals_zero) ? SEQ_Z(al_in) : nullptr; const float* beg = (with_d && !duals_zero) ? SEQ_Z(be_in) : nullptr;
         if (c.ni > 0)
-        for (int o = threadIdx.x; o < (a_hi - c.i0) * FZ_M2; o += FZ_THREADS) {
-            const int rl = o / FZ_M2, j = o - rl * FZ_M2, row = c.i0 + rl;
-            const bool own = row < c.p1;
-            const int m = j < FZ_M ? j : j - FZ_M;
-            float v;
-            if (own) v = j < FZ_M ? s.z[(row - c.p0) * FZ_M + m] : s.y[(row - c.p0) * FZ_M + m];
-            else v = __ldcg((j < FZ_M ? zg : yg) + (size_t)row * FZ_M + m);
-            float zyv = v >= med ? mf * v : 0.f;
-            if (own && zy_out >= 0) SEQ_ZY(zy_out)[(size_t)row * FZ_M2 + j] = zyv;
-            if (with_d) {
-                float fxv, ab;
-                if (own) { fxv = s.fx[(row - c.p0) * FZ_M2 + j]; ab = j < FZ_M ? s.al[(row - c.p0) * FZ_M + m] : s.be[(row - c.p0) * FZ_M + m]; }
-                else { fxv = __ldcg(fxg + (size_t)row * FZ_M2 + j); ab = duals_zero ? 0.f : __ldcg((j < FZ_M ? alg : beg) + (size_t)row * FZ_M + m); }
-                zyv = fxv - (zyv - ab);
-                if (own && dd_out >= 0) SEQ_ZY(dd_out)[(size_t)row * FZ_M2 + j] = zyv;
+        for (int o0 = 0; o0 < (a_hi - c.i0) * FZ_M2; o0 += 4 * FZ_THREADS) {
+            // four elements per thread, all their global loads (the 11 halo rows come from what the neighbours published) issued before the first
+            // store: the destination is a generic pointer, so the compiler keeps loads behind earlier stores and each element would pay its own L2 round trip
+            float v[4], fxv[4], ab[4];
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int o = o0 + u * FZ_THREADS + threadIdx.x;
+                v[u] = 0.f; fxv[u] = 0.f; ab[u] = 0.f;
+                if (o < (a_hi - c.i0) * FZ_M2) {
+                    const int rl = o / FZ_M2, j = o - rl * FZ_M2, row = c.i0 + rl;
+                    const bool own = row < c.p1;
+                    const int m = j < FZ_M ? j : j - FZ_M;
+                    if (own) v[u] = j < FZ_M ? s.z[(row - c.p0) * FZ_M + m] : s.y[(row - c.p0) * FZ_M + m];
+                    else v[u] = __ldcg((j < FZ_M ? zg : yg) + (size_t)row * FZ_M + m);
+                    if (with_d) {
+                        if (own) { fxv[u] = s.fx[(row - c.p0) * FZ_M2 + j]; ab[u] = j < FZ_M ? s.al[(row - c.p0) * FZ_M + m] : s.be[(row - c.p0) * FZ_M + m]; }
+                        else { fxv[u] = __ldcg(fxg + (size_t)row * FZ_M2 + j); ab[u] = duals_zero ? 0.f : __ldcg((j < FZ_M ? alg : beg) + (size_t)row * FZ_M + m); }
+                    }
+                }
             }
-            s.A[o] = zyv;
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int o = o0 + u * FZ_THREADS + threadIdx.x;
+                if (o < (a_hi - c.i0) * FZ_M2) {
+                    const int rl = o / FZ_M2, j = o - rl * FZ_M2, row = c.i0 + rl;
+                    const bool own = row < c.p1;
+                    float zyv = v[u] >= med ? mf * v[u] : 0.f;
+                    if (own && zy_out >= 0) SEQ_ZY(zy_out)[(size_t)row * FZ_M2 + j] = zyv;
+                    if (with_d) {
+                        zyv = fxv[u] - (zyv - ab[u]);
+                        if (own && dd_out >= 0) SEQ_ZY(dd_out)[(size_t)row * FZ_M2 + j] = zyv;
+                    }
+                    s.A[o] = zyv;
+                }
+            }
         }
         // rows of zy / d that no x row reaches (i >= l) still belong to somebody's tape tensors
         if (c.p1 > max(c.i1 + FZ_H - 1, c.p0) || c.ni == 0) {
