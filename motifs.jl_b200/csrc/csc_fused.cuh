@@ -40,6 +40,9 @@
 #define FZ_CNTSEL 512             // candidate sets up to this size are settled by counting (one candidate per thread), larger ones by radix passes
 #endif
 #define FZ_BINS 4096
+#ifndef FZ_CALL
+#define FZ_CALL                   // EXTRA_DEFS="-DFZ_CALL=__noinline__": the large phase routines as real calls (forward kernel 24 k -> 14 k SASS instructions).
+#endif                            // Measured slower (0.548 -> 0.64 ms per step: Ctx / Smem then live in local memory, no per-site specialisation)
 #ifndef FZ_CAND
 #define FZ_CAND 2048
 #endif
@@ -228,7 +231,7 @@ __device__ __forceinline__ void carve(Smem& s, float* base, int R, int Lb) {
 
 // ---- batch median of the positive entries of (z, y) over the whole group; every CTA holds its rows in s.z / s.y -------------
 // (create_ZY_mask, model.jl:194-204; Statistics.median: mean of the two middle values for an even count; no positives: -inf = no mask)
-__device__ float group_median(Ctx& c, const Smem& s, const FzBufs& B, int mi, int nmed) {
+__device__ FZ_CALL float group_median(Ctx& c, const Smem& s, const FzBufs& B, int mi, int nmed) {
     unsigned int* lhist = reinterpret_cast<unsigned int*>(s.w);
     float* cand = s.w + FZ_BINS;
     unsigned int* wsum = reinterpret_cast<unsigned int*>(s.red);          // 32 uints
@@ -420,7 +423,7 @@ __device__ __forceinline__ void build_Dt(const Smem& s) {
 // recon of base positions [q0, q1): rec[4q+a] = sum_{j<8} sum_m z[q-j][m] D[4j+a][m] + y[q-j][m] D[31-4j-a][m]  (model.jl:238-239,276-277,313-314)
 // from the staged rows [lo, hi); half a warp per base position, lanes over m, four taps per 16-byte filter load.  Writes
 // s.sig[t - 4 q0] = rec + sgn*S and, for own positions [wq0, wq1), rec to global (may be null)
-__device__ void recon_rows(const Ctx& c, const Smem& s, int lo, int hi, int q0, int q1, float sgn, float* rec_g, int wq0, int wq1, int Lb) {
+__device__ FZ_CALL void recon_rows(const Ctx& c, const Smem& s, int lo, int hi, int q0, int q1, float sgn, float* rec_g, int wq0, int wq1, int Lb) {
     const int sub = threadIdx.x & 15, hw = threadIdx.x >> 4;
     const float* zh = s.A; const float* yh = s.A + (hi - lo) * FZ_M;
     const int cc = Lb - FZ_FL + 1;
@@ -460,7 +463,7 @@ __device__ void recon_rows(const Ctx& c, const Smem& s, int lo, int hi, int q0, 
 
 // ---- F layer ---------------------------------------------------------------------------------------------------------------
 // out[i][k] = sum_{a<12} sum_{j<100} A[i+a][j] F[a][j][k] for the CTA's ni rows; A rows [i0, i1+11) in s.A; result in s.gout
-__device__ void corr2d_rows(const Smem& s, const float* Fm, int ni) {
+__device__ FZ_CALL void corr2d_rows(const Smem& s, const float* Fm, int ni) {
     const int ntr = (ni + 2) / 3, ntile = ntr * 6;
     const int nslice = ntile ? min(FZ_THREADS / ntile, 64) : 0;
     const int tile = ntile ? threadIdx.x % ntile : 0, slice = ntile ? threadIdx.x / ntile : 0;
@@ -507,7 +510,7 @@ __device__ void corr2d_rows(const Smem& s, const float* Fm, int ni) {
 // then one thread per output (row, j) walks only those.  cnt <= lcap (a longer list held in li/lv): every output walks the whole list.
 // Otherwise (forward only: more codes than the list holds) the dense tensor xg is read from global.  out: [nr][100].  Uses s.w.
 // Filter element (a, j, k) sits at Fm[a*sa + j*sj + k*sk]: (2M*K, K, 1) for the [a][j][k] layout of F, (2M, 1, h*2M) for a k-major copy.
-__device__ void tconv_list(const Ctx& c, const Smem& s, const float* Fm, const int* li, const float* lv, int cnt, int lcap, const float* xg, int l, float* out,
+__device__ FZ_CALL void tconv_list(const Ctx& c, const Smem& s, const float* Fm, const int* li, const float* lv, int cnt, int lcap, const float* xg, int l, float* out,
                            int sa = FZ_M2 * FZ_K, int sj = FZ_K, int sk = 1) {
     const int R = c.nr;
     int* rcnt = reinterpret_cast<int*>(s.w); int* roff = rcnt + 32; float* rval = s.w + 32 + 32 * LIST_CAP;      // rows <= 32
@@ -563,7 +566,7 @@ __device__ __forceinline__ void tconv_rows(const Ctx& c, const Smem& s, const fl
 
 // per-sequence top-q (generate_bitmat / project_X, model.jl:181-192) on v = xprev + om * g over all l*K entries, redundantly in every CTA of
 // the cluster; writes own rows of x and the bitmap, rank 0 writes the ordered code list; leaves the list in s.li / s.lv / s.lc
-__device__ void topq_all(Ctx& c, const Smem& s, const float* g_g, const float* xprev_g, bool have_prev, float om, int l, int q,
+__device__ FZ_CALL void topq_all(Ctx& c, const Smem& s, const float* g_g, const float* xprev_g, bool have_prev, float om, int l, int q,
                          float* xout_g, uint8_t* bits_g, int32_t* lcnt_g, uint16_t* lidx_g, float* lval_g) {
     const int E = l * FZ_K;
     float* sv = s.w;
@@ -813,12 +816,13 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
         for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) fo[(size_t)c.p0 * FZ_M2 + o] = s.fx[o];
         FZ_T(7);
     };
-    x_chain(0, P.z0, P.y0, P.med0, false, 0, 0, 0, true, P.zy0, -1, P.g0, 0, false, P.x0, P.bits0, P.xl0, sc[P.i_om_w], P.fx0);
-
-    // ---- ADMM_XYZ passes (model.jl:256-268) --------------------------------------------------------------------------------
-    for (int n = 0; n < P.npx; ++n) {
-        const FzPass& X = P.px[n];
+    // ---- warm-up x chain (n = -1), then the ADMM_XYZ passes (model.jl:256-268); ONE instance of the chain's code for both ---------------
+    #pragma unroll 1
+    for (int n = -1; n < P.npx; ++n) {
+        const bool wu = n < 0;
+        const FzPass& X = P.px[wu ? 0 : n];
         const float eta = sc[X.i_eta], lam = sc[X.i_lam], rho = sc[X.i_rho], om = sc[X.i_om];
+        if (!wu) {
         // (1) recon of base positions [p0, p1 + 7) from rows [p0 - 7, p1 + 7) of the previous z, y; residual r = recon - S
         {
             const int lo = max(0, c.p0 - 7), hi = min(cc, c.p1 + 7);
@@ -851,10 +855,13 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
             __syncthreads();
         }
         FZ_T(9);
+        }
         // (3) mask, d, corr2d, top-q, tconv
-        x_chain(n + 1, X.z_out, X.y_out, X.med, true, X.fx_in, X.al_in, X.be_in, n == 0, -1, X.dd, X.g, X.x_in, true, X.x_out, X.bits, X.xl_out, -om, X.fx_out);
+        x_chain(n + 1, wu ? P.z0 : X.z_out, wu ? P.y0 : X.y_out, wu ? P.med0 : X.med, !wu, X.fx_in, X.al_in, X.be_in, n <= 0, wu ? P.zy0 : (int64_t)-1,
+                wu ? (int64_t)-1 : X.dd, wu ? P.g0 : X.g, X.x_in, !wu, wu ? P.x0 : X.x_out, wu ? P.bits0 : X.bits, wu ? P.xl0 : X.xl_out,
+                wu ? sc[P.i_om_w] : -om, wu ? P.fx0 : X.fx_out);
         // (4) duals (model.jl:265-266); the duals after the last pass are never read
-        if (X.al_out >= 0) {
+        if (!wu && X.al_out >= 0) {
             float* ao = SEQ_Z(X.al_out); float* bo = SEQ_Z(X.be_out);
             for (int o = threadIdx.x; o < c.nr * FZ_M; o += FZ_THREADS) {
                 const int pl = o / FZ_M, m = o - pl * FZ_M;

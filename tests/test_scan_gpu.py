@@ -470,3 +470,35 @@ def test_tensor_path_many_motifs(ctx):
     thr2 = synth.stated_thresholds(ms2, 0.6)
     assert _tc_path(ctx, a[:100], ms2, thr2) == 0
     _check(ctx, a[:100], ms2, thr2)
+
+
+def test_config4_sample_of_100k_sequences_against_the_oracle(ctx):
+    """counts of a 100 000-sequence sample and the hit lists of 1 % of it must equal the oracle's (50 of the
+    bench's 500 PWMs, so that the CPU side stays within seconds); both kernels."""
+    N, Lb = 100_000, 200
+    cms = synth.random_count_matrices(500, 8, 40, 4)                                           # bench.py's motif set
+    ms = synth.motifs_from_count_matrices([cms[i] for i in range(0, 500, 10)])
+    thr = synth.stated_thresholds(ms, 0.7)
+    pw, lens = so.pack_pwms(ms.pwms)
+    a = synth.random_ascii(N, Lb, 2024)
+    codes = so.ascii_to_codes(a)
+    seqs = ctx.seqs_from_ascii(a)
+    _, c_tc = ctx.scan(seqs, pw, lens, thr, want_hits=False)
+    assert _lib.scan_last_path(ctx) == 1
+    seqs.free()
+    s20 = ctx.seqs_from_ascii(a[:20_000])
+    _, c_gt0 = ctx.scan(s20, pw, lens, None, want_hits=False)                   # the reference's own semantics: hit = score > 0
+    s20.free()
+    _, oc = so.scan(pw, lens, codes, thr, want_hits=False)
+    assert np.array_equal(c_tc, oc)
+    _, oc0 = so.scan(pw, lens, codes[:20_000], None, want_hits=False)
+    assert np.array_equal(c_gt0, oc0)
+    sub = a[37_000:38_000]
+    s = ctx.seqs_from_ascii(sub)
+    for t in (thr, None):
+        hits, _ = ctx.scan(s, pw, lens, t, hits_cap=4_000_000)
+        ohits, _ = so.scan(pw, lens, codes[37_000:38_000], t)
+        assert len(hits) == len(ohits) and len(hits) > 0
+        for f in ("seq", "pos", "motif", "score_f16", "comp"):
+            assert np.array_equal(hits[f], ohits[f]), f
+    s.free()
