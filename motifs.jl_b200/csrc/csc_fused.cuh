@@ -742,10 +742,21 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
     // shared by warm-up and the passes: masked/scaled codes of rows [i0, i1 + 11) -> s.A (optionally d = fx - (zy' - [al be])), corr2d, top-q, tconv
     auto x_chain = [&](int mi, int64_t z_off, int64_t y_off, int64_t med_off, bool with_d, int64_t fx_in, int64_t al_in, int64_t be_in, bool duals_zero,
                        int64_t zy_out, int64_t dd_out, int64_t g_off, int64_t x_in, bool have_prev, int64_t x_out, int64_t bits_off, int xl_out, float om,
-                       int64_t fx_out) {
+                       int64_t fx_out, bool final_mask) {
         const float med = group_median(c, s, B, mi, nmed);
         FZ_T(2);
         if (c.gidx == 0 && threadIdx.x == 0) data[med_off + c.g] = med;
+        if (final_mask) {                                      // the mask ADMM_DF works with (model.jl:365): zyF on own rows, nothing else
+            float* zo = SEQ_ZY(zy_out);
+            for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) {
+                const int rl = o / FZ_M2, j = o - rl * FZ_M2, m = j < FZ_M ? j : j - FZ_M;
+                const float v = j < FZ_M ? s.z[rl * FZ_M + m] : s.y[rl * FZ_M + m];
+                const float zyv = v >= med ? mf * v : 0.f;
+                s.zyF[o] = zyv; zo[(size_t)c.p0 * FZ_M2 + o] = zyv;
+            }
+            __syncthreads();
+            return;
+        }
         // A tile rows [i0, i1 + 11): own rows from shared memory, the rest recomputed from what the neighbours published
         const int a_hi = min(cc, c.i1 + FZ_H - 1);
         const float* zg = SEQ_Z(z_off); const float* yg = SEQ_Z(y_off);
@@ -816,13 +827,16 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
         for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) fo[(size_t)c.p0 * FZ_M2 + o] = s.fx[o];
         FZ_T(7);
     };
-    // ---- warm-up x chain (n = -1), then the ADMM_XYZ passes (model.jl:256-268); ONE instance of the chain's code for both ---------------
+    // ---- warm-up x chain (n = -1), the ADMM_XYZ passes (model.jl:256-268), and the batch median + mask ADMM_DF starts with (n = npx): ONE
+    //      instance of the chain's code (the kernel is ~18 k SASS instructions; every duplicated phase costs instruction-cache misses on the
+    //      critical path of all warps at once) ----------------------------------------------------------------------------------------------
+    const int n_end = P.forward_only ? P.npx : P.npx + 1;
     #pragma unroll 1
-    for (int n = -1; n < P.npx; ++n) {
-        const bool wu = n < 0;
-        const FzPass& X = P.px[wu ? 0 : n];
+    for (int n = -1; n < n_end; ++n) {
+        const bool wu = n < 0, fin = n == P.npx;
+        const FzPass& X = P.px[wu ? 0 : (fin ? P.npx - 1 : n)];
         const float eta = sc[X.i_eta], lam = sc[X.i_lam], rho = sc[X.i_rho], om = sc[X.i_om];
-        if (!wu) {
+        if (!wu && !fin) {
         // (1) recon of base positions [p0, p1 + 7) from rows [p0 - 7, p1 + 7) of the previous z, y; residual r = recon - S
         {
             const int lo = max(0, c.p0 - 7), hi = min(cc, c.p1 + 7);
@@ -857,9 +871,10 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
         FZ_T(9);
         }
         // (3) mask, d, corr2d, top-q, tconv
-        x_chain(n + 1, wu ? P.z0 : X.z_out, wu ? P.y0 : X.y_out, wu ? P.med0 : X.med, !wu, X.fx_in, X.al_in, X.be_in, n <= 0, wu ? P.zy0 : (int64_t)-1,
-                wu ? (int64_t)-1 : X.dd, wu ? P.g0 : X.g, X.x_in, !wu, wu ? P.x0 : X.x_out, wu ? P.bits0 : X.bits, wu ? P.xl0 : X.xl_out,
-                wu ? sc[P.i_om_w] : -om, wu ? P.fx0 : X.fx_out);
+        x_chain(n + 1, wu ? P.z0 : X.z_out, wu ? P.y0 : X.y_out, wu ? P.med0 : (fin ? P.medF : X.med), !wu, X.fx_in, X.al_in, X.be_in, n <= 0,
+                wu ? P.zy0 : (fin ? P.zyF : (int64_t)-1), wu ? (int64_t)-1 : X.dd, wu ? P.g0 : X.g, X.x_in, !wu, wu ? P.x0 : X.x_out, wu ? P.bits0 : X.bits,
+                wu ? P.xl0 : X.xl_out, wu ? sc[P.i_om_w] : -om, wu ? P.fx0 : X.fx_out, fin);
+        if (fin) break;
         // (4) duals (model.jl:265-266); the duals after the last pass are never read
         if (!wu && X.al_out >= 0) {
             float* ao = SEQ_Z(X.al_out); float* bo = SEQ_Z(X.be_out);
@@ -877,31 +892,25 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
 
     // ---- ADMM_DF (model.jl:362-373) ----------------------------------------------------------------------------------------
     const FzPass& XL = P.px[P.npx - 1];
-    {
-        const float med = group_median(c, s, B, P.npx + 1, nmed);
-        if (c.gidx == 0 && threadIdx.x == 0) data[P.medF + c.g] = med;
-        float* zo = SEQ_ZY(P.zyF);
-        for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) {
-            const int rl = o / FZ_M2, j = o - rl * FZ_M2, m = j < FZ_M ? j : j - FZ_M;
-            const float v = j < FZ_M ? s.z[rl * FZ_M + m] : s.y[rl * FZ_M + m];
-            const float zyv = v >= med ? mf * v : 0.f;
-            s.zyF[o] = zyv; zo[(size_t)c.p0 * FZ_M2 + o] = zyv;
-        }
-        __syncthreads();
-    }
     float* part = B.part + ((size_t)c.g * c.ng + c.gidx) * FZ_PART;
     float* gpart = B.part + (size_t)c.g * c.ng * FZ_PART;
     const int lo7 = max(0, c.p0 - 7), hi7 = min(cc, c.p1 + 7);
-    for (int n = 0; n < P.npd; ++n) {
-        const FzDf& Y = P.df[n];
+    // s.fx holds fx(x, F) of the sequence's final codes with the CURRENT F on own rows: the last pass's x chain left it there, and every DF pass
+    // renews it after its F update -- the e of the next pass, theta and the loss all read that one transposed convolution.
+    // Iteration n = npd is the loss (model.jl:310-325, with the updated D and F): it shares the recon code with the passes.
+    #pragma unroll 1
+    for (int n = 0; n <= P.npd; ++n) {
+        const bool last = n == P.npd;
+        const FzDf& Y = P.df[last ? max(P.npd - 1, 0) : n];
         const float mu = sc[Y.i_mu], kap = sc[Y.i_kap], kaps = sc[Y.i_kaps];
-        // D chain: recon with the current D, R = recon + S ('+S': model.jl:282-285), partial 32-lag gradient over own rows
+        // D chain: recon with the current D, R = recon + S ('+S': model.jl:282-285; the loss: recon - S), partial 32-lag gradient over own rows
         {
             FZ_S0(c);
             stage_zy_halo(s, SEQ_Z(XL.z_out), SEQ_Z(XL.y_out), lo7, hi7);
             __syncthreads();
-            recon_rows(c, s, lo7, hi7, c.p0, min(Lb, max(c.p1 + 7, c.q1)), +1.f, SEQ_S(Y.rec), c.p0, c.q1, Lb);
+            recon_rows(c, s, lo7, hi7, c.p0, min(Lb, max(c.p1 + 7, c.q1)), last ? -1.f : +1.f, SEQ_S(last ? P.recL : Y.rec), c.p0, c.q1, Lb);
             __syncthreads();
+            if (last) break;
             // G[tau][m] += z[p][m] R[4p + tau] + y[p][m] R[4p + 31 - tau] over own rows: tile of 4 taus x 2 filters per thread (16-byte signal loads)
             FZ_S(c, 16);
             float* Gp = s.w;                                       // this CTA's partial [32][50]
@@ -942,10 +951,8 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
         FZ_T(11);
         // F chain: e = fx(x, F) - (zyF + theta) on own rows (model.jl:294)
         {
-            tconv_rows(c, s, s.F, SEQ_X(XL.x_out), l, s.A);
-            __syncthreads();
             float* eg = SEQ_ZY(Y.e);
-            for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) eg[(size_t)c.p0 * FZ_M2 + o] = s.A[o] - s.zyF[o] - s.th[o];
+            for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) eg[(size_t)c.p0 * FZ_M2 + o] = s.fx[o] - s.zyF[o] - s.th[o];
         }
         FZ_T(12);
         group_barrier(c);                                      // partial D gradients and e are published
@@ -1048,30 +1055,24 @@ __global__ void __cluster_dims__(FZ_CL, 1, 1) __launch_bounds__(FZ_THREADS, 1) k
         group_barrier(c);                                      // the updated F is published
         stage_f4<8>(reinterpret_cast<float4*>(s.F), reinterpret_cast<const float4*>(data + Y.Fn + (int64_t)c.g * nF), (int)nF / 4);
         __syncthreads();
-        // theta <- theta + fx(x, F_new) - zyF (model.jl:370), only needed by the next pass
+        // fx(x, F_new): read by theta <- theta + fx - zyF (model.jl:370, only needed by the next pass), by the next pass's e and by the loss
+        tconv_rows(c, s, s.F, SEQ_X(XL.x_out), l, s.fx);
+        __syncthreads();
         if (Y.has_theta_out) {
-            tconv_rows(c, s, s.F, SEQ_X(XL.x_out), l, s.A);
-            __syncthreads();
             float* tg = SEQ_ZY(Y.thn);
-            for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) { const float t = s.A[o] - s.zyF[o] + s.th[o]; s.th[o] = t; tg[(size_t)c.p0 * FZ_M2 + o] = t; }
+            for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) { const float t = s.fx[o] - s.zyF[o] + s.th[o]; s.th[o] = t; tg[(size_t)c.p0 * FZ_M2 + o] = t; }
             __syncthreads();
         }
     }
     FZ_T(15);
     FZ_S0(c);
     // ---- loss (model.jl:310-325) with the updated D, F -----------------------------------------------------------------------
-    {
-        stage_zy_halo(s, SEQ_Z(XL.z_out), SEQ_Z(XL.y_out), lo7, hi7);
-        __syncthreads();
-        recon_rows(c, s, lo7, hi7, c.p0, min(Lb, max(c.p1 + 7, c.q1)), -1.f, SEQ_S(P.recL), c.p0, c.q1, Lb);
-        __syncthreads();
+    {   // the residual of the loss's recon is in s.sig (last trip of the loop above), fx(x, F) with the final F in s.fx
         FZ_S(c, 19);
         float a = 0.f, b = 0.f;
         for (int t = threadIdx.x; t < 4 * (c.q1 - c.p0); t += FZ_THREADS) { const float r = s.sig[t]; a += r * r; }
-        tconv_rows(c, s, s.F, SEQ_X(XL.x_out), l, s.A);
-        __syncthreads();
         float* fg = SEQ_ZY(P.fxL);
-        for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) { const float v = s.A[o]; fg[(size_t)c.p0 * FZ_M2 + o] = v; const float dlt = v - s.zyF[o]; b += dlt * dlt; }
+        for (int o = threadIdx.x; o < c.nr * FZ_M2; o += FZ_THREADS) { const float v = s.fx[o]; fg[(size_t)c.p0 * FZ_M2 + o] = v; const float dlt = v - s.zyF[o]; b += dlt * dlt; }
         FZ_S(c, 20);
         a = block_sum512(a, s.red);
         b = block_sum512(b, s.red);
