@@ -505,7 +505,10 @@ def bench_train(args, ctx, torch, dist, world, rank, local, dev, N, Lb, opt_step
                                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
                                 "fp32_simt_peak_tflops": FP32_SIMT_TFLOPS, "frac_of_fp32_simt_peak": tf / FP32_SIMT_TFLOPS,
                                 "algorithmic_flops_per_seq": flops_per_seq(Lb), "kernels_per_optimizer_step": launches / n_opt,
-                                "us_per_kernel": 1e3 * ms_opt / max(1.0, launches / n_opt), "traffic": None,
+                                "us_per_kernel": 1e3 * ms_opt / max(1.0, launches / n_opt),
+                                "traffic": 586752.0 if (groups == 1 and Lb == 100) else None,
+                                "traffic_source": "ncu --set full of one k_csc_fused_fwd launch (the dominant kernel, 59 % of the step): dram read + write = 0.587 MB "
+                                                  "(profiles/r02_csc_fused_fwd_ncu_full_summary.csv); the working set is L2 resident" if (groups == 1 and Lb == 100) else None,
                                 "note": "a batch of 6 is a dependent chain of small fp32 ops (SURVEY §8d): the step is bound by launch / dependency latency, "
                                         "neither by HBM nor by the tensor pipe; achieved = algorithmic F-layer flops (fwd + reverse = 3 x fwd) x seq/s"},
                    "final_loss": state["loss"], "final_l1_F": state["l1"], "wall_s": wall, "optimizer_steps_timed": n_opt, "checks": checks}
