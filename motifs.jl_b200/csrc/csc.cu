@@ -75,6 +75,7 @@ struct mb200_csc {
     bool tensor = false;                                 // forward-only handle using the tcgen05 BF16 path for corr2d
     __nv_bfloat16 *tc_A = nullptr, *tc_F = nullptr; int tc_tiles = 0, tc_ld = 104;
     size_t tc_smem3 = 0; int64_t tc_arows = 0;
+    C2sCfg c2s; bool no_c2s = false;                         // register-window corr2d (k_corr2d_s) configuration of this shape
     bool batched = false; float* Ft_scratch = nullptr;      // one-CTA-per-sequence kernels (csc_batched.cuh) for many-group shapes      // tap-grouped kernel (k_corr2d_tc3)
     cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr; bool graph_ok = false;
     const uint32_t* graph_words = nullptr; int64_t graph_rowwords = 0;
@@ -186,7 +187,11 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
             return;
         }
         // one CTA per sequence wins from ~190 sequences up (measured)
-        if (S->batched && d.G >= 32 && fastK && d.M2 * 24 <= C2B_PRE * 4 * 64) {
+        if (S->batched && d.G >= 32 && S->c2s.tr && !S->no_c2s) {
+            if (S->c2s.tr == 6) lk(k_corr2d_s<6, 12>, d.NS / S->c2s.spc, S->c2s.threads, S->c2s.smem, q, A, filt, gs, out, acc, S->c2s.spc, S->c2s.js, S->c2s.ldr, d);
+            else lk(k_corr2d_s<8, 12>, d.NS / S->c2s.spc, S->c2s.threads, S->c2s.smem, q, A, filt, gs, out, acc, S->c2s.spc, S->c2s.js, S->c2s.ldr, d);
+        }
+        else if (S->batched && d.G >= 32 && fastK && d.M2 * 24 <= C2B_PRE * 4 * 64) {
             const int ntile = ((d.l + 3) / 4) * 3;            // 4-row x 8-filter register tiles of a sequence
             lk(k_corr2d_b<24>, d.NS, std::min(C2B_THREADS, std::max(64, (ntile + 31) / 32 * 32)), corr2d_b_smem(d, 24), q, A, filt, gs, out, acc, d);
         }
@@ -485,6 +490,12 @@ static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
         MB_CUDA(ctx, cudaFuncSetAttribute(k_corr_sig_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_sig_b_smem(s->d)));
         MB_CUDA(ctx, cudaFuncSetAttribute(k_tconv_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)s->d.c * s->d.M2 * 4)));
         MB_CUDA(ctx, cudaFuncSetAttribute(k_corr2d_b<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr2d_b_smem(s->d, 24)));
+        s->c2s = corr2d_s_pick(s->d, ctx->smem_optin);
+        s->no_c2s = getenv("MB200_CSC_NO_C2S") != nullptr;      // A/B: keep k_corr2d_b
+        if (s->c2s.tr) {
+            MB_CUDA(ctx, cudaFuncSetAttribute(k_corr2d_s<6, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->c2s.smem));
+            MB_CUDA(ctx, cudaFuncSetAttribute(k_corr2d_s<8, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->c2s.smem));
+        }
     }
     MB_CUDA(ctx, cudaMalloc(&s->bits, std::max<size_t>(s->bits_n, 16)));
     MB_CUDA(ctx, cudaMalloc(&s->lcnt, (size_t)std::max(1, s->n_lists) * s->d.NS * 4));

@@ -420,6 +420,129 @@ static inline size_t corr2d_b_smem(const CscDims& d, int KK) {
     return (((rows_pad * (d.M2 + 1) + 3) & ~(size_t)3) + 2 * (size_t)d.M2 * KK) * 4;
 }
 
+// U2 "corr2d" for many groups, register-window form (same contraction as k_corr2d_b, which stays for the shapes this one does not fit).
+// k_corr2d_b issues 6 shared-memory loads per 32 FMAs (18 % of the fp32 peak at 64 groups x 200 bp: the load pipe, not the FMA pipe, paces it).
+// Here ALL of F (h x 2M x 24 floats = 115 KB) and the CTA's sequences (transposed: [column][row], odd row stride) stay in shared memory, and a
+// thread owns TR output rows x 8 filters of one sequence for a RANGE of columns j: per column it loads the TR + h - 1 rows its window touches
+// once and slides the h taps over them in registers -- 17 (TR = 6) row loads + 24 16-byte filter loads (the same address across a warp except
+// for the three filter tiles: multicast) per 576 FMAs.  Threads = (column range) x (sequence, row tile, filter tile): the column range is
+// warp-uniform, its partial sums are combined through shared memory in a fixed order.  The host picks TR, the sequences per CTA and the number
+// of column ranges so that the (sequence, row tile, filter tile) combinations fill whole warps (corr2d_s_pick).
+#define C2S_MAX_THREADS 384
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+template <int TR, int H>
+__global__ void __launch_bounds__(C2S_MAX_THREADS) k_corr2d_s(const float* __restrict__ A, const float* __restrict__ filt, int64_t filt_gs,
+                                                              float* __restrict__ out, int accumulate, int spc, int js_n, int ldr, CscDims d) { PDL_SYNC();
+    extern __shared__ __align__(16) float cs_smem[];
+    constexpr int KK = 24, WN = TR + H - 1;
+    float* sF = cs_smem;                                        // [H][2M][24], later the partial sums [js_n][spc][l][24]
+    float* sA = sF + H * d.M2 * KK;                             // [spc][2M][ldr]
+    const int64_t n0 = (int64_t)blockIdx.x * spc;
+    const float* F = filt + (n0 / d.B) * filt_gs;
+    for (int v = threadIdx.x; v < H * d.M2 * KK / 4; v += blockDim.x) cp_async16(sF + 4 * v, F + 4 * v);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const int rt_n = (d.l + TR - 1) / TR;
+    const int rows_pad = rt_n * TR + H - 1;                     // rows a window may touch (<= ldr); rows >= c read as zero
+    // the rows are transposed on the way in by 4-byte asynchronous copies (no register staging: a thread issues all of its ~50 copies back to
+    // back and waits once; a load + store loop paid an L2 round trip per few elements and was 40 % of the kernel)
+    for (int s = 0; s < spc; ++s) {
+        const float* a_src = A + (n0 + s) * d.c * d.M2;
+        float* dst = sA + (size_t)s * d.M2 * ldr;
+        int r = threadIdx.x / d.M2, j = threadIdx.x - r * d.M2;
+        const int dr = blockDim.x / d.M2, dj = blockDim.x - dr * d.M2;
+        for (int e = threadIdx.x; e < rows_pad * d.M2; e += blockDim.x) {
+            if (r < d.c) cp_async4(dst + j * ldr + r, a_src + e); else dst[j * ldr + r] = 0.f;
+            r += dr; j += dj; if (j >= d.M2) { j -= d.M2; ++r; }
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const int combos = spc * rt_n * 3;
+    const int lanes_pad = (combos + 31) & ~31;
+    const int js = threadIdx.x / lanes_pad;                     // warp-uniform
+    const int cb = threadIdx.x - js * lanes_pad;
+    const bool live = cb < combos && js < js_n;
+    const int kt = cb % 3, t2 = cb / 3, rt = t2 % rt_n, sq = t2 / rt_n;
+    float acc[TR][8];
+    #pragma unroll
+    for (int r = 0; r < TR; ++r)
+        #pragma unroll
+        for (int k = 0; k < 8; ++k) acc[r][k] = 0.f;
+    if (live) {
+        const int j0 = js * d.M2 / js_n, j1 = (js + 1) * d.M2 / js_n;
+        const float* ap = sA + (size_t)sq * d.M2 * ldr + rt * TR;
+        const float* fp = sF + kt * 8;
+        for (int j = j0; j < j1; ++j) {
+            float w[WN];
+            #pragma unroll
+            for (int i = 0; i < WN; ++i) w[i] = ap[j * ldr + i];
+            float4 fa = *reinterpret_cast<const float4*>(fp + j * KK), fb = *reinterpret_cast<const float4*>(fp + j * KK + 4);
+            #pragma unroll
+            for (int a = 0; a < H; ++a) {
+                const float4 fa_n = a + 1 < H ? *reinterpret_cast<const float4*>(fp + ((a + 1) * d.M2 + j) * KK) : fa;      // next tap's filters in flight
+                const float4 fb_n = a + 1 < H ? *reinterpret_cast<const float4*>(fp + ((a + 1) * d.M2 + j) * KK + 4) : fb;  // under this tap's FMAs
+                #pragma unroll
+                for (int r = 0; r < TR; ++r) {
+                    const float av = w[a + r];
+                    acc[r][0] += av * fa.x; acc[r][1] += av * fa.y; acc[r][2] += av * fa.z; acc[r][3] += av * fa.w;
+                    acc[r][4] += av * fb.x; acc[r][5] += av * fb.y; acc[r][6] += av * fb.z; acc[r][7] += av * fb.w;
+                }
+                fa = fa_n; fb = fb_n;
+            }
+        }
+    }
+    __syncthreads();                                            // F is no longer read: its space takes the partial sums
+    float* part = sF;
+    if (live) {
+        #pragma unroll
+        for (int r = 0; r < TR; ++r) {
+            const int i = rt * TR + r;
+            if (i < d.l) {
+                float4* o = reinterpret_cast<float4*>(part + (((size_t)js * spc + sq) * d.l + i) * KK + kt * 8);
+                o[0] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]); o[1] = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+            }
+        }
+    }
+    __syncthreads();
+    const int nout = spc * d.l * KK / 4;                        // the CTA's sequences are consecutive in out
+    float4* og = reinterpret_cast<float4*>(out + n0 * d.l * KK);
+    const float4* p4 = reinterpret_cast<const float4*>(part);
+    for (int v = threadIdx.x; v < nout; v += blockDim.x) {
+        float4 sum = p4[v];
+        for (int q = 1; q < js_n; ++q) { const float4 t = p4[(size_t)q * nout + v]; sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w; }
+        if (accumulate) { const float4 t = og[v]; sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w; }
+        og[v] = sum;
+    }
+}
+struct C2sCfg { int tr = 0, spc = 0, js = 0, ldr = 0, threads = 0; size_t smem = 0; };
+// TR in {6, 8}, sequences per CTA in the divisors of the batch, column ranges so that the CTA has ~256-384 threads; tr = 0: the shape does not fit
+static inline C2sCfg corr2d_s_pick(const CscDims& d, size_t smem_optin) {
+    C2sCfg best; double best_score = 0.0;
+    if (d.K != 24 || d.h != 12 || (d.l * 24) % 4) return best;
+    for (int tr = 6; tr <= 8; tr += 2)
+        for (int spc = 1; spc <= d.B; ++spc) {
+            if (d.B % spc) continue;
+            const int rt_n = (d.l + tr - 1) / tr, combos = spc * rt_n * 3, lanes_pad = (combos + 31) & ~31;
+            if (lanes_pad > C2S_MAX_THREADS) continue;
+            int ldr = rt_n * tr + d.h - 1; if (!(ldr & 1)) ++ldr;
+            const size_t smem = ((size_t)d.h * d.M2 * 24 + (size_t)spc * d.M2 * ldr) * 4;
+            if (smem > smem_optin) continue;
+            int js = C2S_MAX_THREADS / lanes_pad;
+            while (js > 1 && ((size_t)js * spc * d.l > (size_t)d.h * d.M2 || js > d.M2 / 8)) --js;
+            if ((size_t)js * spc * d.l > (size_t)d.h * d.M2) continue;
+            const int threads = js * lanes_pad;
+            const double score = (double)combos / lanes_pad * std::min(1.0, threads / 256.0) * (tr == 8 ? 1.02 : 1.0);      // a tie goes to the larger tile
+            if (score > best_score) { best_score = score; best.tr = tr; best.spc = spc; best.js = js; best.ldr = ldr; best.threads = threads; best.smem = smem; }
+        }
+    return best;
+}
+
 // T3 "dgrad" for many-group launches: of[g][tau][m] (+)= sum_{n in g} sum_p ca[n,p,m] r[n,4p+tau] + cb[n,p,m] r[n,4p+31-tau]
 // (model.jl:270-290), one 4-CTA CLUSTER per group.  The per-tau kernels (k_dgrad_c / k_dgrad_b) re-read the codes once per lag: 32 x 30 MB of
 // traffic per launch at 64 groups x 200 bp (441 us).  Here a thread owns a tile of 4 lags x 2 filters, the sequence's signal (with the one-hot
