@@ -15,8 +15,14 @@
 #include "csc_kernels.cuh"
 
 #define RB_THREADS 256
+#define RB_ROUNDS 4              // register tiles a k_recon_b thread may hold: c <= 512 code positions
 
-// dynamic shared memory: a,b [cpad][M] | FT, FrT [M][32] | U [cpad][33]
+__device__ __forceinline__ void cp_async8(float* dst_smem, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+// dynamic shared memory: a,b [cpad][M] (after the products: U [cpad][33]) | FT, FrT [M][32].  The code rows arrive by asynchronous 8-byte copies
+// (a load + store loop paid an L2 round trip per two elements: most of the kernel's time), U re-uses their space, so two CTAs fit an SM and
+// one's fill overlaps the other's products.
 __global__ void __launch_bounds__(RB_THREADS) k_recon_b(const float* __restrict__ ca, const float* __restrict__ cb,
                                                         const float* __restrict__ filt, int64_t filt_gs,
                                                         float* __restrict__ out, int accumulate, CscDims d) { PDL_SYNC();
@@ -26,45 +32,65 @@ __global__ void __launch_bounds__(RB_THREADS) k_recon_b(const float* __restrict_
     float* sb = sa + cpad * d.M;
     float* sFT = sb + cpad * d.M;                 // [M][32]: sFT[m][k] = F[k][m]
     float* sFr = sFT + d.M * 32;                  // [M][32]: sFr[m][k] = F[f_len-1-k][m]
-    float* sU = sFr + d.M * 32;                   // [cpad][33]
+    float* sU = rb_smem;                          // [cpad][33], over a/b once every product is in registers
     const int64_t n = blockIdx.x;
     const float* F = filt + (n / d.B) * filt_gs;
     const float* za = ca + n * d.c * d.M;
     const float* zb = cb + n * d.c * d.M;
     const int E = d.c * d.M;
-    for (int e = threadIdx.x; e < cpad * d.M; e += RB_THREADS) { sa[e] = e < E ? za[e] : 0.f; sb[e] = e < E ? zb[e] : 0.f; }
+    if ((((uintptr_t)za | (uintptr_t)zb) & 7) == 0 && (E & 1) == 0) {
+        for (int e = 2 * threadIdx.x; e < E; e += 2 * RB_THREADS) { cp_async8(sa + e, za + e); cp_async8(sb + e, zb + e); }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        for (int e = E + threadIdx.x; e < cpad * d.M; e += RB_THREADS) { sa[e] = 0.f; sb[e] = 0.f; }
+    } else {
+        for (int e = threadIdx.x; e < cpad * d.M; e += RB_THREADS) { sa[e] = e < E ? za[e] : 0.f; sb[e] = e < E ? zb[e] : 0.f; }
+    }
     for (int e = threadIdx.x; e < d.f_len * d.M; e += RB_THREADS) {
         const int k = e / d.M, m = e - k * d.M;
         const float f = F[e];
         sFT[m * 32 + k] = f; sFr[m * 32 + (d.f_len - 1 - k)] = f;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    // register tiles: 4 positions x 4 taps; a warp holds 4 position tiles x 8 tap tiles, so every operand load is one wavefront
+    // register tiles: 4 positions x 4 taps; a warp holds 4 position tiles x 8 tap tiles, so every operand load is one wavefront.
+    // A thread holds up to RB_ROUNDS tiles (c <= 128 * RB_ROUNDS) until all products are done and U may overwrite a, b.
     const int ntile = (cpad >> 2) * 8;
-    for (int tile = threadIdx.x; tile < ntile; tile += RB_THREADS) {
-        const int pt = tile >> 3, kt = tile & 7;
-        const float* a0 = sa + (pt * 4) * d.M;
-        const float* b0 = sb + (pt * 4) * d.M;
-        float u[4][4];
+    float u[RB_ROUNDS][4][4];
+    #pragma unroll
+    for (int rd = 0; rd < RB_ROUNDS; ++rd) {
+        const int tile = threadIdx.x + rd * RB_THREADS;
         #pragma unroll
         for (int i = 0; i < 4; ++i)
             #pragma unroll
-            for (int j = 0; j < 4; ++j) u[i][j] = 0.f;
-        #pragma unroll 2
-        for (int m = 0; m < d.M; ++m) {
-            const float4 f = *reinterpret_cast<const float4*>(sFT + m * 32 + kt * 4);
-            const float4 g = *reinterpret_cast<const float4*>(sFr + m * 32 + kt * 4);
-            #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float av = a0[i * d.M + m], bv = b0[i * d.M + m];
-                u[i][0] += av * f.x + bv * g.x; u[i][1] += av * f.y + bv * g.y;
-                u[i][2] += av * f.z + bv * g.z; u[i][3] += av * f.w + bv * g.w;
+            for (int j = 0; j < 4; ++j) u[rd][i][j] = 0.f;
+        if (tile < ntile) {
+            const int pt = tile >> 3, kt = tile & 7;
+            const float* a0 = sa + (pt * 4) * d.M;
+            const float* b0 = sb + (pt * 4) * d.M;
+            #pragma unroll 2
+            for (int m = 0; m < d.M; ++m) {
+                const float4 f = *reinterpret_cast<const float4*>(sFT + m * 32 + kt * 4);
+                const float4 g = *reinterpret_cast<const float4*>(sFr + m * 32 + kt * 4);
+                #pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float av = a0[i * d.M + m], bv = b0[i * d.M + m];
+                    u[rd][i][0] += av * f.x + bv * g.x; u[rd][i][1] += av * f.y + bv * g.y;
+                    u[rd][i][2] += av * f.z + bv * g.z; u[rd][i][3] += av * f.w + bv * g.w;
+                }
             }
         }
-        #pragma unroll
-        for (int i = 0; i < 4; ++i)
+    }
+    __syncthreads();
+    #pragma unroll
+    for (int rd = 0; rd < RB_ROUNDS; ++rd) {
+        const int tile = threadIdx.x + rd * RB_THREADS;
+        if (tile < ntile) {
+            const int pt = tile >> 3, kt = tile & 7;
             #pragma unroll
-            for (int j = 0; j < 4; ++j) sU[(pt * 4 + i) * 33 + kt * 4 + j] = u[i][j];
+            for (int i = 0; i < 4; ++i)
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) sU[(pt * 4 + i) * 33 + kt * 4 + j] = u[rd][i][j];
+        }
     }
     __syncthreads();
     for (int t = threadIdx.x; t < d.L4; t += RB_THREADS) {
@@ -78,8 +104,9 @@ __global__ void __launch_bounds__(RB_THREADS) k_recon_b(const float* __restrict_
 }
 static inline size_t recon_b_smem(const CscDims& d) {
     const size_t cpad = (size_t)((d.c + 3) & ~3);
-    return (2 * cpad * d.M + 2 * (size_t)d.M * 32 + cpad * 33) * 4;
+    return (std::max(2 * cpad * d.M, cpad * 33) + 2 * (size_t)d.M * 32) * 4;
 }
+static inline bool recon_b_fits(const CscDims& d) { return ((d.c + 3) >> 2) * 8 <= RB_ROUNDS * RB_THREADS; }
 
 // dynamic shared memory: r [L4 + f_len] | F [f_len][Mp], Mp = M rounded up to a multiple of 4
 __global__ void __launch_bounds__(RB_THREADS) k_corr_sig_b(const float* __restrict__ sig, const uint8_t* __restrict__ bases, float sgn,
@@ -119,10 +146,24 @@ __global__ void __launch_bounds__(RB_THREADS) k_corr_sig_b(const float* __restri
                 b[i][0] += rv * g.x; b[i][1] += rv * g.y; b[i][2] += rv * g.z; b[i][3] += rv * g.w;
             }
         }
+        const bool pairs = (d.M & 1) == 0 && (((uintptr_t)oa | (uintptr_t)ob) & 7) == 0;      // 8-byte stores: row starts and tile starts are even
         #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int p = pt * 4 + i;
             if (p >= d.c) continue;
+            if (pairs) {
+                #pragma unroll
+                for (int j = 0; j < 4; j += 2) {
+                    const int m = mt * 4 + j;
+                    if (m >= d.M) continue;
+                    float2* pa = reinterpret_cast<float2*>(oa + (n * d.c + p) * d.M + m);
+                    float2* pb = reinterpret_cast<float2*>(ob + (n * d.c + p) * d.M + m);
+                    float2 va = make_float2(a[i][j], a[i][j + 1]), vb = make_float2(b[i][j], b[i][j + 1]);
+                    if (accumulate) { const float2 qa = *pa, qb = *pb; va.x += qa.x; va.y += qa.y; vb.x += qb.x; vb.y += qb.y; }
+                    *pa = va; *pb = vb;
+                }
+                continue;
+            }
             #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int m = mt * 4 + j;
