@@ -664,6 +664,92 @@ __global__ void __cluster_dims__(1, DG_SLICES, 1) __launch_bounds__(DG_THREADS) 
     cluster.sync();                                               // remote reads of s_red are done
 }
 
+// k_dgrad_g with the slice's codes of ALL B sequences and their signals staged in shared memory by asynchronous copies issued up front (one
+// wait), then the same tiles and the same order of additions from shared memory: k_dgrad_g walks ~30 dependent rounds of global loads per
+// thread (8 rows per round, a signal refill and two block barriers per sequence) and is pure latency (76 us at 64 groups x 200 bp for 30 MB
+// of codes and 0.5 GFLOP).  Used when B x (2 x rows x M + 4 x rows + 32) floats fit the opt-in shared memory.
+#define DGS_SLICES 4                // CTAs per group of k_dgrad_s (8, i.e. three 60 KB CTAs per SM at 200 bp, measured no faster: 50 vs 47 us)
+static inline size_t dgrad_s_smem(const CscDims& d) {
+    const size_t per = (size_t)(d.c + DGS_SLICES - 1) / DGS_SLICES;
+    return (size_t)d.B * (2 * per * d.M + 4 * per + 32) * 4;
+}
+__global__ void __cluster_dims__(1, DGS_SLICES, 1) __launch_bounds__(DG_THREADS) k_dgrad_s(const float* __restrict__ ca, const float* __restrict__ cb,
+                                                         const float* __restrict__ sig, const uint8_t* __restrict__ bases, float sgn,
+                                                         float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) { PDL_SYNC();
+    extern __shared__ __align__(16) float dg_sm[];                 // z [B][per][M] | y [B][per][M] | r [B][4 per + 32]
+    __shared__ float s_red[32 * 64];                               // the upper half's tile sums, then this CTA's tile sums
+    cg::cluster_group cluster = cg::this_cluster();
+    const int g = blockIdx.x, sl = blockIdx.y;
+    const int half = threadIdx.x >> 8, t = threadIdx.x & 255;
+    const int mpairs = d.M >> 1;
+    const bool active = t < 8 * mpairs;
+    const int tg = active ? t / mpairs : 0, mp = active ? t - tg * mpairs : 0;
+    const int per = (d.c + DGS_SLICES - 1) / DGS_SLICES;
+    const int s_lo = min(d.c, sl * per), s_hi = min(d.c, s_lo + per), p_mid = (s_lo + s_hi + 1) >> 1;
+    const int p_lo = half ? p_mid : s_lo, p_hi = half ? s_hi : p_mid;
+    const int rows = s_hi - s_lo, RL = 4 * per + 32;
+    float* zs = dg_sm; float* ys = zs + d.B * per * d.M; float* rs = ys + d.B * per * d.M;
+    const bool al8 = (((uintptr_t)ca | (uintptr_t)cb) & 7) == 0;
+    for (int nl = 0; nl < d.B; ++nl) {
+        const int64_t n = (int64_t)g * d.B + nl;
+        const float* za = ca + (n * d.c + s_lo) * d.M;
+        const float* yb = cb + (n * d.c + s_lo) * d.M;
+        float* zd = zs + nl * per * d.M; float* yd = ys + nl * per * d.M;
+        if (al8) for (int e = 2 * threadIdx.x; e < rows * d.M; e += 2 * DG_THREADS) { cp_async8(zd + e, za + e); cp_async8(yd + e, yb + e); }
+        else for (int e = threadIdx.x; e < rows * d.M; e += DG_THREADS) { zd[e] = za[e]; yd[e] = yb[e]; }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int nl = 0; nl < d.B; ++nl) {
+        const int64_t n = (int64_t)g * d.B + nl;
+        for (int q = threadIdx.x; q < 4 * rows + 32; q += DG_THREADS) rs[nl * RL + q] = 4 * s_lo + q < d.L4 ? sig_at(sig, bases, sgn, n, 4 * s_lo + q, d) : 0.f;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    float acc[4][2];
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.f;
+    if (active) {
+        for (int nl = 0; nl < d.B; ++nl) {
+            const float* zr = zs + (nl * per - s_lo) * d.M + 2 * mp;
+            const float* yr = ys + (nl * per - s_lo) * d.M + 2 * mp;
+            const float* rr0 = rs + nl * RL - 4 * s_lo;
+            #pragma unroll 4
+            for (int p = p_lo; p < p_hi; ++p) {
+                const float2 z2 = *reinterpret_cast<const float2*>(zr + p * d.M), y2 = *reinterpret_cast<const float2*>(yr + p * d.M);
+                const float4 rf = *reinterpret_cast<const float4*>(rr0 + 4 * p + 4 * tg), rr = *reinterpret_cast<const float4*>(rr0 + 4 * p + 28 - 4 * tg);
+                const float f[4] = {rf.x, rf.y, rf.z, rf.w}, rv[4] = {rr.w, rr.z, rr.y, rr.x};
+                #pragma unroll
+                for (int i = 0; i < 4; ++i) { acc[i][0] += z2.x * f[i] + y2.x * rv[i]; acc[i][1] += z2.y * f[i] + y2.y * rv[i]; }
+            }
+        }
+    }
+    if (active && half) {
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) { s_red[(4 * tg + i) * 64 + 2 * mp] = acc[i][0]; s_red[(4 * tg + i) * 64 + 2 * mp + 1] = acc[i][1]; }
+    }
+    __syncthreads();
+    if (active && !half) {
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) { s_red[(4 * tg + i) * 64 + 2 * mp] += acc[i][0]; s_red[(4 * tg + i) * 64 + 2 * mp + 1] += acc[i][1]; }
+    }
+    cluster.sync();                                               // every CTA's tile sums are in its s_red
+    if (sl == 0 && active && !half) {
+        #pragma unroll
+        for (int i = 0; i < 4; ++i)
+            #pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int tau = 4 * tg + i, m = 2 * mp + u;
+                float v = 0.f;
+                #pragma unroll
+                for (int r = 0; r < DGS_SLICES; ++r) v += cluster.map_shared_rank(s_red, r)[tau * 64 + m];
+                float* o = of + (int64_t)g * out_gs + tau * d.M + m;
+                if (out_gs == 0 && d.G > 1) atomicAdd(o, v);
+                else if (accumulate) *o += v; else *o = v;
+            }
+    }
+    cluster.sync();                                               // remote reads of s_red are done
+}
+
 // U2 "corr2d" restricted to the entries a top-q kept: out[n,i,k] (+)= sum_{a<h} sum_{j<2M} A[n,i+a,j] F[a][j][k] for (i,k) with bits[n][i*K+k] != 0.
 // Every corr2d of the reverse pass produces the adjoint of a top-q OUTPUT, and the top-q adjoint (model.jl:190) discards it outside the kept
 // support: ~32 dot products of h*2M terms per sequence instead of l*K (x 136 less work at Lb = 200).  One CTA per sequence, one warp per entry.
