@@ -224,7 +224,10 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         } else lk(k_tconv_l, d.NS * d.c, 128, 0, q, x, LCNT(L), LIDX(L), LVAL(L), filt, gs, out, acc, d);
     };
     auto run_fgrad = [=](const float* A, const float* x, int L, float* of, int64_t ogs, int acc, cudaStream_t q) {
-        lk(k_fgrad_l, dim3(d.K, d.h, d.G), 128, 0, q, A, x, LCNT(L), LIDX(L), LVAL(L), of, ogs, acc, d);
+        // many groups: one CTA per (group, 8 filters); needs 16-byte aligned per-group outputs (ogs, of) when it stores vectors
+        if (batched && !S->no_c2s && (d.K & 7) == 0 && (ogs & 3) == 0 && ((uintptr_t)of & 15) == 0)
+            lk(k_fgrad_g, dim3(d.G, d.K / 8, (d.h * d.M2 + FG_THREADS - 1) / FG_THREADS), FG_THREADS, 0, q, A, x, LCNT(L), LIDX(L), LVAL(L), of, ogs, acc, d);
+        else lk(k_fgrad_l, dim3(d.K, d.h, d.G), 128, 0, q, A, x, LCNT(L), LIDX(L), LVAL(L), of, ogs, acc, d);
     };
     // two independent adjoint kernels of one op: the second runs on the aux stream (a parallel branch of the captured graph)
     auto par2 = [=](cudaStream_t q, const std::function<void(cudaStream_t)>& k1, const std::function<void(cudaStream_t)>& k2) {

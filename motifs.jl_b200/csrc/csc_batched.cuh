@@ -750,6 +750,90 @@ __global__ void __cluster_dims__(1, DGS_SLICES, 1) __launch_bounds__(DG_THREADS)
     cluster.sync();                                               // remote reads of s_red are done
 }
 
+// U3 "fgrad" for many-group launches: of[g][a][j][k] (+)= sum over the group's list entries (n, i, k, v) of v * A[n][i + a][j]  (model.jl:292-302).
+// Rows i .. i+h-1 of A are ONE contiguous window of h*2M floats, so filter k's gradient is a sum of ~B*q/K windows.  k_fgrad_l runs one block
+// per (k, a, group) -- 18 432 blocks of 128 threads at 64 groups, each repeating the gather and storing 4 bytes every 96 (57 us for 15 MFLOP).
+// Here one CTA per (group, 8 filters): warp w gathers filter k0 + w's entries in (sequence, list) order (the order k_fgrad_l adds them in), a
+// thread owns window offsets e = tid, tid + 256, ... for all eight filters (coalesced window reads), and stores 32 contiguous bytes per offset.
+#define FG_THREADS 256
+#define FG_QCAP 96                  // entries kept per filter and group (B * LIST_CAP = 384 slots over 24 filters: 16 expected)
+__global__ void __launch_bounds__(FG_THREADS) k_fgrad_g(const float* __restrict__ A, const float* __restrict__ x, const int32_t* __restrict__ lcnt,
+                                                        const uint16_t* __restrict__ lidx, const float* __restrict__ lval,
+                                                        float* __restrict__ of, int64_t out_gs, int accumulate, CscDims d) { PDL_SYNC();
+    __shared__ int s_off[8][FG_QCAP];             // window start (floats) of the entry
+    __shared__ float s_v[8][FG_QCAP];
+    __shared__ int s_cnt[8];
+    __shared__ int s_dense;
+    const int g = blockIdx.x, k0 = blockIdx.y * 8;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int HJ = d.h * d.M2;
+    if (threadIdx.x == 0) s_dense = 0;
+    __syncthreads();
+    {   // warp w: ordered gather of the entries with fil == k0 + w
+        const int total_slots = d.B * LIST_CAP;
+        int running = 0;
+        for (int base0 = 0; base0 < total_slots; base0 += 32) {
+            const int slot = base0 + lane;
+            const int b = slot / LIST_CAP, q = slot - b * LIST_CAP;
+            bool hit = false; int e = 0; float v = 0.f;
+            const int n = g * d.B + b;
+            if (slot < total_slots) {
+                const int c = lcnt[n];
+                if (c > LIST_CAP) s_dense = 1;
+                else if (q < c) { e = lidx[(int64_t)n * LIST_CAP + q]; hit = (e % d.K) == k0 + w; if (hit) v = lval[(int64_t)n * LIST_CAP + q]; }
+            }
+            const unsigned mk = __ballot_sync(FULLMASK, hit);
+            if (hit) {
+                const int o = running + __popc(mk & ((1u << lane) - 1u));
+                if (o < FG_QCAP) { s_off[w][o] = (b * d.c + e / d.K) * d.M2; s_v[w][o] = v; }
+            }
+            running += __popc(mk);
+        }
+        if (lane == 0) { s_cnt[w] = running; if (running > FG_QCAP) s_dense = 1; }
+    }
+    __syncthreads();
+    const float* Ag = A + (int64_t)g * d.B * d.c * d.M2;
+    const int e = blockIdx.z * FG_THREADS + threadIdx.x;       // this thread's window offset
+    const bool live = e < HJ;
+    float acc[8];
+    #pragma unroll
+    for (int kl = 0; kl < 8; ++kl) acc[kl] = 0.f;
+    if (!s_dense) {
+        #pragma unroll
+        for (int kl = 0; kl < 8; ++kl) {
+            const int cnt = s_cnt[kl];
+            for (int q0 = 0; q0 < cnt; q0 += 8) {           // eight window reads in flight, added in list order
+                float wv[8];
+                #pragma unroll
+                for (int u = 0; u < 8; ++u) wv[u] = (live && q0 + u < cnt) ? Ag[s_off[kl][q0 + u] + e] : 0.f;
+                #pragma unroll
+                for (int u = 0; u < 8; ++u) if (q0 + u < cnt) acc[kl] += s_v[kl][q0 + u] * wv[u];
+            }
+        }
+    } else {                                      // a list overflowed: walk x itself in the same (sequence, position) order
+        #pragma unroll
+        for (int kl = 0; kl < 8; ++kl)
+            for (int b = 0; b < d.B; ++b)
+                for (int i = 0; i < d.l; ++i) {
+                    const float xv = x[(((int64_t)g * d.B + b) * d.l + i) * d.K + k0 + kl];
+                    if (xv == 0.f) continue;
+                    if (live) acc[kl] += xv * Ag[(b * d.c + i) * d.M2 + e];
+                }
+    }
+    if (live) {
+        float* op = of + (int64_t)g * out_gs + (int64_t)e * d.K + k0;
+        if (out_gs == 0 && d.G > 1) {
+            #pragma unroll
+            for (int kl = 0; kl < 8; ++kl) atomicAdd(op + kl, acc[kl]);
+        } else {
+            float4 v0 = make_float4(acc[0], acc[1], acc[2], acc[3]), v1 = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            float4* o4 = reinterpret_cast<float4*>(op);
+            if (accumulate) { const float4 p0 = o4[0], p1 = o4[1]; v0.x += p0.x; v0.y += p0.y; v0.z += p0.z; v0.w += p0.w; v1.x += p1.x; v1.y += p1.y; v1.z += p1.z; v1.w += p1.w; }
+            o4[0] = v0; o4[1] = v1;
+        }
+    }
+}
+
 // U2 "corr2d" restricted to the entries a top-q kept: out[n,i,k] (+)= sum_{a<h} sum_{j<2M} A[n,i+a,j] F[a][j][k] for (i,k) with bits[n][i*K+k] != 0.
 // Every corr2d of the reverse pass produces the adjoint of a top-q OUTPUT, and the top-q adjoint (model.jl:190) discards it outside the kept
 // support: ~32 dot products of h*2M terms per sequence instead of l*K (x 136 less work at Lb = 200).  One CTA per sequence, one warp per entry.
