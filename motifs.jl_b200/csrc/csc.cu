@@ -76,7 +76,7 @@ struct mb200_csc {
     __nv_bfloat16 *tc_A = nullptr, *tc_F = nullptr; int tc_tiles = 0, tc_ld = 104;
     size_t tc_smem3 = 0; int64_t tc_arows = 0;
     C2sCfg c2s; bool no_c2s = false;                         // register-window corr2d (k_corr2d_s) configuration of this shape
-    bool batched = false; float* Ft_scratch = nullptr;      // one-CTA-per-sequence kernels (csc_batched.cuh) for many-group shapes      // tap-grouped kernel (k_corr2d_tc3)
+    bool batched = false; float* Ft_scratch = nullptr; float* Ft_scratch2 = nullptr;      // one-CTA-per-sequence kernels (csc_batched.cuh) for many-group shapes      // tap-grouped kernel (k_corr2d_tc3)
     cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr; bool graph_ok = false;
     const uint32_t* graph_words = nullptr; int64_t graph_rowwords = 0;
     // fused persistent forward kernel (csc_fused.cuh): plan = arena offsets of the tape's buffers, sync area, eligibility
@@ -241,7 +241,11 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
     std::map<size_t, size_t> xbits;              // buffer offset of an x tensor -> offset of the top-q bitmap that produced it
     // the adjoint of a top-q output is only read on the kept support (k_topq_s_bwd masks it): ~32 dot products per sequence instead of the dense contraction
     auto run_corr2d_kept = [=](const float* A, const float* filt, int64_t gs, size_t bo, float* out, int acc, cudaStream_t q) {
-        lk(k_corr2d_kept, d.NS, CK_THREADS, (size_t)d.l * d.K * 4, q, A, filt, gs, (const uint8_t*)(S->bits + bo), out, acc, d);
+        if (batched && S->Ft_scratch2 && !S->no_c2s) {         // the strided filter reads (4 bytes of every 96) were most of this kernel's time: transpose first
+            const int Gf = gs ? d.G : 1;
+            lk(k_transpose_F, nblk((int64_t)Gf * nF, 256), 256, 0, q, filt, gs, S->Ft_scratch2, Gf, d);
+            lk(k_corr2d_kept, d.NS, CK_THREADS, (size_t)d.l * d.K * 4, q, A, (const float*)S->Ft_scratch2, gs ? nF : (int64_t)0, (const uint8_t*)(S->bits + bo), out, acc, 1, d);
+        } else lk(k_corr2d_kept, d.NS, CK_THREADS, (size_t)d.l * d.K * 4, q, A, filt, gs, (const uint8_t*)(S->bits + bo), out, acc, 0, d);
     };
     auto op_recon = [&](Buf ca, Buf cb, Buf filt, int64_t gs, Buf out, const char* nm) {
         T.push_back({[=](cudaStream_t q) { run_recon(S->data + ca.off, S->data + cb.off, S->data + filt.off, gs, S->data + out.off, 0, q); },
@@ -490,6 +494,7 @@ static int csc_alloc(mb200_ctx* ctx, mb200_csc* s) {
     if (!s->xyz_only) { MB_CUDA(ctx, cudaMalloc(&s->grad, s->arena * 4)); MB_CUDA(ctx, cudaMemset(s->grad, 0, s->arena * 4)); }
     if (s->batched) {
         MB_CUDA(ctx, cudaMalloc(&s->Ft_scratch, (size_t)s->d.G * s->d.h * s->d.M2 * s->d.K * 4));
+        MB_CUDA(ctx, cudaMalloc(&s->Ft_scratch2, (size_t)s->d.G * s->d.h * s->d.M2 * s->d.K * 4));       // k_corr2d_kept's own copy (it runs beside k_tconv_b on the other branch)
         MB_CUDA(ctx, cudaFuncSetAttribute(k_recon_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)recon_b_smem(s->d)));
         MB_CUDA(ctx, cudaFuncSetAttribute(k_corr_sig_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_sig_b_smem(s->d)));
         MB_CUDA(ctx, cudaFuncSetAttribute(k_tconv_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)s->d.c * s->d.M2 * 4)));
@@ -659,7 +664,7 @@ extern "C" int32_t mb200_csc_destroy(mb200_ctx* ctx, mb200_csc* s) {
     if (s->graph) cudaGraphDestroy(s->graph);
     if (s->aux) cudaStreamDestroy(s->aux);
     if (s->ev_fork) { cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_join); cudaEventDestroy(s->ev_fork2); cudaEventDestroy(s->ev_join2); }
-    cudaFree(s->p_raw); cudaFree(s->g_raw); cudaFree(s->mt); cudaFree(s->st); cudaFree(s->data); cudaFree(s->grad); cudaFree(s->bits); cudaFree(s->lcnt); cudaFree(s->lidx); cudaFree(s->lval); cudaFree(s->tc_A); cudaFree(s->tc_F); cudaFree(s->Ft_scratch); cudaFree(s->fz_sync); cudaFree(s->fz_bwd_buf); if (s->fz_err_host) cudaFreeHost(s->fz_err_host);
+    cudaFree(s->p_raw); cudaFree(s->g_raw); cudaFree(s->mt); cudaFree(s->st); cudaFree(s->data); cudaFree(s->grad); cudaFree(s->bits); cudaFree(s->lcnt); cudaFree(s->lidx); cudaFree(s->lval); cudaFree(s->tc_A); cudaFree(s->tc_F); cudaFree(s->Ft_scratch); cudaFree(s->Ft_scratch2); cudaFree(s->fz_sync); cudaFree(s->fz_bwd_buf); if (s->fz_err_host) cudaFreeHost(s->fz_err_host);
     cudaFree(s->bases); cudaFree(s->idx_dev); cudaFreeHost(s->idx_pinned); cudaFree(s->idx_identity_dev); cudaFree(s->batch_words); cudaFreeHost(s->batch_pinned); cudaFreeHost(s->host_out);
     delete s;
     return MB200_OK;

@@ -191,6 +191,8 @@ __global__ void __launch_bounds__(256) k_transpose_F(const float* __restrict__ F
     Ft[(g * d.K + k) * hj + e] = F[g * gs + (int64_t)e * d.K + k];
 }
 
+#define TB_PF 4                     // codes whose filter rows a k_tconv_b thread holds ahead
+#define TB_E 5                      // window offsets per thread: h * 2M <= 1280
 // dynamic shared memory: tile [c][2M].  Ft as written by k_transpose_F (ft_gs = K*h*2M per group, or 0 when shared).
 __global__ void __launch_bounds__(RB_THREADS) k_tconv_b(const float* __restrict__ x, const int32_t* __restrict__ lcnt, const uint16_t* __restrict__ lidx,
                                                         const float* __restrict__ lval, const float* __restrict__ Ft, int64_t ft_gs,
@@ -209,14 +211,39 @@ __global__ void __launch_bounds__(RB_THREADS) k_tconv_b(const float* __restrict_
         s_i[threadIdx.x] = e / d.K; s_k[threadIdx.x] = e % d.K; s_v[threadIdx.x] = lval[n * LIST_CAP + threadIdx.x];
     }
     __syncthreads();
-    if (cnt <= LIST_CAP) {
-        // rows i..i+h-1 of the tile are one contiguous window of h*2M floats: window[e] += v * Ft[k][e]
+    if (cnt <= LIST_CAP && hj <= TB_E * RB_THREADS) {
+        // rows i..i+h-1 of the tile are one contiguous window of h*2M floats: window[e] += v * Ft[k][e].  The filter rows of the next TB_PF codes
+        // are already in registers when a code's turn comes: with the load behind the block barrier of the previous code the kernel was a chain
+        // of ~32 L2 round trips per sequence.
+        float fb[TB_PF][TB_E];
+        #pragma unroll
+        for (int u = 0; u < TB_PF; ++u)
+            #pragma unroll
+            for (int r = 0; r < TB_E; ++r) { const int e = threadIdx.x + r * RB_THREADS; fb[u][r] = (u < cnt && e < hj) ? FT[(int64_t)s_k[u] * hj + e] : 0.f; }
+        for (int q0 = 0; q0 < cnt; q0 += TB_PF) {
+            #pragma unroll
+            for (int u = 0; u < TB_PF; ++u) {
+                const int q = q0 + u;
+                if (q < cnt) {                     // block-uniform
+                    float* w = tile + s_i[q] * d.M2;
+                    const float v = s_v[q];
+                    #pragma unroll
+                    for (int r = 0; r < TB_E; ++r) { const int e = threadIdx.x + r * RB_THREADS; if (e < hj) w[e] += v * fb[u][r]; }
+                    if (q + TB_PF < cnt) {
+                        #pragma unroll
+                        for (int r = 0; r < TB_E; ++r) { const int e = threadIdx.x + r * RB_THREADS; if (e < hj) fb[u][r] = FT[(int64_t)s_k[q + TB_PF] * hj + e]; }
+                    }
+                    __syncthreads();               // the next code's window overlaps this one with other threads
+                }
+            }
+        }
+    } else if (cnt <= LIST_CAP) {
         for (int q = 0; q < cnt; ++q) {
             float* w = tile + s_i[q] * d.M2;
             const float* f = FT + (int64_t)s_k[q] * hj;
             const float v = s_v[q];
             for (int e = threadIdx.x; e < hj; e += RB_THREADS) w[e] += v * f[e];
-            __syncthreads();                       // the next code's window overlaps this one with other threads
+            __syncthreads();
         }
     } else {                                       // more than LIST_CAP non-zeros: walk x itself in the same (position, filter) order
         const float* xr = x + n * d.l * d.K;
@@ -839,7 +866,7 @@ __global__ void __launch_bounds__(FG_THREADS) k_fgrad_g(const float* __restrict_
 // support: ~32 dot products of h*2M terms per sequence instead of l*K (x 136 less work at Lb = 200).  One CTA per sequence, one warp per entry.
 #define CK_THREADS 256
 __global__ void __launch_bounds__(CK_THREADS) k_corr2d_kept(const float* __restrict__ A, const float* __restrict__ filt, int64_t filt_gs, const uint8_t* __restrict__ bits,
-                                                            float* __restrict__ out, int accumulate, CscDims d) { PDL_SYNC();
+                                                            float* __restrict__ out, int accumulate, int transposed, CscDims d) { PDL_SYNC();
     extern __shared__ int ck_list[];                               // [l*K] kept entries (any order: every entry is written by exactly one warp)
     __shared__ int s_cnt;
     const int64_t n = blockIdx.x;
@@ -855,8 +882,14 @@ __global__ void __launch_bounds__(CK_THREADS) k_corr2d_kept(const float* __restr
         const int e = ck_list[q], i = e / d.K, k = e - i * d.K;
         const float* rows = A + (n * d.c + i) * d.M2;              // rows i .. i+h-1 are contiguous
         float acc = 0.f;
-        #pragma unroll 4
-        for (int t = lane; t < HJ; t += 32) acc += rows[t] * F[(int64_t)t * d.K + k];
+        if (transposed) {                                          // filt = Ft [K][h*2M] (k_transpose_F): both operands coalesced
+            const float* fk = F + (int64_t)k * HJ;
+            #pragma unroll 4
+            for (int t = lane; t < HJ; t += 32) acc += rows[t] * fk[t];
+        } else {
+            #pragma unroll 4
+            for (int t = lane; t < HJ; t += 32) acc += rows[t] * F[(int64_t)t * d.K + k];
+        }
         acc = warp_sum(acc);
         if (lane == 0) { float* o = out + n * E + e; if (accumulate) *o += acc; else *o = acc; }
     }
