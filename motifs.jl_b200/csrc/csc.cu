@@ -50,7 +50,7 @@ struct mb200_csc {
     uint8_t* bits = nullptr; size_t bits_n = 0;          // top-q bitmasks
     int n_lists = 0;                                     // ordered non-zero lists of the x-role tensors (x and d g)
     int32_t* lcnt = nullptr; uint16_t* lidx = nullptr; float* lval = nullptr;
-    int mask_cap = 0;
+    int mask_cap = 0; int ms_cluster_maxg = 32;             // groups from which the batch median runs as one CTA per group instead of one cluster per group
     cudaStream_t aux = nullptr;                          // second capture stream: independent adjoint kernels / D-F branches run in parallel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
     bool in_branch = false;                              // set while replaying ops of a forked branch (no nested forking)
@@ -311,7 +311,7 @@ static void build_tape(mb200_csc* s, bool xyz_only) {
         Buf med = B.alloc(d.G);
         // one 8-CTA cluster per group minimises latency (training, few groups); with many groups (batched code retrieval) one CTA per
         // group fills the machine better: 148 groups in flight instead of 18 clusters
-        const bool ms_cluster = mask_cap <= MS_MAXV * 512 && d.G < 32;
+        const bool ms_cluster = mask_cap <= MS_MAXV * 512 && d.G < S->ms_cluster_maxg;
         const int ms_cap1 = (int)std::min<int64_t>(2 * (int64_t)d.B * d.c * d.M, 49152);
         T.push_back({[=](cudaStream_t q) {
                          if (ms_cluster) lk(k_mask_scale_c, d.G * CL, MS_THREADS, ((size_t)mask_cap + 2 * MS_BINS + MS_CAND) * 4, q, S->data + z.off, S->data + y.off, S->data + zy.off, S->data + med.off, mask_cap, d);
@@ -654,6 +654,7 @@ extern "C" int32_t mb200_csc_create(mb200_ctx* ctx, const mb200_hparams* hp, int
         const int min_g = e ? atoi(e) : 8;       // measured break-even on B200 (Lb = 100): 8 groups = 48 CTAs
         s->batched = d.G >= min_g && d.f_len == 32 && recon_b_fits(d) && recon_b_smem(d) <= 200 * 1024 && (size_t)d.c * d.M2 * 4 <= 200 * 1024;
     }
+    { const char* e = getenv("MB200_MS_CLUSTER_MAXG"); if (e) s->ms_cluster_maxg = atoi(e); }
     build_tape(s, s->xyz_only);
     int rc = csc_alloc(ctx, s);
     if (rc) { delete s; return rc; }
@@ -994,7 +995,7 @@ extern "C" int32_t mb200_csc_median_mask(mb200_ctx* ctx, mb200_csc* s, const flo
     float *dz = buf, *dy = buf + nZ, *dzy = buf + 2 * nZ, *dmed = buf + 4 * nZ;
     cudaMemcpyAsync(dz, z, nZ * 4, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(dy, y, nZ * 4, cudaMemcpyHostToDevice, ctx->stream);
-    const bool ms_cluster = s->mask_cap <= MS_MAXV * 512 && d.G < 32;
+    const bool ms_cluster = s->mask_cap <= MS_MAXV * 512 && d.G < s->ms_cluster_maxg;
     const int ms_cap1 = (int)std::min<int64_t>(2 * (int64_t)d.B * d.c * d.M, 49152);
     if (ms_cluster) lk(k_mask_scale_c, d.G * CL, MS_THREADS, ((size_t)s->mask_cap + 2 * MS_BINS + MS_CAND) * 4, ctx->stream, dz, dy, dzy, dmed, s->mask_cap, d);
     else if (s->batched) lk(k_mask_scale_g, d.G, MG_THREADS, 0, ctx->stream, dz, dy, dzy, dmed, d);
