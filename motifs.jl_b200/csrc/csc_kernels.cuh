@@ -27,6 +27,12 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
     return v;
 }
+// t = q * div + r.  The element-wise kernels index [NS][c][M] tensors with a 64-bit t; a 64-bit division is ~100 instructions and made those
+// kernels ALU-bound at a third of the HBM rate, so indices below 2^31 (every shape in practice) take the 32-bit path.
+__device__ __forceinline__ void idx_split(int64_t t, int div, int64_t& q, int& r) {
+    if (t < 0x80000000LL) { const unsigned tt = (unsigned)t, qq = tt / (unsigned)div; q = qq; r = (int)(tt - qq * (unsigned)div); }
+    else { q = t / div; r = (int)(t - q * div); }
+}
 // block-wide sum (blockDim.x multiple of 32, <= 1024); result valid in thread 0
 __device__ __forceinline__ float block_sum(float v) {
     __shared__ float s_part[32];
@@ -50,8 +56,7 @@ __global__ void __launch_bounds__(256) k_warm_zy(const uint8_t* __restrict__ bas
                                                  float* __restrict__ z, float* __restrict__ y, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.c * d.M) return;
-    const int m = (int)(t % d.M);
-    const int64_t np = t / d.M;
+    int m; int64_t np; idx_split(t, d.M, np, m);
     const int p = (int)(np % d.c);
     const int64_t n = np / d.c;
     const uint8_t* s = bases + n * d.Lb + p;
@@ -72,8 +77,7 @@ __global__ void __launch_bounds__(256) k_warm_zy_bwd(const uint8_t* __restrict__
                                                      float* __restrict__ dD, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.c * d.M) return;
-    const int m = (int)(t % d.M);
-    const int64_t np = t / d.M;
+    int m; int64_t np; idx_split(t, d.M, np, m);
     const int p = (int)(np % d.c);
     const int64_t n = np / d.c;
     const float eta = sc[i_eta];
@@ -143,8 +147,7 @@ __global__ void __launch_bounds__(256) k_corr_sig(const float* __restrict__ sig,
                                                   float* __restrict__ oa, float* __restrict__ ob, int accumulate, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.c * d.M) return;
-    const int m = (int)(t % d.M);
-    const int64_t np = t / d.M;
+    int m; int64_t np; idx_split(t, d.M, np, m);
     const int p = (int)(np % d.c);
     const int64_t n = np / d.c;
     const float* F = filt + (n / d.B) * filt_gs;
@@ -261,8 +264,7 @@ __global__ void __launch_bounds__(256) k_zy_update(const float* __restrict__ z, 
                                                    float* __restrict__ zn, float* __restrict__ yn, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.c * d.M) return;
-    const int m = (int)(t % d.M);
-    const int64_t np = t / d.M;
+    int m; int64_t np; idx_split(t, d.M, np, m);
     const float eta = sc[i_eta], lam = sc[i_lam], rho = sc[i_rho];
     const float l = fx[np * d.M2 + m], r = fx[np * d.M2 + d.M + m];
     zn[t] = fmaxf(z[t] - eta * (gz[t] + rho * (z[t] - l - al[t])) - lam * eta, 0.f);
@@ -280,8 +282,7 @@ __global__ void __launch_bounds__(256) k_zy_update_bwd(const float* __restrict__
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float s_eta = 0.f, s_lam = 0.f, s_rho = 0.f;
     if (t < (int64_t)d.NS * d.c * d.M) {
-        const int m = (int)(t % d.M);
-        const int64_t np = t / d.M;
+        int m; int64_t np; idx_split(t, d.M, np, m);
         const float eta = sc[i_eta], lam = sc[i_lam], rho = sc[i_rho];
         const float tz = zn[t] > 0.f ? dzn[t] : 0.f;
         const float ty = yn[t] > 0.f ? dyn[t] : 0.f;
@@ -391,9 +392,9 @@ __global__ void __launch_bounds__(256) k_mask_scale_bwd(const float* __restrict_
                                                         const float* __restrict__ dzy, float* __restrict__ dz, float* __restrict__ dy, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.c * d.M2) return;
-    const int j = (int)(t % d.M2);
-    const int64_t np = t / d.M2;
-    const float mg = med[(np / d.c) / d.B];
+    int j; int64_t np; idx_split(t, d.M2, np, j);
+    int64_t gq; int gr; idx_split(np, d.c * d.B, gq, gr);
+    const float mg = med[gq];
     if (j < d.M) { const int64_t o = np * d.M + j; if (z[o] >= mg) dz[o] += d.mf * dzy[t]; }
     else { const int64_t o = np * d.M + (j - d.M); if (y[o] >= mg) dy[o] += d.mf * dzy[t]; }
 }
@@ -403,8 +404,7 @@ __global__ void __launch_bounds__(256) k_d_build(const float* __restrict__ fx, c
                                                  const float* __restrict__ be, float* __restrict__ dd, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.c * d.M2) return;
-    const int j = (int)(t % d.M2);
-    const int64_t np = t / d.M2;
+    int j; int64_t np; idx_split(t, d.M2, np, j);
     const float ab = j < d.M ? al[np * d.M + j] : be[np * d.M + j - d.M];
     dd[t] = fx[t] - (zy[t] - ab);
 }
@@ -412,8 +412,7 @@ __global__ void __launch_bounds__(256) k_d_build_bwd(const float* __restrict__ d
                                                      float* __restrict__ dal, float* __restrict__ dbe, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.c * d.M2) return;
-    const int j = (int)(t % d.M2);
-    const int64_t np = t / d.M2;
+    int j; int64_t np; idx_split(t, d.M2, np, j);
     const float g = ddd[t];
     dfx[t] += g; dzy[t] -= g;
     if (j < d.M) dal[np * d.M + j] += g; else dbe[np * d.M + j - d.M] += g;
@@ -479,8 +478,7 @@ __global__ void __launch_bounds__(256) k_dual(const float* __restrict__ al, cons
                                               const float* __restrict__ z, const float* __restrict__ y, float* __restrict__ an, float* __restrict__ bn, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.c * d.M) return;
-    const int m = (int)(t % d.M);
-    const int64_t np = t / d.M;
+    int m; int64_t np; idx_split(t, d.M, np, m);
     an[t] = (al ? al[t] : 0.f) + fx[np * d.M2 + m] - z[t];
     bn[t] = (be ? be[t] : 0.f) + fx[np * d.M2 + d.M + m] - y[t];
 }
@@ -488,8 +486,7 @@ __global__ void __launch_bounds__(256) k_dual_bwd(const float* __restrict__ dan,
                                                   float* __restrict__ dfx, float* __restrict__ dz, float* __restrict__ dy, CscDims d) { PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)d.NS * d.c * d.M) return;
-    const int m = (int)(t % d.M);
-    const int64_t np = t / d.M;
+    int m; int64_t np; idx_split(t, d.M, np, m);
     const float ga = dan[t], gb = dbn[t];
     if (dal) { dal[t] += ga; dbe[t] += gb; }
     dfx[np * d.M2 + m] += ga; dfx[np * d.M2 + d.M + m] += gb;
