@@ -525,13 +525,13 @@ def bench_train(args, ctx, torch, dist, world, rank, local, dev, N, Lb, opt_step
         p_trained = model.get_params()
         model.free()
         if extras:
-            # code retrieval (inference/_1_code_retrieval.jl:33-56) over the training set with the parameters training just produced: 512 batches of
+            # code retrieval (inference/_1_code_retrieval.jl:33-56) over the training set with the parameters training just produced: 1024 batches of
             # 6 per launch sequence, fp32 (the parity path) and with the dense contraction on the tcgen05 BF16 kernel (stated tolerance); with a
             # communicator the batches are sharded over the ranks and the records all-gathered
             res = {}
             for name, tc in (("fp32", False), ("tensor_cores_bf16", True)):
                 n_dec = n_train - n_train % hp.batch_size
-                G = max(1, min(512, -(-(n_dec // hp.batch_size) // world)))
+                G = max(1, min(1024, -(-(n_dec // hp.batch_size) // world)))
                 mc = CscModel(ctx, hp, Lb, n_groups=G, forward_only=True, tensor_cores=tc)
                 mc.set_params(p_trained)
                 recs = mc.codes(seqs, shard="comm" if world > 1 else None)                    # warm-up (and the records for the comparison)

@@ -186,7 +186,7 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
 
 
-def code_retrieval(data, cdl: ucdl, hp: Hyperparam, model: CscModel | None = None, groups_per_call: int = 512, tensor_cores: bool = False):
+def code_retrieval(data, cdl: ucdl, hp: Hyperparam, model: CscModel | None = None, groups_per_call: int = 1024, tensor_cores: bool = False):
     """code_retrieval (_1_code_retrieval.jl:33-56) -> structured array (position, fil, seq, mag_f16), 0-based, ordered by
     seq, fil, position.  groups_per_call batches of 6 are decoded per kernel sequence (they are independent); with a
     communicator on the ctx the batches are sharded over the ranks and the records all-gathered."""
