@@ -275,7 +275,9 @@ def test_batched_layout_matches_single_batch_layout(ctx):
     (dict(filter_len=4, M=5, h=3, K=4, q=3, batch_size=3, num_pass_xyz=2, num_pass_df=2), 31, 1),      # tiny, every generic kernel
     (dict(filter_len=6, M=70, h=5, K=10, q=7, batch_size=4, num_pass_xyz=3, num_pass_df=2), 60, 1),    # M > 64, K != 24, f_len = 24
     (dict(filter_len=8, M=20, h=12, K=24, q=16, batch_size=2, num_pass_xyz=2, num_pass_df=1), 50, 12), # batched kernels, odd sizes
-    (dict(), 200, 32),                                                                                 # BASELINE config-3 shape on the many-group path (k_dgrad_g, k_corr2d_kept, k_corr2d_b, ...)
+    (dict(), 200, 32),                                                                                 # BASELINE config-3 shape on the many-group path (k_dgrad_s, k_fgrad_g, k_corr2d_kept, k_corr2d_s with one sequence per CTA, ...)
+    (dict(), 150, 32),                                                                                 # k_corr2d_s with two sequences per CTA and two column ranges
+    (dict(batch_size=4, q=16), 57, 40),                                                                # k_corr2d_s with four sequences per CTA, batch of 4
 ])
 def test_non_default_hyperparameters_match_oracle(ctx, hpd, Lb, G):
     """shapes other than the reference's defaults take the generic kernels (k_corr2d, k_dgrad, ...) or the batched ones with other
