@@ -266,7 +266,10 @@ __global__ void __launch_bounds__(RB_THREADS) k_tconv_b(const float* __restrict_
 // no cap on the group size.  (k_mask_scale_s keeps up to 49 152 positives in shared memory and runs four 8-bit radix passes over
 // them with one CTA per SM: 304 us per 500 groups; this kernel: see profiles/.)
 #define MG_THREADS 1024
-__global__ void __launch_bounds__(MG_THREADS) k_mask_scale_g(const float* __restrict__ z, const float* __restrict__ y,
+#ifndef MG_MINB
+#define MG_MINB 1                   // CTAs per SM the register allocation of k_mask_scale_g is held to.  2 (32 registers, ~100 bytes of spills) measured: 135 vs 145 us per call at 500 groups x 100 bp, but 9.19 vs 9.11 ms per 64-group step at 200 bp (64 CTAs: occupancy is not the limit there)
+#endif
+__global__ void __launch_bounds__(MG_THREADS, MG_MINB) k_mask_scale_g(const float* __restrict__ z, const float* __restrict__ y,
                                                              float* __restrict__ zy, float* __restrict__ med_out, CscDims d) { PDL_SYNC();
     __shared__ unsigned int hist[MS_BINS];
     __shared__ float cand[MS_CAND];
@@ -389,10 +392,20 @@ __global__ void __launch_bounds__(MG_THREADS) k_mask_scale_g(const float* __rest
         const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
         const int e0 = 4 * (isz ? v : v - VZ);
         int np = e0 / d.M, m = e0 - np * d.M;
-        #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            og[(int64_t)np * d.M2 + (isz ? 0 : d.M) + m] = fv[i] >= med ? d.mf * fv[i] : 0.f;
-            if (++m == d.M) { m = 0; ++np; }
+        if ((d.M & 1) == 0) {
+            // M even: e0 and m are even, so each PAIR of values stays inside one row and its destination is 8-byte aligned: two 8-byte stores
+            // instead of four 4-byte ones (the scalar stores, with their per-element row arithmetic, were 40 % of this kernel's stall samples)
+            float* o0 = og + (int64_t)np * d.M2 + (isz ? 0 : d.M) + m;
+            *reinterpret_cast<float2*>(o0) = make_float2(fv[0] >= med ? d.mf * fv[0] : 0.f, fv[1] >= med ? d.mf * fv[1] : 0.f);
+            m += 2; if (m == d.M) { m = 0; ++np; }
+            float* o1 = og + (int64_t)np * d.M2 + (isz ? 0 : d.M) + m;
+            *reinterpret_cast<float2*>(o1) = make_float2(fv[2] >= med ? d.mf * fv[2] : 0.f, fv[3] >= med ? d.mf * fv[3] : 0.f);
+        } else {
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                og[(int64_t)np * d.M2 + (isz ? 0 : d.M) + m] = fv[i] >= med ? d.mf * fv[i] : 0.f;
+                if (++m == d.M) { m = 0; ++np; }
+            }
         }
     }
     for (int e = 4 * V2 + threadIdx.x; e < E2; e += MG_THREADS) {
