@@ -1,4 +1,5 @@
 # round-2 closing record on one B200 (final library): smoke, GPU tests, default bench line, reference arm, launch list of a 64-group step, ncu full of k_corr2d_s
+# usage (GPU box, repo root): bash profiles/scripts/r02_closing_record.sh
 mkdir -p gpurun_out
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1; echo "smoke rc $?"; tail -3 gpurun_out/r02_smoke.log
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r02_tests.log 2>&1; echo "tests rc $?"; tail -2 gpurun_out/r02_tests.log
