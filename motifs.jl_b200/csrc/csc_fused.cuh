@@ -125,8 +125,24 @@ __device__ __forceinline__ void stage_f4(float4* dst, const float4* src, int n4)
 // arrivals on one address instead of 96: same-address atomics serialise in L2), a second cluster barrier releases the others.
 // Ordering: the cluster barrier orders every CTA's writes before the leader's gpu-scope fence, which is cumulative over them; the leader's
 // acquire fence after the poll and the second cluster barrier order them before every reader (which reads other CTAs' data with ld.cg).
+#ifndef FZ_GB_ALLPOLL
+#define FZ_GB_ALLPOLL 1           // 1: every CTA polls the counter itself after the leader's arrival; 0: only the leader polls and a second cluster barrier releases the others
+#endif
 __device__ __forceinline__ void group_barrier(Ctx& c) {
     cg::this_cluster().sync();
+#if FZ_GB_ALLPOLL
+    // One arrival per cluster (the leader's, after the cluster barrier above has ordered every CTA's writes before its gpu-scope fence), but every
+    // CTA's thread 0 watches the counter: the release no longer costs a second cluster barrier (~500 clocks) after the leader's poll.  Reader
+    // side: relaxed poll + acquire fence + block barrier in each CTA.
+    if (threadIdx.x == 0) {
+        c.epoch += (unsigned int)c.ncl;
+        if (c.r == 0) { __threadfence(); asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" :: "l"(c.bar) : "memory"); }
+        unsigned int spins = 0;
+        while (ld_relaxed(c.bar) < c.epoch) { if (++spins > (1u << 26)) __trap(); }      // never hang the device
+        __threadfence();
+    }
+    __syncthreads();
+#else
     if (c.r == 0 && threadIdx.x == 0) {
 #ifdef FZ_PROFILE
         const long long tb0 = clock64();
@@ -149,6 +165,7 @@ __device__ __forceinline__ void group_barrier(Ctx& c) {
 #endif
     }
     cg::this_cluster().sync();
+#endif
 }
 __device__ __forceinline__ void cluster_barrier() { cg::this_cluster().sync(); }
 
